@@ -1,0 +1,321 @@
+"""ctypes bindings for the CPU oracle (oracle/liboracle.so) and, when present, the reference
+shims under oracle/_ref/.  TEST INFRASTRUCTURE ONLY: importable from tests/, from
+__graft_entry__.smoke() and from bench.py's cpu_baseline / --impl reference legs.
+"""
+import ctypes as C
+import os
+import struct
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+
+
+class MmpParams(C.Structure):
+    _fields_ = [("seedSAsizeThreshold", C.c_int32), ("seedMinLength", C.c_int32),
+                ("uniqThreshold", C.c_int32), ("indelFuzz", C.c_int32),
+                ("goodSeedLen", C.c_int32), ("reseedLen", C.c_int32),
+                ("reseedRLTratio", C.c_double), ("reseedAbsDiff", C.c_int32),
+                ("shortSeedRatio", C.c_double)]
+
+
+def mmp_params(nt2=False):
+    """[MMP] section of soap4.ini / soap4-nt2.ini."""
+    return MmpParams(30, 17 if nt2 else 22, 6, 5, 27, 18 if nt2 else 23, 0.7, 4, 0.5)
+
+
+SEEDSA = np.dtype([("query_offset", "<u4"), ("pad0", "<u4"), ("sa_l", "<u8"), ("sa_diff", "<u4"), ("seed_len", "<u4")])
+SEEDPOS = np.dtype([("pos", "<u8"), ("strand_readID", "<u4"), ("paired_seedLength", "<u4")])
+CAND = np.dtype([("readIDLeft", "<u4"), ("pad", "<u4"), ("pos0", "<u8"), ("pos1", "<u8")])
+
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", HERE])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.orc_index_load.restype = C.c_void_p
+        L.orc_index_load.argtypes = [C.c_char_p]
+        L.orc_index_free.argtypes = [C.c_void_p]
+        L.orc_text_length.restype = C.c_uint64
+        L.orc_text_length.argtypes = [C.c_void_p]
+        L.orc_inverse_sa0.restype = C.c_uint64
+        L.orc_inverse_sa0.argtypes = [C.c_void_p]
+        L.orc_cum_freq.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_occ_many.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_sa_many.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_lkt.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.orc_text_base.restype = C.c_uint32
+        L.orc_text_base.argtypes = [C.c_void_p, C.c_uint64]
+        L.orc_counters.argtypes = [C.c_void_p, C.c_int]
+        L.orc_mmp.restype = C.c_int
+        L.orc_mmp.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_seed_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_pair_candidates.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
+                                          C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_free.argtypes = [C.c_void_p]
+        L.orc_dp.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                             C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Index:
+    def __init__(self, prefix):
+        self.L = lib()
+        self.h = self.L.orc_index_load(prefix.encode())
+        self.n = self.L.orc_text_length(self.h)
+        self.inverse_sa0 = self.L.orc_inverse_sa0(self.h)
+
+    def occ(self, idx, c):
+        idx = np.ascontiguousarray(idx, dtype=np.uint64)
+        c = np.ascontiguousarray(c, dtype=np.uint32)
+        out = np.empty(len(idx), dtype=np.uint64)
+        self.L.orc_occ_many(self.h, len(idx), ptr(idx), ptr(c), ptr(out))
+        return out
+
+    def sa(self, idx):
+        idx = np.ascontiguousarray(idx, dtype=np.uint64)
+        out = np.empty(len(idx), dtype=np.uint64)
+        self.L.orc_sa_many(self.h, len(idx), ptr(idx), ptr(out))
+        return out
+
+    def lkt(self, key):
+        l, r = C.c_uint64(), C.c_uint64()
+        self.L.orc_lkt(self.h, int(key), C.byref(l), C.byref(r))
+        return l.value, r.value
+
+    def counters(self, reset=False):
+        out = np.zeros(4, dtype=np.uint64)
+        self.L.orc_counters(ptr(out), int(reset))
+        return out
+
+    def mmp(self, read, strand, params):
+        read = np.ascontiguousarray(read, dtype=np.uint8)
+        out = np.zeros(1024, dtype=SEEDSA)
+        n = self.L.orc_mmp(self.h, ptr(read), len(read), strand, C.byref(params), ptr(out), len(out))
+        return out[:n]
+
+    def seed_pairs(self, reads, lens, params):
+        """reads: (2*nPairs, maxLen) uint8 codes; returns (readPos, matePos) SEEDPOS arrays incl. sentinels."""
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        lens = np.ascontiguousarray(lens, dtype=np.uint32)
+        rp, mp = C.c_void_p(), C.c_void_p()
+        nr, nm = C.c_uint64(), C.c_uint64()
+        self.L.orc_seed_pairs(self.h, ptr(reads), ptr(lens), reads.shape[1], reads.shape[0] // 2, C.byref(params),
+                              C.byref(rp), C.byref(nr), C.byref(mp), C.byref(nm))
+        a = np.frombuffer((C.c_char * (nr.value * 16)).from_address(rp.value), dtype=SEEDPOS).copy()
+        b = np.frombuffer((C.c_char * (nm.value * 16)).from_address(mp.value), dtype=SEEDPOS).copy()
+        self.L.orc_free(rp)
+        self.L.orc_free(mp)
+        return a, b
+
+
+def pair_candidates(readPos, matePos, lens, insert_low, insert_high):
+    L = lib()
+    rp = readPos.copy()
+    mp = matePos.copy()
+    lens = np.ascontiguousarray(lens, dtype=np.uint32)
+    out, n = C.c_void_p(), C.c_uint64()
+    L.orc_pair_candidates(ptr(rp), len(rp), ptr(mp), len(mp), ptr(lens), insert_low, insert_high, C.byref(out), C.byref(n))
+    res = np.frombuffer((C.c_char * (n.value * 24)).from_address(out.value), dtype=CAND).copy() if n.value else np.zeros(0, dtype=CAND)
+    L.orc_free(out)
+    return res
+
+
+def dp_cutoff(read_len):
+    """max(0.2*L, 30) truncated (definitions.h:166-167; DV-DPfunctions.cpp:2916)."""
+    return int(max(0.2 * read_len, 30.0))
+
+
+def dp(ref, read, clip_lt=130, clip_rt=130, mismatch=-2, gap_open=-3, cutoff=None):
+    L = lib()
+    ref = np.ascontiguousarray(ref, dtype=np.uint8)
+    read = np.ascontiguousarray(read, dtype=np.uint8)
+    if cutoff is None:
+        cutoff = dp_cutoff(len(read))
+    score, hit, cnt = C.c_int(), C.c_uint32(), C.c_uint32()
+    pat = np.zeros(len(ref) + len(read) + 16, dtype=np.uint8)
+    L.orc_dp(ptr(ref), len(ref), ptr(read), len(read), clip_lt, clip_rt, mismatch, gap_open, cutoff,
+             C.byref(score), C.byref(hit), C.byref(cnt), ptr(pat))
+    return score.value, hit.value, cnt.value, pattern_bytes(pat) if score.value >= cutoff else b""
+
+
+def pattern_bytes(pat):
+    """Pattern up to its terminator; a 'V' is followed by a count byte that may be 0."""
+    i = 0
+    while pat[i] != 0:
+        i += 2 if pat[i] == ord("V") else 1
+    return bytes(pat[:i])
+
+
+# ------------------------------------------------------------------ reference shims
+_ref_dp = None
+_ref_bwt = None
+
+
+def ref_available():
+    return os.path.exists(os.path.join(REF_DIR, "soap4"))
+
+
+def ref_dp_lib():
+    global _ref_dp
+    if _ref_dp is None:
+        L = C.CDLL(os.path.join(REF_DIR, "libref_dp.so"))
+        L.ref_dp_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _ref_dp = L
+    return _ref_dp
+
+
+def ref_dp(refs, dna_lens, reads, read_lens, max_dna, max_read, clip_lt=130, clip_rt=130, mismatch=-2, gap_open=-3):
+    """Runs the reference's own callDP on n tasks.  refs: (n, max_dna) codes, reads: (n, max_read)."""
+    L = ref_dp_lib()
+    n = len(dna_lens)
+    refs = np.ascontiguousarray(refs, dtype=np.uint8)
+    reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    dna_lens = np.ascontiguousarray(dna_lens, dtype=np.uint32)
+    read_lens = np.ascontiguousarray(read_lens, dtype=np.uint32)
+    scores = np.zeros(n, dtype=np.int32)
+    hits = np.zeros(n, dtype=np.uint32)
+    cnts = np.zeros(n, dtype=np.uint32)
+    pats = np.zeros((n, max_dna + max_read), dtype=np.uint8)
+    L.ref_dp_run(n, max_dna, max_read, ptr(refs), ptr(dna_lens), ptr(reads), ptr(read_lens),
+                 clip_lt, clip_rt, mismatch, gap_open, ptr(scores), ptr(hits), ptr(cnts), ptr(pats))
+    return scores, hits, cnts, pats
+
+
+class RefIndex:
+    def __init__(self, prefix):
+        global _ref_bwt
+        if _ref_bwt is None:
+            L = C.CDLL(os.path.join(REF_DIR, "libref_bwt.so"))
+            L.ref_index_load.restype = C.c_void_p
+            L.ref_index_load.argtypes = [C.c_char_p]
+            L.ref_text_length.restype = C.c_uint64
+            L.ref_text_length.argtypes = [C.c_void_p]
+            L.ref_inverse_sa0.restype = C.c_uint64
+            L.ref_inverse_sa0.argtypes = [C.c_void_p]
+            L.ref_occ.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+            L.ref_sa.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+            L.ref_lkt.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+            _ref_bwt = L
+        self.L = _ref_bwt
+        self.h = self.L.ref_index_load(prefix.encode())
+        self.n = self.L.ref_text_length(self.h)
+
+    def occ(self, idx, c):
+        idx = np.ascontiguousarray(idx, dtype=np.uint64)
+        c = np.ascontiguousarray(c, dtype=np.uint32)
+        out = np.empty(len(idx), dtype=np.uint64)
+        self.L.ref_occ(self.h, len(idx), ptr(idx), ptr(c), ptr(out))
+        return out
+
+    def sa(self, idx):
+        idx = np.ascontiguousarray(idx, dtype=np.uint64)
+        out = np.empty(len(idx), dtype=np.uint64)
+        self.L.ref_sa(self.h, len(idx), ptr(idx), ptr(out))
+        return out
+
+    def lkt(self, keys):
+        keys = np.ascontiguousarray(keys, dtype=np.uint32)
+        l = np.empty(len(keys), dtype=np.uint64)
+        r = np.empty(len(keys), dtype=np.uint64)
+        self.L.ref_lkt(self.h, len(keys), ptr(keys), ptr(l), ptr(r))
+        return l, r
+
+
+# ------------------------------------------------------------------ dump readers (oracle/ref_hooks.h)
+def read_seedpos_dump(path):
+    """-> list of (readPos, matePos) per batch."""
+    out = []
+    with open(path, "rb") as f:
+        while True:
+            h = f.read(16)
+            if len(h) < 16:
+                break
+            nr, nm = struct.unpack("<QQ", h)
+            a = np.frombuffer(f.read(16 * nr), dtype=SEEDPOS)
+            b = np.frombuffer(f.read(16 * nm), dtype=SEEDPOS)
+            out.append((a, b))
+    return out
+
+
+def read_cand_dump(path):
+    out = []
+    with open(path, "rb") as f:
+        while True:
+            h = f.read(8)
+            if len(h) < 8:
+                break
+            (n,) = struct.unpack("<Q", h)
+            out.append(np.frombuffer(f.read(24 * n), dtype=CAND))
+    return out
+
+
+def read_dp_dump(path, limit=None):
+    """-> list of dict(header..., tasks=[(ref, read, cutoff, score, hitLoc, count, pattern)])."""
+    out = []
+    with open(path, "rb") as f:
+        data = f.read()
+    o = 0
+    while o + 32 <= len(data):
+        magic, n, maxdna, maxread, cl, cr, mm, go = struct.unpack_from("<8I", data, o)
+        assert magic == 0x5044504D
+        o += 32
+        tasks = []
+        for _ in range(n):
+            dl, rl, co, sc, hl, mc = struct.unpack_from("<IIiiII", data, o)
+            o += 24
+            ref = np.frombuffer(data, dtype=np.uint8, count=dl, offset=o)
+            o += dl
+            rd = np.frombuffer(data, dtype=np.uint8, count=rl, offset=o)
+            o += rl
+            (pl,) = struct.unpack_from("<H", data, o)
+            o += 2
+            pat = data[o:o + pl]
+            o += pl
+            tasks.append((ref, rd, co, sc, hl, mc, pat))
+        out.append(dict(n=n, max_dna=maxdna, max_read=maxread, clip_lt=cl, clip_rt=cr,
+                        mismatch=C.c_int32(mm).value, gap_open=C.c_int32(go).value, tasks=tasks))
+        if limit and len(out) >= limit:
+            break
+    return out
+
+
+def read_fastq_codes(path, max_len=None, trunc=None):
+    """FASTQ -> (codes (n, maxLen) uint8 with N->G, lens).  `trunc`: reads are truncated to
+    trunc bases (QueryParser.cpp:188 truncates to -L minus 1)."""
+    seqs = []
+    with open(path, "rb") as f:
+        for i, line in enumerate(f):
+            if i % 4 == 1:
+                s = line.strip()
+                if trunc is not None:
+                    s = s[:trunc]
+                seqs.append(s)
+    lut = np.zeros(256, dtype=np.uint8)   # unknown -> A(0); N -> G (IndexHandler.cpp:26-45)
+    for ch, v in zip(b"ACGTacgt", [0, 1, 2, 3, 0, 1, 2, 3]):
+        lut[ch] = v
+    lut[ord("U")] = lut[ord("u")] = 3
+    lut[ord("N")] = lut[ord("n")] = 2
+    lens = np.array([len(s) for s in seqs], dtype=np.uint32)
+    ml = max_len or int(lens.max())
+    out = np.zeros((len(seqs), ml), dtype=np.uint8)
+    for i, s in enumerate(seqs):
+        out[i, :len(s)] = lut[np.frombuffer(s, dtype=np.uint8)]
+    return out, lens

@@ -12,9 +12,7 @@
 #include <string>
 #include "2bwt-lib/BWT.h"
 #include "2bwt-lib/MemManager.h"
-extern "C" {
 #include "2bwt-flex/LT.h"
-}
 
 struct RefIndex { BWT *bwt; LT *lt; MMPool *pool; };
 
