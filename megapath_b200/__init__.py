@@ -1,0 +1,280 @@
+"""megapath_b200 -- B200-native soap4 alignment hot path (HKU-BAL/MegaPath), Python host mirror.
+
+The product is libmegapath_b200.so (CUDA kernels + C-ABI, include/megapath_b200.h) and the
+soap4-compatible C++ driver in csrc/.  This module only binds the C-ABI with ctypes so tests
+and bench.py read like the reference's own call sequence (INDEXLoad -> load reads ->
+soap3_dp_pair_align).  There is no CPU fallback: a missing library or GPU raises.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmegapath_b200.so")
+
+
+class MmpParams(C.Structure):
+    _fields_ = [("seedSAsizeThreshold", C.c_int32), ("seedMinLength", C.c_int32),
+                ("uniqThreshold", C.c_int32), ("indelFuzz", C.c_int32),
+                ("goodSeedLen", C.c_int32), ("reseedLen", C.c_int32),
+                ("reseedRLTratio", C.c_double), ("reseedAbsDiff", C.c_int32),
+                ("shortSeedRatio", C.c_double)]
+
+
+class AlignParams(C.Structure):
+    _fields_ = [("mmp", MmpParams),
+                ("matchScore", C.c_int32), ("mismatchScore", C.c_int32),
+                ("openGapScore", C.c_int32), ("extendGapScore", C.c_int32),
+                ("softClipLeft", C.c_int32), ("softClipRight", C.c_int32),
+                ("insert_low", C.c_int32), ("insert_high", C.c_int32),
+                ("peStrandLeftLeg", C.c_int32), ("peStrandRightLeg", C.c_int32),
+                ("skipDefaultDP", C.c_int32), ("maxReadLength", C.c_int32)]
+
+
+class Results(C.Structure):
+    _fields_ = [("pairs", C.c_void_p), ("n_pairs", C.c_uint64),
+                ("rescued", C.c_void_p), ("n_rescued", C.c_uint64),
+                ("singles", C.c_void_p), ("n_singles", C.c_uint64),
+                ("cigars", C.c_void_p), ("cigar_bytes", C.c_uint64),
+                ("numDPAlignedPair", C.c_uint64), ("numDPAlignment", C.c_uint64),
+                ("numSingleDPAligned", C.c_uint64), ("numSingleDPAlignment", C.c_uint64),
+                ("numRescuedPair", C.c_uint64), ("numRescuedAlignment", C.c_uint64),
+                ("n_occ", C.c_uint64), ("n_sa", C.c_uint64), ("n_lkt", C.c_uint64),
+                ("dp_cells", C.c_uint64), ("dp_tasks", C.c_uint64),
+                ("ms_seed", C.c_float), ("ms_sa", C.c_float), ("ms_pair", C.c_float),
+                ("ms_dp", C.c_float), ("ms_total", C.c_float)]
+
+
+SEEDPOS = np.dtype([("pos", "<u8"), ("strand_readID", "<u4"), ("paired_seedLength", "<u4")])
+CAND = np.dtype([("readIDLeft", "<u4"), ("pad", "<u4"), ("pos0", "<u8"), ("pos1", "<u8")])
+PAIR_RESULT = np.dtype([
+    ("readID", "<u4"), ("insertSize", "<i4"), ("algnmt_1", "<u8"), ("algnmt_2", "<u8"),
+    ("score_1", "<i4"), ("score_2", "<i4"), ("editdist_1", "<i4"), ("editdist_2", "<i4"),
+    ("num_sameScore_1", "<i4"), ("num_sameScore_2", "<i4"), ("strand_1", "u1"), ("strand_2", "u1"), ("pad", "<u2"),
+    ("cigar_1", "<u4"), ("cigar_2", "<u4"), ("startPos_1", "<u8"), ("startPos_2", "<u8"),
+    ("refDpLength_1", "<u4"), ("refDpLength_2", "<u4"), ("peLeftAnchor_1", "<u4"), ("peLeftAnchor_2", "<u4"),
+    ("peRightAnchor_1", "<u4"), ("peRightAnchor_2", "<u4")], align=True)
+SINGLE_RESULT = np.dtype([
+    ("readID", "<u4"), ("cigar", "<u4"), ("algnmt", "<u8"), ("score", "<i4"), ("editdist", "<i4"),
+    ("num_sameScore", "<i4"), ("strand", "u1"), ("pad", "u1", (3,)), ("seedAlignmentLength", "<u4"),
+    ("startPos", "<u8"), ("refDpLength", "<u4"), ("pad2", "<u4")], align=True)
+
+_lib = None
+
+
+class MegapathError(RuntimeError):
+    pass
+
+
+def build():
+    """Compile the CUDA extension in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "csrc")])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MegapathError("libmegapath_b200.so is not built (run __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.mp_last_error.restype = C.c_char_p
+        L.mp_init.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.mp_destroy.argtypes = [C.c_void_p]
+        L.mp_index_load.argtypes = [C.c_void_p, C.c_char_p]
+        L.mp_index_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mp_index_build.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.mp_index_save.argtypes = [C.c_void_p, C.c_char_p]
+        L.mp_occ.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.mp_sa.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.mp_lkt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.mp_batch_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        L.mp_seed_pairs.argtypes = [C.c_void_p, C.c_void_p]
+        L.mp_download_seedpos.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mp_download_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mp_free.argtypes = [C.c_void_p]
+        L.mp_dp_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                  C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+        L.mp_align_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mp_results_release.argtypes = [C.c_void_p, C.c_void_p]
+        L.mp_default_params.argtypes = [C.c_void_p, C.c_int]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def default_params(nt2=False, insert_low=1, insert_high=500, max_read_length=120):
+    p = AlignParams()
+    lib().mp_default_params(C.byref(p), int(nt2))
+    p.insert_low, p.insert_high, p.maxReadLength = insert_low, insert_high, max_read_length
+    return p
+
+
+def words_per_query(max_read_length):
+    """getWordPerQuery (dependencies.h:204-207)."""
+    return (max_read_length + 15) // 16
+
+
+def pack_queries(codes, lens, max_read_length):
+    """Host mirror of appendToQueryArrays (QueryParser.cpp:184-203): 2-bit, 16 bases per word
+    LSB-first, 32-read interleaved.  codes: (nReads, >=maxLen) uint8 in 0..3."""
+    n = codes.shape[0]
+    wpq = words_per_query(max_read_length)
+    npad = (n + 31) // 32 * 32
+    width = wpq * 16
+    c = np.zeros((npad, width), dtype=np.uint32)
+    w = min(width, codes.shape[1])
+    c[:n, :w] = codes[:, :w]
+    mask = np.arange(width)[None, :] < np.concatenate([lens, np.zeros(npad - n, dtype=lens.dtype)])[:, None]
+    c *= mask
+    shifts = (2 * (np.arange(width) % 16)).astype(np.uint32)
+    words = (c << shifts[None, :]).reshape(npad, wpq, 16).sum(axis=2, dtype=np.uint64).astype(np.uint32)   # (npad, wpq)
+    il = words.reshape(npad // 32, 32, wpq).transpose(0, 2, 1).reshape(-1)      # word j of read r at grp*32*wpq + 32*j + r%32
+    return np.ascontiguousarray(il, dtype=np.uint32), wpq
+
+
+def pack_dp_interleaved(seqs, lens, max_len):
+    """Host mirror of packRead / repackDNA (DV-DPfunctions.cpp:3009-3073): 2-bit MSB-first,
+    1-based, 32-task interleaved.  seqs: (n, max_len) uint8 codes."""
+    n = seqs.shape[0]
+    w = (max_len + 15) >> 4
+    npad = (n + 31) // 32 * 32
+    out = np.zeros(npad * w, dtype=np.uint32)
+    for t in range(n):
+        base = (t // 32) * 32 * w + (t % 32)
+        for i in range(1, int(lens[t]) + 1):
+            out[base + ((i >> 4) << 5)] |= np.uint32(int(seqs[t, i - 1]) & 3) << np.uint32((15 - (i & 15)) << 1)
+    return out
+
+
+class Context:
+    """One GPU context (mp_context).  Method names follow include/megapath_b200.h."""
+
+    def __init__(self, device=0):
+        self.L = lib()
+        self.h = C.c_void_p()
+        self._check(self.L.mp_init(device, C.byref(self.h)))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise MegapathError("%s (status %d)" % (self.L.mp_last_error().decode(), rc))
+
+    def close(self):
+        if self.h:
+            self.L.mp_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- index ----
+    def index_load(self, prefix):
+        self._check(self.L.mp_index_load(self.h, prefix.encode()))
+
+    def index_build(self, text2bit, n):
+        text2bit = np.ascontiguousarray(text2bit, dtype=np.uint8)
+        self._check(self.L.mp_index_build(self.h, _ptr(text2bit), n))
+
+    def index_save(self, prefix):
+        self._check(self.L.mp_index_save(self.h, prefix.encode()))
+
+    def index_info(self):
+        n, isa0, hbm = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        cum = (C.c_uint64 * 5)()
+        self._check(self.L.mp_index_info(self.h, C.byref(n), C.byref(isa0), cum, C.byref(hbm)))
+        return dict(textLength=n.value, inverseSa0=isa0.value, cumFreq=list(cum), hbmBytes=hbm.value)
+
+    def occ(self, idx, c):
+        idx = np.ascontiguousarray(idx, dtype=np.uint64)
+        c = np.ascontiguousarray(c, dtype=np.uint32)
+        out = np.empty(len(idx), dtype=np.uint64)
+        self._check(self.L.mp_occ(self.h, _ptr(idx), _ptr(c), _ptr(out), len(idx)))
+        return out
+
+    def sa(self, idx):
+        idx = np.ascontiguousarray(idx, dtype=np.uint64)
+        out = np.empty(len(idx), dtype=np.uint64)
+        self._check(self.L.mp_sa(self.h, _ptr(idx), _ptr(out), len(idx)))
+        return out
+
+    def lkt(self, keys):
+        keys = np.ascontiguousarray(keys, dtype=np.uint32)
+        l = np.empty(len(keys), dtype=np.uint64)
+        r = np.empty(len(keys), dtype=np.uint64)
+        self._check(self.L.mp_lkt(self.h, _ptr(keys), _ptr(l), _ptr(r), len(keys)))
+        return l, r
+
+    # ---- batch ----
+    def batch_upload(self, queries, read_lengths, wpq):
+        queries = np.ascontiguousarray(queries, dtype=np.uint32)
+        read_lengths = np.ascontiguousarray(read_lengths, dtype=np.uint32)
+        self._keep = (queries, read_lengths)
+        self._check(self.L.mp_batch_upload(self.h, _ptr(queries), _ptr(read_lengths), len(read_lengths), wpq))
+
+    def seed_pairs(self, params):
+        self._check(self.L.mp_seed_pairs(self.h, C.byref(params)))
+
+    def download_seedpos(self):
+        rp, mp = C.c_void_p(), C.c_void_p()
+        nr, nm = C.c_uint64(), C.c_uint64()
+        self._check(self.L.mp_download_seedpos(self.h, C.byref(rp), C.byref(nr), C.byref(mp), C.byref(nm)))
+        a = np.frombuffer((C.c_char * (nr.value * 16)).from_address(rp.value), dtype=SEEDPOS).copy()
+        b = np.frombuffer((C.c_char * (nm.value * 16)).from_address(mp.value), dtype=SEEDPOS).copy()
+        self.L.mp_free(rp)
+        self.L.mp_free(mp)
+        return a, b
+
+    def download_candidates(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        self._check(self.L.mp_download_candidates(self.h, C.byref(p), C.byref(n)))
+        out = np.frombuffer((C.c_char * (n.value * 24)).from_address(p.value), dtype=CAND).copy() if n.value else np.zeros(0, CAND)
+        self.L.mp_free(p)
+        return out
+
+    # ---- DP seam ----
+    def dp_batch(self, packed_dna, dna_lens, max_dna, packed_read, read_lens, max_read, cutoffs,
+                 clip_lt=130, clip_rt=130, mismatch=-2, gap_open=-3):
+        n = len(dna_lens)
+        dna_lens = np.ascontiguousarray(dna_lens, dtype=np.uint32)
+        read_lens = np.ascontiguousarray(read_lens, dtype=np.uint32)
+        cutoffs = np.ascontiguousarray(cutoffs, dtype=np.int32)
+        scores = np.zeros(n, dtype=np.int32)
+        hits = np.zeros(n, dtype=np.uint32)
+        cnts = np.zeros(n, dtype=np.uint32)
+        pats = np.zeros((n, max_dna + max_read), dtype=np.uint8)
+        cl = np.full(max(n, 1), clip_lt, dtype=np.uint32)
+        cr = np.full(max(n, 1), clip_rt, dtype=np.uint32)
+        self._check(self.L.mp_dp_batch(self.h, _ptr(packed_dna), _ptr(dna_lens), max_dna, _ptr(packed_read), _ptr(read_lens),
+                                       max_read, _ptr(cutoffs), _ptr(scores), _ptr(hits), _ptr(cnts), _ptr(pats), n,
+                                       _ptr(cl), _ptr(cr), mismatch, gap_open))
+        return scores, hits, cnts, pats
+
+    # ---- whole stage sequence ----
+    def align_pairs(self, params):
+        """-> dict with numpy copies of the result arrays and the counters."""
+        res = Results()
+        self._check(self.L.mp_align_pairs(self.h, C.byref(params), C.byref(res)))
+
+        def arr(p, n, dt):
+            if not n:
+                return np.zeros(0, dtype=dt)
+            return np.frombuffer((C.c_char * (n * dt.itemsize)).from_address(p), dtype=dt).copy()
+        out = dict(pairs=arr(res.pairs, res.n_pairs, PAIR_RESULT), rescued=arr(res.rescued, res.n_rescued, PAIR_RESULT),
+                   singles=arr(res.singles, res.n_singles, SINGLE_RESULT),
+                   cigars=bytes((C.c_char * res.cigar_bytes).from_address(res.cigars)) if res.cigar_bytes else b"")
+        for name, _ in Results._fields_[8:]:
+            out[name] = getattr(res, name)
+        self.L.mp_results_release(self.h, C.byref(res))
+        return out
+
+
+def cigar_at(cigars, off):
+    end = cigars.index(b"\0", off)
+    return cigars[off:end]

@@ -1,0 +1,472 @@
+// mp_align.cu -- stage orchestration on the device + the C-ABI entry points.
+//
+// Stage S1 "deep DP" (alignment.cpp:91-137 -> DPForUnalignPairs2 -> DeepDPWrapper):
+//   task packing   PairEndAlgnBatch::packLeft / packRight        DV-DPfunctions.cpp:2857-3007
+//   result assembly DP2CPUAlgnThread + CigarStringEncoder         DV-DPfunctions.cpp:3391-3540, .h:344-427
+//   per-pair dedup  OutputBuffer::ready / ResultCompare           DV-DPfunctions.h:198-243, .cpp:253-258
+#include "mp_context.h"
+#include <cub/device/device_scan.cuh>
+#include <algorithm>
+#include <tuple>
+#include <string.h>
+#include <stdlib.h>
+
+int mps_upload(mp_context *ctx, const uint32_t *queries, const uint32_t *readLengths, uint32_t nReads, uint32_t wpq);
+int mps_download_seedpos(mp_context *ctx, mp_seed_pos **readPos, uint64_t *nReadPos, mp_seed_pos **matePos, uint64_t *nMatePos);
+
+#define MP_MARGIN(l) (((l) > 100) ? 30 : 25)       // DP2_MARGIN, DV-DPfunctions.cpp:1760
+
+__host__ __device__ inline int dp_cutoff(uint32_t readLen)           // definitions.h:166-167
+{
+    double v = 0.2 * readLen; if (v < 30.0) v = 30.0; return (int)v;
+}
+
+// ---- packLeft (DV-DPfunctions.cpp:2857-2924) ----
+__global__ void k_left_tasks(const mp_candidate *__restrict__ cands, uint32_t n, const uint32_t *__restrict__ lens,
+                             uint64_t fullLen, int strandLeft, MpDpTask *__restrict__ tasks)
+{
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    mp_candidate ci = cands[c];
+    uint32_t readLength = lens[ci.readIDLeft];
+    uint32_t margin = MP_MARGIN(readLength);
+    uint64_t start = ci.pos[0] - margin;
+    if (start >= fullLen) start = 0;
+    uint32_t dnaLen = readLength + margin * 2;
+    if (start + dnaLen > fullLen) dnaLen = (uint32_t)(fullLen - start);
+    MpDpTask t; t.refStart = start; t.refLen = dnaLen; t.readID = ci.readIDLeft; t.readLen = (uint16_t)readLength;
+    t.strand = (uint8_t)strandLeft; t.valid = 1; t.cutoff = dp_cutoff(readLength);
+    tasks[c] = t;
+}
+// ---- packRight (DV-DPfunctions.cpp:2926-3007) ----
+__global__ void k_right_tasks(const mp_candidate *__restrict__ cands, uint32_t n, const uint32_t *__restrict__ lens,
+                              uint64_t fullLen, int strandRight, int insert_high, const MpDpTask *__restrict__ left,
+                              const MpDpOut *__restrict__ leftOut, MpDpTask *__restrict__ tasks)
+{
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    mp_candidate ci = cands[c];
+    MpDpTask t; memset(&t, 0, sizeof t);
+    if (leftOut[c].score >= left[c].cutoff) {
+        uint32_t readIDRight = ci.readIDLeft ^ 1u;
+        uint32_t readLength = lens[readIDRight];
+        uint32_t margin = MP_MARGIN(readLength);
+        uint64_t start = ci.pos[1] - margin;
+        if (start >= fullLen) start = 0;
+        uint32_t dnaLen = readLength + margin * 2;
+        if (start + dnaLen > fullLen) dnaLen = (uint32_t)(fullLen - start);
+        uint64_t hitPosLeft = left[c].refStart + leftOut[c].hitLoc;
+        uint64_t bounded = hitPosLeft + (uint64_t)(int64_t)insert_high - start;     // restrict maximum insert size
+        if (bounded < dnaLen) dnaLen = (uint32_t)bounded;
+        t.refStart = start; t.refLen = dnaLen; t.readID = readIDRight; t.readLen = (uint16_t)readLength;
+        t.strand = (uint8_t)strandRight; t.valid = 1; t.cutoff = dp_cutoff(readLength);
+    }
+    tasks[c] = t;
+}
+
+// ---- pattern -> special CIGAR (CigarStringEncoder, DV-DPfunctions.h:344-427; use at .cpp:3447-3471) ----
+struct CigStats { int nI, nD, nS, gapPenalty, textLen; };
+__device__ inline int ndigits(int v) { return v >= 100 ? 3 : v >= 10 ? 2 : 1; }
+// The encoder merges consecutive equal types while scanning the (end -> start) pattern and prints the
+// runs in reverse.  `out` == nullptr: measure only.  Text is written backwards from out + textLen.
+__device__ CigStats cigar_encode(const uint8_t *__restrict__ pat, int open, int ext, char *out, int textLen)
+{
+    CigStats st; st.nI = st.nD = st.nS = st.gapPenalty = st.textLen = 0;
+    char *w = out ? out + textLen : nullptr;
+    int curType = 'N', curCnt = 0, lastType = 'N';
+    const uint8_t *p = pat;
+    while (true) {
+        int type, cnt; bool end = false;
+        if (*p == 0) { type = 0; cnt = 0; end = true; }
+        else if (*p == 'V') { type = lastType; cnt = (int)p[1] - 1; p += 2; }
+        else { type = *p; cnt = 1; lastType = type; ++p; }
+        if (!end && type == curType) { curCnt += cnt; continue; }
+        // flush the finished run
+        if (curCnt > 0 && curType != 'N') {
+            int nd = ndigits(curCnt);
+            st.textLen += nd + 1;
+            if (curType == 'I') st.nI += curCnt; else if (curType == 'D') st.nD += curCnt; else if (curType == 'S') st.nS += curCnt;
+            if (curType == 'I' || curType == 'D') st.gapPenalty += open + (curCnt - 1) * ext;
+            if (w) {
+                *--w = (char)curType;
+                int v = curCnt;
+                for (int d = 0; d < nd; ++d) { *--w = (char)('0' + v % 10); v /= 10; }
+            }
+        }
+        if (end) break;
+        curType = type; curCnt = cnt;
+    }
+    return st;
+}
+
+struct PairWork { uint32_t ok; uint32_t cigLen[2]; };
+
+__global__ void k_assemble_measure(uint32_t n, const MpDpTask *__restrict__ lt, const MpDpOut *__restrict__ lo,
+                                   const MpDpTask *__restrict__ rt, const MpDpOut *__restrict__ ro,
+                                   const uint8_t *__restrict__ lpat, const uint8_t *__restrict__ rpat, uint32_t patStride,
+                                   int open, int ext, uint32_t *__restrict__ okFlag, uint32_t *__restrict__ cigBytes)
+{
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    bool ok = lo[c].score >= lt[c].cutoff && rt[c].valid && ro[c].score >= rt[c].cutoff;
+    uint32_t bytes = 0;
+    if (ok) {
+        CigStats a = cigar_encode(lpat + (size_t)c * patStride, open, ext, nullptr, 0);
+        CigStats b = cigar_encode(rpat + (size_t)c * patStride, open, ext, nullptr, 0);
+        bytes = a.textLen + 1 + b.textLen + 1;
+    }
+    okFlag[c] = ok; cigBytes[c] = bytes;
+}
+
+struct AsmParams { int match, mm, open, ext, strandLeft, strandRight, insert_low; uint32_t maxDNALength; };
+
+__global__ void k_assemble_write(uint32_t n, const mp_candidate *__restrict__ cands, const MpDpTask *__restrict__ lt,
+                                 const MpDpOut *__restrict__ lo, const MpDpTask *__restrict__ rt, const MpDpOut *__restrict__ ro,
+                                 const uint8_t *__restrict__ lpat, const uint8_t *__restrict__ rpat, uint32_t patStride,
+                                 AsmParams A, const uint32_t *__restrict__ okFlag, const uint32_t *__restrict__ outIdx,
+                                 const uint32_t *__restrict__ cigOff, uint32_t cigBase, mp_pair_result *__restrict__ res, char *__restrict__ cig)
+{
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n || !okFlag[c]) return;
+    // index 0 = left leg, 1 = right leg (DV-DPfunctions.cpp:3432-3530)
+    const uint8_t *pat[2] = { lpat + (size_t)c * patStride, rpat + (size_t)c * patStride };
+    const MpDpTask *tk[2] = { lt + c, rt + c };
+    const MpDpOut *ou[2] = { lo + c, ro + c };
+    int editdist[2], DIS[2]; uint32_t cigPos[2];
+    uint32_t off = cigOff[c];
+    const int lengths_i = rt[c].readLen;                // batch->lengths[i] was overwritten by packRight
+    for (int s = 0; s < 2; ++s) {
+        CigStats m = cigar_encode(pat[s], A.open, A.ext, nullptr, 0);
+        cigar_encode(pat[s], A.open, A.ext, cig + off, m.textLen);
+        cig[off + m.textLen] = 0;
+        cigPos[s] = cigBase + off;
+        off += m.textLen + 1;
+        int L = lengths_i - m.nI - m.nS;
+        int numMis = (L * A.match + m.gapPenalty - ou[s]->score) / (A.match - A.mm);
+        editdist[s] = m.nI + m.nD + numMis;
+        DIS[s] = m.nD - m.nI - m.nS;
+    }
+    uint32_t readIDLeft = cands[c].readIDLeft;
+    int readSide = readIDLeft & 1, mateSide = 1 - readSide;
+    mp_pair_result r; memset(&r, 0, sizeof r);
+    r.readID = readIDLeft - readSide;
+    r.strand_1 = (uint8_t)(readSide == 0 ? A.strandLeft : A.strandRight);
+    r.strand_2 = (uint8_t)(mateSide == 0 ? A.strandLeft : A.strandRight);
+    r.algnmt_1 = tk[readSide]->refStart + ou[readSide]->hitLoc;
+    r.algnmt_2 = tk[mateSide]->refStart + ou[mateSide]->hitLoc;
+    r.cigar_1 = cigPos[readSide]; r.cigar_2 = cigPos[mateSide];
+    r.score_1 = ou[readSide]->score; r.score_2 = ou[mateSide]->score;
+    r.editdist_1 = editdist[readSide]; r.editdist_2 = editdist[mateSide];
+    r.startPos_1 = (uint32_t)tk[readSide]->refStart;      // unsigned int in the reference (PEAlgnmt.h:521)
+    r.startPos_2 = tk[mateSide]->refStart;
+    r.refDpLength_1 = tk[readSide]->refLen; r.refDpLength_2 = tk[mateSide]->refLen;
+    // anchors (DV-DPfunctions.cpp:2885-2886, 2987-2990)
+    uint64_t hitPosLeft = lt[c].refStart + lo[c].hitLoc;
+    long long rightAnchor = (long long)(hitPosLeft + (uint64_t)(int64_t)A.insert_low - rt[c].refStart);
+    uint32_t la[2] = { A.maxDNALength, A.maxDNALength }, ra[2] = { 0u, (uint32_t)(rightAnchor > 0 ? rightAnchor : 0) };
+    r.peLeftAnchor_1 = la[readSide]; r.peLeftAnchor_2 = la[mateSide];
+    r.peRightAnchor_1 = ra[readSide]; r.peRightAnchor_2 = ra[mateSide];
+    if (r.algnmt_1 < r.algnmt_2) r.insertSize = (int32_t)(r.algnmt_2 - r.algnmt_1 + (uint64_t)(int64_t)lengths_i + (uint64_t)(int64_t)DIS[1]);
+    else r.insertSize = (int32_t)(r.algnmt_1 - r.algnmt_2 + (uint64_t)(int64_t)lengths_i + (uint64_t)(int64_t)DIS[1]);
+    r.num_sameScore_1 = (int32_t)ou[readSide]->count; r.num_sameScore_2 = (int32_t)ou[mateSide]->count;
+    res[outIdx[c]] = r;
+}
+
+static int scan_u32(mp_context *ctx, const uint32_t *in, uint32_t *out, uint64_t n)
+{
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, (int64_t)n, ctx->stream);
+    if (ctx->dScanTmp.reserve(tb)) return MP_ERR_CUDA;
+    cub::DeviceScan::ExclusiveSum(ctx->dScanTmp.p, tb, in, out, (int64_t)n, ctx->stream);
+    return 0;
+}
+
+// ---- stage S1 over all candidates, in chunks ----
+static int deep_dp(mp_context *ctx, const mp_align_params *P, mp_results *out, uint64_t &cells, uint64_t &tasksRun)
+{
+    cudaStream_t st = ctx->stream;
+    const uint64_t nC = ctx->nCands;
+    const uint32_t inputMax = (uint32_t)P->maxReadLength;
+    const uint32_t maxReadLength = (inputMax / 4 + 1) * 4;                       // DV-DPfunctions.cpp:3166-3167
+    const uint32_t maxDNALength = maxReadLength + 2 * MP_MARGIN(inputMax) + 8;
+    const uint32_t patStride = maxDNALength + maxReadLength;
+    MpDpParams dpl, dpr;
+    // softClipLtSizes/RtSizes per leg (DV-DPfunctions.cpp:2908-2911, 2994-2997); callDP uses task 0's pair
+    dpl.mismatch = dpr.mismatch = P->mismatchScore; dpl.open = dpr.open = P->openGapScore;
+    dpl.clipLt = P->peStrandLeftLeg == 1 ? P->softClipLeft : P->softClipRight;
+    dpl.clipRt = P->peStrandLeftLeg == 1 ? P->softClipRight : P->softClipLeft;
+    dpr.clipLt = P->peStrandRightLeg == 1 ? P->softClipLeft : P->softClipRight;
+    dpr.clipRt = P->peStrandRightLeg == 1 ? P->softClipRight : P->softClipLeft;
+    AsmParams A; A.match = P->matchScore; A.mm = P->mismatchScore; A.open = P->openGapScore; A.ext = P->extendGapScore;
+    A.strandLeft = P->peStrandLeftLeg; A.strandRight = P->peStrandRightLeg; A.insert_low = P->insert_low; A.maxDNALength = maxDNALength;
+
+    const uint32_t CH = 1u << 18;
+    DevBuf dLT, dRT, dLO, dRO, dLP, dRP, dOk, dBytes, dIdx, dOff, dRes, dCig;
+    uint32_t chunkCap = (uint32_t)std::min<uint64_t>(CH, nC ? nC : 1);
+    if (dLT.reserve((size_t)chunkCap * sizeof(MpDpTask)) || dRT.reserve((size_t)chunkCap * sizeof(MpDpTask)) ||
+        dLO.reserve((size_t)chunkCap * sizeof(MpDpOut)) || dRO.reserve((size_t)chunkCap * sizeof(MpDpOut)) ||
+        dLP.reserve((size_t)chunkCap * patStride) || dRP.reserve((size_t)chunkCap * patStride) ||
+        dOk.reserve(((size_t)chunkCap + 1) * 4) || dBytes.reserve(((size_t)chunkCap + 1) * 4) ||
+        dIdx.reserve(((size_t)chunkCap + 1) * 4) || dOff.reserve(((size_t)chunkCap + 1) * 4) ||
+        dRes.reserve((size_t)chunkCap * sizeof(mp_pair_result))) return MP_ERR_CUDA;
+    std::vector<mp_pair_result> &H = ctx->hPairs;
+    std::vector<char> &HC = ctx->hCigars;
+    const uint64_t fullLen = ctx->ix.n;
+    for (uint64_t base = 0; base < nC; base += CH) {
+        uint32_t n = (uint32_t)std::min<uint64_t>(CH, nC - base);
+        const mp_candidate *cands = ctx->dCands.as<mp_candidate>() + base;
+        unsigned g = (n + 127) / 128;
+        k_left_tasks<<<g, 128, 0, st>>>(cands, n, ctx->dLens.as<uint32_t>(), fullLen, P->peStrandLeftLeg, dLT.as<MpDpTask>());
+        if (int rc = mpd_run_tasks(ctx, dLT.as<MpDpTask>(), n, maxDNALength, maxReadLength, dpl, dLO.as<MpDpOut>(), dLP.as<uint8_t>(), patStride)) return rc;
+        k_right_tasks<<<g, 128, 0, st>>>(cands, n, ctx->dLens.as<uint32_t>(), fullLen, P->peStrandRightLeg, P->insert_high,
+                                         dLT.as<MpDpTask>(), dLO.as<MpDpOut>(), dRT.as<MpDpTask>());
+        if (int rc = mpd_run_tasks(ctx, dRT.as<MpDpTask>(), n, maxDNALength, maxReadLength, dpr, dRO.as<MpDpOut>(), dRP.as<uint8_t>(), patStride)) return rc;
+        MP_CUDA(cudaMemsetAsync(dOk.p, 0, ((size_t)n + 1) * 4, st));
+        MP_CUDA(cudaMemsetAsync(dBytes.p, 0, ((size_t)n + 1) * 4, st));
+        k_assemble_measure<<<g, 128, 0, st>>>(n, dLT.as<MpDpTask>(), dLO.as<MpDpOut>(), dRT.as<MpDpTask>(), dRO.as<MpDpOut>(),
+                                              dLP.as<uint8_t>(), dRP.as<uint8_t>(), patStride, P->openGapScore, P->extendGapScore,
+                                              dOk.as<uint32_t>(), dBytes.as<uint32_t>());
+        if (scan_u32(ctx, dOk.as<uint32_t>(), dIdx.as<uint32_t>(), (uint64_t)n + 1)) return MP_ERR_CUDA;
+        if (scan_u32(ctx, dBytes.as<uint32_t>(), dOff.as<uint32_t>(), (uint64_t)n + 1)) return MP_ERR_CUDA;
+        uint32_t nOk = 0, nBytes = 0;
+        MP_CUDA(cudaMemcpyAsync(&nOk, dIdx.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
+        MP_CUDA(cudaMemcpyAsync(&nBytes, dOff.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
+        MP_CUDA(cudaStreamSynchronize(st));
+        if (dCig.reserve((size_t)nBytes + 16)) return MP_ERR_CUDA;
+        uint32_t cigBase = (uint32_t)HC.size();
+        if (nOk) {
+            k_assemble_write<<<g, 128, 0, st>>>(n, cands, dLT.as<MpDpTask>(), dLO.as<MpDpOut>(), dRT.as<MpDpTask>(), dRO.as<MpDpOut>(),
+                                                dLP.as<uint8_t>(), dRP.as<uint8_t>(), patStride, A, dOk.as<uint32_t>(), dIdx.as<uint32_t>(),
+                                                dOff.as<uint32_t>(), cigBase, dRes.as<mp_pair_result>(), dCig.as<char>());
+            MP_CUDA(cudaGetLastError());
+            size_t h0 = H.size();
+            H.resize(h0 + nOk); HC.resize((size_t)cigBase + nBytes);
+            MP_CUDA(cudaMemcpyAsync(H.data() + h0, dRes.p, (size_t)nOk * sizeof(mp_pair_result), cudaMemcpyDeviceToHost, st));
+            MP_CUDA(cudaMemcpyAsync(HC.data() + cigBase, dCig.p, nBytes, cudaMemcpyDeviceToHost, st));
+            MP_CUDA(cudaStreamSynchronize(st));
+        }
+        // work accounting: one left task per candidate, one right task per passing left
+        {
+            std::vector<MpDpTask> hl(n), hr(n);
+            MP_CUDA(cudaMemcpy(hl.data(), dLT.p, (size_t)n * sizeof(MpDpTask), cudaMemcpyDeviceToHost));
+            MP_CUDA(cudaMemcpy(hr.data(), dRT.p, (size_t)n * sizeof(MpDpTask), cudaMemcpyDeviceToHost));
+            for (uint32_t c = 0; c < n; ++c) {
+                cells += (uint64_t)hl[c].refLen * hl[c].readLen; ++tasksRun;
+                if (hr[c].valid) { cells += (uint64_t)hr[c].refLen * hr[c].readLen; ++tasksRun; }
+            }
+        }
+    }
+    dLT.release(); dRT.release(); dLO.release(); dRO.release(); dLP.release(); dRP.release();
+    dOk.release(); dBytes.release(); dIdx.release(); dOff.release(); dRes.release(); dCig.release();
+    // ---- per pair: sort, drop exact duplicates (OutputBuffer::arrayCopyNRemoveDuplicate, DV-DPfunctions.h:167-196) ----
+    auto key = [](const mp_pair_result &a) { return std::make_tuple(a.algnmt_1, a.algnmt_2, a.score_1, a.score_2); };
+    size_t w = 0, i = 0;
+    uint64_t nPairsAligned = 0;
+    while (i < H.size()) {
+        size_t j = i;
+        while (j < H.size() && H[j].readID == H[i].readID) ++j;
+        std::stable_sort(H.begin() + i, H.begin() + j, [&](const mp_pair_result &a, const mp_pair_result &b) { return key(a) < key(b); });
+        size_t first = w;
+        H[w++] = H[i];
+        for (size_t k = i + 1; k < j; ++k) if (key(H[w - 1]) < key(H[k])) H[w++] = H[k];
+        (void)first;
+        ++nPairsAligned;
+        i = j;
+    }
+    H.resize(w);
+    out->numDPAlignedPair = nPairsAligned; out->numDPAlignment = w;
+    return 0;
+}
+
+// =====================================================================================
+// C-ABI
+// =====================================================================================
+extern "C" int mp_init(int device, mp_context **pctx)
+{
+    if (!pctx) { mp_set_error("mp_init: null argument"); return MP_ERR_ARG; }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) { mp_set_error("mp_init: no CUDA device (%s); there is no CPU fallback", cudaGetErrorString(e)); return MP_ERR_CUDA; }
+    if (device < 0 || device >= count) { mp_set_error("mp_init: device %d out of range (%d devices)", device, count); return MP_ERR_ARG; }
+    MP_CUDA(cudaSetDevice(device));
+    mp_context *ctx = new mp_context;
+    ctx->device = device;
+    MP_CUDA(cudaStreamCreate(&ctx->stream));
+    for (int i = 0; i < 8; ++i) MP_CUDA(cudaEventCreate(&ctx->ev[i]));
+    *pctx = ctx;
+    return 0;
+}
+extern "C" void mp_destroy(mp_context *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    DevBuf *bufs[] = { &ctx->dBlocks, &ctx->dSuper, &ctx->dSa, &ctx->dLkt, &ctx->dPac, &ctx->dReadsIl, &ctx->dReads, &ctx->dLens,
+                       &ctx->dCounters, &ctx->dSeeds, &ctx->dStubs, &ctx->dHitsPerRead, &ctx->dHitStart, &ctx->dCursor, &ctx->dHits,
+                       &ctx->dSeedPos, &ctx->dNPos, &ctx->dNNeg, &ctx->dCandCount, &ctx->dCandStart, &ctx->dCands, &ctx->dScanTmp,
+                       &ctx->dTasks, &ctx->dRefSeq, &ctx->dReadSeq, &ctx->dTable, &ctx->dPattern, &ctx->dDpOut };
+    for (DevBuf *b : bufs) b->release();
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+extern "C" int mp_index_load(mp_context *ctx, const char *prefix)
+{
+    if (!ctx || !prefix) { mp_set_error("mp_index_load: null argument"); return MP_ERR_ARG; }
+    return mpi_load(ctx, prefix);
+}
+extern "C" int mp_index_info(mp_context *ctx, uint64_t *textLength, uint64_t *inverseSa0, uint64_t cumFreq[5], uint64_t *hbmBytes)
+{
+    if (!ctx || !ctx->hasIndex) { mp_set_error("mp_index_info: no index loaded"); return MP_ERR_STATE; }
+    if (textLength) *textLength = ctx->ix.n;
+    if (inverseSa0) *inverseSa0 = ctx->ix.inverseSa0;
+    if (cumFreq) for (int i = 0; i < 5; ++i) cumFreq[i] = ctx->ix.cum[i];
+    if (hbmBytes) *hbmBytes = ctx->hbmBytes;
+    return 0;
+}
+extern "C" int mp_batch_upload(mp_context *ctx, const uint32_t *queries, const uint32_t *readLengths, uint32_t nReads, uint32_t wordPerQuery)
+{
+    if (!ctx || !queries || !readLengths) { mp_set_error("mp_batch_upload: null argument"); return MP_ERR_ARG; }
+    if (nReads == 0 || (nReads & 1) || wordPerQuery == 0) { mp_set_error("mp_batch_upload: nReads must be even and non-zero"); return MP_ERR_ARG; }
+    MP_CUDA(cudaSetDevice(ctx->device));
+    return mps_upload(ctx, queries, readLengths, nReads, wordPerQuery);
+}
+extern "C" int mp_seed_pairs(mp_context *ctx, const mp_align_params *params)
+{
+    if (!ctx || !params) { mp_set_error("mp_seed_pairs: null argument"); return MP_ERR_ARG; }
+    if (!ctx->hasIndex || !ctx->hasBatch) { mp_set_error("mp_seed_pairs: index and batch must be loaded first"); return MP_ERR_STATE; }
+    if (params->peStrandLeftLeg != 1 || params->peStrandRightLeg != 2) { mp_set_error("only StrandArrangement +/- is supported"); return MP_ERR_ARG; }
+    MP_CUDA(cudaSetDevice(ctx->device));
+    return mps_seed_pairs(ctx, params);
+}
+extern "C" int mp_download_seedpos(mp_context *ctx, mp_seed_pos **readPos, uint64_t *nReadPos, mp_seed_pos **matePos, uint64_t *nMatePos)
+{
+    if (!ctx || !ctx->seeded) { mp_set_error("mp_download_seedpos: mp_seed_pairs has not run"); return MP_ERR_STATE; }
+    return mps_download_seedpos(ctx, readPos, nReadPos, matePos, nMatePos);
+}
+extern "C" int mp_download_candidates(mp_context *ctx, mp_candidate **cands, uint64_t *nCands)
+{
+    if (!ctx || !ctx->seeded) { mp_set_error("mp_download_candidates: mp_seed_pairs has not run"); return MP_ERR_STATE; }
+    *nCands = ctx->nCands;
+    *cands = (mp_candidate *)malloc((ctx->nCands + 1) * sizeof(mp_candidate));
+    if (ctx->nCands) MP_CUDA(cudaMemcpy(*cands, ctx->dCands.p, ctx->nCands * sizeof(mp_candidate), cudaMemcpyDeviceToHost));
+    return 0;
+}
+extern "C" void mp_free(void *p) { free(p); }
+
+extern "C" void mp_default_params(mp_align_params *p, int nt2)
+{
+    memset(p, 0, sizeof *p);
+    p->mmp.seedSAsizeThreshold = 30; p->mmp.seedMinLength = nt2 ? 17 : 22; p->mmp.uniqThreshold = 6; p->mmp.indelFuzz = 5;
+    p->mmp.goodSeedLen = 27; p->mmp.reseedLen = nt2 ? 18 : 23; p->mmp.reseedRLTratio = 0.7; p->mmp.reseedAbsDiff = 4;
+    p->mmp.shortSeedRatio = 0.5;
+    p->matchScore = 1; p->mismatchScore = -2; p->openGapScore = -3; p->extendGapScore = -1;
+    p->softClipLeft = 130; p->softClipRight = 130;
+    p->insert_low = 1; p->insert_high = 500;
+    p->peStrandLeftLeg = 1; p->peStrandRightLeg = 2; p->skipDefaultDP = 0; p->maxReadLength = 120;
+}
+
+// SemiGlobalAligner::performAlignment seam (CPU_DPfunctions.h:103-111)
+extern "C" int mp_dp_batch(mp_context *ctx,
+                           const uint32_t *packedDNA, const uint32_t *DNALengths, uint32_t maxDNALength,
+                           const uint32_t *packedRead, const uint32_t *readLengths, uint32_t maxReadLength,
+                           const int32_t *cutoffs, int32_t *scores, uint32_t *hitLocs, uint32_t *maxScoreCounts,
+                           uint8_t *pattern, uint32_t n, const uint32_t *clipLt, const uint32_t *clipRt,
+                           int32_t mismatchScore, int32_t openGapScore)
+{
+    if (!ctx || !packedDNA || !DNALengths || !packedRead || !readLengths || !cutoffs || !scores || !hitLocs || !maxScoreCounts || !pattern || !clipLt || !clipRt) {
+        mp_set_error("mp_dp_batch: null argument"); return MP_ERR_ARG;
+    }
+    if (mismatchScore > -1 || mismatchScore < openGapScore * 2 || mismatchScore < -4 || openGapScore < -6 || openGapScore >= -1) {
+        mp_set_error("mp_dp_batch: score parameters outside the supported range (CPU_DP.cpp:199-208)"); return MP_ERR_ARG;
+    }
+    if (n == 0) return 0;
+    MP_CUDA(cudaSetDevice(ctx->device));
+    const uint32_t wDNA = (maxDNALength + 15) >> 4, wRead = (maxReadLength + 15) >> 4;
+    // un-interleave into one byte per base (host side of the seam; the kernels take bytes)
+    std::vector<uint8_t> hRef((size_t)n * maxDNALength), hRead((size_t)n * maxReadLength);
+    for (uint32_t t = 0; t < n; ++t) {
+        size_t dT = (size_t)(t / 32) * 32 * wDNA + (t % 32), rT = (size_t)(t / 32) * 32 * wRead + (t % 32);
+        for (uint32_t i = 1; i <= DNALengths[t] && i <= maxDNALength; ++i)
+            hRef[(size_t)t * maxDNALength + i - 1] = (packedDNA[dT + ((i >> 4) << 5)] >> ((15 - (i & 15)) << 1)) & 3;
+        for (uint32_t i = 1; i <= readLengths[t] && i <= maxReadLength; ++i)
+            hRead[(size_t)t * maxReadLength + i - 1] = (packedRead[rT + ((i >> 4) << 5)] >> ((15 - (i & 15)) << 1)) & 3;
+    }
+    DevBuf dRef, dRead, dRL, dDL, dCo, dOut, dPat;
+    const uint32_t patStride = maxDNALength + maxReadLength;
+    if (dRef.reserve(hRef.size()) || dRead.reserve(hRead.size()) || dRL.reserve((size_t)n * 4) || dDL.reserve((size_t)n * 4) ||
+        dCo.reserve((size_t)n * 4) || dOut.reserve((size_t)n * sizeof(MpDpOut)) || dPat.reserve((size_t)n * patStride)) return MP_ERR_CUDA;
+    MP_CUDA(cudaMemcpy(dRef.p, hRef.data(), hRef.size(), cudaMemcpyHostToDevice));
+    MP_CUDA(cudaMemcpy(dRead.p, hRead.data(), hRead.size(), cudaMemcpyHostToDevice));
+    MP_CUDA(cudaMemcpy(dDL.p, DNALengths, (size_t)n * 4, cudaMemcpyHostToDevice));
+    MP_CUDA(cudaMemcpy(dRL.p, readLengths, (size_t)n * 4, cudaMemcpyHostToDevice));
+    MP_CUDA(cudaMemcpy(dCo.p, cutoffs, (size_t)n * 4, cudaMemcpyHostToDevice));
+    MpDpParams P; P.clipLt = (int)clipLt[0]; P.clipRt = (int)clipRt[0]; P.mismatch = mismatchScore; P.open = openGapScore;
+    int rc = mpd_run_explicit(ctx, dRef.as<uint8_t>(), dDL.as<uint32_t>(), maxDNALength, dRead.as<uint8_t>(), dRL.as<uint32_t>(),
+                              maxReadLength, dCo.as<int32_t>(), n, P, dOut.as<MpDpOut>(), dPat.as<uint8_t>(), patStride);
+    if (rc) return rc;
+    std::vector<MpDpOut> ho(n);
+    std::vector<uint8_t> hp((size_t)n * patStride);
+    MP_CUDA(cudaMemcpyAsync(ho.data(), dOut.p, (size_t)n * sizeof(MpDpOut), cudaMemcpyDeviceToHost, ctx->stream));
+    MP_CUDA(cudaMemcpyAsync(hp.data(), dPat.p, hp.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    MP_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t t = 0; t < n; ++t) {
+        scores[t] = ho[t].score; hitLocs[t] = ho[t].hitLoc; maxScoreCounts[t] = ho[t].count;
+        if (ho[t].patLen) memcpy(pattern + (size_t)t * patStride, hp.data() + (size_t)t * patStride, ho[t].patLen + 1);
+    }
+    dRef.release(); dRead.release(); dRL.release(); dDL.release(); dCo.release(); dOut.release(); dPat.release();
+    return 0;
+}
+
+extern "C" int mp_align_pairs(mp_context *ctx, const mp_align_params *params, mp_results *out)
+{
+    if (!ctx || !params || !out) { mp_set_error("mp_align_pairs: null argument"); return MP_ERR_ARG; }
+    if (!ctx->hasIndex || !ctx->hasBatch) { mp_set_error("mp_align_pairs: index and batch must be loaded first"); return MP_ERR_STATE; }
+    if (params->matchScore != 1 || params->extendGapScore != -1 || params->mismatchScore > -1 || params->mismatchScore < params->openGapScore * 2 ||
+        params->mismatchScore < -4 || params->openGapScore < -6 || params->openGapScore >= -1) {
+        mp_set_error("mp_align_pairs: score parameters outside the supported range (CPU_DP.cpp:199-208)"); return MP_ERR_ARG;
+    }
+    MP_CUDA(cudaSetDevice(ctx->device));
+    memset(out, 0, sizeof *out);
+    ctx->hPairs.clear(); ctx->hRescued.clear(); ctx->hSingles.clear(); ctx->hCigars.clear();
+    MP_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
+    if (!ctx->seeded) { if (int rc = mp_seed_pairs(ctx, params)) return rc; }
+    MP_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
+    uint64_t cells = 0, tasksRun = 0;
+    if (int rc = deep_dp(ctx, params, out, cells, tasksRun)) return rc;
+    MP_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
+    MP_CUDA(cudaStreamSynchronize(ctx->stream));
+    unsigned long long hc[16];
+    MP_CUDA(cudaMemcpy(hc, ctx->dCounters.p, sizeof hc, cudaMemcpyDeviceToHost));
+    out->n_occ = hc[2] + hc[5]; out->n_sa = hc[3]; out->n_lkt = hc[4];
+    out->dp_cells = cells; out->dp_tasks = tasksRun;
+    cudaEventElapsedTime(&out->ms_seed, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&out->ms_sa, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&out->ms_pair, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&out->ms_dp, ctx->ev[5], ctx->ev[6]);
+    cudaEventElapsedTime(&out->ms_total, ctx->ev[4], ctx->ev[6]);
+    out->pairs = ctx->hPairs.data(); out->n_pairs = ctx->hPairs.size();
+    out->rescued = ctx->hRescued.data(); out->n_rescued = ctx->hRescued.size();
+    out->singles = ctx->hSingles.data(); out->n_singles = ctx->hSingles.size();
+    out->cigars = ctx->hCigars.data(); out->cigar_bytes = ctx->hCigars.size();
+    ctx->seeded = false;       // the batch has been consumed
+    return 0;
+}
+extern "C" void mp_results_release(mp_context *ctx, mp_results *res)
+{
+    if (!ctx) return;
+    ctx->hPairs.clear(); ctx->hRescued.clear(); ctx->hSingles.clear(); ctx->hCigars.clear();
+    if (res) memset(res, 0, sizeof *res);
+}
+
+extern "C" int mp_index_build(mp_context *ctx, const uint8_t *text2bit, uint64_t textLength)
+{
+    (void)ctx; (void)text2bit; (void)textLength;
+    mp_set_error("mp_index_build: not implemented yet");
+    return MP_ERR_STATE;
+}
+extern "C" int mp_index_save(mp_context *ctx, const char *prefix)
+{
+    (void)ctx; (void)prefix;
+    mp_set_error("mp_index_save: not implemented yet");
+    return MP_ERR_STATE;
+}

@@ -1,0 +1,100 @@
+// mp_context.h -- library-internal context (one per GPU) and helpers.
+#pragma once
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../../include/megapath_b200.h"
+#include "mp_index.cuh"
+
+void mp_set_error(const char *fmt, ...);
+
+#define MP_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    mp_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); \
+    return MP_ERR_CUDA; } } while (0)
+
+// growable device buffer
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { mp_set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); return MP_ERR_CUDA; }
+        cap = want; return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return (T *)p; }
+};
+
+// ---- seeding records (device) ----
+struct MpSeed {            // SeedSAalign (DV-DPfunctions.cpp:2161-2171) + owner
+    uint64_t sa_l;
+    uint32_t strandIdx;    // read * 2 + (strand == '-')
+    uint32_t hitBase;      // first slot of this seed in the hit-stub list
+    uint16_t query_offset, seed_len, sa_diff, pad;
+};
+struct MpHit {             // SeedAlign (DV-DPfunctions.cpp:2144-2159)
+    uint64_t offset;       // target text position (u64, wraps like the reference)
+    uint16_t length, query_offset, multiplicity;
+    uint16_t strand;       // 0 '+', 1 '-'
+};
+struct MpDpTask {          // one semi-global DP instance
+    uint64_t refStart;     // window start in the text
+    uint32_t refLen;       // DNALength
+    uint32_t readID;
+    uint16_t readLen;
+    uint8_t  strand;       // 1 '+', 2 '-' (read is reverse-complemented)
+    uint8_t  valid;
+    int32_t  cutoff;
+};
+struct MpDpOut {
+    int32_t score; uint32_t hitLoc; uint32_t count; uint32_t patLen;
+};
+
+struct mp_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8];
+    // index
+    bool hasIndex = false;
+    MpIndexView ix;
+    DevBuf dBlocks, dSuper, dSa, dLkt, dPac;
+    uint64_t hbmBytes = 0;
+    std::vector<uint64_t> hSa; uint64_t saInterval = 16;   // kept for mp_index_save
+    // batch
+    bool hasBatch = false, seeded = false;
+    uint32_t nReads = 0, wpq = 0;
+    DevBuf dReadsIl, dReads, dLens;
+    // seeding
+    DevBuf dCounters;                 // u64[16]: 0 seeds, 1 hit stubs, 2 occ, 3 sa, 4 lkt, 5 lf, 6 work-queue
+    DevBuf dSeeds, dStubs, dHitsPerRead, dHitStart, dCursor, dHits, dSeedPos, dNPos, dNNeg;
+    DevBuf dCandCount, dCandStart, dCands, dScanTmp;
+    uint64_t nSeeds = 0, nHits = 0, nCands = 0;
+    uint64_t capSeeds = 0, capStubs = 0;
+    mp_align_params seedParams;
+    // DP
+    DevBuf dTasks, dRefSeq, dReadSeq, dTable, dPattern, dDpOut;
+    // results (host, owned until release)
+    std::vector<mp_pair_result> hPairs, hRescued;
+    std::vector<mp_single_result> hSingles;
+    std::vector<char> hCigars;
+};
+
+// mp_index.cu
+int mpi_load(mp_context *ctx, const char *prefix);
+int mpi_build_from_words(mp_context *ctx, const uint32_t *hBwtWords, uint64_t n, uint64_t inverseSa0, const uint64_t cum[5]);
+// mp_seed.cu
+int mps_seed_pairs(mp_context *ctx, const mp_align_params *P);
+// mp_dp.cu
+struct MpDpParams { int clipLt, clipRt, mismatch, open; };
+// tasks (device) -> outs (device); sequences are extracted from the index / uploaded reads
+int mpd_run_tasks(mp_context *ctx, const MpDpTask *dTasks, uint32_t nTasks, uint32_t maxRefLen, uint32_t maxReadLen,
+                  const MpDpParams &P, MpDpOut *dOuts, uint8_t *dPatterns, uint32_t patStride);
+// explicit sequences (one byte per base, stride maxRefLen / maxReadLen)
+int mpd_run_explicit(mp_context *ctx, const uint8_t *dRef, const uint32_t *dRefLens, uint32_t maxRefLen,
+                     const uint8_t *dRead, const uint32_t *dReadLens, uint32_t maxReadLen, const int32_t *dCutoffs,
+                     uint32_t nTasks, const MpDpParams &P, MpDpOut *dOuts, uint8_t *dPatterns, uint32_t patStride);

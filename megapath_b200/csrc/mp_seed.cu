@@ -1,0 +1,415 @@
+// mp_seed.cu -- MMP seeding, SA resolution, seed merging/filtering and paired-end candidate
+// generation on the device.  Replaces, for all pairs of a batch,
+//   mmp<0>/mmp<2> + CHECK_AND_SET_LAST / CHECK_AND_ADD_RANGE   DV-DPfunctions.cpp:2188-2377
+//   PairEndSeedingBatch::mmpSeeding post-processing             DV-DPfunctions.cpp:2474-2553
+//   pairEndMerge / findRevStart / mergeAndPairPairedEnd         DV-DPfunctions.cpp:1844-2119
+//
+// Kernels (DESIGN.md "Seeding"):
+//   k_mmp      4 lanes per read-strand; every backward-search step fetches the two 64-byte
+//              occ blocks of (l, r+1) as one 16-byte load per lane and reduces the partial
+//              ranks with two quad shuffles.  Quads pull read-strands from a work counter.
+//   k_expand   one thread per (seed, k) suffix-array hit: LF walk to the next sampled SA
+//              index, text position, SeedAlign record written into its read's segment.
+//   k_merge    one thread per read: sort hits by (strand, position), chain within indelFuzz,
+//              covered-length union, uniqueness / length filters -> SeedPos entries.
+//   k_pair     one thread per pair and orientation: window join -> CandidateInfo.
+#include "mp_context.h"
+#include <cub/device/device_scan.cuh>
+
+struct MmpDev {
+    int seedSAsizeThreshold, seedMinLength, uniqThreshold, indelFuzz, goodSeedLen, reseedLen, reseedAbsDiff;
+    double reseedRLTratio, shortSeedRatio;
+};
+
+// ------------------------------------------------------------------------------------
+// de-interleave the 32-read interleaved query buffer (QueryParser.cpp:184-203)
+// ------------------------------------------------------------------------------------
+__global__ void k_deinterleave(const uint32_t *__restrict__ il, uint32_t *__restrict__ out, uint32_t nReads, uint32_t wpq)
+{
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t total = (uint64_t)nReads * wpq;
+    if (t >= total) return;
+    // consecutive threads read consecutive interleaved words
+    uint64_t grp = t / (32ull * wpq);
+    uint32_t within = (uint32_t)(t - grp * 32ull * wpq);
+    uint32_t j = within >> 5, r32 = within & 31;
+    uint64_t r = grp * 32 + r32;
+    if (r < nReads) out[r * wpq + j] = il[t];
+}
+
+__device__ __forceinline__ uint32_t read_base(const uint32_t *__restrict__ rd, int p)
+{
+    return (__ldg(rd + (p >> 4)) >> ((p & 15) << 1)) & 3;
+}
+
+// 13-mer key at scan position i (DV-DPfunctions.cpp:2233-2239, 2326-2332): q[i+k] at bits 2k
+__device__ __forceinline__ uint32_t lkt_key(const uint32_t *__restrict__ rd, int len, int i, int strand)
+{
+    int p0 = strand ? i : len - 13 - i;                       // lowest read position of the 13-mer
+    uint32_t w0 = __ldg(rd + (p0 >> 4)), w1 = __ldg(rd + (p0 >> 4) + 1);
+    uint32_t x = __funnelshift_r(w0, w1, (p0 & 15) << 1);      // base p0 in the low bits
+    if (strand) return (~x) & 0x3FFFFFFu;                      // complemented, same order
+    uint32_t t = __brev(x);                                    // reverse the order of the 2-bit groups
+    t = ((t >> 1) & 0x55555555u) | ((t & 0x55555555u) << 1);
+    return (t >> 6) & 0x3FFFFFFu;
+}
+
+// rank of symbol c in one lane's quarter of a 64-byte block
+__device__ __forceinline__ uint32_t quad_partial(uint4 v, uint32_t sub, uint32_t c, uint32_t off)
+{
+    if (sub == 0) return c == 0 ? v.x : c == 1 ? v.y : c == 2 ? v.z : v.w;
+    int r = (int)off - 64 * (int)(sub - 1);
+    if (r <= 0) return 0;
+    return mp_word_count(v.x, c, min(r, 16)) + mp_word_count(v.y, c, min(max(r - 16, 0), 16)) +
+           mp_word_count(v.z, c, min(max(r - 32, 0), 16)) + mp_word_count(v.w, c, min(max(r - 48, 0), 16));
+}
+
+__global__ void __launch_bounds__(256)
+k_mmp(MpIndexView ix, const uint32_t *__restrict__ reads, const uint32_t *__restrict__ lens, uint32_t wpq,
+      uint32_t nStrands, MmpDev P, MpSeed *__restrict__ seeds, uint32_t *__restrict__ stubs,
+      unsigned long long *__restrict__ counters, uint32_t *__restrict__ hitsPerRead,
+      uint32_t capSeeds, uint32_t capStubs)
+{
+    const unsigned lane = threadIdx.x & 31, sub = lane & 3, qbase = lane & ~3u;
+    const unsigned qmask = 0xFu << qbase;
+    const uint64_t n = ix.n;
+    unsigned long long nOcc = 0, nLkt = 0;
+    while (true) {
+        uint32_t s = 0;
+        if (sub == 0) s = (uint32_t)atomicAdd(&counters[6], 1ull);
+        s = __shfl_sync(qmask, s, qbase);
+        if (s >= nStrands) break;
+        const uint32_t read = s >> 1, strand = s & 1;
+        const int len = (int)lens[read];
+        const uint32_t *rd = reads + (size_t)read * wpq;
+        int i = 0, seed_len = 0;
+        uint64_t l = 0, r = n, nextl = 0, nextr = 0, last_l = 0, last_r = n;
+        int last_seed_len = 0;
+        bool done = false;
+        while (!done) {
+            bool emit = false; int x = 0;
+            if (i < len) {
+                bool step = true;
+                if (seed_len == 0) {
+                    if (len - i < P.seedMinLength) { step = false; emit = true; x = strand ? len - seed_len : 0; done = true; }
+                    else {
+                        uint32_t key = lkt_key(rd, len, i, strand);
+                        nextl = key == 0 ? 1 : __ldg(ix.lkt + key - 1) + 1;
+                        nextr = __ldg(ix.lkt + key);
+                        i += 12; seed_len = 12; ++nLkt;
+                    }
+                } else {
+                    uint32_t c = strand ? 3 - read_base(rd, i) : read_base(rd, len - 1 - i);
+                    uint64_t a = l - (l > ix.inverseSa0), b = (r + 1) - ((r + 1) > ix.inverseSa0);
+                    uint64_t ba = a / MP_BLK_SYMS, bb = b / MP_BLK_SYMS;
+                    uint32_t oa = (uint32_t)(a - ba * MP_BLK_SYMS), ob = (uint32_t)(b - bb * MP_BLK_SYMS);
+                    uint4 va = __ldg(ix.blocks + ba * 4 + sub);
+                    uint4 vb = __ldg(ix.blocks + bb * 4 + sub);
+                    uint32_t pa = quad_partial(va, sub, c, oa), pb = quad_partial(vb, sub, c, ob);
+                    pa += __shfl_xor_sync(qmask, pa, 1); pb += __shfl_xor_sync(qmask, pb, 1);
+                    pa += __shfl_xor_sync(qmask, pa, 2); pb += __shfl_xor_sync(qmask, pb, 2);
+                    nextl = mp_cum(ix, c) + __ldg(ix.super + (ba >> MP_SUPER_SHIFT) * 4 + c) + pa + 1;
+                    nextr = mp_cum(ix, c) + __ldg(ix.super + (bb >> MP_SUPER_SHIFT) * 4 + c) + pb;
+                    nOcc += 2;
+                }
+                if (step) {
+                    if (nextl <= nextr) {
+                        if (seed_len >= P.seedMinLength && nextr - nextl < r - l) { last_r = r; last_l = l; last_seed_len = seed_len; }
+                        l = nextl; r = nextr; ++seed_len;
+                    } else { emit = true; x = strand ? i - seed_len : len - i; }
+                }
+            } else { emit = true; x = strand ? len - seed_len : 0; done = true; }
+            if (emit) {
+                // CHECK_AND_ADD_RANGE (DV-DPfunctions.cpp:2197-2219)
+                int diff = 0;
+                if (seed_len >= P.seedMinLength) {
+                    if (seed_len >= P.reseedLen && last_r - last_l + 1 <= (uint64_t)P.seedSAsizeThreshold &&
+                        ((uint64_t)(seed_len - last_seed_len) <= (uint64_t)P.reseedAbsDiff ||
+                         seed_len * P.reseedRLTratio < (double)last_seed_len)) {
+                        diff = seed_len - last_seed_len;
+                        l = last_l; r = last_r; seed_len = last_seed_len;
+                    }
+                    uint64_t d = r - l; if (d > (uint64_t)P.seedSAsizeThreshold) d = P.seedSAsizeThreshold;
+                    uint32_t cnt = (uint32_t)d + 1;
+                    uint32_t slot = 0, hb = 0;
+                    if (sub == 0) {
+                        slot = (uint32_t)atomicAdd(&counters[0], 1ull);
+                        hb = (uint32_t)atomicAdd(&counters[1], (unsigned long long)cnt);
+                        atomicAdd(&hitsPerRead[read], cnt);
+                        if (slot < capSeeds) {
+                            MpSeed sd; sd.sa_l = l; sd.strandIdx = s; sd.hitBase = hb;
+                            sd.query_offset = (uint16_t)(x & 0x3ff); sd.seed_len = (uint16_t)(seed_len & 0xfff);
+                            sd.sa_diff = (uint16_t)d; sd.pad = 0;
+                            seeds[slot] = sd;
+                        }
+                    }
+                    slot = __shfl_sync(qmask, slot, qbase); hb = __shfl_sync(qmask, hb, qbase);
+                    for (uint32_t k = sub; k < cnt; k += 4) if (hb + k < capStubs) stubs[hb + k] = slot;
+                }
+                i -= diff;
+                i -= min(seed_len, P.seedMinLength);
+                l = 0; r = n; seed_len = 0; last_l = 0; last_r = n; last_seed_len = 0;
+            }
+            ++i;
+        }
+    }
+    if (sub == 0) { atomicAdd(&counters[2], nOcc); atomicAdd(&counters[4], nLkt); }
+}
+
+// ------------------------------------------------------------------------------------
+// SA hits -> SeedAlign records (DV-DPfunctions.cpp:2477-2499)
+// ------------------------------------------------------------------------------------
+__global__ void k_expand(MpIndexView ix, const MpSeed *__restrict__ seeds, const uint32_t *__restrict__ stubs, uint64_t nStubs,
+                         const uint32_t *__restrict__ lens, MmpDev P, const uint32_t *__restrict__ hitStart,
+                         uint32_t *__restrict__ cursor, MpHit *__restrict__ hits, unsigned long long *__restrict__ counters)
+{
+    uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= nStubs) return;
+    MpSeed sd = seeds[stubs[h]];
+    uint32_t k = (uint32_t)h - sd.hitBase;
+    uint32_t steps = 0;
+    uint64_t sa = mp_sa(ix, sd.sa_l + k, &steps);
+    uint32_t read = sd.strandIdx >> 1, strand = sd.strandIdx & 1;
+    uint32_t readLen = lens[read], off = sd.query_offset, seedlen = sd.seed_len;
+    uint64_t t = strand == 0 ? sa - off : sa - (uint64_t)(uint32_t)(readLen - seedlen - off);
+    MpHit hit;
+    hit.offset = t;
+    hit.multiplicity = ((int)seedlen >= P.goodSeedLen || seedlen >= readLen / 2) ? 1 : (uint16_t)(sd.sa_diff + 1);
+    hit.length = (uint16_t)seedlen; hit.query_offset = (uint16_t)off; hit.strand = (uint16_t)strand;
+    uint32_t slot = hitStart[read] + atomicAdd(&cursor[read], 1u);
+    hits[slot] = hit;
+    atomicAdd(&counters[3], 1ull);
+    atomicAdd(&counters[5], (unsigned long long)steps);
+}
+
+// ------------------------------------------------------------------------------------
+// per-read merge + filter (DV-DPfunctions.cpp:2501-2553).  Output SeedPos entries are
+// written over the read's own hit segment: '+' entries first, then '-'.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ bool hit_less(const MpHit &a, const MpHit &b)
+{
+    return a.strand != b.strand ? a.strand < b.strand : a.offset < b.offset;
+}
+__global__ void k_merge(const uint32_t *__restrict__ hitStart, MpHit *__restrict__ hits, uint32_t nReads, MmpDev P,
+                        mp_seed_pos *__restrict__ outSeeds, uint32_t *__restrict__ nPos, uint32_t *__restrict__ nNeg)
+{
+    uint32_t rdx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rdx >= nReads) return;
+    uint32_t s0 = hitStart[rdx], s1 = hitStart[rdx + 1];
+    MpHit *h = hits + s0;
+    int cnt = (int)(s1 - s0);
+    for (int a = 1; a < cnt; ++a) {                 // insertion sort by (strand, offset)
+        MpHit key = h[a]; int b = a - 1;
+        while (b >= 0 && hit_less(key, h[b])) { h[b + 1] = h[b]; --b; }
+        h[b + 1] = key;
+    }
+    // pass 1: chains -> (pos, total_len, keep) written to a compact list in place
+    uint32_t maxLen = 0; int nOut = 0, m = 0;
+    mp_seed_pos *out = outSeeds + s0;
+    const uint32_t evenID = rdx & ~1u;
+    while (m < cnt) {
+        uint32_t strand = h[m].strand;
+        uint64_t pos = h[m].offset;
+        int e = m + 1;
+        while (e < cnt && h[e].strand == strand && h[e].offset <= pos + (uint64_t)P.indelFuzz) ++e;
+        bool uniq = false;
+        for (int a = m; a < e; ++a) uniq |= (int)h[a].multiplicity <= P.uniqThreshold && (int)h[a].length >= P.seedMinLength;
+        // sort the chain's read intervals by (start, end)
+        for (int a = m + 1; a < e; ++a) {
+            MpHit key = h[a]; int b = a - 1;
+            uint32_t ks = key.query_offset, ke = key.query_offset + key.length;
+            while (b >= m && (h[b].query_offset > ks || (h[b].query_offset == ks && (uint32_t)h[b].query_offset + h[b].length > ke))) { h[b + 1] = h[b]; --b; }
+            h[b + 1] = key;
+        }
+        uint32_t total = 0, cs = 0, ce = 0;
+        for (int a = m; a < e; ++a) {
+            uint32_t f = h[a].query_offset, g = (uint32_t)h[a].query_offset + h[a].length;
+            if (f >= ce) { total += ce - cs; cs = f; }
+            ce = max(ce, g);
+        }
+        total += ce - cs;
+        maxLen = max(maxLen, total);
+        if (uniq || (int)total >= P.goodSeedLen) {
+            mp_seed_pos sp; sp.pos = pos; sp.paired_seedLength = total; sp.strand_readID = evenID | (strand << 31);
+            out[nOut++] = sp;      // nOut <= m < e: never overtakes unread hits (16-byte records over 16-byte records)
+        }
+        m = e;
+    }
+    // pass 2: shortSeedRatio filter, compact
+    int w = 0, np = 0;
+    for (int a = 0; a < nOut; ++a) {
+        mp_seed_pos sp = out[a];
+        if ((double)sp.paired_seedLength >= P.shortSeedRatio * (double)maxLen) {
+            out[w++] = sp; np += !(sp.strand_readID >> 31);
+        }
+    }
+    nPos[rdx] = np; nNeg[rdx] = w - np;
+}
+
+// ------------------------------------------------------------------------------------
+// pairing (DV-DPfunctions.cpp:1968-2070).  write == nullptr: count only.
+// ------------------------------------------------------------------------------------
+#define MP_MARGIN(l) (((l) > 100) ? 30 : 25)       // DP2_MARGIN, DV-DPfunctions.cpp:1760
+__device__ uint32_t pair_one(const mp_seed_pos *left, int nLeft, const mp_seed_pos *right, int nRight,
+                             int negLen, int insert_low, int insert_high, uint32_t readIDLeft, mp_candidate *write)
+{
+    if (nLeft == 0 || nRight == 0) return 0;
+    int margin = MP_MARGIN(negLen);
+    int length_low = insert_low - negLen - margin; if (length_low < 0) length_low = 0;
+    int length_high = insert_high - negLen + margin;
+    uint32_t nc = 0;
+    int preStart = 0;
+    uint64_t prevLoc = 0;
+    for (int a = 0; a < nLeft; ++a) {
+        uint64_t readLoc = left[a].pos;
+        if (a > 0 && !(prevLoc + 5 < readLoc)) continue;     // MC_Compress :2015-2026
+        prevLoc = readLoc;
+        for (int b = preStart; b < nRight; ++b) {
+            uint64_t mateLoc = right[b].pos;
+            if (readLoc + (uint64_t)(int64_t)length_high < mateLoc) break;
+            else if (readLoc + (uint64_t)(int64_t)length_low <= mateLoc) {
+                if (write) { mp_candidate ci; ci.readIDLeft = readIDLeft; ci.pad = 0; ci.pos[0] = readLoc; ci.pos[1] = mateLoc; write[nc] = ci; }
+                ++nc; preStart = b;
+            }
+        }
+    }
+    return nc;
+}
+__global__ void k_pair(const uint32_t *__restrict__ hitStart, const mp_seed_pos *__restrict__ sp, const uint32_t *__restrict__ nPos,
+                       const uint32_t *__restrict__ nNeg, const uint32_t *__restrict__ lens, uint32_t nPairs, int insert_low, int insert_high,
+                       uint32_t *__restrict__ candCount, const uint32_t *__restrict__ candStart, mp_candidate *__restrict__ cands)
+{
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nPairs) return;
+    uint32_t r1 = 2 * p, r2 = 2 * p + 1;
+    const mp_seed_pos *pos1 = sp + hitStart[r1], *neg1 = pos1 + nPos[r1];
+    const mp_seed_pos *pos2 = sp + hitStart[r2], *neg2 = pos2 + nPos[r2];
+    mp_candidate *w = cands ? cands + candStart[p] : nullptr;
+    // read '+' with mate '-' (readIDLeft even), then mate '+' with read '-' (odd)
+    uint32_t c0 = pair_one(pos1, nPos[r1], neg2, nNeg[r2], (int)lens[r2], insert_low, insert_high, r1, w);
+    uint32_t c1 = pair_one(pos2, nPos[r2], neg1, nNeg[r1], (int)lens[r1], insert_low, insert_high, r2, w ? w + c0 : nullptr);
+    if (!cands) candCount[p] = c0 + c1;
+}
+
+// ------------------------------------------------------------------------------------
+static int exclusive_scan_u32(mp_context *ctx, const uint32_t *in, uint32_t *out, uint64_t n)
+{
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, (int64_t)n, ctx->stream);
+    if (ctx->dScanTmp.reserve(tb)) return MP_ERR_CUDA;
+    cub::DeviceScan::ExclusiveSum(ctx->dScanTmp.p, tb, in, out, (int64_t)n, ctx->stream);
+    return 0;
+}
+
+int mps_upload(mp_context *ctx, const uint32_t *queries, const uint32_t *readLengths, uint32_t nReads, uint32_t wpq)
+{
+    uint64_t nPad = ((uint64_t)nReads + 31) / 32 * 32;
+    size_t bytes = nPad * wpq * 4;
+    if (ctx->dReadsIl.reserve(bytes) || ctx->dReads.reserve(bytes + 64) || ctx->dLens.reserve((size_t)nReads * 4)) return MP_ERR_CUDA;
+    MP_CUDA(cudaMemcpyAsync(ctx->dReadsIl.p, queries, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    MP_CUDA(cudaMemcpyAsync(ctx->dLens.p, readLengths, (size_t)nReads * 4, cudaMemcpyHostToDevice, ctx->stream));
+    MP_CUDA(cudaMemsetAsync(ctx->dReads.p, 0, bytes + 64, ctx->stream));
+    uint64_t total = nPad * wpq;
+    k_deinterleave<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(ctx->dReadsIl.as<uint32_t>(), ctx->dReads.as<uint32_t>(), nReads, wpq);
+    MP_CUDA(cudaGetLastError());
+    ctx->nReads = nReads; ctx->wpq = wpq; ctx->hasBatch = true; ctx->seeded = false;
+    return 0;
+}
+
+int mps_seed_pairs(mp_context *ctx, const mp_align_params *AP)
+{
+    const mp_mmp_params &mp = AP->mmp;
+    MmpDev P;
+    P.seedSAsizeThreshold = mp.seedSAsizeThreshold; P.seedMinLength = mp.seedMinLength; P.uniqThreshold = mp.uniqThreshold;
+    P.indelFuzz = mp.indelFuzz; P.goodSeedLen = mp.goodSeedLen; P.reseedLen = mp.reseedLen; P.reseedAbsDiff = mp.reseedAbsDiff;
+    P.reseedRLTratio = mp.reseedRLTratio; P.shortSeedRatio = mp.shortSeedRatio;
+    if (P.seedMinLength < 13 || P.seedSAsizeThreshold > 1000) { mp_set_error("mmp parameters out of range"); return MP_ERR_ARG; }
+    const uint32_t nReads = ctx->nReads, nStrands = nReads * 2, nPairs = nReads / 2;
+    cudaStream_t st = ctx->stream;
+    if (ctx->dCounters.reserve(16 * 8) || ctx->dHitsPerRead.reserve(((size_t)nReads + 1) * 4) ||
+        ctx->dHitStart.reserve(((size_t)nReads + 1) * 4) || ctx->dCursor.reserve(((size_t)nReads + 1) * 4) ||
+        ctx->dNPos.reserve((size_t)nReads * 4) || ctx->dNNeg.reserve((size_t)nReads * 4)) return MP_ERR_CUDA;
+    if (ctx->capSeeds < (uint64_t)nStrands * 4) ctx->capSeeds = (uint64_t)nStrands * 4;
+    if (ctx->capStubs < (uint64_t)nStrands * 8) ctx->capStubs = (uint64_t)nStrands * 8;
+    unsigned long long hc[16];
+    int dev = 0, nSM = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, dev);
+    MP_CUDA(cudaEventRecord(ctx->ev[0], st));
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        if (ctx->capSeeds > 0xFFFFFFF0ull || ctx->capStubs > 0xFFFFFFF0ull) { mp_set_error("seed buffers exceed 32-bit indexing; use smaller batches"); return MP_ERR_CAPACITY; }
+        if (ctx->dSeeds.reserve(ctx->capSeeds * sizeof(MpSeed)) || ctx->dStubs.reserve(ctx->capStubs * 4)) return MP_ERR_CUDA;
+        MP_CUDA(cudaMemsetAsync(ctx->dCounters.p, 0, 16 * 8, st));
+        MP_CUDA(cudaMemsetAsync(ctx->dHitsPerRead.p, 0, ((size_t)nReads + 1) * 4, st));
+        // persistent grid: 6 CTAs of 256 threads per SM (register bound), quads pull work
+        k_mmp<<<nSM * 6, 256, 0, st>>>(ctx->ix, ctx->dReads.as<uint32_t>(), ctx->dLens.as<uint32_t>(), ctx->wpq, nStrands, P,
+                                      ctx->dSeeds.as<MpSeed>(), ctx->dStubs.as<uint32_t>(), ctx->dCounters.as<unsigned long long>(),
+                                      ctx->dHitsPerRead.as<uint32_t>(), (uint32_t)ctx->capSeeds, (uint32_t)ctx->capStubs);
+        MP_CUDA(cudaGetLastError());
+        MP_CUDA(cudaMemcpyAsync(hc, ctx->dCounters.p, 16 * 8, cudaMemcpyDeviceToHost, st));
+        MP_CUDA(cudaStreamSynchronize(st));
+        if (hc[0] <= ctx->capSeeds && hc[1] <= ctx->capStubs) break;
+        ctx->capSeeds = hc[0] + hc[0] / 8 + 1024; ctx->capStubs = hc[1] + hc[1] / 8 + 1024;   // rerun with exact room
+        if (attempt == 3) { mp_set_error("seed buffers overflowed repeatedly"); return MP_ERR_CAPACITY; }
+    }
+    MP_CUDA(cudaEventRecord(ctx->ev[1], st));
+    ctx->nSeeds = hc[0]; ctx->nHits = hc[1];
+    if (ctx->nHits > 0xFFFFFFF0ull) { mp_set_error("too many seed hits in one batch"); return MP_ERR_CAPACITY; }
+    if (exclusive_scan_u32(ctx, ctx->dHitsPerRead.as<uint32_t>(), ctx->dHitStart.as<uint32_t>(), (uint64_t)nReads + 1)) return MP_ERR_CUDA;
+    size_t hitBytes = (ctx->nHits + 1) * sizeof(MpHit);
+    if (ctx->dHits.reserve(hitBytes) || ctx->dSeedPos.reserve((ctx->nHits + 1) * sizeof(mp_seed_pos))) return MP_ERR_CUDA;
+    MP_CUDA(cudaMemsetAsync(ctx->dCursor.p, 0, ((size_t)nReads + 1) * 4, st));
+    if (ctx->nHits)
+        k_expand<<<(unsigned)((ctx->nHits + 127) / 128), 128, 0, st>>>(ctx->ix, ctx->dSeeds.as<MpSeed>(), ctx->dStubs.as<uint32_t>(), ctx->nHits,
+            ctx->dLens.as<uint32_t>(), P, ctx->dHitStart.as<uint32_t>(), ctx->dCursor.as<uint32_t>(), ctx->dHits.as<MpHit>(),
+            ctx->dCounters.as<unsigned long long>());
+    MP_CUDA(cudaGetLastError());
+    MP_CUDA(cudaEventRecord(ctx->ev[2], st));
+    k_merge<<<(nReads + 127) / 128, 128, 0, st>>>(ctx->dHitStart.as<uint32_t>(), ctx->dHits.as<MpHit>(), nReads, P,
+                                                 ctx->dSeedPos.as<mp_seed_pos>(), ctx->dNPos.as<uint32_t>(), ctx->dNNeg.as<uint32_t>());
+    MP_CUDA(cudaGetLastError());
+    // pairing: count, scan, write
+    if (ctx->dCandCount.reserve(((size_t)nPairs + 1) * 4) || ctx->dCandStart.reserve(((size_t)nPairs + 1) * 4)) return MP_ERR_CUDA;
+    MP_CUDA(cudaMemsetAsync(ctx->dCandCount.p, 0, ((size_t)nPairs + 1) * 4, st));
+    k_pair<<<(nPairs + 127) / 128, 128, 0, st>>>(ctx->dHitStart.as<uint32_t>(), ctx->dSeedPos.as<mp_seed_pos>(), ctx->dNPos.as<uint32_t>(),
+        ctx->dNNeg.as<uint32_t>(), ctx->dLens.as<uint32_t>(), nPairs, AP->insert_low, AP->insert_high,
+        ctx->dCandCount.as<uint32_t>(), nullptr, nullptr);
+    if (exclusive_scan_u32(ctx, ctx->dCandCount.as<uint32_t>(), ctx->dCandStart.as<uint32_t>(), (uint64_t)nPairs + 1)) return MP_ERR_CUDA;
+    uint32_t total = 0;
+    MP_CUDA(cudaMemcpyAsync(&total, ctx->dCandStart.as<uint32_t>() + nPairs, 4, cudaMemcpyDeviceToHost, st));
+    MP_CUDA(cudaStreamSynchronize(st));
+    ctx->nCands = total;
+    if (ctx->dCands.reserve(((size_t)total + 1) * sizeof(mp_candidate))) return MP_ERR_CUDA;
+    if (total)
+        k_pair<<<(nPairs + 127) / 128, 128, 0, st>>>(ctx->dHitStart.as<uint32_t>(), ctx->dSeedPos.as<mp_seed_pos>(), ctx->dNPos.as<uint32_t>(),
+            ctx->dNNeg.as<uint32_t>(), ctx->dLens.as<uint32_t>(), nPairs, AP->insert_low, AP->insert_high,
+            ctx->dCandCount.as<uint32_t>(), ctx->dCandStart.as<uint32_t>(), ctx->dCands.as<mp_candidate>());
+    MP_CUDA(cudaGetLastError());
+    MP_CUDA(cudaEventRecord(ctx->ev[3], st));
+    MP_CUDA(cudaStreamSynchronize(st));
+    ctx->seedParams = *AP;
+    ctx->seeded = true;
+    return 0;
+}
+
+// ---- downloads in the reference's array layout (DV-DPfunctions.cpp:2555-2594) ----
+int mps_download_seedpos(mp_context *ctx, mp_seed_pos **readPos, uint64_t *nReadPos, mp_seed_pos **matePos, uint64_t *nMatePos)
+{
+    const uint32_t nReads = ctx->nReads;
+    std::vector<uint32_t> hs(nReads + 1), np(nReads), nn(nReads);
+    std::vector<mp_seed_pos> sp(ctx->nHits + 1);
+    MP_CUDA(cudaMemcpy(hs.data(), ctx->dHitStart.p, ((size_t)nReads + 1) * 4, cudaMemcpyDeviceToHost));
+    MP_CUDA(cudaMemcpy(np.data(), ctx->dNPos.p, (size_t)nReads * 4, cudaMemcpyDeviceToHost));
+    MP_CUDA(cudaMemcpy(nn.data(), ctx->dNNeg.p, (size_t)nReads * 4, cudaMemcpyDeviceToHost));
+    if (ctx->nHits) MP_CUDA(cudaMemcpy(sp.data(), ctx->dSeedPos.p, ctx->nHits * sizeof(mp_seed_pos), cudaMemcpyDeviceToHost));
+    for (int mate = 0; mate < 2; ++mate) {
+        uint64_t tot = 2;
+        for (uint32_t r = mate; r < nReads; r += 2) tot += np[r] + nn[r];
+        mp_seed_pos *o = (mp_seed_pos *)malloc(tot * sizeof(mp_seed_pos));
+        uint64_t k = 0;
+        for (uint32_t r = mate; r < nReads; r += 2) for (uint32_t a = 0; a < np[r]; ++a) o[k++] = sp[hs[r] + a];
+        mp_seed_pos t; t.pos = ~0ull; t.paired_seedLength = 0xffffffffu; t.strand_readID = 0x7fffffffu; o[k++] = t;
+        for (uint32_t r = mate; r < nReads; r += 2) for (uint32_t a = 0; a < nn[r]; ++a) o[k++] = sp[hs[r] + np[r] + a];
+        t.strand_readID = 0xffffffffu; o[k++] = t;
+        if (mate == 0) { *readPos = o; *nReadPos = tot; } else { *matePos = o; *nMatePos = tot; }
+    }
+    return 0;
+}

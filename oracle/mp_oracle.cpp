@@ -133,6 +133,8 @@ extern "C" void orc_lkt(const OrcIndex *ix, uint32_t key, uint64_t *l, uint64_t 
     *r = ix->lkt[key];
 }
 extern "C" uint32_t orc_text_base(const OrcIndex *ix, uint64_t pos) { return (ix->pac[pos >> 2] >> ((3 - (pos & 3)) << 1)) & 3; }
+extern "C" void orc_text_window(const OrcIndex *ix, uint64_t start, uint32_t len, uint8_t *out)
+{ for (uint32_t i = 0; i < len; ++i) out[i] = (uint8_t)orc_text_base(ix, start + i); }
 extern "C" void orc_occ_many(const OrcIndex *ix, int n, const uint64_t *idx, const uint32_t *c, uint64_t *out)
 { for (int i = 0; i < n; ++i) out[i] = orc_occ(ix, idx[i], c[i]); }
 extern "C" void orc_sa_many(const OrcIndex *ix, int n, const uint64_t *idx, uint64_t *out)

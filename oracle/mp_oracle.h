@@ -47,6 +47,7 @@ uint64_t  orc_occ(const OrcIndex *, uint64_t idx, uint32_t c);          // BWTOc
 uint64_t  orc_sa(const OrcIndex *, uint64_t saIndex);                   // BWTSaValue,  BWT.c:968-998
 void      orc_lkt(const OrcIndex *, uint32_t key, uint64_t *l, uint64_t *r); // DV-DPfunctions.cpp:2240-2241
 uint32_t  orc_text_base(const OrcIndex *, uint64_t pos);                // .pac symbol, TextConverter.c:427-479
+void      orc_text_window(const OrcIndex *, uint64_t start, uint32_t len, uint8_t *out);
 void      orc_occ_many(const OrcIndex *, int n, const uint64_t *idx, const uint32_t *c, uint64_t *out);
 void      orc_sa_many(const OrcIndex *, int n, const uint64_t *idx, uint64_t *out);
 // work counters accumulated by the calls below: occ, onspot-occ, sa, lkt

@@ -57,6 +57,7 @@ def lib():
         L.orc_text_base.restype = C.c_uint32
         L.orc_text_base.argtypes = [C.c_void_p, C.c_uint64]
         L.orc_counters.argtypes = [C.c_void_p, C.c_int]
+        L.orc_text_window.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
         L.orc_mmp.restype = C.c_int
         L.orc_mmp.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_seed_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
@@ -98,6 +99,11 @@ class Index:
         l, r = C.c_uint64(), C.c_uint64()
         self.L.orc_lkt(self.h, int(key), C.byref(l), C.byref(r))
         return l.value, r.value
+
+    def text(self, start, length):
+        out = np.empty(length, dtype=np.uint8)
+        self.L.orc_text_window(self.h, int(start), int(length), ptr(out))
+        return out
 
     def counters(self, reset=False):
         out = np.zeros(4, dtype=np.uint64)
@@ -319,3 +325,136 @@ def read_fastq_codes(path, max_len=None, trunc=None):
     for i, s in enumerate(seqs):
         out[i, :len(s)] = lut[np.frombuffer(s, dtype=np.uint8)]
     return out, lens
+
+
+# ------------------------------------------------------------------ deep-DP stage (S1) restatement
+def margin(read_len):
+    """DP2_MARGIN (DV-DPfunctions.cpp:1760)."""
+    return 30 if read_len > 100 else 25
+
+
+def encode_cigar(pattern, gap_open=-3, gap_ext=-1):
+    """CigarStringEncoder (DV-DPfunctions.h:344-427) fed as in DP2CPUAlgnThread
+    (DV-DPfunctions.cpp:3447-3462).  -> (cigar bytes, counts dict, gapPenalty)"""
+    runs = []                      # merged (type, cnt) in pattern (end -> start) order
+    last_type = ord("N")
+    i = 0
+    while i < len(pattern):
+        ch = pattern[i]
+        if ch == ord("V"):
+            t, c = last_type, pattern[i + 1] - 1
+            i += 2
+        else:
+            t, c = ch, 1
+            last_type = ch
+            i += 1
+        if runs and runs[-1][0] == t:
+            runs[-1][1] += c
+        else:
+            runs.append([t, c])
+    out = b""
+    counts = {}
+    gap = 0
+    for t, c in reversed(runs):
+        if c > 0:
+            out += b"%d%c" % (c, t)
+            counts[chr(t)] = counts.get(chr(t), 0) + c
+            if chr(t) in "ID":
+                gap += gap_open + (c - 1) * gap_ext
+    return out, counts, gap
+
+
+def c_div(a, b):
+    """C integer division (truncation toward zero)."""
+    q = abs(a) // abs(b)
+    return q if (a >= 0) == (b >= 0) else -q
+
+
+def read_for_strand(read, strand):
+    return read if strand == 1 else (3 - read[::-1]).astype(np.uint8)
+
+
+def deep_dp(ix, reads, lens, cands, insert_low, insert_high, input_max_read_length,
+            clip_l=130, clip_r=130, mm=-2, gap_open=-3):
+    """PairEndAlgnBatch::packLeft/packRight + DP2CPUAlgnThread result assembly
+    (DV-DPfunctions.cpp:2857-3007, 3391-3540) for StrandArrangement +/-; then per pair
+    OutputBuffer::ready (DV-DPfunctions.h:198-243).  -> list of result dicts grouped by pair."""
+    n = ix.n
+    max_read = (input_max_read_length // 4 + 1) * 4
+    max_dna = max_read + 2 * margin(input_max_read_length) + 8
+    out = []
+    cells = 0
+    for cd in cands:
+        rid_l = int(cd["readIDLeft"])
+        rl = int(lens[rid_l])
+        m = margin(rl)
+        start_l = (int(cd["pos0"]) - m) & 0xFFFFFFFFFFFFFFFF
+        if start_l >= n:
+            start_l = 0
+        dl = rl + 2 * m
+        if start_l + dl > n:
+            dl = n - start_l
+        cut_l = dp_cutoff(rl)
+        sL = dp(ix.text(start_l, dl), read_for_strand(reads[rid_l, :rl], 1), clip_l, clip_r, mm, gap_open, cut_l)
+        cells += dl * rl
+        if sL[0] < cut_l:
+            continue
+        rid_r = rid_l ^ 1
+        rr = int(lens[rid_r])
+        m = margin(rr)
+        start_r = (int(cd["pos1"]) - m) & 0xFFFFFFFFFFFFFFFF
+        if start_r >= n:
+            start_r = 0
+        dr = rr + 2 * m
+        if start_r + dr > n:
+            dr = n - start_r
+        hit_left = start_l + sL[1]
+        bounded = (hit_left + insert_high - start_r) & 0xFFFFFFFFFFFFFFFF
+        if bounded < dr:
+            dr = bounded
+        cut_r = dp_cutoff(rr)
+        sR = dp(ix.text(start_r, dr), read_for_strand(reads[rid_r, :rr], 2), clip_r, clip_l, mm, gap_open, cut_r)
+        cells += dr * rr
+        if sR[0] < cut_r:
+            continue
+        side = []
+        for (sc, hl, cnt, pat), start, dlen in ((sL, start_l, dl), (sR, start_r, dr)):
+            cig, counts, gap = encode_cigar(pat, gap_open, -1)
+            L = rr - counts.get("I", 0) - counts.get("S", 0)          # batch->lengths[i] is the right read's
+            nmis = c_div(L * 1 + gap - sc, 1 - mm)
+            side.append(dict(pos=start + hl, score=sc, cigar=cig, count=cnt, start=start, dlen=dlen,
+                             editdist=counts.get("I", 0) + counts.get("D", 0) + nmis,
+                             dis=counts.get("D", 0) - counts.get("I", 0) - counts.get("S", 0)))
+        read_side = rid_l & 1
+        a, b = side[read_side], side[1 - read_side]
+        ins = (abs(b["pos"] - a["pos"]) + rr + side[1]["dis"]) & 0xFFFFFFFF
+        if ins >= 1 << 31:
+            ins -= 1 << 32
+        right_anchor = hit_left + insert_low - start_r
+        la = [max_dna, max_dna]
+        ra = [0, right_anchor if right_anchor > 0 else 0]
+        out.append(dict(readID=rid_l - read_side, insertSize=ins,
+                        algnmt_1=a["pos"], algnmt_2=b["pos"], score_1=a["score"], score_2=b["score"],
+                        editdist_1=a["editdist"], editdist_2=b["editdist"], cigar_1=a["cigar"], cigar_2=b["cigar"],
+                        num_sameScore_1=a["count"], num_sameScore_2=b["count"],
+                        strand_1=1 if read_side == 0 else 2, strand_2=2 if read_side == 0 else 1,
+                        startPos_1=a["start"] & 0xFFFFFFFF, startPos_2=b["start"],
+                        refDpLength_1=a["dlen"], refDpLength_2=b["dlen"],
+                        peLeftAnchor_1=la[read_side], peLeftAnchor_2=la[1 - read_side],
+                        peRightAnchor_1=ra[read_side], peRightAnchor_2=ra[1 - read_side]))
+    # per pair: sort by (algnmt_1, algnmt_2, score_1, score_2), drop exact duplicates
+    res = []
+    i = 0
+    while i < len(out):
+        j = i
+        while j < len(out) and out[j]["readID"] == out[i]["readID"]:
+            j += 1
+        grp = sorted(out[i:j], key=lambda r: (r["algnmt_1"], r["algnmt_2"], r["score_1"], r["score_2"]))
+        keep = [grp[0]]
+        for r in grp[1:]:
+            k0 = (keep[-1]["algnmt_1"], keep[-1]["algnmt_2"], keep[-1]["score_1"], keep[-1]["score_2"])
+            if k0 < (r["algnmt_1"], r["algnmt_2"], r["score_1"], r["score_2"]):
+                keep.append(r)
+        res.extend(keep)
+        i = j
+    return res, cells

@@ -1,0 +1,82 @@
+import os
+import shutil
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def have_ref():
+    return os.path.exists(os.path.join(REF_DIR, "soap4_dump")) and os.path.exists(os.path.join(REF_DIR, "2bwt-builder"))
+
+
+needs_ref = pytest.mark.skipif(not have_ref(), reason="oracle/_ref (compiled reference) not built")
+
+
+def run_ref_soap4(workdir, index_prefix, fq1, fq2, out_name, max_len_opt, dump=True, ini="soap4.ini", threads=2, extra=()):
+    """Runs the reference binary (instrumented variant) and returns (stdout_path, dump_dir)."""
+    dump_dir = os.path.join(workdir, out_name + ".dump")
+    if os.path.isdir(dump_dir):
+        shutil.rmtree(dump_dir)
+    os.makedirs(dump_dir)
+    env = dict(os.environ)
+    if dump:
+        env["MPH_DUMP_DIR"] = dump_dir
+    out_fq = os.path.join(workdir, out_name + ".fq")
+    cmd = [os.path.join(REF_DIR, "soap4_dump" if dump else "soap4"), "pair", index_prefix, fq1, fq2, "-o", os.path.join(workdir, out_name),
+           "-C", os.path.join(REF_DIR, ini), "-L", str(max_len_opt), "-T", str(threads), "-u", "750", "-F", "-nc"] + list(extra)
+    with open(out_fq, "wb") as fo, open(os.path.join(workdir, out_name + ".err"), "wb") as fe:
+        subprocess.check_call(cmd, stdout=fo, stderr=fe, env=env, cwd=workdir)
+    return out_fq, dump_dir
+
+
+@pytest.fixture(scope="session")
+def workdir(tmp_path_factory):
+    return str(tmp_path_factory.mktemp("mp"))
+
+
+@pytest.fixture(scope="session")
+def small_ref(workdir):
+    """300 kbp, 6 sequences, with a few planted repeats; index built by the reference's 2bwt-builder."""
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    from tools import synth
+    fa = os.path.join(workdir, "ref.fa")
+    seq, bounds = synth.make_ref(300000, 6, seed=42, repeat_frac=0.05)
+    synth.write_fasta(fa, seq, bounds)
+    shutil.copy(os.path.join(REF_DIR, "2bwt-builder.ini"), os.path.join(workdir, "2bwt-builder.ini"))
+    subprocess.check_call([os.path.join(REF_DIR, "2bwt-builder"), fa], cwd=workdir, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return dict(fasta=fa, prefix=fa + ".index", seq=seq, bounds=bounds)
+
+
+def make_reads(workdir, small_ref, name, pairs, rlen, seed, **kw):
+    from tools import synth
+    r1, r2 = synth.make_pairs(small_ref["seq"], small_ref["bounds"], pairs, rlen, seed, **kw)
+    p = os.path.join(workdir, name)
+    synth.write_fastq(p + "_1.fq", r1, 1)
+    synth.write_fastq(p + "_2.fq", r2, 2)
+    return p + "_1.fq", p + "_2.fq"
+
+
+def load_pairs(fq1, fq2, trunc):
+    from oracle import pyoracle as po
+    a, la = po.read_fastq_codes(fq1, trunc=trunc)
+    b, lb = po.read_fastq_codes(fq2, trunc=trunc)
+    n = len(la)
+    w = max(a.shape[1], b.shape[1])
+    reads = np.zeros((2 * n, w), dtype=np.uint8)
+    reads[0::2, :a.shape[1]] = a
+    reads[1::2, :b.shape[1]] = b
+    lens = np.zeros(2 * n, dtype=np.uint32)
+    lens[0::2] = la
+    lens[1::2] = lb
+    return reads, lens

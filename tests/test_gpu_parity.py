@@ -1,0 +1,107 @@
+"""GPU suite: the CUDA path, called through the C-ABI (include/megapath_b200.h), against the
+CPU oracle on the same seeded inputs.  Bit-exact: everything on this path is integer work."""
+import numpy as np
+import pytest
+
+from conftest import make_reads, load_pairs
+from oracle import pyoracle as po
+from test_oracle_vs_ref import random_dp_tasks, DP_SHAPES, ref_detected_len
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx(small_ref):
+    import megapath_b200 as mp
+    c = mp.Context(0)
+    c.index_load(small_ref["prefix"])
+    yield c
+    c.close()
+
+
+def test_gpu_index_primitives(ctx, small_ref):
+    ix = po.Index(small_ref["prefix"])
+    info = ctx.index_info()
+    assert info["textLength"] == ix.n and info["inverseSa0"] == ix.inverse_sa0
+    rng = np.random.default_rng(3)
+    idx = np.concatenate([rng.integers(0, ix.n + 2, size=50000), [0, 1, ix.inverse_sa0, ix.inverse_sa0 + 1, ix.n, ix.n + 1],
+                          np.arange(0, 2000)]).astype(np.uint64)
+    c = rng.integers(0, 4, size=len(idx)).astype(np.uint32)
+    assert (ctx.occ(idx, c) == ix.occ(idx, c)).all()
+    sidx = np.concatenate([rng.integers(0, ix.n + 1, size=20000), [0, ix.inverse_sa0, ix.n]]).astype(np.uint64)
+    assert (ctx.sa(sidx) == ix.sa(sidx)).all()
+    keys = np.concatenate([rng.integers(0, 4 ** 13, size=5000), [0, 1, 4 ** 13 - 1]]).astype(np.uint32)
+    l, r = ctx.lkt(keys)
+    for k, a, b in zip(keys[-400:], l[-400:], r[-400:]):
+        assert ix.lkt(k) == (a, b)
+
+
+@pytest.mark.parametrize("maxdna,maxread,fixed,clips", DP_SHAPES)
+def test_gpu_dp_batch(ctx, maxdna, maxread, fixed, clips):
+    import megapath_b200 as mp
+    rng = np.random.default_rng(maxdna * 11 + maxread + clips[1])
+    n = 300
+    refs, dl, reads, rl = random_dp_tasks(rng, n, maxdna, maxread, fixed)
+    cut = np.array([po.dp_cutoff(int(x)) for x in rl], dtype=np.int32)
+    pd = mp.pack_dp_interleaved(refs, dl, maxdna)
+    pr = mp.pack_dp_interleaved(reads, rl, maxread)
+    sc, hl, mc, pats = ctx.dp_batch(pd, dl, maxdna, pr, rl, maxread, cut, clips[0], clips[1])
+    nhit = 0
+    for t in range(n):
+        want = po.dp(refs[t, :dl[t]], reads[t, :rl[t]], clips[0], clips[1], -2, -3, int(cut[t]))
+        got = (int(sc[t]), int(hl[t]), int(mc[t]), po.pattern_bytes(pats[t]) if sc[t] >= cut[t] else b"")
+        assert got == want, (t, got, want)
+        nhit += want[0] >= cut[t]
+    assert nhit > n // 4
+
+
+READ_SETS = [
+    ("clean", 150, 151, dict(model="clean")),
+    ("div", 100, 101, dict(model="divergent", one_random=0.05, unalignable=0.02)),
+    ("var", 150, 151, dict(model="clean", varlen=True, n_rate=0.002)),
+    ("long", 250, 251, dict(model="divergent")),
+]
+
+
+@pytest.mark.parametrize("name,rlen,lopt,kw", READ_SETS)
+def test_gpu_seed_pair_and_deep_dp(ctx, workdir, small_ref, name, rlen, lopt, kw):
+    import megapath_b200 as mp
+    fq1, fq2 = make_reads(workdir, small_ref, "g_" + name, 1200 if name != "long" else 400, rlen, seed=21, **kw)
+    reads, lens = load_pairs(fq1, fq2, trunc=lopt - 1)
+    ix = po.Index(small_ref["prefix"])
+    rp, mpos = ix.seed_pairs(reads, lens, po.mmp_params())
+    insert_low = max(1, ref_detected_len(lens[0::2]), ref_detected_len(lens[1::2]))
+    cands = po.pair_candidates(rp, mpos, lens, insert_low, 750)
+    q, wpq = mp.pack_queries(reads, lens, lopt)
+    ctx.batch_upload(q, lens, wpq)
+    P = mp.default_params(insert_low=insert_low, insert_high=750, max_read_length=lopt)
+    ctx.seed_pairs(P)
+    grp, gmp = ctx.download_seedpos()
+    assert grp.tobytes() == rp.tobytes() and gmp.tobytes() == mpos.tobytes()
+    gc = ctx.download_candidates()
+    assert gc.tobytes() == cands.tobytes()
+    assert len(gc) > 100
+    # stage S1 through the end-to-end call
+    want, cells = po.deep_dp(ix, reads, lens, cands, insert_low, 750, lopt)
+    res = ctx.align_pairs(P)
+    got = res["pairs"]
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        for f in ("readID", "insertSize", "algnmt_1", "algnmt_2", "score_1", "score_2", "editdist_1", "editdist_2",
+                  "num_sameScore_1", "num_sameScore_2", "strand_1", "strand_2", "startPos_1", "startPos_2",
+                  "refDpLength_1", "refDpLength_2", "peLeftAnchor_1", "peLeftAnchor_2", "peRightAnchor_1", "peRightAnchor_2"):
+            assert int(g[f]) == int(w[f]), (f, g, w)
+        assert mp.cigar_at(res["cigars"], int(g["cigar_1"])) == w["cigar_1"]
+        assert mp.cigar_at(res["cigars"], int(g["cigar_2"])) == w["cigar_2"]
+    assert res["dp_cells"] == cells
+    assert res["numDPAlignment"] == len(want)
+
+
+def test_gpu_errors_are_loud(small_ref):
+    import megapath_b200 as mp
+    c = mp.Context(0)
+    with pytest.raises(mp.MegapathError):
+        c.index_load("/nonexistent/prefix")
+    with pytest.raises(mp.MegapathError):
+        c.seed_pairs(mp.default_params())
+    c.close()

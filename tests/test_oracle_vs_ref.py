@@ -1,0 +1,115 @@
+"""CPU suite: pins the oracle restatement (oracle/mp_oracle*.cpp) against the reference itself
+(oracle/_ref: soap4_dump seam dumps, libref_dp.so = the reference's callDP, libref_bwt.so =
+the reference's BWTOccValue / BWTSaValue / LT)."""
+import numpy as np
+import pytest
+
+from conftest import needs_ref, make_reads, load_pairs, run_ref_soap4
+from oracle import pyoracle as po
+
+
+@needs_ref
+def test_index_primitives_match_reference(small_ref):
+    ix = po.Index(small_ref["prefix"])
+    rx = po.RefIndex(small_ref["prefix"])
+    assert ix.n == rx.n == 300000
+    rng = np.random.default_rng(1)
+    idx = np.concatenate([rng.integers(0, ix.n + 2, size=20000), [0, 1, ix.inverse_sa0, ix.inverse_sa0 + 1, ix.n, ix.n + 1]]).astype(np.uint64)
+    c = rng.integers(0, 4, size=len(idx)).astype(np.uint32)
+    assert (ix.occ(idx, c) == rx.occ(idx, c)).all()
+    sidx = np.concatenate([rng.integers(0, ix.n + 1, size=5000), [0, ix.inverse_sa0, ix.n]]).astype(np.uint64)
+    assert (ix.sa(sidx) == rx.sa(sidx)).all()
+    keys = rng.integers(0, 4 ** 13, size=2000).astype(np.uint32)
+    l, r = rx.lkt(keys)
+    for k, a, b in zip(keys[:300], l, r):
+        assert ix.lkt(k) == (a, b)
+
+
+def random_dp_tasks(rng, n, maxdna, maxread, fixed=False):
+    refs = np.zeros((n, maxdna), np.uint8)
+    reads = np.zeros((n, maxread), np.uint8)
+    dl = np.zeros(n, np.uint32)
+    rl = np.zeros(n, np.uint32)
+    for t in range(n):
+        L = maxread - 2 if fixed else int(rng.integers(30, maxread + 1))
+        alpha = 4 if rng.random() < 0.7 else 2          # low complexity -> many tied maxima
+        rd = rng.integers(0, alpha, size=L).astype(np.uint8)
+        body = list(rd)
+        if rng.random() < 0.5:                           # forces soft clipping at one end
+            k = int(rng.integers(1, 40))
+            body = body[k:] if rng.random() < 0.5 else body[:-k]
+        out = []
+        for ch in body:
+            r = rng.random()
+            if r < 0.03:
+                continue
+            if r < 0.06:
+                out.append(int(rng.integers(0, alpha)))
+            if rng.random() < 0.06:
+                ch = int(rng.integers(0, alpha))
+            out.append(int(ch))
+        w = list(rng.integers(0, alpha, size=int(rng.integers(0, 40)))) + out + list(rng.integers(0, alpha, size=int(rng.integers(0, 40))))
+        if rng.random() < 0.1:
+            w = list(rng.integers(0, 4, size=int(rng.integers(0, maxdna))))
+        w = w[:maxdna]
+        refs[t, :len(w)] = w
+        dl[t] = len(w)
+        reads[t, :L] = rd
+        rl[t] = L
+    return refs, dl, reads, rl
+
+
+DP_SHAPES = [(220, 152, False, (130, 130)), (220, 152, True, (130, 130)), (160, 104, False, (130, 130)),
+             (320, 252, False, (130, 130)), (752, 152, False, (130, 130)), (220, 152, False, (10, 20)), (220, 152, False, (0, 0))]
+
+
+@needs_ref
+@pytest.mark.parametrize("maxdna,maxread,fixed,clips", DP_SHAPES)
+def test_dp_matches_reference_callDP(maxdna, maxread, fixed, clips):
+    rng = np.random.default_rng(maxdna * 7 + maxread + clips[0])
+    n = 192
+    refs, dl, reads, rl = random_dp_tasks(rng, n, maxdna, maxread, fixed)
+    sc, hl, mc, pats = po.ref_dp(refs, dl, reads, rl, maxdna, maxread, clips[0], clips[1])
+    n_hit = n_tie = 0
+    for t in range(n):
+        co = po.dp_cutoff(int(rl[t]))
+        got = po.dp(refs[t, :dl[t]], reads[t, :rl[t]], clips[0], clips[1], -2, -3, co)
+        want = (int(sc[t]), int(hl[t]), int(mc[t]), po.pattern_bytes(pats[t]) if sc[t] >= co else b"")
+        assert got == want, (t, got, want)
+        n_hit += sc[t] >= co
+        n_tie += mc[t] > 1
+    assert n_hit > n // 4
+
+
+@needs_ref
+@pytest.mark.parametrize("name,rlen,lopt,kw", [
+    ("clean", 150, 151, dict(model="clean")),
+    ("div", 100, 101, dict(model="divergent", one_random=0.05, unalignable=0.02)),
+    ("var", 150, 151, dict(model="clean", varlen=True, n_rate=0.002)),
+])
+def test_seeds_candidates_dp_match_reference_dumps(workdir, small_ref, name, rlen, lopt, kw):
+    fq1, fq2 = make_reads(workdir, small_ref, name, 1500, rlen, seed=11, **kw)
+    _, dump = run_ref_soap4(workdir, small_ref["prefix"], fq1, fq2, "ref_" + name, lopt)
+    reads, lens = load_pairs(fq1, fq2, trunc=lopt - 1)
+    ix = po.Index(small_ref["prefix"])
+    rp, mp = ix.seed_pairs(reads, lens, po.mmp_params())
+    (drp, dmp), = po.read_seedpos_dump(dump + "/seedpos.bin")
+    assert rp.tobytes() == drp.tobytes() and mp.tobytes() == dmp.tobytes()
+    # first-batch clamp of insert_low (SOAP4.cpp:465-474): default -v 1 -> max(1, detected lengths)
+    insert_low = max(1, ref_detected_len(lens[0::2]), ref_detected_len(lens[1::2]))
+    cands = po.pair_candidates(rp, mp, lens, insert_low, 750)
+    dc, = po.read_cand_dump(dump + "/cand.bin")
+    assert cands.tobytes() == dc.tobytes()
+    assert len(cands) > 500
+    ntask = 0
+    for rec in po.read_dp_dump(dump + "/dp.bin"):
+        for (ref, rd, co, sc, hl, mc, pat) in rec["tasks"][:400]:
+            got = po.dp(ref, rd, rec["clip_lt"], rec["clip_rt"], rec["mismatch"], rec["gap_open"], co)
+            assert got == (sc, hl, mc, pat)
+            ntask += 1
+    assert ntask > 500
+
+
+def ref_detected_len(lens):
+    """GetReadLength (QueryParser.cpp:2253-2277): maximum over the first 999999 sampled reads."""
+    return int(lens[:999999].max())
