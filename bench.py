@@ -1,0 +1,431 @@
+#!/usr/bin/env python3
+"""bench.py -- read pairs aligned/sec of the soap4 alignment hot path on B200 (BASELINE.json metric).
+
+One "step" = one pass of the whole hot path (MMP seeding -> SA resolution -> pairing -> deep DP with
+traceback -> single-end DP -> mate rescue -> per-pair reduction) over one batch of synthetic read pairs,
+through the C-ABI of libmegapath_b200.so (include/megapath_b200.h).
+
+  value  : pairs/s with the batch already resident in HBM (mp_batch_upload outside the timed region),
+           timed with CUDA events on the library's launching stream (mp_results.ms_total), max over ranks
+  e2e    : pairs/s through the same C-ABI with HOST buffers: pinned-host -> HBM upload of the packed reads
+           and the host-resident result arrays inside the timed region (wall clock between device syncs)
+  roofline : the seeding kernel (k_mmp): algorithmic bytes = 64 B per occ evaluation + 16 B per LKT jump
+            / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline : the reference's own soap4 (oracle/_ref/soap4, compiled from /root/reference by
+           oracle/Makefile.ref) on a bounded sample of the same workload, all host cores
+
+`--impl reference` times only that CPU arm.  Multi-GPU: one process per GPU (torchrun), index replicated,
+disjoint read batches per rank, no collective on the data path ("weak" scaling).
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+READ_LEN = 150
+MAX_READ_LEN_OPT = 151          # soap4 -L 151: reads are truncated to L-1 = 150 (QueryParser.cpp:188)
+INSERT_LO, INSERT_HI = 250, 500
+INSERT_HIGH_OPT = 750           # soap4 -u 750
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-mbp", type=float, default=float(os.environ.get("MP_BENCH_REF_MBP", "3100")))
+    ap.add_argument("--pairs-per-step", type=int, default=int(os.environ.get("MP_BENCH_PAIRS", str(1 << 20))))
+    ap.add_argument("--cpu-sample-pairs", type=int, default=int(os.environ.get("MP_BENCH_CPU_PAIRS", "200000")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workdir", default=os.environ.get("MP_BENCH_DIR", "/tmp/mpbench"))
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic workload (SURVEY.md 8d cfg2 model: uniform i.i.d. ACGT reference in 24 sequences;
+# FR pairs, insert U[250,500), substitutions per read from {0,0,0,1,1,2}, 1% unalignable pairs,
+# 1% pairs with one random mate)
+# ------------------------------------------------------------------------------------------------
+def ref_bounds(n, nseq, seed):
+    rng = np.random.default_rng(seed)
+    cuts = np.sort(rng.choice(np.arange(1000, n - 1000), size=nseq - 1, replace=False))
+    return np.concatenate([[0], cuts, [n]]).astype(np.int64)
+
+
+def gen_ref_codes(n, seed, device):
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    out = torch.empty(n, dtype=torch.uint8, device=device)
+    CH = 1 << 28
+    for o in range(0, n, CH):
+        m = min(CH, n - o)
+        out[o:o + m] = torch.randint(0, 4, (m,), dtype=torch.uint8, device=device, generator=g)
+    return out
+
+
+def gen_batch(ref_codes, bounds_t, npairs, seed, unalignable=0.01, one_random=0.01):
+    """-> (codes (2*npairs, READ_LEN) uint8 on device, mate1 = even rows)."""
+    import torch
+    dev = ref_codes.device
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    L = READ_LEN
+    nseq = bounds_t.numel() - 1
+    isz = torch.randint(INSERT_LO, INSERT_HI, (npairs,), device=dev, generator=g)
+    sid = torch.randint(0, nseq, (npairs,), device=dev, generator=g)
+    lo = bounds_t[sid]
+    hi = torch.maximum(bounds_t[sid + 1] - isz, lo + 1)
+    start = lo + (torch.rand(npairs, device=dev, generator=g, dtype=torch.float64) * (hi - lo).double()).long()
+    start = torch.clamp(start, 0, ref_codes.numel() - INSERT_HI - 1)
+    ar = torch.arange(L, device=dev)
+    out = torch.empty((2 * npairs, L), dtype=torch.uint8, device=dev)
+    CH = 1 << 18
+    for o in range(0, npairs, CH):
+        s = start[o:o + CH]
+        z = isz[o:o + CH]
+        a = ref_codes[s[:, None] + ar[None, :]]
+        b = 3 - ref_codes[(s + z)[:, None] - 1 - ar[None, :]]
+        out[2 * o:2 * (o + len(s)):2] = a
+        out[2 * o + 1:2 * (o + len(s)):2] = b
+    nreads = 2 * npairs
+    nsub = torch.tensor([0, 0, 0, 1, 1, 2], device=dev)[torch.randint(0, 6, (nreads,), device=dev, generator=g)]
+    rows = torch.arange(nreads, device=dev)
+    for k in (1, 2):
+        sel = rows[nsub >= k]
+        cols = torch.randint(0, L, (sel.numel(),), device=dev, generator=g)
+        delta = torch.randint(1, 4, (sel.numel(),), device=dev, generator=g).to(torch.uint8)
+        out[sel, cols] = (out[sel, cols] + delta) & 3
+    u = torch.rand(npairs, device=dev, generator=g)
+    ua = torch.nonzero(u < unalignable).flatten()
+    if ua.numel():
+        out[2 * ua] = torch.randint(0, 4, (ua.numel(), L), dtype=torch.uint8, device=dev, generator=g)
+        out[2 * ua + 1] = torch.randint(0, 4, (ua.numel(), L), dtype=torch.uint8, device=dev, generator=g)
+    one = torch.nonzero((u >= unalignable) & (u < unalignable + one_random)).flatten()
+    if one.numel():
+        out[2 * one + 1] = torch.randint(0, 4, (one.numel(), L), dtype=torch.uint8, device=dev, generator=g)
+    return out
+
+
+def pack_queries_torch(codes, max_len_opt):
+    """appendToQueryArrays layout (QueryParser.cpp:184-203) built with torch on the device:
+    2-bit, 16 bases per word LSB-first, 32-read interleaved.  -> pinned host int32 tensor, wpq."""
+    import torch
+    n, L = codes.shape
+    wpq = (max_len_opt + 15) // 16
+    npad = (n + 31) // 32 * 32
+    c = torch.zeros((npad, wpq * 16), dtype=torch.int64, device=codes.device)
+    c[:n, :L] = codes
+    sh = (2 * (torch.arange(wpq * 16, device=codes.device) % 16))
+    w = (c << sh[None, :]).view(npad, wpq, 16).sum(dim=2)
+    w = w.view(npad // 32, 32, wpq).permute(0, 2, 1).contiguous().view(-1)
+    w32 = (w & 0xFFFFFFFF).to(torch.int64)
+    w32 = torch.where(w32 >= (1 << 31), w32 - (1 << 32), w32).to(torch.int32)
+    host = torch.empty(w32.shape, dtype=torch.int32, pin_memory=True)
+    host.copy_(w32)
+    return host, wpq
+
+
+def write_fastq_sample(path_prefix, codes_np):
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    qual = b"I" * codes_np.shape[1]
+    for mate in (0, 1):
+        with open("%s_%d.fq" % (path_prefix, mate + 1), "wb") as f:
+            rows = lut[codes_np[mate::2]]
+            for i in range(rows.shape[0]):
+                f.write(b"@p%d/%d\n" % (i, mate + 1) + rows[i].tobytes() + b"\n+\n" + qual + b"\n")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# workload cache: index files (reference format, so the reference binary runs on the same index)
+# ------------------------------------------------------------------------------------------------
+def workload_dir(args):
+    n = int(args.ref_mbp * 1e6)
+    return os.path.join(args.workdir, "ref%d" % n), n
+
+
+def ensure_index(args, ctx, device, rank, world):
+    """Builds the synthetic reference + FM-index once per box (rank 0), in HBM, with the library's own GPU
+    builder (mp_index_build), and saves it in the reference's on-disk format; other ranks load the files."""
+    import torch
+    d, n = workload_dir(args)
+    prefix = os.path.join(d, "ref.index")
+    ready = os.path.join(d, "READY")
+    nseq = 24
+    bounds = ref_bounds(n, nseq, 42)
+    ref_codes = gen_ref_codes(n, 42, device)
+    t0 = time.time()
+    if rank == 0 and not os.path.exists(ready):
+        os.makedirs(d, exist_ok=True)
+        ctx.index_build_codes(ref_codes, bounds, prefix)
+        open(ready, "w").write("ok\n")
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    if not ctx.has_index():
+        ctx.index_load(prefix)
+    return prefix, ref_codes, torch.from_numpy(bounds).to(device), time.time() - t0
+
+
+def run_reference_soap4(prefix, fq_prefix, out_prefix, threads):
+    """-> (align_seconds, wall_seconds, stderr text); align = the reference's own
+    'Overall alignment time (excl. read loading)' (SOAP4.cpp:613)."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    exe = os.path.join(ref_dir, "soap4")
+    if not os.path.exists(exe):
+        raise RuntimeError("oracle/_ref/soap4 is not built (oracle/Makefile.ref)")
+    cmd = [exe, "pair", prefix, fq_prefix + "_1.fq", fq_prefix + "_2.fq", "-o", out_prefix, "-C", os.path.join(ref_dir, "soap4.ini"),
+           "-L", str(MAX_READ_LEN_OPT), "-T", str(threads), "-u", str(INSERT_HIGH_OPT), "-F", "-nc"]
+    t0 = time.time()
+    with open(out_prefix + ".stdout.fq", "wb") as fo:
+        p = subprocess.run(cmd, stdout=fo, stderr=subprocess.PIPE, cwd=os.path.dirname(out_prefix))
+    wall = time.time() - t0
+    err = p.stderr.decode(errors="replace")
+    if p.returncode != 0:
+        raise RuntimeError("reference soap4 failed (%d): %s" % (p.returncode, err[-400:]))
+    m = re.search(r"Overall alignment time \(excl\. read loading\)\s*:\s*([0-9.]+)", err)
+    if not m:
+        raise RuntimeError("could not parse the reference's timing line")
+    try:
+        os.remove(out_prefix + ".stdout.fq")
+    except OSError:
+        pass
+    return float(m.group(1)), wall, err
+
+
+def measured_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def workload_name(args):
+    n = int(args.ref_mbp * 1e6)
+    return "%d x %d-pair batches of synthetic 150bp pairs (-L 151 -u 750 soap4.ini) vs %.0f Mbp synthetic reference" % (
+        1, args.pairs_per_step, n / 1e6)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    ncores = os.cpu_count() or 1
+    cfg = {"workload": "cfg2: 150bp pairs vs %.0f Mbp synthetic reference (24 seqs), %d pairs per step, soap4.ini -L 151 -u 750; "
+                       "1%% unalignable pairs, 1%% one-mate-random" % (args.ref_mbp, args.pairs_per_step),
+           "pairs_per_step_per_gpu": args.pairs_per_step, "ref_mbp": args.ref_mbp,
+           "l2": "inputs larger than L2: index %s + a distinct read batch every step",
+           "parallelism": "replicated index, disjoint read batches per GPU, no data-path collective"}
+
+    if args.impl == "reference" and rank != 0:
+        return 0
+
+    import torch
+    import megapath_b200 as mp
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1 and args.impl == "ours":
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+
+    ctx = mp.Context(local)
+    prefix, ref_codes, bounds_t, t_index = ensure_index(args, ctx, device, rank, world if args.impl == "ours" else 1)
+    info = ctx.index_info()
+    cfg["l2"] = "inputs larger than L2: %.2f GB HBM index gathered at random + a distinct read batch every step" % (info["hbmBytes"] / 1e9)
+    d, _ = workload_dir(args)
+
+    sample_codes = None
+    if rank == 0 and (args.impl == "reference" or (world == 1 and not args.no_cpu_baseline)):
+        sample_codes = gen_batch(ref_codes, bounds_t, args.cpu_sample_pairs, 7_000_003).cpu().numpy()
+
+    def cpu_leg(npairs, tag):
+        fqp = os.path.join(d, "sample_%s_%d" % (tag, npairs))
+        if not os.path.exists(fqp + "_2.fq"):
+            write_fastq_sample(fqp, sample_codes[:2 * npairs])
+        align_s, wall_s, _ = run_reference_soap4(prefix, fqp, os.path.join(d, "refout_" + tag), ncores)
+        return npairs / align_s, align_s, wall_s
+
+    if args.impl == "reference":
+        npairs = args.cpu_sample_pairs
+        vals = []
+        for i in range(args.warmup + args.steps):
+            v, a, w = cpu_leg(npairs, "ref")
+            if i >= args.warmup:
+                vals.append((v, a))
+        tot_align = sum(a for _, a in vals)
+        value = npairs * len(vals) / tot_align
+        cb = {"value": value, "unit": "pairs/s", "cores": ncores, "kind": "reference",
+              "sample": "%d pairs per step of the same workload, oracle/_ref/soap4 -T %d, its own 'Overall alignment time (excl. read loading)'" % (npairs, ncores)}
+        print(json.dumps({"impl": "reference", "metric": "read pairs aligned/sec", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_align / max(1, len(vals)),
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16/u8", "data": "synthetic",
+                          "config": cfg, "cpu_baseline": cb,
+                          "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    # ---------------- our arm ----------------
+    P = mp.default_params(insert_low=READ_LEN, insert_high=INSERT_HIGH_OPT, max_read_length=MAX_READ_LEN_OPT)
+    nb = min(args.warmup + args.steps, 6)
+    batches = []
+    lens = np.full(2 * args.pairs_per_step, READ_LEN, dtype=np.uint32)
+    for b in range(nb):
+        codes = gen_batch(ref_codes, bounds_t, args.pairs_per_step, 1000 + 97 * rank + b)
+        host, wpq = pack_queries_torch(codes, MAX_READ_LEN_OPT)
+        batches.append(host)
+        del codes
+    del ref_codes
+    torch.cuda.empty_cache()
+    h2d = batches[0].numel() * 4 + lens.nbytes
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i, timed_upload):
+        q = batches[i % nb]
+        ctx.batch_upload_ptr(q.data_ptr(), lens, wpq)
+        return ctx.align_pairs_summary(P)
+
+    for i in range(args.warmup):
+        step(i, False)
+    sampler = ClockSampler(local)
+    sampler.start()
+    # ---- loop A: device-resident (value) ----
+    barrier()
+    l0 = mp.launch_count()
+    acc = {}
+    dev_ms = 0.0
+    for i in range(args.steps):
+        s = step(args.warmup + i, False)
+        dev_ms += s["ms_total"]
+        for k, v in s.items():
+            acc[k] = acc.get(k, 0) + v
+    barrier()
+    launches = mp.launch_count() - l0
+    if os.environ.get("MP_BENCH_VERBOSE"):
+        sys.stderr.write("loop A: %s\n" % json.dumps({k: v / args.steps for k, v in acc.items()}))
+    # ---- loop B: end to end through the C-ABI with host buffers ----
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for i in range(args.steps):
+        q = batches[(args.warmup + i) % nb]
+        ctx.batch_upload_ptr(q.data_ptr(), lens, wpq)
+        s = ctx.align_pairs_summary(P)
+        d2h = s["result_bytes"]
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    tm = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=device)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = float(tm[0]), float(tm[1])
+    total_pairs = args.pairs_per_step * args.steps * world
+    value = total_pairs / (dev_ms_max / 1e3)
+    e2e = total_pairs / (e2e_ms_max / 1e3)
+
+    peak, peak_kind = measured_peak()
+    occ_bytes = 64.0 * acc["n_occ"] + 16.0 * acc["n_lkt"]
+    ach = occ_bytes / (acc["ms_seed"] / 1e3) / 1e9
+    roof = {"kernel": "k_mmp (MMP backward search: occ-block + LKT gathers)", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+            "frac": ach / peak, "traffic": None, "peak_kind": peak_kind,
+            "algorithmic_bytes_per_launch": occ_bytes / args.steps,
+            "ms_per_launch": acc["ms_seed"] / args.steps,
+            "dp_gcups": acc["dp_cells"] / (acc["ms_dp"] / 1e3) / 1e9 if acc["ms_dp"] else None,
+            "sa_lookup_gbs": (64.0 * acc["n_lf"] + 8.0 * acc["n_sa"]) / (acc["ms_sa"] / 1e3) / 1e9 if acc["ms_sa"] else None,
+            "stage_ms_per_step": {k: acc[k] / args.steps for k in ("ms_seed", "ms_sa", "ms_pair", "ms_dp", "ms_total")}}
+    out = {"metric": "read pairs aligned/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16/u8 (integer DP, 2-bit FM-index)",
+           "data": "synthetic", "config": cfg, "clocks": clocks,
+           "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+           "gpu_launches": int(launches), "roofline": roof,
+           "aligned_fraction": acc["pairs_aligned"] / (args.pairs_per_step * args.steps),
+           "index_prepare_s": t_index}
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        try:
+            v, a, w = cpu_leg(args.cpu_sample_pairs, "cpu")
+            out["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": ncores, "kind": "reference",
+                                   "sample": "%d pairs of the same workload (same index files), oracle/_ref/soap4 -T %d, align loop %.1f s, wall %.1f s" % (
+                                       args.cpu_sample_pairs, ncores, a, w)}
+        except Exception as e:  # the baseline is reported, never the target: say why it is missing
+            out["cpu_baseline"] = {"value": None, "unit": "pairs/s", "cores": ncores, "kind": "reference", "sample": "unavailable: %s" % e}
+    if rank == 0:
+        print(json.dumps(out))
+    ctx.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

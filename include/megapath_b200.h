@@ -107,17 +107,22 @@ typedef struct mp_results {
     uint64_t numDPAlignedPair, numDPAlignment;          /* deep DP */
     uint64_t numSingleDPAligned, numSingleDPAlignment;  /* single-end DP */
     uint64_t numRescuedPair, numRescuedAlignment;       /* default DP */
-    /* algorithmic work of this call: occ evaluations (incl. on-spot), SA lookups,
-     * LKT jumps, DP cells (sum of dnaLen*readLen over required tasks), DP tasks */
-    uint64_t n_occ, n_sa, n_lkt, dp_cells, dp_tasks;
+    /* algorithmic work of this call: occ evaluations of the backward search, on-spot
+     * occ evaluations of the SA walks (LF steps), SA lookups, LKT jumps, DP cells (sum of
+     * dnaLen*readLen over required tasks), DP tasks */
+    uint64_t n_occ, n_lf, n_sa, n_lkt, dp_cells, dp_tasks;
     /* device time of the main kernels in this call, milliseconds (CUDA events) */
     float ms_seed, ms_sa, ms_pair, ms_dp, ms_total;
+    /* host wall clock of the whole mp_align_pairs call, milliseconds */
+    float ms_wall, pad_;
 } mp_results;
 
 /* ---- context ---- */
 int  mp_init(int device, mp_context **ctx);
 void mp_destroy(mp_context *ctx);
 const char *mp_last_error(void);
+/* number of this library's own CUDA kernels launched so far in the process (bench.py "gpu_launches") */
+uint64_t mp_launch_count(void);
 
 /* ---- index: replaces INDEXLoad / INDEXFree (IndexHandler.cpp:49-99, 196-249) ----
  * Host reads <prefix>.{bwt,fmv,sa,lkt,pac}; the library owns the HBM copies (re-laid out).
@@ -131,6 +136,9 @@ int  mp_index_build(mp_context *ctx, const uint8_t *text2bit, uint64_t textLengt
 /* writes the resident index back in the reference's file formats (so the reference binary can
  * be timed on the same index) */
 int  mp_index_save(mp_context *ctx, const char *prefix);
+/* .ann/.amb/.tra of a text without ambiguity runs (HSP.c:569-699), host only */
+int  mp_index_save_annotation(const char *prefix, uint64_t textLength, uint32_t numSeq, const char *const *names,
+                              const uint64_t *starts, const uint64_t *lengths);
 
 /* index primitives, for parity tests against BWTOccValue / BWTSaValue / LT (2bwt-lib/BWT.c:597,968) */
 int  mp_occ(mp_context *ctx, const uint64_t *idx, const uint32_t *c, uint64_t *out, uint64_t n);

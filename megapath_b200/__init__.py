@@ -40,10 +40,10 @@ class Results(C.Structure):
                 ("numDPAlignedPair", C.c_uint64), ("numDPAlignment", C.c_uint64),
                 ("numSingleDPAligned", C.c_uint64), ("numSingleDPAlignment", C.c_uint64),
                 ("numRescuedPair", C.c_uint64), ("numRescuedAlignment", C.c_uint64),
-                ("n_occ", C.c_uint64), ("n_sa", C.c_uint64), ("n_lkt", C.c_uint64),
+                ("n_occ", C.c_uint64), ("n_lf", C.c_uint64), ("n_sa", C.c_uint64), ("n_lkt", C.c_uint64),
                 ("dp_cells", C.c_uint64), ("dp_tasks", C.c_uint64),
                 ("ms_seed", C.c_float), ("ms_sa", C.c_float), ("ms_pair", C.c_float),
-                ("ms_dp", C.c_float), ("ms_total", C.c_float)]
+                ("ms_dp", C.c_float), ("ms_total", C.c_float), ("ms_wall", C.c_float), ("pad_", C.c_float)]
 
 
 SEEDPOS = np.dtype([("pos", "<u8"), ("strand_readID", "<u4"), ("paired_seedLength", "<u4")])
@@ -85,6 +85,8 @@ def lib():
         L.mp_index_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mp_index_build.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.mp_index_save.argtypes = [C.c_void_p, C.c_char_p]
+        L.mp_index_save_annotation.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mp_launch_count.restype = C.c_uint64
         L.mp_occ.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.mp_sa.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.mp_lkt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
@@ -101,6 +103,30 @@ def lib():
         L.mp_default_params.argtypes = [C.c_void_p, C.c_int]
         _lib = L
     return _lib
+
+
+def launch_count():
+    """Kernels of libmegapath_b200.so launched so far in this process."""
+    return int(lib().mp_launch_count())
+
+
+def save_annotation(prefix, text_length, names, starts, lengths):
+    """.ann/.amb/.tra for an ACGT-only multi-sequence text (HSP.c:569-699)."""
+    arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    st = np.ascontiguousarray(starts, dtype=np.uint64)
+    ln = np.ascontiguousarray(lengths, dtype=np.uint64)
+    rc = lib().mp_index_save_annotation(prefix.encode(), int(text_length), len(names), arr, _ptr(st), _ptr(ln))
+    if rc != 0:
+        raise MegapathError("%s (status %d)" % (lib().mp_last_error().decode(), rc))
+
+
+def pack_text(codes):
+    """codes 0..3 (numpy uint8) -> .pac bytes: 4 bases per byte, first base in the top 2 bits."""
+    n = len(codes)
+    c = np.zeros((n + 3) // 4 * 4, dtype=np.uint8)
+    c[:n] = codes
+    c = c.reshape(-1, 4)
+    return ((c[:, 0] << 6) | (c[:, 1] << 4) | (c[:, 2] << 2) | c[:, 3]).astype(np.uint8)
 
 
 def _ptr(a):
@@ -177,10 +203,32 @@ class Context:
     # ---- index ----
     def index_load(self, prefix):
         self._check(self.L.mp_index_load(self.h, prefix.encode()))
+        self._has_index = True
 
     def index_build(self, text2bit, n):
+        """GPU FM-index construction from a .pac-packed text (replaces 2bwt-builder)."""
         text2bit = np.ascontiguousarray(text2bit, dtype=np.uint8)
         self._check(self.L.mp_index_build(self.h, _ptr(text2bit), n))
+        self._has_index = True
+
+    def index_build_codes(self, codes_t, bounds, prefix=None):
+        """codes_t: torch uint8 tensor of codes 0..3 (any device); bounds: sequence boundaries (nseq+1).
+        Builds the index in HBM and, if prefix is given, exports it in the reference's file formats."""
+        import torch
+        n = codes_t.numel()
+        pad = (-n) % 4
+        c = codes_t if pad == 0 else torch.cat([codes_t, torch.zeros(pad, dtype=torch.uint8, device=codes_t.device)])
+        c = c.view(-1, 4)
+        pac = ((c[:, 0] << 6) | (c[:, 1] << 4) | (c[:, 2] << 2) | c[:, 3]).to(torch.uint8).cpu().numpy()
+        del c
+        self.index_build(pac, n)
+        if prefix is not None:
+            self.index_save(prefix)
+            b = np.asarray(bounds, dtype=np.uint64)
+            save_annotation(prefix, n, ["seq%d" % (i + 1) for i in range(len(b) - 1)], b[:-1], b[1:] - b[:-1])
+
+    def has_index(self):
+        return getattr(self, "_has_index", False)
 
     def index_save(self, prefix):
         self._check(self.L.mp_index_save(self.h, prefix.encode()))
@@ -217,6 +265,12 @@ class Context:
         read_lengths = np.ascontiguousarray(read_lengths, dtype=np.uint32)
         self._keep = (queries, read_lengths)
         self._check(self.L.mp_batch_upload(self.h, _ptr(queries), _ptr(read_lengths), len(read_lengths), wpq))
+
+    def batch_upload_ptr(self, host_ptr, read_lengths, wpq):
+        """Same call with a raw host pointer (e.g. a pinned torch tensor's data_ptr())."""
+        read_lengths = np.ascontiguousarray(read_lengths, dtype=np.uint32)
+        self._keep = (read_lengths,)
+        self._check(self.L.mp_batch_upload(self.h, C.c_void_p(host_ptr), _ptr(read_lengths), len(read_lengths), wpq))
 
     def seed_pairs(self, params):
         self._check(self.L.mp_seed_pairs(self.h, C.byref(params)))
@@ -273,6 +327,22 @@ class Context:
             out[name] = getattr(res, name)
         self.L.mp_results_release(self.h, C.byref(res))
         return out
+
+
+def _summary(self, params):
+    """mp_align_pairs without copying the result arrays out of the library's host arena:
+    -> counters + sizes (bench.py)."""
+    res = Results()
+    self._check(self.L.mp_align_pairs(self.h, C.byref(params), C.byref(res)))
+    out = {name: getattr(res, name) for name, _ in Results._fields_[8:]}
+    out["n_pairs"], out["n_singles"], out["n_rescued"] = res.n_pairs, res.n_singles, res.n_rescued
+    out["result_bytes"] = (res.n_pairs + res.n_rescued) * PAIR_RESULT.itemsize + res.n_singles * SINGLE_RESULT.itemsize + res.cigar_bytes
+    out["pairs_aligned"] = res.numDPAlignedPair + res.numRescuedPair
+    self.L.mp_results_release(self.h, C.byref(res))
+    return out
+
+
+Context.align_pairs_summary = _summary
 
 
 def cigar_at(cigars, off):

@@ -212,18 +212,20 @@ static int deep_dp(mp_context *ctx, const mp_align_params *P, mp_results *out, u
     std::vector<mp_pair_result> &H = ctx->hPairs;
     std::vector<char> &HC = ctx->hCigars;
     const uint64_t fullLen = ctx->ix.n;
+    MpTrace tr;
     for (uint64_t base = 0; base < nC; base += CH) {
         uint32_t n = (uint32_t)std::min<uint64_t>(CH, nC - base);
         const mp_candidate *cands = ctx->dCands.as<mp_candidate>() + base;
         unsigned g = (n + 127) / 128;
-        k_left_tasks<<<g, 128, 0, st>>>(cands, n, ctx->dLens.as<uint32_t>(), fullLen, P->peStrandLeftLeg, dLT.as<MpDpTask>());
+        (++g_mp_launches), k_left_tasks<<<g, 128, 0, st>>>(cands, n, ctx->dLens.as<uint32_t>(), fullLen, P->peStrandLeftLeg, dLT.as<MpDpTask>());
         if (int rc = mpd_run_tasks(ctx, dLT.as<MpDpTask>(), n, maxDNALength, maxReadLength, dpl, dLO.as<MpDpOut>(), dLP.as<uint8_t>(), patStride)) return rc;
-        k_right_tasks<<<g, 128, 0, st>>>(cands, n, ctx->dLens.as<uint32_t>(), fullLen, P->peStrandRightLeg, P->insert_high,
+        (++g_mp_launches), k_right_tasks<<<g, 128, 0, st>>>(cands, n, ctx->dLens.as<uint32_t>(), fullLen, P->peStrandRightLeg, P->insert_high,
                                          dLT.as<MpDpTask>(), dLO.as<MpDpOut>(), dRT.as<MpDpTask>());
         if (int rc = mpd_run_tasks(ctx, dRT.as<MpDpTask>(), n, maxDNALength, maxReadLength, dpr, dRO.as<MpDpOut>(), dRP.as<uint8_t>(), patStride)) return rc;
+        if (tr.on) { cudaStreamSynchronize(st); tr.mark(" dp left+right"); }
         MP_CUDA(cudaMemsetAsync(dOk.p, 0, ((size_t)n + 1) * 4, st));
         MP_CUDA(cudaMemsetAsync(dBytes.p, 0, ((size_t)n + 1) * 4, st));
-        k_assemble_measure<<<g, 128, 0, st>>>(n, dLT.as<MpDpTask>(), dLO.as<MpDpOut>(), dRT.as<MpDpTask>(), dRO.as<MpDpOut>(),
+        (++g_mp_launches), k_assemble_measure<<<g, 128, 0, st>>>(n, dLT.as<MpDpTask>(), dLO.as<MpDpOut>(), dRT.as<MpDpTask>(), dRO.as<MpDpOut>(),
                                               dLP.as<uint8_t>(), dRP.as<uint8_t>(), patStride, P->openGapScore, P->extendGapScore,
                                               dOk.as<uint32_t>(), dBytes.as<uint32_t>());
         if (scan_u32(ctx, dOk.as<uint32_t>(), dIdx.as<uint32_t>(), (uint64_t)n + 1)) return MP_ERR_CUDA;
@@ -235,7 +237,7 @@ static int deep_dp(mp_context *ctx, const mp_align_params *P, mp_results *out, u
         if (dCig.reserve((size_t)nBytes + 16)) return MP_ERR_CUDA;
         uint32_t cigBase = (uint32_t)HC.size();
         if (nOk) {
-            k_assemble_write<<<g, 128, 0, st>>>(n, cands, dLT.as<MpDpTask>(), dLO.as<MpDpOut>(), dRT.as<MpDpTask>(), dRO.as<MpDpOut>(),
+            (++g_mp_launches), k_assemble_write<<<g, 128, 0, st>>>(n, cands, dLT.as<MpDpTask>(), dLO.as<MpDpOut>(), dRT.as<MpDpTask>(), dRO.as<MpDpOut>(),
                                                 dLP.as<uint8_t>(), dRP.as<uint8_t>(), patStride, A, dOk.as<uint32_t>(), dIdx.as<uint32_t>(),
                                                 dOff.as<uint32_t>(), cigBase, dRes.as<mp_pair_result>(), dCig.as<char>());
             MP_CUDA(cudaGetLastError());
@@ -245,6 +247,7 @@ static int deep_dp(mp_context *ctx, const mp_align_params *P, mp_results *out, u
             MP_CUDA(cudaMemcpyAsync(HC.data() + cigBase, dCig.p, nBytes, cudaMemcpyDeviceToHost, st));
             MP_CUDA(cudaStreamSynchronize(st));
         }
+        tr.mark(" assemble+download");
         // work accounting: one left task per candidate, one right task per passing left
         {
             std::vector<MpDpTask> hl(n), hr(n);
@@ -256,8 +259,10 @@ static int deep_dp(mp_context *ctx, const mp_align_params *P, mp_results *out, u
             }
         }
     }
+    tr.mark(" accounting");
     dLT.release(); dRT.release(); dLO.release(); dRO.release(); dLP.release(); dRP.release();
     dOk.release(); dBytes.release(); dIdx.release(); dOff.release(); dRes.release(); dCig.release();
+    tr.mark(" release");
     // ---- per pair: sort, drop exact duplicates (OutputBuffer::arrayCopyNRemoveDuplicate, DV-DPfunctions.h:167-196) ----
     auto key = [](const mp_pair_result &a) { return std::make_tuple(a.algnmt_1, a.algnmt_2, a.score_1, a.score_2); };
     size_t w = 0, i = 0;
@@ -274,6 +279,7 @@ static int deep_dp(mp_context *ctx, const mp_align_params *P, mp_results *out, u
         i = j;
     }
     H.resize(w);
+    tr.mark(" host sort/dedup");
     out->numDPAlignedPair = nPairsAligned; out->numDPAlignment = w;
     return 0;
 }
@@ -426,18 +432,22 @@ extern "C" int mp_align_pairs(mp_context *ctx, const mp_align_params *params, mp
         mp_set_error("mp_align_pairs: score parameters outside the supported range (CPU_DP.cpp:199-208)"); return MP_ERR_ARG;
     }
     MP_CUDA(cudaSetDevice(ctx->device));
+    const double wall0 = mp_now_ms();
+    MpTrace tr;
     memset(out, 0, sizeof *out);
     ctx->hPairs.clear(); ctx->hRescued.clear(); ctx->hSingles.clear(); ctx->hCigars.clear();
     MP_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
     if (!ctx->seeded) { if (int rc = mp_seed_pairs(ctx, params)) return rc; }
     MP_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
+    tr.mark("seed_pairs");
     uint64_t cells = 0, tasksRun = 0;
     if (int rc = deep_dp(ctx, params, out, cells, tasksRun)) return rc;
     MP_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
     MP_CUDA(cudaStreamSynchronize(ctx->stream));
+    tr.mark("deep_dp");
     unsigned long long hc[16];
     MP_CUDA(cudaMemcpy(hc, ctx->dCounters.p, sizeof hc, cudaMemcpyDeviceToHost));
-    out->n_occ = hc[2] + hc[5]; out->n_sa = hc[3]; out->n_lkt = hc[4];
+    out->n_occ = hc[2]; out->n_lf = hc[5]; out->n_sa = hc[3]; out->n_lkt = hc[4];
     out->dp_cells = cells; out->dp_tasks = tasksRun;
     cudaEventElapsedTime(&out->ms_seed, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&out->ms_sa, ctx->ev[1], ctx->ev[2]);
@@ -449,6 +459,8 @@ extern "C" int mp_align_pairs(mp_context *ctx, const mp_align_params *params, mp
     out->singles = ctx->hSingles.data(); out->n_singles = ctx->hSingles.size();
     out->cigars = ctx->hCigars.data(); out->cigar_bytes = ctx->hCigars.size();
     ctx->seeded = false;       // the batch has been consumed
+    out->ms_wall = (float)(mp_now_ms() - wall0);
+    tr.mark("finish");
     return 0;
 }
 extern "C" void mp_results_release(mp_context *ctx, mp_results *res)
@@ -458,15 +470,3 @@ extern "C" void mp_results_release(mp_context *ctx, mp_results *res)
     if (res) memset(res, 0, sizeof *res);
 }
 
-extern "C" int mp_index_build(mp_context *ctx, const uint8_t *text2bit, uint64_t textLength)
-{
-    (void)ctx; (void)text2bit; (void)textLength;
-    mp_set_error("mp_index_build: not implemented yet");
-    return MP_ERR_STATE;
-}
-extern "C" int mp_index_save(mp_context *ctx, const char *prefix)
-{
-    (void)ctx; (void)prefix;
-    mp_set_error("mp_index_save: not implemented yet");
-    return MP_ERR_STATE;
-}

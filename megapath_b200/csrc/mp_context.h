@@ -2,13 +2,23 @@
 #pragma once
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
+#include <chrono>
 #include "../../include/megapath_b200.h"
 #include "mp_index.cuh"
 
 void mp_set_error(const char *fmt, ...);
+extern unsigned long long g_mp_launches;
+static inline double mp_now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+// MP_TRACE=1: wall-clock phase marks on stderr
+struct MpTrace {
+    bool on; double t0, last;
+    MpTrace() { const char *e = getenv("MP_TRACE"); on = e && *e && *e != '0'; t0 = last = mp_now_ms(); }
+    void mark(const char *what) { if (!on) return; double t = mp_now_ms(); fprintf(stderr, "[mp_trace] %-28s +%9.3f ms (%9.3f)\n", what, t - last, t - t0); last = t; }
+};     // kernels of this library launched so far (mp_launch_count)
 
 #define MP_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     mp_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); \

@@ -241,7 +241,7 @@ static int launch_dp(mp_context *ctx, const uint8_t *dRef, const uint32_t *dRefL
     if (ctx->dTable.reserve((size_t)warps * tableStride)) return MP_ERR_CUDA;
     dim3 grid(warps / 4), block(128);
     uint8_t *tab = ctx->dTable.as<uint8_t>();
-#define LAUNCH(KK) k_dp<KK><<<grid, block, 0, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, \
+#define LAUNCH(KK) (++g_mp_launches), k_dp<KK><<<grid, block, 0, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, \
         nTasks, P, tab, tableStride, dOuts, dPatterns, patStride)
     if (K == 4) LAUNCH(4); else if (K == 5) LAUNCH(5); else if (K == 8) LAUNCH(8); else LAUNCH(10);
 #undef LAUNCH
@@ -267,7 +267,7 @@ int mpd_run_tasks(mp_context *ctx, const MpDpTask *dTasks, uint32_t nTasks, uint
     uint32_t *dRefLens = (uint32_t *)(dRef + refB);
     uint32_t *dReadLens = dRefLens + nTasks;
     int32_t *dCutoffs = (int32_t *)(dReadLens + nTasks);
-    k_extract<<<nTasks, 64, 0, ctx->stream>>>(ctx->ix, ctx->dReads.as<uint32_t>(), ctx->wpq, dTasks, nTasks, dRef, maxRefLen,
+    (++g_mp_launches), k_extract<<<nTasks, 64, 0, ctx->stream>>>(ctx->ix, ctx->dReads.as<uint32_t>(), ctx->wpq, dTasks, nTasks, dRef, maxRefLen,
                                              ctx->dReadSeq.as<uint8_t>(), maxReadLen, dRefLens, dReadLens, dCutoffs);
     MP_CUDA(cudaGetLastError());
     return launch_dp(ctx, dRef, dRefLens, maxRefLen, ctx->dReadSeq.as<uint8_t>(), dReadLens, maxReadLen, dCutoffs, nTasks,

@@ -15,6 +15,8 @@ void mp_set_error(const char *fmt, ...)
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
 }
 extern "C" const char *mp_last_error(void) { return g_err; }
+unsigned long long g_mp_launches = 0;
+extern "C" uint64_t mp_launch_count(void) { return g_mp_launches; }
 
 // ---- file -> device in bounded chunks ----
 static int upload_region(FILE *f, uint64_t fileOff, uint64_t bytes, void *dst)
@@ -95,10 +97,10 @@ static int relayout(mp_context *ctx, const uint32_t *dWords, uint64_t n)
     if (tmp.reserve(tmpBytes)) return MP_ERR_CUDA;
     unsigned g = (unsigned)((nBlocks + 255) / 256);
     for (uint32_t c = 0; c < 4; ++c) {
-        k_block_counts<<<g, 256>>>(dWords, n, nBlocks, c, cnt.as<uint64_t>());
+        (++g_mp_launches), k_block_counts<<<g, 256>>>(dWords, n, nBlocks, c, cnt.as<uint64_t>());
         cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, cnt.as<uint64_t>(), scan.as<uint64_t>(), (int64_t)nBlocks);
-        k_super<<<(unsigned)((nSuper + 255) / 256), 256>>>(scan.as<uint64_t>(), nBlocks, c, ctx->dSuper.as<uint64_t>());
-        k_build_blocks<<<g, 256>>>(dWords, scan.as<uint64_t>(), ctx->dSuper.as<uint64_t>(), nBlocks, c, ctx->dBlocks.as<uint32_t>());
+        (++g_mp_launches), k_super<<<(unsigned)((nSuper + 255) / 256), 256>>>(scan.as<uint64_t>(), nBlocks, c, ctx->dSuper.as<uint64_t>());
+        (++g_mp_launches), k_build_blocks<<<g, 256>>>(dWords, scan.as<uint64_t>(), ctx->dSuper.as<uint64_t>(), nBlocks, c, ctx->dBlocks.as<uint32_t>());
     }
     MP_CUDA(cudaDeviceSynchronize());
     cnt.release(); scan.release(); tmp.release();
@@ -107,6 +109,8 @@ static int relayout(mp_context *ctx, const uint32_t *dWords, uint64_t n)
     ctx->ix.super = ctx->dSuper.as<uint64_t>();
     return 0;
 }
+
+int mpi_relayout_words(mp_context *ctx, const uint32_t *dWords, uint64_t n) { return relayout(ctx, dWords, n); }
 
 int mpi_build_from_words(mp_context *ctx, const uint32_t *hBwtWords, uint64_t n, uint64_t inverseSa0, const uint64_t cum[5])
 {
@@ -230,7 +234,7 @@ extern "C" int mp_occ(mp_context *ctx, const uint64_t *idx, const uint32_t *c, u
     if (a.reserve(n * 8) || b.reserve(n * 4) || o.reserve(n * 8)) return MP_ERR_CUDA;
     MP_CUDA(cudaMemcpy(a.p, idx, n * 8, cudaMemcpyHostToDevice));
     MP_CUDA(cudaMemcpy(b.p, c, n * 4, cudaMemcpyHostToDevice));
-    k_occ<<<(unsigned)((n + 255) / 256), 256>>>(ctx->ix, a.as<uint64_t>(), b.as<uint32_t>(), o.as<uint64_t>(), n);
+    (++g_mp_launches), k_occ<<<(unsigned)((n + 255) / 256), 256>>>(ctx->ix, a.as<uint64_t>(), b.as<uint32_t>(), o.as<uint64_t>(), n);
     MP_CUDA(cudaMemcpy(out, o.p, n * 8, cudaMemcpyDeviceToHost));
     a.release(); b.release(); o.release();
     return 0;
@@ -241,7 +245,7 @@ extern "C" int mp_sa(mp_context *ctx, const uint64_t *idx, uint64_t *out, uint64
     DevBuf a, o;
     if (a.reserve(n * 8) || o.reserve(n * 8)) return MP_ERR_CUDA;
     MP_CUDA(cudaMemcpy(a.p, idx, n * 8, cudaMemcpyHostToDevice));
-    k_sa<<<(unsigned)((n + 255) / 256), 256>>>(ctx->ix, a.as<uint64_t>(), o.as<uint64_t>(), n);
+    (++g_mp_launches), k_sa<<<(unsigned)((n + 255) / 256), 256>>>(ctx->ix, a.as<uint64_t>(), o.as<uint64_t>(), n);
     MP_CUDA(cudaMemcpy(out, o.p, n * 8, cudaMemcpyDeviceToHost));
     a.release(); o.release();
     return 0;
@@ -252,7 +256,7 @@ extern "C" int mp_lkt(mp_context *ctx, const uint32_t *key, uint64_t *l, uint64_
     DevBuf a, o1, o2;
     if (a.reserve(n * 4) || o1.reserve(n * 8) || o2.reserve(n * 8)) return MP_ERR_CUDA;
     MP_CUDA(cudaMemcpy(a.p, key, n * 4, cudaMemcpyHostToDevice));
-    k_lkt<<<(unsigned)((n + 255) / 256), 256>>>(ctx->ix, a.as<uint32_t>(), o1.as<uint64_t>(), o2.as<uint64_t>(), n);
+    (++g_mp_launches), k_lkt<<<(unsigned)((n + 255) / 256), 256>>>(ctx->ix, a.as<uint32_t>(), o1.as<uint64_t>(), o2.as<uint64_t>(), n);
     MP_CUDA(cudaMemcpy(l, o1.p, n * 8, cudaMemcpyDeviceToHost));
     MP_CUDA(cudaMemcpy(r, o2.p, n * 8, cudaMemcpyDeviceToHost));
     a.release(); o1.release(); o2.release();

@@ -310,7 +310,7 @@ int mps_upload(mp_context *ctx, const uint32_t *queries, const uint32_t *readLen
     MP_CUDA(cudaMemcpyAsync(ctx->dLens.p, readLengths, (size_t)nReads * 4, cudaMemcpyHostToDevice, ctx->stream));
     MP_CUDA(cudaMemsetAsync(ctx->dReads.p, 0, bytes + 64, ctx->stream));
     uint64_t total = nPad * wpq;
-    k_deinterleave<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(ctx->dReadsIl.as<uint32_t>(), ctx->dReads.as<uint32_t>(), nReads, wpq);
+    (++g_mp_launches), k_deinterleave<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(ctx->dReadsIl.as<uint32_t>(), ctx->dReads.as<uint32_t>(), nReads, wpq);
     MP_CUDA(cudaGetLastError());
     ctx->nReads = nReads; ctx->wpq = wpq; ctx->hasBatch = true; ctx->seeded = false;
     return 0;
@@ -340,7 +340,7 @@ int mps_seed_pairs(mp_context *ctx, const mp_align_params *AP)
         MP_CUDA(cudaMemsetAsync(ctx->dCounters.p, 0, 16 * 8, st));
         MP_CUDA(cudaMemsetAsync(ctx->dHitsPerRead.p, 0, ((size_t)nReads + 1) * 4, st));
         // persistent grid: 6 CTAs of 256 threads per SM (register bound), quads pull work
-        k_mmp<<<nSM * 6, 256, 0, st>>>(ctx->ix, ctx->dReads.as<uint32_t>(), ctx->dLens.as<uint32_t>(), ctx->wpq, nStrands, P,
+        (++g_mp_launches), k_mmp<<<nSM * 6, 256, 0, st>>>(ctx->ix, ctx->dReads.as<uint32_t>(), ctx->dLens.as<uint32_t>(), ctx->wpq, nStrands, P,
                                       ctx->dSeeds.as<MpSeed>(), ctx->dStubs.as<uint32_t>(), ctx->dCounters.as<unsigned long long>(),
                                       ctx->dHitsPerRead.as<uint32_t>(), (uint32_t)ctx->capSeeds, (uint32_t)ctx->capStubs);
         MP_CUDA(cudaGetLastError());
@@ -358,18 +358,18 @@ int mps_seed_pairs(mp_context *ctx, const mp_align_params *AP)
     if (ctx->dHits.reserve(hitBytes) || ctx->dSeedPos.reserve((ctx->nHits + 1) * sizeof(mp_seed_pos))) return MP_ERR_CUDA;
     MP_CUDA(cudaMemsetAsync(ctx->dCursor.p, 0, ((size_t)nReads + 1) * 4, st));
     if (ctx->nHits)
-        k_expand<<<(unsigned)((ctx->nHits + 127) / 128), 128, 0, st>>>(ctx->ix, ctx->dSeeds.as<MpSeed>(), ctx->dStubs.as<uint32_t>(), ctx->nHits,
+        (++g_mp_launches), k_expand<<<(unsigned)((ctx->nHits + 127) / 128), 128, 0, st>>>(ctx->ix, ctx->dSeeds.as<MpSeed>(), ctx->dStubs.as<uint32_t>(), ctx->nHits,
             ctx->dLens.as<uint32_t>(), P, ctx->dHitStart.as<uint32_t>(), ctx->dCursor.as<uint32_t>(), ctx->dHits.as<MpHit>(),
             ctx->dCounters.as<unsigned long long>());
     MP_CUDA(cudaGetLastError());
     MP_CUDA(cudaEventRecord(ctx->ev[2], st));
-    k_merge<<<(nReads + 127) / 128, 128, 0, st>>>(ctx->dHitStart.as<uint32_t>(), ctx->dHits.as<MpHit>(), nReads, P,
+    (++g_mp_launches), k_merge<<<(nReads + 127) / 128, 128, 0, st>>>(ctx->dHitStart.as<uint32_t>(), ctx->dHits.as<MpHit>(), nReads, P,
                                                  ctx->dSeedPos.as<mp_seed_pos>(), ctx->dNPos.as<uint32_t>(), ctx->dNNeg.as<uint32_t>());
     MP_CUDA(cudaGetLastError());
     // pairing: count, scan, write
     if (ctx->dCandCount.reserve(((size_t)nPairs + 1) * 4) || ctx->dCandStart.reserve(((size_t)nPairs + 1) * 4)) return MP_ERR_CUDA;
     MP_CUDA(cudaMemsetAsync(ctx->dCandCount.p, 0, ((size_t)nPairs + 1) * 4, st));
-    k_pair<<<(nPairs + 127) / 128, 128, 0, st>>>(ctx->dHitStart.as<uint32_t>(), ctx->dSeedPos.as<mp_seed_pos>(), ctx->dNPos.as<uint32_t>(),
+    (++g_mp_launches), k_pair<<<(nPairs + 127) / 128, 128, 0, st>>>(ctx->dHitStart.as<uint32_t>(), ctx->dSeedPos.as<mp_seed_pos>(), ctx->dNPos.as<uint32_t>(),
         ctx->dNNeg.as<uint32_t>(), ctx->dLens.as<uint32_t>(), nPairs, AP->insert_low, AP->insert_high,
         ctx->dCandCount.as<uint32_t>(), nullptr, nullptr);
     if (exclusive_scan_u32(ctx, ctx->dCandCount.as<uint32_t>(), ctx->dCandStart.as<uint32_t>(), (uint64_t)nPairs + 1)) return MP_ERR_CUDA;
@@ -379,7 +379,7 @@ int mps_seed_pairs(mp_context *ctx, const mp_align_params *AP)
     ctx->nCands = total;
     if (ctx->dCands.reserve(((size_t)total + 1) * sizeof(mp_candidate))) return MP_ERR_CUDA;
     if (total)
-        k_pair<<<(nPairs + 127) / 128, 128, 0, st>>>(ctx->dHitStart.as<uint32_t>(), ctx->dSeedPos.as<mp_seed_pos>(), ctx->dNPos.as<uint32_t>(),
+        (++g_mp_launches), k_pair<<<(nPairs + 127) / 128, 128, 0, st>>>(ctx->dHitStart.as<uint32_t>(), ctx->dSeedPos.as<mp_seed_pos>(), ctx->dNPos.as<uint32_t>(),
             ctx->dNNeg.as<uint32_t>(), ctx->dLens.as<uint32_t>(), nPairs, AP->insert_low, AP->insert_high,
             ctx->dCandCount.as<uint32_t>(), ctx->dCandStart.as<uint32_t>(), ctx->dCands.as<mp_candidate>());
     MP_CUDA(cudaGetLastError());

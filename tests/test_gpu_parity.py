@@ -105,3 +105,43 @@ def test_gpu_errors_are_loud(small_ref):
     with pytest.raises(mp.MegapathError):
         c.seed_pairs(mp.default_params())
     c.close()
+
+
+@pytest.mark.parametrize("total,nseq,repeat_frac,seed", [(300000, 6, 0.05, 42), (70001, 1, 0.3, 5), (131072 + 255, 3, 0.0, 9), (65536 * 3, 2, 0.6, 11)])
+def test_gpu_index_build_matches_reference_builder(workdir, total, nseq, repeat_frac, seed):
+    """mp_index_build + mp_index_save against the files 2bwt-builder writes for the same text
+    (2BWT-Builder.c; BWTConstruct.c:994-1393; LTConstruct.c:46-96; HSP.c:560-699): byte-identical."""
+    import os
+    import shutil
+    import subprocess
+    import megapath_b200 as mp
+    from conftest import REF_DIR, have_ref
+    from tools import synth
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    d = os.path.join(workdir, "b%d" % total)
+    os.makedirs(d, exist_ok=True)
+    seq, bounds = synth.make_ref(total, nseq, seed=seed, repeat_frac=repeat_frac)
+    fa = os.path.join(d, "r.fa")
+    synth.write_fasta(fa, seq, bounds)
+    shutil.copy(os.path.join(REF_DIR, "2bwt-builder.ini"), os.path.join(d, "2bwt-builder.ini"))
+    subprocess.check_call([os.path.join(REF_DIR, "2bwt-builder"), fa], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    codes = np.searchsorted(np.frombuffer(b"ACGT", dtype=np.uint8), seq).astype(np.uint8)
+    c = mp.Context(0)
+    c.index_build(mp.pack_text(codes), total)
+    out = os.path.join(d, "mine.index")
+    c.index_save(out)
+    mp.save_annotation(out, total, ["seq%d" % (i + 1) for i in range(nseq)], bounds[:-1], np.diff(bounds))
+    info = c.index_info()
+    assert info["textLength"] == total
+    for ext in (".pac", ".bwt", ".fmv", ".sa", ".lkt", ".tra", ".amb"):
+        a = open(fa + ".index" + ext, "rb").read()
+        b = open(out + ext, "rb").read()
+        assert len(a) == len(b), ext
+        assert a == b, ext
+    # the built index answers like the loaded one
+    ix = po.Index(fa + ".index")
+    rng = np.random.default_rng(1)
+    sidx = rng.integers(0, total + 1, size=4000).astype(np.uint64)
+    assert (c.sa(sidx) == ix.sa(sidx)).all()
+    c.close()
