@@ -68,14 +68,28 @@ extern "C" OrcIndex *orc_index_load(const char *prefix)
         memcpy(ix->sa.data(), b.data() + 48, cnt * 8);
         ix->sa[0] = (uint64_t)-1;
     }
-    {   // .lkt : i32 tableSize(13), 4^13 u64
+    ix->pac = slurp(p + ".pac");
+    FILE *lf = fopen((p + ".lkt").c_str(), "rb");
+    if (lf) {   // .lkt : i32 tableSize(13), 4^13 u64
+        fclose(lf);
         std::vector<uint8_t> b = slurp(p + ".lkt");
         int ts = *(const int32_t *)b.data();
         uint64_t cnt = 1ull << (2 * ts);
         ix->lkt.resize(cnt);
         memcpy(ix->lkt.data(), b.data() + 4, cnt * 8);
+    } else {    // no .lkt (the 512 MiB table is not kept with the small golden fixtures): rebuild it as
+                // BuildLookupTable does (2bwt-lib/LTConstruct.c:46-96): count the 13-mer starting at every
+                // text position, windows running past the end padded with 'A', then inclusive prefix sums
+        const uint64_t cnt = 1ull << 26;
+        ix->lkt.assign(cnt, 0);
+        uint64_t window = 0;
+        for (uint64_t i = 0; i < ix->n + 12; ++i) {
+            uint32_t c = i < ix->n ? ((ix->pac[i >> 2] >> ((3 - (i & 3)) << 1)) & 3) : 0;
+            window = ((window << 2) | c) & (cnt - 1);
+            if (i >= 12) ++ix->lkt[window];
+        }
+        for (uint64_t k = 1; k < cnt; ++k) ix->lkt[k] += ix->lkt[k - 1];
     }
-    ix->pac = slurp(p + ".pac");
     return ix;
 }
 extern "C" void orc_index_free(OrcIndex *ix) { delete ix; }
