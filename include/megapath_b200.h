@@ -91,7 +91,7 @@ typedef struct mp_single_result {
     uint8_t  strand; uint8_t pad[3];
     uint32_t seedAlignmentLength;
     uint64_t startPos;
-    uint32_t refDpLength; uint32_t pad2;
+    uint32_t refDpLength; uint32_t peLeftAnchor;   /* peRightAnchor is always 0 here (DV-DPfunctions.cpp:437-438) */
 } mp_single_result;
 
 /* Result set of one mp_align_pairs call; owned by the library until mp_results_release. */

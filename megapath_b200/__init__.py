@@ -58,7 +58,7 @@ PAIR_RESULT = np.dtype([
 SINGLE_RESULT = np.dtype([
     ("readID", "<u4"), ("cigar", "<u4"), ("algnmt", "<u8"), ("score", "<i4"), ("editdist", "<i4"),
     ("num_sameScore", "<i4"), ("strand", "u1"), ("pad", "u1", (3,)), ("seedAlignmentLength", "<u4"),
-    ("startPos", "<u8"), ("refDpLength", "<u4"), ("pad2", "<u4")], align=True)
+    ("startPos", "<u8"), ("refDpLength", "<u4"), ("peLeftAnchor", "<u4")], align=True)
 
 _lib = None
 

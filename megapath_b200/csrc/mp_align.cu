@@ -5,6 +5,7 @@
 //   result assembly DP2CPUAlgnThread + CigarStringEncoder         DV-DPfunctions.cpp:3391-3540, .h:344-427
 //   per-pair dedup  OutputBuffer::ready / ResultCompare           DV-DPfunctions.h:198-243, .cpp:253-258
 #include "mp_context.h"
+#include "mp_cigar.h"
 #include <cub/device/device_scan.cuh>
 #include <algorithm>
 #include <tuple>
@@ -14,12 +15,6 @@
 int mps_upload(mp_context *ctx, const uint32_t *queries, const uint32_t *readLengths, uint32_t nReads, uint32_t wpq);
 int mps_download_seedpos(mp_context *ctx, mp_seed_pos **readPos, uint64_t *nReadPos, mp_seed_pos **matePos, uint64_t *nMatePos);
 
-#define MP_MARGIN(l) (((l) > 100) ? 30 : 25)       // DP2_MARGIN, DV-DPfunctions.cpp:1760
-
-__host__ __device__ inline int dp_cutoff(uint32_t readLen)           // definitions.h:166-167
-{
-    double v = 0.2 * readLen; if (v < 30.0) v = 30.0; return (int)v;
-}
 
 // ---- packLeft (DV-DPfunctions.cpp:2857-2924) ----
 __global__ void k_left_tasks(const mp_candidate *__restrict__ cands, uint32_t n, const uint32_t *__restrict__ lens,
@@ -62,41 +57,6 @@ __global__ void k_right_tasks(const mp_candidate *__restrict__ cands, uint32_t n
         t.strand = (uint8_t)strandRight; t.valid = 1; t.cutoff = dp_cutoff(readLength);
     }
     tasks[c] = t;
-}
-
-// ---- pattern -> special CIGAR (CigarStringEncoder, DV-DPfunctions.h:344-427; use at .cpp:3447-3471) ----
-struct CigStats { int nI, nD, nS, gapPenalty, textLen; };
-__device__ inline int ndigits(int v) { return v >= 100 ? 3 : v >= 10 ? 2 : 1; }
-// The encoder merges consecutive equal types while scanning the (end -> start) pattern and prints the
-// runs in reverse.  `out` == nullptr: measure only.  Text is written backwards from out + textLen.
-__device__ CigStats cigar_encode(const uint8_t *__restrict__ pat, int open, int ext, char *out, int textLen)
-{
-    CigStats st; st.nI = st.nD = st.nS = st.gapPenalty = st.textLen = 0;
-    char *w = out ? out + textLen : nullptr;
-    int curType = 'N', curCnt = 0, lastType = 'N';
-    const uint8_t *p = pat;
-    while (true) {
-        int type, cnt; bool end = false;
-        if (*p == 0) { type = 0; cnt = 0; end = true; }
-        else if (*p == 'V') { type = lastType; cnt = (int)p[1] - 1; p += 2; }
-        else { type = *p; cnt = 1; lastType = type; ++p; }
-        if (!end && type == curType) { curCnt += cnt; continue; }
-        // flush the finished run
-        if (curCnt > 0 && curType != 'N') {
-            int nd = ndigits(curCnt);
-            st.textLen += nd + 1;
-            if (curType == 'I') st.nI += curCnt; else if (curType == 'D') st.nD += curCnt; else if (curType == 'S') st.nS += curCnt;
-            if (curType == 'I' || curType == 'D') st.gapPenalty += open + (curCnt - 1) * ext;
-            if (w) {
-                *--w = (char)curType;
-                int v = curCnt;
-                for (int d = 0; d < nd; ++d) { *--w = (char)('0' + v % 10); v /= 10; }
-            }
-        }
-        if (end) break;
-        curType = type; curCnt = cnt;
-    }
-    return st;
 }
 
 struct PairWork { uint32_t ok; uint32_t cigLen[2]; };
@@ -201,7 +161,8 @@ static int deep_dp(mp_context *ctx, const mp_align_params *P, mp_results *out, u
     A.strandLeft = P->peStrandLeftLeg; A.strandRight = P->peStrandRightLeg; A.insert_low = P->insert_low; A.maxDNALength = maxDNALength;
 
     const uint32_t CH = 1u << 18;
-    DevBuf dLT, dRT, dLO, dRO, dLP, dRP, dOk, dBytes, dIdx, dOff, dRes, dCig;
+    DevBuf &dLT = ctx->dLT, &dRT = ctx->dRT, &dLO = ctx->dLO, &dRO = ctx->dRO, &dLP = ctx->dLP, &dRP = ctx->dRP, &dOk = ctx->dOk,
+           &dBytes = ctx->dBytes, &dIdx = ctx->dIdx, &dOff = ctx->dOff, &dRes = ctx->dRes, &dCig = ctx->dCig;
     uint32_t chunkCap = (uint32_t)std::min<uint64_t>(CH, nC ? nC : 1);
     if (dLT.reserve((size_t)chunkCap * sizeof(MpDpTask)) || dRT.reserve((size_t)chunkCap * sizeof(MpDpTask)) ||
         dLO.reserve((size_t)chunkCap * sizeof(MpDpOut)) || dRO.reserve((size_t)chunkCap * sizeof(MpDpOut)) ||
@@ -260,9 +221,6 @@ static int deep_dp(mp_context *ctx, const mp_align_params *P, mp_results *out, u
         }
     }
     tr.mark(" accounting");
-    dLT.release(); dRT.release(); dLO.release(); dRO.release(); dLP.release(); dRP.release();
-    dOk.release(); dBytes.release(); dIdx.release(); dOff.release(); dRes.release(); dCig.release();
-    tr.mark(" release");
     // ---- per pair: sort, drop exact duplicates (OutputBuffer::arrayCopyNRemoveDuplicate, DV-DPfunctions.h:167-196) ----
     auto key = [](const mp_pair_result &a) { return std::make_tuple(a.algnmt_1, a.algnmt_2, a.score_1, a.score_2); };
     size_t w = 0, i = 0;
@@ -309,7 +267,9 @@ extern "C" void mp_destroy(mp_context *ctx)
     DevBuf *bufs[] = { &ctx->dBlocks, &ctx->dSuper, &ctx->dSa, &ctx->dLkt, &ctx->dPac, &ctx->dReadsIl, &ctx->dReads, &ctx->dLens,
                        &ctx->dCounters, &ctx->dSeeds, &ctx->dStubs, &ctx->dHitsPerRead, &ctx->dHitStart, &ctx->dCursor, &ctx->dHits,
                        &ctx->dSeedPos, &ctx->dNPos, &ctx->dNNeg, &ctx->dCandCount, &ctx->dCandStart, &ctx->dCands, &ctx->dScanTmp,
-                       &ctx->dTasks, &ctx->dRefSeq, &ctx->dReadSeq, &ctx->dTable, &ctx->dPattern, &ctx->dDpOut };
+                       &ctx->dTasks, &ctx->dRefSeq, &ctx->dReadSeq, &ctx->dTable, &ctx->dPattern, &ctx->dDpOut,
+                       &ctx->dLT, &ctx->dRT, &ctx->dLO, &ctx->dRO, &ctx->dLP, &ctx->dRP, &ctx->dOk, &ctx->dBytes, &ctx->dIdx, &ctx->dOff,
+                       &ctx->dRes, &ctx->dCig };
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->stream);
@@ -442,9 +402,11 @@ extern "C" int mp_align_pairs(mp_context *ctx, const mp_align_params *params, mp
     tr.mark("seed_pairs");
     uint64_t cells = 0, tasksRun = 0;
     if (int rc = deep_dp(ctx, params, out, cells, tasksRun)) return rc;
+    tr.mark("deep_dp");
+    if (int rc = mps_single_and_rescue(ctx, params, out, cells, tasksRun)) return rc;
     MP_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
     MP_CUDA(cudaStreamSynchronize(ctx->stream));
-    tr.mark("deep_dp");
+    tr.mark("single+default dp");
     unsigned long long hc[16];
     MP_CUDA(cudaMemcpy(hc, ctx->dCounters.p, sizeof hc, cudaMemcpyDeviceToHost));
     out->n_occ = hc[2]; out->n_lf = hc[5]; out->n_sa = hc[3]; out->n_lkt = hc[4];

@@ -88,6 +88,7 @@ struct mp_context {
     mp_align_params seedParams;
     // DP
     DevBuf dTasks, dRefSeq, dReadSeq, dTable, dPattern, dDpOut;
+    DevBuf dLT, dRT, dLO, dRO, dLP, dRP, dOk, dBytes, dIdx, dOff, dRes, dCig;   // stage S1 chunk buffers (kept across calls)
     // results (host, owned until release)
     std::vector<mp_pair_result> hPairs, hRescued;
     std::vector<mp_single_result> hSingles;
@@ -104,6 +105,10 @@ struct MpDpParams { int clipLt, clipRt, mismatch, open; };
 // tasks (device) -> outs (device); sequences are extracted from the index / uploaded reads
 int mpd_run_tasks(mp_context *ctx, const MpDpTask *dTasks, uint32_t nTasks, uint32_t maxRefLen, uint32_t maxReadLen,
                   const MpDpParams &P, MpDpOut *dOuts, uint8_t *dPatterns, uint32_t patStride);
+int mpd_run_host_tasks(mp_context *ctx, const std::vector<MpDpTask> &tasks, uint32_t maxRefLen, uint32_t maxReadLen, const MpDpParams &P,
+                       std::vector<MpDpOut> &outs, std::vector<uint8_t> &pats, uint32_t patStride);
+// mp_stages.cu: single-end DP + default DP for the pairs stage S1 left unaligned
+int mps_single_and_rescue(mp_context *ctx, const mp_align_params *P, mp_results *out, uint64_t &cells, uint64_t &tasksRun);
 // explicit sequences (one byte per base, stride maxRefLen / maxReadLen)
 int mpd_run_explicit(mp_context *ctx, const uint8_t *dRef, const uint32_t *dRefLens, uint32_t maxRefLen,
                      const uint8_t *dRead, const uint32_t *dReadLens, uint32_t maxReadLen, const int32_t *dCutoffs,

@@ -27,7 +27,7 @@ struct MmpDev {
 __global__ void k_deinterleave(const uint32_t *__restrict__ il, uint32_t *__restrict__ out, uint32_t nReads, uint32_t wpq)
 {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint64_t total = (uint64_t)nReads * wpq;
+    uint64_t total = ((uint64_t)nReads + 31) / 32 * 32 * wpq;      // whole 32-read groups: the last one may be partial
     if (t >= total) return;
     // consecutive threads read consecutive interleaved words
     uint64_t grp = t / (32ull * wpq);

@@ -80,3 +80,25 @@ def load_pairs(fq1, fq2, trunc):
     lens[0::2] = la
     lens[1::2] = lb
     return reads, lens
+
+
+def canon_fastq(data):
+    """Canonical form of the interleaved stdout FASTQ: pairs (mate 1 and mate 2 are written
+    adjacently) sorted by read name; worker threads of the reference emit pairs in arbitrary order."""
+    lines = data.split(b"\n")
+    recs = [b"\n".join(lines[i:i + 4]) for i in range(0, len(lines) - 3, 4)]
+    pairs = [(recs[i], recs[i + 1]) for i in range(0, len(recs) - 1, 2)]
+    pairs.sort(key=lambda p: p[0].split(b"\t")[0])
+    return b"\n".join(a + b"\n" + b for a, b in pairs) + b"\n"
+
+
+def run_our_soap4(workdir, index_prefix, fq1, fq2, out_name, max_len_opt, ini="soap4.ini", extra=("-F", "-nc"), insert_high=750):
+    """Runs the product's host driver (megapath_b200/bin/soap4) -> stdout bytes."""
+    exe = os.path.join(ROOT, "megapath_b200", "bin", "soap4")
+    ini_path = os.path.join(ROOT, "megapath_b200", "ini", ini)
+    cmd = [exe, "pair", index_prefix, fq1, fq2, "-o", os.path.join(workdir, out_name), "-C", ini_path, "-L", str(max_len_opt),
+           "-T", "2", "-u", str(insert_high)] + list(extra)
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    if p.returncode != 0:
+        raise RuntimeError("soap4 driver failed: " + p.stderr.decode()[-2000:])
+    return p.stdout
