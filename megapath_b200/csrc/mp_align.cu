@@ -254,6 +254,7 @@ extern "C" int mp_init(int device, mp_context **pctx)
     if (device < 0 || device >= count) { mp_set_error("mp_init: device %d out of range (%d devices)", device, count); return MP_ERR_ARG; }
     MP_CUDA(cudaSetDevice(device));
     mp_context *ctx = new mp_context;
+    memset(&ctx->ix, 0, sizeof ctx->ix);
     ctx->device = device;
     MP_CUDA(cudaStreamCreate(&ctx->stream));
     for (int i = 0; i < 8; ++i) MP_CUDA(cudaEventCreate(&ctx->ev[i]));
@@ -264,7 +265,7 @@ extern "C" void mp_destroy(mp_context *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    DevBuf *bufs[] = { &ctx->dBlocks, &ctx->dSuper, &ctx->dSa, &ctx->dLkt, &ctx->dPac, &ctx->dReadsIl, &ctx->dReads, &ctx->dLens,
+    DevBuf *bufs[] = { &ctx->dBlocks, &ctx->dSuper, &ctx->dSa, &ctx->dSa32, &ctx->dBloom, &ctx->dLkt, &ctx->dPac, &ctx->dReadsIl, &ctx->dReads, &ctx->dLens,
                        &ctx->dCounters, &ctx->dSeeds, &ctx->dStubs, &ctx->dHitsPerRead, &ctx->dHitStart, &ctx->dCursor, &ctx->dHits,
                        &ctx->dSeedPos, &ctx->dNPos, &ctx->dNNeg, &ctx->dCandCount, &ctx->dCandStart, &ctx->dCands, &ctx->dScanTmp,
                        &ctx->dTasks, &ctx->dRefSeq, &ctx->dReadSeq, &ctx->dTable, &ctx->dPattern, &ctx->dDpOut,

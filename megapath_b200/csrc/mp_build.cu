@@ -154,6 +154,7 @@ extern "C" int mp_index_build(mp_context *ctx, const uint8_t *text2bit, uint64_t
     if (n + 1 >= 0xFFFFFFF0ull) { mp_set_error("mp_index_build: the GPU builder indexes up to 4.29 Gbp (32-bit suffix indices); load 2bwt-builder files for larger texts"); return MP_ERR_CAPACITY; }
     MP_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    ctx->hasIndex = false; ctx->bloomK = 0; ctx->ix.sa32 = nullptr; ctx->dSa32.release();
     const uint64_t N = n + 1;                       // suffixes incl. the '$' suffix
     const uint64_t pacBytes = (n + 3) / 4;
     // ---- packed text (kept as the index's .pac) ----
@@ -272,6 +273,13 @@ extern "C" int mp_index_build(mp_context *ctx, const uint8_t *text2bit, uint64_t
     ctx->ix.sa = ctx->dSa.as<uint64_t>(); ctx->ix.saShift = saShift; ctx->saInterval = 16;
     // ---- occurrence blocks ----
     if (int rc = mpi_relayout_words(ctx, dWords, n)) return fail(rc);
+    // keep the full suffix array as the dense SA of the resident index (the buffer changes owner)
+    {
+        DevBuf &owner = (sa == valsA.as<uint32_t>()) ? valsA : valsB;
+        ctx->dSa32.release();
+        ctx->dSa32 = owner; owner.p = nullptr; owner.cap = 0;
+        ctx->ix.sa32 = ctx->dSa32.as<uint32_t>();
+    }
     valsA.release(); valsB.release(); keysA.release(); keysB.release(); sortTmp.release();
     // ---- LKT: inclusive cumulative 13-mer counts ----
     const uint64_t nLkt = 1ull << 26;
@@ -289,7 +297,7 @@ extern "C" int mp_index_build(mp_context *ctx, const uint8_t *text2bit, uint64_t
     scanTmp.release();
     ctx->ix.lkt = ctx->dLkt.as<uint64_t>();
     ctx->ix.pac = pac;
-    ctx->hbmBytes = ctx->dBlocks.cap + ctx->dSuper.cap + ctx->dSa.cap + ctx->dLkt.cap + ctx->dPac.cap;
+    ctx->hbmBytes = ctx->dBlocks.cap + ctx->dSuper.cap + ctx->dSa.cap + ctx->dSa32.cap + ctx->dLkt.cap + ctx->dPac.cap;
     ctx->hasIndex = true; ctx->hasBatch = false; ctx->seeded = false;
     return 0;
 }

@@ -72,7 +72,8 @@ struct mp_context {
     // index
     bool hasIndex = false;
     MpIndexView ix;
-    DevBuf dBlocks, dSuper, dSa, dLkt, dPac;
+    DevBuf dBlocks, dSuper, dSa, dSa32, dLkt, dPac, dBloom;
+    int bloomK = 0; uint64_t bloomWords = 0; const void *bloomFor = nullptr;   // K-mer presence filter (mp_seed.cu)
     uint64_t hbmBytes = 0;
     std::vector<uint64_t> hSa; uint64_t saInterval = 16;   // kept for mp_index_save
     // batch

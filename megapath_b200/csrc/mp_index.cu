@@ -126,10 +126,17 @@ int mpi_build_from_words(mp_context *ctx, const uint32_t *hBwtWords, uint64_t n,
     return rc;
 }
 
+__global__ void k_densify_sa(MpIndexView ix, uint32_t *__restrict__ out, uint64_t count)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = (uint32_t)mp_sa(ix, i);      // ix.sa32 is still null here: sampled walk
+}
+
 int mpi_load(mp_context *ctx, const char *prefix)
 {
     std::string p(prefix);
     MP_CUDA(cudaSetDevice(ctx->device));
+    ctx->hasIndex = false; ctx->bloomK = 0;
     // ---- .bwt ----
     FILE *f = open_idx(p + ".bwt");
     if (!f) return MP_ERR_IO;
@@ -205,7 +212,19 @@ int mpi_load(mp_context *ctx, const char *prefix)
         if (rc) return rc;
     }
     ctx->ix.pac = ctx->dPac.as<uint8_t>();
-    ctx->hbmBytes = ctx->dBlocks.cap + ctx->dSuper.cap + ctx->dSa.cap + ctx->dLkt.cap + ctx->dPac.cap;
+    // ---- dense SA: resolve every SA index once at load time (LF walks to the file's 1/16 samples) so that
+    //      lookups on the hot path are a single gather.  MP_DENSE_SA=0 keeps the sampled array only. ----
+    ctx->ix.sa32 = nullptr; ctx->dSa32.release();
+    const char *dense = getenv("MP_DENSE_SA");
+    size_t freeB = 0, totalB = 0; cudaMemGetInfo(&freeB, &totalB);
+    if (!(dense && dense[0] == '0') && n + 1 < 0xFFFFFFF0ull && (n + 1) * 4 < freeB / 2) {
+        if (ctx->dSa32.reserve((n + 1) * 4)) return MP_ERR_CUDA;
+        (++g_mp_launches), k_densify_sa<<<(unsigned)((n + 1 + 255) / 256), 256>>>(ctx->ix, ctx->dSa32.as<uint32_t>(), n + 1);
+        MP_CUDA(cudaGetLastError());
+        MP_CUDA(cudaDeviceSynchronize());
+        ctx->ix.sa32 = ctx->dSa32.as<uint32_t>();
+    }
+    ctx->hbmBytes = ctx->dBlocks.cap + ctx->dSuper.cap + ctx->dSa.cap + ctx->dSa32.cap + ctx->dLkt.cap + ctx->dPac.cap;
     ctx->hasIndex = true;
     return 0;
 }

@@ -11,7 +11,9 @@
 //                            superblock base (superblock = 2^24 blocks, u64 x4, L1/L2 resident)
 //                  [16..63]  192 BWT symbols, 2 bit, 16 per u32, first symbol in the top bits
 //                            (the .bwt word order, so block b is .bwt words [12b, 12b+12))
-//   sa         : sampled suffix array, one value per saInterval SA indices (by index)
+//   sa         : sampled suffix array, one value per saInterval SA indices (by index), as in the .sa file
+//   sa32       : the full suffix array as u32 when the text is shorter than 2^32 (12.4 GB for 3.1 Gbp, HBM has
+//                180 GB): an SA lookup is then one gather instead of a geometric(1/16) LF walk
 //   lkt        : 4^13 cumulative 13-mer counts
 //   pac        : packed text, 4 bases per byte, first base in the top 2 bits
 #pragma once
@@ -30,6 +32,7 @@ struct MpIndexView {
     const uint64_t *super;   // (nBlocks >> 24) + 1 rows of 4
     const uint64_t *sa;      // (n + saInterval) / saInterval values, sa[0] = -1
     uint32_t saShift;        // log2(saInterval)
+    const uint32_t *sa32;    // optional: the whole suffix array (n + 1 entries, texts < 4.29 Gbp); one gather per SA lookup
     const uint64_t *lkt;     // 4^13
     const uint8_t *pac;
 };
@@ -99,6 +102,10 @@ __device__ __forceinline__ uint64_t mp_lf(const MpIndexView &ix, uint64_t i)
 // BWTSaValue (BWT.c:968-998)
 __device__ __forceinline__ uint64_t mp_sa(const MpIndexView &ix, uint64_t saIndex, uint32_t *steps = nullptr)
 {
+    if (ix.sa32) {             // dense SA: any sampling rate gives the same SA[i], this one costs one 4-byte gather
+        if (steps) *steps = 0;
+        return saIndex == 0 ? ~0ull : (uint64_t)__ldg(ix.sa32 + saIndex);
+    }
     uint64_t skipped = 0;
     const uint64_t mask = (1ull << ix.saShift) - 1;
     while (saIndex & mask) { ++skipped; saIndex = mp_lf(ix, saIndex); }

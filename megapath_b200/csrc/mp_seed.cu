@@ -54,31 +54,119 @@ __device__ __forceinline__ uint32_t lkt_key(const uint32_t *__restrict__ rd, int
     return (t >> 6) & 0x3FFFFFFu;
 }
 
-// rank of symbol c in one lane's quarter of a 64-byte block
-__device__ __forceinline__ uint32_t quad_partial(uint4 v, uint32_t sub, uint32_t c, uint32_t off)
+// ------------------------------------------------------------------------------------
+// K-mer presence filter (K = min(seedMinLength, 32)).  A backward search that starts at scan
+// position i0 and empties before seedMinLength bases emits nothing and restarts at i0 + 1
+// (CHECK_AND_ADD_RANGE rewinds by seed_len, DV-DPfunctions.cpp:2197-2219), so a start whose first
+// K bases do not occur in the text can be skipped without touching the FM-index.  The filter is a
+// word-blocked Bloom filter over all K-mers of the text (16 bits per text position, two bits per
+// key inside one 64-bit word): no false negatives, ~2 % false positives which simply take the
+// exact path.  The non-matching strand of every read (and every unalignable read) is rejected
+// with one independent 8-byte gather per start position instead of a dependent chain of
+// LKT + occ-block gathers.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void bloom_slot(uint64_t key, uint64_t nWords, uint64_t &word, uint64_t &mask)
 {
-    if (sub == 0) return c == 0 ? v.x : c == 1 ? v.y : c == 2 ? v.z : v.w;
-    int r = (int)off - 64 * (int)(sub - 1);
-    if (r <= 0) return 0;
-    return mp_word_count(v.x, c, min(r, 16)) + mp_word_count(v.y, c, min(max(r - 16, 0), 16)) +
-           mp_word_count(v.z, c, min(max(r - 32, 0), 16)) + mp_word_count(v.w, c, min(max(r - 48, 0), 16));
+    uint64_t h = key * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+    word = __umul64hi(h, nWords);
+    mask = (1ull << (h & 63)) | (1ull << ((h >> 6) & 63));
+}
+// 2K bits of a 2-bit, LSB-first packed read starting at base `pos` (K <= 32)
+__device__ __forceinline__ uint64_t read_window(const uint32_t *__restrict__ rd, int pos, int K)
+{
+    const int w = pos >> 4, sh = (pos & 15) << 1;
+    uint32_t w0 = __ldg(rd + w), w1 = __ldg(rd + w + 1), w2 = __ldg(rd + w + 2);
+    uint64_t v = (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
+    return K == 32 ? v : v & ((1ull << (2 * K)) - 1);
+}
+// key of the K-mer the backward search would have matched after K steps from scan position i
+// (text order, first base in the most significant 2-bit group)
+__device__ __forceinline__ uint64_t scan_kmer(const uint32_t *__restrict__ rd, int len, int i, int strand, int K)
+{
+    if (strand) {                   // pattern = revcomp(read[i .. i+K-1]): complement, base i least significant
+        uint64_t v = read_window(rd, i, K);
+        return (~v) & (K == 32 ? ~0ull : ((1ull << (2 * K)) - 1));
+    }
+    uint64_t v = read_window(rd, len - i - K, K);     // read[q-K+1 .. q], q = len-1-i, first base least significant
+    v = __brevll(v);                                   // reverse the order of the 2-bit groups
+    v = ((v >> 1) & 0x5555555555555555ull) | ((v & 0x5555555555555555ull) << 1);
+    return v >> (64 - 2 * K);
+}
+__global__ void k_bloom_build(const uint8_t *__restrict__ pac, uint64_t n, int K, unsigned long long *__restrict__ bloom, uint64_t nWords)
+{
+    // each thread rolls over 64 consecutive K-mer end positions
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t first = t * 64;                     // first K-mer start handled here
+    if (first + K > n) return;
+    const uint64_t maskK = K == 32 ? ~0ull : ((1ull << (2 * K)) - 1);
+    uint64_t key = 0;
+    for (int a = 0; a < K - 1; ++a) key = (key << 2) | ((pac[(first + a) >> 2] >> ((3 - ((first + a) & 3)) << 1)) & 3);
+    for (int j = 0; j < 64; ++j) {
+        uint64_t e = first + j + K - 1;                // last base of this K-mer
+        if (e >= n) break;
+        key = ((key << 2) | ((pac[e >> 2] >> ((3 - (e & 3)) << 1)) & 3)) & maskK;
+        uint64_t w, m; bloom_slot(key, nWords, w, m);
+        atomicOr(&bloom[w], (unsigned long long)m);
+    }
 }
 
-__global__ void __launch_bounds__(256)
+// rank of symbol c among the first `off` symbols held in three uint4 of BWT words
+__device__ __forceinline__ uint32_t words_rank(const uint4 &w0, const uint4 &w1, const uint4 &w2, uint32_t c, int off)
+{
+    uint32_t v = 0;
+    const uint4 *w[3] = { &w0, &w1, &w2 };
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        int r = off - 64 * q;
+        if (r > 0) {
+            v += mp_word_count(w[q]->x, c, min(r, 16)) + mp_word_count(w[q]->y, c, min(max(r - 16, 0), 16)) +
+                 mp_word_count(w[q]->z, c, min(max(r - 32, 0), 16)) + mp_word_count(w[q]->w, c, min(max(r - 48, 0), 16));
+        }
+    }
+    return v;
+}
+
+// Occ(a, c) and Occ(b, c), a <= b.  When both positions fall into the same 64-byte block (the usual case once
+// the SA range is narrower than 192) the block is fetched once.
+__device__ __forceinline__ void occ_pair(const MpIndexView &ix, uint64_t a, uint64_t b, uint32_t c, uint64_t &ra, uint64_t &rb)
+{
+    const uint64_t ba = a / MP_BLK_SYMS, bb = b / MP_BLK_SYMS;
+    const int oa = (int)(a - ba * MP_BLK_SYMS), ob = (int)(b - bb * MP_BLK_SYMS);
+    const uint4 *pa = ix.blocks + ba * 4;
+    uint4 h = __ldg(pa), w0 = __ldg(pa + 1), w1 = make_uint4(0, 0, 0, 0), w2 = w1;
+    const int need = ba == bb ? ob : oa;
+    if (need > 64) w1 = __ldg(pa + 2);
+    if (need > 128) w2 = __ldg(pa + 3);
+    uint32_t cnt = c == 0 ? h.x : c == 1 ? h.y : c == 2 ? h.z : h.w;
+    const uint64_t base = __ldg(ix.super + (ba >> MP_SUPER_SHIFT) * 4 + c) + cnt;
+    ra = base + words_rank(w0, w1, w2, c, oa);
+    if (ba == bb) rb = base + words_rank(w0, w1, w2, c, ob);
+    else rb = mp_occ_raw(ix, b, c);
+}
+
+// ------------------------------------------------------------------------------------
+// MMP seeding (mmp<0> / mmp<2>, DV-DPfunctions.cpp:2188-2377), one thread per read-strand.
+//
+// Phase A: LKT jump + backward-search steps while the SA range holds more than one suffix.
+// Phase B: once the range is a single suffix its text position p is looked up (one gather with
+//   the dense SA) and every further backward step "extend with c" is decided by comparing c with
+//   the text base at p-1: for a singleton range the step succeeds iff BWT[l] == c, and BWT[l] is
+//   text[SA[l]-1] ('$' when SA[l] == 0).  The emitted seeds, the reseed bookkeeping (`last` can only
+//   change while the range still shrinks, i.e. in phase A) and the rewind arithmetic are those of the
+//   reference; a seed that ends in phase B already knows its text position and skips SA resolution.
+//   nOcc counts the occ evaluations the reference performs for the same steps (2 per step).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
 k_mmp(MpIndexView ix, const uint32_t *__restrict__ reads, const uint32_t *__restrict__ lens, uint32_t wpq,
       uint32_t nStrands, MmpDev P, MpSeed *__restrict__ seeds, uint32_t *__restrict__ stubs,
       unsigned long long *__restrict__ counters, uint32_t *__restrict__ hitsPerRead,
-      uint32_t capSeeds, uint32_t capStubs)
+      uint32_t capSeeds, uint32_t capStubs, const unsigned long long *__restrict__ bloom, uint64_t bloomWords, int bloomK)
 {
-    const unsigned lane = threadIdx.x & 31, sub = lane & 3, qbase = lane & ~3u;
-    const unsigned qmask = 0xFu << qbase;
     const uint64_t n = ix.n;
-    unsigned long long nOcc = 0, nLkt = 0;
-    while (true) {
-        uint32_t s = 0;
-        if (sub == 0) s = (uint32_t)atomicAdd(&counters[6], 1ull);
-        s = __shfl_sync(qmask, s, qbase);
-        if (s >= nStrands) break;
+    unsigned long long nOcc = 0, nLkt = 0, nSaIn = 0, nLfIn = 0, nProbe = 0, nText = 0;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nStrands; s += stride) {
         const uint32_t read = s >> 1, strand = s & 1;
         const int len = (int)lens[read];
         const uint32_t *rd = reads + (size_t)read * wpq;
@@ -87,10 +175,27 @@ k_mmp(MpIndexView ix, const uint32_t *__restrict__ reads, const uint32_t *__rest
         int last_seed_len = 0;
         bool done = false;
         while (!done) {
-            bool emit = false; int x = 0;
+            bool emit = false, resolved = false; int x = 0;
+            uint64_t textPos = 0;
             if (i < len) {
                 bool step = true;
                 if (seed_len == 0) {
+                    // skip start positions whose first K bases certainly do not occur in the text (4 probes in flight)
+                    while (bloom && len - i >= P.seedMinLength) {
+                        const int m = min(4, len - i - P.seedMinLength + 1);
+                        unsigned long long w[4]; uint64_t mk[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            w[j] = ~0ull; mk[j] = 0;
+                            if (j < m) { uint64_t wi; bloom_slot(scan_kmer(rd, len, i + j, strand, bloomK), bloomWords, wi, mk[j]); w[j] = __ldg(bloom + wi); }
+                        }
+                        nProbe += m;
+                        int hit = m;
+#pragma unroll
+                        for (int j = 3; j >= 0; --j) if (j < m && (w[j] & mk[j]) == mk[j]) hit = j;
+                        i += hit;
+                        if (hit < m) break;
+                    }
                     if (len - i < P.seedMinLength) { step = false; emit = true; x = strand ? len - seed_len : 0; done = true; }
                     else {
                         uint32_t key = lkt_key(rd, len, i, strand);
@@ -101,21 +206,33 @@ k_mmp(MpIndexView ix, const uint32_t *__restrict__ reads, const uint32_t *__rest
                 } else {
                     uint32_t c = strand ? 3 - read_base(rd, i) : read_base(rd, len - 1 - i);
                     uint64_t a = l - (l > ix.inverseSa0), b = (r + 1) - ((r + 1) > ix.inverseSa0);
-                    uint64_t ba = a / MP_BLK_SYMS, bb = b / MP_BLK_SYMS;
-                    uint32_t oa = (uint32_t)(a - ba * MP_BLK_SYMS), ob = (uint32_t)(b - bb * MP_BLK_SYMS);
-                    uint4 va = __ldg(ix.blocks + ba * 4 + sub);
-                    uint4 vb = __ldg(ix.blocks + bb * 4 + sub);
-                    uint32_t pa = quad_partial(va, sub, c, oa), pb = quad_partial(vb, sub, c, ob);
-                    pa += __shfl_xor_sync(qmask, pa, 1); pb += __shfl_xor_sync(qmask, pb, 1);
-                    pa += __shfl_xor_sync(qmask, pa, 2); pb += __shfl_xor_sync(qmask, pb, 2);
-                    nextl = mp_cum(ix, c) + __ldg(ix.super + (ba >> MP_SUPER_SHIFT) * 4 + c) + pa + 1;
-                    nextr = mp_cum(ix, c) + __ldg(ix.super + (bb >> MP_SUPER_SHIFT) * 4 + c) + pb;
+                    uint64_t ra, rb;
+                    occ_pair(ix, a, b, c, ra, rb);
+                    nextl = mp_cum(ix, c) + ra + 1;
+                    nextr = mp_cum(ix, c) + rb;
                     nOcc += 2;
                 }
                 if (step) {
                     if (nextl <= nextr) {
                         if (seed_len >= P.seedMinLength && nextr - nextl < r - l) { last_r = r; last_l = l; last_seed_len = seed_len; }
                         l = nextl; r = nextr; ++seed_len;
+                        if (l == r) {
+                            // ---- phase B: single suffix, extend against the text ----
+                            uint32_t steps = 0;
+                            uint64_t p = mp_sa(ix, l, &steps);
+                            ++nSaIn; nLfIn += steps;
+                            int ii = i + 1;
+                            while (ii < len) {
+                                uint32_t c = strand ? 3 - read_base(rd, ii) : read_base(rd, len - 1 - ii);
+                                nOcc += 2; ++nText;
+                                if (p == 0 || mp_text_base(ix, p - 1) != c) break;
+                                --p; ++seed_len; ++ii;
+                            }
+                            i = ii;
+                            emit = true; resolved = true; textPos = p;
+                            x = strand ? i - seed_len : len - i;
+                            if (i >= len) done = true;
+                        }
                     } else { emit = true; x = strand ? i - seed_len : len - i; }
                 }
             } else { emit = true; x = strand ? len - seed_len : 0; done = true; }
@@ -128,23 +245,20 @@ k_mmp(MpIndexView ix, const uint32_t *__restrict__ reads, const uint32_t *__rest
                          seed_len * P.reseedRLTratio < (double)last_seed_len)) {
                         diff = seed_len - last_seed_len;
                         l = last_l; r = last_r; seed_len = last_seed_len;
+                        resolved = false;
                     }
-                    uint64_t d = r - l; if (d > (uint64_t)P.seedSAsizeThreshold) d = P.seedSAsizeThreshold;
+                    uint64_t d = resolved ? 0 : r - l; if (d > (uint64_t)P.seedSAsizeThreshold) d = P.seedSAsizeThreshold;
                     uint32_t cnt = (uint32_t)d + 1;
-                    uint32_t slot = 0, hb = 0;
-                    if (sub == 0) {
-                        slot = (uint32_t)atomicAdd(&counters[0], 1ull);
-                        hb = (uint32_t)atomicAdd(&counters[1], (unsigned long long)cnt);
-                        atomicAdd(&hitsPerRead[read], cnt);
-                        if (slot < capSeeds) {
-                            MpSeed sd; sd.sa_l = l; sd.strandIdx = s; sd.hitBase = hb;
-                            sd.query_offset = (uint16_t)(x & 0x3ff); sd.seed_len = (uint16_t)(seed_len & 0xfff);
-                            sd.sa_diff = (uint16_t)d; sd.pad = 0;
-                            seeds[slot] = sd;
-                        }
+                    uint32_t slot = (uint32_t)atomicAdd(&counters[0], 1ull);
+                    uint32_t hb = (uint32_t)atomicAdd(&counters[1], (unsigned long long)cnt);
+                    atomicAdd(&hitsPerRead[read], cnt);
+                    if (slot < capSeeds) {
+                        MpSeed sd; sd.sa_l = resolved ? textPos : l; sd.strandIdx = s; sd.hitBase = hb;
+                        sd.query_offset = (uint16_t)(x & 0x3ff); sd.seed_len = (uint16_t)(seed_len & 0xfff);
+                        sd.sa_diff = (uint16_t)d; sd.pad = resolved ? 1 : 0;
+                        seeds[slot] = sd;
                     }
-                    slot = __shfl_sync(qmask, slot, qbase); hb = __shfl_sync(qmask, hb, qbase);
-                    for (uint32_t k = sub; k < cnt; k += 4) if (hb + k < capStubs) stubs[hb + k] = slot;
+                    for (uint32_t k = 0; k < cnt; ++k) if (hb + k < capStubs) stubs[hb + k] = slot;
                 }
                 i -= diff;
                 i -= min(seed_len, P.seedMinLength);
@@ -153,7 +267,17 @@ k_mmp(MpIndexView ix, const uint32_t *__restrict__ reads, const uint32_t *__rest
             ++i;
         }
     }
-    if (sub == 0) { atomicAdd(&counters[2], nOcc); atomicAdd(&counters[4], nLkt); }
+    // per-warp reduction of the work counters
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        nOcc += __shfl_xor_sync(0xffffffffu, nOcc, d); nLkt += __shfl_xor_sync(0xffffffffu, nLkt, d);
+        nSaIn += __shfl_xor_sync(0xffffffffu, nSaIn, d); nLfIn += __shfl_xor_sync(0xffffffffu, nLfIn, d);
+        nProbe += __shfl_xor_sync(0xffffffffu, nProbe, d); nText += __shfl_xor_sync(0xffffffffu, nText, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&counters[2], nOcc); atomicAdd(&counters[4], nLkt); atomicAdd(&counters[7], nSaIn); atomicAdd(&counters[8], nLfIn);
+        atomicAdd(&counters[9], nProbe); atomicAdd(&counters[10], nText);
+    }
 }
 
 // ------------------------------------------------------------------------------------
@@ -168,7 +292,7 @@ __global__ void k_expand(MpIndexView ix, const MpSeed *__restrict__ seeds, const
     MpSeed sd = seeds[stubs[h]];
     uint32_t k = (uint32_t)h - sd.hitBase;
     uint32_t steps = 0;
-    uint64_t sa = mp_sa(ix, sd.sa_l + k, &steps);
+    uint64_t sa = sd.pad ? sd.sa_l : mp_sa(ix, sd.sa_l + k, &steps);     // pad = 1: text position already known (phase B of k_mmp)
     uint32_t read = sd.strandIdx >> 1, strand = sd.strandIdx & 1;
     uint32_t readLen = lens[read], off = sd.query_offset, seedlen = sd.seed_len;
     uint64_t t = strand == 0 ? sa - off : sa - (uint64_t)(uint32_t)(readLen - seedlen - off);
@@ -316,6 +440,27 @@ int mps_upload(mp_context *ctx, const uint32_t *queries, const uint32_t *readLen
     return 0;
 }
 
+// builds (once per index and K) the K-mer presence filter; MP_BLOOM=0 disables it
+static int ensure_bloom(mp_context *ctx, int seedMinLength)
+{
+    const char *e = getenv("MP_BLOOM");
+    if (e && e[0] == '0') { ctx->bloomK = 0; return 0; }
+    const int K = seedMinLength < 32 ? seedMinLength : 32;
+    const uint64_t n = ctx->ix.n;
+    if (ctx->bloomK == K && ctx->bloomFor == (const void *)ctx->ix.blocks) return 0;
+    if (n < (uint64_t)K) { ctx->bloomK = 0; return 0; }
+    uint64_t nWords = n / 4 + 1024;                      // 16 bits per text position
+    if (ctx->dBloom.reserve(nWords * 8)) return MP_ERR_CUDA;
+    MP_CUDA(cudaMemsetAsync(ctx->dBloom.p, 0, nWords * 8, ctx->stream));
+    uint64_t threads = (n + 63) / 64;
+    (++g_mp_launches), k_bloom_build<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(ctx->ix.pac, n, K, ctx->dBloom.as<unsigned long long>(), nWords);
+    MP_CUDA(cudaGetLastError());
+    MP_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->bloomK = K; ctx->bloomWords = nWords; ctx->bloomFor = (const void *)ctx->ix.blocks;
+    ctx->hbmBytes += ctx->dBloom.cap;
+    return 0;
+}
+
 int mps_seed_pairs(mp_context *ctx, const mp_align_params *AP)
 {
     const mp_mmp_params &mp = AP->mmp;
@@ -331,6 +476,7 @@ int mps_seed_pairs(mp_context *ctx, const mp_align_params *AP)
         ctx->dNPos.reserve((size_t)nReads * 4) || ctx->dNNeg.reserve((size_t)nReads * 4)) return MP_ERR_CUDA;
     if (ctx->capSeeds < (uint64_t)nStrands * 4) ctx->capSeeds = (uint64_t)nStrands * 4;
     if (ctx->capStubs < (uint64_t)nStrands * 8) ctx->capStubs = (uint64_t)nStrands * 8;
+    if (int rc = ensure_bloom(ctx, P.seedMinLength)) return rc;
     unsigned long long hc[16];
     int dev = 0, nSM = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, dev);
     MP_CUDA(cudaEventRecord(ctx->ev[0], st));
@@ -339,10 +485,11 @@ int mps_seed_pairs(mp_context *ctx, const mp_align_params *AP)
         if (ctx->dSeeds.reserve(ctx->capSeeds * sizeof(MpSeed)) || ctx->dStubs.reserve(ctx->capStubs * 4)) return MP_ERR_CUDA;
         MP_CUDA(cudaMemsetAsync(ctx->dCounters.p, 0, 16 * 8, st));
         MP_CUDA(cudaMemsetAsync(ctx->dHitsPerRead.p, 0, ((size_t)nReads + 1) * 4, st));
-        // persistent grid: 6 CTAs of 256 threads per SM (register bound), quads pull work
-        (++g_mp_launches), k_mmp<<<nSM * 6, 256, 0, st>>>(ctx->ix, ctx->dReads.as<uint32_t>(), ctx->dLens.as<uint32_t>(), ctx->wpq, nStrands, P,
+        // grid-stride over read-strands; the two strands of a read sit in neighbouring lanes
+        (++g_mp_launches), k_mmp<<<nSM * 16, 128, 0, st>>>(ctx->ix, ctx->dReads.as<uint32_t>(), ctx->dLens.as<uint32_t>(), ctx->wpq, nStrands, P,
                                       ctx->dSeeds.as<MpSeed>(), ctx->dStubs.as<uint32_t>(), ctx->dCounters.as<unsigned long long>(),
-                                      ctx->dHitsPerRead.as<uint32_t>(), (uint32_t)ctx->capSeeds, (uint32_t)ctx->capStubs);
+                                      ctx->dHitsPerRead.as<uint32_t>(), (uint32_t)ctx->capSeeds, (uint32_t)ctx->capStubs,
+                                      ctx->bloomK ? ctx->dBloom.as<unsigned long long>() : nullptr, ctx->bloomWords, ctx->bloomK);
         MP_CUDA(cudaGetLastError());
         MP_CUDA(cudaMemcpyAsync(hc, ctx->dCounters.p, 16 * 8, cudaMemcpyDeviceToHost, st));
         MP_CUDA(cudaStreamSynchronize(st));
