@@ -88,7 +88,7 @@ struct mp_context {
     uint64_t capSeeds = 0, capStubs = 0;
     mp_align_params seedParams;
     // DP
-    DevBuf dTasks, dRefSeq, dReadSeq, dTable, dPattern, dDpOut;
+    DevBuf dTasks, dRefSeq, dReadSeq, dTable, dFill, dPattern, dDpOut;
     DevBuf dLT, dRT, dLO, dRO, dLP, dRP, dOk, dBytes, dIdx, dOff, dRes, dCig;   // stage S1 chunk buffers (kept across calls)
     // results (host, owned until release)
     std::vector<mp_pair_result> hPairs, hRescued;

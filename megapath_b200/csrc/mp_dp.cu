@@ -6,197 +6,288 @@
 //
 // The reference encodes the recurrence as 8-bit saturating deltas with "score trimming";
 // observable results equal the plain recurrence below (oracle/mp_oracle_dp.cpp,
-// checked against the reference's own callDP).  Integer ALU work, no tensor cores.
+// checked against the reference's own callDP).  Integer ALU / DPX work, no tensor cores.
 //
-// k_dp<K>: one warp per task.  Lane l owns read columns l*K+1 .. l*K+K in registers and walks
-// the reference rows with a one-row skew per lane (anti-diagonal wavefront); the right-most
-// H / I of a lane's strip and the row's reference base travel to lane l+1 in one shuffle.
-// Every cell leaves one traceback byte  (H-Hdiag-mm)*42 + (H-Hleft-open)*3 + flag
-// (flag 0 = raised by the clip floor, 1 = D==H, 2 = otherwise -- same information the
-// reference keeps, CPU_DP.cpp:183, 529-533) in a step-major table so that a warp's stores of
-// one step are one contiguous 32*SLOT-byte segment.  The warp then back-tracks its own table.
+// k_dp_fill<K>: one warp per PAIR of tasks.  The two tasks travel in the low and high 16-bit halves of
+// every register, so each recurrence step is one packed DPX instruction for both (VIADDMNMX.U16x2,
+// VIMNMX3.U16x2, VIMNMX.U16x2); scores carry a +16384 bias so that unsigned halves never borrow.
+// Lane l owns read columns l*K+1 .. l*K+K and walks the reference rows with a one-row skew per lane
+// (anti-diagonal wavefront); the right-most H / I of a lane's strip travel to lane l+1 by shuffle, the
+// reference rows come from shared memory.  Every cell leaves one traceback byte
+//    (H-Hdiag-mm)*42 + (H-Hleft-open)*3 + flag      flag 0 = raised by the clip floor, 1 = D==H, 2 = otherwise
+// (the information the reference keeps, CPU_DP.cpp:183, 529-533) in a step-major table in HBM:
+// a warp's stores of one step are one contiguous 128-byte (+32-byte) segment per task.
+// The answer cell (first strict maximum in row-major order, tie count, CPU_DP.cpp:545-590) is kept per
+// column in packed registers and reduced across the warp at the end.
+// k_dp_tb<K>: one thread per task walks its own table (GPUBacktrack, CPU_DP.cpp:622-786) -- thousands of
+// independent walks in flight hide the dependent-load latency that a single walking lane cannot.
 #include "mp_context.h"
+#include <algorithm>
 
-#define DP_NEG (-20000)
-
-template <int K> struct Slot { static const int BYTES = K <= 4 ? 4 : (K <= 8 ? 8 : 16); };
+#define DP_BIAS   0x4000
+#define DP_BIAS2  0x40004000u
+#define DP_ONE2   0x00010001u
+#define DP_NEG2   0x20C020C0u      /* (bias - 8000) in both halves: "minus infinity" that never underflows */
 
 __device__ __forceinline__ int h0_value(int j, int clipLt, int open)       // row 0 (CPU_DP.cpp:397-429)
 {
     return j <= clipLt ? 0 : open - (j - clipLt - 1);
 }
+__device__ __forceinline__ uint32_t pack2(int v) { return ((uint32_t)v & 0xffffu) * 0x00010001u; }
 
-struct CellInfo { int dd, hd, flag; };   // H - Hdiag, H - Hleft, flag
+struct FillOut { int32_t score; uint32_t row, col, cnt; };
 
+// byte offset of the trace cell (row r >= 1, column c >= 1) inside one task's table of S steps
 template <int K>
-__device__ __forceinline__ uint8_t load_cell(const uint8_t *__restrict__ tab, int r, int c)
+__device__ __forceinline__ size_t cell_offset(int r, int c, int S)
 {
-    int lane = (c - 1) / K, k = (c - 1) - lane * K;
-    return tab[((size_t)(r + lane) * 32 + lane) * Slot<K>::BYTES + k];
+    const int lane = (c - 1) / K, k = (c - 1) - lane * K, t = r + lane;
+    const int words = K / 4, rem = K % 4;
+    if (k < 4 * words) return (size_t)(k >> 2) * S * 128 + (size_t)t * 128 + lane * 4 + (k & 3);
+    return (size_t)words * S * 128 + ((size_t)t * 32 + lane) * rem + (k - 4 * words);
+}
+template <int K>
+__device__ __forceinline__ uint8_t load_cell(const uint8_t *__restrict__ tab, int r, int c, int S)
+{
+    return tab[cell_offset<K>(r, c, S)];
 }
 // flag of any cell including the virtual row 0 / column 0
 template <int K>
-__device__ __forceinline__ int cell_flag(const uint8_t *__restrict__ tab, int r, int c, int clipLt)
+__device__ __forceinline__ int cell_flag(const uint8_t *__restrict__ tab, int r, int c, int clipLt, int S)
 {
     if (c == 0) return 0;                       // column 0 cells are stored as 0 (CPU_DP.cpp:447-450)
     if (r == 0) return c <= clipLt ? 0 : 1;     // row 0 (CPU_DP.cpp:405-427)
-    return load_cell<K>(tab, r, c) % 3;
+    return load_cell<K>(tab, r, c, S) % 3;
 }
 // H[r][c] - H[r][c-1] for any row including row 0
 template <int K>
-__device__ __forceinline__ int cell_hd(const uint8_t *__restrict__ tab, int r, int c, int clipLt, int open)
+__device__ __forceinline__ int cell_hd(const uint8_t *__restrict__ tab, int r, int c, int clipLt, int open, int S)
 {
     if (r == 0) return h0_value(c, clipLt, open) - h0_value(c - 1, clipLt, open);
-    return open + (int)(load_cell<K>(tab, r, c) / 3 % 14);
+    return open + (int)(load_cell<K>(tab, r, c, S) / 3 % 14);
 }
 
 template <int K>
 __global__ void __launch_bounds__(128)
-k_dp(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLens, uint32_t refStride,
-     const uint8_t *__restrict__ readSeq, const uint32_t *__restrict__ readLens, uint32_t readStride,
-     const int32_t *__restrict__ cutoffs, uint32_t nTasks, MpDpParams P,
-     uint8_t *__restrict__ tables, size_t tableStride, MpDpOut *__restrict__ outs,
-     uint8_t *__restrict__ patterns, uint32_t patStride)
+k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLens, uint32_t refStride,
+          const uint8_t *__restrict__ readSeq, const uint32_t *__restrict__ readLens, uint32_t readStride,
+          const int32_t *__restrict__ cutoffs, uint32_t taskBase, uint32_t nTasks, MpDpParams P,
+          uint8_t *__restrict__ tables, size_t tableStride, int S, FillOut *__restrict__ fill)
 {
-    const int SLOT = Slot<K>::BYTES;
-    const int lane = threadIdx.x & 31;
-    const uint32_t warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t warpId = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int mm = P.mismatch, open = P.open, ext = -1, clipLt = P.clipLt;
-    uint8_t *tab = tables + (size_t)warpId * tableStride;
-
-    for (uint32_t task = warpId; task < nTasks; task += warpsPerGrid) {
-        const int N = (int)refLens[task], L = (int)readLens[task], cutoff = cutoffs[task];
-        MpDpOut o; o.score = 0; o.hitLoc = 0; o.count = 0; o.patLen = 0;
-        uint8_t *pat = patterns + (size_t)task * patStride;
-        // CPU_DP.cpp:296-324: outside these bounds the reference aborts the SIMD group
-        if (cutoff > L || cutoff <= 0 || L >= 255 + open - 1 + cutoff || L > 32 * K) {
-            if (lane == 0) outs[task] = o;
-            continue;
+    extern __shared__ uint32_t refShared[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t pairId = blockIdx.x * 4 + wib;
+    const uint32_t lA = pairId * 2, lB = lA + 1;             // task slots inside this launch
+    if (lA >= nTasks) return;
+    const uint32_t tA = taskBase + lA, tB = taskBase + lB;
+    const bool hasB = lB < nTasks;
+    const int mm = P.mismatch, open = P.open, clipLt = P.clipLt;
+    int NA = (int)refLens[tA], LA = (int)readLens[tA], cutA = cutoffs[tA];
+    int NB = hasB ? (int)refLens[tB] : 0, LB = hasB ? (int)readLens[tB] : 0, cutB = hasB ? cutoffs[tB] : 0;
+    // CPU_DP.cpp:296-324: outside these bounds the reference aborts the SIMD group
+    const bool okA = !(cutA > LA || cutA <= 0 || LA >= 255 + open - 1 + cutA || LA > 32 * K);
+    const bool okB = hasB && !(cutB > LB || cutB <= 0 || LB >= 255 + open - 1 + cutB || LB > 32 * K);
+    if (!okA) { NA = 0; LA = 0; }
+    if (!okB) { NB = 0; LB = 0; }
+    const int maxN = max(NA, NB), maxL = max(LA, LB);
+    uint32_t *refS = refShared + (size_t)wib * S;
+    {
+        const uint8_t *fa = refSeq + (size_t)tA * refStride, *fb = refSeq + (size_t)tB * refStride;
+        for (int r = lane; r < maxN; r += 32) {
+            uint32_t a = r < NA ? fa[r] : 4u, b = r < NB ? fb[r] : 4u;
+            refS[r] = a | (b << 16);
         }
-        const uint8_t *rs = readSeq + (size_t)task * readStride;
-        const uint8_t *fs = refSeq + (size_t)task * refStride;
-        const int j0 = lane * K + 1;
-        int rb[K], Hp[K], Dp[K];
+    }
+    __syncwarp();
+    const uint8_t *ra = readSeq + (size_t)tA * readStride, *rbp = readSeq + (size_t)tB * readStride;
+    const int j0 = lane * K + 1;
+    const int minColA = max(LA - P.clipRt, 1), minColB = max(LB - P.clipRt, 1);
+    uint32_t rb[K], Hp[K], Dp[K], fl[K], el[K], bestH[K], bestRow[K], cnt[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            int j = j0 + k;
-            rb[k] = j <= L ? (int)rs[j - 1] : 8;
-            Hp[k] = h0_value(j, clipLt, open);
-            Dp[k] = DP_NEG;
-        }
-        int prevHleft = h0_value(j0 - 1, clipLt, open);      // H[i-1][j0-1]
-        const int minCol = max(L - P.clipRt, 1);
-        int best = cutoff - 1, bestRow = 0, bestCol = 0, cnt = 0;
-        uint32_t sendHI = 0; int sendRef = 4;
-        const int steps = N + 31;
-        for (int t = 1; t <= steps; ++t) {
-            uint32_t rHI = __shfl_up_sync(0xffffffffu, sendHI, 1);
-            int rRef = __shfl_up_sync(0xffffffffu, sendRef, 1);
-            const int i = t - lane;
-            int Hleft, Il, refc;
-            if (lane == 0) { Hleft = 0; Il = DP_NEG; refc = t <= N ? (int)fs[t - 1] : 4; }
-            else { Hleft = (int)(int16_t)(rHI & 0xffff); Il = (int)(int16_t)(rHI >> 16); refc = rRef; }
-            if (i >= 1 && i <= N) {
-                int Hdiag = prevHleft;
-                prevHleft = Hleft;
-                uint32_t lo = 0, hi = 0, hi2 = 0;
+    for (int k = 0; k < K; ++k) {
+        const int j = j0 + k;
+        uint32_t a = j <= LA ? ra[j - 1] : 8u, b = j <= LB ? rbp[j - 1] : 8u;
+        rb[k] = a | (b << 16);
+        Hp[k] = pack2(h0_value(j, clipLt, open) + DP_BIAS);
+        Dp[k] = DP_NEG2;
+        fl[k] = j <= clipLt ? DP_BIAS2 : 0u;
+        el[k] = ((j >= minColA && j <= LA) ? 0x0000FFFFu : 0u) | ((j >= minColB && j <= LB) ? 0xFFFF0000u : 0u);
+        bestH[k] = 0; bestRow[k] = 0; cnt[k] = 0;
+    }
+    uint32_t prevHleft = pack2(h0_value(j0 - 1, clipLt, open) + DP_BIAS);
+    const uint32_t OPENABS2 = pack2(-open), MMABS2 = pack2(-mm), MINUS1 = 0xFFFFFFFFu;
+    const uint32_t DELTA = (uint32_t)(1 - mm);                 // match score - mismatch score
+    uint8_t *tabA = tables + (size_t)lA * tableStride, *tabB = tabA + tableStride;
+    constexpr int WORDS = K / 4, REM = K % 4;
+    uint32_t sendH = 0, sendI = 0;
+    const int lastLane = maxL > 0 ? (maxL - 1) / K : 0;
+    const int steps = maxN + lastLane;
+    const bool laneActive = j0 <= maxL;
+    for (int t = 1; t <= steps; ++t) {
+        const uint32_t rH = __shfl_up_sync(0xffffffffu, sendH, 1);
+        const uint32_t rI = __shfl_up_sync(0xffffffffu, sendI, 1);
+        const int i = t - lane;
+        if (laneActive && i >= 1 && i <= maxN) {
+            uint32_t Hleft = lane == 0 ? DP_BIAS2 : rH;
+            uint32_t Il = lane == 0 ? DP_NEG2 : rI;
+            const uint32_t ref2 = refS[i - 1];
+            const uint32_t rowMask = (i <= NA ? 0x0000FFFFu : 0u) | (i <= NB ? 0xFFFF0000u : 0u);
+            const uint32_t row2 = (uint32_t)i * 0x00010001u;
+            uint32_t Hdiag = prevHleft;
+            prevHleft = Hleft;
+            uint32_t code[K];
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const int j = j0 + k;
-                    int s = (refc == rb[k]) ? 1 : mm;
-                    int d = max(Dp[k] + ext, Hp[k] + open);
-                    Il = max(Il + ext, Hleft + open);
-                    int h = max(Hdiag + s, max(d, Il));
-                    int flag = (d == h) ? 1 : 2;
-                    if (j <= clipLt && h < 0) { h = 0; flag = 0; }                   // CPU_DP.cpp:505-510
-                    uint32_t code = (uint32_t)((h - Hdiag - mm) * 42 + (h - Hleft - open) * 3 + flag);
-                    if (k < 4) lo |= code << (8 * k); else if (k < 8) hi |= code << (8 * (k - 4)); else hi2 |= code << (8 * (k - 8));
-                    if (h >= cutoff && j >= minCol && j <= L) {                      // CPU_DP.cpp:545-590
-                        if (h > best) { best = h; bestRow = i; bestCol = j; cnt = 1; }
-                        else if (h == best) ++cnt;
-                    }
-                    Hdiag = Hp[k]; Hp[k] = h; Dp[k] = d; Hleft = h;
-                }
-                uint8_t *dst = tab + ((size_t)t * 32 + lane) * SLOT;
-                if (SLOT == 4) *(uint32_t *)dst = lo;
-                else if (SLOT == 8) *(uint2 *)dst = make_uint2(lo, hi);
-                else *(uint4 *)dst = make_uint4(lo, hi, hi2, 0);
-                sendHI = ((uint32_t)Hleft & 0xffffu) | ((uint32_t)max(Il, -20000) << 16);
-                sendRef = refc;
+            for (int k = 0; k < K; ++k) {
+                const uint32_t m = __vminu2(ref2 ^ rb[k], DP_ONE2);               // 1 where the bases differ
+                const uint32_t hs = Hdiag + DP_ONE2 - m * DELTA;                  // Hdiag + s(i,j)
+                const uint32_t t1 = Hp[k] - OPENABS2;
+                const uint32_t d = __viaddmax_u16x2(Dp[k], MINUS1, t1);           // max(D + ext, Hup + open)
+                const uint32_t t2 = Hleft - OPENABS2;
+                Il = __viaddmax_u16x2(Il, MINUS1, t2);                            // max(I + ext, Hleft + open)
+                const uint32_t h = __vimax3_u16x2(hs, d, Il);
+                const uint32_t hf = __vmaxu2(h, fl[k]);                           // clip floor for j <= clipLt (CPU_DP.cpp:505-510)
+                const uint32_t a = hf - Hdiag + MMABS2;                           // H - Hdiag - mm   >= 0
+                const uint32_t b = hf - t2;                                       // H - Hleft - open >= 0
+                const uint32_t zd = __vminu2(hf - d, DP_ONE2);                    // 0 where D == H
+                const uint32_t zr = __vminu2(hf - h, DP_ONE2);                    // 1 where the floor raised the cell
+                const uint32_t flag = DP_ONE2 + zd - 2u * zr;
+                code[k] = a * 42u + b * 3u + flag;
+                // answer cell per column: first strict maximum, ties counted (CPU_DP.cpp:545-590)
+                const uint32_t hE = hf & el[k] & rowMask;
+                const uint32_t nb = __vmaxu2(bestH[k], hE);
+                const uint32_t msk = __vminu2(nb - bestH[k], DP_ONE2) * 0xFFFFu;  // halves that improved
+                bestRow[k] = (bestRow[k] & ~msk) | (row2 & msk);
+                cnt[k] = (cnt[k] & ~msk) + (DP_ONE2 - __vminu2(nb - hE, DP_ONE2));
+                bestH[k] = nb;
+                Hdiag = Hp[k]; Hp[k] = hf; Dp[k] = d; Hleft = hf;
             }
+            // trace bytes: low halves -> task A, high halves -> task B
+#pragma unroll
+            for (int w = 0; w < WORDS; ++w) {
+                const uint32_t p01 = __byte_perm(code[4 * w], code[4 * w + 1], 0x6240), p23 = __byte_perm(code[4 * w + 2], code[4 * w + 3], 0x6240);
+                // p01 bytes: [c0.lo, c1.lo, c0.hi, c1.hi]
+                const uint32_t wa = __byte_perm(p01, p23, 0x5410), wb = __byte_perm(p01, p23, 0x7632);
+                const size_t off = (size_t)w * S * 128 + (size_t)t * 128 + lane * 4;
+                *(uint32_t *)(tabA + off) = wa;
+                if (hasB) *(uint32_t *)(tabB + off) = wb;
+            }
+            if (REM == 1) {
+                const size_t off = (size_t)WORDS * S * 128 + (size_t)t * 32 + lane;
+                tabA[off] = (uint8_t)code[K - 1];
+                if (hasB) tabB[off] = (uint8_t)(code[K - 1] >> 16);
+            } else if (REM == 2) {
+                const size_t off = (size_t)WORDS * S * 128 + ((size_t)t * 32 + lane) * 2;
+                *(uint16_t *)(tabA + off) = (uint16_t)((code[K - 2] & 0xff) | ((code[K - 1] & 0xff) << 8));
+                if (hasB) *(uint16_t *)(tabB + off) = (uint16_t)(((code[K - 2] >> 16) & 0xff) | (((code[K - 1] >> 16) & 0xff) << 8));
+            }
+            sendH = Hleft; sendI = Il;
         }
-        // ---- winner: max score, then smallest (row, col); ties counted (CPU_DP.cpp:569-590) ----
+    }
+    // ---- winner per task: max score, then smallest (row, col); ties summed ----
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int sh = half * 16;
+        int best = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) best = max(best, (int)((bestH[k] >> sh) & 0xffffu));
         int gbest = best;
 #pragma unroll
-        for (int d = 16; d; d >>= 1) gbest = max(gbest, __shfl_xor_sync(0xffffffffu, gbest, d));
-        if (gbest < cutoff) { if (lane == 0) outs[task] = o; __syncwarp(); continue; }
-        uint32_t key = best == gbest ? ((uint32_t)bestRow << 12) | (uint32_t)bestCol : 0xffffffffu;
-        int c2 = best == gbest ? cnt : 0;
+        for (int dlt = 16; dlt; dlt >>= 1) gbest = max(gbest, __shfl_xor_sync(0xffffffffu, gbest, dlt));
+        uint32_t key = 0xffffffffu; uint32_t c2 = 0;
 #pragma unroll
-        for (int d = 16; d; d >>= 1) { key = min(key, __shfl_xor_sync(0xffffffffu, key, d)); c2 += __shfl_xor_sync(0xffffffffu, c2, d); }
-        __syncwarp();
-        if (lane == 0) {
-            // ---- GPUBacktrack (CPU_DP.cpp:622-786), literal ----
-            const int hitRow = (int)(key >> 12), hitCol = (int)(key & 0xfff);
-            o.score = gbest; o.count = min(c2, 255);
-            uint32_t p = 0;
-            int clipR = L - hitCol;
-            if (clipR > 0) { pat[p++] = 'S'; pat[p++] = 'V'; pat[p++] = (uint8_t)clipR; }
-            int i = L - clipR, j = hitRow;
-            enum { NORMAL, I_EXT, D_EXT, SM_EXIT, SI_EXIT, SD_EXIT };
-            int state = NORMAL;
-            int accum = 0;
-            while (i > 0 && j > 0) {
-                uint32_t cell = load_cell<K>(tab, j, i);
-                int flag = cell % 3;
-                int hd = open + (int)(cell / 3 % 14);
-                int dd = mm + (int)(cell / 42);
-                int vd = dd - cell_hd<K>(tab, j - 1, i, clipLt, open);
-                bool eq = fs[j - 1] == rs[i - 1];
-                int ms = eq ? 1 : mm;
-                if (state == NORMAL) {
-                    if (dd == ms && i != 1 && cell_flag<K>(tab, j - 1, i - 1, clipLt) == 0) { state = SM_EXIT; break; }
-                    else if (dd == ms) { pat[p++] = eq ? 'M' : 'm'; --j; --i; }
-                    else if (flag == 1) {
-                        pat[p++] = 'D'; --j;
-                        if (vd != open) { accum = (int8_t)(vd - ext); state = D_EXT; }
-                    } else {
-                        pat[p++] = 'I'; --i;
-                        if (hd != open) { accum = (int8_t)(hd - ext); state = I_EXT; }
-                    }
-                } else if (state == D_EXT) {
-                    if (vd + accum == open && cell_flag<K>(tab, j - 1, i, clipLt) == 0) { state = SD_EXIT; break; }
-                    pat[p++] = 'D'; --j;
-                    if (vd + accum == open) state = NORMAL; else accum = (int8_t)(accum + vd - ext);
-                } else {
-                    if (hd + accum == open && cell_flag<K>(tab, j, i - 1, clipLt) == 0) { state = SI_EXIT; break; }
-                    pat[p++] = 'I'; --i;
-                    if (hd + accum == open) state = NORMAL; else accum = (int8_t)(accum + hd - ext);
-                }
+        for (int k = 0; k < K; ++k)
+            if ((int)((bestH[k] >> sh) & 0xffffu) == gbest) {
+                key = min(key, (((bestRow[k] >> sh) & 0xffffu) << 12) | (uint32_t)(j0 + k));
+                c2 += (cnt[k] >> sh) & 0xffffu;
             }
-            bool discard = false;
-            if (j == 0) {
-                int sc = min(clipLt & 0xff, i);
-                if (sc < i) { pat[p++] = 'I'; pat[p++] = 'V'; pat[p++] = (uint8_t)(i - sc); }
-                pat[p++] = 'S'; pat[p++] = 'V'; pat[p++] = (uint8_t)sc;
-            } else if (state == SI_EXIT) {
-                pat[p++] = 'I'; pat[p++] = 'S'; pat[p++] = 'V'; pat[p++] = (uint8_t)(i - 1);
-            } else if (state == SD_EXIT) {
-                pat[p++] = 'D'; pat[p++] = 'S'; pat[p++] = 'V'; pat[p++] = (uint8_t)(i - 1);
-                discard = true;                                   // CPU_DP.cpp:842-857
-            } else if (state == SM_EXIT) {
-                pat[p++] = (fs[j - 1] == rs[i - 1]) ? 'M' : 'm';
-                pat[p++] = 'S'; pat[p++] = 'V'; pat[p++] = (uint8_t)(i - 1);
-                j -= 1;
-            }
-            pat[p] = 0;
-            o.patLen = p;
-            if (discard) { o.score = 0; o.hitLoc = 0; } else o.hitLoc = (uint32_t)j;
-            outs[task] = o;
+#pragma unroll
+        for (int dlt = 16; dlt; dlt >>= 1) { key = min(key, __shfl_xor_sync(0xffffffffu, key, dlt)); c2 += __shfl_xor_sync(0xffffffffu, c2, dlt); }
+        if (lane == 0 && (half == 0 || hasB)) {
+            FillOut f; f.score = gbest - DP_BIAS; f.row = key >> 12; f.col = key & 0xfffu; f.cnt = c2;
+            if (gbest == 0) { f.score = 0; f.row = 0; f.col = 0; f.cnt = 0; }
+            fill[half == 0 ? tA : tB] = f;
         }
-        __syncwarp();
     }
+}
+
+// ---- GPUBacktrack (CPU_DP.cpp:622-786), literal; one thread per task ----
+template <int K>
+__global__ void __launch_bounds__(128)
+k_dp_tb(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLens, uint32_t refStride,
+        const uint8_t *__restrict__ readSeq, const uint32_t *__restrict__ readLens, uint32_t readStride,
+        const int32_t *__restrict__ cutoffs, uint32_t taskBase, uint32_t nTasks, MpDpParams P,
+        const uint8_t *__restrict__ tables, size_t tableStride, int S, const FillOut *__restrict__ fill,
+        MpDpOut *__restrict__ outs, uint8_t *__restrict__ patterns, uint32_t patStride)
+{
+    const uint32_t lt = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lt >= nTasks) return;
+    const uint32_t task = taskBase + lt;
+    const int L = (int)readLens[task], cutoff = cutoffs[task];
+    const int mm = P.mismatch, open = P.open, ext = -1, clipLt = P.clipLt;
+    MpDpOut o; o.score = 0; o.hitLoc = 0; o.count = 0; o.patLen = 0;
+    const FillOut f = fill[task];
+    if (cutoff > L || cutoff <= 0 || L >= 255 + open - 1 + cutoff || L > 32 * K || f.score < cutoff) { outs[task] = o; return; }
+    const uint8_t *tab = tables + (size_t)lt * tableStride;
+    const uint8_t *rs = readSeq + (size_t)task * readStride;
+    const uint8_t *fs = refSeq + (size_t)task * refStride;
+    uint8_t *pat = patterns + (size_t)task * patStride;
+    const int hitRow = (int)f.row, hitCol = (int)f.col;
+    o.score = f.score; o.count = min(f.cnt, 255u);
+    uint32_t p = 0;
+    int clipR = L - hitCol;
+    if (clipR > 0) { pat[p++] = 'S'; pat[p++] = 'V'; pat[p++] = (uint8_t)clipR; }
+    int i = L - clipR, j = hitRow;
+    enum { NORMAL, I_EXT, D_EXT, SM_EXIT, SI_EXIT, SD_EXIT };
+    int state = NORMAL;
+    int accum = 0;
+    while (i > 0 && j > 0) {
+        uint32_t cell = load_cell<K>(tab, j, i, S);
+        int flag = cell % 3;
+        int hd = open + (int)(cell / 3 % 14);
+        int dd = mm + (int)(cell / 42);
+        bool eq = fs[j - 1] == rs[i - 1];
+        int ms = eq ? 1 : mm;
+        if (state == NORMAL) {
+            if (dd == ms && i != 1 && cell_flag<K>(tab, j - 1, i - 1, clipLt, S) == 0) { state = SM_EXIT; break; }
+            else if (dd == ms) { pat[p++] = eq ? 'M' : 'm'; --j; --i; }
+            else if (flag == 1) {
+                int vd = dd - cell_hd<K>(tab, j - 1, i, clipLt, open, S);
+                pat[p++] = 'D'; --j;
+                if (vd != open) { accum = (int8_t)(vd - ext); state = D_EXT; }
+            } else {
+                pat[p++] = 'I'; --i;
+                if (hd != open) { accum = (int8_t)(hd - ext); state = I_EXT; }
+            }
+        } else if (state == D_EXT) {
+            int vd = dd - cell_hd<K>(tab, j - 1, i, clipLt, open, S);
+            if (vd + accum == open && cell_flag<K>(tab, j - 1, i, clipLt, S) == 0) { state = SD_EXIT; break; }
+            pat[p++] = 'D'; --j;
+            if (vd + accum == open) state = NORMAL; else accum = (int8_t)(accum + vd - ext);
+        } else {
+            if (hd + accum == open && cell_flag<K>(tab, j, i - 1, clipLt, S) == 0) { state = SI_EXIT; break; }
+            pat[p++] = 'I'; --i;
+            if (hd + accum == open) state = NORMAL; else accum = (int8_t)(accum + hd - ext);
+        }
+    }
+    bool discard = false;
+    if (j == 0) {
+        int sc = min(clipLt & 0xff, i);
+        if (sc < i) { pat[p++] = 'I'; pat[p++] = 'V'; pat[p++] = (uint8_t)(i - sc); }
+        pat[p++] = 'S'; pat[p++] = 'V'; pat[p++] = (uint8_t)sc;
+    } else if (state == SI_EXIT) {
+        pat[p++] = 'I'; pat[p++] = 'S'; pat[p++] = 'V'; pat[p++] = (uint8_t)(i - 1);
+    } else if (state == SD_EXIT) {
+        pat[p++] = 'D'; pat[p++] = 'S'; pat[p++] = 'V'; pat[p++] = (uint8_t)(i - 1);
+        discard = true;                                   // CPU_DP.cpp:842-857
+    } else if (state == SM_EXIT) {
+        pat[p++] = (fs[j - 1] == rs[i - 1]) ? 'M' : 'm';
+        pat[p++] = 'S'; pat[p++] = 'V'; pat[p++] = (uint8_t)(i - 1);
+        j -= 1;
+    }
+    pat[p] = 0;
+    o.patLen = p;
+    if (discard) { o.score = 0; o.hitLoc = 0; } else o.hitLoc = (uint32_t)j;
+    outs[task] = o;
 }
 
 // ------------------------------------------------------------------------------------
@@ -227,25 +318,34 @@ static int launch_dp(mp_context *ctx, const uint8_t *dRef, const uint32_t *dRefL
                      MpDpOut *dOuts, uint8_t *dPatterns, uint32_t patStride)
 {
     if (nTasks == 0) return 0;
-    int K = maxReadLen <= 128 ? 4 : maxReadLen <= 160 ? 5 : maxReadLen <= 256 ? 8 : 10;
+    const int K = maxReadLen <= 160 ? 5 : maxReadLen <= 256 ? 8 : 10;
     if (maxReadLen > 320) { mp_set_error("read length %u exceeds the DP kernel bound 320", maxReadLen); return MP_ERR_ARG; }
-    int slot = K <= 4 ? 4 : (K <= 8 ? 8 : 16);
-    int dev = 0, nSM = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, dev);
-    size_t tableStride = ((size_t)maxRefLen + 34) * 32 * slot;
-    // persistent grid: 4 warps per CTA, up to 8 CTAs per SM, bounded by the task count and by table memory
-    uint32_t warps = (uint32_t)nSM * 8 * 4;
-    if (warps > nTasks) warps = (nTasks + 3) / 4 * 4;
+    const int S = (int)maxRefLen + 33;                        // steps 1 .. maxRefLen + 31, plus slack
+    const size_t tableStride = (size_t)S * 32 * K;
+    if (ctx->dFill.reserve((size_t)nTasks * sizeof(FillOut))) return MP_ERR_CUDA;
+    // the traceback tables of one sub-batch stay in HBM between the two kernels
     size_t freeB = 0, totalB = 0; cudaMemGetInfo(&freeB, &totalB);
-    size_t budget = ctx->dTable.cap > freeB / 2 ? ctx->dTable.cap : freeB / 2;
-    while ((size_t)warps * tableStride > budget && warps > 4) warps = (warps / 2 + 3) / 4 * 4;
-    if (ctx->dTable.reserve((size_t)warps * tableStride)) return MP_ERR_CUDA;
-    dim3 grid(warps / 4), block(128);
+    const size_t maxBytes = std::min<size_t>((size_t)24 << 30, (freeB + ctx->dTable.cap) / 2);
+    const size_t want = std::min<size_t>((size_t)nTasks * tableStride, maxBytes);
+    if (ctx->dTable.cap < want && ctx->dTable.reserve(want)) return MP_ERR_CUDA;
+    uint32_t per = (uint32_t)std::min<size_t>(nTasks, ctx->dTable.cap / tableStride);
+    if (per < nTasks) per &= ~1u;                              // sub-batches start on a task pair
+    if (per == 0) { mp_set_error("not enough device memory for the DP traceback tables"); return MP_ERR_CUDA; }
     uint8_t *tab = ctx->dTable.as<uint8_t>();
-#define LAUNCH(KK) (++g_mp_launches), k_dp<KK><<<grid, block, 0, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, \
-        nTasks, P, tab, tableStride, dOuts, dPatterns, patStride)
-    if (K == 4) LAUNCH(4); else if (K == 5) LAUNCH(5); else if (K == 8) LAUNCH(8); else LAUNCH(10);
+    FillOut *fill = ctx->dFill.as<FillOut>();
+    const size_t smem = (size_t)4 * S * 4;
+    for (uint32_t base = 0; base < nTasks; base += per) {
+        const uint32_t n = std::min<uint32_t>(per, nTasks - base);
+        dim3 gridF((n + 7) / 8), gridT((n + 127) / 128), block(128);
+#define LAUNCH(KK) do { \
+        (++g_mp_launches), k_dp_fill<KK><<<gridF, block, smem, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, \
+            base, n, P, tab, tableStride, S, fill); \
+        (++g_mp_launches), k_dp_tb<KK><<<gridT, block, 0, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, \
+            base, n, P, tab, tableStride, S, fill, dOuts, dPatterns, patStride); } while (0)
+        if (K == 5) LAUNCH(5); else if (K == 8) LAUNCH(8); else LAUNCH(10);
 #undef LAUNCH
-    MP_CUDA(cudaGetLastError());
+        MP_CUDA(cudaGetLastError());
+    }
     return 0;
 }
 
