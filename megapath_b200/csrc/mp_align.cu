@@ -17,11 +17,19 @@ int mps_download_seedpos(mp_context *ctx, mp_seed_pos **readPos, uint64_t *nRead
 
 
 // ---- packLeft (DV-DPfunctions.cpp:2857-2924) ----
+// adds (cells, tasks) of a warp's lanes to counters[11], counters[12] (work accounting)
+__device__ __forceinline__ void account_work(unsigned long long cells, unsigned long long tasks, unsigned long long *__restrict__ counters)
+{
+#pragma unroll
+    for (int d = 16; d; d >>= 1) { cells += __shfl_xor_sync(0xffffffffu, cells, d); tasks += __shfl_xor_sync(0xffffffffu, tasks, d); }
+    if ((threadIdx.x & 31) == 0 && tasks) { atomicAdd(&counters[11], cells); atomicAdd(&counters[12], tasks); }
+}
+
 __global__ void k_left_tasks(const mp_candidate *__restrict__ cands, uint32_t n, const uint32_t *__restrict__ lens,
-                             uint64_t fullLen, int strandLeft, MpDpTask *__restrict__ tasks)
+                             uint64_t fullLen, int strandLeft, MpDpTask *__restrict__ tasks, unsigned long long *__restrict__ counters)
 {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n) return;
+    if (c >= n) { account_work(0, 0, counters); return; }
     mp_candidate ci = cands[c];
     uint32_t readLength = lens[ci.readIDLeft];
     uint32_t margin = MP_MARGIN(readLength);
@@ -32,14 +40,15 @@ __global__ void k_left_tasks(const mp_candidate *__restrict__ cands, uint32_t n,
     MpDpTask t; t.refStart = start; t.refLen = dnaLen; t.readID = ci.readIDLeft; t.readLen = (uint16_t)readLength;
     t.strand = (uint8_t)strandLeft; t.valid = 1; t.cutoff = dp_cutoff(readLength);
     tasks[c] = t;
+    account_work((unsigned long long)dnaLen * readLength, 1, counters);
 }
 // ---- packRight (DV-DPfunctions.cpp:2926-3007) ----
 __global__ void k_right_tasks(const mp_candidate *__restrict__ cands, uint32_t n, const uint32_t *__restrict__ lens,
                               uint64_t fullLen, int strandRight, int insert_high, const MpDpTask *__restrict__ left,
-                              const MpDpOut *__restrict__ leftOut, MpDpTask *__restrict__ tasks)
+                              const MpDpOut *__restrict__ leftOut, MpDpTask *__restrict__ tasks, unsigned long long *__restrict__ counters)
 {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n) return;
+    if (c >= n) { account_work(0, 0, counters); return; }
     mp_candidate ci = cands[c];
     MpDpTask t; memset(&t, 0, sizeof t);
     if (leftOut[c].score >= left[c].cutoff) {
@@ -57,6 +66,7 @@ __global__ void k_right_tasks(const mp_candidate *__restrict__ cands, uint32_t n
         t.strand = (uint8_t)strandRight; t.valid = 1; t.cutoff = dp_cutoff(readLength);
     }
     tasks[c] = t;
+    account_work(t.valid ? (unsigned long long)t.refLen * t.readLen : 0ull, t.valid ? 1ull : 0ull, counters);
 }
 
 struct PairWork { uint32_t ok; uint32_t cigLen[2]; };
@@ -84,7 +94,8 @@ __global__ void k_assemble_write(uint32_t n, const mp_candidate *__restrict__ ca
                                  const MpDpOut *__restrict__ lo, const MpDpTask *__restrict__ rt, const MpDpOut *__restrict__ ro,
                                  const uint8_t *__restrict__ lpat, const uint8_t *__restrict__ rpat, uint32_t patStride,
                                  AsmParams A, const uint32_t *__restrict__ okFlag, const uint32_t *__restrict__ outIdx,
-                                 const uint32_t *__restrict__ cigOff, uint32_t cigBase, mp_pair_result *__restrict__ res, char *__restrict__ cig)
+                                 const uint32_t *__restrict__ cigOff, uint32_t cigBase, mp_pair_result *__restrict__ res, char *__restrict__ cig,
+                                 uint8_t *__restrict__ alignedPair)
 {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n || !okFlag[c]) return;
@@ -130,6 +141,7 @@ __global__ void k_assemble_write(uint32_t n, const mp_candidate *__restrict__ ca
     else r.insertSize = (int32_t)(r.algnmt_1 - r.algnmt_2 + (uint64_t)(int64_t)lengths_i + (uint64_t)(int64_t)DIS[1]);
     r.num_sameScore_1 = (int32_t)ou[readSide]->count; r.num_sameScore_2 = (int32_t)ou[mateSide]->count;
     res[outIdx[c]] = r;
+    alignedPair[r.readID >> 1] = 1;
 }
 
 static int scan_u32(mp_context *ctx, const uint32_t *in, uint32_t *out, uint64_t n)
@@ -170,18 +182,21 @@ static int deep_dp(mp_context *ctx, const mp_align_params *P, mp_results *out, u
         dOk.reserve(((size_t)chunkCap + 1) * 4) || dBytes.reserve(((size_t)chunkCap + 1) * 4) ||
         dIdx.reserve(((size_t)chunkCap + 1) * 4) || dOff.reserve(((size_t)chunkCap + 1) * 4) ||
         dRes.reserve((size_t)chunkCap * sizeof(mp_pair_result))) return MP_ERR_CUDA;
-    std::vector<mp_pair_result> &H = ctx->hPairs;
-    std::vector<char> &HC = ctx->hCigars;
+    PinnedBuf<mp_pair_result> &H = ctx->hPairs;
+    PinnedBuf<char> &HC = ctx->hCigars;
+    unsigned long long *dCnt = ctx->dCounters.as<unsigned long long>();
+    if (ctx->dAligned.reserve((size_t)ctx->nReads / 2 + 8)) return MP_ERR_CUDA;
+    MP_CUDA(cudaMemsetAsync(ctx->dAligned.p, 0, (size_t)ctx->nReads / 2 + 8, st));
     const uint64_t fullLen = ctx->ix.n;
     MpTrace tr;
     for (uint64_t base = 0; base < nC; base += CH) {
         uint32_t n = (uint32_t)std::min<uint64_t>(CH, nC - base);
         const mp_candidate *cands = ctx->dCands.as<mp_candidate>() + base;
         unsigned g = (n + 127) / 128;
-        (++g_mp_launches), k_left_tasks<<<g, 128, 0, st>>>(cands, n, ctx->dLens.as<uint32_t>(), fullLen, P->peStrandLeftLeg, dLT.as<MpDpTask>());
+        (++g_mp_launches), k_left_tasks<<<g, 128, 0, st>>>(cands, n, ctx->dLens.as<uint32_t>(), fullLen, P->peStrandLeftLeg, dLT.as<MpDpTask>(), dCnt);
         if (int rc = mpd_run_tasks(ctx, dLT.as<MpDpTask>(), n, maxDNALength, maxReadLength, dpl, dLO.as<MpDpOut>(), dLP.as<uint8_t>(), patStride)) return rc;
         (++g_mp_launches), k_right_tasks<<<g, 128, 0, st>>>(cands, n, ctx->dLens.as<uint32_t>(), fullLen, P->peStrandRightLeg, P->insert_high,
-                                         dLT.as<MpDpTask>(), dLO.as<MpDpOut>(), dRT.as<MpDpTask>());
+                                         dLT.as<MpDpTask>(), dLO.as<MpDpOut>(), dRT.as<MpDpTask>(), dCnt);
         if (int rc = mpd_run_tasks(ctx, dRT.as<MpDpTask>(), n, maxDNALength, maxReadLength, dpr, dRO.as<MpDpOut>(), dRP.as<uint8_t>(), patStride)) return rc;
         if (tr.on) { cudaStreamSynchronize(st); tr.mark(" dp left+right"); }
         MP_CUDA(cudaMemsetAsync(dOk.p, 0, ((size_t)n + 1) * 4, st));
@@ -200,43 +215,42 @@ static int deep_dp(mp_context *ctx, const mp_align_params *P, mp_results *out, u
         if (nOk) {
             (++g_mp_launches), k_assemble_write<<<g, 128, 0, st>>>(n, cands, dLT.as<MpDpTask>(), dLO.as<MpDpOut>(), dRT.as<MpDpTask>(), dRO.as<MpDpOut>(),
                                                 dLP.as<uint8_t>(), dRP.as<uint8_t>(), patStride, A, dOk.as<uint32_t>(), dIdx.as<uint32_t>(),
-                                                dOff.as<uint32_t>(), cigBase, dRes.as<mp_pair_result>(), dCig.as<char>());
+                                                dOff.as<uint32_t>(), cigBase, dRes.as<mp_pair_result>(), dCig.as<char>(), ctx->dAligned.as<uint8_t>());
             MP_CUDA(cudaGetLastError());
             size_t h0 = H.size();
-            H.resize(h0 + nOk); HC.resize((size_t)cigBase + nBytes);
+            if (H.resize(h0 + nOk) || HC.resize((size_t)cigBase + nBytes)) return MP_ERR_CUDA;
             MP_CUDA(cudaMemcpyAsync(H.data() + h0, dRes.p, (size_t)nOk * sizeof(mp_pair_result), cudaMemcpyDeviceToHost, st));
             MP_CUDA(cudaMemcpyAsync(HC.data() + cigBase, dCig.p, nBytes, cudaMemcpyDeviceToHost, st));
             MP_CUDA(cudaStreamSynchronize(st));
         }
         tr.mark(" assemble+download");
-        // work accounting: one left task per candidate, one right task per passing left
-        {
-            std::vector<MpDpTask> hl(n), hr(n);
-            MP_CUDA(cudaMemcpy(hl.data(), dLT.p, (size_t)n * sizeof(MpDpTask), cudaMemcpyDeviceToHost));
-            MP_CUDA(cudaMemcpy(hr.data(), dRT.p, (size_t)n * sizeof(MpDpTask), cudaMemcpyDeviceToHost));
-            for (uint32_t c = 0; c < n; ++c) {
-                cells += (uint64_t)hl[c].refLen * hl[c].readLen; ++tasksRun;
-                if (hr[c].valid) { cells += (uint64_t)hr[c].refLen * hr[c].readLen; ++tasksRun; }
-            }
-        }
     }
     tr.mark(" accounting");
     // ---- per pair: sort, drop exact duplicates (OutputBuffer::arrayCopyNRemoveDuplicate, DV-DPfunctions.h:167-196) ----
     auto key = [](const mp_pair_result &a) { return std::make_tuple(a.algnmt_1, a.algnmt_2, a.score_1, a.score_2); };
     size_t w = 0, i = 0;
     uint64_t nPairsAligned = 0;
-    while (i < H.size()) {
-        size_t j = i;
-        while (j < H.size() && H[j].readID == H[i].readID) ++j;
-        std::stable_sort(H.begin() + i, H.begin() + j, [&](const mp_pair_result &a, const mp_pair_result &b) { return key(a) < key(b); });
-        size_t first = w;
-        H[w++] = H[i];
-        for (size_t k = i + 1; k < j; ++k) if (key(H[w - 1]) < key(H[k])) H[w++] = H[k];
-        (void)first;
+    const size_t nH = H.size();
+    mp_pair_result *hp = H.data();
+    while (i < nH) {
+        size_t j = i + 1;
+        while (j < nH && hp[j].readID == hp[i].readID) ++j;
+        if (j - i == 1) { if (w != i) hp[w] = hp[i]; ++w; }
+        else {
+            std::stable_sort(hp + i, hp + j, [&](const mp_pair_result &a, const mp_pair_result &b) { return key(a) < key(b); });
+            if (w != i) hp[w] = hp[i];
+            ++w;
+            for (size_t k = i + 1; k < j; ++k) if (key(hp[w - 1]) < key(hp[k])) { if (w != k) hp[w] = hp[k]; ++w; }
+        }
         ++nPairsAligned;
         i = j;
     }
     H.resize(w);
+    {   // cells / tasks counted on the device by k_left_tasks / k_right_tasks
+        unsigned long long hc2[2];
+        MP_CUDA(cudaMemcpy(hc2, dCnt + 11, sizeof hc2, cudaMemcpyDeviceToHost));
+        cells += hc2[0]; tasksRun += hc2[1];
+    }
     tr.mark(" host sort/dedup");
     out->numDPAlignedPair = nPairsAligned; out->numDPAlignment = w;
     return 0;

@@ -3,6 +3,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
@@ -38,6 +39,33 @@ struct DevBuf {
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
     template <class T> T *as() const { return (T *)p; }
+};
+
+// growable pinned host array (results are DMA'd straight into it; cudaMallocHost memory is plain host memory for the caller)
+template <class T> struct PinnedBuf {
+    T *p = nullptr; size_t n = 0, cap = 0;
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+    T *data() { return p; }
+    const T *data() const { return p; }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    void clear() { n = 0; }
+    T &operator[](size_t i) { return p[i]; }
+    const T &operator[](size_t i) const { return p[i]; }
+    T *begin() { return p; }
+    T *end() { return p + n; }
+    int reserve(size_t want) {
+        if (want <= cap) return 0;
+        size_t nc = cap ? cap : 1024;
+        while (nc < want) nc += nc / 2 + 1024;
+        T *q = nullptr;
+        if (cudaMallocHost((void **)&q, nc * sizeof(T)) != cudaSuccess) { mp_set_error("cudaMallocHost(%zu) failed", nc * sizeof(T)); return MP_ERR_CUDA; }
+        if (n) memcpy((void *)q, (const void *)p, n * sizeof(T));
+        if (p) cudaFreeHost(p);
+        p = q; cap = nc; return 0;
+    }
+    int resize(size_t want) { if (reserve(want)) return MP_ERR_CUDA; n = want; return 0; }
+    int push_back(const T &v) { if (n == cap && reserve(n + 1)) return MP_ERR_CUDA; p[n++] = v; return 0; }
 };
 
 // ---- seeding records (device) ----
@@ -91,9 +119,12 @@ struct mp_context {
     DevBuf dTasks, dRefSeq, dReadSeq, dTable, dFill, dPattern, dDpOut;
     DevBuf dLT, dRT, dLO, dRO, dLP, dRP, dOk, dBytes, dIdx, dOff, dRes, dCig;   // stage S1 chunk buffers (kept across calls)
     // results (host, owned until release)
-    std::vector<mp_pair_result> hPairs, hRescued;
+    PinnedBuf<mp_pair_result> hPairs;
+    std::vector<mp_pair_result> hRescued;
     std::vector<mp_single_result> hSingles;
-    std::vector<char> hCigars;
+    PinnedBuf<char> hCigars;
+    std::vector<uint32_t> hLens;            // host copy of the batch's read lengths (stages S2/S3)
+    DevBuf dAligned, dGather;               // per-pair "placed by deep DP" flags; seeds of unplaced reads
 };
 
 // mp_index.cu

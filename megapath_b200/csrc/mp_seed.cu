@@ -436,6 +436,7 @@ int mps_upload(mp_context *ctx, const uint32_t *queries, const uint32_t *readLen
     uint64_t total = nPad * wpq;
     (++g_mp_launches), k_deinterleave<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(ctx->dReadsIl.as<uint32_t>(), ctx->dReads.as<uint32_t>(), nReads, wpq);
     MP_CUDA(cudaGetLastError());
+    ctx->hLens.assign(readLengths, readLengths + nReads);
     ctx->nReads = nReads; ctx->wpq = wpq; ctx->hasBatch = true; ctx->seeded = false;
     return 0;
 }

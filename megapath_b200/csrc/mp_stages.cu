@@ -54,7 +54,7 @@ void single_merge(const std::vector<SCand> &c, std::vector<SCand> &out)
 }
 
 // encode one pattern -> cigar text appended to the arena; returns offset; fills stats
-uint32_t append_cigar(std::vector<char> &arena, const uint8_t *pat, int open, int ext, CigStats &st)
+uint32_t append_cigar(PinnedBuf<char> &arena, const uint8_t *pat, int open, int ext, CigStats &st)
 {
     st = cigar_encode(pat, open, ext, nullptr, 0);
     size_t off = arena.size();
@@ -65,6 +65,27 @@ uint32_t append_cigar(std::vector<char> &arena, const uint8_t *pat, int open, in
 }
 
 }  // namespace
+
+// seeds (SeedPos entries, DV-DPfunctions.cpp:2555-2594 / SeedPool.cpp:191-207) of every read whose pair the deep DP
+// did not place, appended in arbitrary order (the host sorts them as transferSeed does)
+struct GatherRec { uint64_t pos; uint32_t readID; uint32_t strand_len; };
+__global__ void k_gather_unplaced(const uint8_t *__restrict__ alignedPair, uint32_t nReads, const uint32_t *__restrict__ hitStart,
+                                  const uint32_t *__restrict__ nPos, const uint32_t *__restrict__ nNeg, const mp_seed_pos *__restrict__ sp,
+                                  GatherRec *__restrict__ out, uint32_t cap, unsigned int *__restrict__ cursor, unsigned int *__restrict__ nUnplacedPairs)
+{
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nReads || alignedPair[r >> 1]) return;
+    if ((r & 1) == 0) atomicAdd(nUnplacedPairs, 1u);
+    const uint32_t c = nPos[r] + nNeg[r];
+    if (c == 0) return;
+    const uint32_t base = atomicAdd(cursor, c);
+    const mp_seed_pos *src = sp + hitStart[r];
+    for (uint32_t a = 0; a < c; ++a)
+        if (base + a < cap) {
+            GatherRec g; g.pos = src[a].pos; g.readID = r; g.strand_len = (src[a].strand_readID & 0x80000000u) | (src[a].paired_seedLength & 0x7FFFFFFFu);
+            out[base + a] = g;
+        }
+}
 
 // host task list -> DP on the device -> host outputs (chunked)
 int mpd_run_host_tasks(mp_context *ctx, const std::vector<MpDpTask> &tasks, uint32_t maxRefLen, uint32_t maxReadLen, const MpDpParams &P,
@@ -91,33 +112,38 @@ int mps_single_and_rescue(mp_context *ctx, const mp_align_params *P, mp_results 
 {
     const uint32_t nReads = ctx->nReads, nPairs = nReads / 2;
     const uint64_t fullLen = ctx->ix.n;
-    // ---- pairs without a deep-DP result, ascending ----
-    std::vector<uint8_t> aligned(nPairs, 0);
-    for (const mp_pair_result &r : ctx->hPairs) aligned[r.readID >> 1] = 1;
-    std::vector<uint32_t> U;
-    for (uint32_t p = 0; p < nPairs; ++p) if (!aligned[p]) U.push_back(p);
-    if (U.empty()) return 0;
+    // ---- reads of pairs without a deep-DP result: their seeds are gathered on the device ----
+    cudaStream_t st = ctx->stream;
     if (P->softClipLeft != P->softClipRight) {
         mp_set_error("single-end / default DP need MaxFrontLenClipped == MaxEndLenClipped (the reference applies task 0's clip sizes to a whole batch, CPU_DPfunctions.cpp:300)");
         return MP_ERR_ARG;
     }
-    std::vector<uint32_t> lens(nReads);
-    MP_CUDA(cudaMemcpy(lens.data(), ctx->dLens.p, (size_t)nReads * 4, cudaMemcpyDeviceToHost));
-    // ---- S2: seeds of those reads out of the seed store (SeedPool) ----
-    std::vector<uint32_t> hs(nReads + 1), np(nReads), nn(nReads);
-    std::vector<mp_seed_pos> sp(ctx->nHits + 1);
-    MP_CUDA(cudaMemcpy(hs.data(), ctx->dHitStart.p, ((size_t)nReads + 1) * 4, cudaMemcpyDeviceToHost));
-    MP_CUDA(cudaMemcpy(np.data(), ctx->dNPos.p, (size_t)nReads * 4, cudaMemcpyDeviceToHost));
-    MP_CUDA(cudaMemcpy(nn.data(), ctx->dNNeg.p, (size_t)nReads * 4, cudaMemcpyDeviceToHost));
-    if (ctx->nHits) MP_CUDA(cudaMemcpy(sp.data(), ctx->dSeedPos.p, ctx->nHits * sizeof(mp_seed_pos), cudaMemcpyDeviceToHost));
+    const std::vector<uint32_t> &lens = ctx->hLens;
     std::vector<SCand> cand;
-    for (uint32_t p : U)
-        for (uint32_t r = 2 * p; r < 2 * p + 2; ++r)
-            for (uint32_t a = 0; a < np[r] + nn[r]; ++a) {
-                const mp_seed_pos &s = sp[hs[r] + a];
-                SCand c; c.readID = r; c.strand = (s.strand_readID >> 31) + 1; c.pos = s.pos; c.seedLen = s.paired_seedLength & 0x7FFFFFFFu;
-                cand.push_back(c);
-            }
+    {
+        unsigned int *dCur = (unsigned int *)(ctx->dCounters.as<unsigned long long>() + 13);       // [13]: cursor, unplaced pairs
+        size_t cap = std::max<size_t>(ctx->dGather.cap / sizeof(GatherRec), (size_t)1 << 16);
+        unsigned int hcur[2] = { 0, 0 };
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            if (ctx->dGather.reserve(cap * sizeof(GatherRec))) return MP_ERR_CUDA;
+            MP_CUDA(cudaMemsetAsync(dCur, 0, 8, st));
+            (++g_mp_launches), k_gather_unplaced<<<(nReads + 255) / 256, 256, 0, st>>>(ctx->dAligned.as<uint8_t>(), nReads, ctx->dHitStart.as<uint32_t>(),
+                ctx->dNPos.as<uint32_t>(), ctx->dNNeg.as<uint32_t>(), ctx->dSeedPos.as<mp_seed_pos>(), ctx->dGather.as<GatherRec>(), (uint32_t)cap, dCur, dCur + 1);
+            MP_CUDA(cudaGetLastError());
+            MP_CUDA(cudaMemcpyAsync(hcur, dCur, 8, cudaMemcpyDeviceToHost, st));
+            MP_CUDA(cudaStreamSynchronize(st));
+            if (hcur[0] <= cap) break;
+            cap = (size_t)hcur[0] + 1024;
+        }
+        if (hcur[1] == 0) return 0;                       // every pair was placed by the deep DP
+        std::vector<GatherRec> g(hcur[0]);
+        if (hcur[0]) MP_CUDA(cudaMemcpy(g.data(), ctx->dGather.p, (size_t)hcur[0] * sizeof(GatherRec), cudaMemcpyDeviceToHost));
+        cand.resize(g.size());
+        for (size_t i = 0; i < g.size(); ++i) {
+            SCand c; c.readID = g[i].readID; c.strand = (g[i].strand_len >> 31) + 1; c.pos = g[i].pos; c.seedLen = g[i].strand_len & 0x7FFFFFFFu;
+            cand[i] = c;
+        }
+    }
     SCand sentinel; sentinel.readID = 0x7FFFFFFFu; sentinel.strand = 2; sentinel.pos = 0xFFFFFFFFull; sentinel.seedLen = 0xFFFFFFFFu;
     cand.push_back(sentinel);
     std::sort(cand.begin(), cand.end(), scand_less);
@@ -152,7 +178,7 @@ int mps_single_and_rescue(mp_context *ctx, const mp_align_params *P, mp_results 
     uint32_t patStride = maxDNALengthS + maxReadLength;
     if (int rc = mpd_run_host_tasks(ctx, tasks, maxDNALengthS, maxReadLength, dp, outs, pats, patStride)) return rc;
     std::vector<mp_single_result> &S = ctx->hSingles;
-    std::vector<char> &HC = ctx->hCigars;
+    PinnedBuf<char> &HC = ctx->hCigars;
     for (size_t i = 0; i < tasks.size(); ++i) {
         if (outs[i].score < tasks[i].cutoff) continue;
         CigStats st;
