@@ -111,10 +111,15 @@ typedef struct mp_results {
      * occ evaluations of the SA walks (LF steps), SA lookups, LKT jumps, DP cells (sum of
      * dnaLen*readLen over required tasks), DP tasks */
     uint64_t n_occ, n_lf, n_sa, n_lkt, dp_cells, dp_tasks;
+    /* gathers the seeding kernel actually issued beyond those: K-mer filter probes (8 B each) and text-compare
+     * steps (each replaces the two occ evaluations the reference makes for the same step, counted in n_occ) */
+    uint64_t n_probe, n_text;
     /* device time of the main kernels in this call, milliseconds (CUDA events) */
     float ms_seed, ms_sa, ms_pair, ms_dp, ms_total;
     /* host wall clock of the whole mp_align_pairs call, milliseconds */
-    float ms_wall, pad_;
+    float ms_wall;
+    /* summed device time of the DP fill / traceback kernels of this call (CUDA events around every launch) */
+    float ms_fill, ms_tb;
 } mp_results;
 
 /* ---- context ---- */
@@ -184,6 +189,10 @@ int  mp_dp_batch(mp_context *ctx,
  *      end-to-end call. */
 int  mp_align_pairs(mp_context *ctx, const mp_align_params *params, mp_results *out);
 void mp_results_release(mp_context *ctx, mp_results *res);
+
+/* ---- roofline denominators measured on the spot (bench.py): kind 0 = random 32-byte gathers over an 8 GB table,
+ *      1 = random 64-byte gathers (GB/s of requested bytes), 2 = packed 16-bit DPX issue rate (1e9 thread-instr/s) ---- */
+int  mp_microbench(mp_context *ctx, int kind, double *result);
 
 /* default parameters = soap4.ini (nt2 != 0: soap4-nt2.ini) */
 void mp_default_params(mp_align_params *p, int nt2);

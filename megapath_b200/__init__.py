@@ -41,9 +41,9 @@ class Results(C.Structure):
                 ("numSingleDPAligned", C.c_uint64), ("numSingleDPAlignment", C.c_uint64),
                 ("numRescuedPair", C.c_uint64), ("numRescuedAlignment", C.c_uint64),
                 ("n_occ", C.c_uint64), ("n_lf", C.c_uint64), ("n_sa", C.c_uint64), ("n_lkt", C.c_uint64),
-                ("dp_cells", C.c_uint64), ("dp_tasks", C.c_uint64),
+                ("dp_cells", C.c_uint64), ("dp_tasks", C.c_uint64), ("n_probe", C.c_uint64), ("n_text", C.c_uint64),
                 ("ms_seed", C.c_float), ("ms_sa", C.c_float), ("ms_pair", C.c_float),
-                ("ms_dp", C.c_float), ("ms_total", C.c_float), ("ms_wall", C.c_float), ("pad_", C.c_float)]
+                ("ms_dp", C.c_float), ("ms_total", C.c_float), ("ms_wall", C.c_float), ("ms_fill", C.c_float), ("ms_tb", C.c_float)]
 
 
 SEEDPOS = np.dtype([("pos", "<u8"), ("strand_readID", "<u4"), ("paired_seedLength", "<u4")])
@@ -87,6 +87,7 @@ def lib():
         L.mp_index_save.argtypes = [C.c_void_p, C.c_char_p]
         L.mp_index_save_annotation.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mp_launch_count.restype = C.c_uint64
+        L.mp_microbench.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.mp_occ.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.mp_sa.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.mp_lkt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
@@ -258,6 +259,12 @@ class Context:
         r = np.empty(len(keys), dtype=np.uint64)
         self._check(self.L.mp_lkt(self.h, _ptr(keys), _ptr(l), _ptr(r), len(keys)))
         return l, r
+
+    def microbench(self, kind):
+        """0/1: random 32-/64-byte gather GB/s; 2: packed-16 DPX Ginstr/s (roofline denominators)."""
+        out = C.c_double()
+        self._check(self.L.mp_microbench(self.h, kind, C.byref(out)))
+        return out.value
 
     # ---- batch ----
     def batch_upload(self, queries, read_lengths, wpq):

@@ -279,6 +279,7 @@ extern "C" void mp_destroy(mp_context *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
     DevBuf *bufs[] = { &ctx->dBlocks, &ctx->dSuper, &ctx->dSa, &ctx->dSa32, &ctx->dBloom, &ctx->dLkt, &ctx->dPac, &ctx->dReadsIl, &ctx->dReads, &ctx->dLens,
                        &ctx->dCounters, &ctx->dSeeds, &ctx->dStubs, &ctx->dHitsPerRead, &ctx->dHitStart, &ctx->dCursor, &ctx->dHits,
                        &ctx->dSeedPos, &ctx->dNPos, &ctx->dNNeg, &ctx->dCandCount, &ctx->dCandStart, &ctx->dCands, &ctx->dScanTmp,
@@ -390,6 +391,7 @@ extern "C" int mp_dp_batch(mp_context *ctx,
     MP_CUDA(cudaMemcpyAsync(ho.data(), dOut.p, (size_t)n * sizeof(MpDpOut), cudaMemcpyDeviceToHost, ctx->stream));
     MP_CUDA(cudaMemcpyAsync(hp.data(), dPat.p, hp.size(), cudaMemcpyDeviceToHost, ctx->stream));
     MP_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->evUsed = 0;
     for (uint32_t t = 0; t < n; ++t) {
         scores[t] = ho[t].score; hitLocs[t] = ho[t].hitLoc; maxScoreCounts[t] = ho[t].count;
         if (ho[t].patLen) memcpy(pattern + (size_t)t * patStride, hp.data() + (size_t)t * patStride, ho[t].patLen + 1);
@@ -411,6 +413,7 @@ extern "C" int mp_align_pairs(mp_context *ctx, const mp_align_params *params, mp
     MpTrace tr;
     memset(out, 0, sizeof *out);
     ctx->hPairs.clear(); ctx->hRescued.clear(); ctx->hSingles.clear(); ctx->hCigars.clear();
+    ctx->evUsed = 0;
     MP_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
     if (!ctx->seeded) { if (int rc = mp_seed_pairs(ctx, params)) return rc; }
     MP_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
@@ -424,7 +427,8 @@ extern "C" int mp_align_pairs(mp_context *ctx, const mp_align_params *params, mp
     tr.mark("single+default dp");
     unsigned long long hc[16];
     MP_CUDA(cudaMemcpy(hc, ctx->dCounters.p, sizeof hc, cudaMemcpyDeviceToHost));
-    out->n_occ = hc[2]; out->n_lf = hc[5]; out->n_sa = hc[3]; out->n_lkt = hc[4];
+    out->n_occ = hc[2]; out->n_lf = hc[5] + hc[8]; out->n_sa = hc[3]; out->n_lkt = hc[4]; out->n_probe = hc[9]; out->n_text = hc[10];
+    ctx->ev_collect(out->ms_fill, out->ms_tb);
     out->dp_cells = cells; out->dp_tasks = tasksRun;
     cudaEventElapsedTime(&out->ms_seed, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&out->ms_sa, ctx->ev[1], ctx->ev[2]);

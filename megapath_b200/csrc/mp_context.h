@@ -97,6 +97,20 @@ struct mp_context {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8];
+    // event pairs around the DP kernels of one mp_align_pairs call (kind 0 = fill, 1 = traceback)
+    std::vector<cudaEvent_t> evPool; std::vector<int> evKind; size_t evUsed = 0;
+    cudaEvent_t ev_begin(int kind) {
+        if (evUsed + 2 > evPool.size()) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); evPool.push_back(a); evPool.push_back(b); evKind.push_back(kind); }
+        evKind[evUsed / 2] = kind;
+        cudaEventRecord(evPool[evUsed], stream);
+        return evPool[evUsed + 1];
+    }
+    void ev_end(cudaEvent_t stop) { cudaEventRecord(stop, stream); evUsed += 2; }
+    void ev_collect(float &msFill, float &msTb) {       // after a stream sync
+        msFill = msTb = 0;
+        for (size_t i = 0; i + 1 < evUsed; i += 2) { float t = 0; cudaEventElapsedTime(&t, evPool[i], evPool[i + 1]); (evKind[i / 2] == 0 ? msFill : msTb) += t; }
+        evUsed = 0;
+    }
     // index
     bool hasIndex = false;
     MpIndexView ix;

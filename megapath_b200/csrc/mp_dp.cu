@@ -181,6 +181,22 @@ k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLe
                 if (hasB) *(uint16_t *)(tabB + off) = (uint16_t)(((code[K - 2] >> 16) & 0xff) | (((code[K - 1] >> 16) & 0xff) << 8));
             }
             sendH = Hleft; sendI = Il;
+        } else if (!laneActive && i >= 1 && i <= maxN) {
+            // lanes past the last read column only complete the 32-byte sectors of this step's trace rows, so that
+            // no sector is written partially (a partial sector costs a DRAM read-modify-write when L2 evicts it)
+#pragma unroll
+            for (int w = 0; w < WORDS; ++w) {
+                const size_t off = (size_t)w * S * 128 + (size_t)t * 128 + lane * 4;
+                *(uint32_t *)(tabA + off) = 0u;
+                if (hasB) *(uint32_t *)(tabB + off) = 0u;
+            }
+            if (REM == 1) {
+                const size_t off = (size_t)WORDS * S * 128 + (size_t)t * 32 + lane;
+                tabA[off] = 0; if (hasB) tabB[off] = 0;
+            } else if (REM == 2) {
+                const size_t off = (size_t)WORDS * S * 128 + ((size_t)t * 32 + lane) * 2;
+                *(uint16_t *)(tabA + off) = 0; if (hasB) *(uint16_t *)(tabB + off) = 0;
+            }
         }
     }
     // ---- winner per task: max score, then smallest (row, col); ties summed ----
@@ -338,10 +354,13 @@ static int launch_dp(mp_context *ctx, const uint8_t *dRef, const uint32_t *dRefL
         const uint32_t n = std::min<uint32_t>(per, nTasks - base);
         dim3 gridF((n + 7) / 8), gridT((n + 127) / 128), block(128);
 #define LAUNCH(KK) do { \
+        cudaEvent_t stop_ = ctx->ev_begin(0); \
         (++g_mp_launches), k_dp_fill<KK><<<gridF, block, smem, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, \
             base, n, P, tab, tableStride, S, fill); \
+        ctx->ev_end(stop_); stop_ = ctx->ev_begin(1); \
         (++g_mp_launches), k_dp_tb<KK><<<gridT, block, 0, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, \
-            base, n, P, tab, tableStride, S, fill, dOuts, dPatterns, patStride); } while (0)
+            base, n, P, tab, tableStride, S, fill, dOuts, dPatterns, patStride); \
+        ctx->ev_end(stop_); } while (0)
         if (K == 5) LAUNCH(5); else if (K == 8) LAUNCH(8); else LAUNCH(10);
 #undef LAUNCH
         MP_CUDA(cudaGetLastError());
