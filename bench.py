@@ -298,6 +298,23 @@ def workload_name(args):
 
 def main():
     args = parse_args()
+    # stdout carries exactly one JSON line: anything libraries print while we work (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        return run(args, saved_stdout)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+
+
+def emit(saved_stdout, obj):
+    sys.stdout.flush()
+    os.write(saved_stdout, (json.dumps(obj) + "\n").encode())
+
+
+def run(args, saved_stdout):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -349,11 +366,11 @@ def main():
         value = npairs * len(vals) / tot_align
         cb = {"value": value, "unit": "pairs/s", "cores": ncores, "kind": "reference",
               "sample": "%d pairs per step of the same workload, oracle/_ref/soap4 -T %d, its own 'Overall alignment time (excl. read loading)'" % (npairs, ncores)}
-        print(json.dumps({"impl": "reference", "metric": "read pairs aligned/sec", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        emit(saved_stdout, {"impl": "reference", "metric": "read pairs aligned/sec", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_align / max(1, len(vals)),
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16/u8", "data": "synthetic",
                           "config": cfg, "cpu_baseline": cb,
-                          "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                          "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return 0
 
     # ---------------- our arm ----------------
@@ -399,7 +416,7 @@ def main():
     barrier()
     launches = mp.launch_count() - l0
     if os.environ.get("MP_BENCH_VERBOSE"):
-        sys.stderr.write("loop A: %s\n" % json.dumps({k: v / args.steps for k, v in acc.items()}))
+        sys.stderr.write("rank %d loop A: %s\n" % (rank, json.dumps({k: round(v / args.steps, 3) for k, v in acc.items() if k.startswith("ms_")})))
     # ---- loop B: end to end through the C-ABI with host buffers ----
     barrier()
     t0 = time.perf_counter()
@@ -413,11 +430,10 @@ def main():
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
 
-    tm = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=device)
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_ms_max = float(tm[0]), float(tm[1])
+    from megapath_b200 import shard
+    dev_ms_max, e2e_ms_max = shard.max_over_ranks([dev_ms, e2e_s * 1e3], device=device)     # slowest rank decides
+    tot = shard.sum_counters({"pairs_aligned": acc["pairs_aligned"]}, device=device)
+    acc_pairs_all = tot["pairs_aligned"]
     total_pairs = args.pairs_per_step * args.steps * world
     value = total_pairs / (dev_ms_max / 1e3)
     e2e = total_pairs / (e2e_ms_max / 1e3)
@@ -463,7 +479,7 @@ def main():
            "data": "synthetic", "config": cfg, "clocks": clocks,
            "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
            "gpu_launches": int(launches), "roofline": roof,
-           "aligned_fraction": acc["pairs_aligned"] / (args.pairs_per_step * args.steps),
+           "aligned_fraction": acc_pairs_all / (args.pairs_per_step * args.steps * world),
            "index_prepare_s": t_index}
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         try:
@@ -474,7 +490,7 @@ def main():
         except Exception as e:  # the baseline is reported, never the target: say why it is missing
             out["cpu_baseline"] = {"value": None, "unit": "pairs/s", "cores": ncores, "kind": "reference", "sample": "unavailable: %s" % e}
     if rank == 0:
-        print(json.dumps(out))
+        emit(saved_stdout, out)
     ctx.close()
     if world > 1:
         import torch.distributed as dist

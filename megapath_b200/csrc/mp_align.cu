@@ -185,6 +185,8 @@ static int deep_dp(mp_context *ctx, const mp_align_params *P, mp_results *out, u
     PinnedBuf<mp_pair_result> &H = ctx->hPairs;
     PinnedBuf<char> &HC = ctx->hCigars;
     unsigned long long *dCnt = ctx->dCounters.as<unsigned long long>();
+    // room for about one result per candidate up front: growing a pinned arena mid-batch costs a cudaMallocHost
+    if (H.reserve((size_t)nC + nC / 8 + 1024) || HC.reserve(((size_t)nC + nC / 8 + 1024) * 20)) return MP_ERR_CUDA;
     if (ctx->dAligned.reserve((size_t)ctx->nReads / 2 + 8)) return MP_ERR_CUDA;
     MP_CUDA(cudaMemsetAsync(ctx->dAligned.p, 0, (size_t)ctx->nReads / 2 + 8, st));
     const uint64_t fullLen = ctx->ix.n;
