@@ -14,7 +14,7 @@
 //                            OutputDPResult.cpp:65-265; BGS-IO.cpp:163-190, 1312-1446, 1966-2091
 //   unpaired bookkeeping     filterOutUnpairedSingleReads, DPSOutputUnpairedAlignment
 //                            SeedPool.cpp:267-322; DV-DPfunctions.cpp:841-920
-// BAM output (-b) is not implemented yet; the flag is accepted and reported on stderr.
+//   BAM output (-b)          bam_out.h
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -28,6 +28,7 @@
 #include <tuple>
 #include <vector>
 #include "megapath_b200.h"
+#include "bam_out.h"
 
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -104,6 +105,7 @@ struct Ini {
 struct Annotation {
     uint64_t dnaLength = 0; uint32_t numSeq = 0;
     std::vector<std::string> names;
+    std::vector<uint64_t> seqStart, seqLen, actualLen;
     std::vector<uint32_t> grid;
     struct Tr { uint64_t startPos; uint32_t chrID; uint64_t correction; };
     std::vector<Tr> tr;
@@ -119,6 +121,7 @@ struct Annotation {
             size_t l = strlen(buf); if (l && buf[l - 1] == '\n') buf[l - 1] = 0;
             names.push_back(buf);
             unsigned long long a, b; int c; if (fscanf(f, "%llu %llu %d\n", &a, &b, &c) != 3) break;
+            seqStart.push_back(a); seqLen.push_back(b);
         }
         fclose(f);
         if (names.size() != ns) { fprintf(stderr, "Annotation missing entries!\n"); return false; }
@@ -133,15 +136,31 @@ struct Annotation {
             if (fscanf(f, "%llu %u %llu\n", &s, &id, &c) != 3) { fclose(f); fprintf(stderr, "Translate missing entries!\n"); return false; }
             tr[j].startPos = s; tr[j].chrID = id; tr[j].correction = c;
         }
+        for (uint32_t j = 0; j < ns; ++j) {
+            unsigned long long a, l;
+            if (fscanf(f, "%llu %llu\n", &a, &l) != 2) { actualLen.clear(); break; }
+            actualLen.push_back(l);
+        }
+        if (actualLen.size() != ns) actualLen = seqLen;
         fclose(f);
         return true;
     }
-    void chrAndPos(uint64_t ambPos, uint64_t *tp, uint32_t *chr) const {
+    // -> end of the translate segment that holds ambPos (getChrAndPos, BGS-IO.cpp:163-190)
+    uint64_t chrAndPos(uint64_t ambPos, uint64_t *tp, uint32_t *chr) const {
         uint64_t idx = ambPos >> 18;
         if (idx >= grid.size()) idx = grid.size() - 1;
         uint32_t v = grid[idx];
         while (tr[v].startPos > ambPos) v--;
         *tp = ambPos - tr[v].correction; *chr = tr[v].chrID;
+        return (size_t)v + 1 < tr.size() ? tr[v + 1].startPos - 1 : dnaLength;
+    }
+    // getChrAndPosWithBoundaryCheckDP (BGS-IO.cpp:414-432)
+    long long chrAndPosBoundaryDP(uint64_t readLength, uint64_t ambPos, const char *cigar, uint64_t *tp, uint32_t *chr, std::string &newCigar) const {
+        uint64_t segEnd = chrAndPos(ambPos, tp, chr);
+        uint64_t chrEnd = seqStart[*chr - 1] + seqLen[*chr - 1] - 1, corrected = 0;
+        long long ret = boundary_check_dp(ambPos, chrEnd, (long long)readLength, cigar, segEnd, corrected, newCigar);
+        if (ret && corrected > ambPos) chrAndPos(corrected, tp, chr);
+        return ret;
     }
     // decideTargetChr (BGS-IO.cpp:1312-1341): -1 when the read window [pos, pos+readLen) crosses sequences
     int targetChr(uint64_t ambPos, uint32_t readLen) const {
@@ -296,44 +315,261 @@ static void header_line(std::string &ret, const ReadBatch &b, uint32_t id, const
     ret += "\n";
 }
 
-// pairDeepDPOutputFastqAPI (BGS-IO.cpp:1966-2091) for the results [first, last) of one pair
-static void pair_fastq(std::string &ret, const ReadBatch &b, const Annotation &ann, const mp_pair_result *first, const mp_pair_result *last,
-                       int megapathMode, double top, bool ignoreComments)
+struct OutCtx {
+    const ReadBatch *b; const Annotation *ann; int megapathMode; double top; bool ignoreComments;
+    // BAM side
+    BamWriter *bam = nullptr; std::string readGroup; bool printMDNM = false; int alignmentType = 2;
+    int mismatchScore = -2, matchScore = 1, minMAPQ = 1, maxMAPQ = 60; bool bwaLike = true;
+    AnnEx ax;
+};
+struct PairAln {       // mutable copy of one DeepDPAlignResult (the FASTQ writer edits scores / positions before the BAM writer runs)
+    uint64_t a1, a2; int s1, s2, strand1, strand2, ed1, ed2, ns1, ns2, insertSize; const char *c1, *c2;
+};
+struct SingleAln { uint64_t algnmt; int score, strand, editdist, num_sameScore; const char *cigar; };
+
+static void unpack_read(const ReadBatch &b, uint32_t id, std::vector<uint8_t> &codes)
 {
-    const uint32_t r1 = first->readID, r2 = r1 + 1;
-    int best1 = 0, best2 = 0;
-    std::vector<std::pair<int, int>> h1, h2;
-    for (const mp_pair_result *p = first; p != last; ++p) {
-        int chr1 = ann.targetChr(p->algnmt_1, b.lens[r1]), chr2 = ann.targetChr(p->algnmt_2, b.lens[r2]);
-        int s1 = chr1 == -1 ? 0 : p->score_1, s2 = chr2 == -1 ? 0 : p->score_2;
-        bool a1 = chr1 != -1, a2 = chr2 != -1;
-        if (megapathMode == 2 && (!a1 || !a2)) { a1 = a2 = false; s1 = s2 = 0; }
-        if (!a1) s1 = 0;
-        if (!a2) s2 = 0;
-        if (chr1 == chr2 && a1 && a2) { int sum = s1 + s2; s1 = s2 = sum; }          // normalizeScore
-        if (best1 < s1) best1 = s1;
-        if (best2 < s2) best2 = s2;
-        if (chr1 != -1) h1.push_back(std::make_pair(chr1, -s1));
-        if (chr2 != -1) h2.push_back(std::make_pair(chr2, -s2));
-    }
-    header_line(ret, b, r1, ann, h1, best1, top, ignoreComments); seq_and_qual(ret, b, r1);
-    header_line(ret, b, r2, ann, h2, best2, top, ignoreComments); seq_and_qual(ret, b, r2);
+    const uint32_t *q = b.queries.data() + ((size_t)(id / 32) * 32 * b.wpq + id % 32);
+    codes.resize(b.lens[id]);
+    for (uint32_t i = 0; i < b.lens[id]; ++i) codes[i] = (q[(i >> 4) * 32] >> ((i & 15) << 1)) & 3;
+}
+static std::string xa_entry(const Annotation &ann, uint64_t algnmt, int strand, const char *spCigar, int editdist)
+{
+    uint64_t tp; uint32_t chr; ann.chrAndPos(algnmt, &tp, &chr);
+    return ann.names[chr - 1] + "," + (strand == 2 ? "-" : "+") + std::to_string((unsigned long long)tp) + "," + convert_cigar(spCigar) + "," + std::to_string(editdist) + ";";
 }
 
-// unproperlypairDPOutputFastqAPI (BGS-IO.cpp:1384-1446) for one read and its (de-duplicated) single-end hits
-static void single_fastq(std::string &ret, const ReadBatch &b, const Annotation &ann, uint32_t id,
-                         const std::vector<std::pair<uint64_t, int>> &hits, int megapathMode, double top, bool ignoreComments)
+// one pair placed by deep DP or mate rescue: outputDeepDPResult2 (best = first maximal score sum, OutputDPResult.cpp:156-232)
+// -> pairDeepDPOutputSAMAPI = pairDeepDPOutputFastqAPI (stdout) + BAM records (BGS-IO.cpp:1966-2800)
+static void output_pair(OutCtx &o, std::string &fq, const mp_pair_result *first, const mp_pair_result *last, const char *cigars, int stageId)
 {
-    int best = 0;
-    std::vector<std::pair<int, int>> h;
-    if (megapathMode != 2)
-        for (const auto &a : hits) {
-            int chr = ann.targetChr(a.first, b.lens[id]);
-            int sc = a.second;
-            if (chr < 0) sc = 0; else h.push_back(std::make_pair(chr, -sc));
-            if (best < sc) best = sc;
+    const ReadBatch &b = *o.b; const Annotation &ann = *o.ann;
+    const uint32_t r1 = first->readID, r2 = r1 + 1;
+    const int readlen1 = (int)b.lens[r1], readlen2 = (int)b.lens[r2];
+    std::vector<PairAln> v; v.reserve(last - first);
+    for (const mp_pair_result *p = first; p != last; ++p) {
+        PairAln a; a.a1 = p->algnmt_1; a.a2 = p->algnmt_2; a.s1 = p->score_1; a.s2 = p->score_2; a.strand1 = p->strand_1; a.strand2 = p->strand_2;
+        a.ed1 = p->editdist_1; a.ed2 = p->editdist_2; a.ns1 = p->num_sameScore_1; a.ns2 = p->num_sameScore_2; a.insertSize = p->insertSize;
+        a.c1 = cigars + p->cigar_1; a.c2 = cigars + p->cigar_2;
+        v.push_back(a);
+    }
+    size_t best = 0; int maxScore = v[0].s1 + v[0].s2;
+    for (size_t i = 1; i < v.size(); ++i) if (v[i].s1 + v[i].s2 > maxScore) { best = i; maxScore = v[i].s1 + v[i].s2; }
+    if (o.megapathMode) {
+        int best1 = 0, best2 = 0;
+        std::vector<std::pair<int, int>> h1, h2;
+        for (PairAln &a : v) {
+            int chr1 = -1, chr2 = -1;
+            if (a.a1 != NOT_ALIGNED) chr1 = ann.targetChr(a.a1, readlen1);
+            if (a.a2 != NOT_ALIGNED) chr2 = ann.targetChr(a.a2, readlen2);
+            if (chr1 == -1) { a.a1 = NOT_ALIGNED; a.s1 = 0; }
+            if (chr2 == -1) { a.a2 = NOT_ALIGNED; a.s2 = 0; }
+            if (o.megapathMode == 2 && (a.a1 == NOT_ALIGNED || a.a2 == NOT_ALIGNED)) { a.a1 = a.a2 = NOT_ALIGNED; a.s1 = a.s2 = 0; }
+            if (a.a1 == NOT_ALIGNED) a.s1 = 0;                                              // normalizeScore
+            if (a.a2 == NOT_ALIGNED) a.s2 = 0;
+            if (chr1 == chr2 && a.a1 != NOT_ALIGNED && a.a2 != NOT_ALIGNED) { int sum = a.s1 + a.s2; a.s1 = a.s2 = sum; }
+            if (best1 < a.s1) best1 = a.s1;
+            if (best2 < a.s2) best2 = a.s2;
+            if (chr1 != -1) h1.push_back(std::make_pair(chr1, -a.s1));
+            if (chr2 != -1) h2.push_back(std::make_pair(chr2, -a.s2));
         }
-    header_line(ret, b, id, ann, h, best, top, ignoreComments); seq_and_qual(ret, b, id);
+        header_line(fq, b, r1, ann, h1, best1, o.top, o.ignoreComments); seq_and_qual(fq, b, r1);
+        header_line(fq, b, r2, ann, h2, best2, o.top, o.ignoreComments); seq_and_qual(fq, b, r2);
+    }
+    if (!o.bam) return;
+    // ---- BAM (pairDeepDPOutputSAMAPI, BGS-IO.cpp:2112-2800) ----
+    PairAln &B = v[best];
+    if (B.a1 == NOT_ALIGNED && B.a2 == NOT_ALIGNED) return;
+    std::vector<uint8_t> q1, q2; unpack_read(b, r1, q1); unpack_read(b, r2, q2);
+    ReadView rv1 = { &b.names[r1], q1.data(), b.quals[r1].c_str(), readlen1 }, rv2 = { &b.names[r2], q2.data(), b.quals[r2].c_str(), readlen2 };
+    const int num = (int)v.size();
+    uint64_t tp_1 = 0, tp_2 = 0; uint32_t chr_1 = 0, chr_2 = 0;
+    long long boundTrim1 = 0, boundTrim2 = 0; std::string newCigar1, newCigar2, cigarStr1, cigarStr2;
+    MisInfo mi1, mi2; int rr1 = readlen1, rr2 = readlen2;
+    int best_insert = (B.a1 != NOT_ALIGNED && B.a2 != NOT_ALIGNED) ? B.insertSize : 0;
+    if (B.a1 != NOT_ALIGNED) {
+        boundTrim1 = ann.chrAndPosBoundaryDP(readlen1, B.a1, B.c1, &tp_1, &chr_1, newCigar1);
+        cigarStr1 = boundTrim1 ? convert_cigar(newCigar1.c_str()) : convert_cigar(B.c1);
+        mi1 = mis_info_for_dp(o.ax, b.quals[r1].c_str(), readlen1, B.a1, B.strand1, boundTrim1 ? newCigar1.c_str() : B.c1, boundTrim1);
+        rr1 = ref_len_of_cigar(B.c1);
+    }
+    if (B.a2 != NOT_ALIGNED) {
+        boundTrim2 = ann.chrAndPosBoundaryDP(readlen2, B.a2, B.c2, &tp_2, &chr_2, newCigar2);
+        cigarStr2 = boundTrim2 ? convert_cigar(newCigar2.c_str()) : convert_cigar(B.c2);
+        mi2 = mis_info_for_dp(o.ax, b.quals[r2].c_str(), readlen2, B.a2, B.strand2, boundTrim2 ? newCigar2.c_str() : B.c2, boundTrim2);
+        rr2 = ref_len_of_cigar(B.c2);
+    }
+    int bestPairNum = 0, bestPairScore = 0, secBestPairScore = 0;
+    if (B.a1 != NOT_ALIGNED && B.a2 != NOT_ALIGNED) {
+        bestPairNum = 1; bestPairScore = B.s1 + B.s2;
+        for (int i = 0; i < num; ++i) {
+            if ((size_t)i == best) continue;
+            if (v[i].s1 + v[i].s2 == bestPairScore) bestPairNum++;
+            else if (v[i].s1 + v[i].s2 > secBestPairScore) secBestPairScore = v[i].s1 + v[i].s2;
+        }
+    }
+    // X0 / X1 of each end (BGS-IO.cpp:2311-2437)
+    auto hit_counts = [&](bool firstEnd, int &bestHitNum, int &secBestHitNum) {
+        bestHitNum = 0; secBestHitNum = 0;
+        int bestScore = 0, secBestScore = 0; uint64_t bestPos = NOT_ALIGNED, secBestPos = NOT_ALIGNED;
+        const uint64_t Ba = firstEnd ? B.a1 : B.a2;
+        if (Ba != NOT_ALIGNED) { bestScore = firstEnd ? B.s1 : B.s2; bestPos = Ba; bestHitNum = 1; }
+        if (Ba != NOT_ALIGNED && num > 1)
+            for (int i = 0; i < num; ++i) {
+                if ((size_t)i == best) continue;
+                const int sc = firstEnd ? v[i].s1 : v[i].s2, ns = firstEnd ? v[i].ns1 : v[i].ns2; const uint64_t al = firstEnd ? v[i].a1 : v[i].a2;
+                if (sc >= bestScore) {
+                    if (sc == bestScore) { if (al != bestPos) bestHitNum += ns; }
+                    else { secBestScore = bestScore; secBestHitNum = bestHitNum; secBestPos = bestPos; bestScore = sc; bestHitNum = ns; bestPos = al; }
+                } else if (sc >= secBestScore) {
+                    if (sc == secBestScore) { if (al != secBestPos) secBestHitNum += ns; }
+                    else { secBestScore = sc; secBestPos = al; secBestHitNum = ns; }
+                }
+            }
+    };
+    int bestHitNum1, secBestHitNum1, bestHitNum2, secBestHitNum2;
+    hit_counts(true, bestHitNum1, secBestHitNum1); hit_counts(false, bestHitNum2, secBestHitNum2);
+    int mapq1 = 255, mapq2 = 255;
+    if (o.alignmentType == 1 || o.alignmentType == 2) {
+        bwa_like_pair(bestHitNum1, secBestHitNum1, bestHitNum2, secBestHitNum2, bestPairScore, bestPairNum, secBestPairScore, num - bestPairNum, readlen1, readlen2, &mapq1, &mapq2);
+        if (boundTrim1) mapq1 = 0;
+        if (boundTrim2) mapq2 = 0;
+    }
+    for (int end = 0; end < 2; ++end) {
+        const bool e1 = end == 0;
+        const uint64_t mine = e1 ? B.a1 : B.a2, mate = e1 ? B.a2 : B.a1;
+        std::string xa;
+        if (mine != NOT_ALIGNED && num > 1)
+            for (int i = 0; i < num; ++i) {
+                if ((size_t)i == best) continue;
+                if (o.alignmentType == 2 && v[i].s1 + v[i].s2 < bestPairScore) continue;
+                const uint64_t al = e1 ? v[i].a1 : v[i].a2;
+                if (al == NOT_ALIGNED) continue;
+                xa += xa_entry(ann, al, e1 ? v[i].strand1 : v[i].strand2, e1 ? v[i].c1 : v[i].c2, e1 ? v[i].ed1 : v[i].ed2);
+            }
+        int bh = e1 ? bestHitNum1 : bestHitNum2, sbh = e1 ? secBestHitNum1 : secBestHitNum2;
+        if (o.alignmentType == 4) { bh = -1; sbh = -1; } else if (o.alignmentType != 1 && o.alignmentType != 2) sbh = -1;
+        const MisInfo &mi = e1 ? mi1 : mi2; const ReadView &rv = e1 ? rv1 : rv2;
+        const int strand = e1 ? B.strand1 : B.strand2, readlen = e1 ? readlen1 : readlen2;
+        BamRecord rec;
+        if (mine != NOT_ALIGNED) {
+            int mq = e1 ? mapq1 : mapq2;
+            if (mate == NOT_ALIGNED) {
+                mq = mapq_for_dp(bh, e1 ? B.s1 : B.s2, readlen * o.matchScore, mi.avgMismatchQual, o.maxMAPQ, o.minMAPQ);
+                if (e1 ? boundTrim1 : boundTrim2) mq = 0;
+            }
+            init_mapped(rec, rv, strand, xa, e1 ? cigarStr1 : cigarStr2, mi.numMismatch, mi.numMismatch + mi.gapExt, bh, sbh, mi.gapOpen, mi.gapExt, mi.md, mq,
+                        o.readGroup, o.printMDNM, stageId);
+        } else init_unmapped(rec, rv, e1 ? 1 : 1, "", o.readGroup);
+        uint32_t flag = 1;
+        if (B.a1 != NOT_ALIGNED && B.a2 != NOT_ALIGNED) flag |= 0x2;
+        flag |= e1 ? 0x40 : 0x80;
+        if (mine == NOT_ALIGNED) flag |= 0x4;
+        if (mate == NOT_ALIGNED) flag |= 0x8;
+        if (mine != NOT_ALIGNED && strand == 2) flag |= 0x10;
+        if (mate != NOT_ALIGNED && (e1 ? B.strand2 : B.strand1) == 2) flag |= 0x20;
+        rec.flag = flag;
+        const uint32_t cm = e1 ? chr_1 : chr_2, co = e1 ? chr_2 : chr_1; const uint64_t tm = e1 ? tp_1 : tp_2, to = e1 ? tp_2 : tp_1;
+        rec.tid = cm == 0 ? (co == 0 ? -1 : (int32_t)co - 1) : (int32_t)cm - 1;
+        rec.pos = tm == 0 ? (to == 0 ? -1 : (int32_t)(to - 1)) : (int32_t)(tm - 1);
+        rec.mtid = co == 0 ? (cm == 0 ? -1 : (int32_t)cm - 1) : (int32_t)co - 1;
+        rec.mpos = to == 0 ? (tm == 0 ? -1 : (int32_t)(tm - 1)) : (int32_t)(to - 1);
+        if (best_insert > 0) {
+            const int rm = e1 ? rr1 : rr2, ro = e1 ? rr2 : rr1;
+            if (tm > to) rec.isize = -(int32_t)(tm + rm - to); else rec.isize = (int32_t)(to + ro - tm);
+        } else rec.isize = 0;
+        o.bam->write(rec, rv.name->size() + 1);
+    }
+}
+
+// a pair that is neither placed nor rescued: per-read single-end hits (unproperlypairDPOutputSAMAPI, BGS-IO.cpp:1448-1915)
+static void output_unpaired(OutCtx &o, std::string &fq, uint32_t r1, std::vector<SingleAln> hits[2], int stageId)
+{
+    const ReadBatch &b = *o.b; const Annotation &ann = *o.ann;
+    const uint32_t ids[2] = { r1, r1 + 1 };
+    if (o.megapathMode) {
+        for (int e = 0; e < 2; ++e) {
+            int best = 0; std::vector<std::pair<int, int>> h;
+            const int hitNum = o.megapathMode == 2 ? 0 : (int)hits[e].size();
+            for (int i = 0; i < hitNum; ++i) {
+                SingleAln &a = hits[e][i];
+                int chr = ann.targetChr(a.algnmt, b.lens[ids[e]]);
+                if (chr < 0) { a.algnmt = NOT_ALIGNED; a.score = 0; } else h.push_back(std::make_pair(chr, -a.score));
+                if (best < a.score) best = a.score;
+            }
+            header_line(fq, b, ids[e], ann, h, best, o.top, o.ignoreComments); seq_and_qual(fq, b, ids[e]);
+        }
+    }
+    if (!o.bam) return;
+    const int readlen[2] = { (int)b.lens[ids[0]], (int)b.lens[ids[1]] };
+    std::vector<uint8_t> q[2]; unpack_read(b, ids[0], q[0]); unpack_read(b, ids[1], q[1]);
+    ReadView rv[2] = { { &b.names[ids[0]], q[0].data(), b.quals[ids[0]].c_str(), readlen[0] }, { &b.names[ids[1]], q[1].data(), b.quals[ids[1]].c_str(), readlen[1] } };
+    int bestIdx[2] = { -1, -1 }, bestScore[2] = { 0, 0 }, bestScoreNum[2] = { 0, 0 }, x1_t1[2] = { 0, 0 }, x1_t2[2] = { 0, 0 }, secondBestNum[2];
+    uint64_t tp[2] = { 0, 0 }; uint32_t chr[2] = { 0, 0 }; long long boundTrim[2] = { 0, 0 }; int deletedEnd[2] = { 0, 0 }, mapq[2] = { 0, 0 };
+    std::string newCigar[2], cigarStr[2]; MisInfo mi[2];
+    for (int e = 0; e < 2; ++e) {
+        const std::vector<SingleAln> &L = hits[e];
+        if (!L.empty()) {
+            bestIdx[e] = 0; bestScore[e] = L[0].score; bestScoreNum[e] = 1;
+            for (size_t i = 1; i < L.size(); ++i) {
+                if (L[i].score > bestScore[e]) { bestIdx[e] = (int)i; bestScore[e] = L[i].score; bestScoreNum[e] = 1; }
+                else if (L[i].score == bestScore[e]) bestScoreNum[e]++;
+            }
+        }
+        int secondBestScore = -9999; const int thres = (int)(0.7 * bestScore[e]);
+        for (const SingleAln &a : L)
+            if (a.score < bestScore[e]) { if (a.score > secondBestScore) secondBestScore = a.score; if (a.score >= thres) x1_t1[e]++; else x1_t2[e]++; }
+        secondBestNum[e] = (o.alignmentType == 4 || o.alignmentType == 3) ? -1 : x1_t1[e] + x1_t2[e];
+        if (bestIdx[e] >= 0 && L[bestIdx[e]].algnmt != NOT_ALIGNED && (o.alignmentType != 3 || bestScoreNum[e] == 1)) {
+            const SingleAln &A = L[bestIdx[e]];
+            boundTrim[e] = ann.chrAndPosBoundaryDP(readlen[e], A.algnmt, A.cigar, &tp[e], &chr[e], newCigar[e]);
+            cigarStr[e] = boundTrim[e] ? convert_cigar(newCigar[e].c_str()) : convert_cigar(A.cigar, &deletedEnd[e]);
+            mi[e] = mis_info_for_dp(o.ax, b.quals[ids[e]].c_str(), readlen[e], A.algnmt, A.strand, boundTrim[e] ? newCigar[e].c_str() : A.cigar, boundTrim[e]);
+            if (o.alignmentType == 4 || o.alignmentType == 3) mapq[e] = 255;
+            else {
+                double thr = 0.2 * readlen[e]; if (thr < 30.0) thr = 30.0;
+                mapq[e] = mapq_for_single_dp(readlen[e] * o.matchScore, mi[e].avgMismatchQual, bestScoreNum[e], x1_t1[e], x1_t2[e], bestScore[e], secondBestScore,
+                                             o.maxMAPQ, o.minMAPQ, (int)thr, o.bwaLike ? 1 : 0);
+                if (!o.bwaLike) mapq[e] >>= 1;
+                if (mapq[e] < o.minMAPQ) mapq[e] = o.minMAPQ;
+                if (boundTrim[e]) mapq[e] = 0;        // (for the second read the reference resets it inside the same branch)
+            }
+            if ((o.alignmentType == 4 || o.alignmentType == 3) && e == 0 && boundTrim[e]) mapq[e] = 0;
+        } else bestIdx[e] = -1;
+    }
+    if (!(o.alignmentType == 1 || o.alignmentType == 2)) return;       // the reference writes these records only for all-valid / all-best
+    for (int e = 0; e < 2; ++e) {
+        const int m = 1 - e;
+        std::string xa;
+        for (size_t i = 0; i < hits[e].size(); ++i) {
+            if ((int)i == bestIdx[e]) continue;
+            if (o.alignmentType == 2 && hits[e][i].score < bestScore[e]) continue;
+            if (hits[e][i].algnmt == NOT_ALIGNED) continue;
+            xa += xa_entry(ann, hits[e][i].algnmt, hits[e][i].strand, hits[e][i].cigar, hits[e][i].editdist);
+        }
+        BamRecord rec;
+        if (bestIdx[e] >= 0)
+            init_mapped(rec, rv[e], hits[e][bestIdx[e]].strand, xa, cigarStr[e], mi[e].numMismatch, mi[e].numMismatch + mi[e].gapExt, bestScoreNum[e], secondBestNum[e],
+                        mi[e].gapOpen, mi[e].gapExt, mi[e].md, mapq[e], o.readGroup, o.printMDNM, stageId);
+        else init_unmapped(rec, rv[e], 1, xa, o.readGroup);
+        uint32_t flag = 1;
+        if (bestIdx[e] < 0) flag |= 0x4;
+        if (bestIdx[m] < 0) flag |= 0x8;
+        flag |= e == 0 ? 0x40 : 0x80;
+        if (bestIdx[e] >= 0 && hits[e][bestIdx[e]].strand == 2) flag |= 0x10;
+        if (bestIdx[m] >= 0 && hits[m][bestIdx[m]].strand == 2) flag |= 0x20;
+        rec.flag = flag;
+        rec.tid = chr[e] == 0 ? (chr[m] == 0 ? -1 : (int32_t)chr[m] - 1) : (int32_t)chr[e] - 1;
+        rec.pos = tp[e] == 0 ? (tp[m] == 0 ? -1 : (int32_t)(tp[m] - 1)) : (int32_t)(tp[e] - 1);
+        rec.mtid = chr[m] == 0 ? (chr[e] == 0 ? -1 : (int32_t)chr[e] - 1) : (int32_t)chr[m] - 1;
+        rec.mpos = tp[m] == 0 ? (tp[e] == 0 ? -1 : (int32_t)(tp[e] - 1)) : (int32_t)(tp[m] - 1);
+        if (chr[0] > 0 && chr[0] == chr[1]) {
+            // first record: tp_2 > tp_1 ? +(tp_2 - del2 + len2 - tp_1) : -(tp_1 - del1 + len1 - tp_2); second record mirrored (BGS-IO.cpp:1797-1803, 1893-1899)
+            if (e == 0) rec.isize = tp[1] > tp[0] ? (int32_t)(tp[1] - deletedEnd[1] + readlen[1] - tp[0]) : -(int32_t)(tp[0] - deletedEnd[0] + readlen[0] - tp[1]);
+            else rec.isize = tp[0] > tp[1] ? (int32_t)(tp[0] - deletedEnd[0] + readlen[0] - tp[1]) : -(int32_t)(tp[1] - deletedEnd[1] + readlen[1] - tp[0]);
+        } else rec.isize = 0;
+        o.bam->write(rec, rv[e].name->size() + 1);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -379,7 +615,38 @@ int main(int argc, char **argv)
     fprintf(stderr, "[Main] Loading time : %9.4f seconds\n\n", tIndex - t0);
     fprintf(stderr, "[Main] top_percentage: %f\n", top);
     fprintf(stderr, "[Main] Reference sequence length : %llu\n\n", (unsigned long long)ann.dnaLength);
-    if (opt.outputBAM) fprintf(stderr, "[Main] note: BAM output (-b) is not implemented in this build; only the stdout FASTQ is produced\n");
+    OutCtx octx;
+    octx.ann = &ann; octx.megapathMode = opt.megapathMode; octx.top = top; octx.ignoreComments = opt.ignoreComments != 0;
+    octx.readGroup = opt.query1; octx.printMDNM = opt.printMDNM != 0; octx.alignmentType = opt.alignmentType;
+    octx.mismatchScore = P.mismatchScore; octx.matchScore = P.matchScore; octx.minMAPQ = ini.geti("Score:MinMAPQ", 1); octx.maxMAPQ = ini.geti("Score:MaxMAPQ", 40);
+    octx.bwaLike = ini.geti("Score:BWALikeScore", 0) != 0;
+    BamWriter bamDP, bamGout, bamUnpair;
+    std::vector<uint8_t> hostPac;
+    if (opt.outputBAM) {
+        if (!octx.bwaLike) { fprintf(stderr, "-b needs Score:BWALikeScore=1 (the only MAPQ scheme of the shipped .ini files)\n"); return 1; }
+        bwase_initialize();
+        // SAMOutputHeaderConstruct (SAM.cpp:83-134)
+        std::vector<std::string> tnames; std::vector<uint32_t> tlens; std::string sq;
+        for (uint32_t i = 0; i < ann.numSeq; ++i) {
+            std::string nm = ann.names[i]; size_t e = nm.find_first_of(" \t\r\n"); if (e != std::string::npos) nm.resize(e);
+            tnames.push_back(nm); tlens.push_back((uint32_t)ann.actualLen[i]);
+            sq += "@SQ\tSN:" + nm + "\tLN:" + std::to_string(tlens.back()) + "\n";
+        }
+        std::string text = "@HD\tVN:1.3\tSO:unsorted\n@RG\tID:" + octx.readGroup + "\tSM:\t\n" + sq + "@PG\tID:soap4\tPN:soap4\tVN:megapath_b200\n";
+        bool ok = bamDP.open(opt.outputPrefix + ".dpout.1", text, tnames, tlens) && bamUnpair.open(opt.outputPrefix + ".unpair", text, tnames, tlens) &&
+                  bamGout.open(opt.outputPrefix + ".gout.1", text, tnames, tlens);
+        for (int t = 2; ok && t <= opt.numCpuThreads; ++t) {       // the reference opens one .gout file per CPU thread; the pipeline globs them
+            BamWriter extra; ok = extra.open(opt.outputPrefix + ".gout." + std::to_string(t), text, tnames, tlens); extra.close();
+        }
+        if (!ok) { fprintf(stderr, "cannot create the BAM output files with prefix %s\n", opt.outputPrefix.c_str()); return 1; }
+        if (opt.printMDNM) {                                        // MD strings need the text
+            FILE *pf = fopen((opt.indexName + ".pac").c_str(), "rb");
+            if (!pf) { fprintf(stderr, "cannot open %s.pac\n", opt.indexName.c_str()); return 1; }
+            hostPac.resize((ann.dnaLength + 3) / 4 + 8);
+            if (fread(hostPac.data(), 1, (ann.dnaLength + 3) / 4, pf) != (ann.dnaLength + 3) / 4) { fprintf(stderr, "short .pac\n"); return 1; }
+            fclose(pf); octx.ax.pac = hostPac.data();
+        }
+    }
 
     fill_char_map();
     SeqReader r1, r2;
@@ -414,32 +681,42 @@ int main(int argc, char **argv)
         fprintf(stderr, "[Main] Number of pairs aligned by DP: %llu\n", (unsigned long long)R.numRescuedPair);
         fprintf(stderr, "[Main] Number of alignments aligned by DP: %llu\n", (unsigned long long)R.numRescuedAlignment);
         totalPairsAligned += R.numDPAlignedPair + R.numRescuedPair;
-        // ---- output ----
-        if (opt.megapathMode) {
+        // ---- output: stage order of the reference (deep DP pairs, rescued pairs, then everything else) ----
+        if (opt.megapathMode || opt.outputBAM) {
+            octx.b = &b;
             std::vector<uint8_t> done(nPairs, 0);
             for (int which = 0; which < 2; ++which) {
                 const mp_pair_result *arrp = which == 0 ? R.pairs : R.rescued; uint64_t n = which == 0 ? R.n_pairs : R.n_rescued;
+                octx.bam = !opt.outputBAM ? nullptr : which == 0 ? &bamDP : &bamGout;
                 for (uint64_t i = 0, j; i < n; i = j) {
                     j = i + 1;
                     while (j < n && arrp[j].readID == arrp[i].readID) ++j;
-                    pair_fastq(outbuf, b, ann, arrp + i, arrp + j, opt.megapathMode, top, opt.ignoreComments);
+                    output_pair(octx, outbuf, arrp + i, arrp + j, R.cigars, which == 0 ? 1 : 2);      // PH: hspaux->dpStageId
                     done[arrp[i].readID >> 1] = 1;
                     if (outbuf.size() > (1u << 22)) { fwrite(outbuf.data(), 1, outbuf.size(), stdout); outbuf.clear(); }
                 }
             }
             // pairs neither placed by deep DP nor rescued: per-read single-end hits (alignment.cpp:299-351)
+            octx.bam = opt.outputBAM ? &bamUnpair : nullptr;
+            const int stageUnpaired = P.skipDefaultDP ? 2 : 3;
             uint64_t si = 0;
             for (uint32_t p = 0; p < nPairs; ++p) {
                 if (done[p]) continue;
-                for (uint32_t id = 2 * p; id < 2 * p + 2; ++id) {
+                std::vector<SingleAln> hits[2];
+                for (uint32_t e = 0; e < 2; ++e) {
+                    const uint32_t id = 2 * p + e;
                     while (si < R.n_singles && R.singles[si].readID < id) ++si;
-                    std::vector<std::pair<uint64_t, int>> hits;
-                    uint64_t e = si;
-                    while (e < R.n_singles && R.singles[e].readID == id) { hits.push_back(std::make_pair(R.singles[e].algnmt, R.singles[e].score)); ++e; }
-                    std::sort(hits.begin(), hits.end());                                     // OutputBuffer::ready: ResultCompare + unique
-                    hits.erase(std::unique(hits.begin(), hits.end()), hits.end());
-                    single_fastq(outbuf, b, ann, id, hits, opt.megapathMode, top, opt.ignoreComments);
+                    uint64_t en = si;
+                    while (en < R.n_singles && R.singles[en].readID == id) {
+                        const mp_single_result &sr = R.singles[en];
+                        SingleAln a = { sr.algnmt, sr.score, (int)sr.strand, sr.editdist, sr.num_sameScore, R.cigars + sr.cigar };
+                        hits[e].push_back(a); ++en;
+                    }
+                    // OutputBuffer::ready: sort by (algnmt, score), drop duplicates (DV-DPfunctions.h:167-196, .cpp:248-251)
+                    std::sort(hits[e].begin(), hits[e].end(), [](const SingleAln &x, const SingleAln &y) { return std::make_pair(x.algnmt, x.score) < std::make_pair(y.algnmt, y.score); });
+                    hits[e].erase(std::unique(hits[e].begin(), hits[e].end(), [](const SingleAln &x, const SingleAln &y) { return x.algnmt == y.algnmt && x.score == y.score; }), hits[e].end());
                 }
+                output_unpaired(octx, outbuf, 2 * p, hits, stageUnpaired);
                 if (outbuf.size() > (1u << 22)) { fwrite(outbuf.data(), 1, outbuf.size(), stdout); outbuf.clear(); }
             }
             fwrite(outbuf.data(), 1, outbuf.size(), stdout); outbuf.clear();
@@ -450,6 +727,7 @@ int main(int argc, char **argv)
         totalAlign += t - last; last = t;
     }
     fflush(stdout);
+    if (opt.outputBAM) { bamDP.close(); bamGout.close(); bamUnpair.close(); }
     fprintf(stderr, "[Main] Overall number of pairs of reads aligned: %llu\n", (unsigned long long)totalPairsAligned);
     fprintf(stderr, "[Main] Overall read load time : %9.4f seconds\n", totalLoad);
     fprintf(stderr, "[Main] Overall alignment time (excl. read loading) : %9.4f seconds\n", totalAlign);

@@ -102,3 +102,52 @@ def run_our_soap4(workdir, index_prefix, fq1, fq2, out_name, max_len_opt, ini="s
     if p.returncode != 0:
         raise RuntimeError("soap4 driver failed: " + p.stderr.decode()[-2000:])
     return p.stdout
+
+
+def read_bam(path):
+    """Minimal BAM decoder (BGZF members are gzip members) -> (target names, target lengths, records).
+    A record is a tuple of every field the reference writes: qname, flag, tid, pos, mapq, cigar, mtid, mpos, isize,
+    seq, qual and the raw aux bytes."""
+    import gzip
+    import struct
+    data = gzip.open(path, "rb").read()
+    assert data[:4] == b"BAM\x01"
+    l_text, = struct.unpack_from("<i", data, 4)
+    o = 8 + l_text
+    n_ref, = struct.unpack_from("<i", data, o)
+    o += 4
+    names, lens = [], []
+    for _ in range(n_ref):
+        ln, = struct.unpack_from("<i", data, o)
+        names.append(data[o + 4:o + 4 + ln - 1].decode())
+        lens.append(struct.unpack_from("<i", data, o + 4 + ln)[0])
+        o += 8 + ln
+    recs = []
+    while o < len(data):
+        bs, tid, pos, bmn, fnc, lseq, mtid, mpos, isize = struct.unpack_from("<iiiIIiiii", data, o)
+        body = data[o + 36:o + 4 + bs]
+        l_qname, mapq, nb = bmn & 0xff, (bmn >> 8) & 0xff, bmn >> 16
+        flag, ncig = fnc >> 16, fnc & 0xffff
+        qname = body[:l_qname - 1]
+        p = l_qname
+        cig = struct.unpack_from("<%dI" % ncig, body, p)
+        p += 4 * ncig
+        cigar = "".join("%d%s" % (c >> 4, "MIDNSHP=X"[c & 15]) for c in cig)
+        seq = body[p:p + (lseq + 1) // 2]
+        p += (lseq + 1) // 2
+        qual = body[p:p + lseq]
+        p += lseq
+        recs.append((qname, flag, tid, pos, mapq, cigar, mtid, mpos, isize, nb, bytes(seq), bytes(qual), bytes(body[p:])))
+        o += 4 + bs
+    return names, lens, recs
+
+
+def canon_bam(paths):
+    out = []
+    hdr = None
+    for p in paths:
+        names, lens, recs = read_bam(p)
+        hdr = (names, lens)
+        out.extend(recs)
+    out.sort(key=lambda r: (r[0], r[1] & 0xC0))
+    return hdr, out

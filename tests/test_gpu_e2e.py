@@ -62,3 +62,46 @@ def test_e2e_stdout_matches_golden(tmp_path, name):
                                     ini="soap4-nt2.ini" if nt2 else "soap4.ini"))
     want = bytes(z["fastq"])
     assert got == want, first_diff(got, want)
+
+
+BAM_SETS = [
+    ("clean", 150, 151, dict(model="clean"), "soap4.ini", ("-b", "-F", "-nc")),
+    ("mixed", 100, 101, dict(model="divergent", one_random=0.10, unalignable=0.05), "soap4.ini", ("-b", "-F", "-nc")),
+    ("nofq", 100, 101, dict(model="divergent", one_random=0.10, unalignable=0.05), "soap4.ini", ("-b",)),
+    ("span", 150, 151, dict(model="clean", span_frac=0.08), "soap4.ini", ("-b", "-F", "-nc")),
+    ("nt2p", 150, 151, dict(model="divergent", one_random=0.10), "soap4-nt2.ini", ("-b", "-F", "-nc", "-top", "95", "-p")),
+]
+
+
+@needs_ref
+@pytest.mark.parametrize("name,rlen,lopt,kw,ini,extra", BAM_SETS)
+def test_e2e_bam_matches_reference(workdir, small_ref, name, rlen, lopt, kw, ini, extra):
+    """-b: decoded records of .dpout.1 + .gout.* + .unpair (flag, pos, MAPQ, CIGAR, mate fields, isize, seq, qual, every tag)
+    equal the reference's after sorting by (read name, mate)."""
+    import glob
+    from conftest import canon_bam
+    fq1, fq2 = make_reads(workdir, small_ref, "bam_" + name, 2500, rlen, seed=41, **kw)
+    pre_r, pre_o = os.path.join(workdir, "bamref_" + name), os.path.join(workdir, "bamour_" + name)
+    for f in glob.glob(pre_r + ".*") + glob.glob(pre_o + ".*"):
+        if os.path.isfile(f):
+            os.remove(f)
+    ref_fq, _ = run_ref_soap4(workdir, small_ref["prefix"], fq1, fq2, "bamref_" + name, lopt, dump=False, ini=ini, threads=3,
+                              extra=[x for x in extra if x not in ("-F", "-nc")])
+    # run_ref_soap4 always passes -F -nc; the "nofq" set needs a run without them
+    if "-F" not in extra:
+        import subprocess
+        from conftest import REF_DIR
+        for f in glob.glob(pre_r + ".*"):
+            if os.path.isfile(f) and not f.endswith(".fq"):
+                os.remove(f)
+        subprocess.check_call([os.path.join(REF_DIR, "soap4"), "pair", small_ref["prefix"], fq1, fq2, "-o", pre_r, "-C", os.path.join(REF_DIR, ini),
+                               "-L", str(lopt), "-T", "3", "-u", "750"] + list(extra), stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=workdir)
+    got_fq = run_our_soap4(workdir, small_ref["prefix"], fq1, fq2, "bamour_" + name, lopt, ini=ini, extra=extra)
+    if "-F" in extra:
+        assert canon_fastq(got_fq) == canon_fastq(open(ref_fq, "rb").read())
+    files = lambda pre: [pre + ".dpout.1", pre + ".unpair"] + sorted(glob.glob(pre + ".gout.*"))
+    (hn_r, recs_r), (hn_o, recs_o) = canon_bam(files(pre_r)), canon_bam(files(pre_o))
+    assert hn_r == hn_o
+    assert len(recs_r) == len(recs_o) == 2 * 2500
+    for a, b in zip(recs_o, recs_r):
+        assert a == b, (a, b)
