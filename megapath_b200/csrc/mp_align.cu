@@ -269,6 +269,11 @@ extern "C" int mp_init(int device, mp_context **pctx)
     if (e != cudaSuccess || count == 0) { mp_set_error("mp_init: no CUDA device (%s); there is no CPU fallback", cudaGetErrorString(e)); return MP_ERR_CUDA; }
     if (device < 0 || device >= count) { mp_set_error("mp_init: device %d out of range (%d devices)", device, count); return MP_ERR_ARG; }
     MP_CUDA(cudaSetDevice(device));
+    {   // MP_L2_FETCH=32|64|128: optional L2 fill-granularity hint (measured: no effect on the scattered-read kernels here)
+        const char *e = getenv("MP_L2_FETCH");
+        size_t g = e ? (size_t)atoi(e) : 0;
+        if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g);
+    }
     mp_context *ctx = new mp_context;
     memset(&ctx->ix, 0, sizeof ctx->ix);
     ctx->device = device;
