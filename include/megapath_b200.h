@@ -125,6 +125,11 @@ typedef struct mp_results {
 /* ---- context ---- */
 int  mp_init(int device, mp_context **ctx);
 void mp_destroy(mp_context *ctx);
+/* second context on the same GPU that shares the resident index (and K-mer filter) of `src` without owning it: own stream,
+ * own batch / work buffers.  Two contexts driven by two host threads overlap one batch's host-side list plumbing and
+ * latency-bound traceback with the other batch's compute-bound kernels (the reference double-buffers batches the same
+ * way, SOAP4.cpp:424-441, 576-585).  `src` must outlive the clone. */
+int  mp_clone(mp_context *src, mp_context **ctx);
 const char *mp_last_error(void);
 /* number of this library's own CUDA kernels launched so far in the process (bench.py "gpu_launches") */
 uint64_t mp_launch_count(void);

@@ -81,6 +81,7 @@ def lib():
         L.mp_last_error.restype = C.c_char_p
         L.mp_init.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         L.mp_destroy.argtypes = [C.c_void_p]
+        L.mp_clone.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.mp_index_load.argtypes = [C.c_void_p, C.c_char_p]
         L.mp_index_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mp_index_build.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
@@ -181,10 +182,19 @@ def pack_dp_interleaved(seqs, lens, max_len):
 class Context:
     """One GPU context (mp_context).  Method names follow include/megapath_b200.h."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, _clone_of=None):
         self.L = lib()
         self.h = C.c_void_p()
-        self._check(self.L.mp_init(device, C.byref(self.h)))
+        if _clone_of is None:
+            self._check(self.L.mp_init(device, C.byref(self.h)))
+        else:
+            self._check(self.L.mp_clone(_clone_of.h, C.byref(self.h)))
+            self._has_index = True
+            self._parent = _clone_of          # the index owner must outlive the clone
+
+    def clone(self):
+        """Second context on the same GPU sharing this context's resident index (mp_clone)."""
+        return Context(_clone_of=self)
 
     def _check(self, rc):
         if rc != 0:

@@ -175,7 +175,8 @@ static int deep_dp(mp_context *ctx, const mp_align_params *P, mp_results *out, u
     const uint32_t CH = 1u << 18;
     DevBuf &dLT = ctx->dLT, &dRT = ctx->dRT, &dLO = ctx->dLO, &dRO = ctx->dRO, &dLP = ctx->dLP, &dRP = ctx->dRP, &dOk = ctx->dOk,
            &dBytes = ctx->dBytes, &dIdx = ctx->dIdx, &dOff = ctx->dOff, &dRes = ctx->dRes, &dCig = ctx->dCig;
-    uint32_t chunkCap = (uint32_t)std::min<uint64_t>(CH, nC ? nC : 1);
+    // full-size chunk buffers unless the whole batch is small: batch-to-batch variation must not re-allocate
+    uint32_t chunkCap = (uint32_t)std::min<uint64_t>(CH, std::max<uint64_t>((nC + nC / 4 + 1024), 1));
     if (dLT.reserve((size_t)chunkCap * sizeof(MpDpTask)) || dRT.reserve((size_t)chunkCap * sizeof(MpDpTask)) ||
         dLO.reserve((size_t)chunkCap * sizeof(MpDpOut)) || dRO.reserve((size_t)chunkCap * sizeof(MpDpOut)) ||
         dLP.reserve((size_t)chunkCap * patStride) || dRP.reserve((size_t)chunkCap * patStride) ||
@@ -200,7 +201,8 @@ static int deep_dp(mp_context *ctx, const mp_align_params *P, mp_results *out, u
         (++g_mp_launches), k_right_tasks<<<g, 128, 0, st>>>(cands, n, ctx->dLens.as<uint32_t>(), fullLen, P->peStrandRightLeg, P->insert_high,
                                          dLT.as<MpDpTask>(), dLO.as<MpDpOut>(), dRT.as<MpDpTask>(), dCnt);
         if (int rc = mpd_run_tasks(ctx, dRT.as<MpDpTask>(), n, maxDNALength, maxReadLength, dpr, dRO.as<MpDpOut>(), dRP.as<uint8_t>(), patStride)) return rc;
-        if (tr.on) { cudaStreamSynchronize(st); tr.mark(" dp left+right"); }
+        if (tr.sync) cudaStreamSynchronize(st);
+        tr.mark(" dp left+right (enqueue)");
         MP_CUDA(cudaMemsetAsync(dOk.p, 0, ((size_t)n + 1) * 4, st));
         MP_CUDA(cudaMemsetAsync(dBytes.p, 0, ((size_t)n + 1) * 4, st));
         (++g_mp_launches), k_assemble_measure<<<g, 128, 0, st>>>(n, dLT.as<MpDpTask>(), dLO.as<MpDpOut>(), dRT.as<MpDpTask>(), dRO.as<MpDpOut>(),
@@ -212,7 +214,8 @@ static int deep_dp(mp_context *ctx, const mp_align_params *P, mp_results *out, u
         MP_CUDA(cudaMemcpyAsync(&nOk, dIdx.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
         MP_CUDA(cudaMemcpyAsync(&nBytes, dOff.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
         MP_CUDA(cudaStreamSynchronize(st));
-        if (dCig.reserve((size_t)nBytes + 16)) return MP_ERR_CUDA;
+        tr.mark(" sync after measure");
+        if (dCig.reserve(std::max<size_t>((size_t)nBytes + 16, (size_t)chunkCap * 40))) return MP_ERR_CUDA;
         uint32_t cigBase = (uint32_t)HC.size();
         if (nOk) {
             (++g_mp_launches), k_assemble_write<<<g, 128, 0, st>>>(n, cands, dLT.as<MpDpTask>(), dLO.as<MpDpOut>(), dRT.as<MpDpTask>(), dRO.as<MpDpOut>(),
@@ -282,10 +285,23 @@ extern "C" int mp_init(int device, mp_context **pctx)
     *pctx = ctx;
     return 0;
 }
+extern "C" int mp_clone(mp_context *src, mp_context **pctx)
+{
+    if (!src || !pctx) { mp_set_error("mp_clone: null argument"); return MP_ERR_ARG; }
+    if (!src->hasIndex) { mp_set_error("mp_clone: the source context has no index"); return MP_ERR_STATE; }
+    if (int rc = mp_init(src->device, pctx)) return rc;
+    mp_context *c = *pctx;
+    c->ix = src->ix; c->saInterval = src->saInterval; c->hbmBytes = src->hbmBytes;
+    c->hasIndex = true; c->sharedIndex = true;
+    c->bloomK = src->bloomK; c->bloomWords = src->bloomWords; c->bloomFor = src->bloomFor;
+    c->dBloom.p = src->dBloom.p; c->dBloom.cap = 0;          // borrowed: never freed or grown by the clone
+    return 0;
+}
 extern "C" void mp_destroy(mp_context *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->sharedIndex && ctx->dBloom.cap == 0) ctx->dBloom.p = nullptr;
     for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
     DevBuf *bufs[] = { &ctx->dBlocks, &ctx->dSuper, &ctx->dSa, &ctx->dSa32, &ctx->dBloom, &ctx->dLkt, &ctx->dPac, &ctx->dReadsIl, &ctx->dReads, &ctx->dLens,
                        &ctx->dCounters, &ctx->dSeeds, &ctx->dStubs, &ctx->dHitsPerRead, &ctx->dHitStart, &ctx->dCursor, &ctx->dHits,

@@ -8,16 +8,17 @@
 #include <vector>
 #include <cuda_runtime.h>
 #include <chrono>
+#include <atomic>
 #include "../../include/megapath_b200.h"
 #include "mp_index.cuh"
 
 void mp_set_error(const char *fmt, ...);
-extern unsigned long long g_mp_launches;
+extern std::atomic<unsigned long long> g_mp_launches;
 static inline double mp_now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 // MP_TRACE=1: wall-clock phase marks on stderr
 struct MpTrace {
-    bool on; double t0, last;
-    MpTrace() { const char *e = getenv("MP_TRACE"); on = e && *e && *e != '0'; t0 = last = mp_now_ms(); }
+    bool on, sync; double t0, last;      // MP_TRACE=1: marks + extra stream syncs at phase ends; MP_TRACE=2: marks only
+    MpTrace() { const char *e = getenv("MP_TRACE"); on = e && *e && *e != '0'; sync = on && *e == '1'; t0 = last = mp_now_ms(); }
     void mark(const char *what) { if (!on) return; double t = mp_now_ms(); fprintf(stderr, "[mp_trace] %-28s +%9.3f ms (%9.3f)\n", what, t - last, t - t0); last = t; }
 };     // kernels of this library launched so far (mp_launch_count)
 
@@ -112,7 +113,7 @@ struct mp_context {
         evUsed = 0;
     }
     // index
-    bool hasIndex = false;
+    bool hasIndex = false, sharedIndex = false;   // sharedIndex: index buffers belong to another context (mp_clone)
     MpIndexView ix;
     DevBuf dBlocks, dSuper, dSa, dSa32, dLkt, dPac, dBloom;
     int bloomK = 0; uint64_t bloomWords = 0; const void *bloomFor = nullptr;   // K-mer presence filter (mp_seed.cu)

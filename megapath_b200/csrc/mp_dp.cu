@@ -339,11 +339,16 @@ static int launch_dp(mp_context *ctx, const uint8_t *dRef, const uint32_t *dRefL
     const int S = (int)maxRefLen + 33;                        // steps 1 .. maxRefLen + 31, plus slack
     const size_t tableStride = (size_t)S * 32 * K;
     if (ctx->dFill.reserve((size_t)nTasks * sizeof(FillOut))) return MP_ERR_CUDA;
-    // the traceback tables of one sub-batch stay in HBM between the two kernels
-    size_t freeB = 0, totalB = 0; cudaMemGetInfo(&freeB, &totalB);
-    const size_t maxBytes = std::min<size_t>((size_t)24 << 30, (freeB + ctx->dTable.cap) / 2);
-    const size_t want = std::min<size_t>((size_t)nTasks * tableStride, maxBytes);
-    if (ctx->dTable.cap < want && ctx->dTable.reserve(want)) return MP_ERR_CUDA;
+    // the traceback tables of one sub-batch stay in HBM between the two kernels.  A chunk of stage S1 has up to 2^18 tasks:
+    // size for that even when this launch is smaller, and only talk to the allocator when the buffer really is too small
+    const size_t typical = nTasks >= (1u << 15) ? (size_t)(1u << 18) * tableStride : (size_t)nTasks * tableStride;
+    const size_t ideal = std::max<size_t>((size_t)nTasks * tableStride, typical);
+    if (ctx->dTable.cap < ideal) {
+        size_t freeB = 0, totalB = 0; cudaMemGetInfo(&freeB, &totalB);
+        const size_t maxBytes = std::min<size_t>((size_t)24 << 30, (freeB + ctx->dTable.cap) / 2);
+        const size_t want = std::min<size_t>(ideal, maxBytes);
+        if (ctx->dTable.cap < want && ctx->dTable.reserve(want)) return MP_ERR_CUDA;
+    }
     uint32_t per = (uint32_t)std::min<size_t>(nTasks, ctx->dTable.cap / tableStride);
     if (per < nTasks) per &= ~1u;                              // sub-batches start on a task pair
     if (per == 0) { mp_set_error("not enough device memory for the DP traceback tables"); return MP_ERR_CUDA; }

@@ -15,8 +15,8 @@ void mp_set_error(const char *fmt, ...)
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
 }
 extern "C" const char *mp_last_error(void) { return g_err; }
-unsigned long long g_mp_launches = 0;
-extern "C" uint64_t mp_launch_count(void) { return g_mp_launches; }
+std::atomic<unsigned long long> g_mp_launches(0);
+extern "C" uint64_t mp_launch_count(void) { return g_mp_launches.load(); }
 
 // ---- file -> device in bounded chunks ----
 static int upload_region(FILE *f, uint64_t fileOff, uint64_t bytes, void *dst)

@@ -15,6 +15,7 @@
 //   k_pair     one thread per pair and orientation: window join -> CandidateInfo.
 #include "mp_context.h"
 #include <cub/device/device_scan.cuh>
+#include <algorithm>
 
 struct MmpDev {
     int seedSAsizeThreshold, seedMinLength, uniqThreshold, indelFuzz, goodSeedLen, reseedLen, reseedAbsDiff;
@@ -451,6 +452,7 @@ static int ensure_bloom(mp_context *ctx, int seedMinLength)
     if (ctx->bloomK == K && ctx->bloomFor == (const void *)ctx->ix.blocks) return 0;
     if (n < (uint64_t)K) { ctx->bloomK = 0; return 0; }
     uint64_t nWords = n / 4 + 1024;                      // 16 bits per text position
+    if (ctx->sharedIndex && ctx->dBloom.cap == 0) ctx->dBloom.p = nullptr;      // a borrowed filter with another K: build our own
     if (ctx->dBloom.reserve(nWords * 8)) return MP_ERR_CUDA;
     MP_CUDA(cudaMemsetAsync(ctx->dBloom.p, 0, nWords * 8, ctx->stream));
     uint64_t threads = (n + 63) / 64;
@@ -502,8 +504,9 @@ int mps_seed_pairs(mp_context *ctx, const mp_align_params *AP)
     ctx->nSeeds = hc[0]; ctx->nHits = hc[1];
     if (ctx->nHits > 0xFFFFFFF0ull) { mp_set_error("too many seed hits in one batch"); return MP_ERR_CAPACITY; }
     if (exclusive_scan_u32(ctx, ctx->dHitsPerRead.as<uint32_t>(), ctx->dHitStart.as<uint32_t>(), (uint64_t)nReads + 1)) return MP_ERR_CUDA;
-    size_t hitBytes = (ctx->nHits + 1) * sizeof(MpHit);
-    if (ctx->dHits.reserve(hitBytes) || ctx->dSeedPos.reserve((ctx->nHits + 1) * sizeof(mp_seed_pos))) return MP_ERR_CUDA;
+    // sized with a floor per read so that batch-to-batch variation does not trigger re-allocation (a cudaFree synchronises the device)
+    const size_t hitSlots = std::max<size_t>(ctx->nHits + 1, (size_t)nReads * 3);
+    if (ctx->dHits.reserve(hitSlots * sizeof(MpHit)) || ctx->dSeedPos.reserve(hitSlots * sizeof(mp_seed_pos))) return MP_ERR_CUDA;
     MP_CUDA(cudaMemsetAsync(ctx->dCursor.p, 0, ((size_t)nReads + 1) * 4, st));
     if (ctx->nHits)
         (++g_mp_launches), k_expand<<<(unsigned)((ctx->nHits + 127) / 128), 128, 0, st>>>(ctx->ix, ctx->dSeeds.as<MpSeed>(), ctx->dStubs.as<uint32_t>(), ctx->nHits,
@@ -525,7 +528,7 @@ int mps_seed_pairs(mp_context *ctx, const mp_align_params *AP)
     MP_CUDA(cudaMemcpyAsync(&total, ctx->dCandStart.as<uint32_t>() + nPairs, 4, cudaMemcpyDeviceToHost, st));
     MP_CUDA(cudaStreamSynchronize(st));
     ctx->nCands = total;
-    if (ctx->dCands.reserve(((size_t)total + 1) * sizeof(mp_candidate))) return MP_ERR_CUDA;
+    if (ctx->dCands.reserve(std::max<size_t>((size_t)total + 1, (size_t)nPairs * 2) * sizeof(mp_candidate))) return MP_ERR_CUDA;
     if (total)
         (++g_mp_launches), k_pair<<<(nPairs + 127) / 128, 128, 0, st>>>(ctx->dHitStart.as<uint32_t>(), ctx->dSeedPos.as<mp_seed_pos>(), ctx->dNPos.as<uint32_t>(),
             ctx->dNNeg.as<uint32_t>(), ctx->dLens.as<uint32_t>(), nPairs, AP->insert_low, AP->insert_high,

@@ -119,6 +119,7 @@ int mps_single_and_rescue(mp_context *ctx, const mp_align_params *P, mp_results 
         return MP_ERR_ARG;
     }
     const std::vector<uint32_t> &lens = ctx->hLens;
+    MpTrace tr;
     std::vector<SCand> cand;
     {
         unsigned int *dCur = (unsigned int *)(ctx->dCounters.as<unsigned long long>() + 13);       // [13]: cursor, unplaced pairs
@@ -144,6 +145,7 @@ int mps_single_and_rescue(mp_context *ctx, const mp_align_params *P, mp_results 
             cand[i] = c;
         }
     }
+    tr.mark("  s2 gather seeds");
     SCand sentinel; sentinel.readID = 0x7FFFFFFFu; sentinel.strand = 2; sentinel.pos = 0xFFFFFFFFull; sentinel.seedLen = 0xFFFFFFFFu;
     cand.push_back(sentinel);
     std::sort(cand.begin(), cand.end(), scand_less);
@@ -174,9 +176,11 @@ int mps_single_and_rescue(mp_context *ctx, const mp_align_params *P, mp_results 
         tasks[i] = t;
         cells += (uint64_t)dnaLen * readLength; ++tasksRun;
     }
+    tr.mark("  s2 merge+tasks");
     std::vector<MpDpOut> outs; std::vector<uint8_t> pats;
     uint32_t patStride = maxDNALengthS + maxReadLength;
     if (int rc = mpd_run_host_tasks(ctx, tasks, maxDNALengthS, maxReadLength, dp, outs, pats, patStride)) return rc;
+    tr.mark("  s2 dp");
     std::vector<mp_single_result> &S = ctx->hSingles;
     PinnedBuf<char> &HC = ctx->hCigars;
     for (size_t i = 0; i < tasks.size(); ++i) {
@@ -203,6 +207,7 @@ int mps_single_and_rescue(mp_context *ctx, const mp_align_params *P, mp_results 
         out->numSingleDPAligned += 1;
         out->numSingleDPAlignment += (uint64_t)(std::unique(k.begin(), k.end()) - k.begin());
     }
+    tr.mark("  s2 assemble");
     if (P->skipDefaultDP || S.empty()) return 0;
 
     // ---- S3: sort by (readID, score desc) then (readID, score desc, startPos) ----
@@ -252,9 +257,11 @@ int mps_single_and_rescue(mp_context *ctx, const mp_align_params *P, mp_results 
         if (t.refLen > maxDNALengthR) { mp_set_error("default DP window %u exceeds maxDNALength %u", t.refLen, maxDNALengthR); return MP_ERR_CAPACITY; }
         cells += (uint64_t)t.refLen * t.readLen; ++tasksRun;
     }
+    tr.mark("  s3 tasks");
     std::vector<MpDpOut> routs; std::vector<uint8_t> rpats;
     const uint32_t rStride = maxDNALengthR + maxReadLength;
     if (int rc = mpd_run_host_tasks(ctx, rtasks, maxDNALengthR, maxReadLength, dp, routs, rpats, rStride)) return rc;
+    tr.mark("  s3 dp");
     // ---- AlgnmtDPResult records, grouped per pair (DV-DPfunctions.cpp:1476-1747) ----
     struct ADP { uint64_t a1, a2; int s1, s2; int which; mp_pair_result full; };
     std::vector<ADP> group;
@@ -321,5 +328,6 @@ int mps_single_and_rescue(mp_context *ctx, const mp_align_params *P, mp_results 
         group.push_back(a);
     }
     flush();
+    tr.mark("  s3 assemble");
     return 0;
 }
