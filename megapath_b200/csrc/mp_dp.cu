@@ -49,7 +49,7 @@ __device__ __forceinline__ size_t cell_offset(int r, int c, int S)
 template <int K>
 __device__ __forceinline__ uint8_t load_cell(const uint8_t *__restrict__ tab, int r, int c, int S)
 {
-    return tab[cell_offset<K>(r, c, S)];
+    return __ldcs(tab + cell_offset<K>(r, c, S));      // every table byte is read once or twice: do not let it evict the sequences from L1
 }
 // flag of any cell including the virtual row 0 / column 0
 template <int K>
@@ -181,22 +181,6 @@ k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLe
                 if (hasB) *(uint16_t *)(tabB + off) = (uint16_t)(((code[K - 2] >> 16) & 0xff) | (((code[K - 1] >> 16) & 0xff) << 8));
             }
             sendH = Hleft; sendI = Il;
-        } else if (!laneActive && i >= 1 && i <= maxN) {
-            // lanes past the last read column only complete the 32-byte sectors of this step's trace rows, so that
-            // no sector is written partially (a partial sector costs a DRAM read-modify-write when L2 evicts it)
-#pragma unroll
-            for (int w = 0; w < WORDS; ++w) {
-                const size_t off = (size_t)w * S * 128 + (size_t)t * 128 + lane * 4;
-                *(uint32_t *)(tabA + off) = 0u;
-                if (hasB) *(uint32_t *)(tabB + off) = 0u;
-            }
-            if (REM == 1) {
-                const size_t off = (size_t)WORDS * S * 128 + (size_t)t * 32 + lane;
-                tabA[off] = 0; if (hasB) tabB[off] = 0;
-            } else if (REM == 2) {
-                const size_t off = (size_t)WORDS * S * 128 + ((size_t)t * 32 + lane) * 2;
-                *(uint16_t *)(tabA + off) = 0; if (hasB) *(uint16_t *)(tabB + off) = 0;
-            }
         }
     }
     // ---- winner per task: max score, then smallest (row, col); ties summed ----
@@ -256,17 +240,26 @@ k_dp_tb(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLens
     enum { NORMAL, I_EXT, D_EXT, SM_EXIT, SI_EXIT, SD_EXIT };
     int state = NORMAL;
     int accum = 0;
+    // `diagCell` carries the byte of (j-1, i-1) from the clip check of one step to the next step, which usually moves there
+    uint32_t cell = load_cell<K>(tab, j, i, S);
     while (i > 0 && j > 0) {
-        uint32_t cell = load_cell<K>(tab, j, i, S);
         int flag = cell % 3;
         int hd = open + (int)(cell / 3 % 14);
         int dd = mm + (int)(cell / 42);
         bool eq = fs[j - 1] == rs[i - 1];
         int ms = eq ? 1 : mm;
         if (state == NORMAL) {
-            if (dd == ms && i != 1 && cell_flag<K>(tab, j - 1, i - 1, clipLt, S) == 0) { state = SM_EXIT; break; }
-            else if (dd == ms) { pat[p++] = eq ? 'M' : 'm'; --j; --i; }
-            else if (flag == 1) {
+            if (dd == ms) {
+                // flag of the diagonal predecessor, including the virtual row 0 / column 0 (CPU_DP.cpp:405-450)
+                uint32_t diagCell = 0; int dflag;
+                if (i - 1 == 0) dflag = 0;
+                else if (j - 1 == 0) dflag = (i - 1) <= clipLt ? 0 : 1;
+                else { diagCell = load_cell<K>(tab, j - 1, i - 1, S); dflag = diagCell % 3; }
+                if (i != 1 && dflag == 0) { state = SM_EXIT; break; }
+                pat[p++] = eq ? 'M' : 'm'; --j; --i;
+                cell = diagCell;                                     // valid whenever the loop continues (i > 0 && j > 0)
+                continue;
+            } else if (flag == 1) {
                 int vd = dd - cell_hd<K>(tab, j - 1, i, clipLt, open, S);
                 pat[p++] = 'D'; --j;
                 if (vd != open) { accum = (int8_t)(vd - ext); state = D_EXT; }
@@ -284,6 +277,7 @@ k_dp_tb(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLens
             pat[p++] = 'I'; --i;
             if (hd + accum == open) state = NORMAL; else accum = (int8_t)(accum + hd - ext);
         }
+        if (i > 0 && j > 0) cell = load_cell<K>(tab, j, i, S);
     }
     bool discard = false;
     if (j == 0) {

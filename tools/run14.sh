@@ -1,4 +1,7 @@
-export MP_BENCH_VERBOSE=1 MP_BENCH_CONTEXTS=1
-for mode in "MP_BENCH_NO_SAMPLER=1" "MP_BENCH_SAMPLE_MS=200" "MP_BENCH_SAMPLE_MS=1000"; do
-  echo "== $mode"; env $mode python bench.py --no-cpu-baseline --steps 8 2>&1 >/dev/null | grep "ctx " | awk '{printf "%s ", $7}'; echo
+export MP_BENCH_VERBOSE=1
+for c in 1 2; do echo "== contexts $c"; MP_BENCH_CONTEXTS=$c python bench.py --no-cpu-baseline --steps 8 > gpurun_out/bc$c.json 2> gpurun_out/bc$c.err; grep "ctx " gpurun_out/bc$c.err | awk '{printf "%s ", $7}'; echo; python - <<PY
+import json
+d=json.load(open('gpurun_out/bc$c.json'))
+print({k:d[k] for k in ('value','ms_per_step')}, d['e2e']['value'])
+PY
 done
