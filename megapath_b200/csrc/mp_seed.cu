@@ -158,6 +158,28 @@ __device__ __forceinline__ void occ_pair(const MpIndexView &ix, uint64_t a, uint
 //   reference; a seed that ends in phase B already knows its text position and skips SA resolution.
 //   nOcc counts the occ evaluations the reference performs for the same steps (2 per step).
 // ------------------------------------------------------------------------------------
+// 16 text bases ending just before position p (p >= 1), text[p-1-t] at bits 2t; positions before the text start read as 0
+__device__ __forceinline__ uint32_t text_window_before(const MpIndexView &ix, uint64_t p)
+{
+    const int64_t first = (int64_t)p - 16;                          // base offset of the window start (may be negative)
+    const uint64_t f = first < 0 ? 0 : (uint64_t)first;
+    const uint64_t byte0 = (f >> 2) & ~3ull;                        // 4-byte aligned
+    const uint32_t *wp = (const uint32_t *)(ix.pac + byte0);
+    const uint32_t w0 = __byte_perm(__ldg(wp), 0, 0x0123), w1 = __byte_perm(__ldg(wp + 1), 0, 0x0123);   // big-endian: first base in the top bits
+    const uint32_t sh = (uint32_t)(f - byte0 * 4) * 2;
+    uint32_t t = __funnelshift_l(w1, w0, sh);                       // bases f .. f+15, base f in the top bits
+    if (first < 0) t >>= (uint32_t)(-first) * 2;                    // keep text[p-1] in the lowest group
+    return t;
+}
+__device__ __forceinline__ uint32_t group_reverse(uint32_t v)       // reverse the order of the sixteen 2-bit groups
+{
+    v = __brev(v);
+    return ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+}
+
+// one thread per read-strand, written as a state machine: every trip of the loop performs ONE unit of work of the lane's
+// current state (4 filter probes + LKT jump | one backward-search step | up to 16 text bases), so lanes of a warp that
+// are in different phases of their reads still share every trip instead of waiting for each other's inner loops
 __global__ void __launch_bounds__(128)
 k_mmp(MpIndexView ix, const uint32_t *__restrict__ reads, const uint32_t *__restrict__ lens, uint32_t wpq,
       uint32_t nStrands, MmpDev P, MpSeed *__restrict__ seeds, uint32_t *__restrict__ stubs,
@@ -167,78 +189,98 @@ k_mmp(MpIndexView ix, const uint32_t *__restrict__ reads, const uint32_t *__rest
     const uint64_t n = ix.n;
     unsigned long long nOcc = 0, nLkt = 0, nSaIn = 0, nLfIn = 0, nProbe = 0, nText = 0;
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nStrands; s += stride) {
-        const uint32_t read = s >> 1, strand = s & 1;
+    enum { ST_SCAN, ST_STEP, ST_TEXT, ST_DONE };
+    // Work order: first every read on the strand that matches its mate number (mate 1 '+', mate 2 '-': the strand an FR
+    // library aligns on), then every read on the other strand, so that the lanes of a warp mostly share a state.
+    const uint32_t nReadsK = nStrands >> 1;
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < nStrands; w += stride) {
+        const uint32_t group = w >= nReadsK, read = group ? w - nReadsK : w, strand = (read & 1u) ^ group;
+        const uint32_t s = read * 2 + strand;
         const int len = (int)lens[read];
         const uint32_t *rd = reads + (size_t)read * wpq;
-        int i = 0, seed_len = 0;
-        uint64_t l = 0, r = n, nextl = 0, nextr = 0, last_l = 0, last_r = n;
-        int last_seed_len = 0;
-        bool done = false;
-        while (!done) {
-            bool emit = false, resolved = false; int x = 0;
-            uint64_t textPos = 0;
-            if (i < len) {
-                bool step = true;
-                if (seed_len == 0) {
-                    // skip start positions whose first K bases certainly do not occur in the text (4 probes in flight)
-                    while (bloom && len - i >= P.seedMinLength) {
-                        const int m = min(4, len - i - P.seedMinLength + 1);
-                        unsigned long long w[4]; uint64_t mk[4];
+        int i = 0, seed_len = 0, last_seed_len = 0;
+        uint64_t l = 0, r = n, last_l = 0, last_r = n, p = 0;
+        int state = ST_SCAN;
+        while (state != ST_DONE) {
+            bool emit = false, resolved = false, finishing = false, haveNext = false;
+            uint64_t nextl = 0, nextr = 0;
+            if (state == ST_SCAN) {                                   // seed_len == 0: look for the next start worth searching
+                if (len - i < P.seedMinLength) { state = ST_DONE; continue; }
+                bool go = true;
+                if (bloom) {                                          // 4 probes in flight
+                    const int m = min(4, len - i - P.seedMinLength + 1);
+                    unsigned long long wv[4]; uint64_t mk[4];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            w[j] = ~0ull; mk[j] = 0;
-                            if (j < m) { uint64_t wi; bloom_slot(scan_kmer(rd, len, i + j, strand, bloomK), bloomWords, wi, mk[j]); w[j] = __ldg(bloom + wi); }
-                        }
-                        nProbe += m;
-                        int hit = m;
+                    for (int j = 0; j < 4; ++j) {
+                        wv[j] = ~0ull; mk[j] = 0;
+                        if (j < m) { uint64_t wi; bloom_slot(scan_kmer(rd, len, i + j, strand, bloomK), bloomWords, wi, mk[j]); wv[j] = __ldg(bloom + wi); }
+                    }
+                    nProbe += m;
+                    int hit = m;
 #pragma unroll
-                        for (int j = 3; j >= 0; --j) if (j < m && (w[j] & mk[j]) == mk[j]) hit = j;
-                        i += hit;
-                        if (hit < m) break;
-                    }
-                    if (len - i < P.seedMinLength) { step = false; emit = true; x = strand ? len - seed_len : 0; done = true; }
-                    else {
-                        uint32_t key = lkt_key(rd, len, i, strand);
-                        nextl = key == 0 ? 1 : __ldg(ix.lkt + key - 1) + 1;
-                        nextr = __ldg(ix.lkt + key);
-                        i += 12; seed_len = 12; ++nLkt;
-                    }
-                } else {
+                    for (int j = 3; j >= 0; --j) if (j < m && (wv[j] & mk[j]) == mk[j]) hit = j;
+                    i += hit;
+                    go = hit < m;
+                }
+                if (go) {
+                    uint32_t key = lkt_key(rd, len, i, strand);
+                    nextl = key == 0 ? 1 : __ldg(ix.lkt + key - 1) + 1;
+                    nextr = __ldg(ix.lkt + key);
+                    i += 12; seed_len = 12; ++nLkt; haveNext = true;
+                }
+            } else if (state == ST_STEP) {                            // one backward-search step on a range of several suffixes
+                if (i >= len) { emit = true; finishing = true; }
+                else {
                     uint32_t c = strand ? 3 - read_base(rd, i) : read_base(rd, len - 1 - i);
                     uint64_t a = l - (l > ix.inverseSa0), b = (r + 1) - ((r + 1) > ix.inverseSa0);
                     uint64_t ra, rb;
                     occ_pair(ix, a, b, c, ra, rb);
                     nextl = mp_cum(ix, c) + ra + 1;
                     nextr = mp_cum(ix, c) + rb;
-                    nOcc += 2;
+                    nOcc += 2; haveNext = true;
                 }
-                if (step) {
-                    if (nextl <= nextr) {
-                        if (seed_len >= P.seedMinLength && nextr - nextl < r - l) { last_r = r; last_l = l; last_seed_len = seed_len; }
-                        l = nextl; r = nextr; ++seed_len;
-                        if (l == r) {
-                            // ---- phase B: single suffix, extend against the text ----
-                            uint32_t steps = 0;
-                            uint64_t p = mp_sa(ix, l, &steps);
-                            ++nSaIn; nLfIn += steps;
-                            int ii = i + 1;
-                            while (ii < len) {
-                                uint32_t c = strand ? 3 - read_base(rd, ii) : read_base(rd, len - 1 - ii);
-                                nOcc += 2; ++nText;
-                                if (p == 0 || mp_text_base(ix, p - 1) != c) break;
-                                --p; ++seed_len; ++ii;
-                            }
-                            i = ii;
-                            emit = true; resolved = true; textPos = p;
-                            x = strand ? i - seed_len : len - i;
-                            if (i >= len) done = true;
-                        }
-                    } else { emit = true; x = strand ? i - seed_len : len - i; }
+            } else {                                                  // ST_TEXT: single suffix at text position p, up to 16 bases per trip
+                if (i >= len) { emit = true; finishing = true; resolved = true; }
+                else {
+                    const int m = min(16, len - i);
+                    uint32_t tw = text_window_before(ix, p), d;
+                    int matched;
+                    if (strand) {                                     // c_t = 3 - read[i+t] against text[p-1-t]
+                        uint32_t rw = (uint32_t)read_window(rd, i, 16);
+                        d = ~(rw ^ tw);                               // group == 0 where the bases agree
+                        d = (d | (d >> 1)) & 0x55555555u;
+                        matched = d ? (__ffs(d) - 1) >> 1 : 16;
+                    } else {                                          // c_t = read[len-1-i-t] against text[p-1-t]
+                        const int start = len - 1 - i - 15;
+                        uint32_t rw = start >= 0 ? (uint32_t)read_window(rd, start, 16) : ((uint32_t)read_window(rd, 0, 16) << (uint32_t)(-start * 2));
+                        d = rw ^ group_reverse(tw);                   // read[len-1-i-t] and text[p-1-t] both at group 15-t
+                        d = (d | (d >> 1)) & 0x55555555u;
+                        matched = d ? __clz(d) >> 1 : 16;
+                    }
+                    int lim = m; if ((uint64_t)lim > p) lim = (int)p;
+                    const bool failed = matched < lim || lim < m;     // a mismatch, or the text start reached, inside this read
+                    if (matched > lim) matched = lim;
+                    p -= matched; seed_len += matched; i += matched;
+                    nOcc += 2ull * matched; nText += matched;
+                    if (failed) { nOcc += 2; ++nText; emit = true; resolved = true; }
+                    else if (i >= len) { emit = true; finishing = true; resolved = true; }
                 }
-            } else { emit = true; x = strand ? len - seed_len : 0; done = true; }
+            }
+            if (haveNext) {
+                if (nextl <= nextr) {
+                    if (seed_len >= P.seedMinLength && nextr - nextl < r - l) { last_r = r; last_l = l; last_seed_len = seed_len; }
+                    l = nextl; r = nextr; ++seed_len; ++i;
+                    if (l == r) {
+                        uint32_t steps = 0;
+                        p = mp_sa(ix, l, &steps);
+                        ++nSaIn; nLfIn += steps;
+                        state = ST_TEXT;
+                    } else state = ST_STEP;
+                } else emit = true;
+            }
             if (emit) {
-                // CHECK_AND_ADD_RANGE (DV-DPfunctions.cpp:2197-2219)
+                // CHECK_AND_ADD_RANGE (DV-DPfunctions.cpp:2197-2219); x as at DV-DPfunctions.cpp:2252-2262, 2362-2372
+                int x = strand ? (finishing ? len : i) - seed_len : (finishing ? 0 : len - i);
                 int diff = 0;
                 if (seed_len >= P.seedMinLength) {
                     if (seed_len >= P.reseedLen && last_r - last_l + 1 <= (uint64_t)P.seedSAsizeThreshold &&
@@ -254,18 +296,22 @@ k_mmp(MpIndexView ix, const uint32_t *__restrict__ reads, const uint32_t *__rest
                     uint32_t hb = (uint32_t)atomicAdd(&counters[1], (unsigned long long)cnt);
                     atomicAdd(&hitsPerRead[read], cnt);
                     if (slot < capSeeds) {
-                        MpSeed sd; sd.sa_l = resolved ? textPos : l; sd.strandIdx = s; sd.hitBase = hb;
+                        MpSeed sd; sd.sa_l = resolved ? p : l; sd.strandIdx = s; sd.hitBase = hb;
                         sd.query_offset = (uint16_t)(x & 0x3ff); sd.seed_len = (uint16_t)(seed_len & 0xfff);
                         sd.sa_diff = (uint16_t)d; sd.pad = resolved ? 1 : 0;
                         seeds[slot] = sd;
                     }
                     for (uint32_t k = 0; k < cnt; ++k) if (hb + k < capStubs) stubs[hb + k] = slot;
                 }
-                i -= diff;
-                i -= min(seed_len, P.seedMinLength);
-                l = 0; r = n; seed_len = 0; last_l = 0; last_r = n; last_seed_len = 0;
+                if (finishing) state = ST_DONE;
+                else {
+                    i -= diff;
+                    i -= min(seed_len, P.seedMinLength);
+                    ++i;
+                    l = 0; r = n; seed_len = 0; last_l = 0; last_r = n; last_seed_len = 0;
+                    state = ST_SCAN;
+                }
             }
-            ++i;
         }
     }
     // per-warp reduction of the work counters
