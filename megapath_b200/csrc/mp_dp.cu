@@ -14,7 +14,7 @@
 // Lane l owns read columns l*K+1 .. l*K+K and walks the reference rows with a one-row skew per lane
 // (anti-diagonal wavefront); the right-most H / I of a lane's strip travel to lane l+1 by shuffle, the
 // reference rows come from shared memory.  Every cell leaves one traceback byte
-//    (H-Hdiag-mm)*42 + (H-Hleft-open)*3 + flag      flag 0 = raised by the clip floor, 1 = D==H, 2 = otherwise
+//    (H-Hdiag-mm)*42 + (H-Hleft-open)*3 + g          g 0 = D==H, 1 = neither, 2 = raised by the clip floor
 // (the information the reference keeps, CPU_DP.cpp:183, 529-533) in a step-major table in HBM:
 // a warp's stores of one step are one contiguous 128-byte (+32-byte) segment per task.
 // The answer cell (first strict maximum in row-major order, tie count, CPU_DP.cpp:545-590) is kept per
@@ -51,13 +51,15 @@ __device__ __forceinline__ uint8_t load_cell(const uint8_t *__restrict__ tab, in
 {
     return __ldcs(tab + cell_offset<K>(r, c, S));      // every table byte is read once or twice: do not let it evict the sequences from L1
 }
+// third digit of a trace byte -> the reference's flag (0 = raised by the clip floor, 1 = D==H, 2 = otherwise; CPU_DP.cpp:529-533)
+__device__ __forceinline__ int trace_flag(uint32_t cell) { const int g = (int)(cell % 3); return g == 2 ? 0 : g + 1; }
 // flag of any cell including the virtual row 0 / column 0
 template <int K>
 __device__ __forceinline__ int cell_flag(const uint8_t *__restrict__ tab, int r, int c, int clipLt, int S)
 {
     if (c == 0) return 0;                       // column 0 cells are stored as 0 (CPU_DP.cpp:447-450)
     if (r == 0) return c <= clipLt ? 0 : 1;     // row 0 (CPU_DP.cpp:405-427)
-    return load_cell<K>(tab, r, c, S) % 3;
+    return trace_flag(load_cell<K>(tab, r, c, S));
 }
 // H[r][c] - H[r][c-1] for any row including row 0
 template <int K>
@@ -67,7 +69,9 @@ __device__ __forceinline__ int cell_hd(const uint8_t *__restrict__ tab, int r, i
     return open + (int)(load_cell<K>(tab, r, c, S) / 3 % 14);
 }
 
-template <int K>
+// MM / OPEN: mismatch score and gap-open score as compile-time constants (0 = take them from P at run time), so that the
+// packed constants become immediates of the DPX / IADD3 instructions
+template <int K, int MM, int OPEN>
 __global__ void __launch_bounds__(128)
 k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLens, uint32_t refStride,
           const uint8_t *__restrict__ readSeq, const uint32_t *__restrict__ readLens, uint32_t readStride,
@@ -81,7 +85,7 @@ k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLe
     if (lA >= nTasks) return;
     const uint32_t tA = taskBase + lA, tB = taskBase + lB;
     const bool hasB = lB < nTasks;
-    const int mm = P.mismatch, open = P.open, clipLt = P.clipLt;
+    const int mm = MM ? MM : P.mismatch, open = OPEN ? OPEN : P.open, clipLt = P.clipLt;
     int NA = (int)refLens[tA], LA = (int)readLens[tA], cutA = cutoffs[tA];
     int NB = hasB ? (int)refLens[tB] : 0, LB = hasB ? (int)readLens[tB] : 0, cutB = hasB ? cutoffs[tB] : 0;
     // CPU_DP.cpp:296-324: outside these bounds the reference aborts the SIMD group
@@ -149,9 +153,8 @@ k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLe
                 const uint32_t a = hf - Hdiag + MMABS2;                           // H - Hdiag - mm   >= 0
                 const uint32_t b = hf - t2;                                       // H - Hleft - open >= 0
                 const uint32_t zd = __vminu2(hf - d, DP_ONE2);                    // 0 where D == H
-                const uint32_t zr = __vminu2(hf - h, DP_ONE2);                    // 1 where the floor raised the cell
-                const uint32_t flag = DP_ONE2 + zd - 2u * zr;
-                code[k] = a * 42u + b * 3u + flag;
+                const uint32_t zr = __vminu2(hf - h, DP_ONE2);                    // 1 where the floor raised the cell (then zd == 1 too)
+                code[k] = a * 42u + (b * 3u + (zd + zr));                         // third digit: 0 = D==H, 1 = neither, 2 = raised by the clip floor
                 // answer cell per column: first strict maximum, ties counted (CPU_DP.cpp:545-590)
                 const uint32_t hE = hf & el[k] & rowMask;
                 const uint32_t nb = __vmaxu2(bestH[k], hE);
@@ -243,7 +246,7 @@ k_dp_tb(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLens
     // `diagCell` carries the byte of (j-1, i-1) from the clip check of one step to the next step, which usually moves there
     uint32_t cell = load_cell<K>(tab, j, i, S);
     while (i > 0 && j > 0) {
-        int flag = cell % 3;
+        int flag = trace_flag(cell);
         int hd = open + (int)(cell / 3 % 14);
         int dd = mm + (int)(cell / 42);
         bool eq = fs[j - 1] == rs[i - 1];
@@ -254,7 +257,7 @@ k_dp_tb(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLens
                 uint32_t diagCell = 0; int dflag;
                 if (i - 1 == 0) dflag = 0;
                 else if (j - 1 == 0) dflag = (i - 1) <= clipLt ? 0 : 1;
-                else { diagCell = load_cell<K>(tab, j - 1, i - 1, S); dflag = diagCell % 3; }
+                else { diagCell = load_cell<K>(tab, j - 1, i - 1, S); dflag = trace_flag(diagCell); }
                 if (i != 1 && dflag == 0) { state = SM_EXIT; break; }
                 pat[p++] = eq ? 'M' : 'm'; --j; --i;
                 cell = diagCell;                                     // valid whenever the loop continues (i > 0 && j > 0)
@@ -354,8 +357,12 @@ static int launch_dp(mp_context *ctx, const uint8_t *dRef, const uint32_t *dRefL
         dim3 gridF((n + 7) / 8), gridT((n + 127) / 128), block(128);
 #define LAUNCH(KK) do { \
         cudaEvent_t stop_ = ctx->ev_begin(0); \
-        (++g_mp_launches), k_dp_fill<KK><<<gridF, block, smem, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, \
-            base, n, P, tab, tableStride, S, fill); \
+        if (P.mismatch == -2 && P.open == -3) \
+            (++g_mp_launches), k_dp_fill<KK, -2, -3><<<gridF, block, smem, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, \
+                base, n, P, tab, tableStride, S, fill); \
+        else \
+            (++g_mp_launches), k_dp_fill<KK, 0, 0><<<gridF, block, smem, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, \
+                base, n, P, tab, tableStride, S, fill); \
         ctx->ev_end(stop_); stop_ = ctx->ev_begin(1); \
         (++g_mp_launches), k_dp_tb<KK><<<gridT, block, 0, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, \
             base, n, P, tab, tableStride, S, fill, dOuts, dPatterns, patStride); \
