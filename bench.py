@@ -490,15 +490,17 @@ def run(args, saved_stdout):
     seed_sectors = 32.0 * acc["n_probe"] + 32.0 * acc["n_lkt"] + 128.0 * occ_steps + 32.0 * acc["n_sa"] + 32.0 * acc["n_text"] / 32.0
     seed_ach = seed_bytes / (acc["ms_seed"] / 1e3) / 1e9
     traffic = ncu_traffic("k_dp_fill")
-    roof = {"kernel": "k_dp_fill<5> (packed 16-bit DPX table fill, the kernel with the largest share of the step)",
+    roof = {"kernel": "k_dp_fill<5,-2,-3> (packed 16-bit DPX table fill, the kernel with the largest share of the step)",
             "bound": "hbm", "achieved": fill_ach, "peak": peak, "unit": "GB/s", "frac": fill_ach / peak, "traffic": traffic,
             "peak_kind": peak_kind, "algorithmic": "1 traceback byte written per DP cell (SURVEY 8d cells = sum refLen*readLen)",
             "ms_per_step": acc["ms_fill"] / steps,
-            "note": "integer-issue bound, not bandwidth bound: ncu issue slots 88% busy, ALU pipe 85% (profiles/r01_ncu_full_v2_cfg2.txt)",
+            "note": "integer-issue bound, not bandwidth bound: ncu issue slots ~90% busy, ALU pipe ~83% (profiles/r01_ncu_full_v3_cfg2.txt); "
+                    "per-kernel times come from a single-context pass (loop R), value/e2e from the pipelined passes",
             "compute": {"gcups_fill": gcups_fill, "gcups_fill_plus_traceback": gcups_dp,
                         "dpx_peak_ginstr_s": dpx_peak, "dpx_instr_per_cell": 5.0,
                         "dpx_frac": (gcups_fill * 5.0 / dpx_peak) if dpx_peak else None,
-                        "issue_peak_gcups_at_45_instr_per_cell_pair": 148 * 4 * 32 * 2 * (clocks_hint() / 1e3) / 45.0},
+                        "sass_instr_per_cell_pair": 42.4,
+                        "issue_peak_gcups_at_that_instr_count": 148 * 4 * 32 * 2 * (clocks_hint() / 1e3) / 42.4},
             "seeding": {"kernel": "k_mmp", "ms_per_step": acc["ms_seed"] / steps, "bytes_gathered_gbs": seed_ach,
                         "sector_gbs": seed_sectors / (acc["ms_seed"] / 1e3) / 1e9, "gather32_peak_gbs": gather32, "gather64_peak_gbs": gather64,
                         "frac_of_gather32_peak": (seed_sectors / (acc["ms_seed"] / 1e3) / 1e9 / gather32) if gather32 else None,

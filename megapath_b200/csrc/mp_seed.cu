@@ -497,7 +497,13 @@ static int ensure_bloom(mp_context *ctx, int seedMinLength)
     const uint64_t n = ctx->ix.n;
     if (ctx->bloomK == K && ctx->bloomFor == (const void *)ctx->ix.blocks) return 0;
     if (n < (uint64_t)K) { ctx->bloomK = 0; return 0; }
-    uint64_t nWords = n / 4 + 1024;                      // 16 bits per text position
+    uint64_t nWords = n / 4 + 1024;                      // 16 bits per text position ...
+    {                                                    // ... unless that would take more than a third of what is free (60 Gbp texts)
+        size_t freeB = 0, totalB = 0; cudaMemGetInfo(&freeB, &totalB);
+        const uint64_t room = (uint64_t)(freeB / 3) / 8;
+        if (nWords > room) nWords = room;
+        if (nWords < 1024) { ctx->bloomK = 0; return 0; }
+    }
     if (ctx->sharedIndex && ctx->dBloom.cap == 0) ctx->dBloom.p = nullptr;      // a borrowed filter with another K: build our own
     if (ctx->dBloom.reserve(nWords * 8)) return MP_ERR_CUDA;
     MP_CUDA(cudaMemsetAsync(ctx->dBloom.p, 0, nWords * 8, ctx->stream));

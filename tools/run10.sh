@@ -1,3 +1,3 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; echo rc=$?; tail -3 gpurun_out/bench_full.err; cat gpurun_out/bench_full.json
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo rc=$?; tail -2 gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json | cut -c1-600
+python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; echo rc=$?; tail -2 gpurun_out/bench_full.err; cat gpurun_out/bench_full.json
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo rc=$?; cut -c1-400 gpurun_out/bench_ref.json
+python bench.py --steps 4 --warmup 3 > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 500 --csv --log-file gpurun_out/launches_v4.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu.log 2>&1; echo ncu rc=$?
