@@ -416,7 +416,8 @@ def run(args, saved_stdout):
             for k, v in s.items():
                 acc_out[k] = acc_out.get(k, 0) + v
 
-    # ---- warm-up (also builds the K-mer filter once, before the other contexts borrow it) ----
+    # ---- warm-up (the K-mer filter is built once, before the other contexts borrow it) ----
+    ctx.index_prepare(P)
     run_steps(ctx, range(min(1, args.warmup)), True, {})
     for _ in range(nctx - 1):
         ctxs.append(ctx.clone())

@@ -150,6 +150,11 @@ int  mp_index_save(mp_context *ctx, const char *prefix);
 int  mp_index_save_annotation(const char *prefix, uint64_t textLength, uint32_t numSeq, const char *const *names,
                               const uint64_t *starts, const uint64_t *lengths);
 
+/* builds the per-parameter acceleration structures of the resident index now (the K-mer presence filter for
+ * params->mmp.seedMinLength) instead of lazily in the first mp_seed_pairs call; call it before mp_clone so that the
+ * clones share them */
+int  mp_index_prepare(mp_context *ctx, const mp_align_params *params);
+
 /* index primitives, for parity tests against BWTOccValue / BWTSaValue / LT (2bwt-lib/BWT.c:597,968) */
 int  mp_occ(mp_context *ctx, const uint64_t *idx, const uint32_t *c, uint64_t *out, uint64_t n);
 int  mp_sa(mp_context *ctx, const uint64_t *saIndex, uint64_t *out, uint64_t n);

@@ -82,6 +82,7 @@ def lib():
         L.mp_init.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         L.mp_destroy.argtypes = [C.c_void_p]
         L.mp_clone.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.mp_index_prepare.argtypes = [C.c_void_p, C.c_void_p]
         L.mp_index_load.argtypes = [C.c_void_p, C.c_char_p]
         L.mp_index_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mp_index_build.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
@@ -237,6 +238,10 @@ class Context:
             self.index_save(prefix)
             b = np.asarray(bounds, dtype=np.uint64)
             save_annotation(prefix, n, ["seq%d" % (i + 1) for i in range(len(b) - 1)], b[:-1], b[1:] - b[:-1])
+
+    def index_prepare(self, params):
+        """Builds the K-mer presence filter for these parameters now (before clone())."""
+        self._check(self.L.mp_index_prepare(self.h, C.byref(params)))
 
     def has_index(self):
         return getattr(self, "_has_index", False)

@@ -67,6 +67,7 @@ struct BamRecord {
 
 struct BamWriter {
     BgzfWriter z;
+    std::vector<uint8_t> *capture = nullptr;                       // when set, encoded records are appended here instead of being compressed
     bool open(const std::string &path, const std::string &text, const std::vector<std::string> &names, const std::vector<uint32_t> &lens) {
         if (!z.open(path)) return false;
         z.write("BAM\1", 4);
@@ -84,8 +85,13 @@ struct BamWriter {
         uint32_t x[8];
         x[0] = (uint32_t)r.tid; x[1] = (uint32_t)r.pos; x[2] = (bin << 16) | ((r.mapq & 0xff) << 8) | (uint32_t)(l_qname & 0xff);
         x[3] = (r.flag << 16) | (r.n_cigar & 0xffff); x[4] = r.l_qseq; x[5] = (uint32_t)r.mtid; x[6] = (uint32_t)r.mpos; x[7] = (uint32_t)r.isize;
-        z.write(&block, 4); z.write(x, 32); z.write(r.data.data(), r.data.size());
+        if (capture) {
+            const uint8_t *b4 = (const uint8_t *)&block, *xb = (const uint8_t *)x;
+            capture->insert(capture->end(), b4, b4 + 4); capture->insert(capture->end(), xb, xb + 32);
+            capture->insert(capture->end(), r.data.begin(), r.data.end());
+        } else { z.write(&block, 4); z.write(x, 32); z.write(r.data.data(), r.data.size()); }
     }
+    void write_raw(const std::vector<uint8_t> &bytes) { if (!bytes.empty()) z.write(bytes.data(), bytes.size()); }
     void close() { z.close(); }
 };
 

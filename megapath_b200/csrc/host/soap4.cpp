@@ -27,6 +27,10 @@
 #include <string>
 #include <tuple>
 #include <vector>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include "megapath_b200.h"
 #include "bam_out.h"
 
@@ -37,6 +41,7 @@ struct Options {
     std::string indexName, query1, query2, outputPrefix, iniFile;
     int maxReadLength = 120, insert_low = 1, insert_high = 500, outputBAM = 0, numCpuThreads = 4, device = 0;
     int megapathMode = 0, top = 95, ignoreComments = 0, alignmentType = 2, printMDNM = 0;
+    int numGpus = 1, contextsPerGpu = 2;       // extensions: -G <n> uses GPUs device..device+n-1; MP_CONTEXTS_PER_GPU overrides 2
 };
 
 static bool parse_args(int argc, char **argv, Options &o)
@@ -61,6 +66,7 @@ static bool parse_args(int argc, char **argv, Options &o)
         else if (!strcmp(a, "-o")) { if (!need("the output file prefix")) return false; o.outputPrefix = argv[++i]; }
         else if (!strcmp(a, "-c")) { if (!need("the GPU device ID")) return false; o.device = atoi(argv[++i]); if (o.device < 0) { fprintf(stderr, "The GPU device ID should not be less than 0\n"); return false; } }
         else if (!strcmp(a, "-p")) o.printMDNM = 1;
+        else if (!strcmp(a, "-G")) { if (!need("the number of GPUs")) return false; o.numGpus = atoi(argv[++i]); if (o.numGpus <= 0) { fprintf(stderr, "The number of GPUs should be positive\n"); return false; } }
         else if (!strcmp(a, "-T")) { if (!need("the number of CPU threads")) return false; o.numCpuThreads = atoi(argv[++i]); if (o.numCpuThreads <= 0) { fprintf(stderr, "Please specify a positive number of CPU threads after '-T'\n"); return false; } }
         else if (!strcmp(a, "-C")) { if (!need("ini file name")) return false; o.iniFile = argv[++i]; }
         else if (!strcmp(a, "-F")) o.megapathMode = 1;
@@ -604,10 +610,28 @@ int main(int argc, char **argv)
     P.maxReadLength = maxLen; P.insert_high = opt.insert_high;
     const double top = opt.top / 100.0;
 
-    mp_context *gpu = nullptr;
-    if (mp_init(opt.device, &gpu)) { fprintf(stderr, "%s\n", mp_last_error()); return 1; }
+    // one index replica per GPU (loaded in parallel), contextsPerGpu contexts sharing it (mp_clone)
+    if (const char *e = getenv("MP_CONTEXTS_PER_GPU")) { int v = atoi(e); if (v >= 1 && v <= 8) opt.contextsPerGpu = v; }
     fprintf(stderr, "[Main] loading index into device...\n");
-    if (mp_index_load(gpu, opt.indexName.c_str())) { fprintf(stderr, "%s\n", mp_last_error()); return 1; }
+    std::vector<mp_context *> owners(opt.numGpus, nullptr), contexts;
+    {
+        std::vector<std::thread> loaders; std::vector<std::string> errs(opt.numGpus);
+        for (int g = 0; g < opt.numGpus; ++g)
+            loaders.emplace_back([&, g]() {
+                if (mp_init(opt.device + g, &owners[g]) || mp_index_load(owners[g], opt.indexName.c_str())) errs[g] = mp_last_error();
+            });
+        for (std::thread &t : loaders) t.join();
+        for (int g = 0; g < opt.numGpus; ++g) if (!errs[g].empty()) { fprintf(stderr, "%s\n", errs[g].c_str()); return 1; }
+        for (int g = 0; g < opt.numGpus; ++g) {
+            if (mp_index_prepare(owners[g], &P)) { fprintf(stderr, "%s\n", mp_last_error()); return 1; }
+            contexts.push_back(owners[g]);
+            for (int k = 1; k < opt.contextsPerGpu; ++k) {
+                mp_context *c = nullptr;
+                if (mp_clone(owners[g], &c)) { fprintf(stderr, "%s\n", mp_last_error()); return 1; }
+                contexts.push_back(c);
+            }
+        }
+    }
     Annotation ann;
     if (!ann.load(opt.indexName)) return 1;
     fprintf(stderr, "[Main] Finished loading index into device.\n");
@@ -651,87 +675,147 @@ int main(int argc, char **argv)
     fill_char_map();
     SeqReader r1, r2;
     if (!r1.open(opt.query1) || !r2.open(opt.query2)) { fprintf(stderr, "Cannot open the read files\n"); return 1; }
-    ReadBatch b; b.maxReadLength = (uint32_t)maxLen; b.wpq = ((uint32_t)maxLen + 15) / 16;
     const uint32_t maxNumQueries = 12 * 8192 * 128 / 6;            // SOAP4.cpp:206
-    double totalLoad = 0, totalAlign = 0, last = now_s();
-    uint64_t totalPairsAligned = 0;
-    bool detected = false;
-    std::string outbuf;
-    while (load_batch(r1, r2, b, maxNumQueries) > 0) {
-        const uint32_t numQueries = b.nReads, nPairs = numQueries / 2;
-        fprintf(stderr, "[Main] Loaded %u short reads from the query file.\n", numQueries);
-        double t = now_s();
-        fprintf(stderr, "[Main] Elapsed time on host : %9.4f seconds\n\n", t - last);
-        totalLoad += t - last; last = t;
-        if (!detected) {
-            uint32_t d1 = detect_read_length(b.lens, numQueries, 0), d2 = detect_read_length(b.lens, numQueries, 1);
-            if (opt.insert_low < (int)d2) opt.insert_low = (int)d2;
-            if (opt.insert_low < (int)d1) opt.insert_low = (int)d1;
-            fprintf(stderr, "All reads are directly processed by DP\n");
-            detected = true;
-        }
-        P.insert_low = opt.insert_low;
-        mp_results R;
-        if (mp_batch_upload(gpu, b.queries.data(), b.lens.data(), numQueries, b.wpq) || mp_align_pairs(gpu, &P, &R)) { fprintf(stderr, "%s\n", mp_last_error()); return 1; }
-        fprintf(stderr, "[Main] %u pairs of reads are proceeded to deep DP Round 1.\n", nPairs);
-        fprintf(stderr, "[Main] Number of pairs aligned by DP: %llu\n", (unsigned long long)R.numDPAlignedPair);
-        fprintf(stderr, "[Main] Number of alignments aligned by DP: %llu\n", (unsigned long long)R.numDPAlignment);
-        fprintf(stderr, "[Main] Number of reads aligned by single-end DP: %llu\n", (unsigned long long)R.numSingleDPAligned);
-        fprintf(stderr, "[Main] Number of alignments aligned by DP: %llu\n", (unsigned long long)R.numSingleDPAlignment);
-        fprintf(stderr, "[Main] Number of pairs aligned by DP: %llu\n", (unsigned long long)R.numRescuedPair);
-        fprintf(stderr, "[Main] Number of alignments aligned by DP: %llu\n", (unsigned long long)R.numRescuedAlignment);
-        totalPairsAligned += R.numDPAlignedPair + R.numRescuedPair;
-        // ---- output: stage order of the reference (deep DP pairs, rescued pairs, then everything else) ----
-        if (opt.megapathMode || opt.outputBAM) {
-            octx.b = &b;
-            std::vector<uint8_t> done(nPairs, 0);
-            for (int which = 0; which < 2; ++which) {
-                const mp_pair_result *arrp = which == 0 ? R.pairs : R.rescued; uint64_t n = which == 0 ? R.n_pairs : R.n_rescued;
-                octx.bam = !opt.outputBAM ? nullptr : which == 0 ? &bamDP : &bamGout;
-                for (uint64_t i = 0, j; i < n; i = j) {
-                    j = i + 1;
-                    while (j < n && arrp[j].readID == arrp[i].readID) ++j;
-                    output_pair(octx, outbuf, arrp + i, arrp + j, R.cigars, which == 0 ? 1 : 2);      // PH: hspaux->dpStageId
-                    done[arrp[i].readID >> 1] = 1;
-                    if (outbuf.size() > (1u << 22)) { fwrite(outbuf.data(), 1, outbuf.size(), stdout); outbuf.clear(); }
-                }
+
+    // ---- pipeline: reader thread -> GPU workers (one per context; each formats its own batch) -> ordered writer (this thread).
+    //      The reference overlaps read loading with alignment the same way (aio_thread.cpp:804, SOAP4.cpp:424-441, 576-585). ----
+    struct Job {
+        uint64_t seq = 0; ReadBatch b; std::string fq, log; std::vector<uint8_t> bam[3];
+        uint64_t pairsAligned = 0; double loadSeconds = 0, alignSeconds = 0; bool failed = false;
+    };
+    std::mutex mu; std::condition_variable cvIn, cvOut, cvRoom;
+    std::deque<Job *> inq; std::map<uint64_t, Job *> doneq; bool readerDone = false; size_t inflight = 0;
+    const size_t maxInflight = contexts.size() + 2;
+    const int stageUnpaired = P.skipDefaultDP ? 2 : 3;
+
+    std::thread reader([&]() {
+        uint64_t seq = 0; bool detected = false; double last = now_s();
+        for (;;) {
+            Job *j = new Job; j->b.maxReadLength = (uint32_t)maxLen; j->b.wpq = ((uint32_t)maxLen + 15) / 16;
+            if (load_batch(r1, r2, j->b, maxNumQueries) == 0) { delete j; break; }
+            j->seq = seq++;
+            double t = now_s(); j->loadSeconds = t - last;
+            if (!detected) {                                       // first batch: read-length detection and insert_low clamp (SOAP4.cpp:458-474)
+                uint32_t d1 = detect_read_length(j->b.lens, j->b.nReads, 0), d2 = detect_read_length(j->b.lens, j->b.nReads, 1);
+                if (opt.insert_low < (int)d2) opt.insert_low = (int)d2;
+                if (opt.insert_low < (int)d1) opt.insert_low = (int)d1;
+                P.insert_low = opt.insert_low;
+                detected = true;
             }
-            // pairs neither placed by deep DP nor rescued: per-read single-end hits (alignment.cpp:299-351)
-            octx.bam = opt.outputBAM ? &bamUnpair : nullptr;
-            const int stageUnpaired = P.skipDefaultDP ? 2 : 3;
-            uint64_t si = 0;
-            for (uint32_t p = 0; p < nPairs; ++p) {
-                if (done[p]) continue;
-                std::vector<SingleAln> hits[2];
-                for (uint32_t e = 0; e < 2; ++e) {
-                    const uint32_t id = 2 * p + e;
-                    while (si < R.n_singles && R.singles[si].readID < id) ++si;
-                    uint64_t en = si;
-                    while (en < R.n_singles && R.singles[en].readID == id) {
-                        const mp_single_result &sr = R.singles[en];
-                        SingleAln a = { sr.algnmt, sr.score, (int)sr.strand, sr.editdist, sr.num_sameScore, R.cigars + sr.cigar };
-                        hits[e].push_back(a); ++en;
+            std::unique_lock<std::mutex> lk(mu);
+            cvRoom.wait(lk, [&] { return inflight < maxInflight; });
+            ++inflight; inq.push_back(j);
+            cvIn.notify_one();
+            lk.unlock();
+            last = now_s();
+        }
+        std::lock_guard<std::mutex> lk(mu); readerDone = true; cvIn.notify_all(); cvOut.notify_all();
+    });
+
+    auto worker = [&](mp_context *gpu) {
+        OutCtx oc = octx;                                           // per-worker copy: own batch pointer and BAM capture sinks
+        BamWriter cap[3];
+        for (;;) {
+            Job *j = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cvIn.wait(lk, [&] { return !inq.empty() || readerDone; });
+                if (inq.empty()) return;
+                j = inq.front(); inq.pop_front();
+            }
+            const double ts = now_s();
+            ReadBatch &b = j->b;
+            const uint32_t numQueries = b.nReads, nPairs = numQueries / 2;
+            mp_results R;
+            if (mp_batch_upload(gpu, b.queries.data(), b.lens.data(), numQueries, b.wpq) || mp_align_pairs(gpu, &P, &R)) {
+                j->log = std::string(mp_last_error()) + "\n"; j->failed = true;
+            } else {
+                char line[512];
+                snprintf(line, sizeof line, "[Main] %u pairs of reads are proceeded to deep DP Round 1.\n[Main] Number of pairs aligned by DP: %llu\n[Main] Number of alignments aligned by DP: %llu\n"
+                         "[Main] Number of reads aligned by single-end DP: %llu\n[Main] Number of alignments aligned by DP: %llu\n[Main] Number of pairs aligned by DP: %llu\n[Main] Number of alignments aligned by DP: %llu\n",
+                         nPairs, (unsigned long long)R.numDPAlignedPair, (unsigned long long)R.numDPAlignment, (unsigned long long)R.numSingleDPAligned,
+                         (unsigned long long)R.numSingleDPAlignment, (unsigned long long)R.numRescuedPair, (unsigned long long)R.numRescuedAlignment);
+                j->log = line;
+                j->pairsAligned = R.numDPAlignedPair + R.numRescuedPair;
+                // ---- output: stage order of the reference (deep DP pairs, rescued pairs, then everything else) ----
+                if (opt.megapathMode || opt.outputBAM) {
+                    oc.b = &b;
+                    for (int k = 0; k < 3; ++k) cap[k].capture = &j->bam[k];
+                    std::vector<uint8_t> done(nPairs, 0);
+                    for (int which = 0; which < 2; ++which) {
+                        const mp_pair_result *arrp = which == 0 ? R.pairs : R.rescued; uint64_t n = which == 0 ? R.n_pairs : R.n_rescued;
+                        oc.bam = !opt.outputBAM ? nullptr : &cap[which];
+                        for (uint64_t i = 0, e; i < n; i = e) {
+                            e = i + 1;
+                            while (e < n && arrp[e].readID == arrp[i].readID) ++e;
+                            output_pair(oc, j->fq, arrp + i, arrp + e, R.cigars, which == 0 ? 1 : 2);      // PH: hspaux->dpStageId
+                            done[arrp[i].readID >> 1] = 1;
+                        }
                     }
-                    // OutputBuffer::ready: sort by (algnmt, score), drop duplicates (DV-DPfunctions.h:167-196, .cpp:248-251)
-                    std::sort(hits[e].begin(), hits[e].end(), [](const SingleAln &x, const SingleAln &y) { return std::make_pair(x.algnmt, x.score) < std::make_pair(y.algnmt, y.score); });
-                    hits[e].erase(std::unique(hits[e].begin(), hits[e].end(), [](const SingleAln &x, const SingleAln &y) { return x.algnmt == y.algnmt && x.score == y.score; }), hits[e].end());
+                    // pairs neither placed by deep DP nor rescued: per-read single-end hits (alignment.cpp:299-351)
+                    oc.bam = opt.outputBAM ? &cap[2] : nullptr;
+                    uint64_t si = 0;
+                    for (uint32_t p = 0; p < nPairs; ++p) {
+                        if (done[p]) continue;
+                        std::vector<SingleAln> hits[2];
+                        for (uint32_t e = 0; e < 2; ++e) {
+                            const uint32_t id = 2 * p + e;
+                            while (si < R.n_singles && R.singles[si].readID < id) ++si;
+                            uint64_t en = si;
+                            while (en < R.n_singles && R.singles[en].readID == id) {
+                                const mp_single_result &sr = R.singles[en];
+                                SingleAln a = { sr.algnmt, sr.score, (int)sr.strand, sr.editdist, sr.num_sameScore, R.cigars + sr.cigar };
+                                hits[e].push_back(a); ++en;
+                            }
+                            // OutputBuffer::ready: sort by (algnmt, score), drop duplicates (DV-DPfunctions.h:167-196, .cpp:248-251)
+                            std::sort(hits[e].begin(), hits[e].end(), [](const SingleAln &x, const SingleAln &y) { return std::make_pair(x.algnmt, x.score) < std::make_pair(y.algnmt, y.score); });
+                            hits[e].erase(std::unique(hits[e].begin(), hits[e].end(), [](const SingleAln &x, const SingleAln &y) { return x.algnmt == y.algnmt && x.score == y.score; }), hits[e].end());
+                        }
+                        output_unpaired(oc, j->fq, 2 * p, hits, stageUnpaired);
+                    }
                 }
-                output_unpaired(octx, outbuf, 2 * p, hits, stageUnpaired);
-                if (outbuf.size() > (1u << 22)) { fwrite(outbuf.data(), 1, outbuf.size(), stdout); outbuf.clear(); }
+                mp_results_release(gpu, &R);
             }
-            fwrite(outbuf.data(), 1, outbuf.size(), stdout); outbuf.clear();
+            j->alignSeconds = now_s() - ts;
+            { ReadBatch empty; std::swap(j->b.queries, empty.queries); std::swap(j->b.quals, empty.quals); std::swap(j->b.names, empty.names); std::swap(j->b.comments, empty.comments); }
+            std::lock_guard<std::mutex> lk(mu);
+            doneq[j->seq] = j; cvOut.notify_all();
         }
-        mp_results_release(gpu, &R);
-        t = now_s();
-        fprintf(stderr, "[Main] Elapsed time : %9.4f seconds\n\n", t - last);
-        totalAlign += t - last; last = t;
+    };
+    std::vector<std::thread> workers;
+    for (mp_context *c : contexts) workers.emplace_back(worker, c);
+
+    // ---- ordered writer ----
+    double totalLoad = 0, totalAlign = 0; const double tLoop0 = now_s();
+    uint64_t totalPairsAligned = 0, next = 0; bool failed = false, announced = false;
+    for (;;) {
+        Job *j = nullptr;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cvOut.wait(lk, [&] { return doneq.count(next) || (readerDone && inflight == 0); });
+            auto it = doneq.find(next);
+            if (it == doneq.end()) break;
+            j = it->second; doneq.erase(it); --inflight; cvRoom.notify_one();
+        }
+        fprintf(stderr, "[Main] Loaded %u short reads from the query file.\n[Main] Elapsed time on host : %9.4f seconds\n\n", j->b.nReads, j->loadSeconds);
+        if (!announced) { fprintf(stderr, "All reads are directly processed by DP\n"); announced = true; }
+        fputs(j->log.c_str(), stderr);
+        if (j->failed) failed = true;
+        if (!j->fq.empty()) fwrite(j->fq.data(), 1, j->fq.size(), stdout);
+        if (opt.outputBAM) { bamDP.write_raw(j->bam[0]); bamGout.write_raw(j->bam[1]); bamUnpair.write_raw(j->bam[2]); }
+        fprintf(stderr, "[Main] Elapsed time : %9.4f seconds\n\n", j->alignSeconds);
+        totalLoad += j->loadSeconds; totalAlign += j->alignSeconds; totalPairsAligned += j->pairsAligned;
+        delete j; ++next;
     }
+    reader.join();
+    for (std::thread &t : workers) t.join();
     fflush(stdout);
     if (opt.outputBAM) { bamDP.close(); bamGout.close(); bamUnpair.close(); }
+    if (failed) return 1;
     fprintf(stderr, "[Main] Overall number of pairs of reads aligned: %llu\n", (unsigned long long)totalPairsAligned);
     fprintf(stderr, "[Main] Overall read load time : %9.4f seconds\n", totalLoad);
-    fprintf(stderr, "[Main] Overall alignment time (excl. read loading) : %9.4f seconds\n", totalAlign);
-    mp_destroy(gpu);
+    fprintf(stderr, "[Main] Overall alignment time (excl. read loading) : %9.4f seconds\n", now_s() - tLoop0);
+    for (size_t k = contexts.size(); k-- > 0;) mp_destroy(contexts[k]);
     fprintf(stderr, "[Main] Overall running time: %f\n", now_s() - t0);
     return 0;
 }

@@ -516,6 +516,14 @@ static int ensure_bloom(mp_context *ctx, int seedMinLength)
     return 0;
 }
 
+extern "C" int mp_index_prepare(mp_context *ctx, const mp_align_params *params)
+{
+    if (!ctx || !params) { mp_set_error("mp_index_prepare: null argument"); return MP_ERR_ARG; }
+    if (!ctx->hasIndex) { mp_set_error("mp_index_prepare: no index resident"); return MP_ERR_STATE; }
+    MP_CUDA(cudaSetDevice(ctx->device));
+    return ensure_bloom(ctx, params->mmp.seedMinLength);
+}
+
 int mps_seed_pairs(mp_context *ctx, const mp_align_params *AP)
 {
     const mp_mmp_params &mp = AP->mmp;

@@ -98,7 +98,7 @@ def run_our_soap4(workdir, index_prefix, fq1, fq2, out_name, max_len_opt, ini="s
     ini_path = os.path.join(ROOT, "megapath_b200", "ini", ini)
     cmd = [exe, "pair", index_prefix, fq1, fq2, "-o", os.path.join(workdir, out_name), "-C", ini_path, "-L", str(max_len_opt),
            "-T", "2", "-u", str(insert_high)] + list(extra)
-    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
     if p.returncode != 0:
         raise RuntimeError("soap4 driver failed: " + p.stderr.decode()[-2000:])
     return p.stdout
