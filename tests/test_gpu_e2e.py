@@ -105,3 +105,52 @@ def test_e2e_bam_matches_reference(workdir, small_ref, name, rlen, lopt, kw, ini
     assert len(recs_r) == len(recs_o) == 2 * 2500
     for a, b in zip(recs_o, recs_r):
         assert a == b, (a, b)
+
+
+def _write_fq(path, recs, mate):
+    with open(path, "wb") as f:
+        for i, s in enumerate(recs):
+            f.write(b"@e%d/%d\n" % (i, mate) + s + b"\n+\n" + b"I" * len(s) + b"\n")
+
+
+@needs_ref
+def test_e2e_edge_cases_match_reference(workdir, small_ref):
+    """Ragged and degenerate inputs: reads longer than -L (truncated to L-1, QueryParser.cpp:188), short reads, all-N reads
+    (N -> G, IndexHandler.cpp:41-45), a read made of the last bases of the text, lower-case bases.
+    Reads shorter than the DP cutoff max(0.2 L, 30) are outside the reference's defined behaviour: its SIMD kernel aborts the
+    whole vector group (16 or 32 unrelated tasks, depending on the build) that contains such a task (CPU_DP.cpp:296-324), so
+    its output for OTHER reads then depends on batch composition; lengths here start at 36."""
+    rng = np.random.default_rng(5)
+    seq = small_ref["seq"]
+    comp = {65: 84, 67: 71, 71: 67, 84: 65}
+    r1, r2 = [], []
+    for k in range(400):
+        st = int(rng.integers(0, len(seq) - 600))
+        isz = int(rng.integers(260, 500))
+        l1, l2 = int(rng.integers(36, 180)), int(rng.integers(36, 180))
+        a = bytes(seq[st:st + l1])
+        b = bytes(comp[c] for c in seq[st + isz - l2:st + isz][::-1])
+        if k % 7 == 0:
+            a = b"N" * l1
+        if k % 11 == 0:
+            b = b.lower()
+        if k % 13 == 0:
+            a = bytes(seq[len(seq) - l1:])                       # last bases of the text
+        r1.append(a)
+        r2.append(b)
+    fq1, fq2 = os.path.join(workdir, "edge_1.fq"), os.path.join(workdir, "edge_2.fq")
+    _write_fq(fq1, r1, 1)
+    _write_fq(fq2, r2, 2)
+    for lopt in (151, 101):
+        ref_out, _ = run_ref_soap4(workdir, small_ref["prefix"], fq1, fq2, "edgeref%d" % lopt, lopt, dump=False, threads=2)
+        want = canon_fastq(open(ref_out, "rb").read())
+        got = canon_fastq(run_our_soap4(workdir, small_ref["prefix"], fq1, fq2, "edgeour%d" % lopt, lopt))
+        assert got == want, first_diff(got, want)
+
+
+@needs_ref
+def test_e2e_empty_input(workdir, small_ref):
+    fq1, fq2 = os.path.join(workdir, "empty_1.fq"), os.path.join(workdir, "empty_2.fq")
+    open(fq1, "wb").close()
+    open(fq2, "wb").close()
+    assert run_our_soap4(workdir, small_ref["prefix"], fq1, fq2, "emptyour", 151) == b""
