@@ -23,6 +23,7 @@
 // independent walks in flight hide the dependent-load latency that a single walking lane cannot.
 #include "mp_context.h"
 #include <algorithm>
+#include <type_traits>
 
 #define DP_BIAS   0x4000
 #define DP_BIAS2  0x40004000u
@@ -37,14 +38,22 @@ __device__ __forceinline__ uint32_t pack2(int v) { return ((uint32_t)v & 0xffffu
 
 struct FillOut { int32_t score; uint32_t row, col, cnt; };
 
-// byte offset of the trace cell (row r >= 1, column c >= 1) inside one task's table of S steps
+// Trace table of one task PAIR (S steps, S a multiple of 4; 2*S*32*K bytes).  Step t = row + lane.
+//   word region  : step-major blocks of WORDS*256 bytes: [word w][task half h][lane] u32; byte c holds column 4w+c of the lane's
+//                  strip for the row it had 3-c steps earlier, i.e. four cells of one DIAGONAL: the traceback's usual move stays
+//                  inside one 32-byte sector
+//   remainder    : the K%4 left-over columns of four consecutive steps share u32 words: group g = (t-1)/4 holds REM*256 bytes
+//                  [word][half][lane] u32, byte position ((t-1)%4)*REM + (k-4*WORDS)
+// so that every store of a warp is a full 128-byte line per task and one running pointer serves both tasks.
+// cell_offset is relative to (pair table + half*128).
 template <int K>
 __device__ __forceinline__ size_t cell_offset(int r, int c, int S)
 {
     const int lane = (c - 1) / K, k = (c - 1) - lane * K, t = r + lane;
-    const int words = K / 4, rem = K % 4;
-    if (k < 4 * words) return (size_t)(k >> 2) * S * 128 + (size_t)t * 128 + lane * 4 + (k & 3);
-    return (size_t)words * S * 128 + ((size_t)t * 32 + lane) * rem + (k - 4 * words);
+    constexpr int WORDS = K / 4, REM = K % 4, WB = WORDS * 256;
+    if (k < 4 * WORDS) return (size_t)(t + 3 - (k & 3)) * WB + (size_t)(k >> 2) * 256 + lane * 4 + (k & 3);
+    const int b = ((t - 1) & 3) * REM + (k - 4 * WORDS);
+    return (size_t)S * WB + (size_t)((t - 1) >> 2) * (REM * 256) + (size_t)(b >> 2) * 256 + lane * 4 + (b & 3);
 }
 template <int K>
 __device__ __forceinline__ uint8_t load_cell(const uint8_t *__restrict__ tab, int r, int c, int S)
@@ -105,8 +114,7 @@ k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLe
     __syncwarp();
     const uint8_t *ra = readSeq + (size_t)tA * readStride, *rbp = readSeq + (size_t)tB * readStride;
     const int j0 = lane * K + 1;
-    const int minColA = max(LA - P.clipRt, 1), minColB = max(LB - P.clipRt, 1);
-    uint32_t rb[K], Hp[K], Dp[K], fl[K], el[K], bestH[K], bestRow[K], cnt[K];
+    uint32_t rb[K], Hp[K], Dp[K], fl[K], bestH[K], bestRow[K], cnt[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int j = j0 + k;
@@ -115,23 +123,39 @@ k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLe
         Hp[k] = pack2(h0_value(j, clipLt, open) + DP_BIAS);
         Dp[k] = DP_NEG2;
         fl[k] = j <= clipLt ? DP_BIAS2 : 0u;
-        el[k] = ((j >= minColA && j <= LA) ? 0x0000FFFFu : 0u) | ((j >= minColB && j <= LB) ? 0xFFFF0000u : 0u);
         bestH[k] = 0; bestRow[k] = 0; cnt[k] = 0;
     }
     uint32_t prevHleft = pack2(h0_value(j0 - 1, clipLt, open) + DP_BIAS);
     const uint32_t OPENABS2 = pack2(-open), MMABS2 = pack2(-mm), MINUS1 = 0xFFFFFFFFu;
     const uint32_t DELTA = (uint32_t)(1 - mm);                 // match score - mismatch score
-    uint8_t *tabA = tables + (size_t)lA * tableStride, *tabB = tabA + tableStride;
-    constexpr int WORDS = K / 4, REM = K % 4;
+    constexpr int WORDS = K / 4, REM = K % 4, WB = WORDS * 256;
+    uint8_t *tabP = tables + (size_t)lA * tableStride;          // pair table: 2 * tableStride bytes
+    uint8_t *pw = tabP + WB + lane * 4;                         // word block of step 1
+    uint8_t *pr = tabP + (size_t)S * WB + lane * 4;             // remainder group 0
     uint32_t sendH = 0, sendI = 0;
     const int lastLane = maxL > 0 ? (maxL - 1) / K : 0;
     const int steps = maxN + lastLane;
-    const bool laneActive = j0 <= maxL;
-    for (int t = 1; t <= steps; ++t) {
-        const uint32_t rH = __shfl_up_sync(0xffffffffu, sendH, 1);
-        const uint32_t rI = __shfl_up_sync(0xffffffffu, sendI, 1);
+    const uint32_t amask = lastLane >= 31 ? 0xffffffffu : ((2u << lastLane) - 1u);     // lanes that own read columns
+    uint32_t accA[REM ? REM : 1] = {0}, accB[REM ? REM : 1] = {0};
+    uint32_t hist[WORDS][3][4];                                 // codes of the last steps, slot = step % 4 (see cell_offset)
+#pragma unroll
+    for (int w = 0; w < WORDS; ++w)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) hist[w][c][q] = 0;
+    // One wavefront step of this lane; u = (t-1) % 4 is a compile-time constant in every caller.
+    // CHECKED = false in the steady phase, where every owning lane has a row that exists in BOTH tasks: no range test, no row mask,
+    // and the four unrolled steps need no register shuffling between them.
+    auto step = [&](const int t, auto uTag, auto checked) {
+        constexpr int u = decltype(uTag)::value;
+        constexpr bool CHECKED = decltype(checked)::value;
+        const uint32_t rH = __shfl_up_sync(amask, sendH, 1);
+        const uint32_t rI = __shfl_up_sync(amask, sendI, 1);
         const int i = t - lane;
-        if (laneActive && i >= 1 && i <= maxN) {
+        uint32_t code[K] = {};
+        const bool compute = !CHECKED || (i >= 1 && i <= maxN);
+        if (compute) {
             uint32_t Hleft = lane == 0 ? DP_BIAS2 : rH;
             uint32_t Il = lane == 0 ? DP_NEG2 : rI;
             const uint32_t ref2 = refS[i - 1];
@@ -139,7 +163,6 @@ k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLe
             const uint32_t row2 = (uint32_t)i * 0x00010001u;
             uint32_t Hdiag = prevHleft;
             prevHleft = Hleft;
-            uint32_t code[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const uint32_t m = __vminu2(ref2 ^ rb[k], DP_ONE2);               // 1 where the bases differ
@@ -155,51 +178,98 @@ k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLe
                 const uint32_t zd = __vminu2(hf - d, DP_ONE2);                    // 0 where D == H
                 const uint32_t zr = __vminu2(hf - h, DP_ONE2);                    // 1 where the floor raised the cell (then zd == 1 too)
                 code[k] = a * 42u + (b * 3u + (zd + zr));                         // third digit: 0 = D==H, 1 = neither, 2 = raised by the clip floor
-                // answer cell per column: first strict maximum, ties counted (CPU_DP.cpp:545-590)
-                const uint32_t hE = hf & el[k] & rowMask;
-                const uint32_t nb = __vmaxu2(bestH[k], hE);
-                const uint32_t msk = __vminu2(nb - bestH[k], DP_ONE2) * 0xFFFFu;  // halves that improved
-                bestRow[k] = (bestRow[k] & ~msk) | (row2 & msk);
-                cnt[k] = (cnt[k] & ~msk) + (DP_ONE2 - __vminu2(nb - hE, DP_ONE2));
-                bestH[k] = nb;
+                // answer cell per column: first strict maximum, ties counted (CPU_DP.cpp:545-590).  Column eligibility is applied
+                // when the columns are reduced; rows past the end of the shorter task only occur in the CHECKED variant.
+                const uint32_t hE = CHECKED ? (hf & rowMask) : hf;
+                const uint32_t q = bestH[k] + 0x80008000u - hE;                   // per half: bit 15 set <=> best >= this cell (no borrow: values < 0x8000)
+                uint32_t keep;                                                    // 0xFFFF in the halves that did NOT improve
+                asm("prmt.b32 %0, %1, %1, 0xBB99;" : "=r"(keep) : "r"(q));        // replicate the sign bits of bytes 1 and 3
+                const uint32_t lower = __viaddmin_s16x2_relu(q, 0x80008000u, DP_ONE2);   // 1 where this cell is below the best so far
+                bestH[k] = __vmaxu2(bestH[k], hE);
+                bestRow[k] = (bestRow[k] & keep) | (row2 & ~keep);
+                cnt[k] = ((cnt[k] + DP_ONE2 - lower) & keep) | (DP_ONE2 & ~keep);
                 Hdiag = Hp[k]; Hp[k] = hf; Dp[k] = d; Hleft = hf;
             }
-            // trace bytes: low halves -> task A, high halves -> task B
+            sendH = Hleft; sendI = Il;
+#pragma unroll
+            for (int kk = 0; kk < REM; ++kk) {
+                const int bpos = u * REM + kk, pos = bpos & 3;                     // byte position inside the group's remainder words
+                const uint32_t selA = 0x3210u ^ ((uint32_t)(4 ^ pos) << (4 * pos)), selB = 0x3210u ^ ((uint32_t)(6 ^ pos) << (4 * pos));
+#pragma unroll
+                for (int q = 0; q < REM; ++q)
+                    if (q == (bpos >> 2)) {
+                        accA[q] = __byte_perm(accA[q], code[4 * WORDS + kk], selA);
+                        accB[q] = __byte_perm(accB[q], code[4 * WORDS + kk], selB);
+                    }
+            }
+#pragma unroll
+            for (int w = 0; w < WORDS; ++w)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) hist[w][c][u] = code[4 * w + c];
+        }
+        // trace words: byte c of word w holds column 4w+c of row i-(3-c), so that a diagonal run of four cells shares one word.
+        // Low halves -> task A, high halves -> task B.  Rows maxN+1..maxN+3 only flush the older bytes.
+        if (!CHECKED || (i >= 1 && i <= maxN + 3)) {
 #pragma unroll
             for (int w = 0; w < WORDS; ++w) {
-                const uint32_t p01 = __byte_perm(code[4 * w], code[4 * w + 1], 0x6240), p23 = __byte_perm(code[4 * w + 2], code[4 * w + 3], 0x6240);
+                const uint32_t c0 = hist[w][0][(u + 1) & 3], c1 = hist[w][1][(u + 2) & 3], c2 = hist[w][2][(u + 3) & 3], c3 = code[4 * w + 3];
+                const uint32_t p01 = __byte_perm(c0, c1, 0x6240), p23 = __byte_perm(c2, c3, 0x6240);
                 // p01 bytes: [c0.lo, c1.lo, c0.hi, c1.hi]
                 const uint32_t wa = __byte_perm(p01, p23, 0x5410), wb = __byte_perm(p01, p23, 0x7632);
-                const size_t off = (size_t)w * S * 128 + (size_t)t * 128 + lane * 4;
-                *(uint32_t *)(tabA + off) = wa;
-                if (hasB) *(uint32_t *)(tabB + off) = wb;
+                *(uint32_t *)(pw + u * WB + w * 256) = wa;
+                if (hasB) *(uint32_t *)(pw + u * WB + w * 256 + 128) = wb;
             }
-            if (REM == 1) {
-                const size_t off = (size_t)WORDS * S * 128 + (size_t)t * 32 + lane;
-                tabA[off] = (uint8_t)code[K - 1];
-                if (hasB) tabB[off] = (uint8_t)(code[K - 1] >> 16);
-            } else if (REM == 2) {
-                const size_t off = (size_t)WORDS * S * 128 + ((size_t)t * 32 + lane) * 2;
-                *(uint16_t *)(tabA + off) = (uint16_t)((code[K - 2] & 0xff) | ((code[K - 1] & 0xff) << 8));
-                if (hasB) *(uint16_t *)(tabB + off) = (uint16_t)(((code[K - 2] >> 16) & 0xff) | (((code[K - 1] >> 16) & 0xff) << 8));
-            }
-            sendH = Hleft; sendI = Il;
         }
+    };
+    // remainder words of the four-step group that ends at step t
+    auto flush = [&](const int t) {
+        if (REM && t - lane >= 1 && t - 3 - lane <= maxN) {
+#pragma unroll
+            for (int q = 0; q < REM; ++q) {
+                *(uint32_t *)(pr + q * 256) = accA[q];
+                if (hasB) *(uint32_t *)(pr + q * 256 + 128) = accB[q];
+            }
+        }
+        pr += REM * 256;
+    };
+    auto group = [&](const int t, auto checked) {
+        step(t, std::integral_constant<int, 0>(), checked);
+        step(t + 1, std::integral_constant<int, 1>(), checked);
+        step(t + 2, std::integral_constant<int, 2>(), checked);
+        step(t + 3, std::integral_constant<int, 3>(), checked);
+        flush(t + 3);
+        pw += 4 * WB;
+    };
+    if (lane <= lastLane && maxL > 0) {
+        const int steadyN = (NA > 0 && NB > 0) ? min(NA, NB) : maxN;    // rows present in every live task of the pair
+        const int stepsR = (steps + 3 + 3) & ~3;                        // + 3 flush steps, whole groups
+        const int rampEnd = min((lastLane + 3) & ~3, stepsR);           // from here on every owning lane has started
+        const int steadyEnd = max(steadyN & ~3, rampEnd);               // up to here no owning lane has run out of rows
+        int t = 1;
+#pragma unroll 1
+        for (; t <= rampEnd; t += 4) group(t, std::true_type());
+#pragma unroll 1
+        for (; t <= steadyEnd; t += 4) group(t, std::false_type());
+#pragma unroll 1
+        for (; t <= stepsR; t += 4) group(t, std::true_type());
     }
-    // ---- winner per task: max score, then smallest (row, col); ties summed ----
+    __syncwarp();
+    // ---- winner per task: max score over the eligible columns, then smallest (row, col); ties summed ----
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         const int sh = half * 16;
+        const int Lh = half ? LB : LA, minCol = max(Lh - P.clipRt, 1);
         int best = 0;
 #pragma unroll
-        for (int k = 0; k < K; ++k) best = max(best, (int)((bestH[k] >> sh) & 0xffffu));
+        for (int k = 0; k < K; ++k)
+            if (j0 + k >= minCol && j0 + k <= Lh) best = max(best, (int)((bestH[k] >> sh) & 0xffffu));
         int gbest = best;
 #pragma unroll
         for (int dlt = 16; dlt; dlt >>= 1) gbest = max(gbest, __shfl_xor_sync(0xffffffffu, gbest, dlt));
         uint32_t key = 0xffffffffu; uint32_t c2 = 0;
 #pragma unroll
         for (int k = 0; k < K; ++k)
-            if ((int)((bestH[k] >> sh) & 0xffffu) == gbest) {
+            if (j0 + k >= minCol && j0 + k <= Lh && (int)((bestH[k] >> sh) & 0xffffu) == gbest) {
                 key = min(key, (((bestRow[k] >> sh) & 0xffffu) << 12) | (uint32_t)(j0 + k));
                 c2 += (cnt[k] >> sh) & 0xffffu;
             }
@@ -207,7 +277,7 @@ k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLe
         for (int dlt = 16; dlt; dlt >>= 1) { key = min(key, __shfl_xor_sync(0xffffffffu, key, dlt)); c2 += __shfl_xor_sync(0xffffffffu, c2, dlt); }
         if (lane == 0 && (half == 0 || hasB)) {
             FillOut f; f.score = gbest - DP_BIAS; f.row = key >> 12; f.col = key & 0xfffu; f.cnt = c2;
-            if (gbest == 0) { f.score = 0; f.row = 0; f.col = 0; f.cnt = 0; }
+            if (gbest == 0 || !(half ? okB : okA)) { f.score = 0; f.row = 0; f.col = 0; f.cnt = 0; }
             fill[half == 0 ? tA : tB] = f;
         }
     }
@@ -230,7 +300,7 @@ k_dp_tb(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLens
     MpDpOut o; o.score = 0; o.hitLoc = 0; o.count = 0; o.patLen = 0;
     const FillOut f = fill[task];
     if (cutoff > L || cutoff <= 0 || L >= 255 + open - 1 + cutoff || L > 32 * K || f.score < cutoff) { outs[task] = o; return; }
-    const uint8_t *tab = tables + (size_t)lt * tableStride;
+    const uint8_t *tab = tables + (size_t)(lt & ~1u) * tableStride + (lt & 1u) * 128;   // pair table + this task's half
     const uint8_t *rs = readSeq + (size_t)task * readStride;
     const uint8_t *fs = refSeq + (size_t)task * refStride;
     uint8_t *pat = patterns + (size_t)task * patStride;
@@ -333,21 +403,21 @@ static int launch_dp(mp_context *ctx, const uint8_t *dRef, const uint32_t *dRefL
     if (nTasks == 0) return 0;
     const int K = maxReadLen <= 160 ? 5 : maxReadLen <= 256 ? 8 : 10;
     if (maxReadLen > 320) { mp_set_error("read length %u exceeds the DP kernel bound 320", maxReadLen); return MP_ERR_ARG; }
-    const int S = (int)maxRefLen + 33;                        // steps 1 .. maxRefLen + 31, plus slack
+    const int S = ((int)maxRefLen + 44) & ~3;                 // steps 1 .. maxRefLen + 31 + 3 flush steps, rounded up to groups of four, plus slack
     const size_t tableStride = (size_t)S * 32 * K;
     if (ctx->dFill.reserve((size_t)nTasks * sizeof(FillOut))) return MP_ERR_CUDA;
     // the traceback tables of one sub-batch stay in HBM between the two kernels.  A chunk of stage S1 has up to 2^18 tasks:
     // size for that even when this launch is smaller, and only talk to the allocator when the buffer really is too small
-    const size_t typical = nTasks >= (1u << 15) ? (size_t)(1u << 18) * tableStride : (size_t)nTasks * tableStride;
-    const size_t ideal = std::max<size_t>((size_t)nTasks * tableStride, typical);
+    const size_t typical = nTasks >= (1u << 15) ? (size_t)(1u << 18) * tableStride : (size_t)(nTasks + 1) * tableStride;
+    const size_t ideal = std::max<size_t>((size_t)(nTasks + 1) * tableStride, typical);
     if (ctx->dTable.cap < ideal) {
         size_t freeB = 0, totalB = 0; cudaMemGetInfo(&freeB, &totalB);
         const size_t maxBytes = std::min<size_t>((size_t)24 << 30, (freeB + ctx->dTable.cap) / 2);
         const size_t want = std::min<size_t>(ideal, maxBytes);
         if (ctx->dTable.cap < want && ctx->dTable.reserve(want)) return MP_ERR_CUDA;
     }
-    uint32_t per = (uint32_t)std::min<size_t>(nTasks, ctx->dTable.cap / tableStride);
-    if (per < nTasks) per &= ~1u;                              // sub-batches start on a task pair
+    // tables are laid out per task PAIR: an odd final task still needs a whole pair table
+    const uint32_t per = (uint32_t)std::min<size_t>(nTasks, (ctx->dTable.cap / tableStride) & ~(size_t)1);
     if (per == 0) { mp_set_error("not enough device memory for the DP traceback tables"); return MP_ERR_CUDA; }
     uint8_t *tab = ctx->dTable.as<uint8_t>();
     FillOut *fill = ctx->dFill.as<FillOut>();
