@@ -161,7 +161,7 @@ static int deep_dp(mp_context *ctx, const mp_align_params *P, mp_results *out, u
     const uint32_t inputMax = (uint32_t)P->maxReadLength;
     const uint32_t maxReadLength = (inputMax / 4 + 1) * 4;                       // DV-DPfunctions.cpp:3166-3167
     const uint32_t maxDNALength = maxReadLength + 2 * MP_MARGIN(inputMax) + 8;
-    const uint32_t patStride = maxDNALength + maxReadLength;
+    const uint32_t patStride = (maxDNALength + maxReadLength + 3) & ~3u;         // word-aligned rows: k_dp_tb stores four pattern bytes at a time
     MpDpParams dpl, dpr;
     // softClipLtSizes/RtSizes per leg (DV-DPfunctions.cpp:2908-2911, 2994-2997); callDP uses task 0's pair
     dpl.mismatch = dpr.mismatch = P->mismatchScore; dpl.open = dpr.open = P->openGapScore;

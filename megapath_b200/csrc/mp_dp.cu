@@ -55,29 +55,8 @@ __device__ __forceinline__ size_t cell_offset(int r, int c, int S)
     const int b = ((t - 1) & 3) * REM + (k - 4 * WORDS);
     return (size_t)S * WB + (size_t)((t - 1) >> 2) * (REM * 256) + (size_t)(b >> 2) * 256 + lane * 4 + (b & 3);
 }
-template <int K>
-__device__ __forceinline__ uint8_t load_cell(const uint8_t *__restrict__ tab, int r, int c, int S)
-{
-    return __ldcs(tab + cell_offset<K>(r, c, S));      // every table byte is read once or twice: do not let it evict the sequences from L1
-}
 // third digit of a trace byte -> the reference's flag (0 = raised by the clip floor, 1 = D==H, 2 = otherwise; CPU_DP.cpp:529-533)
 __device__ __forceinline__ int trace_flag(uint32_t cell) { const int g = (int)(cell % 3); return g == 2 ? 0 : g + 1; }
-// flag of any cell including the virtual row 0 / column 0
-template <int K>
-__device__ __forceinline__ int cell_flag(const uint8_t *__restrict__ tab, int r, int c, int clipLt, int S)
-{
-    if (c == 0) return 0;                       // column 0 cells are stored as 0 (CPU_DP.cpp:447-450)
-    if (r == 0) return c <= clipLt ? 0 : 1;     // row 0 (CPU_DP.cpp:405-427)
-    return trace_flag(load_cell<K>(tab, r, c, S));
-}
-// H[r][c] - H[r][c-1] for any row including row 0
-template <int K>
-__device__ __forceinline__ int cell_hd(const uint8_t *__restrict__ tab, int r, int c, int clipLt, int open, int S)
-{
-    if (r == 0) return h0_value(c, clipLt, open) - h0_value(c - 1, clipLt, open);
-    return open + (int)(load_cell<K>(tab, r, c, S) / 3 % 14);
-}
-
 // MM / OPEN: mismatch score and gap-open score as compile-time constants (0 = take them from P at run time), so that the
 // packed constants become immediates of the DPX / IADD3 instructions
 template <int K, int MM, int OPEN>
@@ -284,7 +263,10 @@ k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLe
 }
 
 // ---- GPUBacktrack (CPU_DP.cpp:622-786), literal; one thread per task ----
-template <int K>
+// The walk is bound by memory TRANSACTIONS (every lane of a warp touches its own sector), so all three streams go through
+// one-word register caches: the trace table (a diagonal run of four cells shares a word, see cell_offset), the two sequences
+// (aligned 4-base words) and the pattern (four bytes per store; WORDPAT needs patStride % 4 == 0).
+template <int K, bool WORDPAT>
 __global__ void __launch_bounds__(128)
 k_dp_tb(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLens, uint32_t refStride,
         const uint8_t *__restrict__ readSeq, const uint32_t *__restrict__ readLens, uint32_t readStride,
@@ -301,74 +283,108 @@ k_dp_tb(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLens
     const FillOut f = fill[task];
     if (cutoff > L || cutoff <= 0 || L >= 255 + open - 1 + cutoff || L > 32 * K || f.score < cutoff) { outs[task] = o; return; }
     const uint8_t *tab = tables + (size_t)(lt & ~1u) * tableStride + (lt & 1u) * 128;   // pair table + this task's half
-    const uint8_t *rs = readSeq + (size_t)task * readStride;
-    const uint8_t *fs = refSeq + (size_t)task * refStride;
     uint8_t *pat = patterns + (size_t)task * patStride;
+    // ---- cached accessors ----
+    uint32_t tabW = 0; size_t tabIdx = ~(size_t)0;
+    auto cellAt = [&](int r, int c) -> uint32_t {           // trace byte of (row r >= 1, column c >= 1)
+        const size_t off = cell_offset<K>(r, c, S);
+        if ((off >> 2) != tabIdx) { tabIdx = off >> 2; tabW = __ldcs((const uint32_t *)tab + tabIdx); }   // read once or twice: keep it out of L1
+        return (tabW >> ((off & 3) * 8)) & 0xffu;
+    };
+    auto flagAt = [&](int r, int c) -> int {                // flag of any cell including the virtual row 0 / column 0
+        if (c == 0) return 0;                               // column 0 cells are stored as 0 (CPU_DP.cpp:447-450)
+        if (r == 0) return c <= clipLt ? 0 : 1;             // row 0 (CPU_DP.cpp:405-427)
+        return trace_flag(cellAt(r, c));
+    };
+    auto hdAt = [&](int r, int c) -> int {                  // H[r][c] - H[r][c-1] for any row including row 0
+        if (r == 0) return h0_value(c, clipLt, open) - h0_value(c - 1, clipLt, open);
+        return open + (int)(cellAt(r, c) / 3 % 14);
+    };
+    const size_t rsOff = (size_t)task * readStride, fsOff = (size_t)task * refStride;
+    uint32_t rsW = 0, fsW = 0; size_t rsIdx = ~(size_t)0, fsIdx = ~(size_t)0;
+    auto readBase = [&](int x) -> uint32_t {
+        const size_t a = rsOff + x;
+        if ((a >> 2) != rsIdx) { rsIdx = a >> 2; rsW = __ldg((const uint32_t *)readSeq + rsIdx); }
+        return (rsW >> ((a & 3) * 8)) & 0xffu;
+    };
+    auto refBase = [&](int x) -> uint32_t {
+        const size_t a = fsOff + x;
+        if ((a >> 2) != fsIdx) { fsIdx = a >> 2; fsW = __ldg((const uint32_t *)refSeq + fsIdx); }
+        return (fsW >> ((a & 3) * 8)) & 0xffu;
+    };
+    uint32_t p = 0, pacc = 0;
+    auto emit = [&](uint32_t byte) {
+        if (WORDPAT) {
+            pacc |= byte << ((p & 3) * 8);
+            if ((p & 3) == 3) { ((uint32_t *)pat)[p >> 2] = pacc; pacc = 0; }
+        } else pat[p] = (uint8_t)byte;
+        ++p;
+    };
     const int hitRow = (int)f.row, hitCol = (int)f.col;
     o.score = f.score; o.count = min(f.cnt, 255u);
-    uint32_t p = 0;
     int clipR = L - hitCol;
-    if (clipR > 0) { pat[p++] = 'S'; pat[p++] = 'V'; pat[p++] = (uint8_t)clipR; }
+    if (clipR > 0) { emit('S'); emit('V'); emit((uint32_t)clipR & 0xffu); }
     int i = L - clipR, j = hitRow;
     enum { NORMAL, I_EXT, D_EXT, SM_EXIT, SI_EXIT, SD_EXIT };
     int state = NORMAL;
     int accum = 0;
     // `diagCell` carries the byte of (j-1, i-1) from the clip check of one step to the next step, which usually moves there
-    uint32_t cell = load_cell<K>(tab, j, i, S);
+    uint32_t cell = cellAt(j, i);
     while (i > 0 && j > 0) {
         int flag = trace_flag(cell);
         int hd = open + (int)(cell / 3 % 14);
         int dd = mm + (int)(cell / 42);
-        bool eq = fs[j - 1] == rs[i - 1];
-        int ms = eq ? 1 : mm;
         if (state == NORMAL) {
+            bool eq = refBase(j - 1) == readBase(i - 1);
+            int ms = eq ? 1 : mm;
             if (dd == ms) {
                 // flag of the diagonal predecessor, including the virtual row 0 / column 0 (CPU_DP.cpp:405-450)
                 uint32_t diagCell = 0; int dflag;
                 if (i - 1 == 0) dflag = 0;
                 else if (j - 1 == 0) dflag = (i - 1) <= clipLt ? 0 : 1;
-                else { diagCell = load_cell<K>(tab, j - 1, i - 1, S); dflag = trace_flag(diagCell); }
+                else { diagCell = cellAt(j - 1, i - 1); dflag = trace_flag(diagCell); }
                 if (i != 1 && dflag == 0) { state = SM_EXIT; break; }
-                pat[p++] = eq ? 'M' : 'm'; --j; --i;
+                emit(eq ? 'M' : 'm'); --j; --i;
                 cell = diagCell;                                     // valid whenever the loop continues (i > 0 && j > 0)
                 continue;
             } else if (flag == 1) {
-                int vd = dd - cell_hd<K>(tab, j - 1, i, clipLt, open, S);
-                pat[p++] = 'D'; --j;
+                int vd = dd - hdAt(j - 1, i);
+                emit('D'); --j;
                 if (vd != open) { accum = (int8_t)(vd - ext); state = D_EXT; }
             } else {
-                pat[p++] = 'I'; --i;
+                emit('I'); --i;
                 if (hd != open) { accum = (int8_t)(hd - ext); state = I_EXT; }
             }
         } else if (state == D_EXT) {
-            int vd = dd - cell_hd<K>(tab, j - 1, i, clipLt, open, S);
-            if (vd + accum == open && cell_flag<K>(tab, j - 1, i, clipLt, S) == 0) { state = SD_EXIT; break; }
-            pat[p++] = 'D'; --j;
+            int vd = dd - hdAt(j - 1, i);
+            if (vd + accum == open && flagAt(j - 1, i) == 0) { state = SD_EXIT; break; }
+            emit('D'); --j;
             if (vd + accum == open) state = NORMAL; else accum = (int8_t)(accum + vd - ext);
         } else {
-            if (hd + accum == open && cell_flag<K>(tab, j, i - 1, clipLt, S) == 0) { state = SI_EXIT; break; }
-            pat[p++] = 'I'; --i;
+            if (hd + accum == open && flagAt(j, i - 1) == 0) { state = SI_EXIT; break; }
+            emit('I'); --i;
             if (hd + accum == open) state = NORMAL; else accum = (int8_t)(accum + hd - ext);
         }
-        if (i > 0 && j > 0) cell = load_cell<K>(tab, j, i, S);
+        if (i > 0 && j > 0) cell = cellAt(j, i);
     }
     bool discard = false;
     if (j == 0) {
         int sc = min(clipLt & 0xff, i);
-        if (sc < i) { pat[p++] = 'I'; pat[p++] = 'V'; pat[p++] = (uint8_t)(i - sc); }
-        pat[p++] = 'S'; pat[p++] = 'V'; pat[p++] = (uint8_t)sc;
+        if (sc < i) { emit('I'); emit('V'); emit((uint32_t)(i - sc) & 0xffu); }
+        emit('S'); emit('V'); emit((uint32_t)sc & 0xffu);
     } else if (state == SI_EXIT) {
-        pat[p++] = 'I'; pat[p++] = 'S'; pat[p++] = 'V'; pat[p++] = (uint8_t)(i - 1);
+        emit('I'); emit('S'); emit('V'); emit((uint32_t)(i - 1) & 0xffu);
     } else if (state == SD_EXIT) {
-        pat[p++] = 'D'; pat[p++] = 'S'; pat[p++] = 'V'; pat[p++] = (uint8_t)(i - 1);
+        emit('D'); emit('S'); emit('V'); emit((uint32_t)(i - 1) & 0xffu);
         discard = true;                                   // CPU_DP.cpp:842-857
     } else if (state == SM_EXIT) {
-        pat[p++] = (fs[j - 1] == rs[i - 1]) ? 'M' : 'm';
-        pat[p++] = 'S'; pat[p++] = 'V'; pat[p++] = (uint8_t)(i - 1);
+        emit((refBase(j - 1) == readBase(i - 1)) ? 'M' : 'm');
+        emit('S'); emit('V'); emit((uint32_t)(i - 1) & 0xffu);
         j -= 1;
     }
-    pat[p] = 0;
     o.patLen = p;
+    emit(0);                                              // terminator
+    if (WORDPAT && (p & 3)) ((uint32_t *)pat)[p >> 2] = pacc;
     if (discard) { o.score = 0; o.hitLoc = 0; } else o.hitLoc = (uint32_t)j;
     outs[task] = o;
 }
@@ -434,8 +450,12 @@ static int launch_dp(mp_context *ctx, const uint8_t *dRef, const uint32_t *dRefL
             (++g_mp_launches), k_dp_fill<KK, 0, 0><<<gridF, block, smem, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, \
                 base, n, P, tab, tableStride, S, fill); \
         ctx->ev_end(stop_); stop_ = ctx->ev_begin(1); \
-        (++g_mp_launches), k_dp_tb<KK><<<gridT, block, 0, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, \
-            base, n, P, tab, tableStride, S, fill, dOuts, dPatterns, patStride); \
+        if ((patStride & 3) == 0 && ((uintptr_t)dPatterns & 3) == 0) \
+            (++g_mp_launches), k_dp_tb<KK, true><<<gridT, block, 0, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, \
+                base, n, P, tab, tableStride, S, fill, dOuts, dPatterns, patStride); \
+        else \
+            (++g_mp_launches), k_dp_tb<KK, false><<<gridT, block, 0, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, \
+                base, n, P, tab, tableStride, S, fill, dOuts, dPatterns, patStride); \
         ctx->ev_end(stop_); } while (0)
         if (K == 5) LAUNCH(5); else if (K == 8) LAUNCH(8); else LAUNCH(10);
 #undef LAUNCH

@@ -178,7 +178,7 @@ int mps_single_and_rescue(mp_context *ctx, const mp_align_params *P, mp_results 
     }
     tr.mark("  s2 merge+tasks");
     std::vector<MpDpOut> outs; std::vector<uint8_t> pats;
-    uint32_t patStride = maxDNALengthS + maxReadLength;
+    uint32_t patStride = (maxDNALengthS + maxReadLength + 3) & ~3u;
     if (int rc = mpd_run_host_tasks(ctx, tasks, maxDNALengthS, maxReadLength, dp, outs, pats, patStride)) return rc;
     tr.mark("  s2 dp");
     std::vector<mp_single_result> &S = ctx->hSingles;
