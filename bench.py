@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--contexts", type=int, default=int(os.environ.get("MP_BENCH_CONTEXTS", "2")),
                     help="contexts (host thread + stream each) per GPU sharing one resident index; batches alternate between them")
     ap.add_argument("--workdir", default=os.environ.get("MP_BENCH_DIR", "/tmp/mpbench"))
+    ap.add_argument("--profile-step", action="store_true",
+                    help="profiling aid (ncu --profile-from-start off): after the warm-up run ONE step on one context between "
+                         "cudaProfilerStart/Stop and exit; prints no bench value")
     return ap.parse_args()
 
 
@@ -423,6 +426,14 @@ def run(args, saved_stdout):
         ctxs.append(ctx.clone())
     for ci, c in enumerate(ctxs):
         run_steps(c, range(ci, ci + max(args.warmup - (1 if ci == 0 else 0), 1)), True, {})
+    if args.profile_step:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        run_steps(ctx, [args.warmup], True, {})
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        emit(saved_stdout, {"profile_step": True, "note": "one step under the profiler; not a bench value"})
+        return 0
     sampler = ClockSampler(local)
     sampler.start()
 
@@ -495,13 +506,14 @@ def run(args, saved_stdout):
             "bound": "hbm", "achieved": fill_ach, "peak": peak, "unit": "GB/s", "frac": fill_ach / peak, "traffic": traffic,
             "peak_kind": peak_kind, "algorithmic": "1 traceback byte written per DP cell (SURVEY 8d cells = sum refLen*readLen)",
             "ms_per_step": acc["ms_fill"] / steps,
-            "note": "integer-issue bound, not bandwidth bound: ncu issue slots ~90% busy, ALU pipe ~83% (profiles/r01_ncu_full_v3_cfg2.txt); "
-                    "per-kernel times come from a single-context pass (loop R), value/e2e from the pipelined passes",
+            "note": "integer-ALU bound, not bandwidth bound: ncu ALU pipe 90.8% busy, issue slots 79.7%, top stall math_pipe_throttle "
+                    "(profiles/r01_ncu_full_v5_cfg2.txt); per-kernel times come from a single-context pass (loop R), value/e2e from the pipelined passes",
             "compute": {"gcups_fill": gcups_fill, "gcups_fill_plus_traceback": gcups_dp,
                         "dpx_peak_ginstr_s": dpx_peak, "dpx_instr_per_cell": 5.0,
                         "dpx_frac": (gcups_fill * 5.0 / dpx_peak) if dpx_peak else None,
-                        "sass_instr_per_cell_pair": 42.4,
-                        "issue_peak_gcups_at_that_instr_count": 148 * 4 * 32 * 2 * (clocks_hint() / 1e3) / 42.4},
+                        # ncu smsp__inst_executed.sum of one launch x 32 lanes / (cells / 2): includes idle lanes of the wavefront ramps
+                        "warp_instr_lane_slots_per_cell_pair": 42.6,
+                        "issue_peak_gcups_at_that_instr_count": 148 * 4 * 32 * 2 * (clocks_hint() / 1e3) / 42.6},
             "seeding": {"kernel": "k_mmp", "ms_per_step": acc["ms_seed"] / steps, "bytes_gathered_gbs": seed_ach,
                         "sector_gbs": seed_sectors / (acc["ms_seed"] / 1e3) / 1e9, "gather32_peak_gbs": gather32, "gather64_peak_gbs": gather64,
                         "frac_of_gather32_peak": (seed_sectors / (acc["ms_seed"] / 1e3) / 1e9 / gather32) if gather32 else None,
