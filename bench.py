@@ -509,8 +509,8 @@ def run(args, saved_stdout):
             "note": "integer-ALU bound, not bandwidth bound: ncu ALU pipe 90.8% busy, issue slots 79.7%, top stall math_pipe_throttle "
                     "(profiles/r01_ncu_full_v5_cfg2.txt); per-kernel times come from a single-context pass (loop R), value/e2e from the pipelined passes",
             "compute": {"gcups_fill": gcups_fill, "gcups_fill_plus_traceback": gcups_dp,
-                        "dpx_peak_ginstr_s": dpx_peak, "dpx_instr_per_cell": 5.0,
-                        "dpx_frac": (gcups_fill * 5.0 / dpx_peak) if dpx_peak else None,
+                        "dpx_peak_ginstr_s": dpx_peak, "dpx_instr_per_cell": 4.5,   # 9 packed min/max/add-max instructions per cell PAIR in the steady loop
+                        "dpx_frac": (gcups_fill * 4.5 / dpx_peak) if dpx_peak else None,
                         # ncu smsp__inst_executed.sum of one launch x 32 lanes / (cells / 2): includes idle lanes of the wavefront ramps
                         "warp_instr_lane_slots_per_cell_pair": 42.6,
                         "issue_peak_gcups_at_that_instr_count": 148 * 4 * 32 * 2 * (clocks_hint() / 1e3) / 42.6},
