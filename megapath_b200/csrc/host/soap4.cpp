@@ -24,11 +24,13 @@
 #include <algorithm>
 #include <chrono>
 #include <map>
+#include <memory>
 #include <string>
 #include <tuple>
 #include <vector>
 #include <condition_variable>
 #include <deque>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include "megapath_b200.h"
@@ -180,12 +182,61 @@ struct Annotation {
 // FASTA/FASTQ reader with kseq semantics (name up to the first blank, comment = rest of the header)
 struct SeqReader {
     gzFile f = nullptr; std::vector<char> buf; size_t pos = 0, end = 0; bool eof = false; int last = 0;
-    bool open(const std::string &path) { f = gzopen(path.c_str(), "rb"); if (!f) return false; gzbuffer(f, 1 << 20); buf.resize(1 << 20); return true; }
-    int getc_() { if (pos >= end) { if (eof) return -1; int n = gzread(f, buf.data(), (unsigned)buf.size()); if (n <= 0) { eof = true; return -1; } pos = 0; end = (size_t)n; } return (unsigned char)buf[pos++]; }
-    // reads up to the delimiter class: 0 = blank (space/tab/newline), 2 = newline; returns delimiter or -1
+    bool open(const std::string &path) { f = gzopen(path.c_str(), "rb"); if (!f) return false; gzbuffer(f, 1 << 22); buf.resize(1 << 22); return true; }
+    bool fill() { if (eof) return false; int n = gzread(f, buf.data(), (unsigned)buf.size()); if (n <= 0) { eof = true; return false; } pos = 0; end = (size_t)n; return true; }
+    int getc_() { if (pos >= end && !fill()) return -1; return (unsigned char)buf[pos++]; }
+    // reads up to the delimiter class: 0 = blank (space/tab/newline), 2 = newline; returns delimiter or -1.  Whole buffer ranges
+    // are appended at once (the per-character version of this loop was the slowest part of the driver).
     int getuntil(int mode, std::string &s, bool append) {
         if (!append) s.clear();
-        for (;;) { int c = getc_(); if (c < 0) return -1; if (mode == 2 ? c == '\n' : isspace(c)) { if (mode == 2 && !s.empty() && s.back() == '\r') s.pop_back(); return c; } s.push_back((char)c); }
+        for (;;) {
+            if (pos >= end && !fill()) return -1;
+            const char *b = buf.data() + pos, *e = buf.data() + end, *q;
+            if (mode == 2) q = (const char *)memchr(b, '\n', (size_t)(e - b));
+            else { q = b; while (q < e && !isspace((unsigned char)*q)) ++q; if (q == e) q = nullptr; }
+            if (!q) { s.append(b, (size_t)(e - b)); pos = end; continue; }
+            s.append(b, (size_t)(q - b)); pos = (size_t)(q - buf.data()) + 1;
+            if (mode == 2 && !s.empty() && s.back() == '\r') s.pop_back();
+            return (unsigned char)*q;
+        }
+    }
+    // Fast path for the usual four-line FASTQ record lying whole inside the buffer: views into the buffer, no copies.
+    // -> 1: record returned; 0: not applicable here (caller falls back to read(), which gives the same answer); -1: end of file.
+    struct View { const char *name, *comment, *seq, *qual; size_t nameLen, commentLen, seqLen; };
+    int read_fast(View &v) {
+        if (last != 0) return 0;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            if (pos >= end) { if (!fill()) return -1; }
+            const char *b = buf.data() + pos, *e = buf.data() + end;
+            if (*b != '@') return 0;
+            const char *n1 = (const char *)memchr(b, '\n', (size_t)(e - b));
+            const char *n2 = n1 ? (const char *)memchr(n1 + 1, '\n', (size_t)(e - n1 - 1)) : nullptr;
+            const char *n3 = n2 ? (const char *)memchr(n2 + 1, '\n', (size_t)(e - n2 - 1)) : nullptr;
+            const char *n4 = n3 ? (const char *)memchr(n3 + 1, '\n', (size_t)(e - n3 - 1)) : nullptr;
+            if (!n4) {
+                if (attempt == 1 || eof) return 0;
+                // the record crosses the end of the buffer: move the tail to the front and top the buffer up
+                const size_t rest = (size_t)(e - b);
+                if (rest == buf.size()) return 0;                  // a record larger than the buffer: leave it to read()
+                memmove(buf.data(), b, rest); pos = 0; end = rest;
+                int n = gzread(f, buf.data() + end, (unsigned)(buf.size() - end));
+                if (n <= 0) { eof = true; return 0; }
+                end += (size_t)n;
+                continue;
+            }
+            const char *h = b + 1, *he = n1; if (he > h && he[-1] == '\r') --he;
+            const char *q = h; while (q < he && !isspace((unsigned char)*q)) ++q;
+            v.name = h; v.nameLen = (size_t)(q - h);
+            if (q < he) { v.comment = q + 1; v.commentLen = (size_t)(he - q - 1); } else { v.comment = he; v.commentLen = 0; }
+            const char *s0 = n1 + 1, *s1 = n2; if (s1 > s0 && s1[-1] == '\r') --s1;
+            if (s1 == s0 || *s0 == '>' || *s0 == '+' || *s0 == '@' || n2[1] != '+') return 0;
+            const char *q0 = n3 + 1, *q1 = n4; if (q1 > q0 && q1[-1] == '\r') --q1;
+            if ((size_t)(q1 - q0) != (size_t)(s1 - s0)) return 0;
+            v.seq = s0; v.seqLen = (size_t)(s1 - s0); v.qual = q0;
+            pos = (size_t)(n4 - buf.data()) + 1;
+            return 1;
+        }
+        return 0;
     }
     // -> length of the sequence, -1 at end of file
     int read(std::string &name, std::string &comment, std::string &seq, std::string &qual) {
@@ -213,8 +264,10 @@ struct SeqReader {
 struct ReadBatch {
     uint32_t nReads = 0, wpq = 0, maxReadLength = 0;
     std::vector<uint32_t> queries, lens;
-    std::vector<std::string> names, comments, quals;
+    std::vector<std::string> names, comments;
     std::vector<uint8_t> hasComment;
+    std::unique_ptr<char[]> qualBuf; size_t qstride = 0, qcap = 0; std::vector<uint32_t> qlen;   // qualities: one fixed-stride row per read, NUL-terminated
+    const char *qual(uint32_t id) const { return qualBuf.get() + (size_t)id * qstride; }
 };
 
 static unsigned char g_charMap[256];
@@ -225,39 +278,58 @@ static void fill_char_map() {                                    // INDEXFillCha
     g_charMap['U'] = g_charMap['u'] = 3; g_charMap['N'] = g_charMap['n'] = 2;
 }
 
-static void append_read(ReadBatch &b, uint32_t id, std::string &name, const std::string &comment, const std::string &seq, const std::string &qual)
+static void append_read(ReadBatch &b, uint32_t id, const char *name, size_t nameLen, const char *comment, size_t commentLen,
+                        const char *seq, size_t seqLen, const char *qual, size_t qualLen)
 {
-    uint32_t len = seq.size() > b.maxReadLength - 1 ? b.maxReadLength - 1 : (uint32_t)seq.size();     // QueryParser.cpp:188
+    uint32_t len = seqLen > b.maxReadLength - 1 ? b.maxReadLength - 1 : (uint32_t)seqLen;     // QueryParser.cpp:188
     b.lens[id] = len;
     uint32_t *q = b.queries.data() + ((size_t)(id / 32) * 32 * b.wpq + id % 32);
-    uint32_t word = 0; int off = 0;
-    for (uint32_t i = 0; i < len; ++i) {
-        word |= (uint32_t)g_charMap[(unsigned char)seq[i]] << (off * 2);
-        if (++off == 16) { *q = word; q += 32; off = 0; word = 0; }
+    uint32_t i = 0;
+    for (; i + 16 <= len; i += 16, q += 32) {
+        uint32_t word = 0;
+        for (int k = 0; k < 16; ++k) word |= (uint32_t)g_charMap[(unsigned char)seq[i + k]] << (k * 2);
+        *q = word;
     }
-    if (off > 0) *q = word;
-    if (name.size() > 2 && name[name.size() - 2] == '/' && isdigit((unsigned char)name.back())) name.resize(name.size() - 2);   // trim_readno
-    b.names[id] = name;
-    b.hasComment[id] = !comment.empty(); b.comments[id] = comment;
-    b.quals[id] = qual.substr(0, len);
+    if (i < len) { uint32_t word = 0; for (int k = 0; i < len; ++i, ++k) word |= (uint32_t)g_charMap[(unsigned char)seq[i]] << (k * 2); *q = word; }
+    if (nameLen > 2 && name[nameLen - 2] == '/' && isdigit((unsigned char)name[nameLen - 1])) nameLen -= 2;   // trim_readno
+    b.names[id].assign(name, nameLen);
+    b.hasComment[id] = commentLen != 0;
+    if (commentLen) b.comments[id].assign(comment, commentLen); else b.comments[id].clear();
+    const uint32_t ql = (uint32_t)std::min<size_t>(qualLen, len);                                 // qual.substr(0, len)
+    char *qd = b.qualBuf.get() + (size_t)id * b.qstride;
+    memcpy(qd, qual, ql); qd[ql] = 0; b.qlen[id] = ql;
 }
 
 static uint32_t load_batch(SeqReader &r1, SeqReader &r2, ReadBatch &b, uint32_t maxReads)
 {
     size_t words = ((size_t)maxReads + 31) / 32 * 32 * b.wpq;
+    // batches are recycled (see BatchPool): storage that already has the right size is only cleared, so that a long run does
+    // not page-fault half a gigabyte of fresh memory per batch
     b.queries.assign(words, 0); b.lens.assign(maxReads, 0);
-    b.names.assign(maxReads, ""); b.comments.assign(maxReads, ""); b.quals.assign(maxReads, ""); b.hasComment.assign(maxReads, 0);
-    uint32_t n = 0;
-    std::string n1, c1, s1, q1, n2, c2, s2, q2;
-    while (n < maxReads) {
-        int l1 = r1.read(n1, c1, s1, q1), l2 = r2.read(n2, c2, s2, q2);
-        if ((l1 >= 0 && l2 < 0) || (l1 < 0 && l2 >= 0)) { fprintf(stderr, "Error: number of sequences of pair-end files not matched.\n"); exit(1); }
-        if (l1 < 0) break;
-        append_read(b, n++, n1, c1, s1, q1);
-        append_read(b, n++, n2, c2, s2, q2);
+    if (b.names.size() != maxReads) { b.names.assign(maxReads, ""); b.comments.assign(maxReads, ""); }
+    b.hasComment.assign(maxReads, 0); b.qlen.assign(maxReads, 0);
+    if (!b.qualBuf || b.qstride != (size_t)b.maxReadLength + 1 || b.qcap != maxReads) {
+        b.qstride = (size_t)b.maxReadLength + 1; b.qcap = maxReads; b.qualBuf.reset(new char[(size_t)maxReads * b.qstride]);
     }
-    b.nReads = n;
-    return n;
+    // the two files are parsed by two threads: mate 1 fills the even read ids, mate 2 the odd ones (disjoint elements and words)
+    auto half = [&b, maxReads](SeqReader &r, uint32_t first) -> uint32_t {
+        std::string nm, cm, sq, ql; uint32_t n = 0; SeqReader::View v;
+        for (uint32_t id = first; id < maxReads; id += 2, ++n) {
+            const int st = r.read_fast(v);
+            if (st < 0) break;
+            if (st == 1) { append_read(b, id, v.name, v.nameLen, v.comment, v.commentLen, v.seq, v.seqLen, v.qual, v.seqLen); continue; }
+            if (r.read(nm, cm, sq, ql) < 0) break;
+            append_read(b, id, nm.data(), nm.size(), cm.data(), cm.size(), sq.data(), sq.size(), ql.data(), ql.size());
+        }
+        return n;
+    };
+    uint32_t n2 = 0;
+    std::thread t2([&] { n2 = half(r2, 1); });
+    const uint32_t n1 = half(r1, 0);
+    t2.join();
+    if (n1 != n2) { fprintf(stderr, "Error: number of sequences of pair-end files not matched.\n"); exit(1); }
+    b.nReads = 2 * n1;
+    return b.nReads;
 }
 
 static uint32_t detect_read_length(const std::vector<uint32_t> &lens, uint32_t numQueries, uint32_t start)   // GetReadLength (QueryParser.cpp:2253-2277)
@@ -295,10 +367,24 @@ static void seq_and_qual(std::string &out, const ReadBatch &b, uint32_t id)
 {
     const uint32_t *q = b.queries.data() + ((size_t)(id / 32) * 32 * b.wpq + id % 32);
     uint32_t len = b.lens[id];
-    for (uint32_t i = 0; i < len; ++i) out.push_back("ACGT"[(q[(i >> 4) * 32] >> ((i & 15) << 1)) & 3]);
-    out += "\n+\n"; out += b.quals[id]; out.push_back('\n');
+    const size_t at = out.size();
+    out.resize(at + len);
+    char *w = &out[at];
+    for (uint32_t i = 0; i < len; i += 16) {
+        uint32_t word = q[(i >> 4) * 32];
+        const uint32_t m = len - i < 16 ? len - i : 16;
+        for (uint32_t k = 0; k < m; ++k, word >>= 2) w[i + k] = "ACGT"[word & 3];
+    }
+    out += "\n+\n"; out.append(b.qual(id), b.qlen[id]); out.push_back('\n');
 }
 
+static inline void append_int(std::string &s, long long v)
+{
+    char tmp[24]; int n = 0; bool neg = v < 0; unsigned long long u = neg ? 0ull - (unsigned long long)v : (unsigned long long)v;
+    do { tmp[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+    if (neg) s.push_back('-');
+    while (n) s.push_back(tmp[--n]);
+}
 static void header_line(std::string &ret, const ReadBatch &b, uint32_t id, const Annotation &ann, std::vector<std::pair<int, int>> &chrHits,
                         int bestScore, double top, bool ignoreComments)
 {
@@ -309,20 +395,22 @@ static void header_line(std::string &ret, const ReadBatch &b, uint32_t id, const
     std::vector<HeaderHit> v;
     int prev = mapping_from_header(comment, v, top, bestScore * top);
     if (prev > bestScore) bestScore = prev;
-    ret += "\tSCORE:" + std::to_string((long long)bestScore) + ";";
+    ret += "\tSCORE:"; append_int(ret, bestScore); ret.push_back(';');
     if (bestScore > 0)
         for (size_t i = 0; i < chrHits.size(); ++i) {
             if (i > 0 && chrHits[i].first == chrHits[i - 1].first) continue;
             if (-chrHits[i].second > 0 && -chrHits[i].second >= bestScore * top)
-                ret += std::to_string(-(long long)chrHits[i].second) + "," + ann.names[chrHits[i].first - 1] + ";";
+                { append_int(ret, -(long long)chrHits[i].second); ret.push_back(','); ret += ann.names[chrHits[i].first - 1]; ret.push_back(';'); }
         }
     for (size_t i = 0; i < v.size(); ++i)
-        if (v[i].score >= bestScore * top) { ret += comment->substr(v[i].s, v[i].e - v[i].s); ret += ";"; }
+        if (v[i].score >= bestScore * top) { ret.append(*comment, v[i].s, v[i].e - v[i].s); ret.push_back(';'); }
     ret += "\n";
 }
 
+struct OutScratch;
 struct OutCtx {
     const ReadBatch *b; const Annotation *ann; int megapathMode; double top; bool ignoreComments;
+    OutScratch *scratch = nullptr;
     // BAM side
     BamWriter *bam = nullptr; std::string readGroup; bool printMDNM = false; int alignmentType = 2;
     int mismatchScore = -2, matchScore = 1, minMAPQ = 1, maxMAPQ = 60; bool bwaLike = true;
@@ -331,6 +419,7 @@ struct OutCtx {
 struct PairAln {       // mutable copy of one DeepDPAlignResult (the FASTQ writer edits scores / positions before the BAM writer runs)
     uint64_t a1, a2; int s1, s2, strand1, strand2, ed1, ed2, ns1, ns2, insertSize; const char *c1, *c2;
 };
+struct OutScratch { std::vector<PairAln> v; std::vector<std::pair<int, int>> h1, h2; };   // reused per formatting thread: no allocation per pair
 struct SingleAln { uint64_t algnmt; int score, strand, editdist, num_sameScore; const char *cigar; };
 
 static void unpack_read(const ReadBatch &b, uint32_t id, std::vector<uint8_t> &codes)
@@ -352,7 +441,7 @@ static void output_pair(OutCtx &o, std::string &fq, const mp_pair_result *first,
     const ReadBatch &b = *o.b; const Annotation &ann = *o.ann;
     const uint32_t r1 = first->readID, r2 = r1 + 1;
     const int readlen1 = (int)b.lens[r1], readlen2 = (int)b.lens[r2];
-    std::vector<PairAln> v; v.reserve(last - first);
+    std::vector<PairAln> &v = o.scratch->v; v.clear();
     for (const mp_pair_result *p = first; p != last; ++p) {
         PairAln a; a.a1 = p->algnmt_1; a.a2 = p->algnmt_2; a.s1 = p->score_1; a.s2 = p->score_2; a.strand1 = p->strand_1; a.strand2 = p->strand_2;
         a.ed1 = p->editdist_1; a.ed2 = p->editdist_2; a.ns1 = p->num_sameScore_1; a.ns2 = p->num_sameScore_2; a.insertSize = p->insertSize;
@@ -363,7 +452,7 @@ static void output_pair(OutCtx &o, std::string &fq, const mp_pair_result *first,
     for (size_t i = 1; i < v.size(); ++i) if (v[i].s1 + v[i].s2 > maxScore) { best = i; maxScore = v[i].s1 + v[i].s2; }
     if (o.megapathMode) {
         int best1 = 0, best2 = 0;
-        std::vector<std::pair<int, int>> h1, h2;
+        std::vector<std::pair<int, int>> &h1 = o.scratch->h1, &h2 = o.scratch->h2; h1.clear(); h2.clear();
         for (PairAln &a : v) {
             int chr1 = -1, chr2 = -1;
             if (a.a1 != NOT_ALIGNED) chr1 = ann.targetChr(a.a1, readlen1);
@@ -387,7 +476,7 @@ static void output_pair(OutCtx &o, std::string &fq, const mp_pair_result *first,
     PairAln &B = v[best];
     if (B.a1 == NOT_ALIGNED && B.a2 == NOT_ALIGNED) return;
     std::vector<uint8_t> q1, q2; unpack_read(b, r1, q1); unpack_read(b, r2, q2);
-    ReadView rv1 = { &b.names[r1], q1.data(), b.quals[r1].c_str(), readlen1 }, rv2 = { &b.names[r2], q2.data(), b.quals[r2].c_str(), readlen2 };
+    ReadView rv1 = { &b.names[r1], q1.data(), b.qual(r1), readlen1 }, rv2 = { &b.names[r2], q2.data(), b.qual(r2), readlen2 };
     const int num = (int)v.size();
     uint64_t tp_1 = 0, tp_2 = 0; uint32_t chr_1 = 0, chr_2 = 0;
     long long boundTrim1 = 0, boundTrim2 = 0; std::string newCigar1, newCigar2, cigarStr1, cigarStr2;
@@ -396,13 +485,13 @@ static void output_pair(OutCtx &o, std::string &fq, const mp_pair_result *first,
     if (B.a1 != NOT_ALIGNED) {
         boundTrim1 = ann.chrAndPosBoundaryDP(readlen1, B.a1, B.c1, &tp_1, &chr_1, newCigar1);
         cigarStr1 = boundTrim1 ? convert_cigar(newCigar1.c_str()) : convert_cigar(B.c1);
-        mi1 = mis_info_for_dp(o.ax, b.quals[r1].c_str(), readlen1, B.a1, B.strand1, boundTrim1 ? newCigar1.c_str() : B.c1, boundTrim1);
+        mi1 = mis_info_for_dp(o.ax, b.qual(r1), readlen1, B.a1, B.strand1, boundTrim1 ? newCigar1.c_str() : B.c1, boundTrim1);
         rr1 = ref_len_of_cigar(B.c1);
     }
     if (B.a2 != NOT_ALIGNED) {
         boundTrim2 = ann.chrAndPosBoundaryDP(readlen2, B.a2, B.c2, &tp_2, &chr_2, newCigar2);
         cigarStr2 = boundTrim2 ? convert_cigar(newCigar2.c_str()) : convert_cigar(B.c2);
-        mi2 = mis_info_for_dp(o.ax, b.quals[r2].c_str(), readlen2, B.a2, B.strand2, boundTrim2 ? newCigar2.c_str() : B.c2, boundTrim2);
+        mi2 = mis_info_for_dp(o.ax, b.qual(r2), readlen2, B.a2, B.strand2, boundTrim2 ? newCigar2.c_str() : B.c2, boundTrim2);
         rr2 = ref_len_of_cigar(B.c2);
     }
     int bestPairNum = 0, bestPairScore = 0, secBestPairScore = 0;
@@ -495,7 +584,7 @@ static void output_unpaired(OutCtx &o, std::string &fq, uint32_t r1, std::vector
     const uint32_t ids[2] = { r1, r1 + 1 };
     if (o.megapathMode) {
         for (int e = 0; e < 2; ++e) {
-            int best = 0; std::vector<std::pair<int, int>> h;
+            int best = 0; std::vector<std::pair<int, int>> &h = o.scratch->h1; h.clear();
             const int hitNum = o.megapathMode == 2 ? 0 : (int)hits[e].size();
             for (int i = 0; i < hitNum; ++i) {
                 SingleAln &a = hits[e][i];
@@ -509,7 +598,7 @@ static void output_unpaired(OutCtx &o, std::string &fq, uint32_t r1, std::vector
     if (!o.bam) return;
     const int readlen[2] = { (int)b.lens[ids[0]], (int)b.lens[ids[1]] };
     std::vector<uint8_t> q[2]; unpack_read(b, ids[0], q[0]); unpack_read(b, ids[1], q[1]);
-    ReadView rv[2] = { { &b.names[ids[0]], q[0].data(), b.quals[ids[0]].c_str(), readlen[0] }, { &b.names[ids[1]], q[1].data(), b.quals[ids[1]].c_str(), readlen[1] } };
+    ReadView rv[2] = { { &b.names[ids[0]], q[0].data(), b.qual(ids[0]), readlen[0] }, { &b.names[ids[1]], q[1].data(), b.qual(ids[1]), readlen[1] } };
     int bestIdx[2] = { -1, -1 }, bestScore[2] = { 0, 0 }, bestScoreNum[2] = { 0, 0 }, x1_t1[2] = { 0, 0 }, x1_t2[2] = { 0, 0 }, secondBestNum[2];
     uint64_t tp[2] = { 0, 0 }; uint32_t chr[2] = { 0, 0 }; long long boundTrim[2] = { 0, 0 }; int deletedEnd[2] = { 0, 0 }, mapq[2] = { 0, 0 };
     std::string newCigar[2], cigarStr[2]; MisInfo mi[2];
@@ -530,7 +619,7 @@ static void output_unpaired(OutCtx &o, std::string &fq, uint32_t r1, std::vector
             const SingleAln &A = L[bestIdx[e]];
             boundTrim[e] = ann.chrAndPosBoundaryDP(readlen[e], A.algnmt, A.cigar, &tp[e], &chr[e], newCigar[e]);
             cigarStr[e] = boundTrim[e] ? convert_cigar(newCigar[e].c_str()) : convert_cigar(A.cigar, &deletedEnd[e]);
-            mi[e] = mis_info_for_dp(o.ax, b.quals[ids[e]].c_str(), readlen[e], A.algnmt, A.strand, boundTrim[e] ? newCigar[e].c_str() : A.cigar, boundTrim[e]);
+            mi[e] = mis_info_for_dp(o.ax, b.qual(ids[e]), readlen[e], A.algnmt, A.strand, boundTrim[e] ? newCigar[e].c_str() : A.cigar, boundTrim[e]);
             if (o.alignmentType == 4 || o.alignmentType == 3) mapq[e] = 255;
             else {
                 double thr = 0.2 * readlen[e]; if (thr < 30.0) thr = 30.0;
@@ -581,6 +670,37 @@ static void output_unpaired(OutCtx &o, std::string &fq, uint32_t r1, std::vector
 // ------------------------------------------------------------------------------------------------
 int main(int argc, char **argv)
 {
+    // hidden self-check used by tests/test_driver_host.py (no GPU needed): dump the records of a read file as the batch loader sees
+    // them, through the zero-copy fast path (default) or through the kseq-style parser only ("generic")
+    if (argc >= 5 && !strcmp(argv[1], "__load")) {           // hidden: time the batch loader alone (no GPU): __load r1 r2 maxReadLength
+        fill_char_map();
+        SeqReader r1, r2; if (!r1.open(argv[2]) || !r2.open(argv[3])) return 1;
+        const uint32_t maxLen = (uint32_t)atoi(argv[4]);
+        uint64_t total = 0, sum = 0; const double t0 = now_s();
+        ReadBatch b; b.maxReadLength = maxLen; b.wpq = (maxLen + 15) / 16;
+        for (;;) {
+            const double t1 = now_s();
+            uint32_t n = load_batch(r1, r2, b, 12 * 8192 * 128 / 6);
+            if (n == 0) break;
+            total += n; for (uint32_t i = 0; i < n; i += 1000) sum += b.lens[i] + b.queries[i] + (unsigned char)b.qual(i)[0];
+            fprintf(stderr, "batch of %u reads in %.3f s\n", n, now_s() - t1);
+        }
+        fprintf(stderr, "%llu reads in %.3f s (checksum %llu)\n", (unsigned long long)total, now_s() - t0, (unsigned long long)sum);
+        return 0;
+    }
+    if (argc >= 3 && !strcmp(argv[1], "__parse")) {
+        SeqReader r; if (!r.open(argv[2])) { fprintf(stderr, "cannot open %s\n", argv[2]); return 1; }
+        const bool generic = argc >= 4 && !strcmp(argv[3], "generic");
+        std::string nm, cm, sq, ql; SeqReader::View v;
+        for (;;) {
+            int st = generic ? 0 : r.read_fast(v);
+            if (st < 0) break;
+            if (st == 1) { nm.assign(v.name, v.nameLen); cm.assign(v.comment, v.commentLen); sq.assign(v.seq, v.seqLen); ql.assign(v.qual, v.seqLen); }
+            else { int l = r.read(nm, cm, sq, ql); if (l < 0) { if (l == -2) printf("ERR\n"); break; } }
+            printf("%s|%s|%s|%s\n", nm.c_str(), cm.c_str(), sq.c_str(), ql.c_str());
+        }
+        return 0;
+    }
     Options opt;
     if (!parse_args(argc, argv, opt)) return 1;
     const double t0 = now_s();
@@ -680,10 +800,11 @@ int main(int argc, char **argv)
     // ---- pipeline: reader thread -> GPU workers (one per context; each formats its own batch) -> ordered writer (this thread).
     //      The reference overlaps read loading with alignment the same way (aio_thread.cpp:804, SOAP4.cpp:424-441, 576-585). ----
     struct Job {
-        uint64_t seq = 0; ReadBatch b; std::string fq, log; std::vector<uint8_t> bam[3];
+        uint64_t seq = 0; ReadBatch *b = nullptr; uint32_t nReads = 0; std::vector<std::string> fqParts; std::string log; std::vector<uint8_t> bam[3];
         uint64_t pairsAligned = 0; double loadSeconds = 0, alignSeconds = 0; bool failed = false;
     };
     std::mutex mu; std::condition_variable cvIn, cvOut, cvRoom;
+    std::vector<ReadBatch *> batchPool;                            // recycled read batches (guarded by mu)
     std::deque<Job *> inq; std::map<uint64_t, Job *> doneq; bool readerDone = false; size_t inflight = 0;
     const size_t maxInflight = contexts.size() + 2;
     const int stageUnpaired = P.skipDefaultDP ? 2 : 3;
@@ -691,12 +812,15 @@ int main(int argc, char **argv)
     std::thread reader([&]() {
         uint64_t seq = 0; bool detected = false; double last = now_s();
         for (;;) {
-            Job *j = new Job; j->b.maxReadLength = (uint32_t)maxLen; j->b.wpq = ((uint32_t)maxLen + 15) / 16;
-            if (load_batch(r1, r2, j->b, maxNumQueries) == 0) { delete j; break; }
-            j->seq = seq++;
+            Job *j = new Job;
+            { std::lock_guard<std::mutex> lk(mu); if (!batchPool.empty()) { j->b = batchPool.back(); batchPool.pop_back(); } }
+            if (!j->b) j->b = new ReadBatch;
+            j->b->maxReadLength = (uint32_t)maxLen; j->b->wpq = ((uint32_t)maxLen + 15) / 16;
+            if (load_batch(r1, r2, *j->b, maxNumQueries) == 0) { delete j->b; delete j; break; }
+            j->seq = seq++; j->nReads = j->b->nReads;
             double t = now_s(); j->loadSeconds = t - last;
             if (!detected) {                                       // first batch: read-length detection and insert_low clamp (SOAP4.cpp:458-474)
-                uint32_t d1 = detect_read_length(j->b.lens, j->b.nReads, 0), d2 = detect_read_length(j->b.lens, j->b.nReads, 1);
+                uint32_t d1 = detect_read_length(j->b->lens, j->b->nReads, 0), d2 = detect_read_length(j->b->lens, j->b->nReads, 1);
                 if (opt.insert_low < (int)d2) opt.insert_low = (int)d2;
                 if (opt.insert_low < (int)d1) opt.insert_low = (int)d1;
                 P.insert_low = opt.insert_low;
@@ -713,8 +837,7 @@ int main(int argc, char **argv)
     });
 
     auto worker = [&](mp_context *gpu) {
-        OutCtx oc = octx;                                           // per-worker copy: own batch pointer and BAM capture sinks
-        BamWriter cap[3];
+        OutCtx oc = octx;                                           // per-worker copy: own batch pointer
         for (;;) {
             Job *j = nullptr;
             {
@@ -724,10 +847,14 @@ int main(int argc, char **argv)
                 j = inq.front(); inq.pop_front();
             }
             const double ts = now_s();
-            ReadBatch &b = j->b;
+            ReadBatch &b = *j->b;
             const uint32_t numQueries = b.nReads, nPairs = numQueries / 2;
             mp_results R;
-            if (mp_batch_upload(gpu, b.queries.data(), b.lens.data(), numQueries, b.wpq) || mp_align_pairs(gpu, &P, &R)) {
+            static const bool timing = getenv("MP_DRIVER_TIMING") != nullptr;      // per-batch host breakdown on stderr
+            double tUp = 0, tAl = 0, tFmt = 0;
+            int rcUp = mp_batch_upload(gpu, b.queries.data(), b.lens.data(), numQueries, b.wpq);
+            tUp = now_s();
+            if (rcUp || mp_align_pairs(gpu, &P, &R)) {
                 j->log = std::string(mp_last_error()) + "\n"; j->failed = true;
             } else {
                 char line[512];
@@ -737,48 +864,85 @@ int main(int argc, char **argv)
                          (unsigned long long)R.numSingleDPAlignment, (unsigned long long)R.numRescuedPair, (unsigned long long)R.numRescuedAlignment);
                 j->log = line;
                 j->pairsAligned = R.numDPAlignedPair + R.numRescuedPair;
+                tAl = now_s();
                 // ---- output: stage order of the reference (deep DP pairs, rescued pairs, then everything else) ----
                 if (opt.megapathMode || opt.outputBAM) {
                     oc.b = &b;
-                    for (int k = 0; k < 3; ++k) cap[k].capture = &j->bam[k];
+                    // Formatting is spread over the -T host threads: every chunk of pairs writes its own text / BAM records, and the
+                    // chunks are concatenated in order, so the stream is the one a single thread would have produced.
+                    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+                    const unsigned nThr = std::min<unsigned>((unsigned)std::max(1, opt.numCpuThreads), std::max<unsigned>(1u, hw / (unsigned)contexts.size()));
+                    struct Chunk { std::string fq; std::vector<uint8_t> bam; };
+                    auto run_chunks = [&](uint64_t nItems, int bamSlot, const std::function<uint64_t(uint64_t)> &alignStart,
+                                          const std::function<void(OutCtx &, std::string &, uint64_t, uint64_t)> &body) {
+                        if (nItems == 0) return;
+                        const unsigned nc = (unsigned)std::min<uint64_t>(nThr, (nItems + 4095) / 4096);
+                        std::vector<uint64_t> cut(nc + 1, nItems);
+                        cut[0] = 0;
+                        for (unsigned c = 1; c < nc; ++c) cut[c] = std::max(cut[c - 1], alignStart(nItems * c / nc));
+                        std::vector<Chunk> chunks(nc);
+                        auto one = [&](unsigned c) {
+                            OutCtx occ = oc; BamWriter capw; capw.capture = &chunks[c].bam;
+                            OutScratch scr; occ.scratch = &scr;
+                            occ.bam = opt.outputBAM ? &capw : nullptr;
+                            chunks[c].fq.reserve((size_t)(cut[c + 1] - cut[c]) * 512);
+                            body(occ, chunks[c].fq, cut[c], cut[c + 1]);
+                        };
+                        std::vector<std::thread> ths;
+                        for (unsigned c = 1; c < nc; ++c) ths.emplace_back(one, c);
+                        one(0);
+                        for (std::thread &t : ths) t.join();
+                        // the chunks stay separate strings (no 700 MB concatenation): the writer emits them in this order
+                        for (Chunk &c : chunks) { j->fqParts.emplace_back(std::move(c.fq)); j->bam[bamSlot].insert(j->bam[bamSlot].end(), c.bam.begin(), c.bam.end()); }
+                    };
                     std::vector<uint8_t> done(nPairs, 0);
                     for (int which = 0; which < 2; ++which) {
-                        const mp_pair_result *arrp = which == 0 ? R.pairs : R.rescued; uint64_t n = which == 0 ? R.n_pairs : R.n_rescued;
-                        oc.bam = !opt.outputBAM ? nullptr : &cap[which];
-                        for (uint64_t i = 0, e; i < n; i = e) {
-                            e = i + 1;
-                            while (e < n && arrp[e].readID == arrp[i].readID) ++e;
-                            output_pair(oc, j->fq, arrp + i, arrp + e, R.cigars, which == 0 ? 1 : 2);      // PH: hspaux->dpStageId
-                            done[arrp[i].readID >> 1] = 1;
-                        }
+                        const mp_pair_result *arrp = which == 0 ? R.pairs : R.rescued; const uint64_t n = which == 0 ? R.n_pairs : R.n_rescued;
+                        run_chunks(n, which,
+                                   [&](uint64_t i) { while (i > 0 && i < n && arrp[i].readID == arrp[i - 1].readID) ++i; return i; },   // keep the hits of one pair together
+                                   [&](OutCtx &occ, std::string &fq, uint64_t lo, uint64_t hi) {
+                                       for (uint64_t i = lo, e; i < hi; i = e) {
+                                           e = i + 1;
+                                           while (e < n && arrp[e].readID == arrp[i].readID) ++e;
+                                           output_pair(occ, fq, arrp + i, arrp + e, R.cigars, which == 0 ? 1 : 2);      // PH: hspaux->dpStageId
+                                           done[arrp[i].readID >> 1] = 1;
+                                       }
+                                   });
                     }
                     // pairs neither placed by deep DP nor rescued: per-read single-end hits (alignment.cpp:299-351)
-                    oc.bam = opt.outputBAM ? &cap[2] : nullptr;
-                    uint64_t si = 0;
-                    for (uint32_t p = 0; p < nPairs; ++p) {
-                        if (done[p]) continue;
-                        std::vector<SingleAln> hits[2];
-                        for (uint32_t e = 0; e < 2; ++e) {
-                            const uint32_t id = 2 * p + e;
-                            while (si < R.n_singles && R.singles[si].readID < id) ++si;
-                            uint64_t en = si;
-                            while (en < R.n_singles && R.singles[en].readID == id) {
-                                const mp_single_result &sr = R.singles[en];
-                                SingleAln a = { sr.algnmt, sr.score, (int)sr.strand, sr.editdist, sr.num_sameScore, R.cigars + sr.cigar };
-                                hits[e].push_back(a); ++en;
-                            }
-                            // OutputBuffer::ready: sort by (algnmt, score), drop duplicates (DV-DPfunctions.h:167-196, .cpp:248-251)
-                            std::sort(hits[e].begin(), hits[e].end(), [](const SingleAln &x, const SingleAln &y) { return std::make_pair(x.algnmt, x.score) < std::make_pair(y.algnmt, y.score); });
-                            hits[e].erase(std::unique(hits[e].begin(), hits[e].end(), [](const SingleAln &x, const SingleAln &y) { return x.algnmt == y.algnmt && x.score == y.score; }), hits[e].end());
-                        }
-                        output_unpaired(oc, j->fq, 2 * p, hits, stageUnpaired);
-                    }
+                    run_chunks(nPairs, 2, [](uint64_t p) { return p; },
+                               [&](OutCtx &occ, std::string &fq, uint64_t lo, uint64_t hi) {
+                                   // singles are ordered by readID: find where this chunk starts
+                                   uint64_t si = 0;
+                                   { uint64_t a = 0, z = R.n_singles; while (a < z) { uint64_t m = (a + z) / 2; if (R.singles[m].readID < 2 * lo) a = m + 1; else z = m; } si = a; }
+                                   for (uint64_t p = lo; p < hi; ++p) {
+                                       if (done[p]) continue;
+                                       std::vector<SingleAln> hits[2];
+                                       for (uint32_t e = 0; e < 2; ++e) {
+                                           const uint32_t id = (uint32_t)(2 * p + e);
+                                           while (si < R.n_singles && R.singles[si].readID < id) ++si;
+                                           uint64_t en = si;
+                                           while (en < R.n_singles && R.singles[en].readID == id) {
+                                               const mp_single_result &sr = R.singles[en];
+                                               SingleAln a = { sr.algnmt, sr.score, (int)sr.strand, sr.editdist, sr.num_sameScore, R.cigars + sr.cigar };
+                                               hits[e].push_back(a); ++en;
+                                           }
+                                           // OutputBuffer::ready: sort by (algnmt, score), drop duplicates (DV-DPfunctions.h:167-196, .cpp:248-251)
+                                           std::sort(hits[e].begin(), hits[e].end(), [](const SingleAln &x, const SingleAln &y) { return std::make_pair(x.algnmt, x.score) < std::make_pair(y.algnmt, y.score); });
+                                           hits[e].erase(std::unique(hits[e].begin(), hits[e].end(), [](const SingleAln &x, const SingleAln &y) { return x.algnmt == y.algnmt && x.score == y.score; }), hits[e].end());
+                                       }
+                                       output_unpaired(occ, fq, (uint32_t)(2 * p), hits, stageUnpaired);
+                                   }
+                               });
                 }
+                tFmt = now_s();
                 mp_results_release(gpu, &R);
             }
+            if (timing) fprintf(stderr, "[timing] batch %llu: upload %.3f align %.3f (lib wall %.3f) format %.3f release %.3f s\n", (unsigned long long)j->seq,
+                                tUp - ts, tAl - tUp, R.ms_wall / 1e3, tFmt - tAl, now_s() - tFmt);
             j->alignSeconds = now_s() - ts;
-            { ReadBatch empty; std::swap(j->b.queries, empty.queries); std::swap(j->b.quals, empty.quals); std::swap(j->b.names, empty.names); std::swap(j->b.comments, empty.comments); }
             std::lock_guard<std::mutex> lk(mu);
+            batchPool.push_back(j->b); j->b = nullptr;              // the text output no longer refers to the batch
             doneq[j->seq] = j; cvOut.notify_all();
         }
     };
@@ -797,11 +961,11 @@ int main(int argc, char **argv)
             if (it == doneq.end()) break;
             j = it->second; doneq.erase(it); --inflight; cvRoom.notify_one();
         }
-        fprintf(stderr, "[Main] Loaded %u short reads from the query file.\n[Main] Elapsed time on host : %9.4f seconds\n\n", j->b.nReads, j->loadSeconds);
+        fprintf(stderr, "[Main] Loaded %u short reads from the query file.\n[Main] Elapsed time on host : %9.4f seconds\n\n", j->nReads, j->loadSeconds);
         if (!announced) { fprintf(stderr, "All reads are directly processed by DP\n"); announced = true; }
         fputs(j->log.c_str(), stderr);
         if (j->failed) failed = true;
-        if (!j->fq.empty()) fwrite(j->fq.data(), 1, j->fq.size(), stdout);
+        for (const std::string &part : j->fqParts) if (!part.empty()) fwrite(part.data(), 1, part.size(), stdout);
         if (opt.outputBAM) { bamDP.write_raw(j->bam[0]); bamGout.write_raw(j->bam[1]); bamUnpair.write_raw(j->bam[2]); }
         fprintf(stderr, "[Main] Elapsed time : %9.4f seconds\n\n", j->alignSeconds);
         totalLoad += j->loadSeconds; totalAlign += j->alignSeconds; totalPairsAligned += j->pairsAligned;
@@ -809,6 +973,7 @@ int main(int argc, char **argv)
     }
     reader.join();
     for (std::thread &t : workers) t.join();
+    for (ReadBatch *rb : batchPool) delete rb;
     fflush(stdout);
     if (opt.outputBAM) { bamDP.close(); bamGout.close(); bamUnpair.close(); }
     if (failed) return 1;

@@ -59,4 +59,14 @@ for g in ([1, 2] if torch.cuda.device_count() >= 2 else [1]):
     tail = [l for l in p.stderr.decode().splitlines() if "Overall" in l or "Loading time" in l]
     print("ours -G %d: %.1f s wall (%d pairs/s incl. index load and FASTQ parsing) md5 %s %s" % (g, t_our, npairs / t_our, got, "OK" if got == want else "MISMATCH"), tail, flush=True)
     assert got == want
+# throughput of the driver itself: stdout to a file, all host threads
+for T in (4, os.cpu_count()):
+    t0 = time.time()
+    with open(os.path.join(d, "our.out"), "wb") as fo:
+        p = subprocess.run([exe, "pair", prefix, fq1, fq2, "-o", os.path.join(d, "ouro"), "-C", ini, "-L", "151", "-T", str(T), "-u", "750", "-F", "-nc"],
+                           stdout=fo, stderr=subprocess.PIPE, timeout=600, env=dict(os.environ, MP_DRIVER_TIMING="1"))
+    t_our = time.time() - t0
+    lines = p.stderr.decode().splitlines()
+    tail = [l for l in lines if "Overall" in l or "Loading time" in l or "Elapsed time" in l or "[timing]" in l]
+    print("ours -T %d to a file: %.1f s wall" % (T, t_our), tail, flush=True)
 print("big e2e ok")

@@ -1,0 +1,54 @@
+#!/usr/bin/env python3
+"""Steady-state throughput of the soap4 driver itself (FASTQ files in, annotated FASTQ out) on the GPU box:
+20 Mbp GPU-built reference, 1.2 M synthetic pairs replicated 8x (9.6 M pairs, ~3 GB per mate file)."""
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench
+import megapath_b200 as mp
+
+d = "/tmp/mp_thr"
+os.makedirs(d, exist_ok=True)
+n, npairs, rep = 20_000_000, 1_200_000, int(sys.argv[1]) if len(sys.argv) > 1 else 8
+dev = torch.device("cuda", 0)
+codes = bench.gen_ref_codes(n, 5, dev)
+bounds = bench.ref_bounds(n, 12, 5)
+ctx = mp.Context(0)
+prefix = os.path.join(d, "ref.index")
+ctx.index_build_codes(codes, bounds, prefix)
+ctx.close()
+reads = bench.gen_batch(codes, torch.from_numpy(bounds).to(dev), npairs, 99, unalignable=0.02, one_random=0.03).cpu().numpy()
+lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+for mate in (0, 1):
+    rows = lut[reads[mate::2]]
+    L = rows.shape[1]
+    names = np.char.add(np.char.add("@p", np.arange(npairs).astype(str)), "/%d" % (mate + 1)).astype("S")
+    qual = b"I" * L
+    blob = b"".join(names[i] + b"\n" + rows[i].tobytes() + b"\n+\n" + qual + b"\n" for i in range(npairs))
+    with open(os.path.join(d, "r_%d.fq" % (mate + 1)), "wb") as f:
+        for _ in range(rep):
+            f.write(blob)
+fq1, fq2 = os.path.join(d, "r_1.fq"), os.path.join(d, "r_2.fq")
+exe = os.path.join(ROOT, "megapath_b200", "bin", "soap4")
+ini = os.path.join(ROOT, "megapath_b200", "ini", "soap4.ini")
+total = npairs * rep
+for T, ctxs, sink in ((8, 2, "/dev/null"), (8, 3, "/dev/null"), (8, 2, os.path.join(d, "our.out"))):
+    t0 = time.time()
+    with open(sink, "wb") as fo:
+        p = subprocess.run([exe, "pair", prefix, fq1, fq2, "-o", os.path.join(d, "ouro"), "-C", ini, "-L", "151", "-T", str(T), "-u", "750", "-F", "-nc"],
+                           stdout=fo, stderr=subprocess.PIPE, timeout=900, env=dict(os.environ, MP_CONTEXTS_PER_GPU=str(ctxs), MP_DRIVER_TIMING="1"))
+    wall = time.time() - t0
+    assert p.returncode == 0, p.stderr.decode()[-2000:]
+    lines = p.stderr.decode().splitlines()
+    loop = [float(l.split(":")[1].split()[0]) for l in lines if "Overall alignment time" in l][0]
+    load = [l for l in lines if "Elapsed time on host" in l]
+    tim = [l for l in lines if "[timing]" in l]
+    print("-T %d, %d contexts, out=%s: wall %.1f s; batch loop %.2f s = %.2f M pairs/s; reader per batch %s; last batches %s" % (
+        T, ctxs, sink, wall, loop, total / loop / 1e6, [l.split(":")[1].split()[0] for l in load[-4:-1]], tim[-3:]), flush=True)
