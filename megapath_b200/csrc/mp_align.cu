@@ -293,7 +293,7 @@ extern "C" int mp_clone(mp_context *src, mp_context **pctx)
     mp_context *c = *pctx;
     c->ix = src->ix; c->saInterval = src->saInterval; c->hbmBytes = src->hbmBytes;
     c->hasIndex = true; c->sharedIndex = true;
-    c->bloomK = src->bloomK; c->bloomWords = src->bloomWords; c->bloomFor = src->bloomFor;
+    c->bloomK = src->bloomK; c->bloomStride = src->bloomStride; c->bloomSeedMin = src->bloomSeedMin; c->bloomWords = src->bloomWords; c->bloomFor = src->bloomFor;
     c->dBloom.p = src->dBloom.p; c->dBloom.cap = 0;          // borrowed: never freed or grown by the clone
     return 0;
 }

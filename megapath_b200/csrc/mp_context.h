@@ -116,7 +116,7 @@ struct mp_context {
     bool hasIndex = false, sharedIndex = false;   // sharedIndex: index buffers belong to another context (mp_clone)
     MpIndexView ix;
     DevBuf dBlocks, dSuper, dSa, dSa32, dLkt, dPac, dBloom;
-    int bloomK = 0; uint64_t bloomWords = 0; const void *bloomFor = nullptr;   // K-mer presence filter (mp_seed.cu)
+    int bloomK = 0, bloomStride = 1, bloomSeedMin = 0; uint64_t bloomWords = 0; const void *bloomFor = nullptr;   // K-mer presence filter (mp_seed.cu)
     uint64_t hbmBytes = 0;
     std::vector<uint64_t> hSa; uint64_t saInterval = 16;   // kept for mp_index_save
     // batch

@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(128)
 k_mmp(MpIndexView ix, const uint32_t *__restrict__ reads, const uint32_t *__restrict__ lens, uint32_t wpq,
       uint32_t nStrands, MmpDev P, MpSeed *__restrict__ seeds, uint32_t *__restrict__ stubs,
       unsigned long long *__restrict__ counters, uint32_t *__restrict__ hitsPerRead,
-      uint32_t capSeeds, uint32_t capStubs, const unsigned long long *__restrict__ bloom, uint64_t bloomWords, int bloomK)
+      uint32_t capSeeds, uint32_t capStubs, const unsigned long long *__restrict__ bloom, uint64_t bloomWords, int bloomK, int bloomStride)
 {
     const uint64_t n = ix.n;
     unsigned long long nOcc = 0, nLkt = 0, nSaIn = 0, nLfIn = 0, nProbe = 0, nText = 0;
@@ -208,19 +208,27 @@ k_mmp(MpIndexView ix, const uint32_t *__restrict__ reads, const uint32_t *__rest
                 if (len - i < P.seedMinLength) { state = ST_DONE; continue; }
                 bool go = true;
                 if (bloom) {                                          // 4 probes in flight
-                    const int m = min(4, len - i - P.seedMinLength + 1);
+                    // Start i0 is decided by the bloomK-mer at p = the first multiple of bloomStride >= i0: a match of seedMinLength
+                    // bases from i0 covers [p, p + bloomK) because bloomK = seedMinLength - (bloomStride - 1).  One probe therefore
+                    // rules out up to bloomStride starts.
+                    const int lastStart = len - P.seedMinLength;
+                    const int p0 = (i + bloomStride - 1) / bloomStride * bloomStride;
+                    int m = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (p0 + j * bloomStride - bloomStride + 1 <= lastStart) m = j + 1;
                     unsigned long long wv[4]; uint64_t mk[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         wv[j] = ~0ull; mk[j] = 0;
-                        if (j < m) { uint64_t wi; bloom_slot(scan_kmer(rd, len, i + j, strand, bloomK), bloomWords, wi, mk[j]); wv[j] = __ldg(bloom + wi); }
+                        if (j < m) { uint64_t wi; bloom_slot(scan_kmer(rd, len, p0 + j * bloomStride, strand, bloomK), bloomWords, wi, mk[j]); wv[j] = __ldg(bloom + wi); }
                     }
                     nProbe += m;
                     int hit = m;
 #pragma unroll
                     for (int j = 3; j >= 0; --j) if (j < m && (wv[j] & mk[j]) == mk[j]) hit = j;
-                    i += hit;
                     go = hit < m;
+                    if (go) i = max(i, p0 + hit * bloomStride - bloomStride + 1);      // first start that probe does not rule out
+                    else i = p0 + (m - 1) * bloomStride + 1;                             // every start up to the last probe is dead
                 }
                 if (go) {
                     uint32_t key = lkt_key(rd, len, i, strand);
@@ -493,9 +501,18 @@ static int ensure_bloom(mp_context *ctx, int seedMinLength)
 {
     const char *e = getenv("MP_BLOOM");
     if (e && e[0] == '0') { ctx->bloomK = 0; return 0; }
-    const int K = seedMinLength < 32 ? seedMinLength : 32;
     const uint64_t n = ctx->ix.n;
-    if (ctx->bloomK == K && ctx->bloomFor == (const void *)ctx->ix.blocks) return 0;
+    // Probe stride s: K = seedMinLength - (s - 1) must stay long enough that a random K-mer is rarely in the text
+    // (4^K >= 256 n), else too many starts survive the filter and are walked.  3.1 Gbp, seedMinLength 22 -> s = 3, K = 20
+    // (measured k_mmp time per 1 Mi pairs: s=1 16.3 ms, s=2 13.8, s=3 13.7, s=4 14.7, s=5 19.5).
+    int kMin = 4; for (uint64_t v = 1; v < n && kMin < 40; v <<= 2) ++kMin;
+    int stride = seedMinLength - kMin + 1;
+    if (const char *es = getenv("MP_BLOOM_STRIDE")) stride = atoi(es);
+    if (stride > 8) stride = 8;
+    if (stride < 1) stride = 1;
+    if (stride > seedMinLength - 12) stride = seedMinLength - 12 > 1 ? seedMinLength - 12 : 1;
+    int K = seedMinLength - (stride - 1); if (K > 32) K = 32;
+    if (ctx->bloomK == K && ctx->bloomStride == stride && ctx->bloomSeedMin == seedMinLength && ctx->bloomFor == (const void *)ctx->ix.blocks) return 0;
     if (n < (uint64_t)K) { ctx->bloomK = 0; return 0; }
     uint64_t nWords = n / 4 + 1024;                      // 16 bits per text position ...
     {                                                    // ... unless that would take more than a third of what is free (60 Gbp texts)
@@ -511,7 +528,7 @@ static int ensure_bloom(mp_context *ctx, int seedMinLength)
     (++g_mp_launches), k_bloom_build<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(ctx->ix.pac, n, K, ctx->dBloom.as<unsigned long long>(), nWords);
     MP_CUDA(cudaGetLastError());
     MP_CUDA(cudaStreamSynchronize(ctx->stream));
-    ctx->bloomK = K; ctx->bloomWords = nWords; ctx->bloomFor = (const void *)ctx->ix.blocks;
+    ctx->bloomK = K; ctx->bloomStride = stride; ctx->bloomSeedMin = seedMinLength; ctx->bloomWords = nWords; ctx->bloomFor = (const void *)ctx->ix.blocks;
     ctx->hbmBytes += ctx->dBloom.cap;
     return 0;
 }
@@ -552,7 +569,7 @@ int mps_seed_pairs(mp_context *ctx, const mp_align_params *AP)
         (++g_mp_launches), k_mmp<<<nSM * 16, 128, 0, st>>>(ctx->ix, ctx->dReads.as<uint32_t>(), ctx->dLens.as<uint32_t>(), ctx->wpq, nStrands, P,
                                       ctx->dSeeds.as<MpSeed>(), ctx->dStubs.as<uint32_t>(), ctx->dCounters.as<unsigned long long>(),
                                       ctx->dHitsPerRead.as<uint32_t>(), (uint32_t)ctx->capSeeds, (uint32_t)ctx->capStubs,
-                                      ctx->bloomK ? ctx->dBloom.as<unsigned long long>() : nullptr, ctx->bloomWords, ctx->bloomK);
+                                      ctx->bloomK ? ctx->dBloom.as<unsigned long long>() : nullptr, ctx->bloomWords, ctx->bloomK, ctx->bloomStride);
         MP_CUDA(cudaGetLastError());
         MP_CUDA(cudaMemcpyAsync(hc, ctx->dCounters.p, 16 * 8, cudaMemcpyDeviceToHost, st));
         MP_CUDA(cudaStreamSynchronize(st));
