@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--pairs-per-step", type=int, default=int(os.environ.get("MP_BENCH_PAIRS", str(1 << 20))))
     ap.add_argument("--cpu-sample-pairs", type=int, default=int(os.environ.get("MP_BENCH_CPU_PAIRS", "200000")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--contexts", type=int, default=int(os.environ.get("MP_BENCH_CONTEXTS", "2")),
+    ap.add_argument("--contexts", type=int, default=int(os.environ.get("MP_BENCH_CONTEXTS", "3")),
                     help="contexts (host thread + stream each) per GPU sharing one resident index; batches alternate between them")
     ap.add_argument("--workdir", default=os.environ.get("MP_BENCH_DIR", "/tmp/mpbench"))
     ap.add_argument("--profile-step", action="store_true",
@@ -518,7 +518,9 @@ def run(args, saved_stdout):
                         "sector_gbs": seed_sectors / (acc["ms_seed"] / 1e3) / 1e9, "gather32_peak_gbs": gather32, "gather64_peak_gbs": gather64,
                         "frac_of_gather32_peak": (seed_sectors / (acc["ms_seed"] / 1e3) / 1e9 / gather32) if gather32 else None,
                         "reference_algorithm_equiv_gbs": (64.0 * acc["n_occ"] + 16.0 * acc["n_lkt"] + 8.0 * acc["n_sa"]) / (acc["ms_seed"] / 1e3) / 1e9,
-                        "note": "n_occ counts the occ evaluations the reference makes for the executed steps; starts rejected by the K-mer filter are not walked at all"},
+                        "counters_per_step": {k: acc[k] / steps for k in ("n_probe", "n_lkt", "n_occ", "n_sa", "n_text", "n_lf") if k in acc},
+                        "note": "n_occ counts the occ evaluations the reference makes for the executed steps; starts rejected by the K-mer filter are not walked at all; "
+                                "n_probe counts every filter probe issued, including re-probes that hit in L1"},
             "sa_lookup_gbs": (64.0 * acc["n_lf"] + 8.0 * acc["n_sa"]) / (acc["ms_sa"] / 1e3) / 1e9 if acc["ms_sa"] else None,
             "stage_ms_per_step": {k: acc[k] / steps for k in ("ms_seed", "ms_sa", "ms_pair", "ms_dp", "ms_fill", "ms_tb", "ms_total", "ms_wall")}}
     out = {"metric": "read pairs aligned/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
