@@ -449,10 +449,21 @@ def run(args, saved_stdout):
         sys.stderr.write("rank %d loop R: %s\n" % (rank, json.dumps({k: round(v / args.steps, 3) for k, v in acc.items() if k.startswith("ms_")})))
 
     def pipelined(upload):
-        """K steps dealt round-robin to the contexts, one host thread each; -> wall seconds between device syncs"""
+        """K steps pulled from one queue by the contexts (one host thread each), so that a K that is not a multiple of the
+        number of contexts leaves no context idle longer than one step; -> wall seconds between device syncs"""
         accs = [dict() for _ in ctxs]
-        ths = [threading.Thread(target=run_steps, args=(c, range(args.warmup + ci, args.warmup + args.steps, nctx), upload, accs[ci]))
-               for ci, c in enumerate(ctxs)]
+        lock = threading.Lock()
+        nxt = [args.warmup]
+
+        def ids():
+            while True:
+                with lock:
+                    i = nxt[0]
+                    nxt[0] += 1
+                if i >= args.warmup + args.steps:
+                    return
+                yield i
+        ths = [threading.Thread(target=run_steps, args=(c, ids(), upload, accs[ci])) for ci, c in enumerate(ctxs)]
         barrier()
         t0 = time.perf_counter()
         for t in ths:
@@ -471,7 +482,7 @@ def run(args, saved_stdout):
     pairs_aligned_A = sum(a.get("pairs_aligned", 0) for a in accsA)
     # ---- loop B (e2e): the same through host buffers: pinned-host -> HBM upload of every batch, results in host memory ----
     e2e_s, accsB = pipelined(True)
-    d2h = max(a.get("result_bytes", 0) / max(1, len(range(args.warmup + ci, args.warmup + args.steps, nctx))) for ci, a in enumerate(accsB)) if accsB else 0
+    d2h = sum(a.get("result_bytes", 0) for a in accsB) / max(1, args.steps)
     clocks = sampler.stop()
 
     from megapath_b200 import shard
