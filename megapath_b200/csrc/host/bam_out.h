@@ -26,19 +26,37 @@ static const uint64_t NOT_ALIGNED = ~0ull;
 struct BgzfWriter {
     FILE *f = nullptr; std::vector<uint8_t> buf;
     bool open(const std::string &path) { f = fopen(path.c_str(), "wb"); buf.reserve(0xff00); return f != nullptr; }
-    void flush_block(const uint8_t *data, size_t len) {
-        uint8_t out[0x10000 + 64];
+    // one BGZF block (<= 0xff00 input bytes) appended to `out`
+    static void compress_block(const uint8_t *data, size_t len, std::vector<uint8_t> &out) {
+        const size_t at = out.size();
+        out.resize(at + 0x10000 + 64);
+        uint8_t *o = out.data() + at;
         z_stream zs; memset(&zs, 0, sizeof zs);
         deflateInit2(&zs, Z_DEFAULT_COMPRESSION, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
-        zs.next_in = (Bytef *)data; zs.avail_in = (uInt)len; zs.next_out = out + 18; zs.avail_out = sizeof out - 18 - 8;
+        zs.next_in = (Bytef *)data; zs.avail_in = (uInt)len; zs.next_out = o + 18; zs.avail_out = 0x10000 + 64 - 18 - 8;
         deflate(&zs, Z_FINISH);
         size_t clen = zs.total_out; deflateEnd(&zs);
         static const uint8_t hdr[16] = { 31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 'B', 'C', 2, 0 };
-        memcpy(out, hdr, 16);
-        uint16_t bsize = (uint16_t)(clen + 25); out[16] = bsize & 0xff; out[17] = bsize >> 8;
+        memcpy(o, hdr, 16);
+        uint16_t bsize = (uint16_t)(clen + 25); o[16] = bsize & 0xff; o[17] = bsize >> 8;
         uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), data, (uInt)len), isz = (uint32_t)len;
-        memcpy(out + 18 + clen, &crc, 4); memcpy(out + 22 + clen, &isz, 4);
-        fwrite(out, 1, clen + 26, f);
+        memcpy(o + 18 + clen, &crc, 4); memcpy(o + 22 + clen, &isz, 4);
+        out.resize(at + clen + 26);
+    }
+    // any number of bytes -> a run of complete BGZF blocks in memory (formatting threads compress their own chunks;
+    // BGZF blocks are independent, so the concatenation of the chunks' blocks is a valid stream)
+    static void compress_all(const uint8_t *data, size_t len, std::vector<uint8_t> &out) {
+        for (size_t at = 0; at < len; at += 0xff00) compress_block(data + at, len - at < 0xff00 ? len - at : 0xff00, out);
+    }
+    void flush_block(const uint8_t *data, size_t len) {
+        std::vector<uint8_t> out; compress_block(data, len, out);
+        fwrite(out.data(), 1, out.size(), f);
+    }
+    // blocks compressed elsewhere: close the block in progress, then copy them through
+    void write_blocks(const std::vector<uint8_t> &blocks) {
+        if (blocks.empty()) return;
+        if (!buf.empty()) { flush_block(buf.data(), buf.size()); buf.clear(); }
+        fwrite(blocks.data(), 1, blocks.size(), f);
     }
     void write(const void *p, size_t n) {
         const uint8_t *s = (const uint8_t *)p;
@@ -92,6 +110,7 @@ struct BamWriter {
         } else { z.write(&block, 4); z.write(x, 32); z.write(r.data.data(), r.data.size()); }
     }
     void write_raw(const std::vector<uint8_t> &bytes) { if (!bytes.empty()) z.write(bytes.data(), bytes.size()); }
+    void write_blocks(const std::vector<uint8_t> &blocks) { z.write_blocks(blocks); }
     void close() { z.close(); }
 };
 

@@ -872,7 +872,7 @@ int main(int argc, char **argv)
                     // chunks are concatenated in order, so the stream is the one a single thread would have produced.
                     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
                     const unsigned nThr = std::min<unsigned>((unsigned)std::max(1, opt.numCpuThreads), std::max<unsigned>(1u, hw / (unsigned)contexts.size()));
-                    struct Chunk { std::string fq; std::vector<uint8_t> bam; };
+                    struct Chunk { std::string fq; std::vector<uint8_t> bam, bamz; };   // bamz: the chunk's BAM records as BGZF blocks
                     auto run_chunks = [&](uint64_t nItems, int bamSlot, const std::function<uint64_t(uint64_t)> &alignStart,
                                           const std::function<void(OutCtx &, std::string &, uint64_t, uint64_t)> &body) {
                         if (nItems == 0) return;
@@ -887,13 +887,14 @@ int main(int argc, char **argv)
                             occ.bam = opt.outputBAM ? &capw : nullptr;
                             chunks[c].fq.reserve((size_t)(cut[c + 1] - cut[c]) * 512);
                             body(occ, chunks[c].fq, cut[c], cut[c + 1]);
+                            if (!chunks[c].bam.empty()) { BgzfWriter::compress_all(chunks[c].bam.data(), chunks[c].bam.size(), chunks[c].bamz); std::vector<uint8_t>().swap(chunks[c].bam); }
                         };
                         std::vector<std::thread> ths;
                         for (unsigned c = 1; c < nc; ++c) ths.emplace_back(one, c);
                         one(0);
                         for (std::thread &t : ths) t.join();
                         // the chunks stay separate strings (no 700 MB concatenation): the writer emits them in this order
-                        for (Chunk &c : chunks) { j->fqParts.emplace_back(std::move(c.fq)); j->bam[bamSlot].insert(j->bam[bamSlot].end(), c.bam.begin(), c.bam.end()); }
+                        for (Chunk &c : chunks) { j->fqParts.emplace_back(std::move(c.fq)); j->bam[bamSlot].insert(j->bam[bamSlot].end(), c.bamz.begin(), c.bamz.end()); }
                     };
                     std::vector<uint8_t> done(nPairs, 0);
                     for (int which = 0; which < 2; ++which) {
@@ -966,7 +967,7 @@ int main(int argc, char **argv)
         fputs(j->log.c_str(), stderr);
         if (j->failed) failed = true;
         for (const std::string &part : j->fqParts) if (!part.empty()) fwrite(part.data(), 1, part.size(), stdout);
-        if (opt.outputBAM) { bamDP.write_raw(j->bam[0]); bamGout.write_raw(j->bam[1]); bamUnpair.write_raw(j->bam[2]); }
+        if (opt.outputBAM) { bamDP.write_blocks(j->bam[0]); bamGout.write_blocks(j->bam[1]); bamUnpair.write_blocks(j->bam[2]); }
         fprintf(stderr, "[Main] Elapsed time : %9.4f seconds\n\n", j->alignSeconds);
         totalLoad += j->loadSeconds; totalAlign += j->alignSeconds; totalPairsAligned += j->pairsAligned;
         delete j; ++next;

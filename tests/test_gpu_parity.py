@@ -146,3 +146,31 @@ def test_gpu_index_build_matches_reference_builder(workdir, total, nseq, repeat_
     sidx = rng.integers(0, total + 1, size=4000).astype(np.uint64)
     assert (c.sa(sidx) == ix.sa(sidx)).all()
     c.close()
+
+
+@pytest.mark.parametrize("stride", ["0", "1", "2", "3", "5", "8"])
+def test_gpu_seeding_is_exact_for_every_filter_stride(workdir, small_ref, stride, monkeypatch):
+    """The K-mer presence filter only skips starts that cannot produce a seed: SeedPos arrays must equal the oracle's with the
+    filter off (MP_BLOOM=0) and with every probe stride (K = seedMinLength - (stride - 1)); the bench's 3.1 Gbp text uses
+    stride 3, the small test texts would pick 8 on their own."""
+    import megapath_b200 as mp
+    if stride == "0":
+        monkeypatch.setenv("MP_BLOOM", "0")
+    else:
+        monkeypatch.setenv("MP_BLOOM_STRIDE", stride)
+    c = mp.Context(0)
+    try:
+        c.index_load(small_ref["prefix"])
+        ix = po.Index(small_ref["prefix"])
+        for name, rlen, lopt, kw in READ_SETS[:3]:
+            fq1, fq2 = make_reads(workdir, small_ref, "s_" + name, 600, rlen, seed=33, **kw)
+            reads, lens = load_pairs(fq1, fq2, trunc=lopt - 1)
+            rp, mpos = ix.seed_pairs(reads, lens, po.mmp_params())
+            q, wpq = mp.pack_queries(reads, lens, lopt)
+            c.batch_upload(q, lens, wpq)
+            P = mp.default_params(insert_low=max(1, int(lens.max())), insert_high=750, max_read_length=lopt)
+            c.seed_pairs(P)
+            grp, gmp = c.download_seedpos()
+            assert grp.tobytes() == rp.tobytes() and gmp.tobytes() == mpos.tobytes(), (stride, name)
+    finally:
+        c.close()
