@@ -74,7 +74,8 @@ struct PairWork { uint32_t ok; uint32_t cigLen[2]; };
 __global__ void k_assemble_measure(uint32_t n, const MpDpTask *__restrict__ lt, const MpDpOut *__restrict__ lo,
                                    const MpDpTask *__restrict__ rt, const MpDpOut *__restrict__ ro,
                                    const uint8_t *__restrict__ lpat, const uint8_t *__restrict__ rpat, uint32_t patStride,
-                                   int open, int ext, uint32_t *__restrict__ okFlag, uint32_t *__restrict__ cigBytes)
+                                   int open, int ext, uint32_t *__restrict__ okFlag, uint32_t *__restrict__ cigBytes,
+                                   uint32_t *__restrict__ leftLen)
 {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
@@ -84,6 +85,7 @@ __global__ void k_assemble_measure(uint32_t n, const MpDpTask *__restrict__ lt, 
         CigStats a = cigar_encode(lpat + (size_t)c * patStride, open, ext, nullptr, 0);
         CigStats b = cigar_encode(rpat + (size_t)c * patStride, open, ext, nullptr, 0);
         bytes = a.textLen + 1 + b.textLen + 1;
+        leftLen[c] = a.textLen;                       // the write pass encodes each leg once, backwards from its known length
     }
     okFlag[c] = ok; cigBytes[c] = bytes;
 }
@@ -94,8 +96,8 @@ __global__ void k_assemble_write(uint32_t n, const mp_candidate *__restrict__ ca
                                  const MpDpOut *__restrict__ lo, const MpDpTask *__restrict__ rt, const MpDpOut *__restrict__ ro,
                                  const uint8_t *__restrict__ lpat, const uint8_t *__restrict__ rpat, uint32_t patStride,
                                  AsmParams A, const uint32_t *__restrict__ okFlag, const uint32_t *__restrict__ outIdx,
-                                 const uint32_t *__restrict__ cigOff, uint32_t cigBase, mp_pair_result *__restrict__ res, char *__restrict__ cig,
-                                 uint8_t *__restrict__ alignedPair)
+                                 const uint32_t *__restrict__ cigOff, const uint32_t *__restrict__ leftLen, uint32_t cigBase,
+                                 mp_pair_result *__restrict__ res, char *__restrict__ cig, uint8_t *__restrict__ alignedPair)
 {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n || !okFlag[c]) return;
@@ -106,9 +108,9 @@ __global__ void k_assemble_write(uint32_t n, const mp_candidate *__restrict__ ca
     int editdist[2], DIS[2]; uint32_t cigPos[2];
     uint32_t off = cigOff[c];
     const int lengths_i = rt[c].readLen;                // batch->lengths[i] was overwritten by packRight
+    const int textLen[2] = { (int)leftLen[c], (int)(cigOff[c + 1] - cigOff[c]) - (int)leftLen[c] - 2 };
     for (int s = 0; s < 2; ++s) {
-        CigStats m = cigar_encode(pat[s], A.open, A.ext, nullptr, 0);
-        cigar_encode(pat[s], A.open, A.ext, cig + off, m.textLen);
+        CigStats m = cigar_encode(pat[s], A.open, A.ext, cig + off, textLen[s]);
         cig[off + m.textLen] = 0;
         cigPos[s] = cigBase + off;
         off += m.textLen + 1;
@@ -180,7 +182,7 @@ static int deep_dp(mp_context *ctx, const mp_align_params *P, mp_results *out, u
     if (dLT.reserve((size_t)chunkCap * sizeof(MpDpTask)) || dRT.reserve((size_t)chunkCap * sizeof(MpDpTask)) ||
         dLO.reserve((size_t)chunkCap * sizeof(MpDpOut)) || dRO.reserve((size_t)chunkCap * sizeof(MpDpOut)) ||
         dLP.reserve((size_t)chunkCap * patStride) || dRP.reserve((size_t)chunkCap * patStride) ||
-        dOk.reserve(((size_t)chunkCap + 1) * 4) || dBytes.reserve(((size_t)chunkCap + 1) * 4) ||
+        dOk.reserve(((size_t)chunkCap + 1) * 4) || dBytes.reserve(((size_t)chunkCap + 1) * 4 * 2) ||
         dIdx.reserve(((size_t)chunkCap + 1) * 4) || dOff.reserve(((size_t)chunkCap + 1) * 4) ||
         dRes.reserve((size_t)chunkCap * sizeof(mp_pair_result))) return MP_ERR_CUDA;
     PinnedBuf<mp_pair_result> &H = ctx->hPairs;
@@ -207,7 +209,7 @@ static int deep_dp(mp_context *ctx, const mp_align_params *P, mp_results *out, u
         MP_CUDA(cudaMemsetAsync(dBytes.p, 0, ((size_t)n + 1) * 4, st));
         (++g_mp_launches), k_assemble_measure<<<g, 128, 0, st>>>(n, dLT.as<MpDpTask>(), dLO.as<MpDpOut>(), dRT.as<MpDpTask>(), dRO.as<MpDpOut>(),
                                               dLP.as<uint8_t>(), dRP.as<uint8_t>(), patStride, P->openGapScore, P->extendGapScore,
-                                              dOk.as<uint32_t>(), dBytes.as<uint32_t>());
+                                              dOk.as<uint32_t>(), dBytes.as<uint32_t>(), dBytes.as<uint32_t>() + chunkCap + 1);
         if (scan_u32(ctx, dOk.as<uint32_t>(), dIdx.as<uint32_t>(), (uint64_t)n + 1)) return MP_ERR_CUDA;
         if (scan_u32(ctx, dBytes.as<uint32_t>(), dOff.as<uint32_t>(), (uint64_t)n + 1)) return MP_ERR_CUDA;
         uint32_t nOk = 0, nBytes = 0;
@@ -220,7 +222,8 @@ static int deep_dp(mp_context *ctx, const mp_align_params *P, mp_results *out, u
         if (nOk) {
             (++g_mp_launches), k_assemble_write<<<g, 128, 0, st>>>(n, cands, dLT.as<MpDpTask>(), dLO.as<MpDpOut>(), dRT.as<MpDpTask>(), dRO.as<MpDpOut>(),
                                                 dLP.as<uint8_t>(), dRP.as<uint8_t>(), patStride, A, dOk.as<uint32_t>(), dIdx.as<uint32_t>(),
-                                                dOff.as<uint32_t>(), cigBase, dRes.as<mp_pair_result>(), dCig.as<char>(), ctx->dAligned.as<uint8_t>());
+                                                dOff.as<uint32_t>(), dBytes.as<uint32_t>() + chunkCap + 1, cigBase, dRes.as<mp_pair_result>(), dCig.as<char>(),
+                                                ctx->dAligned.as<uint8_t>());
             MP_CUDA(cudaGetLastError());
             size_t h0 = H.size();
             if (H.resize(h0 + nOk) || HC.resize((size_t)cigBase + nBytes)) return MP_ERR_CUDA;
