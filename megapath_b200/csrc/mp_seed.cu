@@ -14,6 +14,10 @@
 //              covered-length union, uniqueness / length filters -> SeedPos entries.
 //   k_pair     one thread per pair and orientation: window join -> CandidateInfo.
 #include "mp_context.h"
+#include <cooperative_groups.h>
+#include <cooperative_groups/scan.h>
+#include <cooperative_groups/reduce.h>
+namespace cg = cooperative_groups;
 #include <cub/device/device_scan.cuh>
 #include <algorithm>
 
@@ -300,8 +304,19 @@ k_mmp(MpIndexView ix, const uint32_t *__restrict__ reads, const uint32_t *__rest
                     }
                     uint64_t d = resolved ? 0 : r - l; if (d > (uint64_t)P.seedSAsizeThreshold) d = P.seedSAsizeThreshold;
                     uint32_t cnt = (uint32_t)d + 1;
-                    uint32_t slot = (uint32_t)atomicAdd(&counters[0], 1ull);
-                    uint32_t hb = (uint32_t)atomicAdd(&counters[1], (unsigned long long)cnt);
+                    // seed slot and hit range: the lanes of the warp that emit in this trip share one pair of atomics
+                    uint32_t slot, hb;
+                    {
+                        cg::coalesced_group grp = cg::coalesced_threads();
+                        const uint32_t before = cg::exclusive_scan(grp, cnt), total = cg::reduce(grp, cnt, cg::plus<uint32_t>());
+                        uint32_t s0 = 0, h0 = 0;
+                        if (grp.thread_rank() == 0) {
+                            s0 = (uint32_t)atomicAdd(&counters[0], (unsigned long long)grp.size());
+                            h0 = (uint32_t)atomicAdd(&counters[1], (unsigned long long)total);
+                        }
+                        slot = grp.shfl(s0, 0) + grp.thread_rank();
+                        hb = grp.shfl(h0, 0) + before;
+                    }
                     atomicAdd(&hitsPerRead[read], cnt);
                     if (slot < capSeeds) {
                         MpSeed sd; sd.sa_l = resolved ? p : l; sd.strandIdx = s; sd.hitBase = hb;
@@ -343,22 +358,28 @@ __global__ void k_expand(MpIndexView ix, const MpSeed *__restrict__ seeds, const
                          uint32_t *__restrict__ cursor, MpHit *__restrict__ hits, unsigned long long *__restrict__ counters)
 {
     uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= nStubs) return;
-    MpSeed sd = seeds[stubs[h]];
-    uint32_t k = (uint32_t)h - sd.hitBase;
-    uint32_t steps = 0;
-    uint64_t sa = sd.pad ? sd.sa_l : mp_sa(ix, sd.sa_l + k, &steps);     // pad = 1: text position already known (phase B of k_mmp)
-    uint32_t read = sd.strandIdx >> 1, strand = sd.strandIdx & 1;
-    uint32_t readLen = lens[read], off = sd.query_offset, seedlen = sd.seed_len;
-    uint64_t t = strand == 0 ? sa - off : sa - (uint64_t)(uint32_t)(readLen - seedlen - off);
-    MpHit hit;
-    hit.offset = t;
-    hit.multiplicity = ((int)seedlen >= P.goodSeedLen || seedlen >= readLen / 2) ? 1 : (uint16_t)(sd.sa_diff + 1);
-    hit.length = (uint16_t)seedlen; hit.query_offset = (uint16_t)off; hit.strand = (uint16_t)strand;
-    uint32_t slot = hitStart[read] + atomicAdd(&cursor[read], 1u);
-    hits[slot] = hit;
-    atomicAdd(&counters[3], 1ull);
-    atomicAdd(&counters[5], (unsigned long long)steps);
+    uint32_t steps = 0, done = 0;
+    if (h < nStubs) {
+        MpSeed sd = seeds[stubs[h]];
+        uint32_t k = (uint32_t)h - sd.hitBase;
+        uint64_t sa = sd.pad ? sd.sa_l : mp_sa(ix, sd.sa_l + k, &steps);     // pad = 1: text position already known (phase B of k_mmp)
+        uint32_t read = sd.strandIdx >> 1, strand = sd.strandIdx & 1;
+        uint32_t readLen = lens[read], off = sd.query_offset, seedlen = sd.seed_len;
+        uint64_t t = strand == 0 ? sa - off : sa - (uint64_t)(uint32_t)(readLen - seedlen - off);
+        MpHit hit;
+        hit.offset = t;
+        hit.multiplicity = ((int)seedlen >= P.goodSeedLen || seedlen >= readLen / 2) ? 1 : (uint16_t)(sd.sa_diff + 1);
+        hit.length = (uint16_t)seedlen; hit.query_offset = (uint16_t)off; hit.strand = (uint16_t)strand;
+        uint32_t slot = hitStart[read] + atomicAdd(&cursor[read], 1u);
+        hits[slot] = hit;
+        done = 1;
+    }
+    // work counters: one atomic per warp, not two per hit on the same two addresses
+    done = __reduce_add_sync(0xffffffffu, done); steps = __reduce_add_sync(0xffffffffu, steps);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&counters[3], (unsigned long long)done);
+        if (steps) atomicAdd(&counters[5], (unsigned long long)steps);
+    }
 }
 
 // ------------------------------------------------------------------------------------
