@@ -518,7 +518,7 @@ def run(args, saved_stdout):
             "peak_kind": peak_kind, "algorithmic": "1 traceback byte written per DP cell (SURVEY 8d cells = sum refLen*readLen)",
             "ms_per_step": acc["ms_fill"] / steps,
             "note": "integer-ALU bound, not bandwidth bound: ncu ALU pipe 90.8% busy, issue slots 79.7%, top stall math_pipe_throttle "
-                    "(profiles/r01_ncu_full_v5_cfg2.txt); per-kernel times come from a single-context pass (loop R), value/e2e from the pipelined passes",
+                    "(profiles/r01_ncu_full_v7_cfg2.txt); per-kernel times come from a single-context pass (loop R), value/e2e from the pipelined passes",
             "compute": {"gcups_fill": gcups_fill, "gcups_fill_plus_traceback": gcups_dp,
                         "dpx_peak_ginstr_s": dpx_peak, "dpx_instr_per_cell": 4.5,   # 9 packed min/max/add-max instructions per cell PAIR in the steady loop
                         "dpx_frac": (gcups_fill * 4.5 / dpx_peak) if dpx_peak else None,
