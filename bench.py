@@ -446,7 +446,7 @@ def run(args, saved_stdout):
     launches = mp.launch_count() - l0
     acc["n_fill_launches"] = 0
     if os.environ.get("MP_BENCH_VERBOSE"):
-        sys.stderr.write("rank %d loop R: %s\n" % (rank, json.dumps({k: round(v / args.steps, 3) for k, v in acc.items() if k.startswith("ms_")})))
+        sys.stderr.write("rank %d loop R: %s\n" % (rank, json.dumps(dict({k: round(v / args.steps, 3) for k, v in acc.items() if k.startswith("ms_")}, exact=acc.get("dp_tasks_exact", 0) / max(1, acc.get("dp_tasks", 1))))))
 
     def pipelined(upload):
         """K steps pulled from one queue by the contexts (one host thread each), so that a K that is not a multiple of the
@@ -502,10 +502,13 @@ def run(args, saved_stdout):
     steps = args.steps
     n_fill_launches = max(1, acc.get("n_fill_launches", 0))
     # dominant kernel: k_dp_fill (DP table fill).  Algorithmic bytes = one traceback byte written per DP cell.
-    fill_bytes = float(acc["dp_cells"])
+    # cells the fill kernel really computed: tasks whose read occurs unchanged in its window are answered by the exact-occurrence
+    # test (k_dp_exact, bit-identical results) and never reach it; dp_cells counts what the reference computes
+    cells_filled = float(acc.get("dp_cells_filled") or acc["dp_cells"])
+    fill_bytes = cells_filled
     fill_ach = fill_bytes / (acc["ms_fill"] / 1e3) / 1e9
-    gcups_fill = acc["dp_cells"] / (acc["ms_fill"] / 1e3) / 1e9
-    gcups_dp = acc["dp_cells"] / ((acc["ms_fill"] + acc["ms_tb"]) / 1e3) / 1e9
+    gcups_fill = cells_filled / (acc["ms_fill"] / 1e3) / 1e9
+    gcups_dp = acc["dp_cells"] / ((acc["ms_fill"] + acc["ms_tb"] + acc.get("ms_exact", 0.0)) / 1e3) / 1e9
     # seeding kernel: bytes it must gather = 8-byte filter probes + 16-byte LKT pairs + 64-byte occ blocks
     # (two per backward-search step that is not a text-compare step) + 4-byte SA values + 1 text byte per compare
     occ_steps = max(0.0, (acc["n_occ"] - 2.0 * acc["n_text"]) / 2.0)
@@ -515,11 +518,14 @@ def run(args, saved_stdout):
     traffic = ncu_traffic("k_dp_fill")
     roof = {"kernel": "k_dp_fill<5,-2,-3> (packed 16-bit DPX table fill, the kernel with the largest share of the step)",
             "bound": "hbm", "achieved": fill_ach, "peak": peak, "unit": "GB/s", "frac": fill_ach / peak, "traffic": traffic,
-            "peak_kind": peak_kind, "algorithmic": "1 traceback byte written per DP cell (SURVEY 8d cells = sum refLen*readLen)",
+            "peak_kind": peak_kind, "algorithmic": "1 traceback byte written per DP cell the kernel computes (SURVEY 8d cells = sum refLen*readLen over the tasks it is given)",
             "ms_per_step": acc["ms_fill"] / steps,
             "note": "integer-ALU bound, not bandwidth bound: ncu ALU pipe 90.8% busy, issue slots 79.7%, top stall math_pipe_throttle "
                     "(profiles/r01_ncu_full_v7_cfg2.txt); per-kernel times come from a single-context pass (loop R), value/e2e from the pipelined passes",
-            "compute": {"gcups_fill": gcups_fill, "gcups_fill_plus_traceback": gcups_dp,
+            "compute": {"gcups_fill": gcups_fill, "gcups_reference_equivalent_all_dp_kernels": gcups_dp,
+                        "exact_occurrence_test": {"tasks_per_step": acc.get("dp_tasks_exact", 0) / steps, "of_tasks_per_step": acc["dp_tasks"] / steps,
+                                                  "ms_per_step": acc.get("ms_exact", 0.0) / steps,
+                                                  "cells_filled_per_step": cells_filled / steps, "cells_reference_per_step": acc["dp_cells"] / steps},
                         "dpx_peak_ginstr_s": dpx_peak, "dpx_instr_per_cell": 4.5,   # 9 packed min/max/add-max instructions per cell PAIR in the steady loop
                         "dpx_frac": (gcups_fill * 4.5 / dpx_peak) if dpx_peak else None,
                         # ncu smsp__inst_executed.sum of one launch x 32 lanes / (cells / 2): includes idle lanes of the wavefront ramps
@@ -533,7 +539,7 @@ def run(args, saved_stdout):
                         "note": "n_occ counts the occ evaluations the reference makes for the executed steps; starts rejected by the K-mer filter are not walked at all; "
                                 "n_probe counts every filter probe issued, including re-probes that hit in L1"},
             "sa_lookup_gbs": (64.0 * acc["n_lf"] + 8.0 * acc["n_sa"]) / (acc["ms_sa"] / 1e3) / 1e9 if acc["ms_sa"] else None,
-            "stage_ms_per_step": {k: acc[k] / steps for k in ("ms_seed", "ms_sa", "ms_pair", "ms_dp", "ms_fill", "ms_tb", "ms_total", "ms_wall")}}
+            "stage_ms_per_step": {k: acc[k] / steps for k in ("ms_seed", "ms_sa", "ms_pair", "ms_dp", "ms_fill", "ms_tb", "ms_exact", "ms_total", "ms_wall") if k in acc}}
     out = {"metric": "read pairs aligned/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16/u8 (integer DP, 2-bit FM-index)",
            "data": "synthetic", "config": cfg, "clocks": clocks,

@@ -120,6 +120,11 @@ typedef struct mp_results {
     float ms_wall;
     /* summed device time of the DP fill / traceback kernels of this call (CUDA events around every launch) */
     float ms_fill, ms_tb;
+    /* DP tasks answered by the exact-occurrence test instead of the DP kernels (bit-identical results, see mp_dp.cu), and the cells the
+     * fill kernel really computed (dp_cells counts what the reference computes) */
+    uint64_t dp_tasks_exact, dp_cells_filled;
+    /* summed device time of that test and of compacting the remaining tasks */
+    float ms_exact, reserved_;
 } mp_results;
 
 /* ---- context ---- */

@@ -43,7 +43,8 @@ class Results(C.Structure):
                 ("n_occ", C.c_uint64), ("n_lf", C.c_uint64), ("n_sa", C.c_uint64), ("n_lkt", C.c_uint64),
                 ("dp_cells", C.c_uint64), ("dp_tasks", C.c_uint64), ("n_probe", C.c_uint64), ("n_text", C.c_uint64),
                 ("ms_seed", C.c_float), ("ms_sa", C.c_float), ("ms_pair", C.c_float),
-                ("ms_dp", C.c_float), ("ms_total", C.c_float), ("ms_wall", C.c_float), ("ms_fill", C.c_float), ("ms_tb", C.c_float)]
+                ("ms_dp", C.c_float), ("ms_total", C.c_float), ("ms_wall", C.c_float), ("ms_fill", C.c_float), ("ms_tb", C.c_float),
+                ("dp_tasks_exact", C.c_uint64), ("dp_cells_filled", C.c_uint64), ("ms_exact", C.c_float), ("reserved_", C.c_float)]
 
 
 SEEDPOS = np.dtype([("pos", "<u8"), ("strand_readID", "<u4"), ("paired_seedLength", "<u4")])

@@ -454,8 +454,8 @@ extern "C" int mp_align_pairs(mp_context *ctx, const mp_align_params *params, mp
     unsigned long long hc[16];
     MP_CUDA(cudaMemcpy(hc, ctx->dCounters.p, sizeof hc, cudaMemcpyDeviceToHost));
     out->n_occ = hc[2]; out->n_lf = hc[5] + hc[8]; out->n_sa = hc[3]; out->n_lkt = hc[4]; out->n_probe = hc[9]; out->n_text = hc[10];
-    ctx->ev_collect(out->ms_fill, out->ms_tb);
-    out->dp_cells = cells; out->dp_tasks = tasksRun;
+    ctx->ev_collect(out->ms_fill, out->ms_tb, out->ms_exact);
+    out->dp_cells = cells; out->dp_tasks = tasksRun; out->dp_tasks_exact = hc[14]; out->dp_cells_filled = hc[15];
     cudaEventElapsedTime(&out->ms_seed, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&out->ms_sa, ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&out->ms_pair, ctx->ev[2], ctx->ev[3]);

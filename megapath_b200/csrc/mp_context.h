@@ -107,9 +107,12 @@ struct mp_context {
         return evPool[evUsed + 1];
     }
     void ev_end(cudaEvent_t stop) { cudaEventRecord(stop, stream); evUsed += 2; }
-    void ev_collect(float &msFill, float &msTb) {       // after a stream sync
-        msFill = msTb = 0;
-        for (size_t i = 0; i + 1 < evUsed; i += 2) { float t = 0; cudaEventElapsedTime(&t, evPool[i], evPool[i + 1]); (evKind[i / 2] == 0 ? msFill : msTb) += t; }
+    void ev_collect(float &msFill, float &msTb, float &msExact) {       // after a stream sync; kinds 0 fill, 1 traceback, 2 exact-occurrence test
+        msFill = msTb = msExact = 0;
+        for (size_t i = 0; i + 1 < evUsed; i += 2) {
+            float t = 0; cudaEventElapsedTime(&t, evPool[i], evPool[i + 1]);
+            (evKind[i / 2] == 0 ? msFill : evKind[i / 2] == 1 ? msTb : msExact) += t;
+        }
         evUsed = 0;
     }
     // index
@@ -132,6 +135,7 @@ struct mp_context {
     mp_align_params seedParams;
     // DP
     DevBuf dTasks, dRefSeq, dReadSeq, dTable, dFill, dPattern, dDpOut;
+    DevBuf dExFlag, dExPos, dExIdx;                                              // exact-occurrence test: flags, scan, active slots (mp_dp.cu)
     DevBuf dLT, dRT, dLO, dRO, dLP, dRP, dOk, dBytes, dIdx, dOff, dRes, dCig;   // stage S1 chunk buffers (kept across calls)
     // results (host, owned until release)
     PinnedBuf<mp_pair_result> hPairs;

@@ -22,6 +22,7 @@
 // k_dp_tb<K>: one thread per task walks its own table (GPUBacktrack, CPU_DP.cpp:622-786) -- thousands of
 // independent walks in flight hide the dependent-load latency that a single walking lane cannot.
 #include "mp_context.h"
+#include <cub/device/device_scan.cuh>
 #include <algorithm>
 #include <type_traits>
 
@@ -64,15 +65,17 @@ __global__ void __launch_bounds__(128)
 k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLens, uint32_t refStride,
           const uint8_t *__restrict__ readSeq, const uint32_t *__restrict__ readLens, uint32_t readStride,
           const int32_t *__restrict__ cutoffs, uint32_t taskBase, uint32_t nTasks, MpDpParams P,
-          uint8_t *__restrict__ tables, size_t tableStride, int S, FillOut *__restrict__ fill)
+          uint8_t *__restrict__ tables, size_t tableStride, int S, FillOut *__restrict__ fill,
+          const uint32_t *__restrict__ active, const uint32_t *__restrict__ nActive)
 {
     extern __shared__ uint32_t refShared[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t pairId = blockIdx.x * 4 + wib;
-    const uint32_t lA = pairId * 2, lB = lA + 1;             // task slots inside this launch
+    const uint32_t lA = pairId * 2, lB = lA + 1;             // slots inside this launch: tables are indexed by slot
+    if (active) nTasks = *nActive;                           // only the tasks the exact-occurrence test left over (k_dp_exact)
     if (lA >= nTasks) return;
-    const uint32_t tA = taskBase + lA, tB = taskBase + lB;
     const bool hasB = lB < nTasks;
+    const uint32_t tA = taskBase + (active ? active[lA] : lA), tB = hasB ? taskBase + (active ? active[lB] : lB) : tA;
     const int mm = MM ? MM : P.mismatch, open = OPEN ? OPEN : P.open, clipLt = P.clipLt;
     int NA = (int)refLens[tA], LA = (int)readLens[tA], cutA = cutoffs[tA];
     int NB = hasB ? (int)refLens[tB] : 0, LB = hasB ? (int)readLens[tB] : 0, cutB = hasB ? cutoffs[tB] : 0;
@@ -272,11 +275,13 @@ k_dp_tb(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLens
         const uint8_t *__restrict__ readSeq, const uint32_t *__restrict__ readLens, uint32_t readStride,
         const int32_t *__restrict__ cutoffs, uint32_t taskBase, uint32_t nTasks, MpDpParams P,
         const uint8_t *__restrict__ tables, size_t tableStride, int S, const FillOut *__restrict__ fill,
-        MpDpOut *__restrict__ outs, uint8_t *__restrict__ patterns, uint32_t patStride)
+        MpDpOut *__restrict__ outs, uint8_t *__restrict__ patterns, uint32_t patStride,
+        const uint32_t *__restrict__ active, const uint32_t *__restrict__ nActive)
 {
     const uint32_t lt = blockIdx.x * blockDim.x + threadIdx.x;
+    if (active) nTasks = *nActive;
     if (lt >= nTasks) return;
-    const uint32_t task = taskBase + lt;
+    const uint32_t task = taskBase + (active ? active[lt] : lt);
     const int L = (int)readLens[task], cutoff = cutoffs[task];
     const int mm = P.mismatch, open = P.open, ext = -1, clipLt = P.clipLt;
     MpDpOut o; o.score = 0; o.hitLoc = 0; o.count = 0; o.patLen = 0;
@@ -390,6 +395,82 @@ k_dp_tb(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLens
 }
 
 // ------------------------------------------------------------------------------------
+// Exact-occurrence test.  If the read occurs in its reference window without a single difference, the DP answer is known:
+//  * no cell can exceed its column index (a column adds at most the match score 1; clips, gaps and mismatches add <= 0), so the
+//    maximum over the eligible columns is L, reached only in column L, exactly at the rows where an occurrence ends;
+//  * the answer cell is the first such row (row-major order), the tie count the number of occurrences (CPU_DP.cpp:545-590);
+//  * on the diagonal of an occurrence H = column index, so every traceback step sees H - Hdiag = 1 with equal bases, no cell of the
+//    diagonal was raised by the clip floor (H >= 1 there), and GPUBacktrack emits L times 'M'; it stops at column 0, and when that
+//    is also row 0 it appends the zero-length left clip "SV\0" (CPU_DP.cpp:788-871).
+// Such tasks skip k_dp_fill / k_dp_tb; the others are compacted into `active`.  One warp per task, one lane per window offset.
+// ------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(128)
+k_dp_exact(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLens, uint32_t refStride,
+           const uint8_t *__restrict__ readSeq, const uint32_t *__restrict__ readLens, uint32_t readStride,
+           const int32_t *__restrict__ cutoffs, uint32_t taskBase, uint32_t nTasks, MpDpParams P,
+           MpDpOut *__restrict__ outs, uint8_t *__restrict__ patterns, uint32_t patStride, uint32_t *__restrict__ needDp)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (lt >= nTasks) return;
+    const uint32_t task = taskBase + lt;
+    const int N = (int)refLens[task], L = (int)readLens[task], cutoff = cutoffs[task];
+    // same admission test as the DP kernels; scores must be the usual kind (match 1, everything else <= 0)
+    const bool ok = !(cutoff > L || cutoff <= 0 || L >= 255 + P.open - 1 + cutoff || L > 32 * K) && L > 0 && N >= L &&
+                    P.mismatch <= 0 && P.open <= 0;
+    uint32_t occ = 0; int first = -1;
+    if (ok) {
+        const uint8_t *fs = refSeq + (size_t)task * refStride, *rs = readSeq + (size_t)task * readStride;
+        const int shifts = N - L + 1;
+        // every lane screens one window offset with the first bases of the read; the few offsets that survive are then verified by
+        // the whole warp, one base per lane and trip
+        const int PRE = L < 8 ? L : 8;
+        for (int base = 0; base < shifts; base += 32) {
+            const int o = base + lane;
+            bool alive = o < shifts;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (alive && k < PRE) alive = fs[o + k] == rs[k];
+            uint32_t cand = __ballot_sync(0xffffffffu, alive);
+            while (cand) {
+                const int oc = base + __ffs(cand) - 1;
+                cand &= cand - 1;
+                bool same = true;
+                for (int k = PRE + lane; k < L; k += 32) same = same && fs[oc + k] == rs[k];
+                if (__all_sync(0xffffffffu, same)) { if (first < 0) first = oc; ++occ; }
+            }
+        }
+    }
+    if (occ == 0) { if (lane == 0) needDp[lt] = 1; return; }
+    uint8_t *pat = patterns + (size_t)task * patStride;
+    for (int k = lane; k < L; k += 32) pat[k] = 'M';
+    if (lane == 0) {
+        uint32_t p = (uint32_t)L;
+        if (first == 0) { pat[p++] = 'S'; pat[p++] = 'V'; pat[p++] = 0; }      // j == 0: min(clipLt, i = 0) = 0 clipped bases
+        pat[p] = 0;
+        MpDpOut o; o.score = L; o.hitLoc = (uint32_t)first; o.count = min(occ, 255u); o.patLen = p;
+        outs[task] = o;
+        needDp[lt] = 0;
+    }
+}
+// slots of the tasks that still need the DP, in order; also adds up what the fill kernel is about to do (work accounting)
+__global__ void k_dp_compact(const uint32_t *__restrict__ needDp, const uint32_t *__restrict__ pos, uint32_t nTasks, uint32_t taskBase,
+                             const uint32_t *__restrict__ refLens, const uint32_t *__restrict__ readLens,
+                             uint32_t *__restrict__ active, unsigned long long *__restrict__ counters)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long cells = 0; uint32_t exact = 0;
+    if (t < nTasks) {
+        if (needDp[t]) { active[pos[t]] = t; cells = (unsigned long long)refLens[taskBase + t] * readLens[taskBase + t]; }
+        else exact = 1;
+    }
+    cells = __reduce_add_sync(0xffffffffu, (uint32_t)cells);        // refLen * readLen < 2^24 per task: 32 of them fit 32 bits
+    exact = __reduce_add_sync(0xffffffffu, exact);
+    if ((threadIdx.x & 31) == 0 && counters) { if (cells) atomicAdd(&counters[15], cells); if (exact) atomicAdd(&counters[14], (unsigned long long)exact); }
+}
+
+// ------------------------------------------------------------------------------------
 // task sequence extraction (replaces packRead / repackDNA): one byte per base
 // ------------------------------------------------------------------------------------
 __global__ void k_extract(MpIndexView ix, const uint32_t *__restrict__ reads, uint32_t wpq, const MpDpTask *__restrict__ tasks,
@@ -438,27 +519,47 @@ static int launch_dp(mp_context *ctx, const uint8_t *dRef, const uint32_t *dRefL
     uint8_t *tab = ctx->dTable.as<uint8_t>();
     FillOut *fill = ctx->dFill.as<FillOut>();
     const size_t smem = (size_t)4 * S * 4;
+    // exact-occurrence shortcut (k_dp_exact): MP_DP_EXACT=0 sends every task through the DP kernels
+    static const bool useExact = !(getenv("MP_DP_EXACT") && getenv("MP_DP_EXACT")[0] == '0');
+    const uint32_t perMax = std::min<uint32_t>(per, nTasks);
+    if (useExact && (ctx->dExFlag.reserve(((size_t)perMax + 1) * 4) || ctx->dExPos.reserve(((size_t)perMax + 1) * 4) ||
+                     ctx->dExIdx.reserve(((size_t)perMax + 1) * 4) || ctx->dCounters.reserve(16 * 8))) return MP_ERR_CUDA;
     for (uint32_t base = 0; base < nTasks; base += per) {
         const uint32_t n = std::min<uint32_t>(per, nTasks - base);
         dim3 gridF((n + 7) / 8), gridT((n + 127) / 128), block(128);
+        const uint32_t *active = nullptr, *nActive = nullptr;
+#define LAUNCH_EXACT(KK) do { \
+        cudaEvent_t stop_ = ctx->ev_begin(2); \
+        MP_CUDA(cudaMemsetAsync(ctx->dExFlag.p, 0, ((size_t)n + 1) * 4, ctx->stream)); \
+        (++g_mp_launches), k_dp_exact<KK><<<(n + 3) / 4, block, 0, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, \
+            base, n, P, dOuts, dPatterns, patStride, ctx->dExFlag.as<uint32_t>()); \
+        { size_t tb_ = 0; cub::DeviceScan::ExclusiveSum(nullptr, tb_, ctx->dExFlag.as<uint32_t>(), ctx->dExPos.as<uint32_t>(), (int64_t)n + 1, ctx->stream); \
+          if (ctx->dScanTmp.reserve(tb_)) return MP_ERR_CUDA; \
+          cub::DeviceScan::ExclusiveSum(ctx->dScanTmp.p, tb_, ctx->dExFlag.as<uint32_t>(), ctx->dExPos.as<uint32_t>(), (int64_t)n + 1, ctx->stream); } \
+        (++g_mp_launches), k_dp_compact<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->dExFlag.as<uint32_t>(), ctx->dExPos.as<uint32_t>(), n, base, \
+            dRefLens, dReadLens, ctx->dExIdx.as<uint32_t>(), ctx->dCounters.as<unsigned long long>()); \
+        active = ctx->dExIdx.as<uint32_t>(); nActive = ctx->dExPos.as<uint32_t>() + n; \
+        ctx->ev_end(stop_); } while (0)
 #define LAUNCH(KK) do { \
+        if (useExact) LAUNCH_EXACT(KK); \
         cudaEvent_t stop_ = ctx->ev_begin(0); \
         if (P.mismatch == -2 && P.open == -3) \
             (++g_mp_launches), k_dp_fill<KK, -2, -3><<<gridF, block, smem, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, \
-                base, n, P, tab, tableStride, S, fill); \
+                base, n, P, tab, tableStride, S, fill, active, nActive); \
         else \
             (++g_mp_launches), k_dp_fill<KK, 0, 0><<<gridF, block, smem, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, \
-                base, n, P, tab, tableStride, S, fill); \
+                base, n, P, tab, tableStride, S, fill, active, nActive); \
         ctx->ev_end(stop_); stop_ = ctx->ev_begin(1); \
         if ((patStride & 3) == 0 && ((uintptr_t)dPatterns & 3) == 0) \
             (++g_mp_launches), k_dp_tb<KK, true><<<gridT, block, 0, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, \
-                base, n, P, tab, tableStride, S, fill, dOuts, dPatterns, patStride); \
+                base, n, P, tab, tableStride, S, fill, dOuts, dPatterns, patStride, active, nActive); \
         else \
             (++g_mp_launches), k_dp_tb<KK, false><<<gridT, block, 0, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, \
-                base, n, P, tab, tableStride, S, fill, dOuts, dPatterns, patStride); \
+                base, n, P, tab, tableStride, S, fill, dOuts, dPatterns, patStride, active, nActive); \
         ctx->ev_end(stop_); } while (0)
         if (K == 5) LAUNCH(5); else if (K == 8) LAUNCH(8); else LAUNCH(10);
 #undef LAUNCH
+#undef LAUNCH_EXACT
         MP_CUDA(cudaGetLastError());
     }
     return 0;
