@@ -5,7 +5,7 @@ import pytest
 
 from conftest import make_reads, load_pairs
 from oracle import pyoracle as po
-from test_oracle_vs_ref import random_dp_tasks, DP_SHAPES, ref_detected_len
+from test_oracle_vs_ref import random_dp_tasks, exact_occurrence_tasks, DP_SHAPES, ref_detected_len
 
 pytestmark = pytest.mark.gpu
 
@@ -174,3 +174,24 @@ def test_gpu_seeding_is_exact_for_every_filter_stride(workdir, small_ref, stride
             assert grp.tobytes() == rp.tobytes() and gmp.tobytes() == mpos.tobytes(), (stride, name)
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("clips", [(130, 130), (10, 20), (0, 0)])
+def test_gpu_dp_exact_occurrences(ctx, clips):
+    """tasks the exact-occurrence test answers (occurrence at the window start / end, window == read, homopolymer and tandem
+    windows with many occurrences, near-misses that must still go through the DP) == oracle, which
+    test_dp_exact_occurrences_match_reference_callDP pins to the reference's callDP on the same tasks"""
+    import megapath_b200 as mp
+    rng = np.random.default_rng(977 + clips[0])
+    n, maxdna, maxread = 192, 220, 152
+    refs, dl, reads, rl = exact_occurrence_tasks(rng, n, maxdna, maxread)
+    cut = np.array([po.dp_cutoff(int(x)) for x in rl], dtype=np.int32)
+    sc, hl, mc, pats = ctx.dp_batch(mp.pack_dp_interleaved(refs, dl, maxdna), dl, maxdna, mp.pack_dp_interleaved(reads, rl, maxread), rl, maxread,
+                                    cut, clips[0], clips[1])
+    full = 0
+    for t in range(n):
+        want = po.dp(refs[t, :dl[t]], reads[t, :rl[t]], clips[0], clips[1], -2, -3, int(cut[t]))
+        got = (int(sc[t]), int(hl[t]), int(mc[t]), po.pattern_bytes(pats[t]) if sc[t] >= cut[t] else b"")
+        assert got == want, (t, got, want)
+        full += want[0] == int(rl[t])
+    assert full > n // 2

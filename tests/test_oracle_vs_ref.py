@@ -63,6 +63,65 @@ DP_SHAPES = [(220, 152, False, (130, 130)), (220, 152, True, (130, 130)), (160, 
              (320, 252, False, (130, 130)), (752, 152, False, (130, 130)), (220, 152, False, (10, 20)), (220, 152, False, (0, 0))]
 
 
+def exact_occurrence_tasks(rng, n, maxdna, maxread):
+    """DP tasks whose read occurs WITHOUT any difference in the reference window: at offset 0, at the last offset, in the
+    middle, several times (tandem / homopolymer windows), next to near-misses -- the cases the CUDA path answers without
+    running the DP (k_dp_exact), so both the restatement and the CUDA path are pinned on them."""
+    refs = np.zeros((n, maxdna), np.uint8)
+    reads = np.zeros((n, maxread), np.uint8)
+    dl = np.zeros(n, np.uint32)
+    rl = np.zeros(n, np.uint32)
+    for t in range(n):
+        L = int(rng.integers(30, maxread + 1))
+        kind = t % 8
+        if kind == 5:                                    # homopolymer read in a homopolymer window: one occurrence per offset
+            rd = np.full(L, int(rng.integers(0, 4)), np.uint8)
+        elif kind == 6:                                  # short period: occurrences every `per` bases
+            per = int(rng.integers(2, 6))
+            rd = np.resize(rng.integers(0, 4, size=per).astype(np.uint8), L)
+        else:
+            rd = rng.integers(0, 4, size=L).astype(np.uint8)
+        room = maxdna - L
+        if kind == 0:
+            left, right = 0, int(rng.integers(0, room + 1))                  # occurrence at the window start (row 0 reached)
+        elif kind == 1:
+            left, right = int(rng.integers(0, room + 1)), 0                  # ... at the window end
+        elif kind == 2:
+            left, right = 0, 0                                               # window == read
+        else:
+            left = int(rng.integers(0, room + 1)); right = int(rng.integers(0, room - left + 1))
+        if kind in (5, 6):
+            w = np.resize(rd[:per] if kind == 6 else rd[:1], left + L + right)
+            if kind == 6:
+                w = np.roll(w, left % per)               # keep an occurrence at `left`
+        else:
+            w = np.concatenate([rng.integers(0, 4, size=left), rd, rng.integers(0, 4, size=right)]).astype(np.uint8)
+        if kind == 7 and left + L + right >= L + 1:      # a near-miss: one substitution, no exact occurrence (control)
+            w = w.copy(); w[left + int(rng.integers(0, L))] ^= 1
+        refs[t, :len(w)] = w
+        dl[t] = len(w)
+        reads[t, :L] = rd
+        rl[t] = L
+    return refs, dl, reads, rl
+
+
+@needs_ref
+@pytest.mark.parametrize("clips", [(130, 130), (10, 20), (0, 0)])
+def test_dp_exact_occurrences_match_reference_callDP(clips):
+    rng = np.random.default_rng(977 + clips[0])
+    n, maxdna, maxread = 192, 220, 152
+    refs, dl, reads, rl = exact_occurrence_tasks(rng, n, maxdna, maxread)
+    sc, hl, mc, pats = po.ref_dp(refs, dl, reads, rl, maxdna, maxread, clips[0], clips[1])
+    full = 0
+    for t in range(n):
+        co = po.dp_cutoff(int(rl[t]))
+        got = po.dp(refs[t, :dl[t]], reads[t, :rl[t]], clips[0], clips[1], -2, -3, co)
+        want = (int(sc[t]), int(hl[t]), int(mc[t]), po.pattern_bytes(pats[t]) if sc[t] >= co else b"")
+        assert got == want, (t, got, want)
+        full += int(sc[t]) == int(rl[t])
+    assert full > n // 2
+
+
 @needs_ref
 @pytest.mark.parametrize("maxdna,maxread,fixed,clips", DP_SHAPES)
 def test_dp_matches_reference_callDP(maxdna, maxread, fixed, clips):
