@@ -521,7 +521,7 @@ def run(args, saved_stdout):
             "peak_kind": peak_kind, "algorithmic": "1 traceback byte written per DP cell the kernel computes (SURVEY 8d cells = sum refLen*readLen over the tasks it is given)",
             "ms_per_step": acc["ms_fill"] / steps,
             "note": "integer-ALU bound, not bandwidth bound: ncu ALU pipe 90.8% busy, issue slots 79.7%, top stall math_pipe_throttle "
-                    "(profiles/r01_ncu_full_v7_cfg2.txt); per-kernel times come from a single-context pass (loop R), value/e2e from the pipelined passes",
+                    "(profiles/r01_ncu_full_v8_cfg2.txt); per-kernel times come from a single-context pass (loop R), value/e2e from the pipelined passes",
             "compute": {"gcups_fill": gcups_fill, "gcups_reference_equivalent_all_dp_kernels": gcups_dp,
                         "exact_occurrence_test": {"tasks_per_step": acc.get("dp_tasks_exact", 0) / steps, "of_tasks_per_step": acc["dp_tasks"] / steps,
                                                   "ms_per_step": acc.get("ms_exact", 0.0) / steps,
