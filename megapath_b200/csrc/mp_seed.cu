@@ -162,23 +162,24 @@ __device__ __forceinline__ void occ_pair(const MpIndexView &ix, uint64_t a, uint
 //   reference; a seed that ends in phase B already knows its text position and skips SA resolution.
 //   nOcc counts the occ evaluations the reference performs for the same steps (2 per step).
 // ------------------------------------------------------------------------------------
-// 16 text bases ending just before position p (p >= 1), text[p-1-t] at bits 2t; positions before the text start read as 0
-__device__ __forceinline__ uint32_t text_window_before(const MpIndexView &ix, uint64_t p)
+// 32 text bases ending just before position p (p >= 1), text[p-1-t] at bits 2t; positions before the text start read as 0
+__device__ __forceinline__ uint64_t text_window_before(const MpIndexView &ix, uint64_t p)
 {
-    const int64_t first = (int64_t)p - 16;                          // base offset of the window start (may be negative)
+    const int64_t first = (int64_t)p - 32;                          // base offset of the window start (may be negative)
     const uint64_t f = first < 0 ? 0 : (uint64_t)first;
     const uint64_t byte0 = (f >> 2) & ~3ull;                        // 4-byte aligned
     const uint32_t *wp = (const uint32_t *)(ix.pac + byte0);
-    const uint32_t w0 = __byte_perm(__ldg(wp), 0, 0x0123), w1 = __byte_perm(__ldg(wp + 1), 0, 0x0123);   // big-endian: first base in the top bits
+    // big-endian: first base in the top bits; 48 bases cover any 32-base window that starts inside the first word
+    const uint32_t w0 = __byte_perm(__ldg(wp), 0, 0x0123), w1 = __byte_perm(__ldg(wp + 1), 0, 0x0123), w2 = __byte_perm(__ldg(wp + 2), 0, 0x0123);
     const uint32_t sh = (uint32_t)(f - byte0 * 4) * 2;
-    uint32_t t = __funnelshift_l(w1, w0, sh);                       // bases f .. f+15, base f in the top bits
+    uint64_t t = ((uint64_t)__funnelshift_l(w1, w0, sh) << 32) | __funnelshift_l(w2, w1, sh);   // bases f .. f+31, base f in the top bits
     if (first < 0) t >>= (uint32_t)(-first) * 2;                    // keep text[p-1] in the lowest group
     return t;
 }
-__device__ __forceinline__ uint32_t group_reverse(uint32_t v)       // reverse the order of the sixteen 2-bit groups
+__device__ __forceinline__ uint64_t group_reverse(uint64_t v)       // reverse the order of the thirty-two 2-bit groups
 {
-    v = __brev(v);
-    return ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+    v = __brevll(v);
+    return ((v >> 1) & 0x5555555555555555ull) | ((v & 0x5555555555555555ull) << 1);
 }
 
 // one thread per read-strand, written as a state machine: every trip of the loop performs ONE unit of work of the lane's
@@ -251,23 +252,24 @@ k_mmp(MpIndexView ix, const uint32_t *__restrict__ reads, const uint32_t *__rest
                     nextr = mp_cum(ix, c) + rb;
                     nOcc += 2; haveNext = true;
                 }
-            } else {                                                  // ST_TEXT: single suffix at text position p, up to 16 bases per trip
+            } else {                                                  // ST_TEXT: single suffix at text position p, up to 32 bases per trip
                 if (i >= len) { emit = true; finishing = true; resolved = true; }
                 else {
-                    const int m = min(16, len - i);
-                    uint32_t tw = text_window_before(ix, p), d;
+                    const int m = min(32, len - i);
+                    const uint64_t tw = text_window_before(ix, p);
+                    uint64_t d;
                     int matched;
                     if (strand) {                                     // c_t = 3 - read[i+t] against text[p-1-t]
-                        uint32_t rw = (uint32_t)read_window(rd, i, 16);
+                        uint64_t rw = read_window(rd, i, 32);
                         d = ~(rw ^ tw);                               // group == 0 where the bases agree
-                        d = (d | (d >> 1)) & 0x55555555u;
-                        matched = d ? (__ffs(d) - 1) >> 1 : 16;
+                        d = (d | (d >> 1)) & 0x5555555555555555ull;
+                        matched = d ? (__ffsll((long long)d) - 1) >> 1 : 32;
                     } else {                                          // c_t = read[len-1-i-t] against text[p-1-t]
-                        const int start = len - 1 - i - 15;
-                        uint32_t rw = start >= 0 ? (uint32_t)read_window(rd, start, 16) : ((uint32_t)read_window(rd, 0, 16) << (uint32_t)(-start * 2));
-                        d = rw ^ group_reverse(tw);                   // read[len-1-i-t] and text[p-1-t] both at group 15-t
-                        d = (d | (d >> 1)) & 0x55555555u;
-                        matched = d ? __clz(d) >> 1 : 16;
+                        const int start = len - 1 - i - 31;
+                        uint64_t rw = start >= 0 ? read_window(rd, start, 32) : (read_window(rd, 0, 32) << (uint32_t)(-start * 2));
+                        d = rw ^ group_reverse(tw);                   // read[len-1-i-t] and text[p-1-t] both at group 31-t
+                        d = (d | (d >> 1)) & 0x5555555555555555ull;
+                        matched = d ? __clzll((long long)d) >> 1 : 32;
                     }
                     int lim = m; if ((uint64_t)lim > p) lim = (int)p;
                     const bool failed = matched < lim || lim < m;     // a mismatch, or the text start reached, inside this read
