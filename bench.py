@@ -517,7 +517,11 @@ def run(args, saved_stdout):
     seed_ach = seed_bytes / (acc["ms_seed"] / 1e3) / 1e9
     traffic = ncu_traffic("k_dp_fill")
     roof = {"kernel": "k_dp_fill<5,-2,-3> (packed 16-bit DPX table fill, the kernel with the largest share of the step)",
-            "bound": "hbm", "achieved": fill_ach, "peak": peak, "unit": "GB/s", "frac": fill_ach / peak, "traffic": traffic,
+            "bound": "hbm", "achieved": fill_ach, "peak": peak, "unit": "GB/s", "frac": fill_ach / peak,
+            # DRAM bytes (read + write) of ONE k_dp_fill launch from the committed ncu --set full capture; the captured launch is the
+            # first of a step: 2^18 left-leg tasks offered, about half of them answered by the exact-occurrence test, so it fills
+            # ~4.1 G cells (= algorithmic bytes) and moves 4.55 GB of writes + 1.42 GB of write-allocate reads
+            "traffic": traffic["bytes_per_launch"] if traffic else None, "traffic_source": traffic["source"] if traffic else None,
             "peak_kind": peak_kind, "algorithmic": "1 traceback byte written per DP cell the kernel computes (SURVEY 8d cells = sum refLen*readLen over the tasks it is given)",
             "ms_per_step": acc["ms_fill"] / steps,
             "note": "integer-ALU bound, not bandwidth bound: ncu ALU pipe 90.8% busy, issue slots 79.7%, top stall math_pipe_throttle "
