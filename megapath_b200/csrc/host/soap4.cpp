@@ -22,6 +22,7 @@
 #include <ctype.h>
 #include <zlib.h>
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <map>
 #include <memory>
@@ -263,11 +264,21 @@ struct SeqReader {
 
 struct ReadBatch {
     uint32_t nReads = 0, wpq = 0, maxReadLength = 0;
-    std::vector<uint32_t> queries, lens;
-    std::vector<std::string> names, comments;
-    std::vector<uint8_t> hasComment;
-    std::unique_ptr<char[]> qualBuf; size_t qstride = 0, qcap = 0; std::vector<uint32_t> qlen;   // qualities: one fixed-stride row per read, NUL-terminated
-    const char *qual(uint32_t id) const { return qualBuf.get() + (size_t)id * qstride; }
+    std::vector<uint32_t> queries, lens;                           // what mp_batch_upload takes (read-id order, 32-read interleaved words)
+    // Everything the two parser threads write is stored mate-major -- slot(id) = (id & 1) * half + id / 2 -- so that the thread
+    // of mate 1 and the thread of mate 2 never write to the same cache line; the 2-bit packing into `queries` (whose layout
+    // interleaves 32 consecutive reads) is done afterwards by worker threads that each own whole groups of 32 reads.
+    uint32_t half = 0;
+    std::vector<std::string> names_, comments_;
+    std::vector<uint8_t> hasComment_;
+    std::vector<uint32_t> qlen_, slen_;
+    std::unique_ptr<char[]> qualBuf, seqBuf; size_t qstride = 0, qcap = 0;   // one fixed-stride row per read; qualities NUL-terminated
+    size_t slot(uint32_t id) const { return (size_t)(id & 1u) * half + (id >> 1); }
+    const std::string &name(uint32_t id) const { return names_[slot(id)]; }
+    const std::string &comment(uint32_t id) const { return comments_[slot(id)]; }
+    bool hasComment(uint32_t id) const { return hasComment_[slot(id)] != 0; }
+    const char *qual(uint32_t id) const { return qualBuf.get() + slot(id) * qstride; }
+    uint32_t qlen(uint32_t id) const { return qlen_[slot(id)]; }
 };
 
 static unsigned char g_charMap[256];
@@ -281,52 +292,97 @@ static void fill_char_map() {                                    // INDEXFillCha
 static void append_read(ReadBatch &b, uint32_t id, const char *name, size_t nameLen, const char *comment, size_t commentLen,
                         const char *seq, size_t seqLen, const char *qual, size_t qualLen)
 {
+    const size_t sl = b.slot(id);
     uint32_t len = seqLen > b.maxReadLength - 1 ? b.maxReadLength - 1 : (uint32_t)seqLen;     // QueryParser.cpp:188
-    b.lens[id] = len;
-    uint32_t *q = b.queries.data() + ((size_t)(id / 32) * 32 * b.wpq + id % 32);
-    uint32_t i = 0;
-    for (; i + 16 <= len; i += 16, q += 32) {
-        uint32_t word = 0;
-        for (int k = 0; k < 16; ++k) word |= (uint32_t)g_charMap[(unsigned char)seq[i + k]] << (k * 2);
-        *q = word;
-    }
-    if (i < len) { uint32_t word = 0; for (int k = 0; i < len; ++i, ++k) word |= (uint32_t)g_charMap[(unsigned char)seq[i]] << (k * 2); *q = word; }
+    b.slen_[sl] = len;
+    memcpy(b.seqBuf.get() + sl * b.qstride, seq, len);
     if (nameLen > 2 && name[nameLen - 2] == '/' && isdigit((unsigned char)name[nameLen - 1])) nameLen -= 2;   // trim_readno
-    b.names[id].assign(name, nameLen);
-    b.hasComment[id] = commentLen != 0;
-    if (commentLen) b.comments[id].assign(comment, commentLen); else b.comments[id].clear();
+    b.names_[sl].assign(name, nameLen);
+    b.hasComment_[sl] = commentLen != 0;
+    if (commentLen) b.comments_[sl].assign(comment, commentLen); else b.comments_[sl].clear();
     const uint32_t ql = (uint32_t)std::min<size_t>(qualLen, len);                                 // qual.substr(0, len)
-    char *qd = b.qualBuf.get() + (size_t)id * b.qstride;
-    memcpy(qd, qual, ql); qd[ql] = 0; b.qlen[id] = ql;
+    char *qd = b.qualBuf.get() + sl * b.qstride;
+    memcpy(qd, qual, ql); qd[ql] = 0; b.qlen_[sl] = ql;
 }
 
-static uint32_t load_batch(SeqReader &r1, SeqReader &r2, ReadBatch &b, uint32_t maxReads)
+// 2-bit packing of reads [first, last) into the 32-read interleaved words (appendToQueryArrays, QueryParser.cpp:184-203)
+static void pack_reads(ReadBatch &b, uint32_t first, uint32_t last)
+{
+    for (uint32_t id = first; id < last; ++id) {
+        const size_t sl = b.slot(id);
+        const uint32_t len = b.slen_[sl];
+        const char *seq = b.seqBuf.get() + sl * b.qstride;
+        b.lens[id] = len;
+        uint32_t *q = b.queries.data() + ((size_t)(id / 32) * 32 * b.wpq + id % 32);
+        uint32_t i = 0;
+        for (; i + 16 <= len; i += 16, q += 32) {
+            uint32_t word = 0;
+            for (int k = 0; k < 16; ++k) word |= (uint32_t)g_charMap[(unsigned char)seq[i + k]] << (k * 2);
+            *q = word;
+        }
+        if (i < len) { uint32_t word = 0; for (int k = 0; i < len; ++i, ++k) word |= (uint32_t)g_charMap[(unsigned char)seq[i]] << (k * 2); *q = word; }
+    }
+}
+
+static uint32_t load_batch(SeqReader &r1, SeqReader &r2, ReadBatch &b, uint32_t maxReads, unsigned packThreads = 4)
 {
     size_t words = ((size_t)maxReads + 31) / 32 * 32 * b.wpq;
     // batches are recycled (see BatchPool): storage that already has the right size is only cleared, so that a long run does
     // not page-fault half a gigabyte of fresh memory per batch
+    b.half = (maxReads + 1) / 2;
+    const size_t slots = (size_t)b.half * 2;
     b.queries.assign(words, 0); b.lens.assign(maxReads, 0);
-    if (b.names.size() != maxReads) { b.names.assign(maxReads, ""); b.comments.assign(maxReads, ""); }
-    b.hasComment.assign(maxReads, 0); b.qlen.assign(maxReads, 0);
-    if (!b.qualBuf || b.qstride != (size_t)b.maxReadLength + 1 || b.qcap != maxReads) {
-        b.qstride = (size_t)b.maxReadLength + 1; b.qcap = maxReads; b.qualBuf.reset(new char[(size_t)maxReads * b.qstride]);
+    if (b.names_.size() != slots) { b.names_.assign(slots, ""); b.comments_.assign(slots, ""); }
+    b.hasComment_.assign(slots, 0); b.qlen_.assign(slots, 0); b.slen_.assign(slots, 0);
+    if (!b.qualBuf || b.qstride != (size_t)b.maxReadLength + 1 || b.qcap != slots) {
+        b.qstride = (size_t)b.maxReadLength + 1; b.qcap = slots;
+        b.qualBuf.reset(new char[slots * b.qstride]); b.seqBuf.reset(new char[slots * b.qstride]);
     }
-    // the two files are parsed by two threads: mate 1 fills the even read ids, mate 2 the odd ones (disjoint elements and words)
-    auto half = [&b, maxReads](SeqReader &r, uint32_t first) -> uint32_t {
+    // the two files are parsed by two threads: mate 1 fills the even read ids, mate 2 the odd ones.  Packing threads follow them:
+    // each owns every nt-th group of 32 reads (the unit the word layout interleaves) and packs a group as soon as both parsers
+    // are past it.
+    std::atomic<uint32_t> prog[2]; prog[0] = 0; prog[1] = 0;        // records parsed so far, per mate
+    std::atomic<int> finished(0);
+    auto half = [&b, &prog, &finished, maxReads](SeqReader &r, uint32_t first) -> uint32_t {
         std::string nm, cm, sq, ql; uint32_t n = 0; SeqReader::View v;
-        for (uint32_t id = first; id < maxReads; id += 2, ++n) {
+        for (uint32_t id = first; id < maxReads; id += 2) {
             const int st = r.read_fast(v);
             if (st < 0) break;
-            if (st == 1) { append_read(b, id, v.name, v.nameLen, v.comment, v.commentLen, v.seq, v.seqLen, v.qual, v.seqLen); continue; }
-            if (r.read(nm, cm, sq, ql) < 0) break;
-            append_read(b, id, nm.data(), nm.size(), cm.data(), cm.size(), sq.data(), sq.size(), ql.data(), ql.size());
+            if (st == 1) append_read(b, id, v.name, v.nameLen, v.comment, v.commentLen, v.seq, v.seqLen, v.qual, v.seqLen);
+            else {
+                if (r.read(nm, cm, sq, ql) < 0) break;
+                append_read(b, id, nm.data(), nm.size(), cm.data(), cm.size(), sq.data(), sq.size(), ql.data(), ql.size());
+            }
+            ++n;
+            if ((n & 255u) == 0) prog[first].store(n, std::memory_order_release);
         }
+        prog[first].store(n, std::memory_order_release);
+        finished.fetch_add(1, std::memory_order_release);
         return n;
     };
+    const unsigned nt = std::max(1u, packThreads);
+    auto packer = [&b, &prog, &finished, nt](unsigned t) {
+        for (uint32_t g = t; ; g += nt) {
+            const uint32_t needPairs = (g + 1) * 16;                // the group holds reads 32g .. 32g+31 = pairs 16g .. 16g+15
+            uint32_t have;
+            for (;;) {
+                const bool fin = finished.load(std::memory_order_acquire) == 2;
+                have = std::min(prog[0].load(std::memory_order_acquire), prog[1].load(std::memory_order_acquire));
+                if (have >= needPairs || fin) break;
+                std::this_thread::sleep_for(std::chrono::microseconds(100));
+            }
+            if (have <= g * 16) break;                              // input ended before this group
+            pack_reads(b, g * 32, std::min(needPairs, have) * 2);
+            if (have < needPairs) break;                            // the last, partial group
+        }
+    };
+    std::vector<std::thread> packers;
+    for (unsigned t = 0; t < nt; ++t) packers.emplace_back(packer, t);
     uint32_t n2 = 0;
     std::thread t2([&] { n2 = half(r2, 1); });
     const uint32_t n1 = half(r1, 0);
     t2.join();
+    for (std::thread &t : packers) t.join();
     if (n1 != n2) { fprintf(stderr, "Error: number of sequences of pair-end files not matched.\n"); exit(1); }
     b.nReads = 2 * n1;
     return b.nReads;
@@ -375,7 +431,7 @@ static void seq_and_qual(std::string &out, const ReadBatch &b, uint32_t id)
         const uint32_t m = len - i < 16 ? len - i : 16;
         for (uint32_t k = 0; k < m; ++k, word >>= 2) w[i + k] = "ACGT"[word & 3];
     }
-    out += "\n+\n"; out.append(b.qual(id), b.qlen[id]); out.push_back('\n');
+    out += "\n+\n"; out.append(b.qual(id), b.qlen(id)); out.push_back('\n');
 }
 
 static inline void append_int(std::string &s, long long v)
@@ -388,8 +444,8 @@ static inline void append_int(std::string &s, long long v)
 static void header_line(std::string &ret, const ReadBatch &b, uint32_t id, const Annotation &ann, std::vector<std::pair<int, int>> &chrHits,
                         int bestScore, double top, bool ignoreComments)
 {
-    const std::string *comment = (!ignoreComments && b.hasComment[id]) ? &b.comments[id] : nullptr;
-    ret += "@"; ret += b.names[id];
+    const std::string *comment = (!ignoreComments && b.hasComment(id)) ? &b.comment(id) : nullptr;
+    ret += "@"; ret += b.name(id);
     if (comment && *comment == "IGNORE") { ret += "\tIGNORE\n"; return; }
     std::sort(chrHits.begin(), chrHits.end());
     std::vector<HeaderHit> v;
@@ -476,7 +532,7 @@ static void output_pair(OutCtx &o, std::string &fq, const mp_pair_result *first,
     PairAln &B = v[best];
     if (B.a1 == NOT_ALIGNED && B.a2 == NOT_ALIGNED) return;
     std::vector<uint8_t> q1, q2; unpack_read(b, r1, q1); unpack_read(b, r2, q2);
-    ReadView rv1 = { &b.names[r1], q1.data(), b.qual(r1), readlen1 }, rv2 = { &b.names[r2], q2.data(), b.qual(r2), readlen2 };
+    ReadView rv1 = { &b.name(r1), q1.data(), b.qual(r1), readlen1 }, rv2 = { &b.name(r2), q2.data(), b.qual(r2), readlen2 };
     const int num = (int)v.size();
     uint64_t tp_1 = 0, tp_2 = 0; uint32_t chr_1 = 0, chr_2 = 0;
     long long boundTrim1 = 0, boundTrim2 = 0; std::string newCigar1, newCigar2, cigarStr1, cigarStr2;
@@ -598,7 +654,7 @@ static void output_unpaired(OutCtx &o, std::string &fq, uint32_t r1, std::vector
     if (!o.bam) return;
     const int readlen[2] = { (int)b.lens[ids[0]], (int)b.lens[ids[1]] };
     std::vector<uint8_t> q[2]; unpack_read(b, ids[0], q[0]); unpack_read(b, ids[1], q[1]);
-    ReadView rv[2] = { { &b.names[ids[0]], q[0].data(), b.qual(ids[0]), readlen[0] }, { &b.names[ids[1]], q[1].data(), b.qual(ids[1]), readlen[1] } };
+    ReadView rv[2] = { { &b.name(ids[0]), q[0].data(), b.qual(ids[0]), readlen[0] }, { &b.name(ids[1]), q[1].data(), b.qual(ids[1]), readlen[1] } };
     int bestIdx[2] = { -1, -1 }, bestScore[2] = { 0, 0 }, bestScoreNum[2] = { 0, 0 }, x1_t1[2] = { 0, 0 }, x1_t2[2] = { 0, 0 }, secondBestNum[2];
     uint64_t tp[2] = { 0, 0 }; uint32_t chr[2] = { 0, 0 }; long long boundTrim[2] = { 0, 0 }; int deletedEnd[2] = { 0, 0 }, mapq[2] = { 0, 0 };
     std::string newCigar[2], cigarStr[2]; MisInfo mi[2];
@@ -680,7 +736,7 @@ int main(int argc, char **argv)
         ReadBatch b; b.maxReadLength = maxLen; b.wpq = (maxLen + 15) / 16;
         for (;;) {
             const double t1 = now_s();
-            uint32_t n = load_batch(r1, r2, b, 12 * 8192 * 128 / 6);
+            uint32_t n = load_batch(r1, r2, b, 12 * 8192 * 128 / 6, argc >= 6 ? (unsigned)atoi(argv[5]) : 4u);
             if (n == 0) break;
             total += n; for (uint32_t i = 0; i < n; i += 1000) sum += b.lens[i] + b.queries[i] + (unsigned char)b.qual(i)[0];
             fprintf(stderr, "batch of %u reads in %.3f s\n", n, now_s() - t1);
@@ -816,7 +872,7 @@ int main(int argc, char **argv)
             { std::lock_guard<std::mutex> lk(mu); if (!batchPool.empty()) { j->b = batchPool.back(); batchPool.pop_back(); } }
             if (!j->b) j->b = new ReadBatch;
             j->b->maxReadLength = (uint32_t)maxLen; j->b->wpq = ((uint32_t)maxLen + 15) / 16;
-            if (load_batch(r1, r2, *j->b, maxNumQueries) == 0) { delete j->b; delete j; break; }
+            if (load_batch(r1, r2, *j->b, maxNumQueries, (unsigned)std::min(8, std::max(1, opt.numCpuThreads))) == 0) { delete j->b; delete j; break; }
             j->seq = seq++; j->nReads = j->b->nReads;
             double t = now_s(); j->loadSeconds = t - last;
             if (!detected) {                                       // first batch: read-length detection and insert_low clamp (SOAP4.cpp:458-474)
