@@ -71,6 +71,16 @@ __global__ void k_right_tasks(const mp_candidate *__restrict__ cands, uint32_t n
 
 struct PairWork { uint32_t ok; uint32_t cigLen[2]; };
 
+// A leg whose score equals its read length matched every base: its pattern is readLen x 'M' and its CIGAR "<readLen>M"
+// (the one exception, an alignment that starts in row 0, carries three more pattern bytes and takes the general path).
+__device__ __forceinline__ bool all_match_leg(const MpDpTask &t, const MpDpOut &o) { return o.score == (int)t.readLen && o.patLen == t.readLen && t.readLen > 0; }
+__device__ __forceinline__ CigStats all_match_cigar(uint32_t readLen, char *out)
+{
+    CigStats st; st.nI = st.nD = st.nS = st.gapPenalty = 0; st.textLen = ndigits((int)readLen) + 1;
+    if (out) { int v = (int)readLen; out[st.textLen - 1] = 'M'; for (int d = st.textLen - 2; d >= 0; --d) { out[d] = (char)('0' + v % 10); v /= 10; } }
+    return st;
+}
+
 __global__ void k_assemble_measure(uint32_t n, const MpDpTask *__restrict__ lt, const MpDpOut *__restrict__ lo,
                                    const MpDpTask *__restrict__ rt, const MpDpOut *__restrict__ ro,
                                    const uint8_t *__restrict__ lpat, const uint8_t *__restrict__ rpat, uint32_t patStride,
@@ -82,8 +92,8 @@ __global__ void k_assemble_measure(uint32_t n, const MpDpTask *__restrict__ lt, 
     bool ok = lo[c].score >= lt[c].cutoff && rt[c].valid && ro[c].score >= rt[c].cutoff;
     uint32_t bytes = 0;
     if (ok) {
-        CigStats a = cigar_encode(lpat + (size_t)c * patStride, open, ext, nullptr, 0);
-        CigStats b = cigar_encode(rpat + (size_t)c * patStride, open, ext, nullptr, 0);
+        CigStats a = all_match_leg(lt[c], lo[c]) ? all_match_cigar(lt[c].readLen, nullptr) : cigar_encode(lpat + (size_t)c * patStride, open, ext, nullptr, 0);
+        CigStats b = all_match_leg(rt[c], ro[c]) ? all_match_cigar(rt[c].readLen, nullptr) : cigar_encode(rpat + (size_t)c * patStride, open, ext, nullptr, 0);
         bytes = a.textLen + 1 + b.textLen + 1;
         leftLen[c] = a.textLen;                       // the write pass encodes each leg once, backwards from its known length
     }
@@ -110,7 +120,7 @@ __global__ void k_assemble_write(uint32_t n, const mp_candidate *__restrict__ ca
     const int lengths_i = rt[c].readLen;                // batch->lengths[i] was overwritten by packRight
     const int textLen[2] = { (int)leftLen[c], (int)(cigOff[c + 1] - cigOff[c]) - (int)leftLen[c] - 2 };
     for (int s = 0; s < 2; ++s) {
-        CigStats m = cigar_encode(pat[s], A.open, A.ext, cig + off, textLen[s]);
+        CigStats m = all_match_leg(*tk[s], *ou[s]) ? all_match_cigar(tk[s]->readLen, cig + off) : cigar_encode(pat[s], A.open, A.ext, cig + off, textLen[s]);
         cig[off + m.textLen] = 0;
         cigPos[s] = cigBase + off;
         off += m.textLen + 1;
