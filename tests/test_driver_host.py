@@ -59,3 +59,27 @@ def test_fast_path_large_and_gz(tmp_path):
     with gzip.open(g, "wb", compresslevel=1) as f:
         f.write(data)
     assert parse(str(g), False) == want
+
+
+@pytest.mark.parametrize("size", [0, 5, 70000, 1 << 20])
+def test_bgzf_chunks_concatenate_to_a_valid_stream(tmp_path, size):
+    """BAM records are compressed into BGZF blocks by the formatting threads, chunk by chunk; the concatenation (after the
+    buffered header bytes, before the EOF block) must decompress to the original bytes and every block must be a proper BGZF member"""
+    rng = np.random.default_rng(size)
+    data = bytes(rng.integers(0, 7, size).astype(np.uint8).tolist())
+    src, dst = tmp_path / "in.bin", tmp_path / "out.bgzf"
+    src.write_bytes(data)
+    subprocess.run([EXE, "__bgzf", str(src), str(dst)], check=True, timeout=120)
+    raw = dst.read_bytes()
+    assert gzip.decompress(raw) == data
+    # walk the members: gzip magic, FEXTRA with the BC subfield, BSIZE consistent, ISIZE <= 0xff00; the last one is the 28-byte EOF marker
+    at, members = 0, 0
+    while at < len(raw):
+        assert raw[at:at + 4] == b"\x1f\x8b\x08\x04" and raw[at + 12:at + 16] == b"BC\x02\x00"
+        bsize = int.from_bytes(raw[at + 16:at + 18], "little") + 1
+        isize = int.from_bytes(raw[at + bsize - 4:at + bsize], "little")
+        assert isize <= 0xff00
+        at += bsize
+        members += 1
+    assert at == len(raw) and raw[-28:] == bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+    assert members >= 2 if size else members == 1
