@@ -15,12 +15,14 @@
 // (anti-diagonal wavefront); the right-most H / I of a lane's strip travel to lane l+1 by shuffle, the
 // reference rows come from shared memory.  Every cell leaves one traceback byte
 //    (H-Hdiag-mm)*42 + (H-Hleft-open)*3 + g          g 0 = D==H, 1 = neither, 2 = raised by the clip floor
-// (the information the reference keeps, CPU_DP.cpp:183, 529-533) in a step-major table in HBM:
-// a warp's stores of one step are one contiguous 128-byte (+32-byte) segment per task.
+// (the information the reference keeps, CPU_DP.cpp:183, 529-533) in a step-major table in HBM (layout at cell_offset):
+// a warp's stores of one step are one full 128-byte line per task.
 // The answer cell (first strict maximum in row-major order, tie count, CPU_DP.cpp:545-590) is kept per
 // column in packed registers and reduced across the warp at the end.
 // k_dp_tb<K>: one thread per task walks its own table (GPUBacktrack, CPU_DP.cpp:622-786) -- thousands of
 // independent walks in flight hide the dependent-load latency that a single walking lane cannot.
+// k_dp_exact<K>: runs first; tasks whose read occurs unchanged in its window get their (provably identical) answer
+// without the DP, the others are compacted for the two kernels above.
 #include "mp_context.h"
 #include <cub/device/device_scan.cuh>
 #include <algorithm>

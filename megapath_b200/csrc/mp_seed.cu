@@ -5,11 +5,11 @@
 //   pairEndMerge / findRevStart / mergeAndPairPairedEnd         DV-DPfunctions.cpp:1844-2119
 //
 // Kernels (DESIGN.md "Seeding"):
-//   k_mmp      4 lanes per read-strand; every backward-search step fetches the two 64-byte
-//              occ blocks of (l, r+1) as one 16-byte load per lane and reduces the partial
-//              ranks with two quad shuffles.  Quads pull read-strands from a work counter.
-//   k_expand   one thread per (seed, k) suffix-array hit: LF walk to the next sampled SA
-//              index, text position, SeedAlign record written into its read's segment.
+//   k_mmp      one thread per read-strand, written as a state machine (filter probes + LKT jump | one backward-search
+//              step | up to 32 text bases per trip once the range is a single suffix); a K-mer presence filter rules out
+//              starts that cannot give a seed; seed slots are allocated with one atomic per warp.
+//   k_expand   one thread per (seed, k) suffix-array hit that k_mmp did not resolve itself: SA lookup (dense 32-bit
+//              array, or LF walk to the next sample), text position, hit record written into its read's segment.
 //   k_merge    one thread per read: sort hits by (strand, position), chain within indelFuzz,
 //              covered-length union, uniqueness / length filters -> SeedPos entries.
 //   k_pair     one thread per pair and orientation: window join -> CandidateInfo.
