@@ -172,3 +172,50 @@ def test_seeds_candidates_dp_match_reference_dumps(workdir, small_ref, name, rle
 def ref_detected_len(lens):
     """GetReadLength (QueryParser.cpp:2253-2277): maximum over the first 999999 sampled reads."""
     return int(lens[:999999].max())
+
+
+def closed_form_for_exact_occurrence(ref, read, cutoff):
+    """What k_dp_exact writes (megapath_b200/csrc/mp_dp.cu) when `read` occurs unchanged in `ref`; None otherwise."""
+    N, L = len(ref), len(read)
+    if L == 0 or N < L or cutoff > L or cutoff <= 0:
+        return None
+    rb, qb = ref.tobytes(), read.tobytes()
+    occ, first, at = 0, -1, rb.find(qb)
+    while at >= 0:
+        occ += 1
+        if first < 0:
+            first = at
+        at = rb.find(qb, at + 1)
+    if occ == 0:
+        return None
+    pat = b"M" * L + (b"SV\x00" if first == 0 else b"")
+    return (L, first, min(occ, 255), pat)
+
+
+def test_exact_occurrence_closed_form_equals_the_dp():
+    """The theorem behind k_dp_exact, checked on thousands of tasks against the DP restatement (which the tests above pin to
+    the reference's callDP): low-complexity alphabets give windows with many occurrences and near-occurrences."""
+    rng = np.random.default_rng(20260)
+    checked = multi = at_start = 0
+    for trial in range(4000):
+        alpha = int(rng.integers(1, 5))
+        L = int(rng.integers(30, 153))
+        N = int(rng.integers(L, 221))
+        read = rng.integers(0, alpha, size=L).astype(np.uint8)
+        ref = rng.integers(0, alpha, size=N).astype(np.uint8)
+        if rng.random() < 0.8:                                    # plant one occurrence (others may exist by chance / periodicity)
+            o = int(rng.integers(0, N - L + 1)) if rng.random() < 0.8 else 0
+            ref[o:o + L] = read
+        clips = [(130, 130), (0, 0), (10, 20), (5, 0), (0, 130)][trial % 5]
+        cutoff = po.dp_cutoff(L)
+        want = closed_form_for_exact_occurrence(ref, read, cutoff)
+        if want is None:
+            continue
+        got = po.dp(ref, read, clips[0], clips[1], -2, -3, cutoff)
+        got = (got[0], got[1], got[2], got[3])
+        # pattern_bytes (the comparison form used by the other tests) ends at the first NUL: compare in that form
+        assert got == (want[0], want[1], want[2], want[3].split(b"\x00")[0] if isinstance(got[3], bytes) and b"\x00" not in got[3] else want[3]), (trial, clips, got, want)
+        checked += 1
+        multi += want[2] > 1
+        at_start += want[1] == 0
+    assert checked > 2500 and multi > 300 and at_start > 300
