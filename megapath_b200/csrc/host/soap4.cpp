@@ -744,6 +744,19 @@ int main(int argc, char **argv)
         fprintf(stderr, "%llu reads in %.3f s (checksum %llu)\n", (unsigned long long)total, now_s() - t0, (unsigned long long)sum);
         return 0;
     }
+    if (argc >= 6 && !strcmp(argv[1], "__pack")) {           // hidden: batch loader output to a file (no GPU): __pack r1 r2 maxReadLength out [threads]
+        fill_char_map();
+        SeqReader r1, r2; if (!r1.open(argv[2]) || !r2.open(argv[3])) return 1;
+        ReadBatch b; b.maxReadLength = (uint32_t)atoi(argv[4]); b.wpq = (b.maxReadLength + 15) / 16;
+        const uint32_t n = load_batch(r1, r2, b, 12 * 8192 * 128 / 6, argc >= 7 ? (unsigned)atoi(argv[6]) : 3u);
+        FILE *o = fopen(argv[5], "wb"); if (!o) return 1;
+        const uint32_t hdr[2] = { n, b.wpq };
+        fwrite(hdr, 4, 2, o); fwrite(b.lens.data(), 4, n, o);
+        fwrite(b.queries.data(), 4, ((size_t)n + 31) / 32 * 32 * b.wpq, o);
+        for (uint32_t id = 0; id < n; ++id) fprintf(o, "%s|%s|%.*s\n", b.name(id).c_str(), b.hasComment(id) ? b.comment(id).c_str() : "", (int)b.qlen(id), b.qual(id));
+        fclose(o);
+        return 0;
+    }
     if (argc >= 4 && !strcmp(argv[1], "__bgzf")) {           // hidden: file -> BGZF blocks compressed in two chunks + EOF block (no GPU)
         FILE *in = fopen(argv[2], "rb"); if (!in) return 1;
         std::vector<uint8_t> data; uint8_t tmp[65536]; size_t n;

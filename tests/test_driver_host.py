@@ -83,3 +83,46 @@ def test_bgzf_chunks_concatenate_to_a_valid_stream(tmp_path, size):
         members += 1
     assert at == len(raw) and raw[-28:] == bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
     assert members >= 2 if size else members == 1
+
+
+@pytest.mark.parametrize("threads", [1, 3, 8])
+def test_batch_loader_layout(tmp_path, threads):
+    """The driver's batch loader (two parser threads writing mate-major storage, packer threads following them) must produce
+    the buffers appendToQueryArrays would (QueryParser.cpp:184-203; megapath_b200.pack_queries is the host mirror the GPU
+    tests feed the library with): read lengths truncated to maxReadLength-1, N -> 2, lower case, names without /1 /2,
+    comments, qualities cut to the kept length, and a last partial group of 32."""
+    import megapath_b200 as mp
+    rng = np.random.default_rng(threads)
+    npairs, maxlen = 1000 + 13, 101
+    lut = np.zeros(256, np.uint8)
+    for ch, v in zip(b"ACGTNacgtn", [0, 1, 2, 3, 2, 0, 1, 2, 3, 2]):
+        lut[ch] = v
+    recs = {1: [], 2: []}
+    want_codes = np.zeros((2 * npairs, maxlen - 1), np.uint8)
+    want_lens = np.zeros(2 * npairs, np.uint32)
+    meta = []
+    for p in range(npairs):
+        for mate in (1, 2):
+            L = int(rng.integers(20, 131))
+            seq = bytes(rng.choice(np.frombuffer(b"ACGTNacgt", dtype=np.uint8), L).tolist())
+            qual = bytes(rng.integers(33, 74, L).astype(np.uint8).tolist()).replace(b"@", b"A")
+            comment = b"SCORE:7;3,chr1;" if p % 11 == 0 else b""
+            recs[mate].append(b"@r%d/%d%s\n%s\n+\n%s\n" % (p, mate, (b" " + comment) if comment else b"", seq, qual))
+            rid = 2 * p + mate - 1
+            keep = min(L, maxlen - 1)
+            want_codes[rid, :keep] = lut[np.frombuffer(seq[:keep], dtype=np.uint8)]
+            want_lens[rid] = keep
+            meta.append(b"r%d|%s|%s" % (p, comment, qual[:keep]))
+    f1, f2, out = tmp_path / "a_1.fq", tmp_path / "a_2.fq", tmp_path / "pack.bin"
+    f1.write_bytes(b"".join(recs[1])); f2.write_bytes(b"".join(recs[2]))
+    subprocess.run([EXE, "__pack", str(f1), str(f2), str(maxlen), str(out), str(threads)], check=True, timeout=120)
+    raw = out.read_bytes()
+    n, wpq = np.frombuffer(raw[:8], dtype=np.uint32)
+    assert n == 2 * npairs
+    lens = np.frombuffer(raw[8:8 + 4 * n], dtype=np.uint32)
+    assert (lens == want_lens).all()
+    nwords = (n + 31) // 32 * 32 * wpq
+    words = np.frombuffer(raw[8 + 4 * n:8 + 4 * n + 4 * nwords], dtype=np.uint32)
+    want_words, want_wpq = mp.pack_queries(want_codes, want_lens, maxlen)
+    assert wpq == want_wpq and (words == want_words).all()
+    assert raw[8 + 4 * n + 4 * nwords:].split(b"\n")[:-1] == meta
