@@ -726,6 +726,8 @@ static void output_unpaired(OutCtx &o, std::string &fq, uint32_t r1, std::vector
 // ------------------------------------------------------------------------------------------------
 int main(int argc, char **argv)
 {
+#ifdef MP_TEST_HOOKS
+    // test-helper build only (bin/soap4_hosttest, tests/test_driver_host.py; no GPU needed): the shipped binary has none of these
     // hidden self-check used by tests/test_driver_host.py (no GPU needed): dump the records of a read file as the batch loader sees
     // them, through the zero-copy fast path (default) or through the kseq-style parser only ("generic")
     if (argc >= 5 && !strcmp(argv[1], "__load")) {           // hidden: time the batch loader alone (no GPU): __load r1 r2 maxReadLength
@@ -786,6 +788,7 @@ int main(int argc, char **argv)
         }
         return 0;
     }
+#endif
     Options opt;
     if (!parse_args(argc, argv, opt)) return 1;
     const double t0 = now_s();

@@ -39,6 +39,7 @@ __global__ void k_left_tasks(const mp_candidate *__restrict__ cands, uint32_t n,
     if (start + dnaLen > fullLen) dnaLen = (uint32_t)(fullLen - start);
     MpDpTask t; t.refStart = start; t.refLen = dnaLen; t.readID = ci.readIDLeft; t.readLen = (uint16_t)readLength;
     t.strand = (uint8_t)strandLeft; t.valid = 1; t.cutoff = dp_cutoff(readLength);
+    t.diag = (int16_t)min((uint64_t)ci.pos[0] - start, (uint64_t)0x7fff); t.pad_ = 0;     // the seed's diagonal inside the window (hint only)
     tasks[c] = t;
     account_work((unsigned long long)dnaLen * readLength, 1, counters);
 }
@@ -64,6 +65,7 @@ __global__ void k_right_tasks(const mp_candidate *__restrict__ cands, uint32_t n
         if (bounded < dnaLen) dnaLen = (uint32_t)bounded;
         t.refStart = start; t.refLen = dnaLen; t.readID = readIDRight; t.readLen = (uint16_t)readLength;
         t.strand = (uint8_t)strandRight; t.valid = 1; t.cutoff = dp_cutoff(readLength);
+        t.diag = (int16_t)min((uint64_t)ci.pos[1] - start, (uint64_t)0x7fff);
     }
     tasks[c] = t;
     account_work(t.valid ? (unsigned long long)t.refLen * t.readLen : 0ull, t.valid ? 1ull : 0ull, counters);
@@ -292,9 +294,17 @@ extern "C" int mp_init(int device, mp_context **pctx)
     }
     mp_context *ctx = new mp_context;
     memset(&ctx->ix, 0, sizeof ctx->ix);
+    for (int i = 0; i < 8; ++i) ctx->ev[i] = nullptr;
     ctx->device = device;
-    MP_CUDA(cudaStreamCreate(&ctx->stream));
-    for (int i = 0; i < 8; ++i) MP_CUDA(cudaEventCreate(&ctx->ev[i]));
+    cudaError_t ce = cudaStreamCreate(&ctx->stream);
+    for (int i = 0; i < 8 && ce == cudaSuccess; ++i) ce = cudaEventCreate(&ctx->ev[i]);
+    if (ce != cudaSuccess) {
+        mp_set_error("mp_init: CUDA error %s: %s", cudaGetErrorName(ce), cudaGetErrorString(ce));
+        for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+        if (ctx->stream) cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return MP_ERR_CUDA;
+    }
     *pctx = ctx;
     return 0;
 }
@@ -321,7 +331,7 @@ extern "C" void mp_destroy(mp_context *ctx)
                        &ctx->dSeedPos, &ctx->dNPos, &ctx->dNNeg, &ctx->dCandCount, &ctx->dCandStart, &ctx->dCands, &ctx->dScanTmp,
                        &ctx->dTasks, &ctx->dRefSeq, &ctx->dReadSeq, &ctx->dTable, &ctx->dFill, &ctx->dPattern, &ctx->dDpOut,
                        &ctx->dLT, &ctx->dRT, &ctx->dLO, &ctx->dRO, &ctx->dLP, &ctx->dRP, &ctx->dOk, &ctx->dBytes, &ctx->dIdx, &ctx->dOff,
-                       &ctx->dRes, &ctx->dCig };
+                       &ctx->dRes, &ctx->dCig, &ctx->dExFlag, &ctx->dExPos, &ctx->dExIdx, &ctx->dAligned, &ctx->dGather };
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->stream);
@@ -353,6 +363,10 @@ extern "C" int mp_seed_pairs(mp_context *ctx, const mp_align_params *params)
     if (!ctx || !params) { mp_set_error("mp_seed_pairs: null argument"); return MP_ERR_ARG; }
     if (!ctx->hasIndex || !ctx->hasBatch) { mp_set_error("mp_seed_pairs: index and batch must be loaded first"); return MP_ERR_STATE; }
     if (params->peStrandLeftLeg != 1 || params->peStrandRightLeg != 2) { mp_set_error("only StrandArrangement +/- is supported"); return MP_ERR_ARG; }
+    if ((int64_t)ctx->maxLenBatch >= (int64_t)params->maxReadLength) {          // the reference truncates reads to -L - 1 (QueryParser.cpp:188)
+        mp_set_error("the batch holds a read of %u bases but maxReadLength is %d (reads must be shorter)", ctx->maxLenBatch, params->maxReadLength);
+        return MP_ERR_ARG;
+    }
     MP_CUDA(cudaSetDevice(ctx->device));
     return mps_seed_pairs(ctx, params);
 }
@@ -398,6 +412,11 @@ extern "C" int mp_dp_batch(mp_context *ctx,
         mp_set_error("mp_dp_batch: score parameters outside the supported range (CPU_DP.cpp:199-208)"); return MP_ERR_ARG;
     }
     if (n == 0) return 0;
+    for (uint32_t t = 0; t < n; ++t)
+        if (DNALengths[t] > maxDNALength || readLengths[t] > maxReadLength) {
+            mp_set_error("mp_dp_batch: task %u has lengths (%u, %u) above the stated maxima (%u, %u)", t, DNALengths[t], readLengths[t], maxDNALength, maxReadLength);
+            return MP_ERR_ARG;
+        }
     MP_CUDA(cudaSetDevice(ctx->device));
     const uint32_t wDNA = (maxDNALength + 15) >> 4, wRead = (maxReadLength + 15) >> 4;
     // un-interleave into one byte per base (host side of the seam; the kernels take bytes)
@@ -443,6 +462,10 @@ extern "C" int mp_align_pairs(mp_context *ctx, const mp_align_params *params, mp
     if (params->matchScore != 1 || params->extendGapScore != -1 || params->mismatchScore > -1 || params->mismatchScore < params->openGapScore * 2 ||
         params->mismatchScore < -4 || params->openGapScore < -6 || params->openGapScore >= -1) {
         mp_set_error("mp_align_pairs: score parameters outside the supported range (CPU_DP.cpp:199-208)"); return MP_ERR_ARG;
+    }
+    if ((int64_t)ctx->maxLenBatch >= (int64_t)params->maxReadLength) {
+        mp_set_error("the batch holds a read of %u bases but maxReadLength is %d (reads must be shorter)", ctx->maxLenBatch, params->maxReadLength);
+        return MP_ERR_ARG;
     }
     MP_CUDA(cudaSetDevice(ctx->device));
     const double wall0 = mp_now_ms();

@@ -89,6 +89,8 @@ struct MpDpTask {          // one semi-global DP instance
     uint8_t  strand;       // 1 '+', 2 '-' (read is reverse-complemented)
     uint8_t  valid;
     int32_t  cutoff;
+    int16_t  diag;         // expected window offset of the read's first base (the seed's diagonal), -1 = unknown; only a hint:
+    uint16_t pad_;         // k_dp_fill derives a lower bound of the best score from it, results do not depend on it
 };
 struct MpDpOut {
     int32_t score; uint32_t hitLoc; uint32_t count; uint32_t patLen;
@@ -124,7 +126,7 @@ struct mp_context {
     std::vector<uint64_t> hSa; uint64_t saInterval = 16;   // kept for mp_index_save
     // batch
     bool hasBatch = false, seeded = false;
-    uint32_t nReads = 0, wpq = 0;
+    uint32_t nReads = 0, wpq = 0, maxLenBatch = 0;       // maxLenBatch: longest read of the uploaded batch
     DevBuf dReadsIl, dReads, dLens;
     // seeding
     DevBuf dCounters;                 // u64[16]: 0 seeds, 1 hit stubs, 2 occ, 3 sa, 4 lkt, 5 lf, 6 work-queue

@@ -30,14 +30,26 @@
 
 #define DP_BIAS   0x4000
 #define DP_BIAS2  0x40004000u
-#define DP_ONE2   0x00010001u
 #define DP_NEG2   0x20C020C0u      /* (bias - 8000) in both halves: "minus infinity" that never underflows */
+#define DP_C      0x5000           /* flag arithmetic: C - hf stays positive, 2C = 0 mod 256 */
+#define DP_C2     0x50005000u
+#define DP_CM1_2  0x4FFF4FFFu
 
 __device__ __forceinline__ int h0_value(int j, int clipLt, int open)       // row 0 (CPU_DP.cpp:397-429)
 {
     return j <= clipLt ? 0 : open - (j - clipLt - 1);
 }
 __device__ __forceinline__ uint32_t pack2(int v) { return ((uint32_t)v & 0xffffu) * 0x00010001u; }
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel)); return d;
+}
+// x * m + y with a multiplier the compiler cannot see through: keeps the add on the FMA pipe (IMAD) instead of the ALU pipe,
+// which carries every min/max/permute of the recurrence and is the pipe that limits the kernel
+__device__ __forceinline__ uint32_t fma_add(uint32_t x, uint32_t m, uint32_t y)
+{
+    uint32_t d; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(m), "r"(y)); return d;
+}
 
 struct FillOut { int32_t score; uint32_t row, col, cnt; };
 
@@ -58,19 +70,35 @@ __device__ __forceinline__ size_t cell_offset(int r, int c, int S)
     const int b = ((t - 1) & 3) * REM + (k - 4 * WORDS);
     return (size_t)S * WB + (size_t)((t - 1) >> 2) * (REM * 256) + (size_t)(b >> 2) * 256 + lane * 4 + (b & 3);
 }
-// third digit of a trace byte -> the reference's flag (0 = raised by the clip floor, 1 = D==H, 2 = otherwise; CPU_DP.cpp:529-533)
-__device__ __forceinline__ int trace_flag(uint32_t cell) { const int g = (int)(cell % 3); return g == 2 ? 0 : g + 1; }
-// MM / OPEN: mismatch score and gap-open score as compile-time constants (0 = take them from P at run time), so that the
-// packed constants become immediates of the DPX / IADD3 instructions
+// Trace byte of a cell: (4*H - zd - zr) mod 256 with zd = 1 unless D == H, zr = 1 where the clip floor raised the cell (then zd = 1 too).
+//   bits 7..2 (after rounding up): H mod 64 -- neighbouring cells differ by less than 8, so every difference GPUBacktrack looks at
+//                                  (H - Hdiag, H - Hleft, H - Hup; CPU_DP.cpp:183, 529-533 keeps the first two as 4-bit deltas) is exact
+//   bits 1..0 = (-(zd + zr)) & 3 : 0 = D == H, 3 = neither, 2 = raised by the clip floor
+__device__ __forceinline__ int trace_h(uint32_t cell) { return (int)(((cell + 3u) >> 2) & 63u); }
+// -> the reference's flag (0 = raised by the clip floor, 1 = D == H, 2 = otherwise; CPU_DP.cpp:529-533)
+__device__ __forceinline__ int trace_flag(uint32_t cell) { const uint32_t g = cell & 3u; return g == 0 ? 1 : g == 3 ? 2 : 0; }
+__device__ __forceinline__ int trace_diff(int a, int b) { return ((a - b + 32) & 63) - 32; }      // a - b for values known mod 64
+
+// k_dp_fill<K, MM, OPEN>: MM / OPEN = mismatch and gap-open score as compile-time constants (0 = take them from P at run time).
+//
+// Scores are carried times four with a +0x4000 bias in unsigned 16-bit halves (task A low, task B high): the two free low bits of
+// every H take the cell's two flags, so a trace byte is one add away from H.  Per cell pair the ALU pipe sees
+//   PRMT (substitution penalty of both tasks from the row's 8-byte table, selector = the column's two read bases),
+//   VIADDMNMX x2 (D, I), VIMNMX3 (H), VIMNMX (clip floor), VIADDMNMX x2 (the two flags), PRMT (byte packing, one per cell)
+// and the FMA pipe the plain adds (IMAD).  The answer cell (first strict maximum in row-major order + tie count, CPU_DP.cpp:545-590)
+// is NOT tracked per cell: a lane compares the maximum of its K cells of a step with a threshold and only cells that reach it
+// take the exact (scalar, per-lane) bookkeeping path.  The threshold starts at max(cutoff, LB) where LB is the score of the ungapped
+// path along the task's hinted diagonal -- a true lower bound of the best score, so no cell that can be the answer or tie with
+// it is skipped -- and follows the lane's own best.
 template <int K, int MM, int OPEN>
 __global__ void __launch_bounds__(128)
 k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLens, uint32_t refStride,
           const uint8_t *__restrict__ readSeq, const uint32_t *__restrict__ readLens, uint32_t readStride,
-          const int32_t *__restrict__ cutoffs, uint32_t taskBase, uint32_t nTasks, MpDpParams P,
+          const int32_t *__restrict__ cutoffs, const int16_t *__restrict__ hints, uint32_t taskBase, uint32_t nTasks, MpDpParams P,
           uint8_t *__restrict__ tables, size_t tableStride, int S, FillOut *__restrict__ fill,
-          const uint32_t *__restrict__ active, const uint32_t *__restrict__ nActive)
+          const uint32_t *__restrict__ active, const uint32_t *__restrict__ nActive, uint32_t one)
 {
-    extern __shared__ uint32_t refShared[];
+    extern __shared__ uint2 refShared[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t pairId = blockIdx.x * 4 + wib;
     const uint32_t lA = pairId * 2, lB = lA + 1;             // slots inside this launch: tables are indexed by slot
@@ -87,31 +115,98 @@ k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLe
     if (!okA) { NA = 0; LA = 0; }
     if (!okB) { NB = 0; LB = 0; }
     const int maxN = max(NA, NB), maxL = max(LA, LB);
-    uint32_t *refS = refShared + (size_t)wib * S;
+    const uint32_t PEN = (uint32_t)(4 * (1 - mm));              // 4 * (match - mismatch) < 0x80
+    // FOLD (compile-time scores with |open| >= |mismatch|): the row tables hold the non-negative ADDEND (open-form diagonal + addend =
+    // diagonal + substitution score), so one H form per column serves the diagonal, D and I.  Otherwise they hold the penalty.
+    constexpr bool FOLD = MM != 0 && OPEN != 0 && (-4 * OPEN + 4 >= 4 * (1 - MM));
+    const uint32_t O4v = (uint32_t)(-4 * open);
+    const uint32_t TMATCH = FOLD ? O4v + 4u : 0u, TMIS = FOLD ? O4v + 4u - PEN : PEN;
+    // ---- reference rows -> substitution tables: bytes 0..3 = penalty of task A's row against read base 0..3, bytes 4..7 task B;
+    //      rows a task does not have mismatch everything ----
+    uint2 *refS = refShared + (size_t)wib * S;
     {
         const uint8_t *fa = refSeq + (size_t)tA * refStride, *fb = refSeq + (size_t)tB * refStride;
+        const uint32_t all = TMIS * 0x01010101u;
         for (int r = lane; r < maxN; r += 32) {
-            uint32_t a = r < NA ? fa[r] : 4u, b = r < NB ? fb[r] : 4u;
-            refS[r] = a | (b << 16);
+            const uint32_t a = r < NA ? fa[r] : 4u, b = r < NB ? fb[r] : 4u;
+            refS[r] = make_uint2(a < 4u ? (all & ~(0xFFu << (8 * a))) | (TMATCH << (8 * a)) : all,
+                                 b < 4u ? (all & ~(0xFFu << (8 * b))) | (TMATCH << (8 * b)) : all);
         }
     }
     __syncwarp();
     const uint8_t *ra = readSeq + (size_t)tA * readStride, *rbp = readSeq + (size_t)tB * readStride;
     const int j0 = lane * K + 1;
-    uint32_t rb[K], Hp[K], Dp[K], fl[K], bestH[K], bestRow[K], cnt[K];
+    // per column: PRMT selector (nibble 0 = A's base, nibble 2 = 4 + B's base, nibbles 1 / 3 replicate the sign bit of the same
+    // byte = 0), H of the row above in open form (H + open: what D and I consume, and with FOLD the diagonal too), D, clip floor
+    uint32_t sel[K], HO[K], Dp[K], fl[K];
+    const uint32_t O4 = pack2(-4 * open), FOUR2 = 0x00040004u, NEG_E4 = 0xFFFCFFFCu;
+    const uint32_t negOne = 0u - one;                           // 0xFFFFFFFF the compiler cannot fold (fma_add)
+    uint32_t basesA = 0, basesB = 0;                            // this lane's read bases, 2 bits each (lower-bound prologue)
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int j = j0 + k;
-        uint32_t a = j <= LA ? ra[j - 1] : 8u, b = j <= LB ? rbp[j - 1] : 8u;
-        rb[k] = a | (b << 16);
-        Hp[k] = pack2(h0_value(j, clipLt, open) + DP_BIAS);
+        const uint32_t a = j <= LA ? ra[j - 1] & 3u : 0u, b = j <= LB ? rbp[j - 1] & 3u : 0u;
+        basesA |= a << (2 * k); basesB |= b << (2 * k);
+        sel[k] = a | ((8u | a) << 4) | ((4u + b) << 8) | ((12u + b) << 12);
+        const uint32_t h0 = pack2(4 * h0_value(j, clipLt, open) + DP_BIAS);
+        HO[k] = h0 - O4;
         Dp[k] = DP_NEG2;
         fl[k] = j <= clipLt ? DP_BIAS2 : 0u;
-        bestH[k] = 0; bestRow[k] = 0; cnt[k] = 0;
+        asm volatile("" : "+r"(fl[k]));                         // keep it in a register: recomputing it costs two ALU-pipe slots per cell
     }
-    uint32_t prevHleft = pack2(h0_value(j0 - 1, clipLt, open) + DP_BIAS);
-    const uint32_t OPENABS2 = pack2(-open), MMABS2 = pack2(-mm), MINUS1 = 0xFFFFFFFFu;
-    const uint32_t DELTA = (uint32_t)(1 - mm);                 // match score - mismatch score
+    // lane 0 takes its left neighbour (column 0: H = 0, no I) from constants; as multiply-adds so the selection stays off the ALU pipe
+    const uint32_t keepLeft = lane == 0 ? 0u : one, leftH0 = lane == 0 ? DP_BIAS2 - O4 : 0u, leftI0 = lane == 0 ? DP_NEG2 : 0u;
+    // ---- threshold: max(cutoff, lower bound from the hinted diagonal), per task ----
+    int thrA = 0x7FF0, thrB = 0x7FF0;                           // biased x4 units; 0x7FF0: nothing can reach it (task absent)
+    {
+        const int minColA = max(LA - P.clipRt, 1), minColB = max(LB - P.clipRt, 1);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const bool live = half ? okB : okA;
+            const int Lh = half ? LB : LA, Nh = half ? NB : NA, cut = half ? cutB : cutA, minCol = half ? minColB : minColA;
+            const int dg = live && hints ? (int)hints[half ? tB : tA] : -1;
+            const uint32_t bases = half ? basesB : basesA;
+            int best = -(1 << 20);
+            if (live) {
+                // ungapped path: column j in row j + dg, starting from H[dg][0] = 0; valid while the row exists
+                int loc[K], tot = 0;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int j = j0 + k, r = j + dg;
+                    int s = 0;
+                    if (dg >= 0 && j <= Lh && r <= Nh) {
+                        const uint2 tb = refS[r - 1];
+                        const uint32_t e = ((half ? tb.y : tb.x) >> (8 * ((bases >> (2 * k)) & 3u))) & 0xFFu;
+                        s = FOLD ? (int)e - (int)O4v : 4 - (int)e;
+                    }
+                    tot += s; loc[k] = tot;
+                }
+                int incl = tot;
+#pragma unroll
+                for (int dlt = 1; dlt < 32; dlt <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, dlt); if (lane >= dlt) incl += v; }
+                const int before = incl - tot;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int j = j0 + k;
+                    if (dg >= 0 && j >= minCol && j <= Lh && j + dg <= Nh) best = max(best, before + loc[k]);
+                }
+            }
+#pragma unroll
+            for (int dlt = 16; dlt; dlt >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, dlt));
+            const int thr = DP_BIAS + max(4 * cut, best);
+            if (live) { if (half) thrB = thr; else thrA = thr; }
+        }
+    }
+    // lane-level answer bookkeeping (exact path): best value (biased x4; thr - 1 = nothing yet), (row << 12 | col) of its first
+    // occurrence in row-major order, number of cells equal to it
+    int lbA = thrA - 1, lbB = thrB - 1;
+    uint32_t keyA = 0xffffffffu, keyB = 0xffffffffu, cntA = 0, cntB = 0;
+    // (H + open) + T2 has bit 15 set <=> H >= threshold
+    auto make_t2 = [&](int a, int b) { return (uint32_t)(0x8000 + (int)O4v - a) | ((uint32_t)(0x8000 + (int)O4v - b) << 16); };
+    uint32_t T2 = make_t2(thrA, thrB);
+    const int minColA = max(LA - P.clipRt, 1), minColB = max(LB - P.clipRt, 1);
+    uint32_t prevLeftO = pack2(4 * h0_value(j0 - 1, clipLt, open) + DP_BIAS) - O4;            // H[i-1][j0-1] in open form
+    const uint2 *rowP = refS - lane;                            // row of step t = 1 is 1 - lane: table index t - 1 - lane
     constexpr int WORDS = K / 4, REM = K % 4, WB = WORDS * 256;
     uint8_t *tabP = tables + (size_t)lA * tableStride;          // pair table: 2 * tableStride bytes
     uint8_t *pw = tabP + WB + lane * 4;                         // word block of step 1
@@ -119,7 +214,7 @@ k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLe
     uint32_t sendH = 0, sendI = 0;
     const int lastLane = maxL > 0 ? (maxL - 1) / K : 0;
     const int steps = maxN + lastLane;
-    const uint32_t amask = lastLane >= 31 ? 0xffffffffu : ((2u << lastLane) - 1u);     // lanes that own read columns
+    const bool mine = lane <= lastLane;                         // lanes that own read columns (every lane runs the loop: full-mask shuffles)
     uint32_t accA[REM ? REM : 1] = {0}, accB[REM ? REM : 1] = {0};
     uint32_t hist[WORDS][3][4];                                 // codes of the last steps, slot = step % 4 (see cell_offset)
 #pragma unroll
@@ -128,53 +223,73 @@ k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLe
         for (int c = 0; c < 3; ++c)
 #pragma unroll
             for (int q = 0; q < 4; ++q) hist[w][c][q] = 0;
+    // exact bookkeeping for the cells of row i that reach the threshold (rare; see the kernel comment)
+    auto exact_path = [&](const int i, const uint32_t q) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            if (!((q >> (16 * half)) & 0x8000u)) continue;
+            const int Lh = half ? LB : LA, Nh = half ? NB : NA, minCol = half ? minColB : minColA;
+            int lb = half ? lbB : lbA; uint32_t key = half ? keyB : keyA, cnt = half ? cntB : cntA;
+            if (i <= Nh) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int j = j0 + k;
+                    const int v = (int)((HO[k] >> (16 * half)) & 0xffffu) + (int)O4v;
+                    if (j >= minCol && j <= Lh) {
+                        if (v > lb) { lb = v; key = ((uint32_t)i << 12) | (uint32_t)j; cnt = 1; }
+                        else if (v == lb) ++cnt;
+                    }
+                }
+            }
+            if (half) { lbB = lb; keyB = key; cntB = cnt; } else { lbA = lb; keyA = key; cntA = cnt; }
+        }
+        // from now on only cells that at least tie with this lane's best matter
+        T2 = make_t2(max(thrA, lbA), max(thrB, lbB));
+    };
     // One wavefront step of this lane; u = (t-1) % 4 is a compile-time constant in every caller.
-    // CHECKED = false in the steady phase, where every owning lane has a row that exists in BOTH tasks: no range test, no row mask,
+    // CHECKED = false in the steady phase, where every owning lane has a row that exists in BOTH tasks: no range test,
     // and the four unrolled steps need no register shuffling between them.
     auto step = [&](const int t, auto uTag, auto checked) {
         constexpr int u = decltype(uTag)::value;
         constexpr bool CHECKED = decltype(checked)::value;
-        const uint32_t rH = __shfl_up_sync(amask, sendH, 1);
-        const uint32_t rI = __shfl_up_sync(amask, sendI, 1);
+        const uint32_t rH = __shfl_up_sync(0xffffffffu, sendH, 1);                // open form: H + open of the left lane's last column
+        const uint32_t rI = __shfl_up_sync(0xffffffffu, sendI, 1);
         const int i = t - lane;
+        const uint2 *rowQ = rowP++;
         uint32_t code[K] = {};
-        const bool compute = !CHECKED || (i >= 1 && i <= maxN);
+        const bool compute = mine && (!CHECKED || (i >= 1 && i <= maxN));
         if (compute) {
-            uint32_t Hleft = lane == 0 ? DP_BIAS2 : rH;
-            uint32_t Il = lane == 0 ? DP_NEG2 : rI;
-            const uint32_t ref2 = refS[i - 1];
-            const uint32_t rowMask = (i <= NA ? 0x0000FFFFu : 0u) | (i <= NB ? 0xFFFF0000u : 0u);
-            const uint32_t row2 = (uint32_t)i * 0x00010001u;
-            uint32_t Hdiag = prevHleft;
-            prevHleft = Hleft;
+            uint32_t t2 = fma_add(rH, keepLeft, leftH0);                          // H left + open
+            uint32_t Il = fma_add(rI, keepLeft, leftI0);
+            const uint2 tb = *rowQ;
+            uint32_t Hd = prevLeftO;                                              // H diag, open form
+            prevLeftO = t2;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const uint32_t m = __vminu2(ref2 ^ rb[k], DP_ONE2);               // 1 where the bases differ
-                const uint32_t hs = Hdiag + DP_ONE2 - m * DELTA;                  // Hdiag + s(i,j)
-                const uint32_t t1 = Hp[k] - OPENABS2;
-                const uint32_t d = __viaddmax_u16x2(Dp[k], MINUS1, t1);           // max(D + ext, Hup + open)
-                const uint32_t t2 = Hleft - OPENABS2;
-                Il = __viaddmax_u16x2(Il, MINUS1, t2);                            // max(I + ext, Hleft + open)
+                const uint32_t e = prmt(tb.x, tb.y, sel[k]);                      // FOLD: substitution score - open (>= 0); else 0 / penalty
+                const uint32_t hs = FOLD ? fma_add(e, one, Hd) : fma_add(e, negOne, Hd + (O4 + FOUR2));     // Hdiag + s(i,j)
+                const uint32_t d = __viaddmax_u16x2(Dp[k], NEG_E4, HO[k]);         // max(D + ext, Hup + open)
+                Il = __viaddmax_u16x2(Il, NEG_E4, t2);                             // max(I + ext, Hleft + open)
                 const uint32_t h = __vimax3_u16x2(hs, d, Il);
-                const uint32_t hf = __vmaxu2(h, fl[k]);                           // clip floor for j <= clipLt (CPU_DP.cpp:505-510)
-                const uint32_t a = hf - Hdiag + MMABS2;                           // H - Hdiag - mm   >= 0
-                const uint32_t b = hf - t2;                                       // H - Hleft - open >= 0
-                const uint32_t zd = __vminu2(hf - d, DP_ONE2);                    // 0 where D == H
-                const uint32_t zr = __vminu2(hf - h, DP_ONE2);                    // 1 where the floor raised the cell (then zd == 1 too)
-                code[k] = a * 42u + (b * 3u + (zd + zr));                         // third digit: 0 = D==H, 1 = neither, 2 = raised by the clip floor
-                // answer cell per column: first strict maximum, ties counted (CPU_DP.cpp:545-590).  Column eligibility is applied
-                // when the columns are reduced; rows past the end of the shorter task only occur in the CHECKED variant.
-                const uint32_t hE = CHECKED ? (hf & rowMask) : hf;
-                const uint32_t q = bestH[k] + 0x80008000u - hE;                   // per half: bit 15 set <=> best >= this cell (no borrow: values < 0x8000)
-                uint32_t keep;                                                    // 0xFFFF in the halves that did NOT improve
-                asm("prmt.b32 %0, %1, %1, 0xBB99;" : "=r"(keep) : "r"(q));        // replicate the sign bits of bytes 1 and 3
-                const uint32_t lower = __viaddmin_s16x2_relu(q, 0x80008000u, DP_ONE2);   // 1 where this cell is below the best so far
-                bestH[k] = __vmaxu2(bestH[k], hE);
-                bestRow[k] = (bestRow[k] & keep) | (row2 & ~keep);
-                cnt[k] = ((cnt[k] + DP_ONE2 - lower) & keep) | (DP_ONE2 & ~keep);
-                Hdiag = Hp[k]; Hp[k] = hf; Dp[k] = d; Hleft = hf;
+                const uint32_t hf = __vmaxu2(h, fl[k]);                            // clip floor for j <= clipLt (CPU_DP.cpp:505-510)
+                const uint32_t nhf = fma_add(hf, negOne, DP_C2);                   // C - H
+                const uint32_t zdc = __viaddmax_u16x2(d, nhf, DP_CM1_2);           // C - (D == H ? 0 : 1)
+                const uint32_t zrc = __viaddmax_u16x2(h, nhf, DP_CM1_2);           // C - (raised by the floor ? 1 : 0)
+                code[k] = fma_add(zdc, one, fma_add(zrc, one, hf));                // low byte: 4H - zd - zr  (2C = 0 mod 256)
+                Hd = HO[k];
+                t2 = HO[k] = fma_add(O4, negOne, hf);
+                Dp[k] = d;
             }
-            sendH = Hleft; sendI = Il;
+            sendH = t2; sendI = Il;
+            // any cell of this step at or above the threshold?  (HO = H + open; T2 carries the offset)
+            {
+                uint32_t cm = HO[0];
+#pragma unroll
+                for (int k = 1; k + 1 < K; k += 2) cm = __vimax3_u16x2(cm, HO[k], HO[k + 1]);
+                if (K % 2 == 0) cm = __vmaxu2(cm, HO[K - 1]);
+                const uint32_t q = cm + T2;
+                if (q & 0x80008000u) exact_path(i, q);
+            }
 #pragma unroll
             for (int kk = 0; kk < REM; ++kk) {
                 const int bpos = u * REM + kk, pos = bpos & 3;                     // byte position inside the group's remainder words
@@ -193,7 +308,7 @@ k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLe
         }
         // trace words: byte c of word w holds column 4w+c of row i-(3-c), so that a diagonal run of four cells shares one word.
         // Low halves -> task A, high halves -> task B.  Rows maxN+1..maxN+3 only flush the older bytes.
-        if (!CHECKED || (i >= 1 && i <= maxN + 3)) {
+        if (mine && (!CHECKED || (i >= 1 && i <= maxN + 3))) {
 #pragma unroll
             for (int w = 0; w < WORDS; ++w) {
                 const uint32_t c0 = hist[w][0][(u + 1) & 3], c1 = hist[w][1][(u + 2) & 3], c2 = hist[w][2][(u + 3) & 3], c3 = code[4 * w + 3];
@@ -207,7 +322,7 @@ k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLe
     };
     // remainder words of the four-step group that ends at step t
     auto flush = [&](const int t) {
-        if (REM && t - lane >= 1 && t - 3 - lane <= maxN) {
+        if (REM && mine && t - lane >= 1 && t - 3 - lane <= maxN) {
 #pragma unroll
             for (int q = 0; q < REM; ++q) {
                 *(uint32_t *)(pr + q * 256) = accA[q];
@@ -224,7 +339,7 @@ k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLe
         flush(t + 3);
         pw += 4 * WB;
     };
-    if (lane <= lastLane && maxL > 0) {
+    if (maxL > 0) {
         const int steadyN = (NA > 0 && NB > 0) ? min(NA, NB) : maxN;    // rows present in every live task of the pair
         const int stepsR = (steps + 3 + 3) & ~3;                        // + 3 flush steps, whole groups
         const int rampEnd = min((lastLane + 3) & ~3, stepsR);           // from here on every owning lane has started
@@ -238,30 +353,19 @@ k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLe
         for (; t <= stepsR; t += 4) group(t, std::true_type());
     }
     __syncwarp();
-    // ---- winner per task: max score over the eligible columns, then smallest (row, col); ties summed ----
+    // ---- winner per task: best value over the lanes, then smallest (row, col); ties summed ----
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-        const int sh = half * 16;
-        const int Lh = half ? LB : LA, minCol = max(Lh - P.clipRt, 1);
-        int best = 0;
-#pragma unroll
-        for (int k = 0; k < K; ++k)
-            if (j0 + k >= minCol && j0 + k <= Lh) best = max(best, (int)((bestH[k] >> sh) & 0xffffu));
-        int gbest = best;
+        const int lb = half ? lbB : lbA, thr = half ? thrB : thrA;
+        int gbest = lb;
 #pragma unroll
         for (int dlt = 16; dlt; dlt >>= 1) gbest = max(gbest, __shfl_xor_sync(0xffffffffu, gbest, dlt));
-        uint32_t key = 0xffffffffu; uint32_t c2 = 0;
-#pragma unroll
-        for (int k = 0; k < K; ++k)
-            if (j0 + k >= minCol && j0 + k <= Lh && (int)((bestH[k] >> sh) & 0xffffu) == gbest) {
-                key = min(key, (((bestRow[k] >> sh) & 0xffffu) << 12) | (uint32_t)(j0 + k));
-                c2 += (cnt[k] >> sh) & 0xffffu;
-            }
+        uint32_t key = lb == gbest ? (half ? keyB : keyA) : 0xffffffffu, c2 = lb == gbest ? (half ? cntB : cntA) : 0u;
 #pragma unroll
         for (int dlt = 16; dlt; dlt >>= 1) { key = min(key, __shfl_xor_sync(0xffffffffu, key, dlt)); c2 += __shfl_xor_sync(0xffffffffu, c2, dlt); }
         if (lane == 0 && (half == 0 || hasB)) {
-            FillOut f; f.score = gbest - DP_BIAS; f.row = key >> 12; f.col = key & 0xfffu; f.cnt = c2;
-            if (gbest == 0 || !(half ? okB : okA)) { f.score = 0; f.row = 0; f.col = 0; f.cnt = 0; }
+            FillOut f; f.score = (gbest - DP_BIAS) >> 2; f.row = key >> 12; f.col = key & 0xfffu; f.cnt = c2;
+            if (gbest < thr || !(half ? okB : okA)) { f.score = 0; f.row = 0; f.col = 0; f.cnt = 0; }
             fill[half == 0 ? tA : tB] = f;
         }
     }
@@ -303,9 +407,10 @@ k_dp_tb(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLens
         if (r == 0) return c <= clipLt ? 0 : 1;             // row 0 (CPU_DP.cpp:405-427)
         return trace_flag(cellAt(r, c));
     };
-    auto hdAt = [&](int r, int c) -> int {                  // H[r][c] - H[r][c-1] for any row including row 0
-        if (r == 0) return h0_value(c, clipLt, open) - h0_value(c - 1, clipLt, open);
-        return open + (int)(cellAt(r, c) / 3 % 14);
+    auto hmodAt = [&](int r, int c) -> int {                // H[r][c] mod 64 for any cell including row 0 / column 0
+        if (r == 0) return h0_value(c, clipLt, open) & 63;
+        if (c == 0) return 0;
+        return trace_h(cellAt(r, c));
     };
     const size_t rsOff = (size_t)task * readStride, fsOff = (size_t)task * refStride;
     uint32_t rsW = 0, fsW = 0; size_t rsIdx = ~(size_t)0, fsIdx = ~(size_t)0;
@@ -335,39 +440,42 @@ k_dp_tb(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLens
     enum { NORMAL, I_EXT, D_EXT, SM_EXIT, SI_EXIT, SD_EXIT };
     int state = NORMAL;
     int accum = 0;
-    // `diagCell` carries the byte of (j-1, i-1) from the clip check of one step to the next step, which usually moves there
+    // Every difference the reference reads from its table is rebuilt from H mod 64 of the two cells (trace byte layout above):
+    // dd = H - Hdiag, hd = H - Hleft, vd = H - Hup.  `hcur` is H mod 64 of the current cell; a diagonal move hands the
+    // predecessor's byte over, so the usual step costs one table access (and stays inside one cached word).
     uint32_t cell = cellAt(j, i);
     while (i > 0 && j > 0) {
-        int flag = trace_flag(cell);
-        int hd = open + (int)(cell / 3 % 14);
-        int dd = mm + (int)(cell / 42);
+        const int flag = trace_flag(cell), hcur = trace_h(cell);
         if (state == NORMAL) {
+            // diagonal predecessor, including the virtual row 0 / column 0 (CPU_DP.cpp:405-450)
+            uint32_t diagCell = 0; int dflag, hdiag;
+            if (i - 1 == 0) { dflag = 0; hdiag = 0; }
+            else if (j - 1 == 0) { dflag = (i - 1) <= clipLt ? 0 : 1; hdiag = h0_value(i - 1, clipLt, open) & 63; }
+            else { diagCell = cellAt(j - 1, i - 1); dflag = trace_flag(diagCell); hdiag = trace_h(diagCell); }
+            const int dd = trace_diff(hcur, hdiag);
             bool eq = refBase(j - 1) == readBase(i - 1);
             int ms = eq ? 1 : mm;
             if (dd == ms) {
-                // flag of the diagonal predecessor, including the virtual row 0 / column 0 (CPU_DP.cpp:405-450)
-                uint32_t diagCell = 0; int dflag;
-                if (i - 1 == 0) dflag = 0;
-                else if (j - 1 == 0) dflag = (i - 1) <= clipLt ? 0 : 1;
-                else { diagCell = cellAt(j - 1, i - 1); dflag = trace_flag(diagCell); }
                 if (i != 1 && dflag == 0) { state = SM_EXIT; break; }
                 emit(eq ? 'M' : 'm'); --j; --i;
                 cell = diagCell;                                     // valid whenever the loop continues (i > 0 && j > 0)
                 continue;
             } else if (flag == 1) {
-                int vd = dd - hdAt(j - 1, i);
+                int vd = trace_diff(hcur, hmodAt(j - 1, i));
                 emit('D'); --j;
                 if (vd != open) { accum = (int8_t)(vd - ext); state = D_EXT; }
             } else {
+                int hd = trace_diff(hcur, hmodAt(j, i - 1));
                 emit('I'); --i;
                 if (hd != open) { accum = (int8_t)(hd - ext); state = I_EXT; }
             }
         } else if (state == D_EXT) {
-            int vd = dd - hdAt(j - 1, i);
+            int vd = trace_diff(hcur, hmodAt(j - 1, i));
             if (vd + accum == open && flagAt(j - 1, i) == 0) { state = SD_EXIT; break; }
             emit('D'); --j;
             if (vd + accum == open) state = NORMAL; else accum = (int8_t)(accum + vd - ext);
         } else {
+            int hd = trace_diff(hcur, hmodAt(j, i - 1));
             if (hd + accum == open && flagAt(j, i - 1) == 0) { state = SI_EXIT; break; }
             emit('I'); --i;
             if (hd + accum == open) state = NORMAL; else accum = (int8_t)(accum + hd - ext);
@@ -477,31 +585,36 @@ __global__ void k_dp_compact(const uint32_t *__restrict__ needDp, const uint32_t
 // ------------------------------------------------------------------------------------
 __global__ void k_extract(MpIndexView ix, const uint32_t *__restrict__ reads, uint32_t wpq, const MpDpTask *__restrict__ tasks,
                           uint32_t nTasks, uint8_t *__restrict__ refSeq, uint32_t refStride, uint8_t *__restrict__ readSeq,
-                          uint32_t readStride, uint32_t *__restrict__ refLens, uint32_t *__restrict__ readLens, int32_t *__restrict__ cutoffs)
+                          uint32_t readStride, uint32_t *__restrict__ refLens, uint32_t *__restrict__ readLens, int32_t *__restrict__ cutoffs,
+                          int16_t *__restrict__ hints)
 {
     const uint32_t task = blockIdx.x;
     if (task >= nTasks) return;
     MpDpTask tk = tasks[task];
-    if (!tk.valid) { tk.refLen = 0; }
+    // a task that does not fit its rows is dropped, never written past them (callers size the strides from -L / -u)
+    if (!tk.valid || tk.refLen > refStride || tk.readLen > readStride) { tk.refLen = 0; tk.valid = 0; }
     for (uint32_t a = threadIdx.x; a < tk.refLen; a += blockDim.x)
         refSeq[(size_t)task * refStride + a] = (uint8_t)mp_text_base(ix, tk.refStart + a);
     const uint32_t *rd = reads + (size_t)tk.readID * wpq;
-    for (uint32_t a = threadIdx.x; a < tk.readLen; a += blockDim.x) {
+    for (uint32_t a = threadIdx.x; tk.valid && a < tk.readLen; a += blockDim.x) {
         uint32_t p = tk.strand == 1 ? a : tk.readLen - 1 - a;
         uint32_t b = (rd[p >> 4] >> ((p & 15) << 1)) & 3;
         readSeq[(size_t)task * readStride + a] = (uint8_t)(tk.strand == 1 ? b : 3 - b);
     }
-    if (threadIdx.x == 0) { refLens[task] = tk.refLen; readLens[task] = tk.valid ? tk.readLen : 0; cutoffs[task] = tk.cutoff; }
+    if (threadIdx.x == 0) { refLens[task] = tk.refLen; readLens[task] = tk.valid ? tk.readLen : 0; cutoffs[task] = tk.cutoff; hints[task] = tk.valid ? tk.diag : (int16_t)-1; }
 }
 
 static int launch_dp(mp_context *ctx, const uint8_t *dRef, const uint32_t *dRefLens, uint32_t refStride,
                      const uint8_t *dRead, const uint32_t *dReadLens, uint32_t readStride, const int32_t *dCutoffs,
                      uint32_t nTasks, uint32_t maxRefLen, uint32_t maxReadLen, const MpDpParams &P,
-                     MpDpOut *dOuts, uint8_t *dPatterns, uint32_t patStride)
+                     MpDpOut *dOuts, uint8_t *dPatterns, uint32_t patStride, const int16_t *dHints)
 {
     if (nTasks == 0) return 0;
     const int K = maxReadLen <= 160 ? 5 : maxReadLen <= 256 ? 8 : 10;
     if (maxReadLen > 320) { mp_set_error("read length %u exceeds the DP kernel bound 320", maxReadLen); return MP_ERR_ARG; }
+    if ((size_t)4 * (((size_t)maxRefLen + 44) & ~(size_t)3) * sizeof(uint2) > 200 * 1024) {
+        mp_set_error("DP window of %u reference bases exceeds the shared-memory staging of the fill kernel (max ~6300)", maxRefLen); return MP_ERR_CAPACITY;
+    }
     const int S = ((int)maxRefLen + 44) & ~3;                 // steps 1 .. maxRefLen + 31 + 3 flush steps, rounded up to groups of four, plus slack
     const size_t tableStride = (size_t)S * 32 * K;
     if (ctx->dFill.reserve((size_t)nTasks * sizeof(FillOut))) return MP_ERR_CUDA;
@@ -520,7 +633,7 @@ static int launch_dp(mp_context *ctx, const uint8_t *dRef, const uint32_t *dRefL
     if (per == 0) { mp_set_error("not enough device memory for the DP traceback tables"); return MP_ERR_CUDA; }
     uint8_t *tab = ctx->dTable.as<uint8_t>();
     FillOut *fill = ctx->dFill.as<FillOut>();
-    const size_t smem = (size_t)4 * S * 4;
+    const size_t smem = (size_t)4 * S * sizeof(uint2);          // one 8-byte substitution table per reference row and warp
     // exact-occurrence shortcut (k_dp_exact): MP_DP_EXACT=0 sends every task through the DP kernels
     static const bool useExact = !(getenv("MP_DP_EXACT") && getenv("MP_DP_EXACT")[0] == '0');
     const uint32_t perMax = std::min<uint32_t>(per, nTasks);
@@ -545,12 +658,15 @@ static int launch_dp(mp_context *ctx, const uint8_t *dRef, const uint32_t *dRefL
 #define LAUNCH(KK) do { \
         if (useExact) LAUNCH_EXACT(KK); \
         cudaEvent_t stop_ = ctx->ev_begin(0); \
-        if (P.mismatch == -2 && P.open == -3) \
-            (++g_mp_launches), k_dp_fill<KK, -2, -3><<<gridF, block, smem, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, \
-                base, n, P, tab, tableStride, S, fill, active, nActive); \
-        else \
-            (++g_mp_launches), k_dp_fill<KK, 0, 0><<<gridF, block, smem, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, \
-                base, n, P, tab, tableStride, S, fill, active, nActive); \
+        if (P.mismatch == -2 && P.open == -3) { \
+            if (smem > 48 * 1024) MP_CUDA(cudaFuncSetAttribute(k_dp_fill<KK, -2, -3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            (++g_mp_launches), k_dp_fill<KK, -2, -3><<<gridF, block, smem, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, dHints, \
+                base, n, P, tab, tableStride, S, fill, active, nActive, 1u); \
+        } else { \
+            if (smem > 48 * 1024) MP_CUDA(cudaFuncSetAttribute(k_dp_fill<KK, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            (++g_mp_launches), k_dp_fill<KK, 0, 0><<<gridF, block, smem, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, dHints, \
+                base, n, P, tab, tableStride, S, fill, active, nActive, 1u); \
+        } \
         ctx->ev_end(stop_); stop_ = ctx->ev_begin(1); \
         if ((patStride & 3) == 0 && ((uintptr_t)dPatterns & 3) == 0) \
             (++g_mp_launches), k_dp_tb<KK, true><<<gridT, block, 0, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, \
@@ -572,7 +688,7 @@ int mpd_run_explicit(mp_context *ctx, const uint8_t *dRef, const uint32_t *dRefL
                      uint32_t nTasks, const MpDpParams &P, MpDpOut *dOuts, uint8_t *dPatterns, uint32_t patStride)
 {
     return launch_dp(ctx, dRef, dRefLens, maxRefLen, dRead, dReadLens, maxReadLen, dCutoffs, nTasks, maxRefLen, maxReadLen, P,
-                     dOuts, dPatterns, patStride);
+                     dOuts, dPatterns, patStride, nullptr);
 }
 
 int mpd_run_tasks(mp_context *ctx, const MpDpTask *dTasks, uint32_t nTasks, uint32_t maxRefLen, uint32_t maxReadLen,
@@ -580,14 +696,15 @@ int mpd_run_tasks(mp_context *ctx, const MpDpTask *dTasks, uint32_t nTasks, uint
 {
     if (nTasks == 0) return 0;
     size_t refB = ((size_t)nTasks * maxRefLen + 15) & ~(size_t)15, readB = (size_t)nTasks * maxReadLen;
-    if (ctx->dRefSeq.reserve(refB + (size_t)nTasks * 12) || ctx->dReadSeq.reserve(readB)) return MP_ERR_CUDA;
+    if (ctx->dRefSeq.reserve(refB + (size_t)nTasks * 14 + 16) || ctx->dReadSeq.reserve(readB)) return MP_ERR_CUDA;
     uint8_t *dRef = ctx->dRefSeq.as<uint8_t>();
     uint32_t *dRefLens = (uint32_t *)(dRef + refB);
     uint32_t *dReadLens = dRefLens + nTasks;
     int32_t *dCutoffs = (int32_t *)(dReadLens + nTasks);
+    int16_t *dHints = (int16_t *)(dCutoffs + nTasks);
     (++g_mp_launches), k_extract<<<nTasks, 64, 0, ctx->stream>>>(ctx->ix, ctx->dReads.as<uint32_t>(), ctx->wpq, dTasks, nTasks, dRef, maxRefLen,
-                                             ctx->dReadSeq.as<uint8_t>(), maxReadLen, dRefLens, dReadLens, dCutoffs);
+                                             ctx->dReadSeq.as<uint8_t>(), maxReadLen, dRefLens, dReadLens, dCutoffs, dHints);
     MP_CUDA(cudaGetLastError());
     return launch_dp(ctx, dRef, dRefLens, maxRefLen, ctx->dReadSeq.as<uint8_t>(), dReadLens, maxReadLen, dCutoffs, nTasks,
-                     maxRefLen, maxReadLen, P, dOuts, dPatterns, patStride);
+                     maxRefLen, maxReadLen, P, dOuts, dPatterns, patStride, dHints);
 }

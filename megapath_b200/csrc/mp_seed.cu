@@ -505,6 +505,12 @@ static int exclusive_scan_u32(mp_context *ctx, const uint32_t *in, uint32_t *out
 
 int mps_upload(mp_context *ctx, const uint32_t *queries, const uint32_t *readLengths, uint32_t nReads, uint32_t wpq)
 {
+    // a read longer than its 2-bit row would make every consumer (seeding, task extraction, the DP kernels' shared-memory rows) run
+    // past its buffers: refuse the batch here, where the lengths are still on the host
+    uint32_t maxLen = 0;
+    for (uint32_t r = 0; r < nReads; ++r) maxLen = readLengths[r] > maxLen ? readLengths[r] : maxLen;
+    if (maxLen > 16u * wpq) { mp_set_error("mp_batch_upload: a read of %u bases does not fit %u words per query", maxLen, wpq); return MP_ERR_ARG; }
+    ctx->maxLenBatch = maxLen;
     uint64_t nPad = ((uint64_t)nReads + 31) / 32 * 32;
     size_t bytes = nPad * wpq * 4;
     if (ctx->dReadsIl.reserve(bytes) || ctx->dReads.reserve(bytes + 64) || ctx->dLens.reserve((size_t)nReads * 4)) return MP_ERR_CUDA;

@@ -54,11 +54,12 @@ void single_merge(const std::vector<SCand> &c, std::vector<SCand> &out)
 }
 
 // encode one pattern -> cigar text appended to the arena; returns offset; fills stats
+// (a failed growth of the pinned arena returns 0xFFFFFFFF and leaves the error message set)
 uint32_t append_cigar(PinnedBuf<char> &arena, const uint8_t *pat, int open, int ext, CigStats &st)
 {
     st = cigar_encode(pat, open, ext, nullptr, 0);
     size_t off = arena.size();
-    arena.resize(off + st.textLen + 1);
+    if (arena.resize(off + st.textLen + 1)) return 0xFFFFFFFFu;
     cigar_encode(pat, open, ext, arena.data() + off, st.textLen);
     arena[off + st.textLen] = 0;
     return (uint32_t)off;
@@ -173,6 +174,7 @@ int mps_single_and_rescue(mp_context *ctx, const mp_align_params *P, mp_results 
         MpDpTask t; memset(&t, 0, sizeof t);
         t.refStart = start; t.refLen = dnaLen; t.readID = c.readID; t.readLen = (uint16_t)readLength; t.strand = (uint8_t)c.strand;
         t.valid = 1; t.cutoff = dp_cutoff(readLength);
+        t.diag = (int16_t)std::min<uint64_t>(c.pos - start, 0x7fff);          // the seed's diagonal inside the window (hint only)
         tasks[i] = t;
         cells += (uint64_t)dnaLen * readLength; ++tasksRun;
     }
@@ -188,6 +190,7 @@ int mps_single_and_rescue(mp_context *ctx, const mp_align_params *P, mp_results 
         CigStats st;
         mp_single_result r; memset(&r, 0, sizeof r);
         r.cigar = append_cigar(HC, pats.data() + i * patStride, P->openGapScore, P->extendGapScore, st);
+        if (r.cigar == 0xFFFFFFFFu) return MP_ERR_CUDA;
         r.readID = tasks[i].readID; r.strand = tasks[i].strand; r.seedAlignmentLength = canStream[i].seedLen;
         r.algnmt = tasks[i].refStart + outs[i].hitLoc; r.score = outs[i].score;
         r.startPos = tasks[i].refStart; r.refDpLength = tasks[i].refLen; r.peLeftAnchor = maxDNALengthS;
@@ -234,6 +237,7 @@ int mps_single_and_rescue(mp_context *ctx, const mp_align_params *P, mp_results 
         const uint32_t alignedLen = lens[alignedReadID], unalignedLen = lens[unalignedReadID];
         MpDpTask t; memset(&t, 0, sizeof t);
         t.readID = unalignedReadID; t.readLen = (uint16_t)unalignedLen; t.valid = 1; t.cutoff = dp_cutoff(unalignedLen);
+        t.diag = -1;                                              // a rescue window has no seed
         if ((int)sr.strand == P->peStrandLeftLeg) {               // aligned read on the left, mate on the right
             uint64_t rightEnd = alignedPos + (uint64_t)(int64_t)insert_high;
             uint64_t rightStart = alignedPos + (uint64_t)(int64_t)insert_low - unalignedLen;
@@ -297,6 +301,7 @@ int mps_single_and_rescue(mp_context *ctx, const mp_align_params *P, mp_results 
         if (routs[id].score >= rtasks[id].cutoff) {
             CigStats st;
             dpCigar = append_cigar(HC, rpats.data() + id * rStride, P->openGapScore, P->extendGapScore, st);
+            if (dpCigar == 0xFFFFFFFFu) return MP_ERR_CUDA;
             int L = (int)rtasks[id].readLen - st.nI - st.nS;
             int numMis = (L * P->matchScore + st.gapPenalty - routs[id].score) / (P->matchScore - P->mismatchScore);
             dpEdit = st.nI + st.nD + numMis;

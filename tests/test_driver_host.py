@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-EXE = os.path.join(ROOT, "megapath_b200", "bin", "soap4")
+EXE = os.path.join(ROOT, "megapath_b200", "bin", "soap4_hosttest")      # the driver built with -DMP_TEST_HOOKS
 
 pytestmark = pytest.mark.skipif(not os.path.exists(EXE), reason="driver binary not built (run __graft_entry__.build())")
 
