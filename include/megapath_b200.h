@@ -47,7 +47,7 @@ typedef struct mp_mmp_params {
 typedef struct mp_align_params {
     mp_mmp_params mmp;
     int32_t matchScore;        /* must be 1  (CPU_DP.cpp:199-208) */
-    int32_t mismatchScore;     /* -4..-1 */
+    int32_t mismatchScore;     /* -4..-2, and > 2 * openGapScore (see mp_align_pairs) */
     int32_t openGapScore;      /* -6..-2 : cost of the first gap base */
     int32_t extendGapScore;    /* must be -1 */
     int32_t softClipLeft;      /* [Clipping] MaxFrontLenClipped */

@@ -883,7 +883,10 @@ int main(int argc, char **argv)
     fill_char_map();
     SeqReader r1, r2;
     if (!r1.open(opt.query1) || !r2.open(opt.query2)) { fprintf(stderr, "Cannot open the read files\n"); return 1; }
-    const uint32_t maxNumQueries = 12 * 8192 * 128 / 6;            // SOAP4.cpp:206
+    uint32_t maxNumQueries = 12 * 8192 * 128 / 6;                  // SOAP4.cpp:206
+    if (const char *e = getenv("MP_BATCH_READS")) {                // smaller batches (multi-batch / multi-context tests on small inputs)
+        const long v = atol(e); if (v >= 64 && v <= 12 * 8192 * 128 / 6) maxNumQueries = (uint32_t)v & ~63u;
+    }
 
     // ---- pipeline: reader thread -> GPU workers (one per context; each formats its own batch) -> ordered writer (this thread).
     //      The reference overlaps read loading with alignment the same way (aio_thread.cpp:804, SOAP4.cpp:424-441, 576-585). ----

@@ -331,7 +331,7 @@ extern "C" void mp_destroy(mp_context *ctx)
                        &ctx->dSeedPos, &ctx->dNPos, &ctx->dNNeg, &ctx->dCandCount, &ctx->dCandStart, &ctx->dCands, &ctx->dScanTmp,
                        &ctx->dTasks, &ctx->dRefSeq, &ctx->dReadSeq, &ctx->dTable, &ctx->dFill, &ctx->dPattern, &ctx->dDpOut,
                        &ctx->dLT, &ctx->dRT, &ctx->dLO, &ctx->dRO, &ctx->dLP, &ctx->dRP, &ctx->dOk, &ctx->dBytes, &ctx->dIdx, &ctx->dOff,
-                       &ctx->dRes, &ctx->dCig, &ctx->dExFlag, &ctx->dExPos, &ctx->dExIdx, &ctx->dAligned, &ctx->dGather };
+                       &ctx->dRes, &ctx->dCig, &ctx->dExFlag, &ctx->dExPos, &ctx->dExIdx, &ctx->dAligned, &ctx->dGather, &ctx->dHintTest };
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->stream);
@@ -408,8 +408,8 @@ extern "C" int mp_dp_batch(mp_context *ctx,
     if (!ctx || !packedDNA || !DNALengths || !packedRead || !readLengths || !cutoffs || !scores || !hitLocs || !maxScoreCounts || !pattern || !clipLt || !clipRt) {
         mp_set_error("mp_dp_batch: null argument"); return MP_ERR_ARG;
     }
-    if (mismatchScore > -1 || mismatchScore < openGapScore * 2 || mismatchScore < -4 || openGapScore < -6 || openGapScore >= -1) {
-        mp_set_error("mp_dp_batch: score parameters outside the supported range (CPU_DP.cpp:199-208)"); return MP_ERR_ARG;
+    if (mismatchScore > -2 || mismatchScore <= openGapScore * 2 || mismatchScore < -4 || openGapScore < -6 || openGapScore >= -1) {
+        mp_set_error("mp_dp_batch: score parameters outside the supported range (CPU_DP.cpp:199-208; mismatch = -1 divides by zero at CPU_DP.cpp:310, and for mismatch == 2 * open the reference traceback prefers I over D where the plain recurrence ties: unpinned, refused)"); return MP_ERR_ARG;
     }
     if (n == 0) return 0;
     for (uint32_t t = 0; t < n; ++t)
@@ -459,9 +459,9 @@ extern "C" int mp_align_pairs(mp_context *ctx, const mp_align_params *params, mp
 {
     if (!ctx || !params || !out) { mp_set_error("mp_align_pairs: null argument"); return MP_ERR_ARG; }
     if (!ctx->hasIndex || !ctx->hasBatch) { mp_set_error("mp_align_pairs: index and batch must be loaded first"); return MP_ERR_STATE; }
-    if (params->matchScore != 1 || params->extendGapScore != -1 || params->mismatchScore > -1 || params->mismatchScore < params->openGapScore * 2 ||
+    if (params->matchScore != 1 || params->extendGapScore != -1 || params->mismatchScore > -2 || params->mismatchScore <= params->openGapScore * 2 ||
         params->mismatchScore < -4 || params->openGapScore < -6 || params->openGapScore >= -1) {
-        mp_set_error("mp_align_pairs: score parameters outside the supported range (CPU_DP.cpp:199-208)"); return MP_ERR_ARG;
+        mp_set_error("mp_align_pairs: score parameters outside the supported range (CPU_DP.cpp:199-208; mismatch = -1 divides by zero at CPU_DP.cpp:310, and for mismatch == 2 * open the reference traceback prefers I over D where the plain recurrence ties: unpinned, refused)"); return MP_ERR_ARG;
     }
     if ((int64_t)ctx->maxLenBatch >= (int64_t)params->maxReadLength) {
         mp_set_error("the batch holds a read of %u bases but maxReadLength is %d (reads must be shorter)", ctx->maxLenBatch, params->maxReadLength);

@@ -137,6 +137,7 @@ struct mp_context {
     mp_align_params seedParams;
     // DP
     DevBuf dTasks, dRefSeq, dReadSeq, dTable, dFill, dPattern, dDpOut;
+    DevBuf dHintTest;                                                             // MP_DP_TEST_HINT (mp_dp.cu)
     DevBuf dExFlag, dExPos, dExIdx;                                              // exact-occurrence test: flags, scan, active slots (mp_dp.cu)
     DevBuf dLT, dRT, dLO, dRO, dLP, dRP, dOk, dBytes, dIdx, dOff, dRes, dCig;   // stage S1 chunk buffers (kept across calls)
     // results (host, owned until release)

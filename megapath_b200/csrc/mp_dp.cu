@@ -79,6 +79,34 @@ __device__ __forceinline__ int trace_h(uint32_t cell) { return (int)(((cell + 3u
 __device__ __forceinline__ int trace_flag(uint32_t cell) { const uint32_t g = cell & 3u; return g == 0 ? 1 : g == 3 ? 2 : 0; }
 __device__ __forceinline__ int trace_diff(int a, int b) { return ((a - b + 32) & 63) - 32; }      // a - b for values known mod 64
 
+// Exact answer bookkeeping of one lane (see k_dp_fill): best value so far (biased x4 units), (row << 12 | col) of its first occurrence
+// in row-major order, number of cells equal to it -- per task of the pair.  Kept out of line: it runs for a handful of steps per
+// task, and inlined into every unrolled step it made the hot loop several times larger than the instruction cache likes.
+struct DpTrack { int lb[2]; uint32_t key[2], cnt[2]; int thr[2], L[2], N[2], minCol[2]; };
+template <int K>
+__device__ __noinline__ uint32_t dp_track_cells(DpTrack *tr, const uint32_t *ho, uint32_t q, int i, int j0, int o4)
+{
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        if (!((q >> (16 * half)) & 0x8000u) || i > tr->N[half]) continue;
+        int lb = tr->lb[half]; uint32_t key = tr->key[half], cnt = tr->cnt[half];
+        const int Lh = tr->L[half], minCol = tr->minCol[half];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int j = j0 + k;
+            const int v = (int)((ho[k] >> (16 * half)) & 0xffffu) + o4;
+            if (j >= minCol && j <= Lh) {
+                if (v > lb) { lb = v; key = ((uint32_t)i << 12) | (uint32_t)j; cnt = 1; }
+                else if (v == lb) ++cnt;
+            }
+        }
+        tr->lb[half] = lb; tr->key[half] = key; tr->cnt[half] = cnt;
+    }
+    // from now on only cells that at least tie with this lane's best matter: (H + open) + T2 has bit 15 set <=> H >= threshold
+    const int a = max(tr->thr[0], tr->lb[0]), b = max(tr->thr[1], tr->lb[1]);
+    return (uint32_t)(0x8000 + o4 - a) | ((uint32_t)(0x8000 + o4 - b) << 16);
+}
+
 // k_dp_fill<K, MM, OPEN>: MM / OPEN = mismatch and gap-open score as compile-time constants (0 = take them from P at run time).
 //
 // Scores are carried times four with a +0x4000 bias in unsigned 16-bit halves (task A low, task B high): the two free low bits of
@@ -197,14 +225,18 @@ k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLe
             if (live) { if (half) thrB = thr; else thrA = thr; }
         }
     }
-    // lane-level answer bookkeeping (exact path): best value (biased x4; thr - 1 = nothing yet), (row << 12 | col) of its first
-    // occurrence in row-major order, number of cells equal to it
-    int lbA = thrA - 1, lbB = thrB - 1;
-    uint32_t keyA = 0xffffffffu, keyB = 0xffffffffu, cntA = 0, cntB = 0;
+    // lane-level answer bookkeeping (dp_track_cells): thr - 1 = nothing yet
+    DpTrack tr;
+    tr.lb[0] = thrA - 1; tr.lb[1] = thrB - 1; tr.key[0] = tr.key[1] = 0xffffffffu; tr.cnt[0] = tr.cnt[1] = 0;
+    tr.thr[0] = thrA; tr.thr[1] = thrB; tr.L[0] = LA; tr.L[1] = LB; tr.N[0] = NA; tr.N[1] = NB;
+    tr.minCol[0] = max(LA - P.clipRt, 1); tr.minCol[1] = max(LB - P.clipRt, 1);
     // (H + open) + T2 has bit 15 set <=> H >= threshold
-    auto make_t2 = [&](int a, int b) { return (uint32_t)(0x8000 + (int)O4v - a) | ((uint32_t)(0x8000 + (int)O4v - b) << 16); };
-    uint32_t T2 = make_t2(thrA, thrB);
-    const int minColA = max(LA - P.clipRt, 1), minColB = max(LB - P.clipRt, 1);
+    const int lastLane = maxL > 0 ? (maxL - 1) / K : 0;
+    const int steps = maxN + lastLane;
+    const bool mine = lane <= lastLane;                         // lanes that own read columns (every lane runs the loop: full-mask shuffles)
+    // lanes without read columns run the steady groups like everyone else (straight-line code, full 128-byte trace lines) on
+    // padding cells; their T2 = 0 never triggers
+    uint32_t T2 = mine ? (uint32_t)(0x8000 + (int)O4v - thrA) | ((uint32_t)(0x8000 + (int)O4v - thrB) << 16) : 0u;
     uint32_t prevLeftO = pack2(4 * h0_value(j0 - 1, clipLt, open) + DP_BIAS) - O4;            // H[i-1][j0-1] in open form
     const uint2 *rowP = refS - lane;                            // row of step t = 1 is 1 - lane: table index t - 1 - lane
     constexpr int WORDS = K / 4, REM = K % 4, WB = WORDS * 256;
@@ -212,9 +244,6 @@ k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLe
     uint8_t *pw = tabP + WB + lane * 4;                         // word block of step 1
     uint8_t *pr = tabP + (size_t)S * WB + lane * 4;             // remainder group 0
     uint32_t sendH = 0, sendI = 0;
-    const int lastLane = maxL > 0 ? (maxL - 1) / K : 0;
-    const int steps = maxN + lastLane;
-    const bool mine = lane <= lastLane;                         // lanes that own read columns (every lane runs the loop: full-mask shuffles)
     uint32_t accA[REM ? REM : 1] = {0}, accB[REM ? REM : 1] = {0};
     uint32_t hist[WORDS][3][4];                                 // codes of the last steps, slot = step % 4 (see cell_offset)
 #pragma unroll
@@ -223,29 +252,6 @@ k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLe
         for (int c = 0; c < 3; ++c)
 #pragma unroll
             for (int q = 0; q < 4; ++q) hist[w][c][q] = 0;
-    // exact bookkeeping for the cells of row i that reach the threshold (rare; see the kernel comment)
-    auto exact_path = [&](const int i, const uint32_t q) {
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            if (!((q >> (16 * half)) & 0x8000u)) continue;
-            const int Lh = half ? LB : LA, Nh = half ? NB : NA, minCol = half ? minColB : minColA;
-            int lb = half ? lbB : lbA; uint32_t key = half ? keyB : keyA, cnt = half ? cntB : cntA;
-            if (i <= Nh) {
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const int j = j0 + k;
-                    const int v = (int)((HO[k] >> (16 * half)) & 0xffffu) + (int)O4v;
-                    if (j >= minCol && j <= Lh) {
-                        if (v > lb) { lb = v; key = ((uint32_t)i << 12) | (uint32_t)j; cnt = 1; }
-                        else if (v == lb) ++cnt;
-                    }
-                }
-            }
-            if (half) { lbB = lb; keyB = key; cntB = cnt; } else { lbA = lb; keyA = key; cntA = cnt; }
-        }
-        // from now on only cells that at least tie with this lane's best matter
-        T2 = make_t2(max(thrA, lbA), max(thrB, lbB));
-    };
     // One wavefront step of this lane; u = (t-1) % 4 is a compile-time constant in every caller.
     // CHECKED = false in the steady phase, where every owning lane has a row that exists in BOTH tasks: no range test,
     // and the four unrolled steps need no register shuffling between them.
@@ -257,7 +263,7 @@ k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLe
         const int i = t - lane;
         const uint2 *rowQ = rowP++;
         uint32_t code[K] = {};
-        const bool compute = mine && (!CHECKED || (i >= 1 && i <= maxN));
+        const bool compute = !CHECKED || (mine && i >= 1 && i <= maxN);
         if (compute) {
             uint32_t t2 = fma_add(rH, keepLeft, leftH0);                          // H left + open
             uint32_t Il = fma_add(rI, keepLeft, leftI0);
@@ -288,7 +294,13 @@ k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLe
                 for (int k = 1; k + 1 < K; k += 2) cm = __vimax3_u16x2(cm, HO[k], HO[k + 1]);
                 if (K % 2 == 0) cm = __vmaxu2(cm, HO[K - 1]);
                 const uint32_t q = cm + T2;
-                if (q & 0x80008000u) exact_path(i, q);
+                if (q & 0x80008000u) {
+                    uint32_t ho[K], z;                                             // a copy: HO itself must stay in registers, and the
+                    asm volatile("mov.u32 %0, 0;" : "=r"(z));                      // copy must not be hoisted out of this rare branch
+#pragma unroll
+                    for (int k = 0; k < K; ++k) ho[k] = HO[k] + z;
+                    T2 = dp_track_cells<K>(&tr, ho, q, i, j0, (int)O4v);
+                }
             }
 #pragma unroll
             for (int kk = 0; kk < REM; ++kk) {
@@ -308,7 +320,7 @@ k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLe
         }
         // trace words: byte c of word w holds column 4w+c of row i-(3-c), so that a diagonal run of four cells shares one word.
         // Low halves -> task A, high halves -> task B.  Rows maxN+1..maxN+3 only flush the older bytes.
-        if (mine && (!CHECKED || (i >= 1 && i <= maxN + 3))) {
+        if (!CHECKED || (mine && i >= 1 && i <= maxN + 3)) {
 #pragma unroll
             for (int w = 0; w < WORDS; ++w) {
                 const uint32_t c0 = hist[w][0][(u + 1) & 3], c1 = hist[w][1][(u + 2) & 3], c2 = hist[w][2][(u + 3) & 3], c3 = code[4 * w + 3];
@@ -338,29 +350,31 @@ k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLe
         step(t + 3, std::integral_constant<int, 3>(), checked);
         flush(t + 3);
         pw += 4 * WB;
+
     };
     if (maxL > 0) {
         const int steadyN = (NA > 0 && NB > 0) ? min(NA, NB) : maxN;    // rows present in every live task of the pair
         const int stepsR = (steps + 3 + 3) & ~3;                        // + 3 flush steps, whole groups
-        const int rampEnd = min((lastLane + 3) & ~3, stepsR);           // from here on every owning lane has started
+        const int rampEnd = min(32, stepsR);                            // from here on every lane (owning or not) has a row >= 1
         const int steadyEnd = max(steadyN & ~3, rampEnd);               // up to here no owning lane has run out of rows
-        int t = 1;
+        // ramp-up and ramp-down share the CHECKED code, the steady groups in between run the straight-line variant
 #pragma unroll 1
-        for (; t <= rampEnd; t += 4) group(t, std::true_type());
+        for (int t = 1; t <= stepsR; ) {
+            if (t > rampEnd && t <= steadyEnd) {
 #pragma unroll 1
-        for (; t <= steadyEnd; t += 4) group(t, std::false_type());
-#pragma unroll 1
-        for (; t <= stepsR; t += 4) group(t, std::true_type());
+                for (; t <= steadyEnd; t += 4) group(t, std::false_type());
+            } else { group(t, std::true_type()); t += 4; }
+        }
     }
     __syncwarp();
     // ---- winner per task: best value over the lanes, then smallest (row, col); ties summed ----
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-        const int lb = half ? lbB : lbA, thr = half ? thrB : thrA;
+        const int lb = tr.lb[half], thr = tr.thr[half];
         int gbest = lb;
 #pragma unroll
         for (int dlt = 16; dlt; dlt >>= 1) gbest = max(gbest, __shfl_xor_sync(0xffffffffu, gbest, dlt));
-        uint32_t key = lb == gbest ? (half ? keyB : keyA) : 0xffffffffu, c2 = lb == gbest ? (half ? cntB : cntA) : 0u;
+        uint32_t key = lb == gbest ? tr.key[half] : 0xffffffffu, c2 = lb == gbest ? tr.cnt[half] : 0u;
 #pragma unroll
         for (int dlt = 16; dlt; dlt >>= 1) { key = min(key, __shfl_xor_sync(0xffffffffu, key, dlt)); c2 += __shfl_xor_sync(0xffffffffu, c2, dlt); }
         if (lane == 0 && (half == 0 || hasB)) {
@@ -687,8 +701,18 @@ int mpd_run_explicit(mp_context *ctx, const uint8_t *dRef, const uint32_t *dRefL
                      const uint8_t *dRead, const uint32_t *dReadLens, uint32_t maxReadLen, const int32_t *dCutoffs,
                      uint32_t nTasks, const MpDpParams &P, MpDpOut *dOuts, uint8_t *dPatterns, uint32_t patStride)
 {
+    // The SemiGlobalAligner seam carries no seed diagonal: the fill kernel's threshold starts at the cutoff.  MP_DP_TEST_HINT=<d> (parity
+    // tests) hands every task the same diagonal hint instead, right or wrong -- results must not depend on it.
+    const int16_t *dHints = nullptr;
+    if (const char *e = getenv("MP_DP_TEST_HINT")) {
+        std::vector<int16_t> h(nTasks, (int16_t)atoi(e));
+        if (ctx->dHintTest.reserve((size_t)nTasks * 2)) return MP_ERR_CUDA;
+        MP_CUDA(cudaMemcpyAsync(ctx->dHintTest.p, h.data(), (size_t)nTasks * 2, cudaMemcpyHostToDevice, ctx->stream));
+        MP_CUDA(cudaStreamSynchronize(ctx->stream));
+        dHints = ctx->dHintTest.as<int16_t>();
+    }
     return launch_dp(ctx, dRef, dRefLens, maxRefLen, dRead, dReadLens, maxReadLen, dCutoffs, nTasks, maxRefLen, maxReadLen, P,
-                     dOuts, dPatterns, patStride, nullptr);
+                     dOuts, dPatterns, patStride, dHints);
 }
 
 int mpd_run_tasks(mp_context *ctx, const MpDpTask *dTasks, uint32_t nTasks, uint32_t maxRefLen, uint32_t maxReadLen,

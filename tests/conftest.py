@@ -58,6 +58,71 @@ def small_ref(workdir):
     return dict(fasta=fa, prefix=fa + ".index", seq=seq, bounds=bounds)
 
 
+@pytest.fixture(scope="session")
+def second_ref(workdir, small_ref):
+    """A second index for the NT-chunk chaining tests (runMegaPath.sh:184-226): three quarters of its sequences are diverged
+    copies (1-3 % substitutions) of sequences of `small_ref`, the rest is unrelated, so that reads placed on `small_ref` hit it
+    with scores above, equal to and below their first-chunk scores.  Built by the reference's 2bwt-builder."""
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    from tools import synth
+    rng = np.random.default_rng(1234)
+    seq, bounds = small_ref["seq"], small_ref["bounds"]
+    parts = []
+    for i in range(len(bounds) - 1):
+        s = seq[bounds[i]:bounds[i + 1]].copy()
+        if i % 4 == 3:
+            s = synth.ALPHA[rng.integers(0, 4, size=len(s))]
+        else:
+            rate = (0.0, 0.01, 0.03)[i % 3]
+            m = rng.random(len(s)) < rate
+            s[m] = synth.ALPHA[rng.integers(0, 4, size=int(m.sum()))]
+        parts.append(s)
+    seq2 = np.concatenate(parts[::-1])
+    b2 = np.concatenate([[0], np.cumsum([len(x) for x in parts[::-1]])]).astype(np.int64)
+    d = os.path.join(workdir, "second")
+    os.makedirs(d, exist_ok=True)
+    fa = os.path.join(d, "ref2.fa")
+    with open(fa, "wb") as f:
+        for i in range(len(b2) - 1):
+            f.write(b">chunk1_%d second index\n" % (i + 1) + seq2[b2[i]:b2[i + 1]].tobytes() + b"\n")
+    shutil.copy(os.path.join(REF_DIR, "2bwt-builder.ini"), os.path.join(d, "2bwt-builder.ini"))
+    subprocess.check_call([os.path.join(REF_DIR, "2bwt-builder"), fa], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return dict(fasta=fa, prefix=fa + ".index", seq=seq2, bounds=b2)
+
+
+def deinterleave(stdout_fastq, prefix, comment_edit=None):
+    """cc/deinterleave.cpp in a few lines: the interleaved `soap4 -F` output -> <prefix>_1.fq / <prefix>_2.fq with the comment
+    kept (kseq: name up to the first white space, comment after it; written back as "@name/<mate> comment").
+    comment_edit(pair_index, mate, comment) may rewrite a comment (IGNORE / hand-made cases)."""
+    lines = stdout_fastq.split(b"\n")
+    recs = [lines[i:i + 4] for i in range(0, len(lines) - 3, 4)]
+    out = [open(prefix + "_1.fq", "wb"), open(prefix + "_2.fq", "wb")]
+    for k in range(0, len(recs) - 1, 2):
+        for mate in (0, 1):
+            hdr, sq, _, ql = recs[k + mate]
+            parts = hdr[1:].split(None, 1)
+            name, comm = parts[0], (parts[1] if len(parts) > 1 else b"")
+            if name.endswith(b"/1") or name.endswith(b"/2"):
+                name = name[:-2]
+            if comment_edit:
+                comm = comment_edit(k // 2, mate, comm)
+            out[mate].write(b"@" + name + b"/%d" % (mate + 1) + (b" " + comm if comm else b"") + b"\n" + sq + b"\n+\n" + ql + b"\n")
+    for f in out:
+        f.close()
+    return prefix + "_1.fq", prefix + "_2.fq"
+
+
+def run_ref_raw(workdir, index_prefix, fq1, fq2, out_name, max_len_opt, ini, flags, threads=3, insert_high=750):
+    """The reference binary with exactly `flags` (no implied -F / -nc) -> stdout bytes."""
+    cmd = [os.path.join(REF_DIR, "soap4"), "pair", index_prefix, fq1, fq2, "-o", os.path.join(workdir, out_name),
+           "-C", os.path.join(REF_DIR, ini), "-L", str(max_len_opt), "-T", str(threads), "-u", str(insert_high)] + list(flags)
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, cwd=workdir, timeout=600)
+    if p.returncode != 0:
+        raise RuntimeError("reference soap4 failed: " + p.stderr.decode(errors="replace")[-1500:])
+    return p.stdout
+
+
 def make_reads(workdir, small_ref, name, pairs, rlen, seed, **kw):
     from tools import synth
     r1, r2 = synth.make_pairs(small_ref["seq"], small_ref["bounds"], pairs, rlen, seed, **kw)

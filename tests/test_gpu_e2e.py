@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import make_reads, run_ref_soap4, run_our_soap4, canon_fastq, needs_ref
+from conftest import make_reads, run_ref_soap4, run_our_soap4, canon_fastq, needs_ref, deinterleave, run_ref_raw
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -154,3 +154,72 @@ def test_e2e_empty_input(workdir, small_ref):
     open(fq1, "wb").close()
     open(fq2, "wb").close()
     assert run_our_soap4(workdir, small_ref["prefix"], fq1, fq2, "emptyour", 151) == b""
+
+
+# ---- header comment chaining: every NT chunk after the first runs WITHOUT -nc (runMegaPath.sh:184-226) and merges the
+#      SCORE: list of the previous chunk into its own (BGS-IO.cpp:1348-1371, 1384-1446, 1966-2091) ----
+def _edit_comments(k, mate, comm):
+    if k % 19 == 3:
+        return b"IGNORE"                         # passes through untouched (BGS-IO.cpp:1399-1401)
+    if k % 23 == 5 and mate == 1:
+        return b"SCORE:0;"                        # an unaligned read of the previous chunk
+    if k % 29 == 7:
+        return b"SCORE:400;400,made_up_hit;"      # better than anything this chunk can find: must survive, and cap -top
+    if k % 31 == 11 and mate == 0:
+        return b""                                # no comment at all
+    return comm
+
+
+@needs_ref
+@pytest.mark.parametrize("mode", ["F", "P", "Fb"])
+def test_e2e_chained_comments_match_reference(workdir, small_ref, second_ref, mode):
+    import glob
+    from conftest import canon_bam
+    fq1, fq2 = make_reads(workdir, small_ref, "chain", 2500, 150, seed=77, model="divergent", one_random=0.10, unalignable=0.04)
+    # chunk 0: -nc; the reference's output (== ours, test_e2e_stdout_matches_reference) feeds chunk 1 of both programs
+    first = run_ref_raw(workdir, small_ref["prefix"], fq1, fq2, "chain0", 151, "soap4-nt2.ini", ["-F", "-nc", "-top", "95"])
+    assert first.count(b"SCORE:") > 4000
+    in1, in2 = deinterleave(first, os.path.join(workdir, "chain_in"), _edit_comments)
+    flags = {"F": ["-F", "-top", "95"], "P": ["-P", "-top", "95"], "Fb": ["-b", "-F", "-top", "95"]}[mode]
+    pre_r, pre_o = os.path.join(workdir, "chain1ref_" + mode), os.path.join(workdir, "chain1our_" + mode)
+    for f in glob.glob(pre_r + ".*") + glob.glob(pre_o + ".*"):
+        if os.path.isfile(f):
+            os.remove(f)
+    want = canon_fastq(run_ref_raw(workdir, second_ref["prefix"], in1, in2, "chain1ref_" + mode, 151, "soap4-nt2.ini", flags))
+    got = canon_fastq(run_our_soap4(workdir, second_ref["prefix"], in1, in2, "chain1our_" + mode, 151, ini="soap4-nt2.ini", extra=flags))
+    assert want.count(b"chunk1_") > 1000 and want.count(b"seq") > 1000 and want.count(b"IGNORE") > 100 and b"made_up_hit" in want
+    assert got == want, first_diff(got, want)
+    if mode == "Fb":
+        files = lambda pre: [pre + ".dpout.1", pre + ".unpair"] + sorted(glob.glob(pre + ".gout.*"))
+        (hn_r, recs_r), (hn_o, recs_o) = canon_bam(files(pre_r)), canon_bam(files(pre_o))
+        assert hn_r == hn_o and len(recs_r) == len(recs_o)
+        for a, b in zip(recs_o, recs_r):
+            assert a == b, (a, b)
+
+
+@needs_ref
+@pytest.mark.parametrize("lopt", [76, 121, 201])
+def test_e2e_max_read_length_sweep(workdir, small_ref, lopt):
+    """-L sweep (BASELINE config 5): reads of exactly L-1 bases and mixed shorter ones, margins 25 / 30, K = 5 and 8 column strips"""
+    rlen = lopt - 1
+    fq1, fq2 = make_reads(workdir, small_ref, "sweep%d" % lopt, 1500 if lopt < 200 else 700, rlen, seed=lopt,
+                          model="divergent", one_random=0.08, unalignable=0.03, varlen=(lopt == 121))
+    ref_out, _ = run_ref_soap4(workdir, small_ref["prefix"], fq1, fq2, "sweepref%d" % lopt, lopt, dump=False, threads=4)
+    want = canon_fastq(open(ref_out, "rb").read())
+    got = canon_fastq(run_our_soap4(workdir, small_ref["prefix"], fq1, fq2, "sweepour%d" % lopt, lopt))
+    assert len(want) > 1000
+    assert got == want, first_diff(got, want)
+
+
+@needs_ref
+def test_e2e_threads_and_contexts(workdir, small_ref, monkeypatch):
+    """-T 7 and two contexts on one GPU (MP_CONTEXTS_PER_GPU=2) over several small batches (MP_BATCH_READS) give the single-context
+    output: batches alternate between contexts that share the resident index (mp_clone)."""
+    fq1, fq2 = make_reads(workdir, small_ref, "ctxs", 6000, 100, seed=91, model="divergent", one_random=0.08, unalignable=0.03)
+    ref_out, _ = run_ref_soap4(workdir, small_ref["prefix"], fq1, fq2, "ctxsref", 101, dump=False, threads=4)
+    want = canon_fastq(open(ref_out, "rb").read())
+    monkeypatch.setenv("MP_BATCH_READS", "2048")
+    for nctx in ("1", "2"):
+        monkeypatch.setenv("MP_CONTEXTS_PER_GPU", nctx)
+        got = canon_fastq(run_our_soap4(workdir, small_ref["prefix"], fq1, fq2, "ctxsour" + nctx, 101, extra=("-F", "-nc", "-T", "7")))
+        assert got == want, (nctx, first_diff(got, want))

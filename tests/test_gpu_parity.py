@@ -195,3 +195,98 @@ def test_gpu_dp_exact_occurrences(ctx, clips):
         assert got == want, (t, got, want)
         full += want[0] == int(rl[t])
     assert full > n // 2
+
+
+@pytest.mark.parametrize("hint", ["0", "17", "30", "95", "400"])
+def test_gpu_dp_result_does_not_depend_on_the_diagonal_hint(ctx, hint, monkeypatch):
+    """k_dp_fill only books cells that reach max(cutoff, lower bound from the task's hinted diagonal).  Whatever the hint says --
+    the true diagonal, a wrong one, one outside the window -- score, tie count, hit offset and pattern must equal the oracle's."""
+    import megapath_b200 as mp
+    monkeypatch.setenv("MP_DP_TEST_HINT", hint)
+    for maxdna, maxread, fixed, clips in (DP_SHAPES[0], DP_SHAPES[-1]):
+        rng = np.random.default_rng(4242 + int(hint))
+        n = 256
+        refs, dl, reads, rl = random_dp_tasks(rng, n, maxdna, maxread, fixed)
+        cut = np.array([po.dp_cutoff(int(x)) for x in rl], dtype=np.int32)
+        sc, hl, mc, pats = ctx.dp_batch(mp.pack_dp_interleaved(refs, dl, maxdna), dl, maxdna, mp.pack_dp_interleaved(reads, rl, maxread), rl, maxread,
+                                        cut, clips[0], clips[1])
+        for t in range(n):
+            want = po.dp(refs[t, :dl[t]], reads[t, :rl[t]], clips[0], clips[1], -2, -3, int(cut[t]))
+            got = (int(sc[t]), int(hl[t]), int(mc[t]), po.pattern_bytes(pats[t]) if sc[t] >= cut[t] else b"")
+            assert got == want, (hint, t, got, want)
+    # exact repeats: many cells tie with the best score, every one of them has to be counted
+    refs, dl, reads, rl = exact_occurrence_tasks(np.random.default_rng(7), 128, 220, 152)
+    monkeypatch.setenv("MP_DP_EXACT", "0")          # read once per process: only effective if this test runs first; harmless otherwise
+    cut = np.array([po.dp_cutoff(int(x)) for x in rl], dtype=np.int32)
+    sc, hl, mc, pats = ctx.dp_batch(mp.pack_dp_interleaved(refs, dl, 220), dl, 220, mp.pack_dp_interleaved(reads, rl, 152), rl, 152, cut, 130, 130)
+    for t in range(128):
+        want = po.dp(refs[t, :dl[t]], reads[t, :rl[t]], 130, 130, -2, -3, int(cut[t]))
+        got = (int(sc[t]), int(hl[t]), int(mc[t]), po.pattern_bytes(pats[t]) if sc[t] >= cut[t] else b"")
+        assert got == want, (hint, t, got, want)
+
+
+@pytest.mark.parametrize("mm,go", [(-3, -2), (-4, -6), (-2, -6), (-3, -3), (-4, -3)])
+def test_gpu_dp_other_score_parameters(ctx, mm, go):
+    """run-time score parameters (the generic kernel instantiation; CPU_DP.cpp:199-208 allows -4 <= mismatch, -6 <= open; mismatch = -1 divides by zero at :310)."""
+    import megapath_b200 as mp
+    rng = np.random.default_rng(100 - mm * 7 - go)
+    n, maxdna, maxread = 160, 220, 152
+    refs, dl, reads, rl = random_dp_tasks(rng, n, maxdna, maxread, False)
+    cut = np.array([po.dp_cutoff(int(x)) for x in rl], dtype=np.int32)
+    sc, hl, mc, pats = ctx.dp_batch(mp.pack_dp_interleaved(refs, dl, maxdna), dl, maxdna, mp.pack_dp_interleaved(reads, rl, maxread), rl, maxread,
+                                    cut, 130, 130, mismatch=mm, gap_open=go)
+    for t in range(n):
+        want = po.dp(refs[t, :dl[t]], reads[t, :rl[t]], 130, 130, mm, go, int(cut[t]))
+        got = (int(sc[t]), int(hl[t]), int(mc[t]), po.pattern_bytes(pats[t]) if sc[t] >= cut[t] else b"")
+        assert got == want, (mm, go, t, got, want)
+
+
+def test_gpu_sampled_sa_path(workdir, small_ref, monkeypatch):
+    """MP_DENSE_SA=0: only the file's 1/16 SA samples are resident and every SA lookup on the hot path is an LF walk (the only mode
+    possible for texts that do not fit a dense 32-bit array).  Seeds, candidates and stage-S1 results must not change."""
+    import megapath_b200 as mp
+    monkeypatch.setenv("MP_DENSE_SA", "0")
+    c = mp.Context(0)
+    try:
+        c.index_load(small_ref["prefix"])
+        ix = po.Index(small_ref["prefix"])
+        rng = np.random.default_rng(5)
+        sidx = np.concatenate([rng.integers(0, ix.n + 1, size=20000), [0, ix.inverse_sa0, ix.n]]).astype(np.uint64)
+        assert (c.sa(sidx) == ix.sa(sidx)).all()
+        for name, rlen, lopt, kw in READ_SETS[:3]:
+            fq1, fq2 = make_reads(workdir, small_ref, "sa_" + name, 800, rlen, seed=77, **kw)
+            reads, lens = load_pairs(fq1, fq2, trunc=lopt - 1)
+            rp, mpos = ix.seed_pairs(reads, lens, po.mmp_params())
+            insert_low = max(1, ref_detected_len(lens[0::2]), ref_detected_len(lens[1::2]))
+            cands = po.pair_candidates(rp, mpos, lens, insert_low, 750)
+            q, wpq = mp.pack_queries(reads, lens, lopt)
+            c.batch_upload(q, lens, wpq)
+            P = mp.default_params(insert_low=insert_low, insert_high=750, max_read_length=lopt)
+            c.seed_pairs(P)
+            grp, gmp = c.download_seedpos()
+            assert grp.tobytes() == rp.tobytes() and gmp.tobytes() == mpos.tobytes(), name
+            assert c.download_candidates().tobytes() == cands.tobytes(), name
+            want, _ = po.deep_dp(ix, reads, lens, cands, insert_low, 750, lopt)
+            res = c.align_pairs(P)
+            assert len(res["pairs"]) == len(want)
+            for g, w in zip(res["pairs"], want):
+                for f in ("readID", "algnmt_1", "algnmt_2", "score_1", "score_2", "num_sameScore_1", "num_sameScore_2", "insertSize"):
+                    assert int(g[f]) == int(w[f]), (name, f, g, w)
+            assert res["n_lf"] > 0               # the walks really happened
+    finally:
+        c.close()
+
+
+def test_gpu_abi_rejects_overlong_reads(ctx):
+    """A read that does not fit its 2-bit row, or is not shorter than maxReadLength, is refused at the C-ABI instead of corrupting
+    neighbouring DP tasks (the reference truncates at parse time, QueryParser.cpp:188)."""
+    import megapath_b200 as mp
+    reads = np.zeros((2, 200), dtype=np.uint8)
+    lens = np.array([200, 100], dtype=np.uint32)
+    q, wpq = mp.pack_queries(reads, np.array([160, 100], dtype=np.uint32), 151)
+    with pytest.raises(mp.MegapathError):
+        ctx.batch_upload(q, lens, wpq)                       # 200 bases > 16 * wpq
+    lens = np.array([155, 100], dtype=np.uint32)
+    ctx.batch_upload(q, lens, wpq)
+    with pytest.raises(mp.MegapathError):
+        ctx.seed_pairs(mp.default_params(insert_low=150, insert_high=750, max_read_length=151))

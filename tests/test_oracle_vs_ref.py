@@ -123,6 +123,21 @@ def test_dp_exact_occurrences_match_reference_callDP(clips):
 
 
 @needs_ref
+@pytest.mark.parametrize("mm,go", [(-3, -2), (-4, -6), (-2, -6), (-3, -3), (-4, -3)])
+def test_dp_other_score_parameters_match_reference_callDP(mm, go):
+    """the restatement against the reference's own callDP for the score range it accepts (CPU_DP.cpp:199-208)"""
+    rng = np.random.default_rng(100 - mm * 7 - go)
+    n, maxdna, maxread = 160, 220, 152
+    refs, dl, reads, rl = random_dp_tasks(rng, n, maxdna, maxread, False)
+    sc, hl, mc, pats = po.ref_dp(refs, dl, reads, rl, maxdna, maxread, 130, 130, mm, go)
+    for t in range(n):
+        co = po.dp_cutoff(int(rl[t]))
+        got = po.dp(refs[t, :dl[t]], reads[t, :rl[t]], 130, 130, mm, go, co)
+        want = (int(sc[t]), int(hl[t]), int(mc[t]), po.pattern_bytes(pats[t]) if sc[t] >= co else b"")
+        assert got == want, (mm, go, t, got, want)
+
+
+@needs_ref
 @pytest.mark.parametrize("maxdna,maxread,fixed,clips", DP_SHAPES)
 def test_dp_matches_reference_callDP(maxdna, maxread, fixed, clips):
     rng = np.random.default_rng(maxdna * 7 + maxread + clips[0])
