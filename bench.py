@@ -31,10 +31,25 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-READ_LEN = 150
-MAX_READ_LEN_OPT = 151          # soap4 -L 151: reads are truncated to L-1 = 150 (QueryParser.cpp:188)
 INSERT_LO, INSERT_HI = 250, 500
 INSERT_HIGH_OPT = 750           # soap4 -u 750
+
+# BASELINE.json configs.  `-L` is read length + 1: the reference truncates reads to L - 1 (QueryParser.cpp:188).
+CONFIGS = {
+    # cfg1: the reference's own CPU-runnable case
+    "cfg1": dict(ref_mbp=50.0, nseq=12, read_len=150, model="subs", unalignable=0.0, one_random=0.0, ini="soap4.ini",
+                 about="150bp pairs (substitutions per read from {0,0,0,1,1,2}) vs a 50 Mbp synthetic reference (12 seqs), soap4.ini -L 151 -u 750"),
+    # cfg2: human-filtering stage; the configuration the metric is quoted on
+    "cfg2": dict(ref_mbp=3100.0, nseq=24, read_len=150, model="subs", unalignable=0.01, one_random=0.01, ini="soap4.ini",
+                 about="150bp pairs vs a 3.1 Gbp human-sized synthetic reference (24 seqs), soap4.ini -L 151 -u 750; 1% unalignable pairs, 1% one-mate-random"),
+    # cfg4: DP-heavy: most reads carry an indel, 5 % of the pairs have one random mate (single-end DP + mate rescue with 752-wide tables)
+    "cfg4": dict(ref_mbp=3100.0, nseq=24, read_len=150, model="divergent", unalignable=0.0, one_random=0.05, ini="soap4.ini",
+                 about="DP-heavy 150bp pairs (4% substitutions, 0.5% 1-3bp deletions, 0.5% 1-3bp insertions per base; 5% of the pairs with one random mate) "
+                       "vs the 3.1 Gbp synthetic reference, soap4.ini -L 151 -u 750"),
+    # cfg5: MegaPath-Amplicon-style read length
+    "cfg5": dict(ref_mbp=100.0, nseq=50, read_len=250, model="subs", unalignable=0.01, one_random=0.01, ini="soap4.ini",
+                 about="250bp pairs vs a 100 Mbp synthetic bacterial panel (50 seqs), soap4.ini -L 251 -u 750; 1% unalignable pairs, 1% one-mate-random"),
+}
 
 
 def parse_args():
@@ -43,17 +58,32 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ref-mbp", type=float, default=float(os.environ.get("MP_BENCH_REF_MBP", "3100")))
+    ap.add_argument("--config", default=os.environ.get("MP_BENCH_CONFIG", "cfg2"), choices=sorted(CONFIGS))
+    ap.add_argument("--ref-mbp", type=float, default=float(os.environ.get("MP_BENCH_REF_MBP", "0")), help="override the config's reference size")
+    ap.add_argument("--read-len", type=int, default=0, help="override the config's read length (-L sweep)")
     ap.add_argument("--pairs-per-step", type=int, default=int(os.environ.get("MP_BENCH_PAIRS", str(1 << 20))))
     ap.add_argument("--cpu-sample-pairs", type=int, default=int(os.environ.get("MP_BENCH_CPU_PAIRS", "200000")))
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cli-pairs", type=int, default=int(os.environ.get("MP_BENCH_CLI_PAIRS", str(3 << 20))),
+                    help="pairs in the FASTQ files of the e2e_cli leg (bin/soap4, FASTQ in -> annotated FASTQ out); 0 = skip")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs (reference sample, parity at scale, e2e_cli)")
     ap.add_argument("--contexts", type=int, default=int(os.environ.get("MP_BENCH_CONTEXTS", "3")),
                     help="contexts (host thread + stream each) per GPU sharing one resident index; batches alternate between them")
     ap.add_argument("--workdir", default=os.environ.get("MP_BENCH_DIR", "/tmp/mpbench"))
+    ap.add_argument("--prepare", action="store_true",
+                    help="build what the CPU legs need and exit: the workload's index files (GPU builder, reference file formats) and the "
+                         "FASTQ samples.  `--impl reference` runs this in a child process, so that the process which times the reference "
+                         "never loads this repo's library")
     ap.add_argument("--profile-step", action="store_true",
                     help="profiling aid (ncu --profile-from-start off): after the warm-up run ONE step on one context between "
                          "cudaProfilerStart/Stop and exit; prints no bench value")
-    return ap.parse_args()
+    a = ap.parse_args()
+    a.cfg = dict(CONFIGS[a.config])
+    if a.ref_mbp > 0:
+        a.cfg["ref_mbp"] = a.ref_mbp
+    if a.read_len > 0:
+        a.cfg["read_len"] = a.read_len
+    a.read_len, a.lopt = a.cfg["read_len"], a.cfg["read_len"] + 1
+    return a
 
 
 # ------------------------------------------------------------------------------------------------
@@ -79,38 +109,67 @@ def gen_ref_codes(n, seed, device):
     return out
 
 
-def gen_batch(ref_codes, bounds_t, npairs, seed, unalignable=0.01, one_random=0.01):
-    """-> (codes (2*npairs, READ_LEN) uint8 on device, mate1 = even rows)."""
+def gen_batch(ref_codes, bounds_t, npairs, seed, read_len=150, model="subs", unalignable=0.01, one_random=0.01):
+    """-> (codes (2*npairs, read_len) uint8 on device, mate1 = even rows).
+    model "subs": per-read substitutions drawn from {0,0,0,1,1,2}; "divergent": per base 4 % substitutions, 0.5 % deletions
+    and 0.5 % insertions of 1-3 bases."""
     import torch
     dev = ref_codes.device
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
-    L = READ_LEN
+    L = read_len
+    W = L + 24 if model == "divergent" else L            # source window: room for deleted bases
     nseq = bounds_t.numel() - 1
-    isz = torch.randint(INSERT_LO, INSERT_HI, (npairs,), device=dev, generator=g)
+    lo_i, hi_i = max(INSERT_LO, W + 10), max(INSERT_HI, W + 60)
+    isz = torch.randint(lo_i, hi_i, (npairs,), device=dev, generator=g)
     sid = torch.randint(0, nseq, (npairs,), device=dev, generator=g)
     lo = bounds_t[sid]
     hi = torch.maximum(bounds_t[sid + 1] - isz, lo + 1)
     start = lo + (torch.rand(npairs, device=dev, generator=g, dtype=torch.float64) * (hi - lo).double()).long()
-    start = torch.clamp(start, 0, ref_codes.numel() - INSERT_HI - 1)
-    ar = torch.arange(L, device=dev)
-    out = torch.empty((2 * npairs, L), dtype=torch.uint8, device=dev)
+    start = torch.clamp(start, 0, ref_codes.numel() - hi_i - 1)
+    ar = torch.arange(W, device=dev)
+    src = torch.empty((2 * npairs, W), dtype=torch.uint8, device=dev)
     CH = 1 << 18
     for o in range(0, npairs, CH):
-        s = start[o:o + CH]
+        s_ = start[o:o + CH]
         z = isz[o:o + CH]
-        a = ref_codes[s[:, None] + ar[None, :]]
-        b = 3 - ref_codes[(s + z)[:, None] - 1 - ar[None, :]]
-        out[2 * o:2 * (o + len(s)):2] = a
-        out[2 * o + 1:2 * (o + len(s)):2] = b
+        src[2 * o:2 * (o + len(s_)):2] = ref_codes[s_[:, None] + ar[None, :]]
+        src[2 * o + 1:2 * (o + len(s_)):2] = 3 - ref_codes[(s_ + z)[:, None] - 1 - ar[None, :]]
     nreads = 2 * npairs
-    nsub = torch.tensor([0, 0, 0, 1, 1, 2], device=dev)[torch.randint(0, 6, (nreads,), device=dev, generator=g)]
-    rows = torch.arange(nreads, device=dev)
-    for k in (1, 2):
-        sel = rows[nsub >= k]
-        cols = torch.randint(0, L, (sel.numel(),), device=dev, generator=g)
-        delta = torch.randint(1, 4, (sel.numel(),), device=dev, generator=g).to(torch.uint8)
-        out[sel, cols] = (out[sel, cols] + delta) & 3
+    if model == "divergent":
+        out = torch.empty((nreads, L), dtype=torch.uint8, device=dev)
+        for o in range(0, nreads, CH):
+            blk = src[o:o + CH]
+            n = blk.shape[0]
+            u = torch.rand((n, W), device=dev, generator=g)
+            sub = u < 0.04
+            dele = (u >= 0.04) & (u < 0.045)
+            ins = (u >= 0.045) & (u < 0.05)
+            k = torch.randint(1, 4, (n, W), device=dev, generator=g)
+            # a deletion event removes k source bases: mark the following k-1 as deleted too
+            dmask = dele.clone()
+            dmask[:, 1:] |= dele[:, :-1] & (k[:, :-1] >= 2)
+            dmask[:, 2:] |= dele[:, :-2] & (k[:, :-2] >= 3)
+            emit = (~dmask).long() + torch.where(ins & ~dmask, k, torch.zeros_like(k))      # bases written for this source base
+            end = torch.cumsum(emit, dim=1)                                                     # kept base lands at end - 1
+            delta = torch.randint(1, 4, (n, W), device=dev, generator=g).to(torch.uint8)
+            base = torch.where(sub, (blk + delta) & 3, blk)
+            o_blk = torch.randint(0, 4, (n, L), dtype=torch.uint8, device=dev, generator=g)    # inserted bases are random
+            pos = end - 1
+            ok = (~dmask) & (pos < L)
+            rows = torch.arange(n, device=dev)[:, None].expand(n, W)
+            o_blk[rows[ok], pos[ok]] = base[ok]
+            out[o:o + n] = o_blk
+        del src
+    else:
+        out = src
+        nsub = torch.tensor([0, 0, 0, 1, 1, 2], device=dev)[torch.randint(0, 6, (nreads,), device=dev, generator=g)]
+        rows = torch.arange(nreads, device=dev)
+        for k in (1, 2):
+            sel = rows[nsub >= k]
+            cols = torch.randint(0, L, (sel.numel(),), device=dev, generator=g)
+            delta = torch.randint(1, 4, (sel.numel(),), device=dev, generator=g).to(torch.uint8)
+            out[sel, cols] = (out[sel, cols] + delta) & 3
     u = torch.rand(npairs, device=dev, generator=g)
     ua = torch.nonzero(u < unalignable).flatten()
     if ua.numel():
@@ -142,13 +201,23 @@ def pack_queries_torch(codes, max_len_opt):
 
 
 def write_fastq_sample(path_prefix, codes_np):
+    """Interleaved rows (mate 1 = even) -> <prefix>_1.fq / _2.fq; fixed-width names so that the files are built with numpy."""
     lut = np.frombuffer(b"ACGT", dtype=np.uint8)
-    qual = b"I" * codes_np.shape[1]
+    n, L = codes_np.shape[0] // 2, codes_np.shape[1]
+    ids = np.arange(n)
+    digits = ((ids[:, None] // (10 ** np.arange(8, -1, -1))[None, :]) % 10 + 48).astype(np.uint8)       # 9 digits
     for mate in (0, 1):
-        with open("%s_%d.fq" % (path_prefix, mate + 1), "wb") as f:
-            rows = lut[codes_np[mate::2]]
-            for i in range(rows.shape[0]):
-                f.write(b"@p%d/%d\n" % (i, mate + 1) + rows[i].tobytes() + b"\n+\n" + qual + b"\n")
+        rec = np.empty((n, 2 + 9 + 3 + L + 3 + L + 1), dtype=np.uint8)
+        rec[:, 0], rec[:, 1] = ord("@"), ord("p")
+        rec[:, 2:11] = digits
+        rec[:, 11], rec[:, 12], rec[:, 13] = ord("/"), ord("1") + mate, 10
+        rec[:, 14:14 + L] = lut[codes_np[mate::2]]
+        rec[:, 14 + L], rec[:, 15 + L], rec[:, 16 + L] = 10, ord("+"), 10
+        rec[:, 17 + L:17 + 2 * L] = ord("I")
+        rec[:, 17 + 2 * L] = 10
+        with open("%s_%d.fq.tmp" % (path_prefix, mate + 1), "wb") as f:
+            f.write(rec.tobytes())
+        os.replace("%s_%d.fq.tmp" % (path_prefix, mate + 1), "%s_%d.fq" % (path_prefix, mate + 1))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -205,11 +274,16 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# workload cache: index files (reference format, so the reference binary runs on the same index)
+# workload cache: index files (reference format, so the reference binary runs on the same index) + FASTQ samples
 # ------------------------------------------------------------------------------------------------
 def workload_dir(args):
-    n = int(args.ref_mbp * 1e6)
-    return os.path.join(args.workdir, "ref%d" % n), n
+    n = int(args.cfg["ref_mbp"] * 1e6)
+    return os.path.join(args.workdir, "ref%d_%d" % (n, args.cfg["nseq"])), n
+
+
+def sample_prefix(args, tag, npairs):
+    d, _ = workload_dir(args)
+    return os.path.join(d, "sample_%s_%s_L%d_%d" % (tag, args.cfg["model"], args.read_len, npairs))
 
 
 def ensure_index(args, ctx, device, rank, world):
@@ -219,8 +293,7 @@ def ensure_index(args, ctx, device, rank, world):
     d, n = workload_dir(args)
     prefix = os.path.join(d, "ref.index")
     ready = os.path.join(d, "READY")
-    nseq = 24
-    bounds = ref_bounds(n, nseq, 42)
+    bounds = ref_bounds(n, args.cfg["nseq"], 42)
     ref_codes = gen_ref_codes(n, 42, device)
     t0 = time.time()
     if rank == 0 and not os.path.exists(ready):
@@ -235,15 +308,63 @@ def ensure_index(args, ctx, device, rank, world):
     return prefix, ref_codes, torch.from_numpy(bounds).to(device), time.time() - t0
 
 
-def run_reference_soap4(prefix, fq_prefix, out_prefix, threads):
-    """-> (align_seconds, wall_seconds, stderr text); align = the reference's own
+def ensure_samples(args, ref_codes, bounds_t, which):
+    """FASTQ files of the CPU legs, written once: "cpu" = the bounded sample the reference is timed on (and parity at scale is
+    checked on), "cli" = the larger file pair of the e2e_cli leg."""
+    for tag, npairs, seed in (("cpu", args.cpu_sample_pairs, 7_000_003), ("cli", args.cli_pairs, 9_000_011)):
+        if tag not in which or npairs <= 0:
+            continue
+        fqp = sample_prefix(args, tag, npairs)
+        if os.path.exists(fqp + "_2.fq"):
+            continue
+        CH = 1 << 19
+        parts = [gen_batch(ref_codes, bounds_t, min(CH, npairs - o), seed + o, args.read_len, args.cfg["model"],
+                           args.cfg["unalignable"], args.cfg["one_random"]).cpu().numpy() for o in range(0, npairs, CH)]
+        write_fastq_sample(fqp, np.concatenate(parts) if len(parts) > 1 else parts[0])
+
+
+def prepare(args):
+    """`bench.py --prepare`: everything the CPU legs need, built by THIS process (which loads the library); the reference arm runs
+    it as a child and then only executes oracle/_ref/soap4."""
+    import torch
+    import megapath_b200 as mp
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --prepare needs a CUDA device (GPU index builder)")
+    device = torch.device("cuda", 0)
+    ctx = mp.Context(0)
+    d, n = workload_dir(args)
+    prefix = os.path.join(d, "ref.index")
+    bounds = ref_bounds(n, args.cfg["nseq"], 42)
+    ref_codes = gen_ref_codes(n, 42, device)
+    if not os.path.exists(os.path.join(d, "READY")):
+        os.makedirs(d, exist_ok=True)
+        ctx.index_build_codes(ref_codes, bounds, prefix)
+        open(os.path.join(d, "READY"), "w").write("ok\n")
+    ctx.close()
+    ensure_samples(args, ref_codes, torch.from_numpy(bounds).to(device), ("cpu",))
+    return 0
+
+
+def soap4_cmd(exe, ini_path, prefix, fq_prefix, out_prefix, lopt, threads):
+    return [exe, "pair", prefix, fq_prefix + "_1.fq", fq_prefix + "_2.fq", "-o", out_prefix, "-C", ini_path,
+            "-L", str(lopt), "-T", str(threads), "-u", str(INSERT_HIGH_OPT), "-F", "-nc"]
+
+
+def parse_align_time(err):
+    m = re.search(r"Overall alignment time \(excl\. read loading\)\s*:\s*([0-9.]+)", err)
+    if not m:
+        raise RuntimeError("could not parse the 'Overall alignment time' line")
+    return float(m.group(1))
+
+
+def run_reference_soap4(args, prefix, fq_prefix, out_prefix, threads, keep_stdout=False):
+    """-> (align_seconds, wall_seconds, stdout path or None); align = the reference's own
     'Overall alignment time (excl. read loading)' (SOAP4.cpp:613)."""
     ref_dir = os.path.join(ROOT, "oracle", "_ref")
     exe = os.path.join(ref_dir, "soap4")
     if not os.path.exists(exe):
         raise RuntimeError("oracle/_ref/soap4 is not built (oracle/Makefile.ref)")
-    cmd = [exe, "pair", prefix, fq_prefix + "_1.fq", fq_prefix + "_2.fq", "-o", out_prefix, "-C", os.path.join(ref_dir, "soap4.ini"),
-           "-L", str(MAX_READ_LEN_OPT), "-T", str(threads), "-u", str(INSERT_HIGH_OPT), "-F", "-nc"]
+    cmd = soap4_cmd(exe, os.path.join(ref_dir, args.cfg["ini"]), prefix, fq_prefix, out_prefix, args.lopt, threads)
     t0 = time.time()
     with open(out_prefix + ".stdout.fq", "wb") as fo:
         p = subprocess.run(cmd, stdout=fo, stderr=subprocess.PIPE, cwd=os.path.dirname(out_prefix))
@@ -251,14 +372,38 @@ def run_reference_soap4(prefix, fq_prefix, out_prefix, threads):
     err = p.stderr.decode(errors="replace")
     if p.returncode != 0:
         raise RuntimeError("reference soap4 failed (%d): %s" % (p.returncode, err[-400:]))
-    m = re.search(r"Overall alignment time \(excl\. read loading\)\s*:\s*([0-9.]+)", err)
-    if not m:
-        raise RuntimeError("could not parse the reference's timing line")
-    try:
-        os.remove(out_prefix + ".stdout.fq")
-    except OSError:
-        pass
-    return float(m.group(1)), wall, err
+    if not keep_stdout:
+        try:
+            os.remove(out_prefix + ".stdout.fq")
+        except OSError:
+            pass
+    return parse_align_time(err), wall, (out_prefix + ".stdout.fq" if keep_stdout else None)
+
+
+def run_our_soap4(args, prefix, fq_prefix, out_prefix, threads, sink=None):
+    """The product's drop-in binary (megapath_b200/bin/soap4): FASTQ files in, annotated FASTQ on stdout.
+    -> (loop_seconds = its 'Overall alignment time' line, wall_seconds, stderr)"""
+    exe = os.path.join(ROOT, "megapath_b200", "bin", "soap4")
+    cmd = soap4_cmd(exe, os.path.join(ROOT, "megapath_b200", "ini", args.cfg["ini"]), prefix, fq_prefix, out_prefix, args.lopt, threads)
+    t0 = time.time()
+    with open(sink or (out_prefix + ".stdout.fq"), "wb") as fo:
+        p = subprocess.run(cmd, stdout=fo, stderr=subprocess.PIPE)
+    wall = time.time() - t0
+    err = p.stderr.decode(errors="replace")
+    if p.returncode != 0:
+        raise RuntimeError("bin/soap4 failed (%d): %s" % (p.returncode, err[-400:]))
+    return parse_align_time(err), wall, err
+
+
+def canonical_pairs(path):
+    """annotated interleaved FASTQ -> sorted list of (mate-1 record, mate-2 record): the reference's worker threads print whole pairs
+    in arbitrary order"""
+    with open(path, "rb") as f:
+        lines = f.read().split(b"\n")
+    recs = [b"\n".join(lines[i:i + 4]) for i in range(0, len(lines) - 3, 4)]
+    pairs = [(recs[i], recs[i + 1]) for i in range(0, len(recs) - 1, 2)]
+    pairs.sort()
+    return pairs
 
 
 def measured_peak():
@@ -269,7 +414,7 @@ def measured_peak():
 
 
 def ncu_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed ncu --set full summary."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the newest committed ncu --set full summary."""
     best = None
     for name in sorted(os.listdir(os.path.join(ROOT, "profiles"))) if os.path.isdir(os.path.join(ROOT, "profiles")) else []:
         if not (name.startswith("r") and "ncu_full" in name and name.endswith(".txt")):
@@ -290,19 +435,6 @@ def ncu_traffic(kernel):
     return best
 
 
-def clocks_hint():
-    try:
-        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["sm_max_mhz"])
-    except Exception:
-        return 1965.0
-
-
-def workload_name(args):
-    n = int(args.ref_mbp * 1e6)
-    return "%d x %d-pair batches of synthetic 150bp pairs (-L 151 -u 750 soap4.ini) vs %.0f Mbp synthetic reference" % (
-        1, args.pairs_per_step, n / 1e6)
-
-
 def main():
     args = parse_args()
     # stdout carries exactly one JSON line: anything libraries print while we work (e.g. NCCL's version banner) goes to stderr
@@ -310,6 +442,10 @@ def main():
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
     try:
+        if args.prepare:
+            return prepare(args)
+        if args.impl == "reference":
+            return run_reference_arm(args, saved_stdout)
         return run(args, saved_stdout)
     finally:
         sys.stdout.flush()
@@ -321,19 +457,59 @@ def emit(saved_stdout, obj):
     os.write(saved_stdout, (json.dumps(obj) + "\n").encode())
 
 
+def base_config(args, pairs_per_step):
+    return {"workload": "%s: %s; %d pairs per step" % (args.config, args.cfg["about"], pairs_per_step),
+            "name": args.config, "pairs_per_step_per_gpu": pairs_per_step, "ref_mbp": args.cfg["ref_mbp"], "read_len": args.read_len,
+            "l2": "", "parallelism": "replicated index, disjoint read batches per GPU, no data-path collective"}
+
+
+def run_reference_arm(args, saved_stdout):
+    """The reference's own CPU implementation (oracle/_ref/soap4 = /root/reference/soap4 compiled by oracle/Makefile.ref, AVX2 build),
+    all host threads, on a bounded sample of the workload.  This process executes nothing of this repo's library: the index files and
+    the FASTQ sample are produced by a child process (`bench.py --prepare`, untimed) when the box does not have them yet."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    ncores = os.cpu_count() or 1
+    d, _ = workload_dir(args)
+    prefix = os.path.join(d, "ref.index")
+    npairs = args.cpu_sample_pairs
+    fqp = sample_prefix(args, "cpu", npairs)
+    if not (os.path.exists(os.path.join(d, "READY")) and os.path.exists(fqp + "_2.fq")):
+        env = dict(os.environ)
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
+        subprocess.check_call([sys.executable, os.path.abspath(__file__), "--prepare", "--config", args.config, "--workdir", args.workdir,
+                               "--cpu-sample-pairs", str(npairs), "--ref-mbp", str(args.cfg["ref_mbp"]), "--read-len", str(args.read_len)],
+                              env=env, stdout=sys.stderr)
+    cfg = base_config(args, npairs)
+    cfg["l2"] = "n/a (CPU run)"
+    cfg["sample"] = "each step = the same bounded sample of %d pairs of the workload (the GPU arm runs %d pairs per step on the same index files)" % (
+        npairs, args.pairs_per_step)
+    vals = []
+    for i in range(args.warmup + args.steps):
+        a, w, _ = run_reference_soap4(args, prefix, fqp, os.path.join(d, "refout_ref"), ncores)
+        if i >= args.warmup:
+            vals.append(a)
+    tot_align = sum(vals)
+    value = npairs * len(vals) / tot_align
+    cb = {"value": value, "unit": "pairs/s", "cores": ncores, "kind": "reference",
+          "sample": "%d pairs per step of the same workload, oracle/_ref/soap4 -T %d (built -O3 -march=x86-64-v3: the AVX2 path, the widest the "
+                    "reference has), its own 'Overall alignment time (excl. read loading)'" % (npairs, ncores)}
+    emit(saved_stdout, {"impl": "reference", "metric": "read pairs aligned/sec", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_align / max(1, len(vals)),
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 (8-bit saturating SIMD DP, 2-bit FM-index)",
+                      "data": "synthetic", "config": cfg, "cpu_baseline": cb,
+                      "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    return 0
+
+
 def run(args, saved_stdout):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     ncores = os.cpu_count() or 1
-    cfg = {"workload": "cfg2: 150bp pairs vs %.0f Mbp synthetic reference (24 seqs), %d pairs per step, soap4.ini -L 151 -u 750; "
-                       "1%% unalignable pairs, 1%% one-mate-random" % (args.ref_mbp, args.pairs_per_step),
-           "pairs_per_step_per_gpu": args.pairs_per_step, "ref_mbp": args.ref_mbp,
-           "l2": "",
-           "parallelism": "replicated index, disjoint read batches per GPU, no data-path collective"}
-
-    if args.impl == "reference" and rank != 0:
-        return 0
+    cfg = base_config(args, args.pairs_per_step)
+    READ_LEN, MAX_READ_LEN_OPT = args.read_len, args.lopt
 
     import torch
     import megapath_b200 as mp
@@ -341,61 +517,35 @@ def run(args, saved_stdout):
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
-    if world > 1 and args.impl == "ours":
+    if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
 
     ctx = mp.Context(local)
-    prefix, ref_codes, bounds_t, t_index = ensure_index(args, ctx, device, rank, world if args.impl == "ours" else 1)
+    prefix, ref_codes, bounds_t, t_index = ensure_index(args, ctx, device, rank, world)
     info = ctx.index_info()
-    cfg["l2"] = ("inputs larger than L2: %.1f GB HBM index gathered at random; every step also writes ~40 GB of traceback tables, "
+    cfg["l2"] = ("inputs larger than L2: %.1f GB HBM index gathered at random; every step also writes tens of GB of traceback tables, "
                  "which flushes the 126 MB L2 between steps" % (info["hbmBytes"] / 1e9))
     cfg["contexts_per_gpu"] = max(1, args.contexts)
     d, _ = workload_dir(args)
-
-    sample_codes = None
-    if rank == 0 and (args.impl == "reference" or (world == 1 and not args.no_cpu_baseline)):
-        sample_codes = gen_batch(ref_codes, bounds_t, args.cpu_sample_pairs, 7_000_003).cpu().numpy()
-
-    def cpu_leg(npairs, tag):
-        fqp = os.path.join(d, "sample_%s_%d" % (tag, npairs))
-        if not os.path.exists(fqp + "_2.fq"):
-            write_fastq_sample(fqp, sample_codes[:2 * npairs])
-        align_s, wall_s, _ = run_reference_soap4(prefix, fqp, os.path.join(d, "refout_" + tag), ncores)
-        return npairs / align_s, align_s, wall_s
-
-    if args.impl == "reference":
-        npairs = args.cpu_sample_pairs
-        vals = []
-        for i in range(args.warmup + args.steps):
-            v, a, w = cpu_leg(npairs, "ref")
-            if i >= args.warmup:
-                vals.append((v, a))
-        tot_align = sum(a for _, a in vals)
-        value = npairs * len(vals) / tot_align
-        cb = {"value": value, "unit": "pairs/s", "cores": ncores, "kind": "reference",
-              "sample": "%d pairs per step of the same workload, oracle/_ref/soap4 -T %d, its own 'Overall alignment time (excl. read loading)'" % (npairs, ncores)}
-        emit(saved_stdout, {"impl": "reference", "metric": "read pairs aligned/sec", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_align / max(1, len(vals)),
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16/u8", "data": "synthetic",
-                          "config": cfg, "cpu_baseline": cb,
-                          "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-        return 0
+    cpu_legs = rank == 0 and world == 1 and not args.no_cpu_baseline
+    if cpu_legs:
+        ensure_samples(args, ref_codes, bounds_t, ("cpu", "cli"))
 
     # ---------------- our arm ----------------
-    P = mp.default_params(insert_low=READ_LEN, insert_high=INSERT_HIGH_OPT, max_read_length=MAX_READ_LEN_OPT)
+    P = mp.default_params(nt2=args.cfg["ini"] == "soap4-nt2.ini", insert_low=READ_LEN, insert_high=INSERT_HIGH_OPT, max_read_length=MAX_READ_LEN_OPT)
     nb = min(args.warmup + args.steps, 6)
     batches = []
     lens = np.full(2 * args.pairs_per_step, READ_LEN, dtype=np.uint32)
     for b in range(nb):
-        codes = gen_batch(ref_codes, bounds_t, args.pairs_per_step, 1000 + 97 * rank + b)
+        codes = gen_batch(ref_codes, bounds_t, args.pairs_per_step, 1000 + 97 * rank + b, READ_LEN, args.cfg["model"],
+                          args.cfg["unalignable"], args.cfg["one_random"])
         host, wpq = pack_queries_torch(codes, MAX_READ_LEN_OPT)
         batches.append(host)
         del codes
     del ref_codes
     torch.cuda.empty_cache()
     h2d = batches[0].numel() * 4 + lens.nbytes
-
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
@@ -493,52 +643,51 @@ def run(args, saved_stdout):
     value = total_pairs / (dev_ms_max / 1e3)
     e2e = total_pairs / (e2e_ms_max / 1e3)
 
-    peak, peak_kind = measured_peak()
+    hbm_peak, hbm_kind = measured_peak()
     # ---- roofline denominators MEASURED_PEAKS.json does not hold, measured now on this GPU ----
     try:
         gather32, gather64, dpx_peak = ctx.microbench(0), ctx.microbench(1), ctx.microbench(2)
     except Exception:
         gather32 = gather64 = dpx_peak = None
     steps = args.steps
-    n_fill_launches = max(1, acc.get("n_fill_launches", 0))
-    # dominant kernel: k_dp_fill (DP table fill).  Algorithmic bytes = one traceback byte written per DP cell.
-    # cells the fill kernel really computed: tasks whose read occurs unchanged in its window are answered by the exact-occurrence
-    # test (k_dp_exact, bit-identical results) and never reach it; dp_cells counts what the reference computes
+    # dominant kernel: k_dp_fill (DP table fill).  cells the fill kernel really computed: tasks whose read occurs unchanged in its window are
+    # answered by the exact-occurrence test (k_dp_exact, bit-identical results) and never reach it; dp_cells counts what the reference computes
     cells_filled = float(acc.get("dp_cells_filled") or acc["dp_cells"])
-    fill_bytes = cells_filled
-    fill_ach = fill_bytes / (acc["ms_fill"] / 1e3) / 1e9
     gcups_fill = cells_filled / (acc["ms_fill"] / 1e3) / 1e9
     gcups_dp = acc["dp_cells"] / ((acc["ms_fill"] + acc["ms_tb"] + acc.get("ms_exact", 0.0)) / 1e3) / 1e9
+    # DPX roofline (the DP is bounded by the integer / DPX pipe).  The affine recurrence needs FOUR packed DPX
+    # instructions per cell pair (D = add-max, I = add-max, H = max3, clip floor = max; two tasks share every 16x2 instruction), i.e. two
+    # thread-instructions per cell; the kernel itself issues 6.4 per cell pair (two more add-max for the traceback flags, 0.4 for the
+    # threshold test).  peak = the packed-16 DPX issue rate measured by mp_microbench(2) on this GPU (thread-instructions / s).
+    DPX_RECURRENCE, DPX_KERNEL = 4.0, 6.4
+    dpx_ach = gcups_fill * DPX_RECURRENCE / 2.0
     # seeding kernel: bytes it must gather = 8-byte filter probes + 16-byte LKT pairs + 64-byte occ blocks
     # (two per backward-search step that is not a text-compare step) + 4-byte SA values + 1 text byte per compare
     occ_steps = max(0.0, (acc["n_occ"] - 2.0 * acc["n_text"]) / 2.0)
     seed_bytes = 8.0 * acc["n_probe"] + 16.0 * acc["n_lkt"] + 128.0 * occ_steps + 4.0 * acc["n_sa"] + 1.0 * acc["n_text"]
-    seed_sectors = 32.0 * acc["n_probe"] + 32.0 * acc["n_lkt"] + 128.0 * occ_steps + 32.0 * acc["n_sa"] + 32.0 * acc["n_text"] / 32.0
     seed_ach = seed_bytes / (acc["ms_seed"] / 1e3) / 1e9
     traffic = ncu_traffic("k_dp_fill")
-    roof = {"kernel": "k_dp_fill<5,-2,-3> (packed 16-bit DPX table fill, the kernel with the largest share of the step)",
-            "bound": "hbm", "achieved": fill_ach, "peak": peak, "unit": "GB/s", "frac": fill_ach / peak,
-            # DRAM bytes (read + write) of ONE k_dp_fill launch from the committed ncu --set full capture; the captured launch is the
-            # first of a step: 2^18 left-leg tasks offered, about half of them answered by the exact-occurrence test, so it fills
-            # ~4.1 G cells (= algorithmic bytes) and moves 4.55 GB of writes + 1.42 GB of write-allocate reads
+    roof = {"kernel": "k_dp_fill<%d,-2,-3> (packed 16-bit DPX table fill, the kernel with the largest share of the step)" % (5 if MAX_READ_LEN_OPT <= 160 else 8 if MAX_READ_LEN_OPT <= 256 else 10),
+            "bound": "dpx", "achieved": dpx_ach, "peak": dpx_peak, "unit": "G DPX thread-instr/s", "frac": (dpx_ach / dpx_peak) if dpx_peak else None,
+            "peak_kind": "measured now (mp_microbench kind 2: packed 16-bit DPX issue rate; MEASURED_PEAKS.json holds no integer-pipe figure)",
+            "algorithmic": "%.0f packed DPX instructions per cell pair for the recurrence (D, I, H, clip floor) x cells the kernel fills / 2; cells = sum refLen*readLen "
+                           "over the tasks it is given (SURVEY 8d)" % DPX_RECURRENCE,
+            "frac_with_the_kernels_own_dpx_count": (gcups_fill * DPX_KERNEL / 2.0 / dpx_peak) if dpx_peak else None,
+            "dpx_instr_per_cell_pair": {"recurrence": DPX_RECURRENCE, "kernel": DPX_KERNEL, "source": "static: SASS of the steady loop, profiles/r02_sass_k_dp_fill_steady_loop.txt"},
+            # DRAM bytes (read + write) of ONE k_dp_fill launch from the newest committed ncu --set full capture
             "traffic": traffic["bytes_per_launch"] if traffic else None, "traffic_source": traffic["source"] if traffic else None,
-            "peak_kind": peak_kind, "algorithmic": "1 traceback byte written per DP cell the kernel computes (SURVEY 8d cells = sum refLen*readLen over the tasks it is given)",
             "ms_per_step": acc["ms_fill"] / steps,
-            "note": "integer-ALU bound, not bandwidth bound: ncu ALU pipe 90.8% busy, issue slots 79.7%, top stall math_pipe_throttle "
-                    "(profiles/r01_ncu_full_v8_cfg2.txt); per-kernel times come from a single-context pass (loop R), value/e2e from the pipelined passes",
+            "hbm_note": {"achieved_gbs": gcups_fill, "peak_gbs": hbm_peak, "peak_kind": hbm_kind, "frac": gcups_fill / hbm_peak,
+                         "algorithmic": "1 traceback byte written per DP cell the kernel computes"},
+            "note": "per-kernel times come from a single-context pass (loop R), value/e2e from the pipelined passes",
             "compute": {"gcups_fill": gcups_fill, "gcups_reference_equivalent_all_dp_kernels": gcups_dp,
                         "exact_occurrence_test": {"tasks_per_step": acc.get("dp_tasks_exact", 0) / steps, "of_tasks_per_step": acc["dp_tasks"] / steps,
                                                   "ms_per_step": acc.get("ms_exact", 0.0) / steps,
-                                                  "cells_filled_per_step": cells_filled / steps, "cells_reference_per_step": acc["dp_cells"] / steps},
-                        "dpx_peak_ginstr_s": dpx_peak, "dpx_instr_per_cell": 4.5,   # 9 packed min/max/add-max instructions per cell PAIR in the steady loop
-                        "dpx_frac": (gcups_fill * 4.5 / dpx_peak) if dpx_peak else None,
-                        # ncu smsp__inst_executed.sum of one launch x 32 lanes / (cells / 2): includes idle lanes of the wavefront ramps
-                        "warp_instr_lane_slots_per_cell_pair": 42.6,
-                        "issue_peak_gcups_at_that_instr_count": 148 * 4 * 32 * 2 * (clocks_hint() / 1e3) / 42.6},
+                                                  "cells_filled_per_step": cells_filled / steps, "cells_reference_per_step": acc["dp_cells"] / steps}},
             "seeding": {"kernel": "k_mmp", "ms_per_step": acc["ms_seed"] / steps, "bytes_gathered_gbs": seed_ach,
-                        "sector_gbs": seed_sectors / (acc["ms_seed"] / 1e3) / 1e9, "gather32_peak_gbs": gather32, "gather64_peak_gbs": gather64,
-                        "frac_of_gather32_peak": (seed_sectors / (acc["ms_seed"] / 1e3) / 1e9 / gather32) if gather32 else None,
-                        "reference_algorithm_equiv_gbs": (64.0 * acc["n_occ"] + 16.0 * acc["n_lkt"] + 8.0 * acc["n_sa"]) / (acc["ms_seed"] / 1e3) / 1e9,
+                        "gather32_peak_gbs": gather32, "gather64_peak_gbs": gather64,
+                        # every gather the kernel needs moves at least one 32-byte sector; occ blocks are 64-byte (two-sector) requests
+                        "frac_of_gather_peak_on_bytes_needed": (seed_ach / gather32) if gather32 else None,
                         "counters_per_step": {k: acc[k] / steps for k in ("n_probe", "n_lkt", "n_occ", "n_sa", "n_text", "n_lf") if k in acc},
                         "note": "n_occ counts the occ evaluations the reference makes for the executed steps; starts rejected by the K-mer filter are not walked at all; "
                                 "n_probe counts every filter probe issued, including re-probes that hit in L1"},
@@ -551,14 +700,47 @@ def run(args, saved_stdout):
            "gpu_launches": int(launches), "roofline": roof,
            "aligned_fraction": acc_pairs_all / (args.pairs_per_step * args.steps * world),
            "index_prepare_s": t_index}
-    if rank == 0 and not args.no_cpu_baseline and world == 1:
+    if cpu_legs:
+        for c in ctxs[1:]:
+            c.close()
+        ctx.close()                       # the CLI legs load the index themselves: free this process's HBM first
+        ctxs = [ctx]
+        torch.cuda.empty_cache()
+        npairs = args.cpu_sample_pairs
+        fqp = sample_prefix(args, "cpu", npairs)
         try:
-            v, a, w = cpu_leg(args.cpu_sample_pairs, "cpu")
-            out["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": ncores, "kind": "reference",
+            a, w, ref_fq = run_reference_soap4(args, prefix, fqp, os.path.join(d, "refout_cpu"), ncores, keep_stdout=True)
+            out["cpu_baseline"] = {"value": npairs / a, "unit": "pairs/s", "cores": ncores, "kind": "reference",
                                    "sample": "%d pairs of the same workload (same index files), oracle/_ref/soap4 -T %d, align loop %.1f s, wall %.1f s" % (
-                                       args.cpu_sample_pairs, ncores, a, w)}
+                                       npairs, ncores, a, w)}
+            # parity where the numbers are made: the drop-in binary on the same index and sample must print the reference's records
+            our_fq = os.path.join(d, "ourout_cpu.stdout.fq")
+            run_our_soap4(args, prefix, fqp, os.path.join(d, "ourout_cpu"), ncores, sink=our_fq)
+            want, got = canonical_pairs(ref_fq), canonical_pairs(our_fq)
+            ndiff = sum(1 for x, y in zip(want, got) if x != y) + abs(len(want) - len(got))
+            out["parity_at_scale"] = bool(ndiff == 0 and len(want) == npairs)
+            out["parity_at_scale_detail"] = {"pairs_compared": len(want), "pairs_differing": ndiff,
+                                             "what": "bin/soap4 vs oracle/_ref/soap4, annotated FASTQ of the CPU sample on the %.0f Mbp index, pairs sorted by name" % args.cfg["ref_mbp"]}
+            for f in (ref_fq, our_fq):
+                os.remove(f)
         except Exception as e:  # the baseline is reported, never the target: say why it is missing
-            out["cpu_baseline"] = {"value": None, "unit": "pairs/s", "cores": ncores, "kind": "reference", "sample": "unavailable: %s" % e}
+            out.setdefault("cpu_baseline", {"value": None, "unit": "pairs/s", "cores": ncores, "kind": "reference", "sample": "unavailable: %s" % e})
+            out.setdefault("parity_at_scale", None)
+            out["parity_at_scale_error"] = str(e)[:300]
+        if args.cli_pairs > 0:
+            # e2e_cli: what the reference's own number means (SOAP4.cpp:613): FASTQ files in, annotated FASTQ out, the batch loop's wall time
+            try:
+                cli = sample_prefix(args, "cli", args.cli_pairs)
+                loop_s, wall_s, _ = run_our_soap4(args, prefix, cli, os.path.join(d, "ourout_cli"), ncores, sink=os.path.join(d, "ourout_cli.stdout.fq"))
+                out_bytes = os.path.getsize(os.path.join(d, "ourout_cli.stdout.fq"))
+                os.remove(os.path.join(d, "ourout_cli.stdout.fq"))
+                out["e2e_cli"] = {"value": args.cli_pairs / loop_s, "unit": "pairs/s", "pairs": args.cli_pairs, "loop_s": loop_s, "process_wall_s": wall_s,
+                                  "stdout_bytes": out_bytes,
+                                  "what": "megapath_b200/bin/soap4 pair <index> r_1.fq r_2.fq -F -nc -T %d, stdout to a file; its 'Overall alignment time (excl. read "
+                                          "loading)' line = wall time of the whole batch loop (parse + pack + upload + align + format + write; index load excluded, "
+                                          "as in the reference)" % ncores}
+            except Exception as e:
+                out["e2e_cli"] = {"value": None, "unit": "pairs/s", "error": str(e)[:300]}
     if rank == 0:
         emit(saved_stdout, out)
     for c in ctxs[1:]:
