@@ -45,6 +45,7 @@ struct Options {
     int maxReadLength = 120, insert_low = 1, insert_high = 500, outputBAM = 0, numCpuThreads = 4, device = 0;
     int megapathMode = 0, top = 95, ignoreComments = 0, alignmentType = 2, printMDNM = 0;
     int numGpus = 1, contextsPerGpu = 2;       // extensions: -G <n> uses GPUs device..device+n-1; MP_CONTEXTS_PER_GPU overrides 2
+    int lsam = -1;                             // extension: -lsam <0|1> prints what `soap4 -F | fastq2lsam <0|1>` prints (cc/fastq2lsam.cpp)
 };
 
 static bool parse_args(int argc, char **argv, Options &o)
@@ -76,6 +77,7 @@ static bool parse_args(int argc, char **argv, Options &o)
         else if (!strcmp(a, "-P")) o.megapathMode = 2;
         else if (!strcmp(a, "-top")) { if (!need("the value of '-top'")) return false; o.top = atoi(argv[i + 1]); }   // the reference does not consume the value (IniParam.cpp:885-892)
         else if (!strcmp(a, "-nc")) o.ignoreComments = 1;
+        else if (!strcmp(a, "-lsam")) { if (!need("0 or 1 (outputSeq)")) return false; o.lsam = atoi(argv[++i]) != 0; }
         else if (!strcmp(a, "-D") || !strcmp(a, "-A") || !strcmp(a, "-R") || !strcmp(a, "-e")) { if (i + 1 < argc) ++i; }
         else if (!strcmp(a, "-I")) { fprintf(stderr, "illumina quality is not supported yet\n"); return false; }
     }
@@ -724,6 +726,70 @@ static void output_unpaired(OutCtx &o, std::string &fq, uint32_t r1, std::vector
 }
 
 // ------------------------------------------------------------------------------------------------
+// -lsam: the first consumer of the stdout contract fused into the driver.  runMegaPath.sh pipes `soap4 -F` into cc/fastq2lsam
+// (:136, 162, 208, 305), which re-parses every record; here a formatted chunk (whole pairs, mate 1 then mate 2) is rewritten into the
+// lines fastq2lsam prints (cc/fastq2lsam.cpp:28-77: name, 64/128/0, score, seq, qual | * *, "score,acc" list | *, [IGNORE]) before it
+// leaves the process.  Records pair up by adjacent equal names after the /<digit> trim, as in fastq2lsam's main loop (:95-108).
+static void fastq_chunk_to_lsam(const std::string &fq, bool outputSeq, std::string &out)
+{
+    struct Rec { const char *name; size_t nameLen; const char *comm; size_t commLen; const char *seq; size_t seqLen; const char *qual; size_t qualLen; };
+    out.clear(); out.reserve(fq.size());
+    auto print = [&](const Rec &r, int whichEnd) {
+        out.append(r.name, r.nameLen); out += '\t';
+        out += whichEnd == 1 ? "64" : whichEnd == 2 ? "128" : "0"; out += '\t';
+        const bool ignore = r.commLen == 6 && !memcmp(r.comm, "IGNORE", 6);
+        const int score = ignore ? -1 : (r.commLen > 6 ? atoi(std::string(r.comm + 6, r.commLen - 6).c_str()) : 0);
+        out += std::to_string(score); out += '\t';
+        if (outputSeq) { out.append(r.seq, r.seqLen); out += '\t'; out.append(r.qual, r.qualLen); out += '\t'; }
+        else out += "*\t*\t";
+        if (score <= 0) out += '*';
+        else {
+            // misc.h splitBy: fields between delimiters, a trailing empty field is dropped.  Every field after the first (the
+            // "SCORE:n" one) is "score,acc[,acc...]" and prints as "score,acc" per accession, joined by ';'
+            bool first = true;
+            int field = 0;
+            for (size_t i = 0, j; i < r.commLen; i = j + 1, ++field) {
+                j = i; while (j < r.commLen && r.comm[j] != ';') ++j;
+                if (field == 0) continue;
+                size_t s0e = i; while (s0e < j && r.comm[s0e] != ',') ++s0e;            // sub[0] = [i, s0e)
+                int sub = 0;
+                for (size_t a = i, e; a < j; a = e + 1, ++sub) {
+                    e = a; while (e < j && r.comm[e] != ',') ++e;
+                    if (sub == 0) continue;
+                    if (!first) out += ';'; else first = false;
+                    out.append(r.comm + i, s0e - i); out += ','; out.append(r.comm + a, e - a);
+                }
+            }
+        }
+        if (score == -1) out += "\tIGNORE";
+        out += '\n';
+    };
+    Rec last{}; bool hasLast = false;
+    const char *p = fq.data(), *end = p + fq.size();
+    while (p < end) {
+        const char *l[4], *e[4];
+        bool ok = true;
+        for (int k = 0; k < 4; ++k) {
+            l[k] = p; const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+            if (!nl) { ok = false; break; }
+            e[k] = nl; p = nl + 1;
+        }
+        if (!ok) break;
+        Rec r{};
+        const char *h = l[0] + 1, *he = e[0];                                       // after '@'
+        const char *ws = h; while (ws < he && !isspace((unsigned char)*ws)) ++ws;
+        r.name = h; r.nameLen = (size_t)(ws - h);
+        if (r.nameLen > 2 && h[r.nameLen - 2] == '/' && isdigit((unsigned char)h[r.nameLen - 1])) r.nameLen -= 2;      // trim_readno
+        r.comm = ws < he ? ws + 1 : he; r.commLen = (size_t)(he - r.comm);
+        r.seq = l[1]; r.seqLen = (size_t)(e[1] - l[1]); r.qual = l[3]; r.qualLen = (size_t)(e[3] - l[3]);
+        if (hasLast) {
+            if (last.nameLen == r.nameLen && !memcmp(last.name, r.name, r.nameLen)) { print(last, 1); print(r, 2); hasLast = false; }
+            else { print(last, 0); last = r; }
+        } else { hasLast = true; last = r; }
+    }
+    if (hasLast) print(last, 0);
+}
+
 int main(int argc, char **argv)
 {
 #ifdef MP_TEST_HOOKS
@@ -773,6 +839,15 @@ int main(int argc, char **argv)
         BgzfWriter::compress_all(data.data() + mid, data.size() - mid, b);
         w.write_blocks(a); w.write_blocks(b);
         w.close();
+        return 0;
+    }
+    if (argc >= 4 && !strcmp(argv[1], "__lsam")) {           // hidden: annotated FASTQ file -> the -lsam lines (no GPU): __lsam file outputSeq
+        FILE *in = fopen(argv[2], "rb"); if (!in) return 1;
+        std::string data; char tmp[65536]; size_t n;
+        while ((n = fread(tmp, 1, sizeof tmp, in)) > 0) data.append(tmp, n);
+        fclose(in);
+        std::string out; fastq_chunk_to_lsam(data, atoi(argv[3]) != 0, out);
+        fwrite(out.data(), 1, out.size(), stdout);
         return 0;
     }
     if (argc >= 3 && !strcmp(argv[1], "__parse")) {
@@ -978,6 +1053,7 @@ int main(int argc, char **argv)
                             occ.bam = opt.outputBAM ? &capw : nullptr;
                             chunks[c].fq.reserve((size_t)(cut[c + 1] - cut[c]) * 512);
                             body(occ, chunks[c].fq, cut[c], cut[c + 1]);
+                            if (opt.lsam >= 0 && !chunks[c].fq.empty()) { std::string ls; fastq_chunk_to_lsam(chunks[c].fq, opt.lsam != 0, ls); chunks[c].fq.swap(ls); }
                             if (!chunks[c].bam.empty()) { BgzfWriter::compress_all(chunks[c].bam.data(), chunks[c].bam.size(), chunks[c].bamz); std::vector<uint8_t>().swap(chunks[c].bam); }
                         };
                         std::vector<std::thread> ths;

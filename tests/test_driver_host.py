@@ -126,3 +126,25 @@ def test_batch_loader_layout(tmp_path, threads):
     want_words, want_wpq = mp.pack_queries(want_codes, want_lens, maxlen)
     assert wpq == want_wpq and (words == want_words).all()
     assert raw[8 + 4 * n + 4 * nwords:].split(b"\n")[:-1] == meta
+
+
+LSAM_CASES = (b"@r1\tSCORE:50;50,seqA;48,seqB,seqC;\nACGT\n+\nIIII\n@r1\tIGNORE\nAC\n+\nII\n"
+              b"@r2\tSCORE:0;\nA\n+\nI\n@r2\tSCORE:7;7,x;\nAA\n+\nII\n"
+              b"@lone\tSCORE:31;31,only one;\nACG\n+\nIII\n"                      # a name that never pairs up
+              b"@p/1\tSCORE:99;99,a;;95,b;\nACGT\n+\nIIII\n@p/2\tSCORE:99;99,a,,c;\nACGT\n+\nIIII\n"      # /1 /2 trimmed; empty fields
+              b"@q\tSCORE:12;12,gi|1|ref|NC_1.1|;12,z\nAC\n+\nII\n@q\tSCORE:-3;5,w;\nAC\n+\nII\n"
+              b"@tail\tSCORE:40;40,t;\nA\n+\nI\n")
+
+
+@pytest.mark.parametrize("output_seq", ["1", "0"])
+def test_lsam_mode_matches_reference_fastq2lsam(tmp_path, output_seq):
+    """-lsam (the fused fastq2lsam step) prints what the reference's own cc/fastq2lsam prints for the same annotated FASTQ"""
+    ref = os.path.join(ROOT, "oracle", "_ref", "fastq2lsam")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/fastq2lsam not built")
+    f = tmp_path / "a.fq"
+    f.write_bytes(LSAM_CASES)
+    want = subprocess.run([ref, output_seq], stdin=open(f, "rb"), capture_output=True, check=True, timeout=60).stdout
+    got = subprocess.run([EXE, "__lsam", str(f), output_seq], capture_output=True, check=True, timeout=60).stdout
+    assert want.count(b"\n") == 10
+    assert got == want

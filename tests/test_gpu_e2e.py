@@ -223,3 +223,21 @@ def test_e2e_threads_and_contexts(workdir, small_ref, monkeypatch):
         monkeypatch.setenv("MP_CONTEXTS_PER_GPU", nctx)
         got = canon_fastq(run_our_soap4(workdir, small_ref["prefix"], fq1, fq2, "ctxsour" + nctx, 101, extra=("-F", "-nc", "-T", "7")))
         assert got == want, (nctx, first_diff(got, want))
+
+
+@needs_ref
+def test_e2e_lsam_mode_matches_reference_pipe(workdir, small_ref):
+    """`soap4 ... -F -lsam 1` == `reference soap4 ... -F | cc/fastq2lsam 1` (runMegaPath.sh:136), pair lines sorted by name"""
+    import subprocess
+    from conftest import REF_DIR
+    fq1, fq2 = make_reads(workdir, small_ref, "lsam", 2000, 150, seed=5, model="divergent", one_random=0.10, unalignable=0.05)
+    first = run_ref_raw(workdir, small_ref["prefix"], fq1, fq2, "lsamref", 151, "soap4-nt2.ini", ["-F", "-nc", "-top", "95"])
+    want = subprocess.run([os.path.join(REF_DIR, "fastq2lsam"), "1"], input=first, capture_output=True, check=True).stdout
+    got = run_our_soap4(workdir, small_ref["prefix"], fq1, fq2, "lsamour", 151, ini="soap4-nt2.ini", extra=("-F", "-nc", "-top", "95", "-lsam", "1"))
+
+    def canon(data):
+        lines = data.split(b"\n")[:-1]
+        pairs = [(lines[i], lines[i + 1]) for i in range(0, len(lines) - 1, 2)]
+        return sorted(pairs)
+    assert len(canon(want)) == 2000 and want.count(b"\t64\t") == 2000
+    assert canon(got) == canon(want)
