@@ -241,3 +241,66 @@ def test_e2e_lsam_mode_matches_reference_pipe(workdir, small_ref):
         return sorted(pairs)
     assert len(canon(want)) == 2000 and want.count(b"\t64\t") == 2000
     assert canon(got) == canon(want)
+
+
+@needs_ref
+def test_e2e_builder_with_ambiguity_runs(workdir):
+    """bin/2bwt-builder on a FASTA with short / long N runs, IUPAC codes and lower case: every index file equals the reference
+    builder's (HSP.c:486-528 cut-outs + translate table), and soap4 on that index prints the reference's records (positions behind
+    cut-out runs go through the translate table's corrections)."""
+    import shutil
+    import subprocess
+    from conftest import REF_DIR, ROOT
+    from test_builder_fasta import fasta_with_ambiguity
+    d = os.path.join(workdir, "amb")
+    os.makedirs(d, exist_ok=True)
+    raw = fasta_with_ambiguity(11, nseq=4, seqlen=60000)
+    fa_ref, fa_our = os.path.join(d, "ref.fa"), os.path.join(d, "our.fa")
+    for p in (fa_ref, fa_our):
+        open(p, "wb").write(raw)
+    shutil.copy(os.path.join(REF_DIR, "2bwt-builder.ini"), os.path.join(d, "2bwt-builder.ini"))
+    subprocess.check_call([os.path.join(REF_DIR, "2bwt-builder"), fa_ref], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.check_call([os.path.join(ROOT, "megapath_b200", "bin", "2bwt-builder"), fa_our], cwd=d, stdout=subprocess.DEVNULL)
+    for ext in ("pac", "bwt", "fmv", "sa", "lkt", "tra", "amb"):
+        assert open(fa_ref + ".index." + ext, "rb").read() == open(fa_our + ".index." + ext, "rb").read(), ext
+    # FR pairs from the raw sequences (windows without ambiguity codes), a third of them right next to a run
+    rng = np.random.default_rng(3)
+    seqs = [b"".join(x.split(b"\n")[1:]).upper() for x in raw.split(b">")[1:]]
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    r1, r2 = [], []
+    while len(r1) < 1500:
+        s = seqs[int(rng.integers(0, len(seqs)))]
+        isz = int(rng.integers(260, 480))
+        if len(r1) % 3 == 0:
+            hits = [i for i in range(0, len(s) - 600, 50) if s[i] not in b"ACGT"]
+            st = (hits[int(rng.integers(0, len(hits)))] + int(rng.integers(1, 40))) if hits else 0
+        else:
+            st = int(rng.integers(0, len(s) - 600))
+        frag = s[st:st + isz]
+        a, b = frag[:150], frag[-150:].translate(comp)[::-1]
+        if len(frag) < isz or any(c not in b"ACGT" for c in a + b):
+            continue
+        r1.append(np.frombuffer(a, dtype=np.uint8))
+        r2.append(np.frombuffer(b, dtype=np.uint8))
+    from tools import synth
+    fq1, fq2 = os.path.join(d, "amb_1.fq"), os.path.join(d, "amb_2.fq")
+    synth.write_fastq(fq1, r1, 1)
+    synth.write_fastq(fq2, r2, 2)
+    ref_out, _ = run_ref_soap4(d, fa_ref + ".index", fq1, fq2, "ambref", 151, dump=False, threads=3)
+    want = canon_fastq(open(ref_out, "rb").read())
+    got = canon_fastq(run_our_soap4(d, fa_our + ".index", fq1, fq2, "ambour", 151))
+    assert want.count(b"SCORE:") == 3000 and want.count(b"SCORE:0;") < 600
+    assert got == want, first_diff(got, want)
+    # and with BAM records (chromosome-relative positions, MD/NM) on the same index
+    import glob
+    from conftest import canon_bam
+    for pre in ("ambrefb", "ambourb"):
+        for f in glob.glob(os.path.join(d, pre) + ".*"):
+            os.remove(f)
+    run_ref_raw(d, fa_ref + ".index", fq1, fq2, "ambrefb", 151, "soap4.ini", ["-b", "-F", "-nc", "-p"])
+    run_our_soap4(d, fa_our + ".index", fq1, fq2, "ambourb", 151, extra=("-b", "-F", "-nc", "-p"))
+    files = lambda pre: [os.path.join(d, pre) + ".dpout.1", os.path.join(d, pre) + ".unpair"] + sorted(glob.glob(os.path.join(d, pre) + ".gout.*"))
+    (hr, rr), (ho, ro) = canon_bam(files("ambrefb")), canon_bam(files("ambourb"))
+    assert hr == ho and len(rr) == len(ro) == 3000
+    for x, y in zip(ro, rr):
+        assert x == y, (x, y)
