@@ -75,7 +75,8 @@ typedef struct mp_pair_result {
     int32_t  score_1, score_2;
     int32_t  editdist_1, editdist_2;
     int32_t  num_sameScore_1, num_sameScore_2;
-    uint8_t  strand_1, strand_2; uint16_t pad;
+    uint8_t  strand_1, strand_2; uint16_t pad; /* pad: 1 on the best pair of its read pair (first maximal score_1 + score_2,
+                                                * OutputDPResult.cpp:156-232), chosen on the device for stage-S1 results; else 0 */
     uint32_t cigar_1, cigar_2; /* offsets into mp_results.cigars */
     uint64_t startPos_1, startPos_2;
     uint32_t refDpLength_1, refDpLength_2;

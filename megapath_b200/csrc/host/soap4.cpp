@@ -506,8 +506,14 @@ static void output_pair(OutCtx &o, std::string &fq, const mp_pair_result *first,
         a.c1 = cigars + p->cigar_1; a.c2 = cigars + p->cigar_2;
         v.push_back(a);
     }
-    size_t best = 0; int maxScore = v[0].s1 + v[0].s2;
-    for (size_t i = 1; i < v.size(); ++i) if (v[i].s1 + v[i].s2 > maxScore) { best = i; maxScore = v[i].s1 + v[i].s2; }
+    // best pair = the first one with the maximal score sum (OutputDPResult.cpp:156-232): stage S1 marks it on the device (pad = 1,
+    // k_pair_ready); mate-rescue groups are assembled on the host and are scanned here
+    size_t best = v.size();
+    for (const mp_pair_result *p = first; p != last; ++p) if (p->pad == 1) { best = (size_t)(p - first); break; }
+    if (best == v.size()) {
+        best = 0; int maxScore = v[0].s1 + v[0].s2;
+        for (size_t i = 1; i < v.size(); ++i) if (v[i].s1 + v[i].s2 > maxScore) { best = i; maxScore = v[i].s1 + v[i].s2; }
+    }
     if (o.megapathMode) {
         int best1 = 0, best2 = 0;
         std::vector<std::pair<int, int>> &h1 = o.scratch->h1, &h2 = o.scratch->h2; h1.clear(); h2.clear();

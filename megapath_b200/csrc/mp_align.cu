@@ -108,23 +108,27 @@ __global__ void k_assemble_write(uint32_t n, const mp_candidate *__restrict__ ca
                                  const MpDpOut *__restrict__ lo, const MpDpTask *__restrict__ rt, const MpDpOut *__restrict__ ro,
                                  const uint8_t *__restrict__ lpat, const uint8_t *__restrict__ rpat, uint32_t patStride,
                                  AsmParams A, const uint32_t *__restrict__ okFlag, const uint32_t *__restrict__ outIdx,
-                                 const uint32_t *__restrict__ cigOff, const uint32_t *__restrict__ leftLen, uint32_t cigBase,
+                                 const uint32_t *__restrict__ cigOff, const uint32_t *__restrict__ leftLen, uint32_t *__restrict__ totals, uint32_t cigCap,
                                  mp_pair_result *__restrict__ res, char *__restrict__ cig, uint8_t *__restrict__ alignedPair)
 {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n || !okFlag[c]) return;
+    // results and CIGAR text of all chunks of a batch go to one device arena each; totals[0] / totals[1] hold what earlier chunks used
+    // (k_add_totals), so no host round trip is needed between chunks
+    const uint32_t resBase = totals[0], cigBase = totals[1];
+    if ((uint64_t)cigBase + cigOff[c + 1] > cigCap) { totals[4] = 1; return; }            // arena too small: the host re-runs the stage with room
     // index 0 = left leg, 1 = right leg (DV-DPfunctions.cpp:3432-3530)
     const uint8_t *pat[2] = { lpat + (size_t)c * patStride, rpat + (size_t)c * patStride };
     const MpDpTask *tk[2] = { lt + c, rt + c };
     const MpDpOut *ou[2] = { lo + c, ro + c };
     int editdist[2], DIS[2]; uint32_t cigPos[2];
-    uint32_t off = cigOff[c];
+    uint32_t off = cigBase + cigOff[c];
     const int lengths_i = rt[c].readLen;                // batch->lengths[i] was overwritten by packRight
     const int textLen[2] = { (int)leftLen[c], (int)(cigOff[c + 1] - cigOff[c]) - (int)leftLen[c] - 2 };
     for (int s = 0; s < 2; ++s) {
         CigStats m = all_match_leg(*tk[s], *ou[s]) ? all_match_cigar(tk[s]->readLen, cig + off) : cigar_encode(pat[s], A.open, A.ext, cig + off, textLen[s]);
         cig[off + m.textLen] = 0;
-        cigPos[s] = cigBase + off;
+        cigPos[s] = off;
         off += m.textLen + 1;
         int L = lengths_i - m.nI - m.nS;
         int numMis = (L * A.match + m.gapPenalty - ou[s]->score) / (A.match - A.mm);
@@ -154,8 +158,62 @@ __global__ void k_assemble_write(uint32_t n, const mp_candidate *__restrict__ ca
     if (r.algnmt_1 < r.algnmt_2) r.insertSize = (int32_t)(r.algnmt_2 - r.algnmt_1 + (uint64_t)(int64_t)lengths_i + (uint64_t)(int64_t)DIS[1]);
     else r.insertSize = (int32_t)(r.algnmt_1 - r.algnmt_2 + (uint64_t)(int64_t)lengths_i + (uint64_t)(int64_t)DIS[1]);
     r.num_sameScore_1 = (int32_t)ou[readSide]->count; r.num_sameScore_2 = (int32_t)ou[mateSide]->count;
-    res[outIdx[c]] = r;
+    res[resBase + outIdx[c]] = r;
     alignedPair[r.readID >> 1] = 1;
+}
+// totals: [0] results so far, [1] CIGAR bytes so far, [2] results kept after dedup, [3] pairs with a result, [4] arena overflow flag
+__global__ void k_add_totals(const uint32_t *__restrict__ idxTotal, const uint32_t *__restrict__ offTotal, uint32_t *__restrict__ totals)
+{
+    totals[0] += *idxTotal; totals[1] += *offTotal;
+}
+
+// ---- per pair: OutputBuffer::ready (DV-DPfunctions.h:198-243 -> arrayCopyNRemoveDuplicate :167-196, ResultCompare .cpp:253-258):
+//      stable sort of the pair's results by (algnmt_1, algnmt_2, score_1, score_2), exact duplicates dropped; then the best-hit choice
+//      of outputDeepDPResult2 (OutputDPResult.cpp:156-232, alignmentType ALL_VALID): the FIRST result with the maximal score_1 + score_2
+//      is marked (pad = 1).  One thread per pair group (groups are contiguous: candidates are sorted by read id); a group is a handful
+//      of records, so an in-place insertion sort is the right tool. ----
+__device__ __forceinline__ bool pair_key_less(const mp_pair_result &a, const mp_pair_result &b)
+{
+    if (a.algnmt_1 != b.algnmt_1) return a.algnmt_1 < b.algnmt_1;
+    if (a.algnmt_2 != b.algnmt_2) return a.algnmt_2 < b.algnmt_2;
+    if (a.score_1 != b.score_1) return a.score_1 < b.score_1;
+    return a.score_2 < b.score_2;
+}
+__global__ void k_pair_ready(mp_pair_result *__restrict__ res, uint32_t *__restrict__ totals, uint32_t *__restrict__ keep)
+{
+    const uint32_t total = totals[0];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t pairs = 0, kept = 0;
+    if (i < total && (i == 0 || res[i - 1].readID != res[i].readID)) {
+        uint32_t e = i + 1;
+        while (e < total && res[e].readID == res[i].readID) ++e;
+        for (uint32_t a = i + 1; a < e; ++a) {                 // stable insertion sort
+            mp_pair_result key = res[a]; uint32_t b = a;
+            while (b > i && pair_key_less(key, res[b - 1])) { res[b] = res[b - 1]; --b; }
+            if (b != a) res[b] = key;
+        }
+        uint32_t lastKept = i, best = i; int bestSum = res[i].score_1 + res[i].score_2;
+        keep[i] = 1; kept = 1;
+        for (uint32_t a = i + 1; a < e; ++a) {
+            const bool k = pair_key_less(res[lastKept], res[a]);
+            keep[a] = k;
+            if (k) {
+                lastKept = a; ++kept;
+                const int sum = res[a].score_1 + res[a].score_2;
+                if (sum > bestSum) { bestSum = sum; best = a; }
+            }
+        }
+        for (uint32_t a = i; a < e; ++a) res[a].pad = a == best ? 1 : 0;
+        pairs = 1;
+    }
+    pairs = __reduce_add_sync(0xffffffffu, pairs); kept = __reduce_add_sync(0xffffffffu, kept);
+    if ((threadIdx.x & 31) == 0 && pairs) { atomicAdd(&totals[3], pairs); atomicAdd(&totals[2], kept); }
+}
+__global__ void k_pair_compact(const mp_pair_result *__restrict__ res, const uint32_t *__restrict__ totals, const uint32_t *__restrict__ keep,
+                               const uint32_t *__restrict__ pos, mp_pair_result *__restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < totals[0] && keep[i]) out[pos[i]] = res[i];
 }
 
 static int scan_u32(mp_context *ctx, const uint32_t *in, uint32_t *out, uint64_t n)
@@ -191,88 +249,86 @@ static int deep_dp(mp_context *ctx, const mp_align_params *P, mp_results *out, u
            &dBytes = ctx->dBytes, &dIdx = ctx->dIdx, &dOff = ctx->dOff, &dRes = ctx->dRes, &dCig = ctx->dCig;
     // full-size chunk buffers unless the whole batch is small: batch-to-batch variation must not re-allocate
     uint32_t chunkCap = (uint32_t)std::min<uint64_t>(CH, std::max<uint64_t>((nC + nC / 4 + 1024), 1));
+    const size_t resCap = (size_t)nC + nC / 8 + 1024;                         // one result per candidate at most
     if (dLT.reserve((size_t)chunkCap * sizeof(MpDpTask)) || dRT.reserve((size_t)chunkCap * sizeof(MpDpTask)) ||
         dLO.reserve((size_t)chunkCap * sizeof(MpDpOut)) || dRO.reserve((size_t)chunkCap * sizeof(MpDpOut)) ||
         dLP.reserve((size_t)chunkCap * patStride) || dRP.reserve((size_t)chunkCap * patStride) ||
         dOk.reserve(((size_t)chunkCap + 1) * 4) || dBytes.reserve(((size_t)chunkCap + 1) * 4 * 2) ||
         dIdx.reserve(((size_t)chunkCap + 1) * 4) || dOff.reserve(((size_t)chunkCap + 1) * 4) ||
-        dRes.reserve((size_t)chunkCap * sizeof(mp_pair_result))) return MP_ERR_CUDA;
+        dRes.reserve(resCap * sizeof(mp_pair_result)) || ctx->dRes2.reserve(resCap * sizeof(mp_pair_result)) ||
+        ctx->dKeep.reserve((resCap + 1) * 4) || ctx->dKeepPos.reserve((resCap + 1) * 4) || ctx->dTotals.reserve(8 * 4)) return MP_ERR_CUDA;
     PinnedBuf<mp_pair_result> &H = ctx->hPairs;
     PinnedBuf<char> &HC = ctx->hCigars;
     unsigned long long *dCnt = ctx->dCounters.as<unsigned long long>();
-    // room for about one result per candidate up front: growing a pinned arena mid-batch costs a cudaMallocHost
-    if (H.reserve((size_t)nC + nC / 8 + 1024) || HC.reserve(((size_t)nC + nC / 8 + 1024) * 20)) return MP_ERR_CUDA;
+    uint32_t *dTot = ctx->dTotals.as<uint32_t>();
     if (ctx->dAligned.reserve((size_t)ctx->nReads / 2 + 8)) return MP_ERR_CUDA;
-    MP_CUDA(cudaMemsetAsync(ctx->dAligned.p, 0, (size_t)ctx->nReads / 2 + 8, st));
     const uint64_t fullLen = ctx->ix.n;
     MpTrace tr;
-    for (uint64_t base = 0; base < nC; base += CH) {
-        uint32_t n = (uint32_t)std::min<uint64_t>(CH, nC - base);
-        const mp_candidate *cands = ctx->dCands.as<mp_candidate>() + base;
-        unsigned g = (n + 127) / 128;
-        (++g_mp_launches), k_left_tasks<<<g, 128, 0, st>>>(cands, n, ctx->dLens.as<uint32_t>(), fullLen, P->peStrandLeftLeg, dLT.as<MpDpTask>(), dCnt);
-        if (int rc = mpd_run_tasks(ctx, dLT.as<MpDpTask>(), n, maxDNALength, maxReadLength, dpl, dLO.as<MpDpOut>(), dLP.as<uint8_t>(), patStride)) return rc;
-        (++g_mp_launches), k_right_tasks<<<g, 128, 0, st>>>(cands, n, ctx->dLens.as<uint32_t>(), fullLen, P->peStrandRightLeg, P->insert_high,
-                                         dLT.as<MpDpTask>(), dLO.as<MpDpOut>(), dRT.as<MpDpTask>(), dCnt);
-        if (int rc = mpd_run_tasks(ctx, dRT.as<MpDpTask>(), n, maxDNALength, maxReadLength, dpr, dRO.as<MpDpOut>(), dRP.as<uint8_t>(), patStride)) return rc;
-        if (tr.sync) cudaStreamSynchronize(st);
-        tr.mark(" dp left+right (enqueue)");
-        MP_CUDA(cudaMemsetAsync(dOk.p, 0, ((size_t)n + 1) * 4, st));
-        MP_CUDA(cudaMemsetAsync(dBytes.p, 0, ((size_t)n + 1) * 4, st));
-        (++g_mp_launches), k_assemble_measure<<<g, 128, 0, st>>>(n, dLT.as<MpDpTask>(), dLO.as<MpDpOut>(), dRT.as<MpDpTask>(), dRO.as<MpDpOut>(),
-                                              dLP.as<uint8_t>(), dRP.as<uint8_t>(), patStride, P->openGapScore, P->extendGapScore,
-                                              dOk.as<uint32_t>(), dBytes.as<uint32_t>(), dBytes.as<uint32_t>() + chunkCap + 1);
-        if (scan_u32(ctx, dOk.as<uint32_t>(), dIdx.as<uint32_t>(), (uint64_t)n + 1)) return MP_ERR_CUDA;
-        if (scan_u32(ctx, dBytes.as<uint32_t>(), dOff.as<uint32_t>(), (uint64_t)n + 1)) return MP_ERR_CUDA;
-        uint32_t nOk = 0, nBytes = 0;
-        MP_CUDA(cudaMemcpyAsync(&nOk, dIdx.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
-        MP_CUDA(cudaMemcpyAsync(&nBytes, dOff.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
-        MP_CUDA(cudaStreamSynchronize(st));
-        tr.mark(" sync after measure");
-        if (dCig.reserve(std::max<size_t>((size_t)nBytes + 16, (size_t)chunkCap * 40))) return MP_ERR_CUDA;
-        uint32_t cigBase = (uint32_t)HC.size();
-        if (nOk) {
+    // CIGAR arena of the batch: ~12 bytes per result on clean reads, a few dozen on divergent ones.  If a batch needs more, the stage
+    // is run again with the size it asked for (the DP patterns of earlier chunks are gone by then).
+    size_t cigCap = std::max<size_t>(ctx->dCig.cap, std::max<size_t>((size_t)resCap * 40, (size_t)1 << 20));
+    uint32_t tot[8] = { 0 };
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        if (cigCap > 0xFFFFFFF0ull) { mp_set_error("CIGAR arena of one batch exceeds 4 GB; use smaller batches"); return MP_ERR_CAPACITY; }
+        if (dCig.reserve(cigCap)) return MP_ERR_CUDA;
+        MP_CUDA(cudaMemsetAsync(dTot, 0, 8 * 4, st));
+        MP_CUDA(cudaMemsetAsync(ctx->dAligned.p, 0, (size_t)ctx->nReads / 2 + 8, st));
+        MP_CUDA(cudaMemsetAsync(dCnt + 11, 0, 16, st));                        // work accounting of k_left_tasks / k_right_tasks
+        for (uint64_t base = 0; base < nC; base += CH) {
+            uint32_t n = (uint32_t)std::min<uint64_t>(CH, nC - base);
+            const mp_candidate *cands = ctx->dCands.as<mp_candidate>() + base;
+            unsigned g = (n + 127) / 128;
+            (++g_mp_launches), k_left_tasks<<<g, 128, 0, st>>>(cands, n, ctx->dLens.as<uint32_t>(), fullLen, P->peStrandLeftLeg, dLT.as<MpDpTask>(), dCnt);
+            if (int rc = mpd_run_tasks(ctx, dLT.as<MpDpTask>(), n, maxDNALength, maxReadLength, dpl, dLO.as<MpDpOut>(), dLP.as<uint8_t>(), patStride)) return rc;
+            (++g_mp_launches), k_right_tasks<<<g, 128, 0, st>>>(cands, n, ctx->dLens.as<uint32_t>(), fullLen, P->peStrandRightLeg, P->insert_high,
+                                             dLT.as<MpDpTask>(), dLO.as<MpDpOut>(), dRT.as<MpDpTask>(), dCnt);
+            if (int rc = mpd_run_tasks(ctx, dRT.as<MpDpTask>(), n, maxDNALength, maxReadLength, dpr, dRO.as<MpDpOut>(), dRP.as<uint8_t>(), patStride)) return rc;
+            if (tr.sync) cudaStreamSynchronize(st);
+            tr.mark(" dp left+right (enqueue)");
+            MP_CUDA(cudaMemsetAsync(dOk.p, 0, ((size_t)n + 1) * 4, st));
+            MP_CUDA(cudaMemsetAsync(dBytes.p, 0, ((size_t)n + 1) * 4, st));
+            (++g_mp_launches), k_assemble_measure<<<g, 128, 0, st>>>(n, dLT.as<MpDpTask>(), dLO.as<MpDpOut>(), dRT.as<MpDpTask>(), dRO.as<MpDpOut>(),
+                                                  dLP.as<uint8_t>(), dRP.as<uint8_t>(), patStride, P->openGapScore, P->extendGapScore,
+                                                  dOk.as<uint32_t>(), dBytes.as<uint32_t>(), dBytes.as<uint32_t>() + chunkCap + 1);
+            if (scan_u32(ctx, dOk.as<uint32_t>(), dIdx.as<uint32_t>(), (uint64_t)n + 1)) return MP_ERR_CUDA;
+            if (scan_u32(ctx, dBytes.as<uint32_t>(), dOff.as<uint32_t>(), (uint64_t)n + 1)) return MP_ERR_CUDA;
             (++g_mp_launches), k_assemble_write<<<g, 128, 0, st>>>(n, cands, dLT.as<MpDpTask>(), dLO.as<MpDpOut>(), dRT.as<MpDpTask>(), dRO.as<MpDpOut>(),
                                                 dLP.as<uint8_t>(), dRP.as<uint8_t>(), patStride, A, dOk.as<uint32_t>(), dIdx.as<uint32_t>(),
-                                                dOff.as<uint32_t>(), dBytes.as<uint32_t>() + chunkCap + 1, cigBase, dRes.as<mp_pair_result>(), dCig.as<char>(),
+                                                dOff.as<uint32_t>(), dBytes.as<uint32_t>() + chunkCap + 1, dTot, (uint32_t)cigCap, dRes.as<mp_pair_result>(), dCig.as<char>(),
                                                 ctx->dAligned.as<uint8_t>());
+            (++g_mp_launches), k_add_totals<<<1, 1, 0, st>>>(dIdx.as<uint32_t>() + n, dOff.as<uint32_t>() + n, dTot);
             MP_CUDA(cudaGetLastError());
-            size_t h0 = H.size();
-            if (H.resize(h0 + nOk) || HC.resize((size_t)cigBase + nBytes)) return MP_ERR_CUDA;
-            MP_CUDA(cudaMemcpyAsync(H.data() + h0, dRes.p, (size_t)nOk * sizeof(mp_pair_result), cudaMemcpyDeviceToHost, st));
-            MP_CUDA(cudaMemcpyAsync(HC.data() + cigBase, dCig.p, nBytes, cudaMemcpyDeviceToHost, st));
-            MP_CUDA(cudaStreamSynchronize(st));
+            tr.mark(" assemble (enqueue)");
         }
-        tr.mark(" assemble+download");
-    }
-    tr.mark(" accounting");
-    // ---- per pair: sort, drop exact duplicates (OutputBuffer::arrayCopyNRemoveDuplicate, DV-DPfunctions.h:167-196) ----
-    auto key = [](const mp_pair_result &a) { return std::make_tuple(a.algnmt_1, a.algnmt_2, a.score_1, a.score_2); };
-    size_t w = 0, i = 0;
-    uint64_t nPairsAligned = 0;
-    const size_t nH = H.size();
-    mp_pair_result *hp = H.data();
-    while (i < nH) {
-        size_t j = i + 1;
-        while (j < nH && hp[j].readID == hp[i].readID) ++j;
-        if (j - i == 1) { if (w != i) hp[w] = hp[i]; ++w; }
-        else {
-            std::stable_sort(hp + i, hp + j, [&](const mp_pair_result &a, const mp_pair_result &b) { return key(a) < key(b); });
-            if (w != i) hp[w] = hp[i];
-            ++w;
-            for (size_t k = i + 1; k < j; ++k) if (key(hp[w - 1]) < key(hp[k])) { if (w != k) hp[w] = hp[k]; ++w; }
+        // ---- per pair: sort, drop exact duplicates, mark the best pair; compact ----
+        if (nC) {
+            const unsigned g = (unsigned)((nC + 127) / 128);
+            MP_CUDA(cudaMemsetAsync(ctx->dKeep.p, 0, (resCap + 1) * 4, st));
+            (++g_mp_launches), k_pair_ready<<<g, 128, 0, st>>>(dRes.as<mp_pair_result>(), dTot, ctx->dKeep.as<uint32_t>());
+            if (scan_u32(ctx, ctx->dKeep.as<uint32_t>(), ctx->dKeepPos.as<uint32_t>(), (uint64_t)nC + 1)) return MP_ERR_CUDA;
+            (++g_mp_launches), k_pair_compact<<<g, 128, 0, st>>>(dRes.as<mp_pair_result>(), dTot, ctx->dKeep.as<uint32_t>(), ctx->dKeepPos.as<uint32_t>(),
+                                                                 ctx->dRes2.as<mp_pair_result>());
+            MP_CUDA(cudaGetLastError());
         }
-        ++nPairsAligned;
-        i = j;
+        MP_CUDA(cudaMemcpyAsync(tot, dTot, sizeof tot, cudaMemcpyDeviceToHost, st));
+        MP_CUDA(cudaStreamSynchronize(st));                                    // the one host round trip of stage S1
+        tr.mark(" s1 device work");
+        if (!tot[4]) break;
+        cigCap = (size_t)tot[1] + tot[1] / 8 + (1 << 20);                       // the arena was too small: run the stage again with room
+        if (attempt == 2) { mp_set_error("CIGAR arena overflowed repeatedly"); return MP_ERR_CAPACITY; }
     }
-    H.resize(w);
+    const uint32_t nKept = tot[2], nBytes = tot[1];
+    if (H.resize(nKept) || HC.resize(nBytes)) return MP_ERR_CUDA;
+    if (nKept) MP_CUDA(cudaMemcpyAsync(H.data(), ctx->dRes2.p, (size_t)nKept * sizeof(mp_pair_result), cudaMemcpyDeviceToHost, st));
+    if (nBytes) MP_CUDA(cudaMemcpyAsync(HC.data(), dCig.p, nBytes, cudaMemcpyDeviceToHost, st));
     {   // cells / tasks counted on the device by k_left_tasks / k_right_tasks
         unsigned long long hc2[2];
-        MP_CUDA(cudaMemcpy(hc2, dCnt + 11, sizeof hc2, cudaMemcpyDeviceToHost));
+        MP_CUDA(cudaMemcpyAsync(hc2, dCnt + 11, sizeof hc2, cudaMemcpyDeviceToHost, st));
+        MP_CUDA(cudaStreamSynchronize(st));
         cells += hc2[0]; tasksRun += hc2[1];
     }
-    tr.mark(" host sort/dedup");
-    out->numDPAlignedPair = nPairsAligned; out->numDPAlignment = w;
+    tr.mark(" s1 download");
+    out->numDPAlignedPair = tot[3]; out->numDPAlignment = nKept;
     return 0;
 }
 
@@ -331,7 +387,7 @@ extern "C" void mp_destroy(mp_context *ctx)
                        &ctx->dSeedPos, &ctx->dNPos, &ctx->dNNeg, &ctx->dCandCount, &ctx->dCandStart, &ctx->dCands, &ctx->dScanTmp,
                        &ctx->dTasks, &ctx->dRefSeq, &ctx->dReadSeq, &ctx->dTable, &ctx->dFill, &ctx->dPattern, &ctx->dDpOut,
                        &ctx->dLT, &ctx->dRT, &ctx->dLO, &ctx->dRO, &ctx->dLP, &ctx->dRP, &ctx->dOk, &ctx->dBytes, &ctx->dIdx, &ctx->dOff,
-                       &ctx->dRes, &ctx->dCig, &ctx->dExFlag, &ctx->dExPos, &ctx->dExIdx, &ctx->dAligned, &ctx->dGather, &ctx->dHintTest };
+                       &ctx->dRes, &ctx->dCig, &ctx->dExFlag, &ctx->dExPos, &ctx->dExIdx, &ctx->dAligned, &ctx->dGather, &ctx->dHintTest, &ctx->dRes2, &ctx->dKeep, &ctx->dKeepPos, &ctx->dTotals };
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->stream);

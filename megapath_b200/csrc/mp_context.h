@@ -140,6 +140,7 @@ struct mp_context {
     DevBuf dHintTest;                                                             // MP_DP_TEST_HINT (mp_dp.cu)
     DevBuf dExFlag, dExPos, dExIdx;                                              // exact-occurrence test: flags, scan, active slots (mp_dp.cu)
     DevBuf dLT, dRT, dLO, dRO, dLP, dRP, dOk, dBytes, dIdx, dOff, dRes, dCig;   // stage S1 chunk buffers (kept across calls)
+    DevBuf dRes2, dKeep, dKeepPos, dTotals;                                      // stage S1 per-pair dedup / best pick (k_pair_ready)
     // results (host, owned until release)
     PinnedBuf<mp_pair_result> hPairs;
     std::vector<mp_pair_result> hRescued;

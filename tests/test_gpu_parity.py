@@ -93,6 +93,16 @@ def test_gpu_seed_pair_and_deep_dp(ctx, workdir, small_ref, name, rlen, lopt, kw
             assert int(g[f]) == int(w[f]), (f, g, w)
         assert mp.cigar_at(res["cigars"], int(g["cigar_1"])) == w["cigar_1"]
         assert mp.cigar_at(res["cigars"], int(g["cigar_2"])) == w["cigar_2"]
+    # best-hit choice on the device: exactly one result per pair is marked, the first with the maximal score sum
+    i = 0
+    while i < len(got):
+        j = i
+        while j < len(got) and got[j]["readID"] == got[i]["readID"]:
+            j += 1
+        sums = [int(got[k]["score_1"]) + int(got[k]["score_2"]) for k in range(i, j)]
+        marks = [int(got[k]["pad"]) for k in range(i, j)]
+        assert marks == [1 if k == sums.index(max(sums)) else 0 for k in range(j - i)], (i, sums, marks)
+        i = j
     # dp_cells also counts the single-end / rescue tasks of pairs stage S1 left unaligned
     assert res["dp_cells"] >= cells and (len(res["singles"]) > 0 or res["dp_cells"] == cells)
     assert res["numDPAlignment"] == len(want)
