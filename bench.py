@@ -63,7 +63,7 @@ def parse_args():
     ap.add_argument("--read-len", type=int, default=0, help="override the config's read length (-L sweep)")
     ap.add_argument("--pairs-per-step", type=int, default=int(os.environ.get("MP_BENCH_PAIRS", str(1 << 20))))
     ap.add_argument("--cpu-sample-pairs", type=int, default=int(os.environ.get("MP_BENCH_CPU_PAIRS", "200000")))
-    ap.add_argument("--cli-pairs", type=int, default=int(os.environ.get("MP_BENCH_CLI_PAIRS", str(3 << 20))),
+    ap.add_argument("--cli-pairs", type=int, default=int(os.environ.get("MP_BENCH_CLI_PAIRS", str(4 << 20))),
                     help="pairs in the FASTQ files of the e2e_cli leg (bin/soap4, FASTQ in -> annotated FASTQ out); 0 = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs (reference sample, parity at scale, e2e_cli)")
     ap.add_argument("--contexts", type=int, default=int(os.environ.get("MP_BENCH_CONTEXTS", "3")),

@@ -161,6 +161,11 @@ int  mp_index_save_annotation(const char *prefix, uint64_t textLength, uint32_t 
  * clones share them */
 int  mp_index_prepare(mp_context *ctx, const mp_align_params *params);
 
+/* sizes the context's per-batch device buffers and pinned result arenas for batches of up to nReads reads (of up to
+ * params->maxReadLength - 1 bases) now instead of on first use: the double-buffered driver (SOAP4.cpp:424-441) calls it for every
+ * context before the batch loop so that no batch pays for allocations (which stall every context of the GPU while they run) */
+int  mp_reserve(mp_context *ctx, const mp_align_params *params, uint32_t nReads);
+
 /* index primitives, for parity tests against BWTOccValue / BWTSaValue / LT (2bwt-lib/BWT.c:597,968) */
 int  mp_occ(mp_context *ctx, const uint64_t *idx, const uint32_t *c, uint64_t *out, uint64_t n);
 int  mp_sa(mp_context *ctx, const uint64_t *saIndex, uint64_t *out, uint64_t n);

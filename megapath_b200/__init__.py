@@ -84,6 +84,7 @@ def lib():
         L.mp_destroy.argtypes = [C.c_void_p]
         L.mp_clone.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.mp_index_prepare.argtypes = [C.c_void_p, C.c_void_p]
+        L.mp_reserve.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.mp_index_load.argtypes = [C.c_void_p, C.c_char_p]
         L.mp_index_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mp_index_build.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
@@ -243,6 +244,10 @@ class Context:
     def index_prepare(self, params):
         """Builds the K-mer presence filter for these parameters now (before clone())."""
         self._check(self.L.mp_index_prepare(self.h, C.byref(params)))
+
+    def reserve(self, params, n_reads):
+        """Pre-sizes the per-batch buffers for batches of up to n_reads reads (mp_reserve)."""
+        self._check(self.L.mp_reserve(self.h, C.byref(params), int(n_reads)))
 
     def has_index(self):
         return getattr(self, "_has_index", False)

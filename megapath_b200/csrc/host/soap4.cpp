@@ -21,6 +21,7 @@
 #include <string.h>
 #include <ctype.h>
 #include <zlib.h>
+#include <sys/stat.h>
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -919,6 +920,15 @@ int main(int argc, char **argv)
                 if (mp_clone(owners[g], &c)) { fprintf(stderr, "%s\n", mp_last_error()); return 1; }
                 contexts.push_back(c);
             }
+        }
+    }
+    {   // large inputs: size every context's batch buffers before the batch loop (part of the set-up time, like the index load) so that
+        // no batch pays for allocations; small inputs keep the lazy sizing
+        struct stat sb;
+        if (stat(opt.query1.c_str(), &sb) == 0 && sb.st_size > (off_t)(48 << 20)) {
+            uint32_t batchReads = 12 * 8192 * 128 / 6;
+            if (const char *e = getenv("MP_BATCH_READS")) { const long v = atol(e); if (v >= 64 && v <= (long)batchReads) batchReads = (uint32_t)v & ~63u; }
+            for (mp_context *c : contexts) if (mp_reserve(c, &P, batchReads)) { fprintf(stderr, "%s\n", mp_last_error()); return 1; }
         }
     }
     Annotation ann;

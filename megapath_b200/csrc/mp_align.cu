@@ -511,6 +511,47 @@ extern "C" int mp_dp_batch(mp_context *ctx,
     return 0;
 }
 
+// Sizes every per-batch buffer for batches of up to nReads reads now.  All of them grow on demand anyway; but the first batch of a
+// context would otherwise pay for a few dozen cudaMalloc / cudaMallocHost calls (tens of GB of traceback tables, pinned result
+// arenas), and every one of them stalls the kernels of the other contexts on the same GPU while it runs.
+extern "C" int mp_reserve(mp_context *ctx, const mp_align_params *P, uint32_t nReads)
+{
+    if (!ctx || !P || nReads == 0) { mp_set_error("mp_reserve: bad argument"); return MP_ERR_ARG; }
+    MP_CUDA(cudaSetDevice(ctx->device));
+    const uint32_t inputMax = (uint32_t)P->maxReadLength, wpq = (inputMax + 15) / 16;
+    const uint64_t nPad = ((uint64_t)nReads + 31) / 32 * 32, nStrands = (uint64_t)nReads * 2, nPairs = nReads / 2;
+    const uint32_t maxReadLength = (inputMax / 4 + 1) * 4, maxDNALength = maxReadLength + 2 * MP_MARGIN(inputMax) + 8;
+    const uint32_t patStride = (maxDNALength + maxReadLength + 3) & ~3u;
+    const uint32_t CH = (uint32_t)std::min<uint64_t>(1u << 18, nPairs + nPairs / 4 + 1024);
+    const size_t resCap = (size_t)(nPairs + nPairs / 4) + 1024, hitSlots = (size_t)nReads * 3;
+    if (ctx->capSeeds < nStrands * 4) ctx->capSeeds = nStrands * 4;
+    if (ctx->capStubs < nStrands * 8) ctx->capStubs = nStrands * 8;
+    const int K = maxReadLength <= 160 ? 5 : maxReadLength <= 256 ? 8 : 10;
+    const size_t tableStride = (size_t)(((int)maxDNALength + 44) & ~3) * 32 * K;
+    size_t freeB = 0, totalB = 0; cudaMemGetInfo(&freeB, &totalB);
+    const size_t tableWant = std::min<size_t>((size_t)(CH >= (1u << 15) ? (1u << 18) : CH + 1) * tableStride, std::min<size_t>((size_t)24 << 30, freeB / 2));
+    if (ctx->dReadsIl.reserve(nPad * wpq * 4) || ctx->dReads.reserve(nPad * wpq * 4 + 64) || ctx->dLens.reserve((size_t)nReads * 4) ||
+        ctx->dCounters.reserve(16 * 8) || ctx->dHitsPerRead.reserve(((size_t)nReads + 1) * 4) || ctx->dHitStart.reserve(((size_t)nReads + 1) * 4) ||
+        ctx->dCursor.reserve(((size_t)nReads + 1) * 4) || ctx->dNPos.reserve((size_t)nReads * 4) || ctx->dNNeg.reserve((size_t)nReads * 4) ||
+        ctx->dSeeds.reserve(ctx->capSeeds * sizeof(MpSeed)) || ctx->dStubs.reserve(ctx->capStubs * 4) ||
+        ctx->dHits.reserve(hitSlots * sizeof(MpHit)) || ctx->dSeedPos.reserve(hitSlots * sizeof(mp_seed_pos)) ||
+        ctx->dCandCount.reserve(((size_t)nPairs + 1) * 4) || ctx->dCandStart.reserve(((size_t)nPairs + 1) * 4) ||
+        ctx->dCands.reserve((size_t)nPairs * 2 * sizeof(mp_candidate)) ||
+        ctx->dLT.reserve((size_t)CH * sizeof(MpDpTask)) || ctx->dRT.reserve((size_t)CH * sizeof(MpDpTask)) ||
+        ctx->dLO.reserve((size_t)CH * sizeof(MpDpOut)) || ctx->dRO.reserve((size_t)CH * sizeof(MpDpOut)) ||
+        ctx->dLP.reserve((size_t)CH * patStride) || ctx->dRP.reserve((size_t)CH * patStride) ||
+        ctx->dOk.reserve(((size_t)CH + 1) * 4) || ctx->dBytes.reserve(((size_t)CH + 1) * 8) || ctx->dIdx.reserve(((size_t)CH + 1) * 4) ||
+        ctx->dOff.reserve(((size_t)CH + 1) * 4) || ctx->dRes.reserve(resCap * sizeof(mp_pair_result)) || ctx->dRes2.reserve(resCap * sizeof(mp_pair_result)) ||
+        ctx->dKeep.reserve((resCap + 1) * 4) || ctx->dKeepPos.reserve((resCap + 1) * 4) || ctx->dTotals.reserve(32) ||
+        ctx->dCig.reserve(std::max<size_t>(resCap * 40, (size_t)1 << 20)) || ctx->dAligned.reserve((size_t)nPairs + 8) ||
+        ctx->dRefSeq.reserve((((size_t)CH * maxDNALength + 15) & ~(size_t)15) + (size_t)CH * 14 + 16) || ctx->dReadSeq.reserve((size_t)CH * maxReadLength) ||
+        ctx->dFill.reserve((size_t)CH * 16) || ctx->dExFlag.reserve(((size_t)CH + 1) * 4) || ctx->dExPos.reserve(((size_t)CH + 1) * 4) ||
+        ctx->dExIdx.reserve(((size_t)CH + 1) * 4) || ctx->dScanTmp.reserve((size_t)1 << 20) || ctx->dGather.reserve((size_t)(1 << 16) * 16) ||
+        (ctx->dTable.cap < tableWant && ctx->dTable.reserve(tableWant))) return MP_ERR_CUDA;
+    if (ctx->hPairs.reserve(resCap) || ctx->hCigars.reserve(resCap * 40)) return MP_ERR_CUDA;
+    return 0;
+}
+
 extern "C" int mp_align_pairs(mp_context *ctx, const mp_align_params *params, mp_results *out)
 {
     if (!ctx || !params || !out) { mp_set_error("mp_align_pairs: null argument"); return MP_ERR_ARG; }
