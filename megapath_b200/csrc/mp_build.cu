@@ -22,6 +22,7 @@
 #include <vector>
 
 int mpi_relayout_words(mp_context *ctx, const uint32_t *dWords, uint64_t n);
+int mpb_build_large(mp_context *ctx, uint64_t n);       // mp_build_large.cu
 
 #define SYM_PER_KEY 21
 
@@ -151,7 +152,8 @@ static inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)(
 extern "C" int mp_index_build(mp_context *ctx, const uint8_t *text2bit, uint64_t n)
 {
     if (!ctx || !text2bit || n < 32) { mp_set_error("mp_index_build: null argument or text shorter than 32 bases"); return MP_ERR_ARG; }
-    if (n + 1 >= 0xFFFFFFF0ull) { mp_set_error("mp_index_build: the GPU builder indexes up to 4.29 Gbp (32-bit suffix indices); load 2bwt-builder files for larger texts"); return MP_ERR_CAPACITY; }
+    // texts of 2^32 bases and more take the bucketed builder of mp_build_large.cu (MP_BUILD_LARGE=1 forces it: parity tests on small texts)
+    const bool large = n + 1 >= 0xFFFFFFF0ull || (getenv("MP_BUILD_LARGE") && getenv("MP_BUILD_LARGE")[0] == '1');
     MP_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     ctx->hasIndex = false; ctx->bloomK = 0; ctx->ix.sa32 = nullptr; ctx->dSa32.release();
@@ -167,6 +169,7 @@ extern "C" int mp_index_build(mp_context *ctx, const uint8_t *text2bit, uint64_t
         MP_CUDA(cudaStreamSynchronize(st));
     }
     const uint8_t *pac = ctx->dPac.as<uint8_t>();
+    if (large) { MP_CUDA(cudaStreamSynchronize(st)); return mpb_build_large(ctx, n); }
 
     DevBuf keysA, keysB, valsA, valsB, rankOf, tmpRank, tmpFlag, tmpDst, sortTmp, scanTmp;
     auto fail = [&](int rc) { keysA.release(); keysB.release(); valsA.release(); valsB.release(); rankOf.release(); tmpRank.release();

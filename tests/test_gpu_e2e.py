@@ -304,3 +304,57 @@ def test_e2e_builder_with_ambiguity_runs(workdir):
     assert hr == ho and len(rr) == len(ro) == 3000
     for x, y in zip(ro, rr):
         assert x == y, (x, y)
+
+
+@needs_ref
+def test_e2e_text_beyond_2_to_32(workdir):
+    """BASELINE config 3 in small: a 4.4 Gbp synthetic reference (> 2^32 bases: 64-bit positions everywhere, bucketed index builder, sampled
+    suffix array with LF walks, no dense 32-bit SA), soap4-nt2.ini -F -top 95, against the reference binary on the same index files.
+    Needs ~60 GB of HBM, ~12 GB of /tmp and a few minutes; skipped when the box cannot hold it or MP_SKIP_HUGE is set."""
+    import shutil
+    import subprocess
+    import torch
+    import megapath_b200 as mp
+    import bench
+    from conftest import REF_DIR
+    if os.environ.get("MP_SKIP_HUGE"):
+        pytest.skip("MP_SKIP_HUGE set")
+    free, total = torch.cuda.mem_get_info(0)
+    if free < 80e9 or shutil.disk_usage("/tmp").free < 20e9:
+        pytest.skip("not enough HBM or /tmp space for the 4.4 Gbp index")
+    d = "/tmp/mp_huge"
+    os.makedirs(d, exist_ok=True)
+    n, nseq = 4_400_000_000, 40
+    dev = torch.device("cuda", 0)
+    prefix = os.path.join(d, "huge.index")
+    codes = bench.gen_ref_codes(n, 17, dev)
+    bounds = bench.ref_bounds(n, nseq, 17)
+    # near-duplicate "genomes": copies of 3 Mbp stretches with 1 % substitutions, so that -top 95 lists are not trivial
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    for k in range(24):
+        src, dst, ln = int(bounds[k % nseq]) + 1000, int(bounds[(k * 7 + 3) % nseq]) + 2_000_000 + 4_000_000 * (k // nseq), 3_000_000
+        blk = codes[src:src + ln].clone()
+        mut = torch.rand(ln, device=dev, generator=g) < 0.01
+        blk[mut] = (blk[mut] + torch.randint(1, 4, (int(mut.sum()),), device=dev, generator=g, dtype=torch.uint8)) & 3
+        codes[dst:dst + ln] = blk
+    ctx = mp.Context(0)
+    ctx.index_build_codes(codes, bounds, prefix)
+    info = ctx.index_info()
+    assert info["textLength"] == n > 2 ** 32
+    bt = torch.from_numpy(bounds).to(dev)
+    reads = bench.gen_batch(codes, bt, 100_000, 23, 150, "divergent", 0.02, 0.05).cpu().numpy()
+    # a third of the pairs from the last 300 Mbp: positions above 2^32
+    hi = bench.gen_batch(codes[-300_000_000:], torch.tensor([0, 300_000_000], device=dev), 30_000, 29, 150, "subs", 0.0, 0.0).cpu().numpy()
+    reads[:60_000] = hi
+    del codes
+    ctx.close()
+    torch.cuda.empty_cache()
+    fqp = os.path.join(d, "huge")
+    bench.write_fastq_sample(fqp, reads)
+    ref = run_ref_raw(d, prefix, fqp + "_1.fq", fqp + "_2.fq", "hugeref", 151, "soap4-nt2.ini", ["-F", "-nc", "-top", "95"], threads=os.cpu_count() or 8)
+    got = run_our_soap4(d, prefix, fqp + "_1.fq", fqp + "_2.fq", "hugeour", 151, ini="soap4-nt2.ini", extra=("-F", "-nc", "-top", "95"))
+    want = canon_fastq(ref)
+    assert want.count(b"SCORE:") == 200_000 and want.count(b"SCORE:0;") < 40_000
+    assert canon_fastq(got) == want, first_diff(canon_fastq(got), want)
+    shutil.rmtree(d, ignore_errors=True)

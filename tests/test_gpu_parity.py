@@ -118,8 +118,9 @@ def test_gpu_errors_are_loud(small_ref):
     c.close()
 
 
+@pytest.mark.parametrize("large", [False, True])
 @pytest.mark.parametrize("total,nseq,repeat_frac,seed", [(300000, 6, 0.05, 42), (70001, 1, 0.3, 5), (131072 + 255, 3, 0.0, 9), (65536 * 3, 2, 0.6, 11)])
-def test_gpu_index_build_matches_reference_builder(workdir, total, nseq, repeat_frac, seed):
+def test_gpu_index_build_matches_reference_builder(workdir, total, nseq, repeat_frac, seed, large, monkeypatch):
     """mp_index_build + mp_index_save against the files 2bwt-builder writes for the same text
     (2BWT-Builder.c; BWTConstruct.c:994-1393; LTConstruct.c:46-96; HSP.c:560-699): byte-identical."""
     import os
@@ -130,6 +131,8 @@ def test_gpu_index_build_matches_reference_builder(workdir, total, nseq, repeat_
     from tools import synth
     if not have_ref():
         pytest.skip("oracle/_ref not built")
+    if large:
+        monkeypatch.setenv("MP_BUILD_LARGE", "1")       # the bucketed builder that texts >= 2^32 take (mp_build_large.cu)
     d = os.path.join(workdir, "b%d" % total)
     os.makedirs(d, exist_ok=True)
     seq, bounds = synth.make_ref(total, nseq, seed=seed, repeat_frac=repeat_frac)
