@@ -42,6 +42,11 @@ CONFIGS = {
     # cfg2: human-filtering stage; the configuration the metric is quoted on
     "cfg2": dict(ref_mbp=3100.0, nseq=24, read_len=150, model="subs", unalignable=0.01, one_random=0.01, ini="soap4.ini",
                  about="150bp pairs vs a 3.1 Gbp human-sized synthetic reference (24 seqs), soap4.ini -L 151 -u 750; 1% unalignable pairs, 1% one-mate-random"),
+    # cfg3: NT classification stage at the largest size the box's disk and the reference arm's run time allow by default (the text is
+    # beyond 2^32 bases: 64-bit positions, bucketed index builder, sampled SA); --ref-mbp raises it (DESIGN.md has the 60 Gbp HBM budget)
+    "cfg3": dict(ref_mbp=8000.0, nseq=400, read_len=150, model="subs", unalignable=0.02, one_random=0.02, ini="soap4-nt2.ini", dups=200,
+                 about="150bp pairs vs an 8 Gbp synthetic multi-genome reference (400 seqs, 200 planted 3 Mbp near-duplicates at 1% divergence), "
+                       "soap4-nt2.ini -L 151 -u 750 -top 95; 2% unalignable pairs, 2% one-mate-random"),
     # cfg4: DP-heavy: most reads carry an indel, 5 % of the pairs have one random mate (single-end DP + mate rescue with 752-wide tables)
     "cfg4": dict(ref_mbp=3100.0, nseq=24, read_len=150, model="divergent", unalignable=0.0, one_random=0.05, ini="soap4.ini",
                  about="DP-heavy 150bp pairs (4% substitutions, 0.5% 1-3bp deletions, 0.5% 1-3bp insertions per base; 5% of the pairs with one random mate) "
@@ -107,6 +112,30 @@ def gen_ref_codes(n, seed, device):
         m = min(CH, n - o)
         out[o:o + m] = torch.randint(0, 4, (m,), dtype=torch.uint8, device=device, generator=g)
     return out
+
+
+def make_reference(args, device):
+    """-> (codes on the device, sequence bounds): uniform i.i.d. ACGT; configs with "dups" get that many near-duplicate 3 Mbp blocks
+    (1 % substitutions) copied between sequences, so that multi-hit / -top lists are not trivial."""
+    import torch
+    n = int(args.cfg["ref_mbp"] * 1e6)
+    bounds = ref_bounds(n, args.cfg["nseq"], 42)
+    codes = gen_ref_codes(n, 42, device)
+    nd = int(args.cfg.get("dups", 0))
+    if nd:
+        g = torch.Generator(device=device)
+        g.manual_seed(77)
+        nseq, ln = args.cfg["nseq"], 3_000_000
+        for k in range(nd):
+            a, b = k % nseq, (k * 7 + 3) % nseq
+            if bounds[a + 1] - bounds[a] < 2 * ln + 2000 or bounds[b + 1] - bounds[b] < 2 * ln + 2000:
+                continue
+            src, dst = int(bounds[a]) + 1000, int(bounds[b + 1]) - ln - 1000
+            blk = codes[src:src + ln].clone()
+            mut = torch.rand(ln, device=device, generator=g) < 0.01
+            blk[mut] = (blk[mut] + torch.randint(1, 4, (int(mut.sum()),), device=device, generator=g, dtype=torch.uint8)) & 3
+            codes[dst:dst + ln] = blk
+    return codes, bounds
 
 
 def gen_batch(ref_codes, bounds_t, npairs, seed, read_len=150, model="subs", unalignable=0.01, one_random=0.01):
@@ -278,7 +307,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 def workload_dir(args):
     n = int(args.cfg["ref_mbp"] * 1e6)
-    return os.path.join(args.workdir, "ref%d_%d" % (n, args.cfg["nseq"])), n
+    return os.path.join(args.workdir, "ref%d_%d_%d" % (n, args.cfg["nseq"], int(args.cfg.get("dups", 0)))), n
 
 
 def sample_prefix(args, tag, npairs):
@@ -293,8 +322,7 @@ def ensure_index(args, ctx, device, rank, world):
     d, n = workload_dir(args)
     prefix = os.path.join(d, "ref.index")
     ready = os.path.join(d, "READY")
-    bounds = ref_bounds(n, args.cfg["nseq"], 42)
-    ref_codes = gen_ref_codes(n, 42, device)
+    ref_codes, bounds = make_reference(args, device)
     t0 = time.time()
     if rank == 0 and not os.path.exists(ready):
         os.makedirs(d, exist_ok=True)
@@ -334,8 +362,7 @@ def prepare(args):
     ctx = mp.Context(0)
     d, n = workload_dir(args)
     prefix = os.path.join(d, "ref.index")
-    bounds = ref_bounds(n, args.cfg["nseq"], 42)
-    ref_codes = gen_ref_codes(n, 42, device)
+    ref_codes, bounds = make_reference(args, device)
     if not os.path.exists(os.path.join(d, "READY")):
         os.makedirs(d, exist_ok=True)
         ctx.index_build_codes(ref_codes, bounds, prefix)
@@ -643,6 +670,15 @@ def run(args, saved_stdout):
     value = total_pairs / (dev_ms_max / 1e3)
     e2e = total_pairs / (e2e_ms_max / 1e3)
 
+    score40 = None
+    if args.config == "cfg3":
+        # the NT stage's downstream score cutoff (reassign / genKrakenReport, runMegaPath.sh:247-256) is applied to soap4's per-read best
+        # score; report which fraction of the reads of one batch passes it (untimed)
+        ctx.batch_upload_ptr(batches[0].data_ptr(), lens, wpq)
+        full = ctx.align_pairs(P)
+        best = full["pairs"][full["pairs"]["pad"] == 1]
+        score40 = float(((best["score_1"] >= 40).sum() + (best["score_2"] >= 40).sum()) / (2.0 * args.pairs_per_step))
+        del full, best
     hbm_peak, hbm_kind = measured_peak()
     # ---- roofline denominators MEASURED_PEAKS.json does not hold, measured now on this GPU ----
     try:
@@ -700,6 +736,8 @@ def run(args, saved_stdout):
            "gpu_launches": int(launches), "roofline": roof,
            "aligned_fraction": acc_pairs_all / (args.pairs_per_step * args.steps * world),
            "index_prepare_s": t_index}
+    if score40 is not None:
+        out["reads_with_score_ge_40_fraction"] = score40
     if cpu_legs:
         for c in ctxs[1:]:
             c.close()

@@ -145,6 +145,12 @@ __global__ void k_count_syms(const uint32_t *__restrict__ words, uint64_t nWords
     }
 }
 
+__global__ void k_sa_subsample(const uint64_t *__restrict__ in, uint64_t nOut, uint64_t step, uint64_t *__restrict__ out)
+{
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nOut) out[t] = in[t * step];
+}
+
 struct MaxU32 { __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; } };
 
 static inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
@@ -324,7 +330,7 @@ extern "C" int mp_index_save(mp_context *ctx, const char *prefix)
 {
     if (!ctx || !prefix) { mp_set_error("mp_index_save: null argument"); return MP_ERR_ARG; }
     if (!ctx->hasIndex) { mp_set_error("mp_index_save: no index resident"); return MP_ERR_STATE; }
-    if (ctx->saInterval != 16) { mp_set_error("mp_index_save: only saInterval 16 can be exported"); return MP_ERR_STATE; }
+    if (ctx->saInterval > 16 || (ctx->saInterval & (ctx->saInterval - 1))) { mp_set_error("mp_index_save: saInterval %llu cannot be exported as the 1/16 samples of the .sa format", (unsigned long long)ctx->saInterval); return MP_ERR_STATE; }
     MP_CUDA(cudaSetDevice(ctx->device));
     const std::string p(prefix);
     const uint64_t n = ctx->ix.n, nBlocks = ctx->ix.nBlocks;
@@ -377,7 +383,14 @@ extern "C" int mp_index_save(mp_context *ctx, const char *prefix)
         std::vector<uint64_t> sa(nSa + 6);
         memcpy(sa.data(), hdr, 40);
         sa[5] = 16;
-        MP_CUDA(cudaMemcpy(sa.data() + 6, ctx->dSa.p, nSa * 8, cudaMemcpyDeviceToHost));
+        if (ctx->saInterval == 16) MP_CUDA(cudaMemcpy(sa.data() + 6, ctx->dSa.p, nSa * 8, cudaMemcpyDeviceToHost));
+        else {                                       // the resident index samples more densely: every (16 / interval)-th sample goes to the file
+            DevBuf tmp;
+            if (tmp.reserve(nSa * 8)) return MP_ERR_CUDA;
+            (++g_mp_launches), k_sa_subsample<<<grid_for(nSa, 256), 256>>>(ctx->dSa.as<uint64_t>(), nSa, 16 / ctx->saInterval, tmp.as<uint64_t>());
+            MP_CUDA(cudaMemcpy(sa.data() + 6, tmp.p, nSa * 8, cudaMemcpyDeviceToHost));
+            tmp.release();
+        }
         sa[6] = n;
         if (int rc = write_all(p + ".sa", nullptr, 0, sa.data(), sa.size() * 8)) return rc;
     }

@@ -183,7 +183,15 @@ int mpb_build_large(mp_context *ctx, uint64_t n)
     const uint64_t N = n + 1;
     const int B = n < (1ull << 34) ? 3 : 4;
     int nBuckets = 1; for (int s = 0; s < B; ++s) nBuckets *= 5;
-    const uint32_t saShift = 4;
+    // SA sampling of the RESIDENT index: every lookup walks LF steps until it reaches a sampled SA index (geometric, mean interval - 1
+    // dependent 64-byte gathers), so the interval is as small as HBM allows: 4 when n/4 samples of 8 bytes fit in 30 % of what is free
+    // (8 Gbp: 16 GB), else 8, else the file format's 16.  mp_index_save subsamples to the 1/16 the .sa file holds.
+    uint32_t saShift = 4;
+    {
+        size_t freeB = 0, totalB = 0; cudaMemGetInfo(&freeB, &totalB);
+        for (uint32_t sh = 2; sh <= 4; ++sh) if ((double)((n >> sh) + 2) * 8.0 <= 0.30 * (double)freeB) { saShift = sh; break; }
+        if (const char *e = getenv("MP_SA_SHIFT")) { const int v = atoi(e); if (v >= 0 && v <= 4) saShift = (uint32_t)v; }
+    }
     DevBuf dHist, dRaw, dIsa, bSuf, bSuf2, bKey, bKey2, bPerm, bPerm2, bGrp, bGrp2, bG2, bG2b, bA, bB, bC, bD, bSa, sortTmp, scanTmp, dCur;
     auto fail = [&](int rc) { for (DevBuf *b : { &dHist, &dRaw, &dIsa, &bSuf, &bSuf2, &bKey, &bKey2, &bPerm, &bPerm2, &bGrp, &bGrp2, &bG2, &bG2b, &bA, &bB, &bC, &bD, &bSa, &sortTmp, &scanTmp, &dCur }) b->release(); return rc; };
     // ---- bucket sizes ----
@@ -198,7 +206,7 @@ int mpb_build_large(mp_context *ctx, uint64_t n)
     if (tot != N) { mp_set_error("mp_index_build: bucket histogram does not add up"); return fail(MP_ERR_STATE); }
     if (maxB >= 0xFFFFFFF0ull) { mp_set_error("mp_index_build: a suffix bucket holds %llu suffixes (32-bit bucket indexing)", maxB); return fail(MP_ERR_CAPACITY); }
     // ---- outputs that live for the whole build ----
-    const uint64_t rawWords = (N + 15) / 16, nSa = (n + 16) / 16;
+    const uint64_t rawWords = (N + 15) / 16, nSa = (n >> saShift) + 1;
     if (dRaw.reserve(rawWords * 4) || ctx->dSa.reserve(nSa * 8)) return fail(MP_ERR_CUDA);
     MP_CUDA(cudaMemsetAsync(dRaw.p, 0, rawWords * 4, st));
     MP_CUDA(cudaMemsetAsync(dIsa.p, 0xFF, 8, st));
@@ -281,7 +289,7 @@ int mpb_build_large(mp_context *ctx, uint64_t n)
     ctx->ix.cum[0] = 0;
     for (int c = 0; c < 4; ++c) ctx->ix.cum[c + 1] = ctx->ix.cum[c] + hc[c];
     if (ctx->ix.cum[4] != n) { dWords.release(); mp_set_error("mp_index_build: symbol counts do not add up"); return fail(MP_ERR_STATE); }
-    ctx->ix.sa = ctx->dSa.as<uint64_t>(); ctx->ix.saShift = saShift; ctx->saInterval = 16;
+    ctx->ix.sa = ctx->dSa.as<uint64_t>(); ctx->ix.saShift = saShift; ctx->saInterval = 1ull << saShift;
     ctx->ix.sa32 = nullptr; ctx->dSa32.release();
     if (int rc = mpi_relayout_words(ctx, dWords.as<uint32_t>(), n)) { dWords.release(); return fail(rc); }
     dWords.release();

@@ -147,7 +147,8 @@ struct mp_context {
     std::vector<mp_single_result> hSingles;
     PinnedBuf<char> hCigars;
     std::vector<uint32_t> hLens;            // host copy of the batch's read lengths (stages S2/S3)
-    DevBuf dAligned, dGather;               // per-pair "placed by deep DP" flags; seeds of unplaced reads
+    DevBuf dAligned, dGather;               // per-pair "placed by deep DP" flags; (dGather: unused scratch kept for mp_reserve)
+    DevBuf dS2Counts, dS2Start, dS2Tasks, dS2Res;   // stage S2 on the device: kept seeds per read, task offsets, tasks, results
 };
 
 // mp_index.cu

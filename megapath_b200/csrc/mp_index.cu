@@ -131,6 +131,12 @@ __global__ void k_densify_sa(MpIndexView ix, uint32_t *__restrict__ out, uint64_
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) out[i] = (uint32_t)mp_sa(ix, i);      // ix.sa32 is still null here: sampled walk
 }
+// texts of 2^32 bases and more: no dense 32-bit array, but a denser 64-bit sample than the file's 1/16 shortens every LF walk
+__global__ void k_resample_sa(MpIndexView ix, uint64_t *__restrict__ out, uint64_t count, uint32_t newShift)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = i == 0 ? ~0ull : mp_sa(ix, i << newShift);
+}
 
 int mpi_load(mp_context *ctx, const char *prefix)
 {
@@ -223,6 +229,22 @@ int mpi_load(mp_context *ctx, const char *prefix)
         MP_CUDA(cudaGetLastError());
         MP_CUDA(cudaDeviceSynchronize());
         ctx->ix.sa32 = ctx->dSa32.as<uint32_t>();
+    }
+    if (!ctx->ix.sa32 && !(dense && dense[0] == '0') && ctx->ix.saShift > 2) {
+        // no dense array (text >= 2^32): resample the file's samples to every 4th (or 8th) SA index when that fits 30 % of free HBM
+        cudaMemGetInfo(&freeB, &totalB);
+        for (uint32_t sh = 2; sh < ctx->ix.saShift; ++sh) {
+            const uint64_t cnt = (n >> sh) + 1;
+            if ((double)cnt * 8.0 > 0.30 * (double)freeB) continue;
+            DevBuf fresh;
+            if (fresh.reserve(cnt * 8)) return MP_ERR_CUDA;
+            (++g_mp_launches), k_resample_sa<<<(unsigned)((cnt + 255) / 256), 256>>>(ctx->ix, fresh.as<uint64_t>(), cnt, sh);
+            MP_CUDA(cudaGetLastError());
+            MP_CUDA(cudaDeviceSynchronize());
+            ctx->dSa.release(); ctx->dSa = fresh; fresh.p = nullptr; fresh.cap = 0;
+            ctx->ix.sa = ctx->dSa.as<uint64_t>(); ctx->ix.saShift = sh; ctx->saInterval = 1ull << sh;
+            break;
+        }
     }
     ctx->hbmBytes = ctx->dBlocks.cap + ctx->dSuper.cap + ctx->dSa.cap + ctx->dSa32.cap + ctx->dLkt.cap + ctx->dPac.cap;
     ctx->hasIndex = true;

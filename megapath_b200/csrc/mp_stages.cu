@@ -10,48 +10,21 @@
 //       HalfEndAlgnBatch::pack                                     DV-DPfunctions.cpp:1151-1231
 //       DP_Space::algnmtCPUThread + DPOutputThread                 DV-DPfunctions.cpp:1476-1747
 //
-// These stages see only the pairs stage S1 could not place (a few percent of a batch).  The DP itself
-// (ref-window extraction from the HBM text, fill, traceback) runs in the same kernels as S1; the list
-// plumbing around it (seed thinning, the reference's sort orders, per-pair grouping) is host code that
-// follows the reference's own containers and std::sort calls so that tie orders match.
+// These stages see only the pairs stage S1 could not place.  Stage S2 runs on the device from end to end: the seeds of every
+// unplaced read are merged, ordered (with libstdc++'s own std::sort algorithm, mp_stdsort.h, because the reference's unstable sort
+// decides which equally long seeds survive the cut) and capped by k_single_merge, turned into DP tasks, aligned by the same kernels
+// as S1, and assembled into SingleAlgnmtResult records + CIGAR text by k_single_measure / k_single_write; the host receives the
+// compact result list only.  Stage S3 (mate rescue) works on that list -- a few records per unplaced pair -- and keeps its list
+// plumbing (the reference's sort orders, the "last four hits" rule, per-pair grouping) on the host.
 #include "mp_context.h"
 #include "mp_cigar.h"
+#include "mp_stdsort.h"
+#include <cub/device/device_scan.cuh>
 #include <algorithm>
 #include <tuple>
 #include <string.h>
 
 namespace {
-
-struct SCand { uint32_t readID; uint32_t strand; uint64_t pos; uint32_t seedLen; };
-
-// RadixTraitsCandidateInfo (DV-DPForSingleReads.cpp:109-119)
-inline bool scand_less(const SCand &x, const SCand &y)
-{
-    return std::make_tuple(x.readID, x.strand, x.pos, x.seedLen) < std::make_tuple(y.readID, y.strand, y.pos, y.seedLen);
-}
-
-// singleMerge (DV-DPfunctions.cpp:295-342); `c` ends with the 0x7FFFFFFF sentinel
-void single_merge(const std::vector<SCand> &c, std::vector<SCand> &out)
-{
-    const SCand *p = c.data();
-    while (p->readID != 0x7FFFFFFFu) {
-        uint32_t readID = p->readID;
-        size_t oldSize = out.size();
-        for (; p->readID == readID; p++) {
-            if (p->seedLen < 17) continue;
-            out.push_back(*p);
-            while ((p + 1)->readID == readID) {
-                if ((p + 1)->pos < out.back().pos + 5 && out.back().strand == (p + 1)->strand) {   // DPS_DIVIDE_GAP
-                    if ((p + 1)->seedLen > out.back().seedLen) out.back() = *(p + 1);
-                } else break;
-                ++p;
-            }
-        }
-        std::sort(out.begin() + oldSize, out.end(), [](const SCand &a, const SCand &b) { return a.seedLen > b.seedLen; });
-        if (oldSize < out.size())
-            while (out.back().seedLen < out[oldSize].seedLen * 0.6) out.pop_back();
-    }
-}
 
 // encode one pattern -> cigar text appended to the arena; returns offset; fills stats
 // (a failed growth of the pinned arena returns 0xFFFFFFFF and leaves the error message set)
@@ -67,25 +40,115 @@ uint32_t append_cigar(PinnedBuf<char> &arena, const uint8_t *pat, int open, int 
 
 }  // namespace
 
-// seeds (SeedPos entries, DV-DPfunctions.cpp:2555-2594 / SeedPool.cpp:191-207) of every read whose pair the deep DP
-// did not place, appended in arbitrary order (the host sorts them as transferSeed does)
-struct GatherRec { uint64_t pos; uint32_t readID; uint32_t strand_len; };
-__global__ void k_gather_unplaced(const uint8_t *__restrict__ alignedPair, uint32_t nReads, const uint32_t *__restrict__ hitStart,
-                                  const uint32_t *__restrict__ nPos, const uint32_t *__restrict__ nNeg, const mp_seed_pos *__restrict__ sp,
-                                  GatherRec *__restrict__ out, uint32_t cap, unsigned int *__restrict__ cursor, unsigned int *__restrict__ nUnplacedPairs)
+// ---- stage S2 on the device ----
+// SingleDPWrapper::transferSeed + SingleEndSeedingEngine::singleMerge (DV-DPForSingleReads.cpp:121-215, DV-DPfunctions.cpp:295-342) for
+// one read per thread.  The read's SeedPos entries (SeedPool.cpp:191-207) are already in the order the reference sorts them into
+// (strand, position; k_merge writes them that way, and no two entries of a read share strand and position), so the radix sort of
+// RadixTraitsCandidateInfo is the identity here.  Kept seeds go to the read's own segment of a scratch array, in their final order.
+struct SSeed { uint64_t pos; uint32_t seedLen; uint32_t strand; };
+struct SSeedLonger { __host__ __device__ bool operator()(const SSeed &a, const SSeed &b) const { return a.seedLen > b.seedLen; } };
+__global__ void k_single_merge(const uint8_t *__restrict__ alignedPair, uint32_t nReads, const uint32_t *__restrict__ hitStart,
+                               const uint32_t *__restrict__ nPos, const uint32_t *__restrict__ nNeg, const mp_seed_pos *__restrict__ sp,
+                               SSeed *__restrict__ scratch, uint32_t *__restrict__ counts, unsigned int *__restrict__ nUnplacedPairs)
 {
-    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nReads || alignedPair[r >> 1]) return;
     if ((r & 1) == 0) atomicAdd(nUnplacedPairs, 1u);
-    const uint32_t c = nPos[r] + nNeg[r];
-    if (c == 0) return;
-    const uint32_t base = atomicAdd(cursor, c);
+    const uint32_t cnt = nPos[r] + nNeg[r];
+    if (cnt == 0) return;
     const mp_seed_pos *src = sp + hitStart[r];
-    for (uint32_t a = 0; a < c; ++a)
-        if (base + a < cap) {
-            GatherRec g; g.pos = src[a].pos; g.readID = r; g.strand_len = (src[a].strand_readID & 0x80000000u) | (src[a].paired_seedLength & 0x7FFFFFFFu);
-            out[base + a] = g;
+    SSeed *out = scratch + hitStart[r];
+    uint32_t nOut = 0;
+    for (uint32_t p = 0; p < cnt; ++p) {
+        SSeed c; c.pos = src[p].pos; c.seedLen = src[p].paired_seedLength & 0x7FFFFFFFu; c.strand = (src[p].strand_readID >> 31) + 1;
+        if (c.seedLen < 17) continue;
+        while (p + 1 < cnt) {                                       // seeds closer than DPS_DIVIDE_GAP collapse to the longest
+            SSeed d; d.pos = src[p + 1].pos; d.seedLen = src[p + 1].paired_seedLength & 0x7FFFFFFFu; d.strand = (src[p + 1].strand_readID >> 31) + 1;
+            if (d.pos < c.pos + 5 && c.strand == d.strand) { if (d.seedLen > c.seedLen) c = d; }
+            else break;
+            ++p;
         }
+        out[nOut++] = c;
+    }
+    mp_stdsort::sort(out, out + nOut, SSeedLonger());
+    if (nOut) while ((double)out[nOut - 1].seedLen < out[0].seedLen * 0.6) --nOut;
+    if (nOut > 200) nOut = 200;                                     // DV-DPForSingleReads.cpp:186-199
+    counts[r] = nOut;
+}
+// SingleEndAlgnBatch::pack (DV-DPfunctions.cpp:401-445): one DP task per kept seed
+__global__ void k_single_tasks(uint32_t nReads, const uint32_t *__restrict__ hitStart, const SSeed *__restrict__ scratch,
+                               const uint32_t *__restrict__ counts, const uint32_t *__restrict__ taskStart, const uint32_t *__restrict__ lens,
+                               uint64_t fullLen, MpDpTask *__restrict__ tasks, unsigned long long *__restrict__ work)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long cells = 0, nt = 0;
+    if (r < nReads) {
+        const uint32_t n = counts[r];
+        const SSeed *in = scratch + hitStart[r];
+        const uint32_t readLength = lens[r], margin = MP_MARGIN(readLength);
+        for (uint32_t k = 0; k < n; ++k) {
+            uint64_t start = in[k].pos - margin;
+            if (start >= fullLen) start = 0;
+            uint32_t dnaLen = readLength + margin * 2;
+            if (start + dnaLen > fullLen) dnaLen = (uint32_t)(fullLen - start);
+            MpDpTask t; t.refStart = start; t.refLen = dnaLen; t.readID = r; t.readLen = (uint16_t)readLength; t.strand = (uint8_t)in[k].strand;
+            t.valid = 1; t.cutoff = dp_cutoff(readLength);
+            t.diag = (int16_t)min(in[k].pos - start, (uint64_t)0x7fff);      // the seed's diagonal inside the window (hint only)
+            t.pad_ = (uint16_t)min(in[k].seedLen, 0xFFFFu);                  // seedAlignmentLength of the result
+            tasks[taskStart[r] + k] = t;
+            cells += (unsigned long long)dnaLen * readLength; ++nt;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) { cells += __shfl_xor_sync(0xffffffffu, cells, d); nt += __shfl_xor_sync(0xffffffffu, nt, d); }
+    if ((threadIdx.x & 31) == 0 && nt) { atomicAdd(&work[0], cells); atomicAdd(&work[1], nt); }
+}
+// SingleDP_Space::algnmtCPUThread (DV-DPfunctions.cpp:678-750): tasks that reached their cutoff become SingleAlgnmtResult records
+__global__ void k_single_measure(uint32_t n, const MpDpTask *__restrict__ tasks, const MpDpOut *__restrict__ outs, const uint8_t *__restrict__ pats,
+                                 uint32_t patStride, int open, int ext, uint32_t *__restrict__ okFlag, uint32_t *__restrict__ cigBytes)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const bool ok = outs[c].score >= tasks[c].cutoff;
+    uint32_t bytes = 0;
+    if (ok) bytes = (uint32_t)cigar_encode(pats + (size_t)c * patStride, open, ext, nullptr, 0).textLen + 1;
+    okFlag[c] = ok; cigBytes[c] = bytes;
+}
+__global__ void k_single_write(uint32_t n, const MpDpTask *__restrict__ tasks, const MpDpOut *__restrict__ outs, const uint8_t *__restrict__ pats,
+                               uint32_t patStride, int match, int mm, int open, int ext, uint32_t leftAnchor, const uint32_t *__restrict__ okFlag,
+                               const uint32_t *__restrict__ outIdx, const uint32_t *__restrict__ cigOff, uint32_t *__restrict__ totals, uint32_t cigCap,
+                               uint32_t cigArenaBase, mp_single_result *__restrict__ res, char *__restrict__ cig)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n || !okFlag[c]) return;
+    const uint32_t off = totals[1] + cigOff[c];
+    if ((uint64_t)totals[1] + cigOff[c + 1] > cigCap) { totals[4] = 1; return; }
+    const int textLen = (int)(cigOff[c + 1] - cigOff[c]) - 1;
+    const CigStats st = cigar_encode(pats + (size_t)c * patStride, open, ext, cig + off, textLen);
+    cig[off + textLen] = 0;
+    const MpDpTask t = tasks[c]; const MpDpOut o = outs[c];
+    mp_single_result r; memset(&r, 0, sizeof r);
+    r.cigar = cigArenaBase + off;
+    r.readID = t.readID; r.strand = t.strand; r.seedAlignmentLength = t.pad_;
+    r.algnmt = t.refStart + o.hitLoc; r.score = o.score;
+    r.startPos = t.refStart; r.refDpLength = t.refLen; r.peLeftAnchor = leftAnchor;
+    const int L = (int)t.readLen - st.nI - st.nS;
+    const int numMis = (L * match + st.gapPenalty - o.score) / (match - mm);
+    r.editdist = st.nI + st.nD + numMis;
+    r.num_sameScore = (int32_t)o.count;
+    res[totals[0] + outIdx[c]] = r;
+}
+__global__ void k_add_totals2(const uint32_t *__restrict__ idxTotal, const uint32_t *__restrict__ offTotal, uint32_t *__restrict__ totals)
+{
+    totals[0] += *idxTotal; totals[1] += *offTotal;
+}
+static int scan_u32_s(mp_context *ctx, const uint32_t *in, uint32_t *out, uint64_t n)
+{
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, (int64_t)n, ctx->stream);
+    if (ctx->dScanTmp.reserve(tb)) return MP_ERR_CUDA;
+    cub::DeviceScan::ExclusiveSum(ctx->dScanTmp.p, tb, in, out, (int64_t)n, ctx->stream);
+    return 0;
 }
 
 // host task list -> DP on the device -> host outputs (chunked)
@@ -121,85 +184,80 @@ int mps_single_and_rescue(mp_context *ctx, const mp_align_params *P, mp_results 
     }
     const std::vector<uint32_t> &lens = ctx->hLens;
     MpTrace tr;
-    std::vector<SCand> cand;
-    {
-        unsigned int *dCur = (unsigned int *)(ctx->dCounters.as<unsigned long long>() + 13);       // [13]: cursor, unplaced pairs
-        size_t cap = std::max<size_t>(ctx->dGather.cap / sizeof(GatherRec), (size_t)1 << 16);
-        unsigned int hcur[2] = { 0, 0 };
-        for (int attempt = 0; attempt < 2; ++attempt) {
-            if (ctx->dGather.reserve(cap * sizeof(GatherRec))) return MP_ERR_CUDA;
-            MP_CUDA(cudaMemsetAsync(dCur, 0, 8, st));
-            (++g_mp_launches), k_gather_unplaced<<<(nReads + 255) / 256, 256, 0, st>>>(ctx->dAligned.as<uint8_t>(), nReads, ctx->dHitStart.as<uint32_t>(),
-                ctx->dNPos.as<uint32_t>(), ctx->dNNeg.as<uint32_t>(), ctx->dSeedPos.as<mp_seed_pos>(), ctx->dGather.as<GatherRec>(), (uint32_t)cap, dCur, dCur + 1);
-            MP_CUDA(cudaGetLastError());
-            MP_CUDA(cudaMemcpyAsync(hcur, dCur, 8, cudaMemcpyDeviceToHost, st));
-            MP_CUDA(cudaStreamSynchronize(st));
-            if (hcur[0] <= cap) break;
-            cap = (size_t)hcur[0] + 1024;
-        }
-        if (hcur[1] == 0) return 0;                       // every pair was placed by the deep DP
-        std::vector<GatherRec> g(hcur[0]);
-        if (hcur[0]) MP_CUDA(cudaMemcpy(g.data(), ctx->dGather.p, (size_t)hcur[0] * sizeof(GatherRec), cudaMemcpyDeviceToHost));
-        cand.resize(g.size());
-        for (size_t i = 0; i < g.size(); ++i) {
-            SCand c; c.readID = g[i].readID; c.strand = (g[i].strand_len >> 31) + 1; c.pos = g[i].pos; c.seedLen = g[i].strand_len & 0x7FFFFFFFu;
-            cand[i] = c;
-        }
-    }
-    tr.mark("  s2 gather seeds");
-    SCand sentinel; sentinel.readID = 0x7FFFFFFFu; sentinel.strand = 2; sentinel.pos = 0xFFFFFFFFull; sentinel.seedLen = 0xFFFFFFFFu;
-    cand.push_back(sentinel);
-    std::sort(cand.begin(), cand.end(), scand_less);
-    std::vector<SCand> merged, canStream;
-    single_merge(cand, merged);
-    for (size_t i = 0, j; i < merged.size(); i = j) {                       // at most 200 per read (:186-199)
-        j = i + 1;
-        while (j < merged.size() && merged[j].readID == merged[i].readID) ++j;
-        for (size_t k = i; k < j && k < i + 200; ++k) canStream.push_back(merged[k]);
-    }
-    // ---- S2 DP ----
     const uint32_t inputMax = (uint32_t)P->maxReadLength;
     const uint32_t maxReadLength = (inputMax / 4 + 1) * 4;
     const uint32_t maxDNALengthS = maxReadLength + 2 * MP_MARGIN(inputMax) + 8;
     MpDpParams dp; dp.mismatch = P->mismatchScore; dp.open = P->openGapScore; dp.clipLt = P->softClipLeft; dp.clipRt = P->softClipRight;
-    std::vector<MpDpTask> tasks(canStream.size());
-    for (size_t i = 0; i < canStream.size(); ++i) {
-        const SCand &c = canStream[i];
-        uint32_t readLength = lens[c.readID];
-        uint32_t margin = MP_MARGIN(readLength);
-        uint64_t start = c.pos - margin;
-        if (start >= fullLen) start = 0;
-        uint32_t dnaLen = readLength + margin * 2;
-        if (start + dnaLen > fullLen) dnaLen = (uint32_t)(fullLen - start);
-        MpDpTask t; memset(&t, 0, sizeof t);
-        t.refStart = start; t.refLen = dnaLen; t.readID = c.readID; t.readLen = (uint16_t)readLength; t.strand = (uint8_t)c.strand;
-        t.valid = 1; t.cutoff = dp_cutoff(readLength);
-        t.diag = (int16_t)std::min<uint64_t>(c.pos - start, 0x7fff);          // the seed's diagonal inside the window (hint only)
-        tasks[i] = t;
-        cells += (uint64_t)dnaLen * readLength; ++tasksRun;
-    }
-    tr.mark("  s2 merge+tasks");
-    std::vector<MpDpOut> outs; std::vector<uint8_t> pats;
-    uint32_t patStride = (maxDNALengthS + maxReadLength + 3) & ~3u;
-    if (int rc = mpd_run_host_tasks(ctx, tasks, maxDNALengthS, maxReadLength, dp, outs, pats, patStride)) return rc;
-    tr.mark("  s2 dp");
     std::vector<mp_single_result> &S = ctx->hSingles;
     PinnedBuf<char> &HC = ctx->hCigars;
-    for (size_t i = 0; i < tasks.size(); ++i) {
-        if (outs[i].score < tasks[i].cutoff) continue;
-        CigStats st;
-        mp_single_result r; memset(&r, 0, sizeof r);
-        r.cigar = append_cigar(HC, pats.data() + i * patStride, P->openGapScore, P->extendGapScore, st);
-        if (r.cigar == 0xFFFFFFFFu) return MP_ERR_CUDA;
-        r.readID = tasks[i].readID; r.strand = tasks[i].strand; r.seedAlignmentLength = canStream[i].seedLen;
-        r.algnmt = tasks[i].refStart + outs[i].hitLoc; r.score = outs[i].score;
-        r.startPos = tasks[i].refStart; r.refDpLength = tasks[i].refLen; r.peLeftAnchor = maxDNALengthS;
-        int L = (int)tasks[i].readLen - st.nI - st.nS;
-        int numMis = (L * P->matchScore + st.gapPenalty - outs[i].score) / (P->matchScore - P->mismatchScore);
-        r.editdist = st.nI + st.nD + numMis;
-        r.num_sameScore = (int32_t)outs[i].count;
-        S.push_back(r);
+    // ---- S2: merge / order / cap the seeds of every unplaced read, one DP task per kept seed (all on the device) ----
+    if (ctx->dS2Counts.reserve(((size_t)nReads + 1) * 4) || ctx->dS2Start.reserve(((size_t)nReads + 1) * 4) || ctx->dTotals.reserve(16 * 4) ||
+        ctx->dCounters.reserve(16 * 8)) return MP_ERR_CUDA;
+    uint32_t *dTot = ctx->dTotals.as<uint32_t>();                              // [0] results, [1] cigar bytes, [4] overflow, [5] unplaced pairs
+    unsigned long long *dWork = ctx->dCounters.as<unsigned long long>() + 11; // cells, tasks of this stage
+    MP_CUDA(cudaMemsetAsync(ctx->dS2Counts.p, 0, ((size_t)nReads + 1) * 4, st));
+    MP_CUDA(cudaMemsetAsync(dTot, 0, 8 * 4, st));
+    MP_CUDA(cudaMemsetAsync(dWork, 0, 16, st));
+    (++g_mp_launches), k_single_merge<<<(nReads + 127) / 128, 128, 0, st>>>(ctx->dAligned.as<uint8_t>(), nReads, ctx->dHitStart.as<uint32_t>(),
+        ctx->dNPos.as<uint32_t>(), ctx->dNNeg.as<uint32_t>(), ctx->dSeedPos.as<mp_seed_pos>(), ctx->dHits.as<SSeed>(), ctx->dS2Counts.as<uint32_t>(), dTot + 5);
+    if (scan_u32_s(ctx, ctx->dS2Counts.as<uint32_t>(), ctx->dS2Start.as<uint32_t>(), (uint64_t)nReads + 1)) return MP_ERR_CUDA;
+    uint32_t nTasks = 0, nUnplaced = 0;
+    MP_CUDA(cudaMemcpyAsync(&nTasks, ctx->dS2Start.as<uint32_t>() + nReads, 4, cudaMemcpyDeviceToHost, st));
+    MP_CUDA(cudaMemcpyAsync(&nUnplaced, dTot + 5, 4, cudaMemcpyDeviceToHost, st));
+    MP_CUDA(cudaStreamSynchronize(st));
+    tr.mark("  s2 merge (device)");
+    if (nUnplaced == 0) return 0;                          // every pair was placed by the deep DP
+    const uint32_t patStride = (maxDNALengthS + maxReadLength + 3) & ~3u;
+    const uint32_t CH = 1u << 18;
+    const uint32_t chunkCap = std::min<uint32_t>(CH, nTasks + 1);
+    if (ctx->dS2Tasks.reserve(((size_t)nTasks + 1) * sizeof(MpDpTask)) || ctx->dS2Res.reserve(((size_t)nTasks + 1) * sizeof(mp_single_result)) ||
+        ctx->dLO.reserve((size_t)chunkCap * sizeof(MpDpOut)) || ctx->dLP.reserve((size_t)chunkCap * patStride) ||
+        ctx->dOk.reserve(((size_t)chunkCap + 1) * 4) || ctx->dBytes.reserve(((size_t)chunkCap + 1) * 8) ||
+        ctx->dIdx.reserve(((size_t)chunkCap + 1) * 4) || ctx->dOff.reserve(((size_t)chunkCap + 1) * 4)) return MP_ERR_CUDA;
+    if (nTasks)
+        (++g_mp_launches), k_single_tasks<<<(nReads + 127) / 128, 128, 0, st>>>(nReads, ctx->dHitStart.as<uint32_t>(), ctx->dHits.as<SSeed>(),
+            ctx->dS2Counts.as<uint32_t>(), ctx->dS2Start.as<uint32_t>(), ctx->dLens.as<uint32_t>(), fullLen, ctx->dS2Tasks.as<MpDpTask>(), dWork);
+    const uint32_t cigArenaBase = (uint32_t)HC.size();
+    size_t cigCap = std::max<size_t>(ctx->dCig.cap, (size_t)1 << 20);
+    uint32_t tot[8] = { 0 };
+    for (int attempt = 0; attempt < 3 && nTasks; ++attempt) {
+        if (ctx->dCig.reserve(cigCap)) return MP_ERR_CUDA;
+        MP_CUDA(cudaMemsetAsync(dTot, 0, 5 * 4, st));
+        for (uint32_t base = 0; base < nTasks; base += CH) {
+            const uint32_t n = std::min<uint32_t>(CH, nTasks - base);
+            const MpDpTask *tk = ctx->dS2Tasks.as<MpDpTask>() + base;
+            const unsigned g = (n + 127) / 128;
+            if (int rc = mpd_run_tasks(ctx, tk, n, maxDNALengthS, maxReadLength, dp, ctx->dLO.as<MpDpOut>(), ctx->dLP.as<uint8_t>(), patStride)) return rc;
+            MP_CUDA(cudaMemsetAsync(ctx->dOk.p, 0, ((size_t)n + 1) * 4, st));
+            MP_CUDA(cudaMemsetAsync(ctx->dBytes.p, 0, ((size_t)n + 1) * 4, st));
+            (++g_mp_launches), k_single_measure<<<g, 128, 0, st>>>(n, tk, ctx->dLO.as<MpDpOut>(), ctx->dLP.as<uint8_t>(), patStride, P->openGapScore, P->extendGapScore,
+                                                                   ctx->dOk.as<uint32_t>(), ctx->dBytes.as<uint32_t>());
+            if (scan_u32_s(ctx, ctx->dOk.as<uint32_t>(), ctx->dIdx.as<uint32_t>(), (uint64_t)n + 1)) return MP_ERR_CUDA;
+            if (scan_u32_s(ctx, ctx->dBytes.as<uint32_t>(), ctx->dOff.as<uint32_t>(), (uint64_t)n + 1)) return MP_ERR_CUDA;
+            (++g_mp_launches), k_single_write<<<g, 128, 0, st>>>(n, tk, ctx->dLO.as<MpDpOut>(), ctx->dLP.as<uint8_t>(), patStride, P->matchScore, P->mismatchScore,
+                P->openGapScore, P->extendGapScore, maxDNALengthS, ctx->dOk.as<uint32_t>(), ctx->dIdx.as<uint32_t>(), ctx->dOff.as<uint32_t>(), dTot,
+                (uint32_t)std::min<size_t>(cigCap, 0xFFFFFFF0u), cigArenaBase, ctx->dS2Res.as<mp_single_result>(), ctx->dCig.as<char>());
+            (++g_mp_launches), k_add_totals2<<<1, 1, 0, st>>>(ctx->dIdx.as<uint32_t>() + n, ctx->dOff.as<uint32_t>() + n, dTot);
+            MP_CUDA(cudaGetLastError());
+        }
+        MP_CUDA(cudaMemcpyAsync(tot, dTot, sizeof tot, cudaMemcpyDeviceToHost, st));
+        MP_CUDA(cudaStreamSynchronize(st));
+        if (!tot[4]) break;
+        cigCap = (size_t)tot[1] + tot[1] / 8 + (1 << 20);
+        if (attempt == 2) { mp_set_error("CIGAR arena of stage S2 overflowed repeatedly"); return MP_ERR_CAPACITY; }
     }
+    tr.mark("  s2 dp + assemble (device)");
+    S.resize(tot[0]);
+    if (HC.resize((size_t)cigArenaBase + tot[1])) return MP_ERR_CUDA;
+    if (tot[0]) MP_CUDA(cudaMemcpyAsync(S.data(), ctx->dS2Res.p, (size_t)tot[0] * sizeof(mp_single_result), cudaMemcpyDeviceToHost, st));
+    if (tot[1]) MP_CUDA(cudaMemcpyAsync(HC.data() + cigArenaBase, ctx->dCig.p, tot[1], cudaMemcpyDeviceToHost, st));
+    {
+        unsigned long long hw[2];
+        MP_CUDA(cudaMemcpyAsync(hw, dWork, sizeof hw, cudaMemcpyDeviceToHost, st));
+        MP_CUDA(cudaStreamSynchronize(st));
+        cells += hw[0]; tasksRun += hw[1];
+    }
+    tr.mark("  s2 download");
     // counters as DPSOutputThread keeps them: reads with >= 1 result; results after per-read de-duplication
     for (size_t i = 0, j; i < S.size(); i = j) {
         j = i + 1;
