@@ -150,6 +150,12 @@ __global__ void k_sa_subsample(const uint64_t *__restrict__ in, uint64_t nOut, u
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < nOut) out[t] = in[t * step];
 }
+// the same from the 40-bit sample arrays of a text >= 2^32 (entry 0 is overwritten by the caller)
+__global__ void k_sa40_subsample(const uint32_t *__restrict__ lo, const uint8_t *__restrict__ hi, uint64_t nOut, uint64_t step, uint64_t *__restrict__ out)
+{
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nOut) out[t] = (uint64_t)lo[t * step] | ((uint64_t)hi[t * step] << 32);
+}
 
 struct MaxU32 { __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; } };
 
@@ -383,7 +389,13 @@ extern "C" int mp_index_save(mp_context *ctx, const char *prefix)
         std::vector<uint64_t> sa(nSa + 6);
         memcpy(sa.data(), hdr, 40);
         sa[5] = 16;
-        if (ctx->saInterval == 16) MP_CUDA(cudaMemcpy(sa.data() + 6, ctx->dSa.p, nSa * 8, cudaMemcpyDeviceToHost));
+        if (ctx->ix.sa40lo) {                       // 40-bit samples (texts >= 2^32) -> the file's u64 samples
+            DevBuf tmp;
+            if (tmp.reserve(nSa * 8)) return MP_ERR_CUDA;
+            (++g_mp_launches), k_sa40_subsample<<<grid_for(nSa, 256), 256>>>(ctx->ix.sa40lo, ctx->ix.sa40hi, nSa, 16 / ctx->saInterval, tmp.as<uint64_t>());
+            MP_CUDA(cudaMemcpy(sa.data() + 6, tmp.p, nSa * 8, cudaMemcpyDeviceToHost));
+            tmp.release();
+        } else if (ctx->saInterval == 16) MP_CUDA(cudaMemcpy(sa.data() + 6, ctx->dSa.p, nSa * 8, cudaMemcpyDeviceToHost));
         else {                                       // the resident index samples more densely: every (16 / interval)-th sample goes to the file
             DevBuf tmp;
             if (tmp.reserve(nSa * 8)) return MP_ERR_CUDA;

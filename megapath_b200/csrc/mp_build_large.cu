@@ -309,7 +309,8 @@ int mpb_build_large(mp_context *ctx, uint64_t n)
     fail(0);
     ctx->ix.lkt = ctx->dLkt.as<uint64_t>();
     ctx->ix.pac = pac;
-    ctx->hbmBytes = ctx->dBlocks.cap + ctx->dSuper.cap + ctx->dSa.cap + ctx->dLkt.cap + ctx->dPac.cap;
+    if (int rc = mpi_finish_sa(ctx)) return rc;
+    ctx->hbmBytes = ctx->dBlocks.cap + ctx->dSuper.cap + ctx->dSa.cap + ctx->dSa40Lo.cap + ctx->dSa40Hi.cap + ctx->dLkt.cap + ctx->dPac.cap;
     ctx->hasIndex = true; ctx->hasBatch = false; ctx->seeded = false;
     return 0;
 }

@@ -120,7 +120,7 @@ struct mp_context {
     // index
     bool hasIndex = false, sharedIndex = false;   // sharedIndex: index buffers belong to another context (mp_clone)
     MpIndexView ix;
-    DevBuf dBlocks, dSuper, dSa, dSa32, dLkt, dPac, dBloom;
+    DevBuf dBlocks, dSuper, dSa, dSa32, dSa40Lo, dSa40Hi, dLkt, dPac, dBloom;
     int bloomK = 0, bloomStride = 1, bloomSeedMin = 0; uint64_t bloomWords = 0; const void *bloomFor = nullptr;   // K-mer presence filter (mp_seed.cu)
     uint64_t hbmBytes = 0;
     std::vector<uint64_t> hSa; uint64_t saInterval = 16;   // kept for mp_index_save
@@ -153,6 +153,7 @@ struct mp_context {
 
 // mp_index.cu
 int mpi_load(mp_context *ctx, const char *prefix);
+int mpi_finish_sa(mp_context *ctx);      // texts >= 2^32: 40-bit SA samples at the densest rate the HBM budget allows
 int mpi_build_from_words(mp_context *ctx, const uint32_t *hBwtWords, uint64_t n, uint64_t inverseSa0, const uint64_t cum[5]);
 // mp_seed.cu
 int mps_seed_pairs(mp_context *ctx, const mp_align_params *P);

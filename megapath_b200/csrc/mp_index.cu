@@ -131,11 +131,42 @@ __global__ void k_densify_sa(MpIndexView ix, uint32_t *__restrict__ out, uint64_
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) out[i] = (uint32_t)mp_sa(ix, i);      // ix.sa32 is still null here: sampled walk
 }
-// texts of 2^32 bases and more: no dense 32-bit array, but a denser 64-bit sample than the file's 1/16 shortens every LF walk
-__global__ void k_resample_sa(MpIndexView ix, uint64_t *__restrict__ out, uint64_t count, uint32_t newShift)
+// texts of 2^32 bases and more: no 32-bit array; 40-bit samples (u32 + u8) at a denser rate than the resident u64 ones
+__global__ void k_sa40_build(MpIndexView ix, uint32_t *__restrict__ lo, uint8_t *__restrict__ hi, uint64_t count, uint32_t newShift)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) out[i] = i == 0 ? ~0ull : mp_sa(ix, i << newShift);
+    if (i >= count) return;
+    const uint64_t v = i == 0 ? 0 : mp_sa(ix, i << newShift);          // entry 0 (SA[0] = -1) is special-cased by mp_sa_sample
+    lo[i] = (uint32_t)v; hi[i] = (uint8_t)(v >> 32);
+}
+
+// Called once the u64 samples (ctx->dSa, ix.saShift) are resident.  Texts shorter than 2^32 keep them (the dense u32 array is built
+// by the callers); longer texts get 40-bit samples at the densest rate whose arrays fit 35 % of the free HBM -- every SA index
+// when possible (8 Gbp: 40 GB), so that an SA lookup is two small gathers instead of an LF walk -- and the u64 array is released.
+// MP_DENSE_SA=0 keeps the file's samples; MP_SA40=<shift> forces the 40-bit arrays at that shift whatever the text length (tests).
+int mpi_finish_sa(mp_context *ctx)
+{
+    ctx->ix.sa40lo = nullptr; ctx->ix.sa40hi = nullptr; ctx->dSa40Lo.release(); ctx->dSa40Hi.release();
+    const uint64_t n = ctx->ix.n;
+    const char *dense = getenv("MP_DENSE_SA"), *force = getenv("MP_SA40");
+    if (dense && dense[0] == '0') return 0;
+    if (ctx->ix.sa32) return 0;
+    if (!force && n + 1 < 0xFFFFFFF0ull) return 0;
+    size_t freeB = 0, totalB = 0; cudaMemGetInfo(&freeB, &totalB);
+    for (uint32_t sh = 0; sh <= ctx->ix.saShift; ++sh) {
+        if (force ? sh != (uint32_t)atoi(force) : (sh == ctx->ix.saShift && sh > 0)) continue;
+        const uint64_t cnt = (n >> sh) + 1;
+        if (!force && (double)cnt * 5.0 > 0.35 * (double)freeB) continue;
+        if (ctx->dSa40Lo.reserve(cnt * 4) || ctx->dSa40Hi.reserve(cnt)) return MP_ERR_CUDA;
+        (++g_mp_launches), k_sa40_build<<<(unsigned)((cnt + 255) / 256), 256>>>(ctx->ix, ctx->dSa40Lo.as<uint32_t>(), ctx->dSa40Hi.as<uint8_t>(), cnt, sh);
+        MP_CUDA(cudaGetLastError());
+        MP_CUDA(cudaDeviceSynchronize());
+        ctx->dSa.release(); ctx->ix.sa = nullptr;
+        ctx->ix.sa40lo = ctx->dSa40Lo.as<uint32_t>(); ctx->ix.sa40hi = ctx->dSa40Hi.as<uint8_t>();
+        ctx->ix.saShift = sh; ctx->saInterval = 1ull << sh;
+        break;
+    }
+    return 0;
 }
 
 int mpi_load(mp_context *ctx, const char *prefix)
@@ -223,30 +254,15 @@ int mpi_load(mp_context *ctx, const char *prefix)
     ctx->ix.sa32 = nullptr; ctx->dSa32.release();
     const char *dense = getenv("MP_DENSE_SA");
     size_t freeB = 0, totalB = 0; cudaMemGetInfo(&freeB, &totalB);
-    if (!(dense && dense[0] == '0') && n + 1 < 0xFFFFFFF0ull && (n + 1) * 4 < freeB / 2) {
+    if (!(dense && dense[0] == '0') && !getenv("MP_SA40") && n + 1 < 0xFFFFFFF0ull && (n + 1) * 4 < freeB / 2) {
         if (ctx->dSa32.reserve((n + 1) * 4)) return MP_ERR_CUDA;
         (++g_mp_launches), k_densify_sa<<<(unsigned)((n + 1 + 255) / 256), 256>>>(ctx->ix, ctx->dSa32.as<uint32_t>(), n + 1);
         MP_CUDA(cudaGetLastError());
         MP_CUDA(cudaDeviceSynchronize());
         ctx->ix.sa32 = ctx->dSa32.as<uint32_t>();
     }
-    if (!ctx->ix.sa32 && !(dense && dense[0] == '0') && ctx->ix.saShift > 2) {
-        // no dense array (text >= 2^32): resample the file's samples to every 4th (or 8th) SA index when that fits 30 % of free HBM
-        cudaMemGetInfo(&freeB, &totalB);
-        for (uint32_t sh = 2; sh < ctx->ix.saShift; ++sh) {
-            const uint64_t cnt = (n >> sh) + 1;
-            if ((double)cnt * 8.0 > 0.30 * (double)freeB) continue;
-            DevBuf fresh;
-            if (fresh.reserve(cnt * 8)) return MP_ERR_CUDA;
-            (++g_mp_launches), k_resample_sa<<<(unsigned)((cnt + 255) / 256), 256>>>(ctx->ix, fresh.as<uint64_t>(), cnt, sh);
-            MP_CUDA(cudaGetLastError());
-            MP_CUDA(cudaDeviceSynchronize());
-            ctx->dSa.release(); ctx->dSa = fresh; fresh.p = nullptr; fresh.cap = 0;
-            ctx->ix.sa = ctx->dSa.as<uint64_t>(); ctx->ix.saShift = sh; ctx->saInterval = 1ull << sh;
-            break;
-        }
-    }
-    ctx->hbmBytes = ctx->dBlocks.cap + ctx->dSuper.cap + ctx->dSa.cap + ctx->dSa32.cap + ctx->dLkt.cap + ctx->dPac.cap;
+    if (int rc = mpi_finish_sa(ctx)) return rc;
+    ctx->hbmBytes = ctx->dBlocks.cap + ctx->dSuper.cap + ctx->dSa.cap + ctx->dSa32.cap + ctx->dSa40Lo.cap + ctx->dSa40Hi.cap + ctx->dLkt.cap + ctx->dPac.cap;
     ctx->hasIndex = true;
     return 0;
 }

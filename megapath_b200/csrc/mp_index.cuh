@@ -14,6 +14,8 @@
 //   sa         : sampled suffix array, one value per saInterval SA indices (by index), as in the .sa file
 //   sa32       : the full suffix array as u32 when the text is shorter than 2^32 (12.4 GB for 3.1 Gbp, HBM has
 //                180 GB): an SA lookup is then one gather instead of a geometric(1/16) LF walk
+//   sa40lo/hi  : texts of 2^32 bases and more: 40-bit samples (u32 + u8 arrays) at the densest rate that fits the HBM
+//                budget -- every index (5 bytes per base: 40 GB for 8 Gbp) down to every 8th (37 GB for 60 Gbp)
 //   lkt        : 4^13 cumulative 13-mer counts
 //   pac        : packed text, 4 bases per byte, first base in the top 2 bits
 #pragma once
@@ -33,6 +35,8 @@ struct MpIndexView {
     const uint64_t *sa;      // (n + saInterval) / saInterval values, sa[0] = -1
     uint32_t saShift;        // log2(saInterval)
     const uint32_t *sa32;    // optional: the whole suffix array (n + 1 entries, texts < 4.29 Gbp); one gather per SA lookup
+    const uint32_t *sa40lo;  // optional (texts >= 2^32): 40-bit samples, one per 2^saShift SA indices, low 32 bits ...
+    const uint8_t *sa40hi;   // ... and bits 32..39; they replace `sa` (saShift 0 = the whole suffix array)
     const uint64_t *lkt;     // 4^13
     const uint8_t *pac;
 };
@@ -99,18 +103,28 @@ __device__ __forceinline__ uint64_t mp_lf(const MpIndexView &ix, uint64_t i)
     return mp_cum(ix, c) + mp_occ_raw(ix, p, c) + 1;
 }
 
+// SA value of an index that has a resident sample (any index when the array is dense; SA[0] reads as -1, BWT.c:241)
+__device__ __forceinline__ bool mp_sa_dense(const MpIndexView &ix) { return ix.sa32 != nullptr || (ix.sa40lo != nullptr && ix.saShift == 0); }
+__device__ __forceinline__ uint64_t mp_sa_sample(const MpIndexView &ix, uint64_t saIndex)
+{
+    if (ix.sa32) return saIndex == 0 ? ~0ull : (uint64_t)__ldg(ix.sa32 + saIndex);
+    if (ix.sa40lo) {
+        const uint64_t k = saIndex >> ix.saShift;
+        return saIndex == 0 ? ~0ull : (uint64_t)__ldg(ix.sa40lo + k) | ((uint64_t)__ldg(ix.sa40hi + k) << 32);
+    }
+    return __ldg(ix.sa + (saIndex >> ix.saShift));
+}
 // BWTSaValue (BWT.c:968-998)
 __device__ __forceinline__ uint64_t mp_sa(const MpIndexView &ix, uint64_t saIndex, uint32_t *steps = nullptr)
 {
-    if (ix.sa32) {             // dense SA: any sampling rate gives the same SA[i], this one costs one 4-byte gather
-        if (steps) *steps = 0;
-        return saIndex == 0 ? ~0ull : (uint64_t)__ldg(ix.sa32 + saIndex);
-    }
+    // dense SA: any sampling rate gives the same SA[i], this one costs one gather
     uint64_t skipped = 0;
-    const uint64_t mask = (1ull << ix.saShift) - 1;
-    while (saIndex & mask) { ++skipped; saIndex = mp_lf(ix, saIndex); }
+    if (!mp_sa_dense(ix)) {
+        const uint64_t mask = (1ull << ix.saShift) - 1;
+        while (saIndex & mask) { ++skipped; saIndex = mp_lf(ix, saIndex); }
+    }
     if (steps) *steps = (uint32_t)skipped;
-    return __ldg(ix.sa + (saIndex >> ix.saShift)) + skipped;
+    return mp_sa_sample(ix, saIndex) + skipped;
 }
 
 __device__ __forceinline__ uint32_t mp_text_base(const MpIndexView &ix, uint64_t pos)

@@ -182,173 +182,205 @@ __device__ __forceinline__ uint64_t group_reverse(uint64_t v)       // reverse t
     return ((v >> 1) & 0x5555555555555555ull) | ((v & 0x5555555555555555ull) << 1);
 }
 
-// one thread per read-strand, written as a state machine: every trip of the loop performs ONE unit of work of the lane's
-// current state (4 filter probes + LKT jump | one backward-search step | up to 16 text bases), so lanes of a warp that
-// are in different phases of their reads still share every trip instead of waiting for each other's inner loops
-__global__ void __launch_bounds__(128)
+// Persistent warps over a queue of read-strands.  A lane holds one read-strand at a time and the loop below is a state machine:
+// every trip performs ONE unit of work of the lane's current state (4 filter probes + LKT jump | one backward-search step | one LF
+// step of a sampled-SA lookup | up to 32 text bases), so lanes that are in different phases of their reads still share every trip.
+// A lane whose strand is finished takes the next one from the warp's chunk of the queue at the top of the next trip (the warp
+// fetches chunks of MMP_CHUNK strands with one atomic), so no lane waits for the slowest strand of its warp: the kernel is bound by
+// the latency of dependent gathers, and what counts is how many lanes have one in flight.
+#define MMP_CHUNK 128u
+__global__ void __launch_bounds__(128, 8)
 k_mmp(MpIndexView ix, const uint32_t *__restrict__ reads, const uint32_t *__restrict__ lens, uint32_t wpq,
       uint32_t nStrands, MmpDev P, MpSeed *__restrict__ seeds, uint32_t *__restrict__ stubs,
       unsigned long long *__restrict__ counters, uint32_t *__restrict__ hitsPerRead,
       uint32_t capSeeds, uint32_t capStubs, const unsigned long long *__restrict__ bloom, uint64_t bloomWords, int bloomK, int bloomStride)
 {
     const uint64_t n = ix.n;
-    unsigned long long nOcc = 0, nLkt = 0, nSaIn = 0, nLfIn = 0, nProbe = 0, nText = 0;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    enum { ST_SCAN, ST_STEP, ST_TEXT, ST_DONE };
+    uint32_t nOcc = 0, nLkt = 0, nSaIn = 0, nLfIn = 0, nProbe = 0, nText = 0;      // per lane: a few thousand per strand, a few dozen strands
+    enum { ST_SCAN, ST_STEP, ST_TEXT, ST_SA, ST_DONE };
     // Work order: first every read on the strand that matches its mate number (mate 1 '+', mate 2 '-': the strand an FR
     // library aligns on), then every read on the other strand, so that the lanes of a warp mostly share a state.
     const uint32_t nReadsK = nStrands >> 1;
-    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < nStrands; w += stride) {
-        const uint32_t group = w >= nReadsK, read = group ? w - nReadsK : w, strand = (read & 1u) ^ group;
-        const uint32_t s = read * 2 + strand;
-        const int len = (int)lens[read];
-        const uint32_t *rd = reads + (size_t)read * wpq;
-        int i = 0, seed_len = 0, last_seed_len = 0;
-        uint64_t l = 0, r = n, last_l = 0, last_r = n, p = 0;
-        int state = ST_SCAN;
-        while (state != ST_DONE) {
-            bool emit = false, resolved = false, finishing = false, haveNext = false;
-            uint64_t nextl = 0, nextr = 0;
-            if (state == ST_SCAN) {                                   // seed_len == 0: look for the next start worth searching
-                if (len - i < P.seedMinLength) { state = ST_DONE; continue; }
-                bool go = true;
-                if (bloom) {                                          // 4 probes in flight
-                    // Start i0 is decided by the bloomK-mer at p = the first multiple of bloomStride >= i0: a match of seedMinLength
-                    // bases from i0 covers [p, p + bloomK) because bloomK = seedMinLength - (bloomStride - 1).  One probe therefore
-                    // rules out up to bloomStride starts.
-                    const int lastStart = len - P.seedMinLength;
-                    const int p0 = (i + bloomStride - 1) / bloomStride * bloomStride;
-                    int m = 0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) if (p0 + j * bloomStride - bloomStride + 1 <= lastStart) m = j + 1;
-                    unsigned long long wv[4]; uint64_t mk[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        wv[j] = ~0ull; mk[j] = 0;
-                        if (j < m) { uint64_t wi; bloom_slot(scan_kmer(rd, len, p0 + j * bloomStride, strand, bloomK), bloomWords, wi, mk[j]); wv[j] = __ldg(bloom + wi); }
-                    }
-                    nProbe += m;
-                    int hit = m;
-#pragma unroll
-                    for (int j = 3; j >= 0; --j) if (j < m && (wv[j] & mk[j]) == mk[j]) hit = j;
-                    go = hit < m;
-                    if (go) i = max(i, p0 + hit * bloomStride - bloomStride + 1);      // first start that probe does not rule out
-                    else i = p0 + (m - 1) * bloomStride + 1;                             // every start up to the last probe is dead
-                }
-                if (go) {
-                    uint32_t key = lkt_key(rd, len, i, strand);
-                    nextl = key == 0 ? 1 : __ldg(ix.lkt + key - 1) + 1;
-                    nextr = __ldg(ix.lkt + key);
-                    i += 12; seed_len = 12; ++nLkt; haveNext = true;
-                }
-            } else if (state == ST_STEP) {                            // one backward-search step on a range of several suffixes
-                if (i >= len) { emit = true; finishing = true; }
-                else {
-                    uint32_t c = strand ? 3 - read_base(rd, i) : read_base(rd, len - 1 - i);
-                    uint64_t a = l - (l > ix.inverseSa0), b = (r + 1) - ((r + 1) > ix.inverseSa0);
-                    uint64_t ra, rb;
-                    occ_pair(ix, a, b, c, ra, rb);
-                    nextl = mp_cum(ix, c) + ra + 1;
-                    nextr = mp_cum(ix, c) + rb;
-                    nOcc += 2; haveNext = true;
-                }
-            } else {                                                  // ST_TEXT: single suffix at text position p, up to 32 bases per trip
-                if (i >= len) { emit = true; finishing = true; resolved = true; }
-                else {
-                    const int m = min(32, len - i);
-                    const uint64_t tw = text_window_before(ix, p);
-                    uint64_t d;
-                    int matched;
-                    if (strand) {                                     // c_t = 3 - read[i+t] against text[p-1-t]
-                        uint64_t rw = read_window(rd, i, 32);
-                        d = ~(rw ^ tw);                               // group == 0 where the bases agree
-                        d = (d | (d >> 1)) & 0x5555555555555555ull;
-                        matched = d ? (__ffsll((long long)d) - 1) >> 1 : 32;
-                    } else {                                          // c_t = read[len-1-i-t] against text[p-1-t]
-                        const int start = len - 1 - i - 31;
-                        uint64_t rw = start >= 0 ? read_window(rd, start, 32) : (read_window(rd, 0, 32) << (uint32_t)(-start * 2));
-                        d = rw ^ group_reverse(tw);                   // read[len-1-i-t] and text[p-1-t] both at group 31-t
-                        d = (d | (d >> 1)) & 0x5555555555555555ull;
-                        matched = d ? __clzll((long long)d) >> 1 : 32;
-                    }
-                    int lim = m; if ((uint64_t)lim > p) lim = (int)p;
-                    const bool failed = matched < lim || lim < m;     // a mismatch, or the text start reached, inside this read
-                    if (matched > lim) matched = lim;
-                    p -= matched; seed_len += matched; i += matched;
-                    nOcc += 2ull * matched; nText += matched;
-                    if (failed) { nOcc += 2; ++nText; emit = true; resolved = true; }
-                    else if (i >= len) { emit = true; finishing = true; resolved = true; }
-                }
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t saMask = (1ull << ix.saShift) - 1;
+    const bool saDense = mp_sa_dense(ix);
+    uint32_t chunkNext = 0, chunkEnd = 0;                             // warp-uniform: the warp's current piece of the queue
+    bool exhausted = false;
+    uint32_t read = 0, strand = 0, skipped = 0;
+    int len = 0, i = 0, seed_len = 0, last_seed_len = 0;
+    const uint32_t *rd = reads;
+    uint64_t l = 0, r = n, last_l = 0, last_r = n, p = 0;
+    int state = ST_DONE;
+    for (;;) {
+        // ---- lanes without a strand take the next ones of the warp's chunk ----
+        const uint32_t idle = __ballot_sync(0xffffffffu, state == ST_DONE);
+        if (idle) {
+            if (chunkNext == chunkEnd && !exhausted) {
+                uint32_t base = 0;
+                if (lane == 0) base = (uint32_t)min(atomicAdd(&counters[6], (unsigned long long)MMP_CHUNK), (unsigned long long)nStrands);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= nStrands) exhausted = true;
+                else { chunkNext = base; chunkEnd = base + min(MMP_CHUNK, nStrands - base); }
             }
-            if (haveNext) {
-                if (nextl <= nextr) {
-                    if (seed_len >= P.seedMinLength && nextr - nextl < r - l) { last_r = r; last_l = l; last_seed_len = seed_len; }
-                    l = nextl; r = nextr; ++seed_len; ++i;
-                    if (l == r) {
-                        uint32_t steps = 0;
-                        p = mp_sa(ix, l, &steps);
-                        ++nSaIn; nLfIn += steps;
-                        state = ST_TEXT;
-                    } else state = ST_STEP;
-                } else emit = true;
-            }
-            if (emit) {
-                // CHECK_AND_ADD_RANGE (DV-DPfunctions.cpp:2197-2219); x as at DV-DPfunctions.cpp:2252-2262, 2362-2372
-                int x = strand ? (finishing ? len : i) - seed_len : (finishing ? 0 : len - i);
-                int diff = 0;
-                if (seed_len >= P.seedMinLength) {
-                    if (seed_len >= P.reseedLen && last_r - last_l + 1 <= (uint64_t)P.seedSAsizeThreshold &&
-                        ((uint64_t)(seed_len - last_seed_len) <= (uint64_t)P.reseedAbsDiff ||
-                         seed_len * P.reseedRLTratio < (double)last_seed_len)) {
-                        diff = seed_len - last_seed_len;
-                        l = last_l; r = last_r; seed_len = last_seed_len;
-                        resolved = false;
-                    }
-                    uint64_t d = resolved ? 0 : r - l; if (d > (uint64_t)P.seedSAsizeThreshold) d = P.seedSAsizeThreshold;
-                    uint32_t cnt = (uint32_t)d + 1;
-                    // seed slot and hit range: the lanes of the warp that emit in this trip share one pair of atomics
-                    uint32_t slot, hb;
-                    {
-                        cg::coalesced_group grp = cg::coalesced_threads();
-                        const uint32_t before = cg::exclusive_scan(grp, cnt), total = cg::reduce(grp, cnt, cg::plus<uint32_t>());
-                        uint32_t s0 = 0, h0 = 0;
-                        if (grp.thread_rank() == 0) {
-                            s0 = (uint32_t)atomicAdd(&counters[0], (unsigned long long)grp.size());
-                            h0 = (uint32_t)atomicAdd(&counters[1], (unsigned long long)total);
-                        }
-                        slot = grp.shfl(s0, 0) + grp.thread_rank();
-                        hb = grp.shfl(h0, 0) + before;
-                    }
-                    atomicAdd(&hitsPerRead[read], cnt);
-                    if (slot < capSeeds) {
-                        MpSeed sd; sd.sa_l = resolved ? p : l; sd.strandIdx = s; sd.hitBase = hb;
-                        sd.query_offset = (uint16_t)(x & 0x3ff); sd.seed_len = (uint16_t)(seed_len & 0xfff);
-                        sd.sa_diff = (uint16_t)d; sd.pad = resolved ? 1 : 0;
-                        seeds[slot] = sd;
-                    }
-                    for (uint32_t k = 0; k < cnt; ++k) if (hb + k < capStubs) stubs[hb + k] = slot;
-                }
-                if (finishing) state = ST_DONE;
-                else {
-                    i -= diff;
-                    i -= min(seed_len, P.seedMinLength);
-                    ++i;
-                    l = 0; r = n; seed_len = 0; last_l = 0; last_r = n; last_seed_len = 0;
+            const uint32_t avail = chunkEnd - chunkNext;
+            if (avail) {
+                const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
+                if (state == ST_DONE && rank < avail) {
+                    const uint32_t w = chunkNext + rank;
+                    const uint32_t group = w >= nReadsK;
+                    read = group ? w - nReadsK : w; strand = (read & 1u) ^ group;
+                    len = (int)lens[read]; rd = reads + (size_t)read * wpq;
+                    i = 0; seed_len = 0; last_seed_len = 0; l = 0; r = n; last_l = 0; last_r = n; p = 0;
                     state = ST_SCAN;
                 }
+                chunkNext += min((uint32_t)__popc(idle), avail);
+            } else if (exhausted && idle == 0xffffffffu) break;
+        }
+        if (state == ST_DONE) continue;
+        bool emit = false, resolved = false, finishing = false, haveNext = false;
+        uint64_t nextl = 0, nextr = 0;
+        if (state == ST_SCAN) {                                   // seed_len == 0: look for the next start worth searching
+            if (len - i < P.seedMinLength) { state = ST_DONE; continue; }
+            bool go = true;
+            if (bloom) {                                          // 4 probes in flight
+                // A match of seedMinLength bases from start i0 covers the bloomK-mer at every p in [i0, i0 + bloomStride - 1]
+                // (bloomK = seedMinLength - (bloomStride - 1)), so the K-mer at p = i + bloomStride - 1 decides the bloomStride starts
+                // i .. p at once, the next probe the bloomStride starts after them, and so on.  (Anchoring the probes at the
+                // current start rather than on a fixed grid matters after a seed that ended on a mismatch: the scan resumes
+                // seedMinLength - 1 bases before it, and the first probe already spans the mismatch.)
+                const int lastStart = len - P.seedMinLength;
+                int m = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (i + j * bloomStride <= lastStart) m = j + 1;
+                unsigned long long wv[4]; uint64_t mk[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    wv[j] = ~0ull; mk[j] = 0;
+                    if (j < m) { uint64_t wi; bloom_slot(scan_kmer(rd, len, i + j * bloomStride + bloomStride - 1, strand, bloomK), bloomWords, wi, mk[j]); wv[j] = __ldg(bloom + wi); }
+                }
+                nProbe += m;
+                int hit = m;
+#pragma unroll
+                for (int j = 3; j >= 0; --j) if (j < m && (wv[j] & mk[j]) == mk[j]) hit = j;
+                go = hit < m;
+                i += hit * bloomStride;                           // first start the probes do not rule out (all dead: past the last probe)
+            }
+            if (go) {
+                uint32_t key = lkt_key(rd, len, i, strand);
+                nextl = key == 0 ? 1 : __ldg(ix.lkt + key - 1) + 1;
+                nextr = __ldg(ix.lkt + key);
+                i += 12; seed_len = 12; ++nLkt; haveNext = true;
+            }
+        } else if (state == ST_STEP) {                            // one backward-search step on a range of several suffixes
+            if (i >= len) { emit = true; finishing = true; }
+            else {
+                uint32_t c = strand ? 3 - read_base(rd, i) : read_base(rd, len - 1 - i);
+                uint64_t a = l - (l > ix.inverseSa0), b = (r + 1) - ((r + 1) > ix.inverseSa0);
+                uint64_t ra, rb;
+                occ_pair(ix, a, b, c, ra, rb);
+                nextl = mp_cum(ix, c) + ra + 1;
+                nextr = mp_cum(ix, c) + rb;
+                nOcc += 2; haveNext = true;
+            }
+        } else if (state == ST_SA) {                              // sampled SA: one LF step per trip until a sampled index (BWTSaValue, BWT.c:968-998)
+            p = mp_lf(ix, p); ++skipped; ++nLfIn;
+            if ((p & saMask) == 0) { p = mp_sa_sample(ix, p) + skipped; state = ST_TEXT; }
+        } else {                                                  // ST_TEXT: single suffix at text position p, up to 32 bases per trip
+            if (i >= len) { emit = true; finishing = true; resolved = true; }
+            else {
+                const int m = min(32, len - i);
+                const uint64_t tw = text_window_before(ix, p);
+                uint64_t d;
+                int matched;
+                if (strand) {                                     // c_t = 3 - read[i+t] against text[p-1-t]
+                    uint64_t rw = read_window(rd, i, 32);
+                    d = ~(rw ^ tw);                               // group == 0 where the bases agree
+                    d = (d | (d >> 1)) & 0x5555555555555555ull;
+                    matched = d ? (__ffsll((long long)d) - 1) >> 1 : 32;
+                } else {                                          // c_t = read[len-1-i-t] against text[p-1-t]
+                    const int start = len - 1 - i - 31;
+                    uint64_t rw = start >= 0 ? read_window(rd, start, 32) : (read_window(rd, 0, 32) << (uint32_t)(-start * 2));
+                    d = rw ^ group_reverse(tw);                   // read[len-1-i-t] and text[p-1-t] both at group 31-t
+                    d = (d | (d >> 1)) & 0x5555555555555555ull;
+                    matched = d ? __clzll((long long)d) >> 1 : 32;
+                }
+                int lim = m; if ((uint64_t)lim > p) lim = (int)p;
+                const bool failed = matched < lim || lim < m;     // a mismatch, or the text start reached, inside this read
+                if (matched > lim) matched = lim;
+                p -= matched; seed_len += matched; i += matched;
+                nOcc += 2u * (uint32_t)matched; nText += matched;
+                if (failed) { nOcc += 2; ++nText; emit = true; resolved = true; }
+                else if (i >= len) { emit = true; finishing = true; resolved = true; }
+            }
+        }
+        if (haveNext) {
+            if (nextl <= nextr) {
+                if (seed_len >= P.seedMinLength && nextr - nextl < r - l) { last_r = r; last_l = l; last_seed_len = seed_len; }
+                l = nextl; r = nextr; ++seed_len; ++i;
+                if (l == r) {                                     // a single suffix: look its text position up, then compare with the text
+                    ++nSaIn;
+                    if (saDense || (l & saMask) == 0) { p = mp_sa_sample(ix, l); state = ST_TEXT; }
+                    else { p = l; skipped = 0; state = ST_SA; }
+                } else state = ST_STEP;
+            } else emit = true;
+        }
+        if (emit) {
+            // CHECK_AND_ADD_RANGE (DV-DPfunctions.cpp:2197-2219); x as at DV-DPfunctions.cpp:2252-2262, 2362-2372
+            int x = strand ? (finishing ? len : i) - seed_len : (finishing ? 0 : len - i);
+            int diff = 0;
+            if (seed_len >= P.seedMinLength) {
+                if (seed_len >= P.reseedLen && last_r - last_l + 1 <= (uint64_t)P.seedSAsizeThreshold &&
+                    ((uint64_t)(seed_len - last_seed_len) <= (uint64_t)P.reseedAbsDiff ||
+                     seed_len * P.reseedRLTratio < (double)last_seed_len)) {
+                    diff = seed_len - last_seed_len;
+                    l = last_l; r = last_r; seed_len = last_seed_len;
+                    resolved = false;
+                }
+                uint64_t d = resolved ? 0 : r - l; if (d > (uint64_t)P.seedSAsizeThreshold) d = P.seedSAsizeThreshold;
+                uint32_t cnt = (uint32_t)d + 1;
+                // seed slot and hit range: the lanes of the warp that emit in this trip share one pair of atomics
+                uint32_t slot, hb;
+                {
+                    cg::coalesced_group grp = cg::coalesced_threads();
+                    const uint32_t before = cg::exclusive_scan(grp, cnt), total = cg::reduce(grp, cnt, cg::plus<uint32_t>());
+                    uint32_t s0 = 0, h0 = 0;
+                    if (grp.thread_rank() == 0) {
+                        s0 = (uint32_t)atomicAdd(&counters[0], (unsigned long long)grp.size());
+                        h0 = (uint32_t)atomicAdd(&counters[1], (unsigned long long)total);
+                    }
+                    slot = grp.shfl(s0, 0) + grp.thread_rank();
+                    hb = grp.shfl(h0, 0) + before;
+                }
+                atomicAdd(&hitsPerRead[read], cnt);
+                if (slot < capSeeds) {
+                    MpSeed sd; sd.sa_l = resolved ? p : l; sd.strandIdx = read * 2 + strand; sd.hitBase = hb;
+                    sd.query_offset = (uint16_t)(x & 0x3ff); sd.seed_len = (uint16_t)(seed_len & 0xfff);
+                    sd.sa_diff = (uint16_t)d; sd.pad = resolved ? 1 : 0;
+                    seeds[slot] = sd;
+                }
+                for (uint32_t k = 0; k < cnt; ++k) if (hb + k < capStubs) stubs[hb + k] = slot;
+            }
+            if (finishing) state = ST_DONE;
+            else {
+                i -= diff;
+                i -= min(seed_len, P.seedMinLength);
+                ++i;
+                l = 0; r = n; seed_len = 0; last_l = 0; last_r = n; last_seed_len = 0;
+                state = ST_SCAN;
             }
         }
     }
     // per-warp reduction of the work counters
+    unsigned long long wOcc = nOcc, wLkt = nLkt, wSa = nSaIn, wLf = nLfIn, wProbe = nProbe, wText = nText;
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
-        nOcc += __shfl_xor_sync(0xffffffffu, nOcc, d); nLkt += __shfl_xor_sync(0xffffffffu, nLkt, d);
-        nSaIn += __shfl_xor_sync(0xffffffffu, nSaIn, d); nLfIn += __shfl_xor_sync(0xffffffffu, nLfIn, d);
-        nProbe += __shfl_xor_sync(0xffffffffu, nProbe, d); nText += __shfl_xor_sync(0xffffffffu, nText, d);
+        wOcc += __shfl_xor_sync(0xffffffffu, wOcc, d); wLkt += __shfl_xor_sync(0xffffffffu, wLkt, d);
+        wSa += __shfl_xor_sync(0xffffffffu, wSa, d); wLf += __shfl_xor_sync(0xffffffffu, wLf, d);
+        wProbe += __shfl_xor_sync(0xffffffffu, wProbe, d); wText += __shfl_xor_sync(0xffffffffu, wText, d);
     }
     if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&counters[2], nOcc); atomicAdd(&counters[4], nLkt); atomicAdd(&counters[7], nSaIn); atomicAdd(&counters[8], nLfIn);
-        atomicAdd(&counters[9], nProbe); atomicAdd(&counters[10], nText);
+        atomicAdd(&counters[2], wOcc); atomicAdd(&counters[4], wLkt); atomicAdd(&counters[7], wSa); atomicAdd(&counters[8], wLf);
+        atomicAdd(&counters[9], wProbe); atomicAdd(&counters[10], wText);
     }
 }
 
@@ -587,15 +619,16 @@ int mps_seed_pairs(mp_context *ctx, const mp_align_params *AP)
     if (ctx->capStubs < (uint64_t)nStrands * 8) ctx->capStubs = (uint64_t)nStrands * 8;
     if (int rc = ensure_bloom(ctx, P.seedMinLength)) return rc;
     unsigned long long hc[16];
-    int dev = 0, nSM = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, dev);
+    int dev = 0, nSM = 148, mmpBlocks = 8; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&mmpBlocks, k_mmp, 128, 0) != cudaSuccess || mmpBlocks < 1) mmpBlocks = 8;
     MP_CUDA(cudaEventRecord(ctx->ev[0], st));
     for (int attempt = 0; attempt < 4; ++attempt) {
         if (ctx->capSeeds > 0xFFFFFFF0ull || ctx->capStubs > 0xFFFFFFF0ull) { mp_set_error("seed buffers exceed 32-bit indexing; use smaller batches"); return MP_ERR_CAPACITY; }
         if (ctx->dSeeds.reserve(ctx->capSeeds * sizeof(MpSeed)) || ctx->dStubs.reserve(ctx->capStubs * 4)) return MP_ERR_CUDA;
         MP_CUDA(cudaMemsetAsync(ctx->dCounters.p, 0, 16 * 8, st));
         MP_CUDA(cudaMemsetAsync(ctx->dHitsPerRead.p, 0, ((size_t)nReads + 1) * 4, st));
-        // grid-stride over read-strands; the two strands of a read sit in neighbouring lanes
-        (++g_mp_launches), k_mmp<<<nSM * 16, 128, 0, st>>>(ctx->ix, ctx->dReads.as<uint32_t>(), ctx->dLens.as<uint32_t>(), ctx->wpq, nStrands, P,
+        // persistent warps: as many blocks as the device holds at once, every warp pulls chunks of read-strands from counters[6]
+        (++g_mp_launches), k_mmp<<<nSM * mmpBlocks, 128, 0, st>>>(ctx->ix, ctx->dReads.as<uint32_t>(), ctx->dLens.as<uint32_t>(), ctx->wpq, nStrands, P,
                                       ctx->dSeeds.as<MpSeed>(), ctx->dStubs.as<uint32_t>(), ctx->dCounters.as<unsigned long long>(),
                                       ctx->dHitsPerRead.as<uint32_t>(), (uint32_t)ctx->capSeeds, (uint32_t)ctx->capStubs,
                                       ctx->bloomK ? ctx->dBloom.as<unsigned long long>() : nullptr, ctx->bloomWords, ctx->bloomK, ctx->bloomStride);

@@ -254,11 +254,14 @@ def test_gpu_dp_other_score_parameters(ctx, mm, go):
         assert got == want, (mm, go, t, got, want)
 
 
-def test_gpu_sampled_sa_path(workdir, small_ref, monkeypatch):
-    """MP_DENSE_SA=0: only the file's 1/16 SA samples are resident and every SA lookup on the hot path is an LF walk (the only mode
-    possible for texts that do not fit a dense 32-bit array).  Seeds, candidates and stage-S1 results must not change."""
+@pytest.mark.parametrize("env,val,walks", [("MP_DENSE_SA", "0", True), ("MP_SA40", "0", False), ("MP_SA40", "2", True), ("MP_SA40", "3", True)])
+def test_gpu_sampled_sa_path(workdir, small_ref, monkeypatch, env, val, walks):
+    """The SA representations of texts that do not fit a dense 32-bit array.  MP_DENSE_SA=0: only the file's 1/16 samples (u64) are
+    resident and every SA lookup on the hot path is an LF walk.  MP_SA40=<shift>: the 40-bit sample arrays (u32 + u8) that texts of
+    2^32 bases and more get, forced here on a small text -- every index (shift 0: no walks) or every 4th / 8th.  Seeds, candidates and
+    stage-S1 results must not change."""
     import megapath_b200 as mp
-    monkeypatch.setenv("MP_DENSE_SA", "0")
+    monkeypatch.setenv(env, val)
     c = mp.Context(0)
     try:
         c.index_load(small_ref["prefix"])
@@ -285,7 +288,7 @@ def test_gpu_sampled_sa_path(workdir, small_ref, monkeypatch):
             for g, w in zip(res["pairs"], want):
                 for f in ("readID", "algnmt_1", "algnmt_2", "score_1", "score_2", "num_sameScore_1", "num_sameScore_2", "insertSize"):
                     assert int(g[f]) == int(w[f]), (name, f, g, w)
-            assert res["n_lf"] > 0               # the walks really happened
+            assert (res["n_lf"] > 0) == walks     # the walks really happened (or, with a sample per index, did not)
     finally:
         c.close()
 
