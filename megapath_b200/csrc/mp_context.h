@@ -143,12 +143,13 @@ struct mp_context {
     DevBuf dRes2, dKeep, dKeepPos, dTotals;                                      // stage S1 per-pair dedup / best pick (k_pair_ready)
     // results (host, owned until release)
     PinnedBuf<mp_pair_result> hPairs;
-    std::vector<mp_pair_result> hRescued;
-    std::vector<mp_single_result> hSingles;
+    PinnedBuf<mp_pair_result> hRescued;
+    PinnedBuf<mp_single_result> hSingles;
     PinnedBuf<char> hCigars;
     std::vector<uint32_t> hLens;            // host copy of the batch's read lengths (stages S2/S3)
     DevBuf dAligned, dGather;               // per-pair "placed by deep DP" flags; (dGather: unused scratch kept for mp_reserve)
     DevBuf dS2Counts, dS2Start, dS2Tasks, dS2Res;   // stage S2 on the device: kept seeds per read, task offsets, tasks, results
+    DevBuf dRsSlotTasks, dRsSlotInfo, dRsFlag, dRsPos, dRsTasks, dRsInfo, dRsRec, dRsOut, dRsKeep, dRsKeepPos;   // stage S3 (mate rescue) on the device
 };
 
 // mp_index.cu
@@ -162,8 +163,6 @@ struct MpDpParams { int clipLt, clipRt, mismatch, open; };
 // tasks (device) -> outs (device); sequences are extracted from the index / uploaded reads
 int mpd_run_tasks(mp_context *ctx, const MpDpTask *dTasks, uint32_t nTasks, uint32_t maxRefLen, uint32_t maxReadLen,
                   const MpDpParams &P, MpDpOut *dOuts, uint8_t *dPatterns, uint32_t patStride);
-int mpd_run_host_tasks(mp_context *ctx, const std::vector<MpDpTask> &tasks, uint32_t maxRefLen, uint32_t maxReadLen, const MpDpParams &P,
-                       std::vector<MpDpOut> &outs, std::vector<uint8_t> &pats, uint32_t patStride);
 // mp_stages.cu: single-end DP + default DP for the pairs stage S1 left unaligned
 int mps_single_and_rescue(mp_context *ctx, const mp_align_params *P, mp_results *out, uint64_t &cells, uint64_t &tasksRun);
 // explicit sequences (one byte per base, stride maxRefLen / maxReadLen)

@@ -14,8 +14,10 @@
 // unplaced read are merged, ordered (with libstdc++'s own std::sort algorithm, mp_stdsort.h, because the reference's unstable sort
 // decides which equally long seeds survive the cut) and capped by k_single_merge, turned into DP tasks, aligned by the same kernels
 // as S1, and assembled into SingleAlgnmtResult records + CIGAR text by k_single_measure / k_single_write; the host receives the
-// compact result list only.  Stage S3 (mate rescue) works on that list -- a few records per unplaced pair -- and keeps its list
-// plumbing (the reference's sort orders, the "last four hits" rule, per-pair grouping) on the host.
+// compact result list only.  Stage S3 (mate rescue) stays on the device as well: k_rescue_select orders a read's single-end hits the
+// way the reference's two sorts do and keeps "the last four" (DV-DPfunctions.cpp:1053-1055), one rescue window per kept hit is
+// aligned with the 752-wide instantiation of the same DP kernels, k_rescue_write assembles the AlgnmtDPResult records + CIGAR text
+// and k_rescue_ready does the per-pair sort / de-duplication of OutputBuffer::ready; the host receives the final list.
 #include "mp_context.h"
 #include "mp_cigar.h"
 #include "mp_stdsort.h"
@@ -24,21 +26,6 @@
 #include <tuple>
 #include <string.h>
 
-namespace {
-
-// encode one pattern -> cigar text appended to the arena; returns offset; fills stats
-// (a failed growth of the pinned arena returns 0xFFFFFFFF and leaves the error message set)
-uint32_t append_cigar(PinnedBuf<char> &arena, const uint8_t *pat, int open, int ext, CigStats &st)
-{
-    st = cigar_encode(pat, open, ext, nullptr, 0);
-    size_t off = arena.size();
-    if (arena.resize(off + st.textLen + 1)) return 0xFFFFFFFFu;
-    cigar_encode(pat, open, ext, arena.data() + off, st.textLen);
-    arena[off + st.textLen] = 0;
-    return (uint32_t)off;
-}
-
-}  // namespace
 
 // ---- stage S2 on the device ----
 // SingleDPWrapper::transferSeed + SingleEndSeedingEngine::singleMerge (DV-DPForSingleReads.cpp:121-215, DV-DPfunctions.cpp:295-342) for
@@ -142,33 +129,209 @@ __global__ void k_add_totals2(const uint32_t *__restrict__ idxTotal, const uint3
 {
     totals[0] += *idxTotal; totals[1] += *offTotal;
 }
+
+// ---- stage S3 on the device ----
+struct RescueInfo { uint32_t refer; uint32_t leftOrRight; };
+// S3 order of a read's single-end hits: (score descending, startPos ascending), ties in list order (the reference sorts by
+// (readID, score desc) and then by (readID, score desc, startPos), DV-SemiDP.cpp:170, 257)
+__device__ __forceinline__ bool rescue_before(const mp_single_result &x, const mp_single_result &y)
+{
+    if (x.score != y.score) return x.score > y.score;
+    return x.startPos < y.startPos;
+}
+// One thread per single-end result; the thread at the head of a read's run (results are ordered by read) handles the run:
+//  * DPSOutputThread's counters: reads with a result, results after per-read de-duplication by (algnmt, score)
+//  * HalfEndOccStream::fetchNextSingleAlgnResult (DV-DPfunctions.cpp:1048-1079): the LAST four hits of the read in S3 order
+//  * HalfEndAlgnBatch::pack (:1151-1231): one rescue window per kept hit, on the side the hit's strand asks for
+// Tasks go to slots [head, head + 4) of slot arrays as long as the result list (a run of n hits yields at most min(n, 4) tasks), flagged for
+// the compaction that follows.
+__global__ void k_rescue_select(const mp_single_result *__restrict__ S, uint32_t nS, const uint32_t *__restrict__ lens, uint64_t fullLen,
+                                int insert_low, int insert_high, int strandLeft, int strandRight, uint32_t maxDNALengthR, int makeTasks,
+                                MpDpTask *__restrict__ slotTasks, RescueInfo *__restrict__ slotInfo, uint32_t *__restrict__ slotFlag,
+                                uint32_t *__restrict__ totals, unsigned long long *__restrict__ work)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long cells = 0; uint32_t nt = 0, readsWith = 0, uniq = 0;
+    if (i < nS && (i == 0 || S[i - 1].readID != S[i].readID)) {
+        const uint32_t readID = S[i].readID;
+        uint32_t e = i + 1;
+        while (e < nS && S[e].readID == readID) ++e;
+        readsWith = 1;
+        for (uint32_t a = i; a < e; ++a) {
+            bool dup = false;
+            const uint64_t al = S[a].algnmt; const int sc = S[a].score;
+            for (uint32_t b = i; b < a && !dup; ++b) dup = S[b].algnmt == al && S[b].score == sc;
+            uniq += !dup;
+        }
+        if (makeTasks) {
+            uint32_t top[4]; int m = 0;                       // the last (up to) four of the run in S3 order, ascending
+            for (uint32_t a = i; a < e; ++a) {
+                const mp_single_result x = S[a];
+                int pos = m;                                  // a goes after everything that is not strictly behind it (stable)
+                while (pos > 0 && rescue_before(x, S[top[pos - 1]])) --pos;
+                if (m < 4) { for (int k = m; k > pos; --k) top[k] = top[k - 1]; top[pos] = a; ++m; }
+                else if (pos > 0) { for (int k = 0; k + 1 < pos; ++k) top[k] = top[k + 1]; top[pos - 1] = a; }
+            }
+            uint32_t slot = i;
+            for (int k = 0; k < m; ++k) {
+                const mp_single_result sr = S[top[k]];
+                const uint32_t alignedReadID = sr.readID, unalignedReadID = alignedReadID ^ 1u;
+                const uint64_t alignedPos = sr.algnmt;
+                const uint32_t alignedLen = lens[alignedReadID], unalignedLen = lens[unalignedReadID];
+                MpDpTask t; memset(&t, 0, sizeof t);
+                t.readID = unalignedReadID; t.readLen = (uint16_t)unalignedLen; t.valid = 1; t.cutoff = dp_cutoff(unalignedLen);
+                t.diag = -1;                                  // a rescue window has no seed
+                bool have = false; uint32_t side = 0;
+                if ((int)sr.strand == strandLeft) {           // aligned read on the left, mate on the right
+                    const uint64_t rightEnd = alignedPos + (uint64_t)(int64_t)insert_high;
+                    uint64_t rightStart = alignedPos + (uint64_t)(int64_t)insert_low - unalignedLen;
+                    if (rightStart < alignedPos) rightStart = alignedPos;
+                    if (rightStart < fullLen && rightEnd <= fullLen) {
+                        t.refStart = rightStart; t.refLen = (uint32_t)(rightEnd - rightStart); t.strand = (uint8_t)strandRight; have = true; side = 1;
+                    }
+                } else if ((int)sr.strand == strandRight) {   // aligned read on the right, mate on the left
+                    const uint64_t leftStart = alignedPos + alignedLen - (uint64_t)(int64_t)insert_high;
+                    uint64_t leftEnd = alignedPos + alignedLen - (uint64_t)(int64_t)insert_low + unalignedLen;
+                    if (leftEnd >= alignedPos + alignedLen) leftEnd = alignedPos + alignedLen - 1;
+                    if (leftStart < fullLen && leftEnd <= fullLen) {
+                        t.refStart = leftStart; t.refLen = (uint32_t)(leftEnd - leftStart); t.strand = (uint8_t)strandLeft; have = true; side = 0;
+                    }
+                }
+                if (!have) continue;
+                if (t.refLen > maxDNALengthR) { totals[5] = 1; continue; }     // cannot happen for reads shorter than -L; reported, never run
+                slotTasks[slot] = t;
+                RescueInfo ri; ri.refer = top[k]; ri.leftOrRight = side; slotInfo[slot] = ri;
+                slotFlag[slot] = 1; ++slot;
+                cells += (unsigned long long)t.refLen * t.readLen; ++nt;
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        cells += __shfl_xor_sync(0xffffffffu, cells, d); nt += __shfl_xor_sync(0xffffffffu, nt, d);
+        readsWith += __shfl_xor_sync(0xffffffffu, readsWith, d); uniq += __shfl_xor_sync(0xffffffffu, uniq, d);
+    }
+    if ((threadIdx.x & 31) == 0 && readsWith) {
+        atomicAdd(&totals[6], readsWith); atomicAdd(&totals[7], uniq);
+        if (nt) { atomicAdd(&work[0], cells); atomicAdd(&work[1], (unsigned long long)nt); }
+    }
+}
+__global__ void k_rescue_compact(uint32_t nS, const uint32_t *__restrict__ slotFlag, const uint32_t *__restrict__ pos, const MpDpTask *__restrict__ slotTasks,
+                                 const RescueInfo *__restrict__ slotInfo, MpDpTask *__restrict__ tasks, RescueInfo *__restrict__ info)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nS && slotFlag[i]) { tasks[pos[i]] = slotTasks[i]; info[pos[i]] = slotInfo[i]; }
+}
+// DP_Space::algnmtCPUThread (DV-DPfunctions.cpp:1476-1623): one AlgnmtDPResult per rescue task -- the single-end hit on one side, the DP
+// result (or "no alignment") on the other.  pad carries (which | alignedIsMate << 4) for k_rescue_ready: which = 0 / 1 the mate the DP
+// placed, 2 = the DP stayed below its cutoff.
+__global__ void k_rescue_write(uint32_t n, const MpDpTask *__restrict__ tasks, const RescueInfo *__restrict__ info, const MpDpOut *__restrict__ outs,
+                               const uint8_t *__restrict__ pats, uint32_t patStride, const mp_single_result *__restrict__ S, const uint32_t *__restrict__ lens,
+                               int match, int mm, int open, int ext, int insert_low, int insert_high, int strandLeft, int strandRight,
+                               uint32_t maxDNALengthR, const uint32_t *__restrict__ cigOff, uint32_t *__restrict__ totals, uint32_t cigCap,
+                               uint32_t cigArenaBase, mp_pair_result *__restrict__ rec, char *__restrict__ cig)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const MpDpTask t = tasks[c]; const MpDpOut o = outs[c]; const RescueInfo ri = info[c];
+    const mp_single_result sr = S[ri.refer];
+    const uint32_t alignedID = sr.readID, alignedIsMate = alignedID & 1u, pairID = alignedID - alignedIsMate;
+    const uint32_t canPos32 = (uint32_t)sr.algnmt;                // `uint canInfoAmbPosition` (DV-DPfunctions.cpp:1516)
+    const int legStrand = ri.leftOrRight == 0 ? strandLeft : strandRight;
+    mp_pair_result f; memset(&f, 0, sizeof f);
+    f.readID = pairID;
+    uint64_t dpPos = ~0ull; const int dpScore = o.score;
+    uint32_t dpCigar = 0, which = 2; int dpEdit = 0; int32_t dpSame = 0;
+    if (o.score >= t.cutoff) {
+        const uint32_t off = totals[1] + cigOff[c];
+        if ((uint64_t)totals[1] + cigOff[c + 1] > cigCap) { totals[4] = 1; return; }
+        const int textLen = (int)(cigOff[c + 1] - cigOff[c]) - 1;
+        const CigStats st = cigar_encode(pats + (size_t)c * patStride, open, ext, cig + off, textLen);
+        cig[off + textLen] = 0;
+        dpCigar = cigArenaBase + off;
+        const int L = (int)t.readLen - st.nI - st.nS;
+        const int numMis = (L * match + st.gapPenalty - o.score) / (match - mm);
+        dpEdit = st.nI + st.nD + numMis;
+        dpPos = t.refStart + o.hitLoc;
+        which = 1u - alignedIsMate;
+        if (dpPos < (uint64_t)canPos32) f.insertSize = (int32_t)((uint64_t)canPos32 - dpPos + lens[alignedID]);
+        else f.insertSize = (int32_t)(dpPos - (uint64_t)canPos32 + t.readLen + st.nD - st.nI - st.nS);
+        dpSame = (int32_t)o.count;
+    }
+    const uint32_t lA = ri.leftOrRight == 1 ? maxDNALengthR : (uint32_t)(insert_high - insert_low + 1);
+    const uint32_t rA = ri.leftOrRight == 1 ? (uint32_t)t.readLen : 0u;
+    if (alignedIsMate == 0) {          // aligned is read (mate 1), DP result is mate 2
+        f.algnmt_1 = sr.algnmt; f.strand_1 = sr.strand; f.score_1 = sr.score; f.editdist_1 = sr.editdist; f.cigar_1 = sr.cigar;
+        f.num_sameScore_1 = sr.num_sameScore; f.startPos_1 = (uint32_t)sr.startPos; f.refDpLength_1 = sr.refDpLength;
+        f.peLeftAnchor_1 = sr.peLeftAnchor; f.peRightAnchor_1 = 0;
+        f.algnmt_2 = dpPos; f.strand_2 = (uint8_t)legStrand; f.score_2 = dpScore; f.editdist_2 = dpEdit; f.cigar_2 = dpCigar;
+        f.num_sameScore_2 = dpSame; f.startPos_2 = t.refStart; f.refDpLength_2 = t.refLen;
+        f.peLeftAnchor_2 = lA; f.peRightAnchor_2 = rA;
+    } else {                           // aligned is mate 2, DP result is mate 1
+        f.algnmt_1 = dpPos; f.strand_1 = (uint8_t)legStrand; f.score_1 = dpScore; f.editdist_1 = dpEdit; f.cigar_1 = dpCigar;
+        f.num_sameScore_1 = dpSame; f.startPos_1 = (uint32_t)t.refStart; f.refDpLength_1 = t.refLen;
+        f.peLeftAnchor_1 = lA; f.peRightAnchor_1 = rA;
+        f.algnmt_2 = sr.algnmt; f.strand_2 = sr.strand; f.score_2 = sr.score; f.editdist_2 = sr.editdist; f.cigar_2 = sr.cigar;
+        f.num_sameScore_2 = sr.num_sameScore; f.startPos_2 = sr.startPos; f.refDpLength_2 = sr.refDpLength;
+        f.peLeftAnchor_2 = sr.peLeftAnchor; f.peRightAnchor_2 = 0;
+    }
+    f.pad = (uint16_t)(which | (alignedIsMate << 4));
+    rec[c] = f;
+}
+// sort key of an AlgnmtDPResult (ResultCompare, DV-DPfunctions.cpp:253-258): the single-end side enters with its 32-bit position
+struct RescueKey { uint64_t a1, a2; int s1, s2; };
+__device__ __forceinline__ RescueKey rescue_key(const mp_pair_result &f)
+{
+    RescueKey k; k.s1 = f.score_1; k.s2 = f.score_2;
+    if ((f.pad >> 4) == 0) { k.a1 = (uint32_t)f.algnmt_1; k.a2 = f.algnmt_2; } else { k.a1 = f.algnmt_1; k.a2 = (uint32_t)f.algnmt_2; }
+    return k;
+}
+__device__ __forceinline__ bool rescue_key_less(const RescueKey &a, const RescueKey &b)
+{
+    if (a.a1 != b.a1) return a.a1 < b.a1;
+    if (a.a2 != b.a2) return a.a2 < b.a2;
+    if (a.s1 != b.s1) return a.s1 < b.s1;
+    return a.s2 < b.s2;
+}
+// DPOutputThread (DV-DPfunctions.cpp:1625-1747) per pair: OutputBuffer::ready(1) = sort + drop duplicates, then the half-aligned entries
+// go.  A pair has at most eight records (four per mate), which std::sort orders by plain insertion: first of equal keys stays first.
+__global__ void k_rescue_ready(mp_pair_result *__restrict__ rec, uint32_t n, uint32_t *__restrict__ keep, uint32_t *__restrict__ totals)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t pairs = 0, kept = 0;
+    if (i < n && (i == 0 || rec[i - 1].readID != rec[i].readID)) {
+        uint32_t e = i + 1;
+        while (e < n && rec[e].readID == rec[i].readID) ++e;
+        for (uint32_t a = i + 1; a < e; ++a) {
+            const mp_pair_result key = rec[a]; const RescueKey kk = rescue_key(key); uint32_t b = a;
+            while (b > i && rescue_key_less(kk, rescue_key(rec[b - 1]))) { rec[b] = rec[b - 1]; --b; }
+            if (b != a) rec[b] = key;
+        }
+        uint32_t last = i;
+        for (uint32_t a = i; a < e; ++a) {
+            const bool fresh = a == i || rescue_key_less(rescue_key(rec[last]), rescue_key(rec[a]));
+            if (fresh) last = a;
+            const bool k = fresh && (rec[a].pad & 0xF) < 2;
+            keep[a] = k; kept += k;
+        }
+        pairs = kept ? 1 : 0;
+    }
+    pairs = __reduce_add_sync(0xffffffffu, pairs); kept = __reduce_add_sync(0xffffffffu, kept);
+    if ((threadIdx.x & 31) == 0 && kept) { atomicAdd(&totals[3], pairs); atomicAdd(&totals[2], kept); }
+}
+__global__ void k_rescue_out(const mp_pair_result *__restrict__ rec, uint32_t n, const uint32_t *__restrict__ keep, const uint32_t *__restrict__ pos,
+                             mp_pair_result *__restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && keep[i]) { mp_pair_result r = rec[i]; r.pad = 0; out[pos[i]] = r; }
+}
+__global__ void k_add_cig_total(const uint32_t *__restrict__ offTotal, uint32_t *__restrict__ totals) { totals[1] += *offTotal; }
 static int scan_u32_s(mp_context *ctx, const uint32_t *in, uint32_t *out, uint64_t n)
 {
     size_t tb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, (int64_t)n, ctx->stream);
     if (ctx->dScanTmp.reserve(tb)) return MP_ERR_CUDA;
     cub::DeviceScan::ExclusiveSum(ctx->dScanTmp.p, tb, in, out, (int64_t)n, ctx->stream);
-    return 0;
-}
-
-// host task list -> DP on the device -> host outputs (chunked)
-int mpd_run_host_tasks(mp_context *ctx, const std::vector<MpDpTask> &tasks, uint32_t maxRefLen, uint32_t maxReadLen, const MpDpParams &P,
-                       std::vector<MpDpOut> &outs, std::vector<uint8_t> &pats, uint32_t patStride)
-{
-    const size_t n = tasks.size();
-    outs.resize(n); pats.assign(n * (size_t)patStride, 0);
-    const size_t CH = 1u << 17;
-    for (size_t base = 0; base < n; base += CH) {
-        uint32_t m = (uint32_t)std::min(CH, n - base);
-        if (ctx->dTasks.reserve((size_t)m * sizeof(MpDpTask)) || ctx->dDpOut.reserve((size_t)m * sizeof(MpDpOut)) ||
-            ctx->dPattern.reserve((size_t)m * patStride)) return MP_ERR_CUDA;
-        MP_CUDA(cudaMemcpyAsync(ctx->dTasks.p, tasks.data() + base, (size_t)m * sizeof(MpDpTask), cudaMemcpyHostToDevice, ctx->stream));
-        if (int rc = mpd_run_tasks(ctx, ctx->dTasks.as<MpDpTask>(), m, maxRefLen, maxReadLen, P, ctx->dDpOut.as<MpDpOut>(),
-                                   ctx->dPattern.as<uint8_t>(), patStride)) return rc;
-        MP_CUDA(cudaMemcpyAsync(outs.data() + base, ctx->dDpOut.p, (size_t)m * sizeof(MpDpOut), cudaMemcpyDeviceToHost, ctx->stream));
-        MP_CUDA(cudaMemcpyAsync(pats.data() + base * patStride, ctx->dPattern.p, (size_t)m * patStride, cudaMemcpyDeviceToHost, ctx->stream));
-        MP_CUDA(cudaStreamSynchronize(ctx->stream));
-    }
     return 0;
 }
 
@@ -182,13 +345,12 @@ int mps_single_and_rescue(mp_context *ctx, const mp_align_params *P, mp_results 
         mp_set_error("single-end / default DP need MaxFrontLenClipped == MaxEndLenClipped (the reference applies task 0's clip sizes to a whole batch, CPU_DPfunctions.cpp:300)");
         return MP_ERR_ARG;
     }
-    const std::vector<uint32_t> &lens = ctx->hLens;
     MpTrace tr;
     const uint32_t inputMax = (uint32_t)P->maxReadLength;
     const uint32_t maxReadLength = (inputMax / 4 + 1) * 4;
     const uint32_t maxDNALengthS = maxReadLength + 2 * MP_MARGIN(inputMax) + 8;
     MpDpParams dp; dp.mismatch = P->mismatchScore; dp.open = P->openGapScore; dp.clipLt = P->softClipLeft; dp.clipRt = P->softClipRight;
-    std::vector<mp_single_result> &S = ctx->hSingles;
+    PinnedBuf<mp_single_result> &S = ctx->hSingles;
     PinnedBuf<char> &HC = ctx->hCigars;
     // ---- S2: merge / order / cap the seeds of every unplaced read, one DP task per kept seed (all on the device) ----
     if (ctx->dS2Counts.reserve(((size_t)nReads + 1) * 4) || ctx->dS2Start.reserve(((size_t)nReads + 1) * 4) || ctx->dTotals.reserve(16 * 4) ||
@@ -247,8 +409,7 @@ int mps_single_and_rescue(mp_context *ctx, const mp_align_params *P, mp_results 
         if (attempt == 2) { mp_set_error("CIGAR arena of stage S2 overflowed repeatedly"); return MP_ERR_CAPACITY; }
     }
     tr.mark("  s2 dp + assemble (device)");
-    S.resize(tot[0]);
-    if (HC.resize((size_t)cigArenaBase + tot[1])) return MP_ERR_CUDA;
+    if (S.resize(tot[0]) || HC.resize((size_t)cigArenaBase + tot[1])) return MP_ERR_CUDA;
     if (tot[0]) MP_CUDA(cudaMemcpyAsync(S.data(), ctx->dS2Res.p, (size_t)tot[0] * sizeof(mp_single_result), cudaMemcpyDeviceToHost, st));
     if (tot[1]) MP_CUDA(cudaMemcpyAsync(HC.data() + cigArenaBase, ctx->dCig.p, tot[1], cudaMemcpyDeviceToHost, st));
     {
@@ -258,139 +419,88 @@ int mps_single_and_rescue(mp_context *ctx, const mp_align_params *P, mp_results 
         cells += hw[0]; tasksRun += hw[1];
     }
     tr.mark("  s2 download");
-    // counters as DPSOutputThread keeps them: reads with >= 1 result; results after per-read de-duplication
-    for (size_t i = 0, j; i < S.size(); i = j) {
-        j = i + 1;
-        while (j < S.size() && S[j].readID == S[i].readID) ++j;
-        std::vector<std::pair<uint64_t, int32_t>> k;
-        for (size_t a = i; a < j; ++a) k.push_back(std::make_pair(S[a].algnmt, S[a].score));
-        std::sort(k.begin(), k.end());
-        out->numSingleDPAligned += 1;
-        out->numSingleDPAlignment += (uint64_t)(std::unique(k.begin(), k.end()) - k.begin());
-    }
-    tr.mark("  s2 assemble");
-    if (P->skipDefaultDP || S.empty()) return 0;
-
-    // ---- S3: sort by (readID, score desc) then (readID, score desc, startPos) ----
-    std::vector<uint32_t> order(S.size());
-    for (size_t i = 0; i < S.size(); ++i) order[i] = (uint32_t)i;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-        const mp_single_result &x = S[a], &y = S[b];
-        if (x.readID != y.readID) return x.readID < y.readID;
-        if (x.score != y.score) return x.score > y.score;
-        return x.startPos < y.startPos;
-    });
-    struct RTask { uint32_t refer; uint32_t leftOrRight; };
-    std::vector<RTask> rinfo;
-    std::vector<MpDpTask> rtasks;
+    // ---- S3 (and the counters DPSOutputThread keeps: reads with >= 1 result, results after per-read de-duplication) ----
+    const uint32_t nS = tot[0];
+    if (nS == 0) return 0;
+    const int doRescue = P->skipDefaultDP ? 0 : 1;
     const int insert_high = P->insert_high, insert_low = P->insert_low;
     const uint32_t maxDNALengthR = (uint32_t)(insert_high - insert_low) + inputMax + 1;
-    size_t it = 0;
-    while (it < order.size()) {
-        while (it + 4 < order.size() && S[order[it]].readID == S[order[it + 4]].readID) ++it;     // keep the last 4 of a read (:1053-1055)
-        const uint32_t ref = order[it++];
-        const mp_single_result &sr = S[ref];
-        const uint32_t alignedReadID = sr.readID, unalignedReadID = alignedReadID ^ 1u;
-        const uint64_t alignedPos = sr.algnmt;
-        const uint32_t alignedLen = lens[alignedReadID], unalignedLen = lens[unalignedReadID];
-        MpDpTask t; memset(&t, 0, sizeof t);
-        t.readID = unalignedReadID; t.readLen = (uint16_t)unalignedLen; t.valid = 1; t.cutoff = dp_cutoff(unalignedLen);
-        t.diag = -1;                                              // a rescue window has no seed
-        if ((int)sr.strand == P->peStrandLeftLeg) {               // aligned read on the left, mate on the right
-            uint64_t rightEnd = alignedPos + (uint64_t)(int64_t)insert_high;
-            uint64_t rightStart = alignedPos + (uint64_t)(int64_t)insert_low - unalignedLen;
-            if (rightStart < alignedPos) rightStart = alignedPos;
-            if (rightStart < fullLen && rightEnd <= fullLen) {
-                t.refStart = rightStart; t.refLen = (uint32_t)(rightEnd - rightStart); t.strand = (uint8_t)P->peStrandRightLeg;
-                rtasks.push_back(t); RTask ri = { ref, 1u }; rinfo.push_back(ri);
-            }
+    const uint32_t rStride = (maxDNALengthR + maxReadLength + 3) & ~3u;
+    uint32_t *dT3 = dTot + 8;                                                  // [1] cigar bytes, [2] kept, [3] pairs, [4] overflow, [5] window error, [6] reads, [7] unique
+    if (ctx->dRsSlotTasks.reserve((size_t)nS * sizeof(MpDpTask)) || ctx->dRsSlotInfo.reserve((size_t)nS * sizeof(RescueInfo)) ||
+        ctx->dRsFlag.reserve(((size_t)nS + 1) * 4) || ctx->dRsPos.reserve(((size_t)nS + 1) * 4)) return MP_ERR_CUDA;
+    MP_CUDA(cudaMemsetAsync(dT3, 0, 8 * 4, st));
+    MP_CUDA(cudaMemsetAsync(dWork, 0, 16, st));
+    MP_CUDA(cudaMemsetAsync(ctx->dRsFlag.p, 0, ((size_t)nS + 1) * 4, st));
+    (++g_mp_launches), k_rescue_select<<<(nS + 127) / 128, 128, 0, st>>>(ctx->dS2Res.as<mp_single_result>(), nS, ctx->dLens.as<uint32_t>(), fullLen, insert_low, insert_high,
+        P->peStrandLeftLeg, P->peStrandRightLeg, maxDNALengthR, doRescue, ctx->dRsSlotTasks.as<MpDpTask>(), ctx->dRsSlotInfo.as<RescueInfo>(),
+        ctx->dRsFlag.as<uint32_t>(), dT3, dWork);
+    if (scan_u32_s(ctx, ctx->dRsFlag.as<uint32_t>(), ctx->dRsPos.as<uint32_t>(), (uint64_t)nS + 1)) return MP_ERR_CUDA;
+    uint32_t nR = 0, t3[8] = { 0 };
+    MP_CUDA(cudaMemcpyAsync(&nR, ctx->dRsPos.as<uint32_t>() + nS, 4, cudaMemcpyDeviceToHost, st));
+    MP_CUDA(cudaMemcpyAsync(t3, dT3, sizeof t3, cudaMemcpyDeviceToHost, st));
+    MP_CUDA(cudaStreamSynchronize(st));
+    out->numSingleDPAligned += t3[6]; out->numSingleDPAlignment += t3[7];
+    if (t3[5]) { mp_set_error("default DP window exceeds maxDNALength %u", maxDNALengthR); return MP_ERR_CAPACITY; }
+    tr.mark("  s3 select (device)");
+    if (!doRescue || nR == 0) return 0;
+    const uint32_t CH3 = 1u << 17;
+    const uint32_t chunkCap3 = std::min<uint32_t>(CH3, nR);
+    if (ctx->dRsTasks.reserve((size_t)nR * sizeof(MpDpTask)) || ctx->dRsInfo.reserve((size_t)nR * sizeof(RescueInfo)) ||
+        ctx->dRsRec.reserve((size_t)nR * sizeof(mp_pair_result)) || ctx->dRsOut.reserve((size_t)nR * sizeof(mp_pair_result)) ||
+        ctx->dRsKeep.reserve(((size_t)nR + 1) * 4) || ctx->dRsKeepPos.reserve(((size_t)nR + 1) * 4) ||
+        ctx->dLO.reserve((size_t)chunkCap3 * sizeof(MpDpOut)) || ctx->dLP.reserve((size_t)chunkCap3 * rStride) ||
+        ctx->dOk.reserve(((size_t)chunkCap3 + 1) * 4) || ctx->dBytes.reserve(((size_t)chunkCap3 + 1) * 8) ||
+        ctx->dOff.reserve(((size_t)chunkCap3 + 1) * 4)) return MP_ERR_CUDA;
+    (++g_mp_launches), k_rescue_compact<<<(nS + 127) / 128, 128, 0, st>>>(nS, ctx->dRsFlag.as<uint32_t>(), ctx->dRsPos.as<uint32_t>(), ctx->dRsSlotTasks.as<MpDpTask>(),
+        ctx->dRsSlotInfo.as<RescueInfo>(), ctx->dRsTasks.as<MpDpTask>(), ctx->dRsInfo.as<RescueInfo>());
+    // the CIGAR text of S2 has left the device: the arena is reused from its start, offsets continue behind S2's in the host arena
+    const uint32_t cigArenaBase3 = (uint32_t)HC.size();
+    size_t cigCap3 = std::max<size_t>(ctx->dCig.cap, std::max<size_t>((size_t)nR * 64, (size_t)1 << 20));
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        if (cigCap3 > 0xFFFFFFF0ull) { mp_set_error("CIGAR arena of stage S3 exceeds 4 GB; use smaller batches"); return MP_ERR_CAPACITY; }
+        if (ctx->dCig.reserve(cigCap3)) return MP_ERR_CUDA;
+        MP_CUDA(cudaMemsetAsync(dT3, 0, 5 * 4, st));
+        for (uint32_t base = 0; base < nR; base += CH3) {
+            const uint32_t n = std::min<uint32_t>(CH3, nR - base);
+            const MpDpTask *tk = ctx->dRsTasks.as<MpDpTask>() + base;
+            const unsigned g = (n + 127) / 128;
+            if (int rc = mpd_run_tasks(ctx, tk, n, maxDNALengthR, maxReadLength, dp, ctx->dLO.as<MpDpOut>(), ctx->dLP.as<uint8_t>(), rStride)) return rc;
+            MP_CUDA(cudaMemsetAsync(ctx->dBytes.p, 0, ((size_t)n + 1) * 4, st));
+            (++g_mp_launches), k_single_measure<<<g, 128, 0, st>>>(n, tk, ctx->dLO.as<MpDpOut>(), ctx->dLP.as<uint8_t>(), rStride, P->openGapScore, P->extendGapScore,
+                                                                   ctx->dOk.as<uint32_t>(), ctx->dBytes.as<uint32_t>());
+            if (scan_u32_s(ctx, ctx->dBytes.as<uint32_t>(), ctx->dOff.as<uint32_t>(), (uint64_t)n + 1)) return MP_ERR_CUDA;
+            (++g_mp_launches), k_rescue_write<<<g, 128, 0, st>>>(n, tk, ctx->dRsInfo.as<RescueInfo>() + base, ctx->dLO.as<MpDpOut>(), ctx->dLP.as<uint8_t>(), rStride,
+                ctx->dS2Res.as<mp_single_result>(), ctx->dLens.as<uint32_t>(), P->matchScore, P->mismatchScore, P->openGapScore, P->extendGapScore,
+                insert_low, insert_high, P->peStrandLeftLeg, P->peStrandRightLeg, maxDNALengthR, ctx->dOff.as<uint32_t>(), dT3,
+                (uint32_t)std::min<size_t>(cigCap3, 0xFFFFFFF0u), cigArenaBase3, ctx->dRsRec.as<mp_pair_result>() + base, ctx->dCig.as<char>());
+            (++g_mp_launches), k_add_cig_total<<<1, 1, 0, st>>>(ctx->dOff.as<uint32_t>() + n, dT3);
+            MP_CUDA(cudaGetLastError());
         }
-        if ((int)sr.strand == P->peStrandRightLeg) {              // aligned read on the right, mate on the left
-            uint64_t leftStart = alignedPos + alignedLen - (uint64_t)(int64_t)insert_high;
-            uint64_t leftEnd = alignedPos + alignedLen - (uint64_t)(int64_t)insert_low + unalignedLen;
-            if (leftEnd >= alignedPos + alignedLen) leftEnd = alignedPos + alignedLen - 1;
-            if (leftStart < fullLen && leftEnd <= fullLen) {
-                t.refStart = leftStart; t.refLen = (uint32_t)(leftEnd - leftStart); t.strand = (uint8_t)P->peStrandLeftLeg;
-                rtasks.push_back(t); RTask ri = { ref, 0u }; rinfo.push_back(ri);
-            }
-        }
+        MP_CUDA(cudaMemsetAsync(ctx->dRsKeep.p, 0, ((size_t)nR + 1) * 4, st));
+        (++g_mp_launches), k_rescue_ready<<<(nR + 127) / 128, 128, 0, st>>>(ctx->dRsRec.as<mp_pair_result>(), nR, ctx->dRsKeep.as<uint32_t>(), dT3);
+        if (scan_u32_s(ctx, ctx->dRsKeep.as<uint32_t>(), ctx->dRsKeepPos.as<uint32_t>(), (uint64_t)nR + 1)) return MP_ERR_CUDA;
+        (++g_mp_launches), k_rescue_out<<<(nR + 127) / 128, 128, 0, st>>>(ctx->dRsRec.as<mp_pair_result>(), nR, ctx->dRsKeep.as<uint32_t>(), ctx->dRsKeepPos.as<uint32_t>(),
+                                                                         ctx->dRsOut.as<mp_pair_result>());
+        MP_CUDA(cudaGetLastError());
+        MP_CUDA(cudaMemcpyAsync(t3, dT3, sizeof t3, cudaMemcpyDeviceToHost, st));
+        MP_CUDA(cudaStreamSynchronize(st));
+        if (!t3[4]) break;
+        cigCap3 = (size_t)t3[1] + t3[1] / 8 + (1 << 20);
+        if (attempt == 2) { mp_set_error("CIGAR arena of stage S3 overflowed repeatedly"); return MP_ERR_CAPACITY; }
     }
-    for (const MpDpTask &t : rtasks) {
-        if (t.refLen > maxDNALengthR) { mp_set_error("default DP window %u exceeds maxDNALength %u", t.refLen, maxDNALengthR); return MP_ERR_CAPACITY; }
-        cells += (uint64_t)t.refLen * t.readLen; ++tasksRun;
+    tr.mark("  s3 dp + assemble (device)");
+    PinnedBuf<mp_pair_result> &R = ctx->hRescued;
+    if (R.resize(t3[2]) || HC.resize((size_t)cigArenaBase3 + t3[1])) return MP_ERR_CUDA;
+    if (t3[2]) MP_CUDA(cudaMemcpyAsync(R.data(), ctx->dRsOut.p, (size_t)t3[2] * sizeof(mp_pair_result), cudaMemcpyDeviceToHost, st));
+    if (t3[1]) MP_CUDA(cudaMemcpyAsync(HC.data() + cigArenaBase3, ctx->dCig.p, t3[1], cudaMemcpyDeviceToHost, st));
+    {
+        unsigned long long hw[2];
+        MP_CUDA(cudaMemcpyAsync(hw, dWork, sizeof hw, cudaMemcpyDeviceToHost, st));
+        MP_CUDA(cudaStreamSynchronize(st));
+        cells += hw[0]; tasksRun += hw[1];
     }
-    tr.mark("  s3 tasks");
-    std::vector<MpDpOut> routs; std::vector<uint8_t> rpats;
-    const uint32_t rStride = maxDNALengthR + maxReadLength;
-    if (int rc = mpd_run_host_tasks(ctx, rtasks, maxDNALengthR, maxReadLength, dp, routs, rpats, rStride)) return rc;
-    tr.mark("  s3 dp");
-    // ---- AlgnmtDPResult records, grouped per pair (DV-DPfunctions.cpp:1476-1747) ----
-    struct ADP { uint64_t a1, a2; int s1, s2; int which; mp_pair_result full; };
-    std::vector<ADP> group;
-    std::vector<mp_pair_result> &R = ctx->hRescued;
-    auto flush = [&]() {
-        if (group.empty()) return;
-        // OutputBuffer::ready(1): sort + drop duplicates (ResultCompare), then drop half-aligned entries
-        std::sort(group.begin(), group.end(), [](const ADP &a, const ADP &b) {
-            return std::make_tuple(a.a1, a.a2, a.s1, a.s2) < std::make_tuple(b.a1, b.a2, b.s1, b.s2); });
-        size_t w = 0;
-        for (size_t i = 1; i < group.size(); ++i)
-            if (std::make_tuple(group[w].a1, group[w].a2, group[w].s1, group[w].s2) < std::make_tuple(group[i].a1, group[i].a2, group[i].s1, group[i].s2))
-                group[++w] = group[i];
-        size_t n = w + 1, valid = 0;
-        for (size_t i = 0; i < n; ++i) if (group[i].which < 2) { R.push_back(group[i].full); ++valid; }
-        if (valid) { out->numRescuedPair += 1; out->numRescuedAlignment += valid; }
-        group.clear();
-    };
-    uint32_t lastPair = 0xFFFFFFFFu;
-    for (size_t id = 0; id < rtasks.size(); ++id) {
-        const mp_single_result &sr = S[rinfo[id].refer];
-        const uint32_t alignedID = sr.readID, alignedIsMate = alignedID & 1u;
-        const uint32_t pairID = alignedID - alignedIsMate;
-        if (pairID != lastPair) { flush(); lastPair = pairID; }
-        const uint32_t canPos32 = (uint32_t)sr.algnmt;           // `uint canInfoAmbPosition` (DV-DPfunctions.cpp:1516)
-        const int legStrand = rinfo[id].leftOrRight == 0 ? P->peStrandLeftLeg : P->peStrandRightLeg;
-        ADP a; memset(&a, 0, sizeof a);
-        mp_pair_result &f = a.full;
-        f.readID = pairID;
-        uint64_t dpPos = ~0ull; int dpScore = routs[id].score;
-        // the DP side
-        uint32_t dpCigar = 0; int dpEdit = 0; int32_t dpSame = 0;
-        if (routs[id].score >= rtasks[id].cutoff) {
-            CigStats st;
-            dpCigar = append_cigar(HC, rpats.data() + id * rStride, P->openGapScore, P->extendGapScore, st);
-            if (dpCigar == 0xFFFFFFFFu) return MP_ERR_CUDA;
-            int L = (int)rtasks[id].readLen - st.nI - st.nS;
-            int numMis = (L * P->matchScore + st.gapPenalty - routs[id].score) / (P->matchScore - P->mismatchScore);
-            dpEdit = st.nI + st.nD + numMis;
-            dpPos = rtasks[id].refStart + routs[id].hitLoc;
-            a.which = 1 - (int)alignedIsMate;
-            if (dpPos < (uint64_t)canPos32) f.insertSize = (int32_t)((uint64_t)canPos32 - dpPos + lens[alignedID]);
-            else f.insertSize = (int32_t)(dpPos - (uint64_t)canPos32 + rtasks[id].readLen + st.nD - st.nI - st.nS);
-            dpSame = (int32_t)routs[id].count;
-        } else a.which = 2;
-        const uint32_t lA = rinfo[id].leftOrRight == 1 ? maxDNALengthR : (uint32_t)(insert_high - insert_low + 1);
-        const uint32_t rA = rinfo[id].leftOrRight == 1 ? (uint32_t)rtasks[id].readLen : 0u;
-        if (alignedIsMate == 0) {          // aligned is read (mate 1), DP result is mate 2
-            a.a1 = canPos32; a.a2 = dpPos; a.s1 = sr.score; a.s2 = dpScore;
-            f.algnmt_1 = sr.algnmt; f.strand_1 = sr.strand; f.score_1 = sr.score; f.editdist_1 = sr.editdist; f.cigar_1 = sr.cigar;
-            f.num_sameScore_1 = sr.num_sameScore; f.startPos_1 = (uint32_t)sr.startPos; f.refDpLength_1 = sr.refDpLength;
-            f.peLeftAnchor_1 = sr.peLeftAnchor; f.peRightAnchor_1 = 0;
-            f.algnmt_2 = dpPos; f.strand_2 = (uint8_t)legStrand; f.score_2 = dpScore; f.editdist_2 = dpEdit; f.cigar_2 = dpCigar;
-            f.num_sameScore_2 = dpSame; f.startPos_2 = rtasks[id].refStart; f.refDpLength_2 = rtasks[id].refLen;
-            f.peLeftAnchor_2 = lA; f.peRightAnchor_2 = rA;
-        } else {                           // aligned is mate 2, DP result is mate 1
-            a.a1 = dpPos; a.a2 = canPos32; a.s1 = dpScore; a.s2 = sr.score;
-            f.algnmt_1 = dpPos; f.strand_1 = (uint8_t)legStrand; f.score_1 = dpScore; f.editdist_1 = dpEdit; f.cigar_1 = dpCigar;
-            f.num_sameScore_1 = dpSame; f.startPos_1 = (uint32_t)rtasks[id].refStart; f.refDpLength_1 = rtasks[id].refLen;
-            f.peLeftAnchor_1 = lA; f.peRightAnchor_1 = rA;
-            f.algnmt_2 = sr.algnmt; f.strand_2 = sr.strand; f.score_2 = sr.score; f.editdist_2 = sr.editdist; f.cigar_2 = sr.cigar;
-            f.num_sameScore_2 = sr.num_sameScore; f.startPos_2 = sr.startPos; f.refDpLength_2 = sr.refDpLength;
-            f.peLeftAnchor_2 = sr.peLeftAnchor; f.peRightAnchor_2 = 0;
-        }
-        group.push_back(a);
-    }
-    flush();
-    tr.mark("  s3 assemble");
+    out->numRescuedPair += t3[3]; out->numRescuedAlignment += t3[2];
+    tr.mark("  s3 download");
     return 0;
 }
