@@ -130,7 +130,7 @@ struct mp_context {
     DevBuf dReadsIl, dReads, dLens;
     // seeding
     DevBuf dCounters;                 // u64[16]: 0 seeds, 1 hit stubs, 2 occ, 3 sa, 4 lkt, 5 lf, 6 work-queue
-    DevBuf dSeeds, dStubs, dHitsPerRead, dHitStart, dCursor, dHits, dSeedPos, dNPos, dNNeg;
+    DevBuf dSeeds, dStubs, dHitsPerRead, dHitStart, dCursor, dHits, dHits2, dSeedPos, dNPos, dNNeg;
     DevBuf dCandCount, dCandStart, dCands, dScanTmp;
     uint64_t nSeeds = 0, nHits = 0, nCands = 0;
     uint64_t capSeeds = 0, capStubs = 0;

@@ -424,19 +424,39 @@ __device__ __forceinline__ bool hit_less(const MpHit &a, const MpHit &b)
 {
     return a.strand != b.strand ? a.strand < b.strand : a.offset < b.offset;
 }
+// Orders the hits of every read by (strand, offset): one warp per read, rank sort.  Lane j counts how many of the read's hits come
+// before hit j (every lane reads the same record at a time: one broadcast load per comparison step) and writes hit j to that
+// position of the second buffer.  NT-like indexes give dozens of hits per read (17-mers repeat by chance in 8 Gbp), where a
+// per-thread insertion sort in global memory was the most expensive part of the seeding post-processing.  Hits with the same strand
+// and offset are told apart by their list position; the merge below does not depend on their order.
+// G = lanes per read: 32 where reads have dozens of hits, 4 where they have a handful (human-sized texts, seedMinLength 22).
+template <int G>
+__global__ void __launch_bounds__(128)
+k_hit_sort(const uint32_t *__restrict__ hitStart, const MpHit *__restrict__ hits, uint32_t nReads, MpHit *__restrict__ sorted)
+{
+    const uint32_t sub = threadIdx.x % G, groupsPerGrid = gridDim.x * (blockDim.x / G);
+    for (uint32_t rdx = blockIdx.x * (blockDim.x / G) + threadIdx.x / G; rdx < nReads; rdx += groupsPerGrid) {
+        const uint32_t s0 = hitStart[rdx], cnt = hitStart[rdx + 1] - s0;
+        const MpHit *h = hits + s0;
+        for (uint32_t j = sub; j < cnt; j += G) {
+            const MpHit mine = h[j];
+            uint32_t rank = 0;
+            for (uint32_t k = 0; k < cnt; ++k) {
+                const MpHit o = h[k];
+                rank += hit_less(o, mine) || (!hit_less(mine, o) && k < j);
+            }
+            sorted[s0 + rank] = mine;
+        }
+    }
+}
 __global__ void k_merge(const uint32_t *__restrict__ hitStart, MpHit *__restrict__ hits, uint32_t nReads, MmpDev P,
                         mp_seed_pos *__restrict__ outSeeds, uint32_t *__restrict__ nPos, uint32_t *__restrict__ nNeg)
 {
     uint32_t rdx = blockIdx.x * blockDim.x + threadIdx.x;
     if (rdx >= nReads) return;
     uint32_t s0 = hitStart[rdx], s1 = hitStart[rdx + 1];
-    MpHit *h = hits + s0;
+    MpHit *h = hits + s0;                           // ordered by (strand, offset) (k_hit_sort)
     int cnt = (int)(s1 - s0);
-    for (int a = 1; a < cnt; ++a) {                 // insertion sort by (strand, offset)
-        MpHit key = h[a]; int b = a - 1;
-        while (b >= 0 && hit_less(key, h[b])) { h[b + 1] = h[b]; --b; }
-        h[b + 1] = key;
-    }
     // pass 1: chains -> (pos, total_len, keep) written to a compact list in place
     uint32_t maxLen = 0; int nOut = 0, m = 0;
     mp_seed_pos *out = outSeeds + s0;
@@ -653,7 +673,12 @@ int mps_seed_pairs(mp_context *ctx, const mp_align_params *AP)
             ctx->dCounters.as<unsigned long long>());
     MP_CUDA(cudaGetLastError());
     MP_CUDA(cudaEventRecord(ctx->ev[2], st));
-    (++g_mp_launches), k_merge<<<(nReads + 127) / 128, 128, 0, st>>>(ctx->dHitStart.as<uint32_t>(), ctx->dHits.as<MpHit>(), nReads, P,
+    if (ctx->dHits2.reserve(hitSlots * sizeof(MpHit))) return MP_ERR_CUDA;
+    if (ctx->nHits > (uint64_t)nReads * 8)
+        (++g_mp_launches), k_hit_sort<32><<<nSM * 16, 128, 0, st>>>(ctx->dHitStart.as<uint32_t>(), ctx->dHits.as<MpHit>(), nReads, ctx->dHits2.as<MpHit>());
+    else
+        (++g_mp_launches), k_hit_sort<4><<<nSM * 16, 128, 0, st>>>(ctx->dHitStart.as<uint32_t>(), ctx->dHits.as<MpHit>(), nReads, ctx->dHits2.as<MpHit>());
+    (++g_mp_launches), k_merge<<<(nReads + 127) / 128, 128, 0, st>>>(ctx->dHitStart.as<uint32_t>(), ctx->dHits2.as<MpHit>(), nReads, P,
                                                  ctx->dSeedPos.as<mp_seed_pos>(), ctx->dNPos.as<uint32_t>(), ctx->dNNeg.as<uint32_t>());
     MP_CUDA(cudaGetLastError());
     // pairing: count, scan, write
