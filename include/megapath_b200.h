@@ -108,6 +108,11 @@ typedef struct mp_results {
     uint64_t numDPAlignedPair, numDPAlignment;          /* deep DP */
     uint64_t numSingleDPAligned, numSingleDPAlignment;  /* single-end DP */
     uint64_t numRescuedPair, numRescuedAlignment;       /* default DP */
+} mp_results;
+
+/* Work counters and device timings of a context's last mp_align_pairs call (instrumentation for bench.py and the roofline
+ * accounting; not part of the result set).  mp_last_stats copies them out. */
+typedef struct mp_stats {
     /* algorithmic work of this call: occ evaluations of the backward search, on-spot
      * occ evaluations of the SA walks (LF steps), SA lookups, LKT jumps, DP cells (sum of
      * dnaLen*readLen over required tasks), DP tasks */
@@ -126,7 +131,7 @@ typedef struct mp_results {
     uint64_t dp_tasks_exact, dp_cells_filled;
     /* summed device time of that test and of compacting the remaining tasks */
     float ms_exact, reserved_;
-} mp_results;
+} mp_stats;
 
 /* ---- context ---- */
 int  mp_init(int device, mp_context **ctx);
@@ -210,6 +215,7 @@ int  mp_dp_batch(mp_context *ctx,
  *      end-to-end call. */
 int  mp_align_pairs(mp_context *ctx, const mp_align_params *params, mp_results *out);
 void mp_results_release(mp_context *ctx, mp_results *res);
+int  mp_last_stats(mp_context *ctx, mp_stats *stats);
 
 /* ---- roofline denominators measured on the spot (bench.py): kind 0 = random 32-byte gathers over an 8 GB table,
  *      1 = random 64-byte gathers (GB/s of requested bytes), 2 = packed 16-bit DPX issue rate (1e9 thread-instr/s) ---- */

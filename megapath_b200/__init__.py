@@ -40,7 +40,11 @@ class Results(C.Structure):
                 ("numDPAlignedPair", C.c_uint64), ("numDPAlignment", C.c_uint64),
                 ("numSingleDPAligned", C.c_uint64), ("numSingleDPAlignment", C.c_uint64),
                 ("numRescuedPair", C.c_uint64), ("numRescuedAlignment", C.c_uint64),
-                ("n_occ", C.c_uint64), ("n_lf", C.c_uint64), ("n_sa", C.c_uint64), ("n_lkt", C.c_uint64),
+                ]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_occ", C.c_uint64), ("n_lf", C.c_uint64), ("n_sa", C.c_uint64), ("n_lkt", C.c_uint64),
                 ("dp_cells", C.c_uint64), ("dp_tasks", C.c_uint64), ("n_probe", C.c_uint64), ("n_text", C.c_uint64),
                 ("ms_seed", C.c_float), ("ms_sa", C.c_float), ("ms_pair", C.c_float),
                 ("ms_dp", C.c_float), ("ms_total", C.c_float), ("ms_wall", C.c_float), ("ms_fill", C.c_float), ("ms_tb", C.c_float),
@@ -105,6 +109,7 @@ def lib():
                                   C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
         L.mp_align_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.mp_results_release.argtypes = [C.c_void_p, C.c_void_p]
+        L.mp_last_stats.argtypes = [C.c_void_p, C.c_void_p]
         L.mp_default_params.argtypes = [C.c_void_p, C.c_int]
         _lib = L
     return _lib
@@ -353,8 +358,15 @@ class Context:
                    cigars=bytes((C.c_char * res.cigar_bytes).from_address(res.cigars)) if res.cigar_bytes else b"")
         for name, _ in Results._fields_[8:]:
             out[name] = getattr(res, name)
+        out.update(self.last_stats())
         self.L.mp_results_release(self.h, C.byref(res))
         return out
+
+    def last_stats(self):
+        """work counters and device timings of this context's last mp_align_pairs call (mp_last_stats)"""
+        st = Stats()
+        self._check(self.L.mp_last_stats(self.h, C.byref(st)))
+        return {name: getattr(st, name) for name, _ in Stats._fields_ if name != "reserved_"}
 
 
 def _summary(self, params):
@@ -363,6 +375,7 @@ def _summary(self, params):
     res = Results()
     self._check(self.L.mp_align_pairs(self.h, C.byref(params), C.byref(res)))
     out = {name: getattr(res, name) for name, _ in Results._fields_[8:]}
+    out.update(self.last_stats())
     out["n_pairs"], out["n_singles"], out["n_rescued"] = res.n_pairs, res.n_singles, res.n_rescued
     out["result_bytes"] = (res.n_pairs + res.n_rescued) * PAIR_RESULT.itemsize + res.n_singles * SINGLE_RESULT.itemsize + res.cigar_bytes
     out["pairs_aligned"] = res.numDPAlignedPair + res.numRescuedPair

@@ -22,6 +22,9 @@
 #include <ctype.h>
 #include <zlib.h>
 #include <sys/stat.h>
+#include <sys/mman.h>
+#include <fcntl.h>
+#include <unistd.h>
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -185,60 +188,86 @@ struct Annotation {
 // ------------------------------------------------------------------------------------------------
 // FASTA/FASTQ reader with kseq semantics (name up to the first blank, comment = rest of the header)
 struct SeqReader {
-    gzFile f = nullptr; std::vector<char> buf; size_t pos = 0, end = 0; bool eof = false; int last = 0;
-    bool open(const std::string &path) { f = gzopen(path.c_str(), "rb"); if (!f) return false; gzbuffer(f, 1 << 22); buf.resize(1 << 22); return true; }
-    bool fill() { if (eof) return false; int n = gzread(f, buf.data(), (unsigned)buf.size()); if (n <= 0) { eof = true; return false; } pos = 0; end = (size_t)n; return true; }
-    int getc_() { if (pos >= end && !fill()) return -1; return (unsigned char)buf[pos++]; }
+    gzFile f = nullptr; std::vector<char> own; char *base = nullptr; size_t pos = 0, end = 0; bool eof = false; int last = 0;
+    // A plain regular file is memory-mapped instead: the whole file is the buffer (nothing left to fill), the record parsers below work
+    // on it unchanged, and load_batch can locate a batch's records and parse them with several threads (parse_mapped).
+    bool mapped = false;
+    bool open(const std::string &path) {
+        if (!getenv("MP_NO_MMAP")) {
+            int fd = ::open(path.c_str(), O_RDONLY);
+            if (fd >= 0) {
+                struct stat sb; unsigned char magic[2] = { 0, 0 };
+                if (fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size >= 2 && pread(fd, magic, 2, 0) == 2 && !(magic[0] == 0x1f && magic[1] == 0x8b)) {
+                    void *m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+                    if (m != MAP_FAILED) {
+                        madvise(m, (size_t)sb.st_size, MADV_SEQUENTIAL);
+                        base = (char *)m; pos = 0; end = (size_t)sb.st_size; eof = true; mapped = true;
+                        ::close(fd);
+                        return true;
+                    }
+                }
+                ::close(fd);
+            }
+        }
+        f = gzopen(path.c_str(), "rb"); if (!f) return false; gzbuffer(f, 1 << 22); own.resize(1 << 22); base = own.data(); return true;
+    }
+    bool fill() { if (eof) return false; int n = gzread(f, base, (unsigned)own.size()); if (n <= 0) { eof = true; return false; } pos = 0; end = (size_t)n; return true; }
+    int getc_() { if (pos >= end && !fill()) return -1; return (unsigned char)base[pos++]; }
     // reads up to the delimiter class: 0 = blank (space/tab/newline), 2 = newline; returns delimiter or -1.  Whole buffer ranges
     // are appended at once (the per-character version of this loop was the slowest part of the driver).
     int getuntil(int mode, std::string &s, bool append) {
         if (!append) s.clear();
         for (;;) {
             if (pos >= end && !fill()) return -1;
-            const char *b = buf.data() + pos, *e = buf.data() + end, *q;
+            const char *b = base + pos, *e = base + end, *q;
             if (mode == 2) q = (const char *)memchr(b, '\n', (size_t)(e - b));
             else { q = b; while (q < e && !isspace((unsigned char)*q)) ++q; if (q == e) q = nullptr; }
             if (!q) { s.append(b, (size_t)(e - b)); pos = end; continue; }
-            s.append(b, (size_t)(q - b)); pos = (size_t)(q - buf.data()) + 1;
+            s.append(b, (size_t)(q - b)); pos = (size_t)(q - base) + 1;
             if (mode == 2 && !s.empty() && s.back() == '\r') s.pop_back();
             return (unsigned char)*q;
         }
     }
-    // Fast path for the usual four-line FASTQ record lying whole inside the buffer: views into the buffer, no copies.
-    // -> 1: record returned; 0: not applicable here (caller falls back to read(), which gives the same answer); -1: end of file.
     struct View { const char *name, *comment, *seq, *qual; size_t nameLen, commentLen, seqLen; };
+    // The usual four-line FASTQ record lying whole inside [b, e): views into the buffer, no copies.
+    // -> 1: record returned, *next = first byte after it; 0: not a plain four-line record; -1: no four newlines before e
+    static int view_record(const char *b, const char *e, View &v, const char **next) {
+        if (b >= e || *b != '@') return 0;
+        const char *n1 = (const char *)memchr(b, '\n', (size_t)(e - b));
+        const char *n2 = n1 ? (const char *)memchr(n1 + 1, '\n', (size_t)(e - n1 - 1)) : nullptr;
+        const char *n3 = n2 ? (const char *)memchr(n2 + 1, '\n', (size_t)(e - n2 - 1)) : nullptr;
+        const char *n4 = n3 ? (const char *)memchr(n3 + 1, '\n', (size_t)(e - n3 - 1)) : nullptr;
+        if (!n4) return -1;
+        const char *h = b + 1, *he = n1; if (he > h && he[-1] == '\r') --he;
+        const char *q = h; while (q < he && !isspace((unsigned char)*q)) ++q;
+        v.name = h; v.nameLen = (size_t)(q - h);
+        if (q < he) { v.comment = q + 1; v.commentLen = (size_t)(he - q - 1); } else { v.comment = he; v.commentLen = 0; }
+        const char *s0 = n1 + 1, *s1 = n2; if (s1 > s0 && s1[-1] == '\r') --s1;
+        if (s1 == s0 || *s0 == '>' || *s0 == '+' || *s0 == '@' || n2[1] != '+') return 0;
+        const char *q0 = n3 + 1, *q1 = n4; if (q1 > q0 && q1[-1] == '\r') --q1;
+        if ((size_t)(q1 - q0) != (size_t)(s1 - s0)) return 0;
+        v.seq = s0; v.seqLen = (size_t)(s1 - s0); v.qual = q0;
+        *next = n4 + 1;
+        return 1;
+    }
+    // Fast path of the sequential reader.
+    // -> 1: record returned; 0: not applicable here (caller falls back to read(), which gives the same answer); -1: end of file.
     int read_fast(View &v) {
         if (last != 0) return 0;
         for (int attempt = 0; attempt < 2; ++attempt) {
             if (pos >= end) { if (!fill()) return -1; }
-            const char *b = buf.data() + pos, *e = buf.data() + end;
-            if (*b != '@') return 0;
-            const char *n1 = (const char *)memchr(b, '\n', (size_t)(e - b));
-            const char *n2 = n1 ? (const char *)memchr(n1 + 1, '\n', (size_t)(e - n1 - 1)) : nullptr;
-            const char *n3 = n2 ? (const char *)memchr(n2 + 1, '\n', (size_t)(e - n2 - 1)) : nullptr;
-            const char *n4 = n3 ? (const char *)memchr(n3 + 1, '\n', (size_t)(e - n3 - 1)) : nullptr;
-            if (!n4) {
-                if (attempt == 1 || eof) return 0;
-                // the record crosses the end of the buffer: move the tail to the front and top the buffer up
-                const size_t rest = (size_t)(e - b);
-                if (rest == buf.size()) return 0;                  // a record larger than the buffer: leave it to read()
-                memmove(buf.data(), b, rest); pos = 0; end = rest;
-                int n = gzread(f, buf.data() + end, (unsigned)(buf.size() - end));
-                if (n <= 0) { eof = true; return 0; }
-                end += (size_t)n;
-                continue;
-            }
-            const char *h = b + 1, *he = n1; if (he > h && he[-1] == '\r') --he;
-            const char *q = h; while (q < he && !isspace((unsigned char)*q)) ++q;
-            v.name = h; v.nameLen = (size_t)(q - h);
-            if (q < he) { v.comment = q + 1; v.commentLen = (size_t)(he - q - 1); } else { v.comment = he; v.commentLen = 0; }
-            const char *s0 = n1 + 1, *s1 = n2; if (s1 > s0 && s1[-1] == '\r') --s1;
-            if (s1 == s0 || *s0 == '>' || *s0 == '+' || *s0 == '@' || n2[1] != '+') return 0;
-            const char *q0 = n3 + 1, *q1 = n4; if (q1 > q0 && q1[-1] == '\r') --q1;
-            if ((size_t)(q1 - q0) != (size_t)(s1 - s0)) return 0;
-            v.seq = s0; v.seqLen = (size_t)(s1 - s0); v.qual = q0;
-            pos = (size_t)(n4 - buf.data()) + 1;
-            return 1;
+            const char *b = base + pos, *e = base + end, *next = nullptr;
+            const int st = view_record(b, e, v, &next);
+            if (st == 1) { pos = (size_t)(next - base); return 1; }
+            if (st == 0) return 0;
+            if (attempt == 1 || eof) return 0;
+            // the record crosses the end of the buffer: move the tail to the front and top the buffer up
+            const size_t rest = (size_t)(e - b);
+            if (rest == own.size()) return 0;                  // a record larger than the buffer: leave it to read()
+            memmove(base, b, rest); pos = 0; end = rest;
+            int n = gzread(f, base + end, (unsigned)(own.size() - end));
+            if (n <= 0) { eof = true; return 0; }
+            end += (size_t)n;
         }
         return 0;
     }
@@ -285,11 +314,13 @@ struct ReadBatch {
 };
 
 static unsigned char g_charMap[256];
+static char g_outChar[256];                                      // the base soap4 prints for an input character: "ACGT"[charMap[c]]
 static void fill_char_map() {                                    // INDEXFillCharMap (IndexHandler.cpp:26-45)
     memset(g_charMap, 0, sizeof g_charMap);
     const char *dna = "ACGT";
     for (int i = 0; i < 4; ++i) { g_charMap[(int)dna[i]] = (unsigned char)i; g_charMap[dna[i] - 'A' + 'a'] = (unsigned char)i; }
     g_charMap['U'] = g_charMap['u'] = 3; g_charMap['N'] = g_charMap['n'] = 2;
+    for (int c = 0; c < 256; ++c) g_outChar[c] = "ACGT"[g_charMap[c]];
 }
 
 static void append_read(ReadBatch &b, uint32_t id, const char *name, size_t nameLen, const char *comment, size_t commentLen,
@@ -327,6 +358,83 @@ static void pack_reads(ReadBatch &b, uint32_t first, uint32_t last)
     }
 }
 
+
+static size_t count_newlines(const char *p, size_t n)
+{
+    size_t c = 0;
+    for (const char *q = p, *e = p + n; (q = (const char *)memchr(q, '\n', (size_t)(e - q))) != nullptr; ++q) ++c;
+    return c;
+}
+
+// A batch out of a memory-mapped FASTQ file, parsed by several threads.  Records are located, not guessed: the newlines of the
+// region are counted in 256 KiB blocks (in parallel), which gives the byte offset of every 4k-th line, and every thread then parses
+// its run of four-line records with the same record view as the sequential reader.  If anything is not a plain four-line record (a
+// multi-line FASTA / FASTQ, a quality string of another length, a missing final newline) nothing is consumed and the caller parses the
+// batch sequentially -- same records either way (tests/test_driver_host.py).
+// -> records parsed, *newPos = offset behind them; -1: use the sequential parser
+static long parse_mapped(const SeqReader &r, ReadBatch &b, uint32_t first, uint32_t maxRec, unsigned nThr, size_t *newPos)
+{
+    const char *beg = r.base + r.pos, *lim = r.base + r.end;
+    *newPos = r.pos;
+    if (r.last != 0) return -1;
+    if (beg >= lim || maxRec == 0) return 0;
+    if (lim[-1] != '\n') return -1;
+    SeqReader::View v0; const char *next0 = nullptr;
+    if (SeqReader::view_record(beg, lim, v0, &next0) != 1) return -1;
+    const size_t B = (size_t)1 << 18, remaining = (size_t)(lim - beg), rec0 = (size_t)(next0 - beg);
+    nThr = std::max(1u, nThr);
+    auto par = [&](size_t n, const std::function<void(size_t)> &fn) {       // fn(k) for k in [0, n), strided over the threads
+        const unsigned T = (unsigned)std::min<size_t>(nThr, std::max<size_t>(n, 1));
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < T; ++t) th.emplace_back([&, t] { for (size_t k = t; k < n; k += T) fn(k); });
+        for (size_t k = 0; k < n; k += T) fn(k);
+        for (std::thread &x : th) x.join();
+    };
+    // ---- newline counts per block, over a window that grows until it holds the batch (or the rest of the file) ----
+    size_t window = std::min(remaining, (size_t)((double)maxRec * (double)rec0 * 1.02) + B), fullCounted = 0;
+    std::vector<uint32_t> cnt;
+    uint64_t lines = 0;
+    for (;;) {
+        const size_t nBlocks = (window + B - 1) / B;
+        cnt.resize(nBlocks);
+        par(nBlocks - fullCounted, [&](size_t k) { const size_t blk = fullCounted + k; cnt[blk] = (uint32_t)count_newlines(beg + blk * B, std::min(B, window - blk * B)); });
+        lines = 0; for (uint32_t c : cnt) lines += c;
+        if (lines >= 4ull * maxRec || window == remaining) break;
+        fullCounted = window / B;                                            // the partial last block is counted again
+        window = std::min(remaining, window + window / 8 + B);
+    }
+    if (lines < 4ull * maxRec && (lines & 3)) return -1;                      // the file ends inside the window, not after a whole record
+    const uint64_t nRec = std::min<uint64_t>(maxRec, lines / 4);
+    if (nRec == 0) return -1;
+    std::vector<uint64_t> pre(cnt.size() + 1, 0);
+    for (size_t k = 0; k < cnt.size(); ++k) pre[k + 1] = pre[k] + cnt[k];
+    auto after_line = [&](uint64_t L) -> const char * {                      // first byte after the L-th newline of the region (L >= 1)
+        const size_t k = (size_t)(std::lower_bound(pre.begin(), pre.end(), L) - pre.begin()) - 1;     // pre[k] < L <= pre[k+1]
+        const char *q = beg + k * B;
+        for (uint64_t need = L - pre[k]; need; --need) q = (const char *)memchr(q, '\n', (size_t)(lim - q)) + 1;
+        return q;
+    };
+    const unsigned T = (unsigned)std::min<uint64_t>(nThr, std::max<uint64_t>(1, nRec / 256));
+    std::vector<const char *> start(T + 1);
+    std::vector<uint64_t> firstRec(T + 1);
+    for (unsigned t = 0; t <= T; ++t) { firstRec[t] = nRec * t / T; start[t] = firstRec[t] == 0 ? beg : after_line(4 * firstRec[t]); }
+    std::atomic<bool> bad(false);
+    par(T, [&](size_t t) {
+        const char *q = start[t], *e = start[t + 1];
+        SeqReader::View v;
+        for (uint64_t rec = firstRec[t]; rec < firstRec[t + 1]; ++rec) {
+            const char *next = nullptr;
+            if (SeqReader::view_record(q, e, v, &next) != 1) { bad.store(true); return; }
+            append_read(b, first + 2 * (uint32_t)rec, v.name, v.nameLen, v.comment, v.commentLen, v.seq, v.seqLen, v.qual, v.seqLen);
+            q = next;
+        }
+        if (q != e) bad.store(true);
+    });
+    if (bad.load()) return -1;
+    *newPos = (size_t)(start[T] - r.base);
+    return (long)nRec;
+}
+
 static uint32_t load_batch(SeqReader &r1, SeqReader &r2, ReadBatch &b, uint32_t maxReads, unsigned packThreads = 4)
 {
     size_t words = ((size_t)maxReads + 31) / 32 * 32 * b.wpq;
@@ -340,6 +448,26 @@ static uint32_t load_batch(SeqReader &r1, SeqReader &r2, ReadBatch &b, uint32_t 
     if (!b.qualBuf || b.qstride != (size_t)b.maxReadLength + 1 || b.qcap != slots) {
         b.qstride = (size_t)b.maxReadLength + 1; b.qcap = slots;
         b.qualBuf.reset(new char[slots * b.qstride]); b.seqBuf.reset(new char[slots * b.qstride]);
+    }
+    // both files memory-mapped: thread teams parse the batch's records of either file, then every thread packs whole groups of 32 reads
+    if (r1.mapped && r2.mapped) {
+        const unsigned team = std::max(1u, packThreads);
+        long n1 = -1, n2 = -1; size_t p1 = r1.pos, p2 = r2.pos;
+        std::thread t2([&] { n2 = parse_mapped(r2, b, 1, maxReads / 2, team, &p2); });
+        n1 = parse_mapped(r1, b, 0, (maxReads + 1) / 2, team, &p1);
+        t2.join();
+        if (n1 >= 0 && n2 >= 0) {
+            if (n1 != n2) { fprintf(stderr, "Error: number of sequences of pair-end files not matched.\n"); exit(1); }
+            r1.pos = p1; r2.pos = p2;
+            b.nReads = 2 * (uint32_t)n1;
+            const uint32_t nGroups = (b.nReads + 31) / 32, T = std::min<uint32_t>(2 * team, std::max(1u, nGroups / 64));
+            std::vector<std::thread> th;
+            for (uint32_t t = 1; t < T; ++t) th.emplace_back([&, t] { pack_reads(b, (uint32_t)((uint64_t)nGroups * t / T) * 32, std::min(b.nReads, (uint32_t)((uint64_t)nGroups * (t + 1) / T) * 32)); });
+            pack_reads(b, 0, std::min(b.nReads, (uint32_t)((uint64_t)nGroups / T) * 32));
+            for (std::thread &x : th) x.join();
+            return b.nReads;
+        }
+        // not plain four-line FASTQ here: nothing was consumed, the sequential parsers below take the batch
     }
     // the two files are parsed by two threads: mate 1 fills the even read ids, mate 2 the odd ones.  Packing threads follow them:
     // each owns every nt-th group of 32 reads (the unit the word layout interleaves) and packs a group as soon as both parsers
@@ -424,46 +552,58 @@ static int mapping_from_header(const std::string *comment, std::vector<HeaderHit
 
 static void seq_and_qual(std::string &out, const ReadBatch &b, uint32_t id)
 {
-    const uint32_t *q = b.queries.data() + ((size_t)(id / 32) * 32 * b.wpq + id % 32);
-    uint32_t len = b.lens[id];
+    // the 2-bit words hold exactly charMap[c] of the parsed characters (pack_reads), so the printed sequence is a table look-up away
+    const uint32_t len = b.lens[id], ql = b.qlen(id);
+    const unsigned char *sq = (const unsigned char *)b.seqBuf.get() + b.slot(id) * b.qstride;
     const size_t at = out.size();
-    out.resize(at + len);
+    out.resize(at + len + 3 + ql + 1);
     char *w = &out[at];
-    for (uint32_t i = 0; i < len; i += 16) {
-        uint32_t word = q[(i >> 4) * 32];
-        const uint32_t m = len - i < 16 ? len - i : 16;
-        for (uint32_t k = 0; k < m; ++k, word >>= 2) w[i + k] = "ACGT"[word & 3];
-    }
-    out += "\n+\n"; out.append(b.qual(id), b.qlen(id)); out.push_back('\n');
+    for (uint32_t i = 0; i < len; ++i) w[i] = g_outChar[sq[i]];
+    w += len; *w++ = '\n'; *w++ = '+'; *w++ = '\n';
+    memcpy(w, b.qual(id), ql); w[ql] = '\n';
 }
 
-static inline void append_int(std::string &s, long long v)
+static inline char *put_int(char *w, long long v)
 {
     char tmp[24]; int n = 0; bool neg = v < 0; unsigned long long u = neg ? 0ull - (unsigned long long)v : (unsigned long long)v;
     do { tmp[n++] = (char)('0' + u % 10); u /= 10; } while (u);
-    if (neg) s.push_back('-');
-    while (n) s.push_back(tmp[--n]);
+    if (neg) *w++ = '-';
+    while (n) *w++ = tmp[--n];
+    return w;
 }
+// One output record: "@name\tSCORE:<best>;<score>,<chr>;...<kept entries of the previous comment>\n" (BGS-IO.cpp:1966-2091, 1348-1371),
+// then sequence, "+", qualities.  Written through a raw pointer into space reserved once per record: at a million pairs per batch the
+// capacity checks of a dozen small std::string appends per read were most of the formatting time.
 static void header_line(std::string &ret, const ReadBatch &b, uint32_t id, const Annotation &ann, std::vector<std::pair<int, int>> &chrHits,
                         int bestScore, double top, bool ignoreComments)
 {
     const std::string *comment = (!ignoreComments && b.hasComment(id)) ? &b.comment(id) : nullptr;
-    ret += "@"; ret += b.name(id);
-    if (comment && *comment == "IGNORE") { ret += "\tIGNORE\n"; return; }
-    std::sort(chrHits.begin(), chrHits.end());
+    const std::string &name = b.name(id);
+    size_t bound = 1 + name.size() + 8 + 24 + 2 + (comment ? comment->size() + 8 : 0);
+    for (size_t i = 0; i < chrHits.size(); ++i) bound += 24 + ann.names[chrHits[i].first - 1].size();
+    const size_t at = ret.size();
+    ret.resize(at + bound);
+    char *w0 = &ret[at], *w = w0;
+    *w++ = '@'; memcpy(w, name.data(), name.size()); w += name.size();
+    if (comment && *comment == "IGNORE") { memcpy(w, "\tIGNORE\n", 8); w += 8; ret.resize(at + (size_t)(w - w0)); return; }
+    if (chrHits.size() > 1) std::sort(chrHits.begin(), chrHits.end());
     std::vector<HeaderHit> v;
     int prev = mapping_from_header(comment, v, top, bestScore * top);
     if (prev > bestScore) bestScore = prev;
-    ret += "\tSCORE:"; append_int(ret, bestScore); ret.push_back(';');
+    memcpy(w, "\tSCORE:", 7); w += 7; w = put_int(w, bestScore); *w++ = ';';
     if (bestScore > 0)
         for (size_t i = 0; i < chrHits.size(); ++i) {
             if (i > 0 && chrHits[i].first == chrHits[i - 1].first) continue;
-            if (-chrHits[i].second > 0 && -chrHits[i].second >= bestScore * top)
-                { append_int(ret, -(long long)chrHits[i].second); ret.push_back(','); ret += ann.names[chrHits[i].first - 1]; ret.push_back(';'); }
+            if (-chrHits[i].second > 0 && -chrHits[i].second >= bestScore * top) {
+                w = put_int(w, -(long long)chrHits[i].second); *w++ = ',';
+                const std::string &cn = ann.names[chrHits[i].first - 1];
+                memcpy(w, cn.data(), cn.size()); w += cn.size(); *w++ = ';';
+            }
         }
     for (size_t i = 0; i < v.size(); ++i)
-        if (v[i].score >= bestScore * top) { ret.append(*comment, v[i].s, v[i].e - v[i].s); ret.push_back(';'); }
-    ret += "\n";
+        if (v[i].score >= bestScore * top) { memcpy(w, comment->data() + v[i].s, v[i].e - v[i].s); w += v[i].e - v[i].s; *w++ = ';'; }
+    *w++ = '\n';
+    ret.resize(at + (size_t)(w - w0));
 }
 
 struct OutScratch;
@@ -1033,7 +1173,7 @@ int main(int argc, char **argv)
             const uint32_t numQueries = b.nReads, nPairs = numQueries / 2;
             mp_results R;
             static const bool timing = getenv("MP_DRIVER_TIMING") != nullptr;      // per-batch host breakdown on stderr
-            double tUp = 0, tAl = 0, tFmt = 0;
+            double tUp = 0, tAl = 0, tFmt = 0, libWallMs = 0;
             int rcUp = mp_batch_upload(gpu, b.queries.data(), b.lens.data(), numQueries, b.wpq);
             tUp = now_s();
             if (rcUp || mp_align_pairs(gpu, &P, &R)) {
@@ -1047,6 +1187,7 @@ int main(int argc, char **argv)
                 j->log = line;
                 j->pairsAligned = R.numDPAlignedPair + R.numRescuedPair;
                 tAl = now_s();
+                if (timing) { mp_stats st; if (mp_last_stats(gpu, &st) == 0) libWallMs = st.ms_wall; }
                 // ---- output: stage order of the reference (deep DP pairs, rescued pairs, then everything else) ----
                 if (opt.megapathMode || opt.outputBAM) {
                     oc.b = &b;
@@ -1067,7 +1208,7 @@ int main(int argc, char **argv)
                             OutCtx occ = oc; BamWriter capw; capw.capture = &chunks[c].bam;
                             OutScratch scr; occ.scratch = &scr;
                             occ.bam = opt.outputBAM ? &capw : nullptr;
-                            chunks[c].fq.reserve((size_t)(cut[c + 1] - cut[c]) * 512);
+                            chunks[c].fq.reserve((size_t)(cut[c + 1] - cut[c]) * (size_t)(4 * maxLen + 160));
                             body(occ, chunks[c].fq, cut[c], cut[c + 1]);
                             if (opt.lsam >= 0 && !chunks[c].fq.empty()) { std::string ls; fastq_chunk_to_lsam(chunks[c].fq, opt.lsam != 0, ls); chunks[c].fq.swap(ls); }
                             if (!chunks[c].bam.empty()) { BgzfWriter::compress_all(chunks[c].bam.data(), chunks[c].bam.size(), chunks[c].bamz); std::vector<uint8_t>().swap(chunks[c].bam); }
@@ -1123,7 +1264,7 @@ int main(int argc, char **argv)
                 mp_results_release(gpu, &R);
             }
             if (timing) fprintf(stderr, "[timing] batch %llu: upload %.3f align %.3f (lib wall %.3f) format %.3f release %.3f s\n", (unsigned long long)j->seq,
-                                tUp - ts, tAl - tUp, R.ms_wall / 1e3, tFmt - tAl, now_s() - tFmt);
+                                tUp - ts, tAl - tUp, libWallMs / 1e3, tFmt - tAl, now_s() - tFmt);
             j->alignSeconds = now_s() - ts;
             std::lock_guard<std::mutex> lk(mu);
             batchPool.push_back(j->b); j->b = nullptr;              // the text output no longer refers to the batch
@@ -1136,6 +1277,7 @@ int main(int argc, char **argv)
     // ---- ordered writer ----
     double totalLoad = 0, totalAlign = 0; const double tLoop0 = now_s();
     uint64_t totalPairsAligned = 0, next = 0; bool failed = false, announced = false;
+    double writeSeconds = 0; uint64_t writtenBytes = 0;
     for (;;) {
         Job *j = nullptr;
         {
@@ -1149,7 +1291,9 @@ int main(int argc, char **argv)
         if (!announced) { fprintf(stderr, "All reads are directly processed by DP\n"); announced = true; }
         fputs(j->log.c_str(), stderr);
         if (j->failed) failed = true;
-        for (const std::string &part : j->fqParts) if (!part.empty()) fwrite(part.data(), 1, part.size(), stdout);
+        const double tw0 = now_s();
+        for (const std::string &part : j->fqParts) if (!part.empty()) { fwrite(part.data(), 1, part.size(), stdout); writtenBytes += part.size(); }
+        writeSeconds += now_s() - tw0;
         if (opt.outputBAM) { bamDP.write_blocks(j->bam[0]); bamGout.write_blocks(j->bam[1]); bamUnpair.write_blocks(j->bam[2]); }
         fprintf(stderr, "[Main] Elapsed time : %9.4f seconds\n\n", j->alignSeconds);
         totalLoad += j->loadSeconds; totalAlign += j->alignSeconds; totalPairsAligned += j->pairsAligned;
@@ -1161,6 +1305,7 @@ int main(int argc, char **argv)
     fflush(stdout);
     if (opt.outputBAM) { bamDP.close(); bamGout.close(); bamUnpair.close(); }
     if (failed) return 1;
+    if (getenv("MP_DRIVER_TIMING")) fprintf(stderr, "[timing] writer: %.3f s in stdout writes, %.1f MB\n", writeSeconds, writtenBytes / 1e6);
     fprintf(stderr, "[Main] Overall number of pairs of reads aligned: %llu\n", (unsigned long long)totalPairsAligned);
     fprintf(stderr, "[Main] Overall read load time : %9.4f seconds\n", totalLoad);
     fprintf(stderr, "[Main] Overall alignment time (excl. read loading) : %9.4f seconds\n", now_s() - tLoop0);

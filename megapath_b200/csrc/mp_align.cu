@@ -584,21 +584,29 @@ extern "C" int mp_align_pairs(mp_context *ctx, const mp_align_params *params, mp
     tr.mark("single+default dp");
     unsigned long long hc[16];
     MP_CUDA(cudaMemcpy(hc, ctx->dCounters.p, sizeof hc, cudaMemcpyDeviceToHost));
-    out->n_occ = hc[2]; out->n_lf = hc[5] + hc[8]; out->n_sa = hc[3]; out->n_lkt = hc[4]; out->n_probe = hc[9]; out->n_text = hc[10];
-    ctx->ev_collect(out->ms_fill, out->ms_tb, out->ms_exact);
-    out->dp_cells = cells; out->dp_tasks = tasksRun; out->dp_tasks_exact = hc[14]; out->dp_cells_filled = hc[15];
-    cudaEventElapsedTime(&out->ms_seed, ctx->ev[0], ctx->ev[1]);
-    cudaEventElapsedTime(&out->ms_sa, ctx->ev[1], ctx->ev[2]);
-    cudaEventElapsedTime(&out->ms_pair, ctx->ev[2], ctx->ev[3]);
-    cudaEventElapsedTime(&out->ms_dp, ctx->ev[5], ctx->ev[6]);
-    cudaEventElapsedTime(&out->ms_total, ctx->ev[4], ctx->ev[6]);
+    mp_stats &S = ctx->stats;
+    memset(&S, 0, sizeof S);
+    S.n_occ = hc[2]; S.n_lf = hc[5] + hc[8]; S.n_sa = hc[3]; S.n_lkt = hc[4]; S.n_probe = hc[9]; S.n_text = hc[10];
+    ctx->ev_collect(S.ms_fill, S.ms_tb, S.ms_exact);
+    S.dp_cells = cells; S.dp_tasks = tasksRun; S.dp_tasks_exact = hc[14]; S.dp_cells_filled = hc[15];
+    cudaEventElapsedTime(&S.ms_seed, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&S.ms_sa, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&S.ms_pair, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&S.ms_dp, ctx->ev[5], ctx->ev[6]);
+    cudaEventElapsedTime(&S.ms_total, ctx->ev[4], ctx->ev[6]);
     out->pairs = ctx->hPairs.data(); out->n_pairs = ctx->hPairs.size();
     out->rescued = ctx->hRescued.data(); out->n_rescued = ctx->hRescued.size();
     out->singles = ctx->hSingles.data(); out->n_singles = ctx->hSingles.size();
     out->cigars = ctx->hCigars.data(); out->cigar_bytes = ctx->hCigars.size();
     ctx->seeded = false;       // the batch has been consumed
-    out->ms_wall = (float)(mp_now_ms() - wall0);
+    S.ms_wall = (float)(mp_now_ms() - wall0);
     tr.mark("finish");
+    return 0;
+}
+extern "C" int mp_last_stats(mp_context *ctx, mp_stats *stats)
+{
+    if (!ctx || !stats) { mp_set_error("mp_last_stats: null argument"); return MP_ERR_ARG; }
+    *stats = ctx->stats;
     return 0;
 }
 extern "C" void mp_results_release(mp_context *ctx, mp_results *res)

@@ -141,6 +141,7 @@ struct mp_context {
     DevBuf dExFlag, dExPos, dExIdx;                                              // exact-occurrence test: flags, scan, active slots (mp_dp.cu)
     DevBuf dLT, dRT, dLO, dRO, dLP, dRP, dOk, dBytes, dIdx, dOff, dRes, dCig;   // stage S1 chunk buffers (kept across calls)
     DevBuf dRes2, dKeep, dKeepPos, dTotals;                                      // stage S1 per-pair dedup / best pick (k_pair_ready)
+    mp_stats stats = {};                    // work counters / timings of the last mp_align_pairs call (mp_last_stats)
     // results (host, owned until release)
     PinnedBuf<mp_pair_result> hPairs;
     PinnedBuf<mp_pair_result> hRescued;

@@ -44,7 +44,7 @@ def test_struct_sizes_match_header():
     assert mp.PAIR_RESULT.itemsize == 104
     assert mp.SINGLE_RESULT.itemsize == 56
     assert ctypes.sizeof(mp.MmpParams) == 48 and ctypes.sizeof(mp.AlignParams) == 48 + 12 * 4
-    assert ctypes.sizeof(mp.Results) == 232
+    assert ctypes.sizeof(mp.Results) == 112 and ctypes.sizeof(mp.Stats) == 120
     assert mp.SEEDPOS.itemsize == 16 and mp.CAND.itemsize == 24
 
 

@@ -148,3 +148,50 @@ def test_lsam_mode_matches_reference_fastq2lsam(tmp_path, output_seq):
     got = subprocess.run([EXE, "__lsam", str(f), output_seq], capture_output=True, check=True, timeout=60).stdout
     assert want.count(b"\n") == 10
     assert got == want
+
+
+def _pack(f1, f2, maxlen, out, threads, env=None):
+    subprocess.run([EXE, "__pack", str(f1), str(f2), str(maxlen), str(out), str(threads)], check=True, timeout=300,
+                   env=dict(os.environ, **(env or {})))
+    return open(out, "rb").read()
+
+
+@pytest.mark.parametrize("kind", ["plain", "crlf", "multiline", "no_final_newline", "qual_mismatch_late"])
+def test_parallel_mapped_parser_equals_sequential(tmp_path, kind):
+    """Plain files are memory-mapped and a batch is parsed by several threads after its record boundaries have been located by
+    counting newlines (parse_mapped); anything that is not strict four-line FASTQ makes the batch fall back to the sequential
+    parser.  Either way the loader must hand over exactly what the sequential gz-style reader (MP_NO_MMAP=1) hands over."""
+    rng = np.random.default_rng(len(kind))
+    npairs = 9000
+    nl = b"\r\n" if kind == "crlf" else b"\n"
+    recs = {1: [], 2: []}
+    for p in range(npairs):
+        for mate in (1, 2):
+            L = int(rng.integers(25, 140))
+            seq = bytes(rng.choice(np.frombuffer(b"ACGTNacgt", dtype=np.uint8), L).tolist())
+            qual = bytes(rng.integers(33, 74, L).astype(np.uint8).tolist())         # '@' and '+' appear at line starts
+            comment = b" SCORE:9;4,chrZ;" if p % 5 == 0 else b""
+            if kind == "multiline" and p % 1000 == 999:
+                h = L // 2
+                recs[mate].append(b"@q%d/%d%s" % (p, mate, comment) + nl + seq[:h] + nl + seq[h:] + nl + b"+" + nl + qual[:h] + nl + qual[h:] + nl)
+            elif kind == "qual_mismatch_late" and p == npairs - 3 and mate == 2:
+                recs[mate].append(b"@q%d/%d" % (p, mate) + nl + seq + nl + b"+" + nl + qual + b"I" + nl)    # refused by both readers the same way?
+            else:
+                recs[mate].append(b"@q%d/%d%s" % (p, mate, comment) + nl + seq + nl + b"+" + nl + qual + nl)
+    d1, d2 = b"".join(recs[1]), b"".join(recs[2])
+    if kind == "no_final_newline":
+        d1, d2 = d1[:-1], d2[:-1]
+    f1, f2 = tmp_path / "p_1.fq", tmp_path / "p_2.fq"
+    f1.write_bytes(d1); f2.write_bytes(d2)
+    if kind == "qual_mismatch_late":
+        # a quality string longer than its sequence is an input error in either mode (kseq returns -2): both must fail, not diverge
+        a = subprocess.run([EXE, "__pack", str(f1), str(f2), "131", str(tmp_path / "a.bin"), "6"], capture_output=True, timeout=300)
+        b = subprocess.run([EXE, "__pack", str(f1), str(f2), "131", str(tmp_path / "b.bin"), "6"], capture_output=True, timeout=300, env=dict(os.environ, MP_NO_MMAP="1"))
+        assert a.returncode == b.returncode
+        if a.returncode == 0:
+            assert open(tmp_path / "a.bin", "rb").read() == open(tmp_path / "b.bin", "rb").read()
+        return
+    got = _pack(f1, f2, 131, tmp_path / "a.bin", 6)
+    want = _pack(f1, f2, 131, tmp_path / "b.bin", 6, {"MP_NO_MMAP": "1"})
+    assert np.frombuffer(want[:4], dtype=np.uint32)[0] == 2 * npairs
+    assert got == want

@@ -39,7 +39,7 @@ fq1, fq2 = os.path.join(d, "r_1.fq"), os.path.join(d, "r_2.fq")
 exe = os.path.join(ROOT, "megapath_b200", "bin", "soap4")
 ini = os.path.join(ROOT, "megapath_b200", "ini", "soap4.ini")
 total = npairs * rep
-for T, ctxs, sink in ((8, 2, "/dev/null"), (8, 3, "/dev/null"), (8, 2, os.path.join(d, "our.out"))):
+for T, ctxs, sink in ((16, 3, "/dev/null"), (16, 3, os.path.join(d, "our.out")), (8, 2, os.path.join(d, "our.out"))):
     t0 = time.time()
     with open(sink, "wb") as fo:
         p = subprocess.run([exe, "pair", prefix, fq1, fq2, "-o", os.path.join(d, "ouro"), "-C", ini, "-L", "151", "-T", str(T), "-u", "750", "-F", "-nc"],
@@ -51,4 +51,4 @@ for T, ctxs, sink in ((8, 2, "/dev/null"), (8, 3, "/dev/null"), (8, 2, os.path.j
     load = [l for l in lines if "Elapsed time on host" in l]
     tim = [l for l in lines if "[timing]" in l]
     print("-T %d, %d contexts, out=%s: wall %.1f s; batch loop %.2f s = %.2f M pairs/s; reader per batch %s; last batches %s" % (
-        T, ctxs, sink, wall, loop, total / loop / 1e6, [l.split(":")[1].split()[0] for l in load[-4:-1]], tim[-3:]), flush=True)
+        T, ctxs, sink, wall, loop, total / loop / 1e6, [l.split(":")[1].split()[0] for l in load[-4:-1]], tim[-4:]), flush=True)
