@@ -28,6 +28,9 @@
 #include <algorithm>
 #include <type_traits>
 
+#ifndef MP_FILL_MINBLOCKS
+#define MP_FILL_MINBLOCKS 6      /* blocks per SM the K = 5 fill kernel is compiled for (register budget 80) */
+#endif
 #define DP_BIAS   0x4000
 #define DP_BIAS2  0x40004000u
 #define DP_NEG2   0x20C020C0u      /* (bias - 8000) in both halves: "minus infinity" that never underflows */
@@ -79,32 +82,69 @@ __device__ __forceinline__ int trace_h(uint32_t cell) { return (int)(((cell + 3u
 __device__ __forceinline__ int trace_flag(uint32_t cell) { const uint32_t g = cell & 3u; return g == 0 ? 1 : g == 3 ? 2 : 0; }
 __device__ __forceinline__ int trace_diff(int a, int b) { return ((a - b + 32) & 63) - 32; }      // a - b for values known mod 64
 
-// Exact answer bookkeeping of one lane (see k_dp_fill): best value so far (biased x4 units), (row << 12 | col) of its first occurrence
-// in row-major order, number of cells equal to it -- per task of the pair.  Kept out of line: it runs for a handful of steps per
-// task, and inlined into every unrolled step it made the hot loop several times larger than the instruction cache likes.
-struct DpTrack { int lb[2]; uint32_t key[2], cnt[2]; int thr[2], L[2], N[2], minCol[2]; };
+// Answer bookkeeping of one lane (see k_dp_fill), per task of the pair: the best value its eligible cells have reached (biased x4 units),
+// and the first and the last ROW in which a cell reached it.  Which column, and how many cells tie, is read back from the lane's own
+// trace bytes when the table is complete (dp_resolve_lane): a step that sets a new best therefore costs a handful of instructions, which
+// matters for divergent reads -- every cell of the optimal path is a new best of its lane, so the tracker runs on most steps there.
+// Kept out of line and in local memory: it must not cost the hot loop registers.
+struct DpTrack { int lb[2], rfirst[2], rlast[2], thrT[2], thr[2], N[2]; uint32_t elig[2]; };
+__device__ __forceinline__ uint32_t dp_track_t2(const DpTrack *tr, int o4)
+{
+    // from now on only cells that at least tie with this lane's best matter: (H + open) + T2 has bit 15 set <=> H >= threshold
+    const int a = max(tr->thrT[0], tr->lb[0]), b = max(tr->thrT[1], tr->lb[1]);
+    return (uint32_t)(0x8000 + o4 - a) | ((uint32_t)(0x8000 + o4 - b) << 16);
+}
+// every column of the lane may hold the answer (all lanes but the one or two at the ends of the eligible column range): cm = packed
+// maximum of the lane's K cells of this row (H + open), q = cm + T2
+__device__ __noinline__ uint32_t dp_track_row(DpTrack *tr, uint32_t cm, uint32_t q, int i, int o4)
+{
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        if (!((q >> (16 * half)) & 0x8000u) || i > tr->N[half] || !tr->elig[half]) continue;      // (padding columns hold anything)
+        const int v = (int)((cm >> (16 * half)) & 0xffffu) + o4;
+        if (v > tr->lb[half]) { tr->lb[half] = v; tr->rfirst[half] = i; tr->rlast[half] = i; }
+        else if (v == tr->lb[half]) tr->rlast[half] = i;
+    }
+    return dp_track_t2(tr, o4);
+}
+// a lane whose columns are only partly eligible (j < L - clipRt, or j > L): the row maximum is taken over the eligible columns
 template <int K>
-__device__ __noinline__ uint32_t dp_track_cells(DpTrack *tr, const uint32_t *ho, uint32_t q, int i, int j0, int o4)
+__device__ __noinline__ uint32_t dp_track_row_masked(DpTrack *tr, const uint32_t *ho, uint32_t q, int i, int o4)
 {
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         if (!((q >> (16 * half)) & 0x8000u) || i > tr->N[half]) continue;
-        int lb = tr->lb[half]; uint32_t key = tr->key[half], cnt = tr->cnt[half];
-        const int Lh = tr->L[half], minCol = tr->minCol[half];
+        int v = -(1 << 20);
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            if ((tr->elig[half] >> k) & 1u) v = max(v, (int)((ho[k] >> (16 * half)) & 0xffffu) + o4);
+        if (v < max(tr->thrT[half], tr->lb[half])) continue;
+        if (v > tr->lb[half]) { tr->lb[half] = v; tr->rfirst[half] = i; tr->rlast[half] = i; }
+        else tr->rlast[half] = i;
+    }
+    return dp_track_t2(tr, o4);
+}
+
+// The cells of one lane that equal the task's best score Ms, looked up in the trace bytes the lane wrote itself: first (row, column) in
+// row-major order and their number, over rows r0..r1 (the first and last row in which the lane's row maximum reached Ms).  A trace byte
+// holds H mod 64.  In row r0 some cell of the lane equals Ms and neighbours in a row differ by at most 1 - open <= 7, so all K <= 10
+// cells lie within 63 of Ms and H is exact; below r0 every cell follows from the one above it (vertical neighbours differ by < 32).
+template <int K>
+__device__ __noinline__ void dp_resolve_lane(const uint8_t *tab, int S, int j0, uint32_t elig, int r0, int r1, int Ms, uint32_t &key, uint32_t &cnt)
+{
+    int H[K], ph[K];
+    uint32_t kfirst = 0xffffffffu, c = 0u;
+    for (int r = r0; r <= r1; ++r) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const int j = j0 + k;
-            const int v = (int)((ho[k] >> (16 * half)) & 0xffffu) + o4;
-            if (j >= minCol && j <= Lh) {
-                if (v > lb) { lb = v; key = ((uint32_t)i << 12) | (uint32_t)j; cnt = 1; }
-                else if (v == lb) ++cnt;
-            }
+            if (!((elig >> k) & 1u)) continue;
+            const int h = trace_h(__ldcg(tab + cell_offset<K>(r, j0 + k, S)));      // written by this lane in this kernel: never the read-only path
+            if (r == r0) H[k] = Ms - ((Ms - h) & 63); else H[k] += trace_diff(h, ph[k]);
+            ph[k] = h;
+            if (H[k] == Ms) { if (kfirst == 0xffffffffu) kfirst = ((uint32_t)r << 12) | (uint32_t)(j0 + k); ++c; }
         }
-        tr->lb[half] = lb; tr->key[half] = key; tr->cnt[half] = cnt;
     }
-    // from now on only cells that at least tie with this lane's best matter: (H + open) + T2 has bit 15 set <=> H >= threshold
-    const int a = max(tr->thr[0], tr->lb[0]), b = max(tr->thr[1], tr->lb[1]);
-    return (uint32_t)(0x8000 + o4 - a) | ((uint32_t)(0x8000 + o4 - b) << 16);
+    key = kfirst; cnt = c;
 }
 
 // k_dp_fill<K, MM, OPEN>: MM / OPEN = mismatch and gap-open score as compile-time constants (0 = take them from P at run time).
@@ -118,8 +158,8 @@ __device__ __noinline__ uint32_t dp_track_cells(DpTrack *tr, const uint32_t *ho,
 // take the exact (scalar, per-lane) bookkeeping path.  The threshold starts at max(cutoff, LB) where LB is the score of the ungapped
 // path along the task's hinted diagonal -- a true lower bound of the best score, so no cell that can be the answer or tie with
 // it is skipped -- and follows the lane's own best.
-template <int K, int MM, int OPEN>
-__global__ void __launch_bounds__(128)
+template <int K, int MM, int OPEN, bool MASKED>
+__global__ void __launch_bounds__(128, K <= 5 ? MP_FILL_MINBLOCKS : K <= 8 ? 5 : 4)
 k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLens, uint32_t refStride,
           const uint8_t *__restrict__ readSeq, const uint32_t *__restrict__ readLens, uint32_t readStride,
           const int32_t *__restrict__ cutoffs, const int16_t *__restrict__ hints, uint32_t taskBase, uint32_t nTasks, MpDpParams P,
@@ -176,6 +216,10 @@ k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLe
         const uint32_t a = j <= LA ? ra[j - 1] & 3u : 0u, b = j <= LB ? rbp[j - 1] & 3u : 0u;
         basesA |= a << (2 * k); basesB |= b << (2 * k);
         sel[k] = a | ((8u | a) << 4) | ((4u + b) << 8) | ((12u + b) << 12);
+        // !MASKED (see the tracker below): a column beyond the read takes addend 0 -- a substitution score of `open`, below any real one
+        // -- by selecting the sign replica (0x00) of a table byte, so that its cells stay below the real cells they derive from
+        if (!MASKED && j > LA) sel[k] = (sel[k] & ~0xFu) | 8u;
+        if (!MASKED && j > LB) sel[k] = (sel[k] & ~0xF00u) | 0xC00u;
         const uint32_t h0 = pack2(4 * h0_value(j, clipLt, open) + DP_BIAS);
         HO[k] = h0 - O4;
         Dp[k] = DP_NEG2;
@@ -225,25 +269,38 @@ k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLe
             if (live) { if (half) thrB = thr; else thrA = thr; }
         }
     }
-    // lane-level answer bookkeeping (dp_track_cells): thr - 1 = nothing yet
+    // lane-level answer bookkeeping (dp_track_row): thr - 1 = nothing yet.  elig: which of the lane's columns may hold the answer
+    // (L - clipRt <= j <= L, CPU_DP.cpp:545-590); a half without eligible columns (or without a task) gets a threshold nothing reaches.
     DpTrack tr;
-    tr.lb[0] = thrA - 1; tr.lb[1] = thrB - 1; tr.key[0] = tr.key[1] = 0xffffffffu; tr.cnt[0] = tr.cnt[1] = 0;
-    tr.thr[0] = thrA; tr.thr[1] = thrB; tr.L[0] = LA; tr.L[1] = LB; tr.N[0] = NA; tr.N[1] = NB;
-    tr.minCol[0] = max(LA - P.clipRt, 1); tr.minCol[1] = max(LB - P.clipRt, 1);
-    // (H + open) + T2 has bit 15 set <=> H >= threshold
+    uint32_t eligA = 0, eligB = 0;
+    {
+        const int minColA = max(LA - P.clipRt, 1), minColB = max(LB - P.clipRt, 1);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int j = j0 + k;
+            eligA |= (uint32_t)(j >= minColA && j <= LA) << k;
+            eligB |= (uint32_t)(j >= minColB && j <= LB) << k;
+        }
+    }
+    tr.lb[0] = thrA - 1; tr.lb[1] = thrB - 1; tr.rfirst[0] = tr.rfirst[1] = 0; tr.rlast[0] = tr.rlast[1] = 0;
+    tr.thr[0] = thrA; tr.thr[1] = thrB;           // read back after the loop: nothing the loop does not need stays in a register
+    tr.thrT[0] = eligA ? thrA : 0x7FF0; tr.thrT[1] = eligB ? thrB : 0x7FF0; tr.N[0] = NA; tr.N[1] = NB; tr.elig[0] = eligA; tr.elig[1] = eligB;
     const int lastLane = maxL > 0 ? (maxL - 1) / K : 0;
     const int steps = maxN + lastLane;
     const bool mine = lane <= lastLane;                         // lanes that own read columns (every lane runs the loop: full-mask shuffles)
     // lanes without read columns run the steady groups like everyone else (straight-line code, full 128-byte trace lines) on
-    // padding cells; their T2 = 0 never triggers
-    uint32_t T2 = mine ? (uint32_t)(0x8000 + (int)O4v - thrA) | ((uint32_t)(0x8000 + (int)O4v - thrB) << 16) : 0u;
+    // padding cells; nothing there reaches their threshold.  (H + open) + T2 has bit 15 set <=> H >= threshold
+    uint32_t T2 = dp_track_t2(&tr, (int)O4v);
     uint32_t prevLeftO = pack2(4 * h0_value(j0 - 1, clipLt, open) + DP_BIAS) - O4;            // H[i-1][j0-1] in open form
     const uint2 *rowP = refS - lane;                            // row of step t = 1 is 1 - lane: table index t - 1 - lane
     constexpr int WORDS = K / 4, REM = K % 4, WB = WORDS * 256;
     uint8_t *tabP = tables + (size_t)lA * tableStride;          // pair table: 2 * tableStride bytes
     uint8_t *pw = tabP + WB + lane * 4;                         // word block of step 1
     uint8_t *pr = tabP + (size_t)S * WB + lane * 4;             // remainder group 0
-    uint32_t sendH = 0, sendI = 0;
+    // what a lane hands to its right neighbour before it has computed anything: the column-0 boundary (H = 0, no I).  Lanes beyond the
+    // read never get real input; with this start their padding cells stay ordinary small scores (never near 0x8000, where the
+    // threshold test of a half without eligible columns would fire)
+    uint32_t sendH = DP_BIAS2 - O4, sendI = DP_NEG2;
     uint32_t accA[REM ? REM : 1] = {0}, accB[REM ? REM : 1] = {0};
     uint32_t hist[WORDS][3][4];                                 // codes of the last steps, slot = step % 4 (see cell_offset)
 #pragma unroll
@@ -295,11 +352,13 @@ k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLe
                 if (K % 2 == 0) cm = __vmaxu2(cm, HO[K - 1]);
                 const uint32_t q = cm + T2;
                 if (q & 0x80008000u) {
-                    uint32_t ho[K], z;                                             // a copy: HO itself must stay in registers, and the
-                    asm volatile("mov.u32 %0, 0;" : "=r"(z));                      // copy must not be hoisted out of this rare branch
+                    if (MASKED) {
+                        uint32_t ho[K], z;                                         // a copy: HO itself must stay in registers, and the
+                        asm volatile("mov.u32 %0, 0;" : "=r"(z));                  // copy must not be hoisted out of this rare branch
 #pragma unroll
-                    for (int k = 0; k < K; ++k) ho[k] = HO[k] + z;
-                    T2 = dp_track_cells<K>(&tr, ho, q, i, j0, (int)O4v);
+                        for (int k = 0; k < K; ++k) ho[k] = HO[k] + z;
+                        T2 = dp_track_row_masked<K>(&tr, ho, q, i, (int)O4v);
+                    } else T2 = dp_track_row(&tr, cm, q, i, (int)O4v);
                 }
             }
 #pragma unroll
@@ -367,19 +426,28 @@ k_dp_fill(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLe
         }
     }
     __syncwarp();
-    // ---- winner per task: best value over the lanes, then smallest (row, col); ties summed ----
+    // ---- winner per task: best value over the lanes; the lanes that hold it read the position of its first cell (row-major) and the
+    //      number of cells that tie back from their own trace bytes ----
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         const int lb = tr.lb[half], thr = tr.thr[half];
         int gbest = lb;
 #pragma unroll
         for (int dlt = 16; dlt; dlt >>= 1) gbest = max(gbest, __shfl_xor_sync(0xffffffffu, gbest, dlt));
-        uint32_t key = lb == gbest ? tr.key[half] : 0xffffffffu, c2 = lb == gbest ? tr.cnt[half] : 0u;
+        uint32_t key = 0xffffffffu, c2 = 0u;
+        if (lb == gbest && gbest >= thr && tr.elig[half])
+            dp_resolve_lane<K>(tables + (size_t)(blockIdx.x * 8 + (threadIdx.x >> 5) * 2) * tableStride + half * 128, S, (int)(threadIdx.x & 31) * K + 1, tr.elig[half], tr.rfirst[half], tr.rlast[half], (gbest - DP_BIAS) >> 2, key, c2);
+#ifdef MP_DEBUG_TRACK
+        if (pairId == 0 && half == 0) printf("dbg lane %d lb %d gbest %d thr %d thrT %d elig %x r0 %d r1 %d T2 %x N %d L %d partial %d key %x\n", lane, lb, gbest, thr, tr.thrT[0], tr.elig[0], tr.rfirst[0], tr.rlast[0], T2, NA, LA, (int)partial, key);
+        if (lb == gbest && gbest >= thr && tr.elig[half] && (key == 0xffffffffu || tr.rfirst[half] < 1 || tr.rlast[half] > (half ? NB : NA)))
+            printf("track: pair %u half %d lane %d gbest %d thr %d lb %d r0 %d r1 %d N %d L %d elig %x key %x cnt %u partial %d\n", pairId, half, lane, gbest, thr, lb,
+                   tr.rfirst[half], tr.rlast[half], half ? NB : NA, half ? LB : LA, tr.elig[half], key, c2, (int)partial);
+#endif
 #pragma unroll
         for (int dlt = 16; dlt; dlt >>= 1) { key = min(key, __shfl_xor_sync(0xffffffffu, key, dlt)); c2 += __shfl_xor_sync(0xffffffffu, c2, dlt); }
         if (lane == 0 && (half == 0 || hasB)) {
             FillOut f; f.score = (gbest - DP_BIAS) >> 2; f.row = key >> 12; f.col = key & 0xfffu; f.cnt = c2;
-            if (gbest < thr || !(half ? okB : okA)) { f.score = 0; f.row = 0; f.col = 0; f.cnt = 0; }
+            if (gbest < thr || !(half ? okB : okA) || key == 0xffffffffu) { f.score = 0; f.row = 0; f.col = 0; f.cnt = 0; }
             fill[half == 0 ? tA : tB] = f;
         }
     }
@@ -650,6 +718,9 @@ static int launch_dp(mp_context *ctx, const uint8_t *dRef, const uint32_t *dRefL
     const size_t smem = (size_t)4 * S * sizeof(uint2);          // one 8-byte substitution table per reference row and warp
     // exact-occurrence shortcut (k_dp_exact): MP_DP_EXACT=0 sends every task through the DP kernels
     static const bool useExact = !(getenv("MP_DP_EXACT") && getenv("MP_DP_EXACT")[0] == '0');
+    // the lean tracker of k_dp_fill takes a lane's row maximum over all of its columns: legal when no column left of the eligible range
+    // (j < L - clipRt) can reach a cutoff, i.e. L - clipRt - 1 < 30 <= cutoff for every read length of the batch (definitions.h:166-167)
+    const bool rowMaxOk = (int)maxReadLen - P.clipRt - 1 < 30;
     const uint32_t perMax = std::min<uint32_t>(per, nTasks);
     if (useExact && (ctx->dExFlag.reserve(((size_t)perMax + 1) * 4) || ctx->dExPos.reserve(((size_t)perMax + 1) * 4) ||
                      ctx->dExIdx.reserve(((size_t)perMax + 1) * 4) || ctx->dCounters.reserve(16 * 8))) return MP_ERR_CUDA;
@@ -672,13 +743,17 @@ static int launch_dp(mp_context *ctx, const uint8_t *dRef, const uint32_t *dRefL
 #define LAUNCH(KK) do { \
         if (useExact) LAUNCH_EXACT(KK); \
         cudaEvent_t stop_ = ctx->ev_begin(0); \
-        if (P.mismatch == -2 && P.open == -3) { \
-            if (smem > 48 * 1024) MP_CUDA(cudaFuncSetAttribute(k_dp_fill<KK, -2, -3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            (++g_mp_launches), k_dp_fill<KK, -2, -3><<<gridF, block, smem, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, dHints, \
+        if (P.mismatch == -2 && P.open == -3 && rowMaxOk) { \
+            if (smem > 48 * 1024) MP_CUDA(cudaFuncSetAttribute(k_dp_fill<KK, -2, -3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            (++g_mp_launches), k_dp_fill<KK, -2, -3, false><<<gridF, block, smem, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, dHints, \
+                base, n, P, tab, tableStride, S, fill, active, nActive, 1u); \
+        } else if (P.mismatch == -2 && P.open == -3) { \
+            if (smem > 48 * 1024) MP_CUDA(cudaFuncSetAttribute(k_dp_fill<KK, -2, -3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            (++g_mp_launches), k_dp_fill<KK, -2, -3, true><<<gridF, block, smem, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, dHints, \
                 base, n, P, tab, tableStride, S, fill, active, nActive, 1u); \
         } else { \
-            if (smem > 48 * 1024) MP_CUDA(cudaFuncSetAttribute(k_dp_fill<KK, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            (++g_mp_launches), k_dp_fill<KK, 0, 0><<<gridF, block, smem, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, dHints, \
+            if (smem > 48 * 1024) MP_CUDA(cudaFuncSetAttribute(k_dp_fill<KK, 0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            (++g_mp_launches), k_dp_fill<KK, 0, 0, true><<<gridF, block, smem, ctx->stream>>>(dRef, dRefLens, refStride, dRead, dReadLens, readStride, dCutoffs, dHints, \
                 base, n, P, tab, tableStride, S, fill, active, nActive, 1u); \
         } \
         ctx->ev_end(stop_); stop_ = ctx->ev_begin(1); \
