@@ -595,6 +595,9 @@ static int ensure_bloom(mp_context *ctx, int seedMinLength)
     int K = seedMinLength - (stride - 1); if (K > 32) K = 32;
     if (ctx->bloomK == K && ctx->bloomStride == stride && ctx->bloomSeedMin == seedMinLength && ctx->bloomFor == (const void *)ctx->ix.blocks) return 0;
     if (n < (uint64_t)K) { ctx->bloomK = 0; return 0; }
+    // a K-mer that occurs in the text more than once on average cannot be ruled out by a presence filter (60 Gbp NT with
+    // seedMinLength 17: 4^17 < n): no filter then, its probes would only add gathers (and tens of GB of HBM)
+    if (K < 32 && (double)n > (double)(1ull << (2 * K))) { ctx->bloomK = 0; return 0; }
     uint64_t nWords = n / 4 + 1024;                      // 16 bits per text position ...
     {                                                    // ... unless that would take more than a third of what is free (60 Gbp texts)
         size_t freeB = 0, totalB = 0; cudaMemGetInfo(&freeB, &totalB);
@@ -674,7 +677,9 @@ int mps_seed_pairs(mp_context *ctx, const mp_align_params *AP)
     MP_CUDA(cudaGetLastError());
     MP_CUDA(cudaEventRecord(ctx->ev[2], st));
     if (ctx->dHits2.reserve(hitSlots * sizeof(MpHit))) return MP_ERR_CUDA;
-    if (ctx->nHits > (uint64_t)nReads * 8)
+    const char *eG = getenv("MP_HIT_SORT_G");                          // tests: 4 or 32 lanes per read whatever the hit density
+    const int forceG = eG ? atoi(eG) : 0;
+    if (forceG ? forceG == 32 : ctx->nHits > (uint64_t)nReads * 8)
         (++g_mp_launches), k_hit_sort<32><<<nSM * 16, 128, 0, st>>>(ctx->dHitStart.as<uint32_t>(), ctx->dHits.as<MpHit>(), nReads, ctx->dHits2.as<MpHit>());
     else
         (++g_mp_launches), k_hit_sort<4><<<nSM * 16, 128, 0, st>>>(ctx->dHitStart.as<uint32_t>(), ctx->dHits.as<MpHit>(), nReads, ctx->dHits2.as<MpHit>());

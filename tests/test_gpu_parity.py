@@ -293,6 +293,30 @@ def test_gpu_sampled_sa_path(workdir, small_ref, monkeypatch, env, val, walks):
         c.close()
 
 
+@pytest.mark.parametrize("lanes", ["4", "32"])
+def test_gpu_hit_sort_group_sizes(workdir, small_ref, lanes, monkeypatch):
+    """k_hit_sort orders a read's hits with 4 lanes per read on human-like data and with 32 on NT-like data (dozens of hits per
+    read); forced either way here, both must give the oracle's SeedPos arrays."""
+    import megapath_b200 as mp
+    monkeypatch.setenv("MP_HIT_SORT_G", lanes)
+    c = mp.Context(0)
+    try:
+        c.index_load(small_ref["prefix"])
+        ix = po.Index(small_ref["prefix"])
+        for name, rlen, lopt, kw in READ_SETS[:4]:
+            fq1, fq2 = make_reads(workdir, small_ref, "hs_" + name, 700, rlen, seed=55, **kw)
+            reads, lens = load_pairs(fq1, fq2, trunc=lopt - 1)
+            rp, mpos = ix.seed_pairs(reads, lens, po.mmp_params())
+            q, wpq = mp.pack_queries(reads, lens, lopt)
+            c.batch_upload(q, lens, wpq)
+            P = mp.default_params(insert_low=max(1, int(lens.max())), insert_high=750, max_read_length=lopt)
+            c.seed_pairs(P)
+            grp, gmp = c.download_seedpos()
+            assert grp.tobytes() == rp.tobytes() and gmp.tobytes() == mpos.tobytes(), (lanes, name)
+    finally:
+        c.close()
+
+
 def test_gpu_abi_rejects_overlong_reads(ctx):
     """A read that does not fit its 2-bit row, or is not shorter than maxReadLength, is refused at the C-ABI instead of corrupting
     neighbouring DP tasks (the reference truncates at parse time, QueryParser.cpp:188)."""
