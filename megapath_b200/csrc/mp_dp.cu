@@ -675,13 +675,43 @@ __global__ void k_extract(MpIndexView ix, const uint32_t *__restrict__ reads, ui
     MpDpTask tk = tasks[task];
     // a task that does not fit its rows is dropped, never written past them (callers size the strides from -L / -u)
     if (!tk.valid || tk.refLen > refStride || tk.readLen > readStride) { tk.refLen = 0; tk.valid = 0; }
-    for (uint32_t a = threadIdx.x; a < tk.refLen; a += blockDim.x)
-        refSeq[(size_t)task * refStride + a] = (uint8_t)mp_text_base(ix, tk.refStart + a);
     const uint32_t *rd = reads + (size_t)tk.readID * wpq;
-    for (uint32_t a = threadIdx.x; tk.valid && a < tk.readLen; a += blockDim.x) {
-        uint32_t p = tk.strand == 1 ? a : tk.readLen - 1 - a;
-        uint32_t b = (rd[p >> 4] >> ((p & 15) << 1)) & 3;
-        readSeq[(size_t)task * readStride + a] = (uint8_t)(tk.strand == 1 ? b : 3 - b);
+    if (((refStride | readStride) & 3u) == 0) {
+        // four bases per thread and trip: one packed byte's worth of text (or of the read) becomes one 32-bit store.  Rows are
+        // multiples of four bytes long, so the last word of a row may carry up to three bases nobody reads.
+        uint32_t *fo = (uint32_t *)(refSeq + (size_t)task * refStride), *ro = (uint32_t *)(readSeq + (size_t)task * readStride);
+        for (uint32_t a = threadIdx.x * 4; a < tk.refLen; a += blockDim.x * 4) {
+            const uint64_t p = tk.refStart + a;
+            const uint32_t x = ((uint32_t)__ldg(ix.pac + (p >> 2)) << 8) | __ldg(ix.pac + (p >> 2) + 1);      // first base in the top bits
+            const uint32_t v = (x >> (8 - 2 * (uint32_t)(p & 3))) & 0xFFu;
+            fo[a >> 2] = (v >> 6) | (((v >> 4) & 3u) << 8) | (((v >> 2) & 3u) << 16) | ((v & 3u) << 24);
+        }
+        const uint32_t L = tk.valid ? tk.readLen : 0;
+        for (uint32_t a = threadIdx.x * 4; a < L; a += blockDim.x * 4) {
+            uint32_t w;
+            if (tk.strand == 1) {
+                const uint32_t v = (rd[a >> 4] >> ((a & 15) << 1)) & 0xFFu;                                     // bases a .. a+3, first in the low bits
+                w = (v & 3u) | (((v >> 2) & 3u) << 8) | (((v >> 4) & 3u) << 16) | ((v >> 6) << 24);
+            } else {
+                // reverse complement: output a+k = 3 - read[L-1-a-k]; the four source bases start at s = L-4-a (may reach below 0)
+                const int s = (int)L - 4 - (int)a;
+                const int s0 = s < 0 ? 0 : s;
+                const uint32_t lo = rd[s0 >> 4], hi = rd[(s0 >> 4) + ((s0 & 15) > 12 ? 1 : 0)];
+                uint32_t v = (__funnelshift_r(lo, hi, (s0 & 15) << 1)) & 0xFFu;                                 // read[s0 .. s0+3], first in the low bits
+                if (s < 0) v <<= (uint32_t)(-s) * 2;                                                            // keep read[L-1-a] in the top pair
+                v = ~v & 0xFFu;
+                w = (v >> 6) | (((v >> 4) & 3u) << 8) | (((v >> 2) & 3u) << 16) | ((v & 3u) << 24);
+            }
+            ro[a >> 2] = w;
+        }
+    } else {
+        for (uint32_t a = threadIdx.x; a < tk.refLen; a += blockDim.x)
+            refSeq[(size_t)task * refStride + a] = (uint8_t)mp_text_base(ix, tk.refStart + a);
+        for (uint32_t a = threadIdx.x; tk.valid && a < tk.readLen; a += blockDim.x) {
+            uint32_t p = tk.strand == 1 ? a : tk.readLen - 1 - a;
+            uint32_t b = (rd[p >> 4] >> ((p & 15) << 1)) & 3;
+            readSeq[(size_t)task * readStride + a] = (uint8_t)(tk.strand == 1 ? b : 3 - b);
+        }
     }
     if (threadIdx.x == 0) { refLens[task] = tk.refLen; readLens[task] = tk.valid ? tk.readLen : 0; cutoffs[task] = tk.cutoff; hints[task] = tk.valid ? tk.diag : (int16_t)-1; }
 }

@@ -42,16 +42,21 @@ __global__ void k_deinterleave(const uint32_t *__restrict__ il, uint32_t *__rest
     if (r < nReads) out[r * wpq + j] = il[t];
 }
 
-__device__ __forceinline__ uint32_t read_base(const uint32_t *__restrict__ rd, int p)
+// A lane's read lives in shared memory while the lane works on it (staged once when the lane takes the strand): word w of the
+// read at rd[w * MMP_RS] -- consecutive threads hold consecutive banks -- followed by two zero words, so that the three-word window
+// fetches below never leave the lane's column.  Every trip of k_mmp re-reads a few of these words; as plain global loads they were two
+// thirds of the kernel's L1 traffic.
+#define MMP_RS 128
+__device__ __forceinline__ uint32_t read_base(const uint32_t *rd, int p)
 {
-    return (__ldg(rd + (p >> 4)) >> ((p & 15) << 1)) & 3;
+    return (rd[(p >> 4) * MMP_RS] >> ((p & 15) << 1)) & 3;
 }
 
 // 13-mer key at scan position i (DV-DPfunctions.cpp:2233-2239, 2326-2332): q[i+k] at bits 2k
-__device__ __forceinline__ uint32_t lkt_key(const uint32_t *__restrict__ rd, int len, int i, int strand)
+__device__ __forceinline__ uint32_t lkt_key(const uint32_t *rd, int len, int i, int strand)
 {
     int p0 = strand ? i : len - 13 - i;                       // lowest read position of the 13-mer
-    uint32_t w0 = __ldg(rd + (p0 >> 4)), w1 = __ldg(rd + (p0 >> 4) + 1);
+    uint32_t w0 = rd[(p0 >> 4) * MMP_RS], w1 = rd[((p0 >> 4) + 1) * MMP_RS];
     uint32_t x = __funnelshift_r(w0, w1, (p0 & 15) << 1);      // base p0 in the low bits
     if (strand) return (~x) & 0x3FFFFFFu;                      // complemented, same order
     uint32_t t = __brev(x);                                    // reverse the order of the 2-bit groups
@@ -78,16 +83,16 @@ __device__ __forceinline__ void bloom_slot(uint64_t key, uint64_t nWords, uint64
     mask = (1ull << (h & 63)) | (1ull << ((h >> 6) & 63));
 }
 // 2K bits of a 2-bit, LSB-first packed read starting at base `pos` (K <= 32)
-__device__ __forceinline__ uint64_t read_window(const uint32_t *__restrict__ rd, int pos, int K)
+__device__ __forceinline__ uint64_t read_window(const uint32_t *rd, int pos, int K)
 {
     const int w = pos >> 4, sh = (pos & 15) << 1;
-    uint32_t w0 = __ldg(rd + w), w1 = __ldg(rd + w + 1), w2 = __ldg(rd + w + 2);
+    uint32_t w0 = rd[w * MMP_RS], w1 = rd[(w + 1) * MMP_RS], w2 = rd[(w + 2) * MMP_RS];
     uint64_t v = (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
     return K == 32 ? v : v & ((1ull << (2 * K)) - 1);
 }
 // key of the K-mer the backward search would have matched after K steps from scan position i
 // (text order, first base in the most significant 2-bit group)
-__device__ __forceinline__ uint64_t scan_kmer(const uint32_t *__restrict__ rd, int len, int i, int strand, int K)
+__device__ __forceinline__ uint64_t scan_kmer(const uint32_t *rd, int len, int i, int strand, int K)
 {
     if (strand) {                   // pattern = revcomp(read[i .. i+K-1]): complement, base i least significant
         uint64_t v = read_window(rd, i, K);
@@ -189,6 +194,9 @@ __device__ __forceinline__ uint64_t group_reverse(uint64_t v)       // reverse t
 // fetches chunks of MMP_CHUNK strands with one atomic), so no lane waits for the slowest strand of its warp: the kernel is bound by
 // the latency of dependent gathers, and what counts is how many lanes have one in flight.
 #define MMP_CHUNK 128u
+#ifndef MMP_PROBES
+#define MMP_PROBES 8       /* filter probes a lane keeps in flight per trip */
+#endif
 __global__ void __launch_bounds__(128, 8)
 k_mmp(MpIndexView ix, const uint32_t *__restrict__ reads, const uint32_t *__restrict__ lens, uint32_t wpq,
       uint32_t nStrands, MmpDev P, MpSeed *__restrict__ seeds, uint32_t *__restrict__ stubs,
@@ -208,7 +216,8 @@ k_mmp(MpIndexView ix, const uint32_t *__restrict__ reads, const uint32_t *__rest
     bool exhausted = false;
     uint32_t read = 0, strand = 0, skipped = 0;
     int len = 0, i = 0, seed_len = 0, last_seed_len = 0;
-    const uint32_t *rd = reads;
+    extern __shared__ uint32_t shReads[];                            // [wpq + 2][blockDim.x]
+    uint32_t *rd = shReads + threadIdx.x;
     uint64_t l = 0, r = n, last_l = 0, last_r = n, p = 0;
     int state = ST_DONE;
     for (;;) {
@@ -229,7 +238,10 @@ k_mmp(MpIndexView ix, const uint32_t *__restrict__ reads, const uint32_t *__rest
                     const uint32_t w = chunkNext + rank;
                     const uint32_t group = w >= nReadsK;
                     read = group ? w - nReadsK : w; strand = (read & 1u) ^ group;
-                    len = (int)lens[read]; rd = reads + (size_t)read * wpq;
+                    len = (int)lens[read];
+                    const uint32_t *src = reads + (size_t)read * wpq;
+                    for (uint32_t k = 0; k < wpq; ++k) rd[k * MMP_RS] = __ldg(src + k);
+                    rd[wpq * MMP_RS] = 0; rd[(wpq + 1) * MMP_RS] = 0;
                     i = 0; seed_len = 0; last_seed_len = 0; l = 0; r = n; last_l = 0; last_r = n; p = 0;
                     state = ST_SCAN;
                 }
@@ -242,26 +254,28 @@ k_mmp(MpIndexView ix, const uint32_t *__restrict__ reads, const uint32_t *__rest
         if (state == ST_SCAN) {                                   // seed_len == 0: look for the next start worth searching
             if (len - i < P.seedMinLength) { state = ST_DONE; continue; }
             bool go = true;
-            if (bloom) {                                          // 4 probes in flight
+            if (bloom) {                                          // MMP_PROBES probes in flight
                 // A match of seedMinLength bases from start i0 covers the bloomK-mer at every p in [i0, i0 + bloomStride - 1]
                 // (bloomK = seedMinLength - (bloomStride - 1)), so the K-mer at p = i + bloomStride - 1 decides the bloomStride starts
                 // i .. p at once, the next probe the bloomStride starts after them, and so on.  (Anchoring the probes at the
                 // current start rather than on a fixed grid matters after a seed that ended on a mismatch: the scan resumes
-                // seedMinLength - 1 bases before it, and the first probe already spans the mismatch.)
+                // seedMinLength - 1 bases before it, and the first probe already spans the mismatch.)  Only the filter words are
+                // kept while the loads are in flight; the two-bit masks are hashed again when they are back.
                 const int lastStart = len - P.seedMinLength;
                 int m = 0;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) if (i + j * bloomStride <= lastStart) m = j + 1;
-                unsigned long long wv[4]; uint64_t mk[4];
+                for (int j = 0; j < MMP_PROBES; ++j) if (i + j * bloomStride <= lastStart) m = j + 1;
+                unsigned long long wv[MMP_PROBES];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    wv[j] = ~0ull; mk[j] = 0;
-                    if (j < m) { uint64_t wi; bloom_slot(scan_kmer(rd, len, i + j * bloomStride + bloomStride - 1, strand, bloomK), bloomWords, wi, mk[j]); wv[j] = __ldg(bloom + wi); }
+                for (int j = 0; j < MMP_PROBES; ++j) {
+                    wv[j] = ~0ull;
+                    if (j < m) { uint64_t wi, mk; bloom_slot(scan_kmer(rd, len, i + j * bloomStride + bloomStride - 1, strand, bloomK), bloomWords, wi, mk); wv[j] = __ldg(bloom + wi); }
                 }
                 nProbe += m;
                 int hit = m;
 #pragma unroll
-                for (int j = 3; j >= 0; --j) if (j < m && (wv[j] & mk[j]) == mk[j]) hit = j;
+                for (int j = MMP_PROBES - 1; j >= 0; --j)
+                    if (j < m) { uint64_t wi, mk; bloom_slot(scan_kmer(rd, len, i + j * bloomStride + bloomStride - 1, strand, bloomK), bloomWords, wi, mk); if ((wv[j] & mk) == mk) hit = j; }
                 go = hit < m;
                 i += hit * bloomStride;                           // first start the probes do not rule out (all dead: past the last probe)
             }
@@ -643,7 +657,9 @@ int mps_seed_pairs(mp_context *ctx, const mp_align_params *AP)
     if (int rc = ensure_bloom(ctx, P.seedMinLength)) return rc;
     unsigned long long hc[16];
     int dev = 0, nSM = 148, mmpBlocks = 8; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&mmpBlocks, k_mmp, 128, 0) != cudaSuccess || mmpBlocks < 1) mmpBlocks = 8;
+    const size_t mmpSmem = ((size_t)ctx->wpq + 2) * MMP_RS * 4;      // the reads the block's lanes are working on
+    if (mmpSmem > 48 * 1024) MP_CUDA(cudaFuncSetAttribute(k_mmp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mmpSmem));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&mmpBlocks, k_mmp, 128, mmpSmem) != cudaSuccess || mmpBlocks < 1) mmpBlocks = 8;
     MP_CUDA(cudaEventRecord(ctx->ev[0], st));
     for (int attempt = 0; attempt < 4; ++attempt) {
         if (ctx->capSeeds > 0xFFFFFFF0ull || ctx->capStubs > 0xFFFFFFF0ull) { mp_set_error("seed buffers exceed 32-bit indexing; use smaller batches"); return MP_ERR_CAPACITY; }
@@ -651,7 +667,7 @@ int mps_seed_pairs(mp_context *ctx, const mp_align_params *AP)
         MP_CUDA(cudaMemsetAsync(ctx->dCounters.p, 0, 16 * 8, st));
         MP_CUDA(cudaMemsetAsync(ctx->dHitsPerRead.p, 0, ((size_t)nReads + 1) * 4, st));
         // persistent warps: as many blocks as the device holds at once, every warp pulls chunks of read-strands from counters[6]
-        (++g_mp_launches), k_mmp<<<nSM * mmpBlocks, 128, 0, st>>>(ctx->ix, ctx->dReads.as<uint32_t>(), ctx->dLens.as<uint32_t>(), ctx->wpq, nStrands, P,
+        (++g_mp_launches), k_mmp<<<nSM * mmpBlocks, 128, mmpSmem, st>>>(ctx->ix, ctx->dReads.as<uint32_t>(), ctx->dLens.as<uint32_t>(), ctx->wpq, nStrands, P,
                                       ctx->dSeeds.as<MpSeed>(), ctx->dStubs.as<uint32_t>(), ctx->dCounters.as<unsigned long long>(),
                                       ctx->dHitsPerRead.as<uint32_t>(), (uint32_t)ctx->capSeeds, (uint32_t)ctx->capStubs,
                                       ctx->bloomK ? ctx->dBloom.as<unsigned long long>() : nullptr, ctx->bloomWords, ctx->bloomK, ctx->bloomStride);
