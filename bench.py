@@ -414,7 +414,8 @@ def run_our_soap4(args, prefix, fq_prefix, out_prefix, threads, sink=None):
     cmd = soap4_cmd(exe, os.path.join(ROOT, "megapath_b200", "ini", args.cfg["ini"]), prefix, fq_prefix, out_prefix, args.lopt, threads)
     t0 = time.time()
     with open(sink or (out_prefix + ".stdout.fq"), "wb") as fo:
-        p = subprocess.run(cmd, stdout=fo, stderr=subprocess.PIPE, env=dict(os.environ, MP_DRIVER_TIMING="1"))
+        p = subprocess.run(cmd, stdout=fo, stderr=subprocess.PIPE,
+                           env=dict(os.environ, MP_DRIVER_TIMING="1", **({"MP_TRACE": "2"} if os.environ.get("MP_BENCH_CLI_TRACE") else {})))
     wall = time.time() - t0
     err = p.stderr.decode(errors="replace")
     if p.returncode != 0:
@@ -770,7 +771,7 @@ def run(args, saved_stdout):
             try:
                 cli = sample_prefix(args, "cli", args.cli_pairs)
                 loop_s, wall_s, cli_err = run_our_soap4(args, prefix, cli, os.path.join(d, "ourout_cli"), ncores, sink=os.path.join(d, "ourout_cli.stdout.fq"))
-                sys.stderr.write("".join(l + "\n" for l in cli_err.splitlines() if "[timing]" in l or "Elapsed time on host" in l))
+                sys.stderr.write("".join(l + "\n" for l in cli_err.splitlines() if "[timing]" in l or "Elapsed time on host" in l or "[mp_trace]" in l))
                 out_bytes = os.path.getsize(os.path.join(d, "ourout_cli.stdout.fq"))
                 os.remove(os.path.join(d, "ourout_cli.stdout.fq"))
                 out["e2e_cli"] = {"value": args.cli_pairs / loop_s, "unit": "pairs/s", "pairs": args.cli_pairs, "loop_s": loop_s, "process_wall_s": wall_s,

@@ -530,7 +530,16 @@ extern "C" int mp_reserve(mp_context *ctx, const mp_align_params *P, uint32_t nR
     const int K = maxReadLength <= 160 ? 5 : maxReadLength <= 256 ? 8 : 10;
     const size_t tableStride = (size_t)(((int)maxDNALength + 44) & ~3) * 32 * K;
     size_t freeB = 0, totalB = 0; cudaMemGetInfo(&freeB, &totalB);
-    const size_t tableWant = std::min<size_t>((size_t)(CH >= (1u << 15) ? (1u << 18) : CH + 1) * tableStride, std::min<size_t>((size_t)24 << 30, freeB / 2));
+    // stage S3 (mate rescue) aligns windows of up to insert_high + L bases: wider rows for the sequence / pattern buffers, and a
+    // traceback table per task three to four times the size of a stage-S1 one.  Sized here for both, so that the first batch with many
+    // rescue tasks does not free and re-allocate tens of GB (a cudaFree stalls every context of the GPU).
+    const uint32_t maxDNALengthR = (uint32_t)std::max(P->insert_high, 0) + inputMax + 1, rStride = (maxDNALengthR + maxReadLength + 3) & ~3u;
+    const uint32_t CH3 = (uint32_t)std::min<uint64_t>(1u << 17, (uint64_t)nReads + 1024);
+    const bool big = CH >= (1u << 15);
+    const size_t tableWant = std::min<size_t>(big ? (size_t)24 << 30 : (size_t)(CH + 1) * tableStride, std::min<size_t>((size_t)24 << 30, freeB / 2));
+    const size_t refSeqWant = std::max<size_t>((((size_t)CH * maxDNALength + 15) & ~(size_t)15) + (size_t)CH * 14 + 16,
+                                               big && !P->skipDefaultDP ? (((size_t)CH3 * maxDNALengthR + 15) & ~(size_t)15) + (size_t)CH3 * 14 + 16 : 0);
+    const size_t patWant = std::max<size_t>((size_t)CH * patStride, big && !P->skipDefaultDP ? (size_t)CH3 * rStride : 0);
     if (ctx->dReadsIl.reserve(nPad * wpq * 4) || ctx->dReads.reserve(nPad * wpq * 4 + 64) || ctx->dLens.reserve((size_t)nReads * 4) ||
         ctx->dCounters.reserve(16 * 8) || ctx->dHitsPerRead.reserve(((size_t)nReads + 1) * 4) || ctx->dHitStart.reserve(((size_t)nReads + 1) * 4) ||
         ctx->dCursor.reserve(((size_t)nReads + 1) * 4) || ctx->dNPos.reserve((size_t)nReads * 4) || ctx->dNNeg.reserve((size_t)nReads * 4) ||
@@ -540,16 +549,23 @@ extern "C" int mp_reserve(mp_context *ctx, const mp_align_params *P, uint32_t nR
         ctx->dCands.reserve((size_t)nPairs * 2 * sizeof(mp_candidate)) ||
         ctx->dLT.reserve((size_t)CH * sizeof(MpDpTask)) || ctx->dRT.reserve((size_t)CH * sizeof(MpDpTask)) ||
         ctx->dLO.reserve((size_t)CH * sizeof(MpDpOut)) || ctx->dRO.reserve((size_t)CH * sizeof(MpDpOut)) ||
-        ctx->dLP.reserve((size_t)CH * patStride) || ctx->dRP.reserve((size_t)CH * patStride) ||
+        ctx->dLP.reserve(patWant) || ctx->dRP.reserve((size_t)CH * patStride) ||
         ctx->dOk.reserve(((size_t)CH + 1) * 4) || ctx->dBytes.reserve(((size_t)CH + 1) * 8) || ctx->dIdx.reserve(((size_t)CH + 1) * 4) ||
         ctx->dOff.reserve(((size_t)CH + 1) * 4) || ctx->dRes.reserve(resCap * sizeof(mp_pair_result)) || ctx->dRes2.reserve(resCap * sizeof(mp_pair_result)) ||
-        ctx->dKeep.reserve((resCap + 1) * 4) || ctx->dKeepPos.reserve((resCap + 1) * 4) || ctx->dTotals.reserve(32) ||
+        ctx->dKeep.reserve((resCap + 1) * 4) || ctx->dKeepPos.reserve((resCap + 1) * 4) || ctx->dTotals.reserve(16 * 4) ||
         ctx->dCig.reserve(std::max<size_t>(resCap * 40, (size_t)1 << 20)) || ctx->dAligned.reserve((size_t)nPairs + 8) ||
-        ctx->dRefSeq.reserve((((size_t)CH * maxDNALength + 15) & ~(size_t)15) + (size_t)CH * 14 + 16) || ctx->dReadSeq.reserve((size_t)CH * maxReadLength) ||
+        ctx->dRefSeq.reserve(refSeqWant) || ctx->dReadSeq.reserve((size_t)CH * maxReadLength) ||
         ctx->dFill.reserve((size_t)CH * 16) || ctx->dExFlag.reserve(((size_t)CH + 1) * 4) || ctx->dExPos.reserve(((size_t)CH + 1) * 4) ||
         ctx->dExIdx.reserve(((size_t)CH + 1) * 4) || ctx->dScanTmp.reserve((size_t)1 << 20) || ctx->dS2Counts.reserve(((size_t)nReads + 1) * 4) || ctx->dS2Start.reserve(((size_t)nReads + 1) * 4) ||
         (ctx->dTable.cap < tableWant && ctx->dTable.reserve(tableWant))) return MP_ERR_CUDA;
-    if (ctx->hPairs.reserve(resCap) || ctx->hCigars.reserve(resCap * 40)) return MP_ERR_CUDA;
+    // stages S2 / S3: a guess (one pair in eight unplaced, a few tasks each); they grow on demand like everything else
+    const size_t s2 = big ? (size_t)nReads / 4 : 0;
+    if (s2 && (ctx->dS2Tasks.reserve(s2 * sizeof(MpDpTask)) || ctx->dS2Res.reserve(s2 * sizeof(mp_single_result)) ||
+               ctx->dRsSlotTasks.reserve(s2 * sizeof(MpDpTask)) || ctx->dRsSlotInfo.reserve(s2 * 8) || ctx->dRsFlag.reserve((s2 + 1) * 4) ||
+               ctx->dRsPos.reserve((s2 + 1) * 4) || ctx->dRsTasks.reserve(s2 * sizeof(MpDpTask)) || ctx->dRsInfo.reserve(s2 * 8) ||
+               ctx->dRsRec.reserve(s2 * sizeof(mp_pair_result)) || ctx->dRsOut.reserve(s2 * sizeof(mp_pair_result)) ||
+               ctx->dRsKeep.reserve((s2 + 1) * 4) || ctx->dRsKeepPos.reserve((s2 + 1) * 4))) return MP_ERR_CUDA;
+    if (ctx->hPairs.reserve(resCap) || ctx->hCigars.reserve(resCap * 40) || (s2 && (ctx->hSingles.reserve(s2) || ctx->hRescued.reserve(s2 / 2)))) return MP_ERR_CUDA;
     return 0;
 }
 

@@ -43,12 +43,14 @@ for T, ctxs, sink in ((16, 3, "/dev/null"), (16, 3, os.path.join(d, "our.out")),
     t0 = time.time()
     with open(sink, "wb") as fo:
         p = subprocess.run([exe, "pair", prefix, fq1, fq2, "-o", os.path.join(d, "ouro"), "-C", ini, "-L", "151", "-T", str(T), "-u", "750", "-F", "-nc"],
-                           stdout=fo, stderr=subprocess.PIPE, timeout=900, env=dict(os.environ, MP_CONTEXTS_PER_GPU=str(ctxs), MP_DRIVER_TIMING="1"))
+                           stdout=fo, stderr=subprocess.PIPE, timeout=900, env=dict(os.environ, MP_CONTEXTS_PER_GPU=str(ctxs), MP_DRIVER_TIMING="1", **({"MP_TRACE": "2"} if os.environ.get("MP_THR_TRACE") else {})))
     wall = time.time() - t0
     assert p.returncode == 0, p.stderr.decode()[-2000:]
     lines = p.stderr.decode().splitlines()
     loop = [float(l.split(":")[1].split()[0]) for l in lines if "Overall alignment time" in l][0]
     load = [l for l in lines if "Elapsed time on host" in l]
     tim = [l for l in lines if "[timing]" in l]
+    if os.environ.get("MP_THR_TRACE"):
+        print("\n".join([l for l in lines if "mp_trace" in l or "[timing]" in l][:70]), flush=True)
     print("-T %d, %d contexts, out=%s: wall %.1f s; batch loop %.2f s = %.2f M pairs/s; reader per batch %s; last batches %s" % (
         T, ctxs, sink, wall, loop, total / loop / 1e6, [l.split(":")[1].split()[0] for l in load[-4:-1]], tim[-4:]), flush=True)
