@@ -437,6 +437,7 @@ static long parse_mapped(const SeqReader &r, ReadBatch &b, uint32_t first, uint3
 
 static uint32_t load_batch(SeqReader &r1, SeqReader &r2, ReadBatch &b, uint32_t maxReads, unsigned packThreads = 4)
 {
+    const double tSetup0 = now_s();
     size_t words = ((size_t)maxReads + 31) / 32 * 32 * b.wpq;
     // batches are recycled (see BatchPool): storage that already has the right size is only cleared, so that a long run does
     // not page-fault half a gigabyte of fresh memory per batch
@@ -451,6 +452,8 @@ static uint32_t load_batch(SeqReader &r1, SeqReader &r2, ReadBatch &b, uint32_t 
     }
     // both files memory-mapped: thread teams parse the batch's records of either file, then every thread packs whole groups of 32 reads
     if (r1.mapped && r2.mapped) {
+        static const bool ltiming = getenv("MP_LOAD_TIMING") != nullptr;
+        const double tl0 = now_s();
         const unsigned team = std::max(1u, packThreads);
         long n1 = -1, n2 = -1; size_t p1 = r1.pos, p2 = r2.pos;
         std::thread t2([&] { n2 = parse_mapped(r2, b, 1, maxReads / 2, team, &p2); });
@@ -460,11 +463,13 @@ static uint32_t load_batch(SeqReader &r1, SeqReader &r2, ReadBatch &b, uint32_t 
             if (n1 != n2) { fprintf(stderr, "Error: number of sequences of pair-end files not matched.\n"); exit(1); }
             r1.pos = p1; r2.pos = p2;
             b.nReads = 2 * (uint32_t)n1;
+            const double tl1 = now_s();
             const uint32_t nGroups = (b.nReads + 31) / 32, T = std::min<uint32_t>(2 * team, std::max(1u, nGroups / 64));
             std::vector<std::thread> th;
             for (uint32_t t = 1; t < T; ++t) th.emplace_back([&, t] { pack_reads(b, (uint32_t)((uint64_t)nGroups * t / T) * 32, std::min(b.nReads, (uint32_t)((uint64_t)nGroups * (t + 1) / T) * 32)); });
             pack_reads(b, 0, std::min(b.nReads, (uint32_t)((uint64_t)nGroups / T) * 32));
             for (std::thread &x : th) x.join();
+            if (ltiming) fprintf(stderr, "[load] setup %.3f parse %.3f pack %.3f s\n", tl0 - tSetup0, tl1 - tl0, now_s() - tl1);
             return b.nReads;
         }
         // not plain four-line FASTQ here: nothing was consumed, the sequential parsers below take the batch
