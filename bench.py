@@ -463,6 +463,26 @@ def ncu_traffic(kernel):
     return best
 
 
+def ncu_metric(kernel, metric):
+    """one metric of `kernel` from the newest committed ncu --set full summary (profiles/rNN_ncu_full_*.txt) -> (value, source) or None"""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    for name in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
+        if not (name.startswith("r") and "ncu_full" in name and name.endswith(".txt")):
+            continue
+        cur = None
+        for ln in open(os.path.join(pdir, name)):
+            if ln.startswith("== "):
+                cur = ln
+            elif cur and kernel in cur and ln.startswith(metric):
+                f = ln.split()
+                try:
+                    best = (float(f[1]), "profiles/" + name)
+                except (IndexError, ValueError):
+                    pass
+    return best
+
+
 def main():
     args = parse_args()
     # stdout carries exactly one JSON line: anything libraries print while we work (e.g. NCCL's version banner) goes to stderr
@@ -711,6 +731,10 @@ def run(args, saved_stdout):
                            "over the tasks it is given (SURVEY 8d)" % DPX_RECURRENCE,
             "frac_with_the_kernels_own_dpx_count": (gcups_fill * DPX_KERNEL / 2.0 / dpx_peak) if dpx_peak else None,
             "dpx_instr_per_cell_pair": {"recurrence": DPX_RECURRENCE, "kernel": DPX_KERNEL, "source": "static: SASS of the steady loop, profiles/r02_sass_k_dp_fill_steady_loop.txt"},
+            # what actually limits the kernel: the integer ALU pipe as a whole (DPX min/max, PRMT, LOP3 share it; 9.8 instructions per
+            # cell pair in the steady loop).  Busy fraction of that pipe from the newest committed ncu --set full capture (static, not live).
+            "alu_pipe_busy_ncu": (lambda m: {"frac": m[0] / 100.0, "source": m[1], "metric": "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"} if m else None)(
+                ncu_metric("k_dp_fill", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active")),
             # DRAM bytes (read + write) of ONE k_dp_fill launch from the newest committed ncu --set full capture
             "traffic": traffic["bytes_per_launch"] if traffic else None, "traffic_source": traffic["source"] if traffic else None,
             "ms_per_step": acc["ms_fill"] / steps,
