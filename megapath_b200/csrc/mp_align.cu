@@ -71,33 +71,31 @@ __global__ void k_right_tasks(const mp_candidate *__restrict__ cands, uint32_t n
     account_work(t.valid ? (unsigned long long)t.refLen * t.readLen : 0ull, t.valid ? 1ull : 0ull, counters);
 }
 
-struct PairWork { uint32_t ok; uint32_t cigLen[2]; };
-
-// A leg whose score equals its read length matched every base: its pattern is readLen x 'M' and its CIGAR "<readLen>M"
-// (the one exception, an alignment that starts in row 0, carries three more pattern bytes and takes the general path).
-__device__ __forceinline__ bool all_match_leg(const MpDpTask &t, const MpDpOut &o) { return o.score == (int)t.readLen && o.patLen == t.readLen && t.readLen > 0; }
-__device__ __forceinline__ CigStats all_match_cigar(uint32_t readLen, char *out)
+// The special CIGAR of a leg and the encoder's statistics.  The traceback (k_dp_tb) and the exact-occurrence test (k_dp_exact) build
+// both while they emit the pattern and leave the text at the end of the task's pattern row; only when pattern and text would not both
+// fit the row (hundreds of one-base runs) is the text encoded here from the pattern.
+__device__ __forceinline__ CigStats leg_stats(const MpDpOut &o)
 {
-    CigStats st; st.nI = st.nD = st.nS = st.gapPenalty = 0; st.textLen = ndigits((int)readLen) + 1;
-    if (out) { int v = (int)readLen; out[st.textLen - 1] = 'M'; for (int d = st.textLen - 2; d >= 0; --d) { out[d] = (char)('0' + v % 10); v /= 10; } }
+    CigStats st; st.nI = o.nI; st.nD = o.nD; st.nS = o.nS; st.gapPenalty = o.gapPenalty; st.textLen = o.cigLen;
     return st;
+}
+__device__ __forceinline__ void leg_text(const MpDpOut &o, const uint8_t *pat, uint32_t patStride, int open, int ext, char *out)
+{
+    if (o.cigStored) { const uint8_t *src = pat + patStride - o.cigLen; for (int k = 0; k < (int)o.cigLen; ++k) out[k] = (char)src[k]; }
+    else cigar_encode(pat, open, ext, out, o.cigLen);
 }
 
 __global__ void k_assemble_measure(uint32_t n, const MpDpTask *__restrict__ lt, const MpDpOut *__restrict__ lo,
                                    const MpDpTask *__restrict__ rt, const MpDpOut *__restrict__ ro,
-                                   const uint8_t *__restrict__ lpat, const uint8_t *__restrict__ rpat, uint32_t patStride,
-                                   int open, int ext, uint32_t *__restrict__ okFlag, uint32_t *__restrict__ cigBytes,
-                                   uint32_t *__restrict__ leftLen)
+                                   uint32_t *__restrict__ okFlag, uint32_t *__restrict__ cigBytes, uint32_t *__restrict__ leftLen)
 {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     bool ok = lo[c].score >= lt[c].cutoff && rt[c].valid && ro[c].score >= rt[c].cutoff;
     uint32_t bytes = 0;
     if (ok) {
-        CigStats a = all_match_leg(lt[c], lo[c]) ? all_match_cigar(lt[c].readLen, nullptr) : cigar_encode(lpat + (size_t)c * patStride, open, ext, nullptr, 0);
-        CigStats b = all_match_leg(rt[c], ro[c]) ? all_match_cigar(rt[c].readLen, nullptr) : cigar_encode(rpat + (size_t)c * patStride, open, ext, nullptr, 0);
-        bytes = a.textLen + 1 + b.textLen + 1;
-        leftLen[c] = a.textLen;                       // the write pass encodes each leg once, backwards from its known length
+        bytes = (uint32_t)lo[c].cigLen + 1 + ro[c].cigLen + 1;
+        leftLen[c] = lo[c].cigLen;
     }
     okFlag[c] = ok; cigBytes[c] = bytes;
 }
@@ -124,9 +122,9 @@ __global__ void k_assemble_write(uint32_t n, const mp_candidate *__restrict__ ca
     int editdist[2], DIS[2]; uint32_t cigPos[2];
     uint32_t off = cigBase + cigOff[c];
     const int lengths_i = rt[c].readLen;                // batch->lengths[i] was overwritten by packRight
-    const int textLen[2] = { (int)leftLen[c], (int)(cigOff[c + 1] - cigOff[c]) - (int)leftLen[c] - 2 };
     for (int s = 0; s < 2; ++s) {
-        CigStats m = all_match_leg(*tk[s], *ou[s]) ? all_match_cigar(tk[s]->readLen, cig + off) : cigar_encode(pat[s], A.open, A.ext, cig + off, textLen[s]);
+        const CigStats m = leg_stats(*ou[s]);
+        leg_text(*ou[s], pat[s], patStride, A.open, A.ext, cig + off);
         cig[off + m.textLen] = 0;
         cigPos[s] = off;
         off += m.textLen + 1;
@@ -288,7 +286,6 @@ static int deep_dp(mp_context *ctx, const mp_align_params *P, mp_results *out, u
             MP_CUDA(cudaMemsetAsync(dOk.p, 0, ((size_t)n + 1) * 4, st));
             MP_CUDA(cudaMemsetAsync(dBytes.p, 0, ((size_t)n + 1) * 4, st));
             (++g_mp_launches), k_assemble_measure<<<g, 128, 0, st>>>(n, dLT.as<MpDpTask>(), dLO.as<MpDpOut>(), dRT.as<MpDpTask>(), dRO.as<MpDpOut>(),
-                                                  dLP.as<uint8_t>(), dRP.as<uint8_t>(), patStride, P->openGapScore, P->extendGapScore,
                                                   dOk.as<uint32_t>(), dBytes.as<uint32_t>(), dBytes.as<uint32_t>() + chunkCap + 1);
             if (scan_u32(ctx, dOk.as<uint32_t>(), dIdx.as<uint32_t>(), (uint64_t)n + 1)) return MP_ERR_CUDA;
             if (scan_u32(ctx, dBytes.as<uint32_t>(), dOff.as<uint32_t>(), (uint64_t)n + 1)) return MP_ERR_CUDA;

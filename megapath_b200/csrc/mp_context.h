@@ -94,6 +94,9 @@ struct MpDpTask {          // one semi-global DP instance
 };
 struct MpDpOut {
     int32_t score; uint32_t hitLoc; uint32_t count; uint32_t patLen;
+    // the special CIGAR of the pattern (CigarStringEncoder, DV-DPfunctions.h:344-427), built by the traceback while it emits: text length,
+    // the encoder's statistics, and whether the text itself sits at the end of the task's pattern row ([patStride - cigLen, patStride))
+    uint16_t cigLen, nI, nD, nS; int16_t gapPenalty; uint8_t cigStored, pad_[5];
 };
 
 struct mp_context {

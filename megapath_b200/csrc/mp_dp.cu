@@ -24,6 +24,7 @@
 // k_dp_exact<K>: runs first; tasks whose read occurs unchanged in its window get their (provably identical) answer
 // without the DP, the others are compacted for the two kernels above.
 #include "mp_context.h"
+#include "mp_cigar.h"
 #include <cub/device/device_scan.cuh>
 #include <algorithm>
 #include <type_traits>
@@ -472,7 +473,7 @@ k_dp_tb(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLens
     const uint32_t task = taskBase + (active ? active[lt] : lt);
     const int L = (int)readLens[task], cutoff = cutoffs[task];
     const int mm = P.mismatch, open = P.open, ext = -1, clipLt = P.clipLt;
-    MpDpOut o; o.score = 0; o.hitLoc = 0; o.count = 0; o.patLen = 0;
+    MpDpOut o; memset(&o, 0, sizeof o);
     const FillOut f = fill[task];
     if (cutoff > L || cutoff <= 0 || L >= 255 + open - 1 + cutoff || L > 32 * K || f.score < cutoff) { outs[task] = o; return; }
     const uint8_t *tab = tables + (size_t)(lt & ~1u) * tableStride + (lt & 1u) * 128;   // pair table + this task's half
@@ -514,10 +515,31 @@ k_dp_tb(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLens
         } else pat[p] = (uint8_t)byte;
         ++p;
     };
+    // The special CIGAR is built while the pattern is emitted (same run merging as cigar_encode, which scans the finished pattern): a
+    // finished run is written backwards from the end of the task's pattern row, so the text ends up in read order.  If pattern and
+    // text would meet (hundreds of one-base runs), only the statistics are kept and the assembly pass encodes from the pattern.
+    int cgType = 'N', cgCnt = 0, cgLast = 'N', cgLen = 0, cgI = 0, cgD = 0, cgS = 0, cgGap = 0;
+    bool cgStored = true;
+    uint8_t *cw = pat + patStride;
+    auto cgFlush = [&]() {
+        if (cgCnt > 0 && cgType != 'N') {
+            const int nd = ndigits(cgCnt);
+            cgLen += nd + 1;
+            if (cgType == 'I') cgI += cgCnt; else if (cgType == 'D') cgD += cgCnt; else if (cgType == 'S') cgS += cgCnt;
+            if (cgType == 'I' || cgType == 'D') cgGap += open + (cgCnt - 1) * ext;
+            if (cgStored) {
+                if (cw - (nd + 1) < pat + p + 8) cgStored = false;
+                else { *--cw = (uint8_t)cgType; int v = cgCnt; for (int d = 0; d < nd; ++d) { *--cw = (uint8_t)('0' + v % 10); v /= 10; } }
+            }
+        }
+    };
+    auto cgEvent = [&](int type, int cnt) { if (type == cgType) cgCnt += cnt; else { cgFlush(); cgType = type; cgCnt = cnt; } };
+    auto sym = [&](uint32_t ch) { emit(ch); cgEvent((int)ch, 1); cgLast = (int)ch; };                                   // one pattern symbol
+    auto rep = [&](uint32_t c) { emit('V'); emit(c & 0xffu); cgEvent(cgLast, (int)(c & 0xffu) - 1); };                   // 'V' <count>: the symbol before it, count times in all
     const int hitRow = (int)f.row, hitCol = (int)f.col;
     o.score = f.score; o.count = min(f.cnt, 255u);
     int clipR = L - hitCol;
-    if (clipR > 0) { emit('S'); emit('V'); emit((uint32_t)clipR & 0xffu); }
+    if (clipR > 0) { sym('S'); rep((uint32_t)clipR); }
     int i = L - clipR, j = hitRow;
     enum { NORMAL, I_EXT, D_EXT, SM_EXIT, SI_EXIT, SD_EXIT };
     int state = NORMAL;
@@ -539,27 +561,27 @@ k_dp_tb(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLens
             int ms = eq ? 1 : mm;
             if (dd == ms) {
                 if (i != 1 && dflag == 0) { state = SM_EXIT; break; }
-                emit(eq ? 'M' : 'm'); --j; --i;
+                sym(eq ? 'M' : 'm'); --j; --i;
                 cell = diagCell;                                     // valid whenever the loop continues (i > 0 && j > 0)
                 continue;
             } else if (flag == 1) {
                 int vd = trace_diff(hcur, hmodAt(j - 1, i));
-                emit('D'); --j;
+                sym('D'); --j;
                 if (vd != open) { accum = (int8_t)(vd - ext); state = D_EXT; }
             } else {
                 int hd = trace_diff(hcur, hmodAt(j, i - 1));
-                emit('I'); --i;
+                sym('I'); --i;
                 if (hd != open) { accum = (int8_t)(hd - ext); state = I_EXT; }
             }
         } else if (state == D_EXT) {
             int vd = trace_diff(hcur, hmodAt(j - 1, i));
             if (vd + accum == open && flagAt(j - 1, i) == 0) { state = SD_EXIT; break; }
-            emit('D'); --j;
+            sym('D'); --j;
             if (vd + accum == open) state = NORMAL; else accum = (int8_t)(accum + vd - ext);
         } else {
             int hd = trace_diff(hcur, hmodAt(j, i - 1));
             if (hd + accum == open && flagAt(j, i - 1) == 0) { state = SI_EXIT; break; }
-            emit('I'); --i;
+            sym('I'); --i;
             if (hd + accum == open) state = NORMAL; else accum = (int8_t)(accum + hd - ext);
         }
         if (i > 0 && j > 0) cell = cellAt(j, i);
@@ -567,21 +589,24 @@ k_dp_tb(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLens
     bool discard = false;
     if (j == 0) {
         int sc = min(clipLt & 0xff, i);
-        if (sc < i) { emit('I'); emit('V'); emit((uint32_t)(i - sc) & 0xffu); }
-        emit('S'); emit('V'); emit((uint32_t)sc & 0xffu);
+        if (sc < i) { sym('I'); rep((uint32_t)(i - sc)); }
+        sym('S'); rep((uint32_t)sc);
     } else if (state == SI_EXIT) {
-        emit('I'); emit('S'); emit('V'); emit((uint32_t)(i - 1) & 0xffu);
+        sym('I'); sym('S'); rep((uint32_t)(i - 1));
     } else if (state == SD_EXIT) {
-        emit('D'); emit('S'); emit('V'); emit((uint32_t)(i - 1) & 0xffu);
+        sym('D'); sym('S'); rep((uint32_t)(i - 1));
         discard = true;                                   // CPU_DP.cpp:842-857
     } else if (state == SM_EXIT) {
-        emit((refBase(j - 1) == readBase(i - 1)) ? 'M' : 'm');
-        emit('S'); emit('V'); emit((uint32_t)(i - 1) & 0xffu);
+        sym((refBase(j - 1) == readBase(i - 1)) ? 'M' : 'm');
+        sym('S'); rep((uint32_t)(i - 1));
         j -= 1;
     }
     o.patLen = p;
     emit(0);                                              // terminator
     if (WORDPAT && (p & 3)) ((uint32_t *)pat)[p >> 2] = pacc;
+    cgFlush();
+    if (cw < pat + p + 8) cgStored = false;               // the pattern grew into the text written earlier: the pattern is intact, the text is not
+    o.cigLen = (uint16_t)cgLen; o.nI = (uint16_t)cgI; o.nD = (uint16_t)cgD; o.nS = (uint16_t)cgS; o.gapPenalty = (int16_t)cgGap; o.cigStored = cgStored ? 1 : 0;
     if (discard) { o.score = 0; o.hitLoc = 0; } else o.hitLoc = (uint32_t)j;
     outs[task] = o;
 }
@@ -641,7 +666,16 @@ k_dp_exact(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refL
         uint32_t p = (uint32_t)L;
         if (first == 0) { pat[p++] = 'S'; pat[p++] = 'V'; pat[p++] = 0; }      // j == 0: min(clipLt, i = 0) = 0 clipped bases
         pat[p] = 0;
-        MpDpOut o; o.score = L; o.hitLoc = (uint32_t)first; o.count = min(occ, 255u); o.patLen = p;
+        MpDpOut o; memset(&o, 0, sizeof o);
+        o.score = L; o.hitLoc = (uint32_t)first; o.count = min(occ, 255u); o.patLen = p;
+        // its CIGAR is "<L>M" (a zero-length clip prints nothing), kept at the end of the pattern row like k_dp_tb does
+        const int nd = ndigits(L);
+        if (p + 8 + nd + 1 <= patStride) {
+            uint8_t *cw = pat + patStride; *--cw = 'M';
+            int v = L; for (int d = 0; d < nd; ++d) { *--cw = (uint8_t)('0' + v % 10); v /= 10; }
+            o.cigStored = 1;
+        }
+        o.cigLen = (uint16_t)(nd + 1);
         outs[task] = o;
         needDp[lt] = 0;
     }
