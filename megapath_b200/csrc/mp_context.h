@@ -163,7 +163,7 @@ int mpi_build_from_words(mp_context *ctx, const uint32_t *hBwtWords, uint64_t n,
 // mp_seed.cu
 int mps_seed_pairs(mp_context *ctx, const mp_align_params *P);
 // mp_dp.cu
-struct MpDpParams { int clipLt, clipRt, mismatch, open; };
+struct MpDpParams { int clipLt, clipRt, mismatch, open; int cigText = 1; };      // cigText = 0: never keep the CIGAR text in the pattern row (test hook MP_CIG_TEXT=0)
 // tasks (device) -> outs (device); sequences are extracted from the index / uploaded reads
 int mpd_run_tasks(mp_context *ctx, const MpDpTask *dTasks, uint32_t nTasks, uint32_t maxRefLen, uint32_t maxReadLen,
                   const MpDpParams &P, MpDpOut *dOuts, uint8_t *dPatterns, uint32_t patStride);

@@ -519,7 +519,7 @@ k_dp_tb(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refLens
     // finished run is written backwards from the end of the task's pattern row, so the text ends up in read order.  If pattern and
     // text would meet (hundreds of one-base runs), only the statistics are kept and the assembly pass encodes from the pattern.
     int cgType = 'N', cgCnt = 0, cgLast = 'N', cgLen = 0, cgI = 0, cgD = 0, cgS = 0, cgGap = 0;
-    bool cgStored = true;
+    bool cgStored = P.cigText != 0;
     uint8_t *cw = pat + patStride;
     auto cgFlush = [&]() {
         if (cgCnt > 0 && cgType != 'N') {
@@ -670,7 +670,7 @@ k_dp_exact(const uint8_t *__restrict__ refSeq, const uint32_t *__restrict__ refL
         o.score = L; o.hitLoc = (uint32_t)first; o.count = min(occ, 255u); o.patLen = p;
         // its CIGAR is "<L>M" (a zero-length clip prints nothing), kept at the end of the pattern row like k_dp_tb does
         const int nd = ndigits(L);
-        if (p + 8 + nd + 1 <= patStride) {
+        if (P.cigText && p + 8 + nd + 1 <= patStride) {
             uint8_t *cw = pat + patStride; *--cw = 'M';
             int v = L; for (int d = 0; d < nd; ++d) { *--cw = (uint8_t)('0' + v % 10); v /= 10; }
             o.cigStored = 1;
@@ -752,10 +752,12 @@ __global__ void k_extract(MpIndexView ix, const uint32_t *__restrict__ reads, ui
 
 static int launch_dp(mp_context *ctx, const uint8_t *dRef, const uint32_t *dRefLens, uint32_t refStride,
                      const uint8_t *dRead, const uint32_t *dReadLens, uint32_t readStride, const int32_t *dCutoffs,
-                     uint32_t nTasks, uint32_t maxRefLen, uint32_t maxReadLen, const MpDpParams &P,
+                     uint32_t nTasks, uint32_t maxRefLen, uint32_t maxReadLen, const MpDpParams &Pin,
                      MpDpOut *dOuts, uint8_t *dPatterns, uint32_t patStride, const int16_t *dHints)
 {
     if (nTasks == 0) return 0;
+    MpDpParams P = Pin;
+    if (const char *e = getenv("MP_CIG_TEXT")) if (e[0] == '0') P.cigText = 0;       // tests: the assembly pass encodes every CIGAR from its pattern
     const int K = maxReadLen <= 160 ? 5 : maxReadLen <= 256 ? 8 : 10;
     if (maxReadLen > 320) { mp_set_error("read length %u exceeds the DP kernel bound 320", maxReadLen); return MP_ERR_ARG; }
     if ((size_t)4 * (((size_t)maxRefLen + 44) & ~(size_t)3) * sizeof(uint2) > 200 * 1024) {

@@ -226,6 +226,16 @@ def test_e2e_threads_and_contexts(workdir, small_ref, monkeypatch):
 
 
 @needs_ref
+def test_e2e_cigar_text_fallback(workdir, small_ref, monkeypatch):
+    """The traceback leaves each special CIGAR at the end of its pattern row and stage-S1 assembly copies it; when pattern and text
+    would not both fit the row the assembly encodes from the pattern instead.  MP_CIG_TEXT=0 forces that path for every result:
+    the decoded BAM records (CIGAR, NM / MD, positions, tags) must still equal the reference's."""
+    monkeypatch.setenv("MP_CIG_TEXT", "0")
+    name, rlen, lopt, kw, ini, extra = BAM_SETS[-1]
+    test_e2e_bam_matches_reference(workdir, small_ref, "cigfb_" + name, rlen, lopt, kw, ini, extra)
+
+
+@needs_ref
 def test_e2e_lsam_mode_matches_reference_pipe(workdir, small_ref):
     """`soap4 ... -F -lsam 1` == `reference soap4 ... -F | cc/fastq2lsam 1` (runMegaPath.sh:136), pair lines sorted by name"""
     import subprocess
