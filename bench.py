@@ -619,9 +619,11 @@ def run(args, saved_stdout):
 
     # ---- warm-up (the K-mer filter is built once, before the other contexts borrow it) ----
     ctx.index_prepare(P)
+    ctx.reserve(P, 2 * args.pairs_per_step)             # as the soap4 driver does before its batch loop (mp_reserve)
     run_steps(ctx, range(min(1, args.warmup)), True, {})
     for _ in range(nctx - 1):
         ctxs.append(ctx.clone())
+        ctxs[-1].reserve(P, 2 * args.pairs_per_step)
     for ci, c in enumerate(ctxs):
         run_steps(c, range(ci, ci + max(args.warmup - (1 if ci == 0 else 0), 1)), True, {})
     if args.profile_step:

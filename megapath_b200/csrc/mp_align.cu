@@ -71,20 +71,6 @@ __global__ void k_right_tasks(const mp_candidate *__restrict__ cands, uint32_t n
     account_work(t.valid ? (unsigned long long)t.refLen * t.readLen : 0ull, t.valid ? 1ull : 0ull, counters);
 }
 
-// The special CIGAR of a leg and the encoder's statistics.  The traceback (k_dp_tb) and the exact-occurrence test (k_dp_exact) build
-// both while they emit the pattern and leave the text at the end of the task's pattern row; only when pattern and text would not both
-// fit the row (hundreds of one-base runs) is the text encoded here from the pattern.
-__device__ __forceinline__ CigStats leg_stats(const MpDpOut &o)
-{
-    CigStats st; st.nI = o.nI; st.nD = o.nD; st.nS = o.nS; st.gapPenalty = o.gapPenalty; st.textLen = o.cigLen;
-    return st;
-}
-__device__ __forceinline__ void leg_text(const MpDpOut &o, const uint8_t *pat, uint32_t patStride, int open, int ext, char *out)
-{
-    if (o.cigStored) { const uint8_t *src = pat + patStride - o.cigLen; for (int k = 0; k < (int)o.cigLen; ++k) out[k] = (char)src[k]; }
-    else cigar_encode(pat, open, ext, out, o.cigLen);
-}
-
 __global__ void k_assemble_measure(uint32_t n, const MpDpTask *__restrict__ lt, const MpDpOut *__restrict__ lo,
                                    const MpDpTask *__restrict__ rt, const MpDpOut *__restrict__ ro,
                                    uint32_t *__restrict__ okFlag, uint32_t *__restrict__ cigBytes, uint32_t *__restrict__ leftLen)

@@ -44,3 +44,19 @@ __host__ __device__ inline CigStats cigar_encode(const uint8_t *__restrict__ pat
     return st;
 }
 
+#ifdef __CUDACC__
+#include "mp_context.h"
+// The special CIGAR of a leg and the encoder's statistics.  The traceback (k_dp_tb) and the exact-occurrence test (k_dp_exact) build
+// both while they emit the pattern and leave the text at the end of the task's pattern row; only when pattern and text would not both
+// fit the row (hundreds of one-base runs) is the text encoded here from the pattern.
+__device__ __forceinline__ CigStats leg_stats(const MpDpOut &o)
+{
+    CigStats st; st.nI = o.nI; st.nD = o.nD; st.nS = o.nS; st.gapPenalty = o.gapPenalty; st.textLen = o.cigLen;
+    return st;
+}
+__device__ __forceinline__ void leg_text(const MpDpOut &o, const uint8_t *pat, uint32_t patStride, int open, int ext, char *out)
+{
+    if (o.cigStored) { const uint8_t *src = pat + patStride - o.cigLen; for (int k = 0; k < (int)o.cigLen; ++k) out[k] = (char)src[k]; }
+    else cigar_encode(pat, open, ext, out, o.cigLen);
+}
+#endif

@@ -97,9 +97,7 @@ __global__ void k_single_measure(uint32_t n, const MpDpTask *__restrict__ tasks,
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     const bool ok = outs[c].score >= tasks[c].cutoff;
-    uint32_t bytes = 0;
-    if (ok) bytes = (uint32_t)cigar_encode(pats + (size_t)c * patStride, open, ext, nullptr, 0).textLen + 1;
-    okFlag[c] = ok; cigBytes[c] = bytes;
+    okFlag[c] = ok; cigBytes[c] = ok ? (uint32_t)outs[c].cigLen + 1 : 0u;       // the traceback measured its CIGAR while it ran
 }
 __global__ void k_single_write(uint32_t n, const MpDpTask *__restrict__ tasks, const MpDpOut *__restrict__ outs, const uint8_t *__restrict__ pats,
                                uint32_t patStride, int match, int mm, int open, int ext, uint32_t leftAnchor, const uint32_t *__restrict__ okFlag,
@@ -111,9 +109,10 @@ __global__ void k_single_write(uint32_t n, const MpDpTask *__restrict__ tasks, c
     const uint32_t off = totals[1] + cigOff[c];
     if ((uint64_t)totals[1] + cigOff[c + 1] > cigCap) { totals[4] = 1; return; }
     const int textLen = (int)(cigOff[c + 1] - cigOff[c]) - 1;
-    const CigStats st = cigar_encode(pats + (size_t)c * patStride, open, ext, cig + off, textLen);
-    cig[off + textLen] = 0;
     const MpDpTask t = tasks[c]; const MpDpOut o = outs[c];
+    const CigStats st = leg_stats(o);
+    leg_text(o, pats + (size_t)c * patStride, patStride, open, ext, cig + off);
+    cig[off + textLen] = 0;
     mp_single_result r; memset(&r, 0, sizeof r);
     r.cigar = cigArenaBase + off;
     r.readID = t.readID; r.strand = t.strand; r.seedAlignmentLength = t.pad_;
@@ -246,7 +245,8 @@ __global__ void k_rescue_write(uint32_t n, const MpDpTask *__restrict__ tasks, c
         const uint32_t off = totals[1] + cigOff[c];
         if ((uint64_t)totals[1] + cigOff[c + 1] > cigCap) { totals[4] = 1; return; }
         const int textLen = (int)(cigOff[c + 1] - cigOff[c]) - 1;
-        const CigStats st = cigar_encode(pats + (size_t)c * patStride, open, ext, cig + off, textLen);
+        const CigStats st = leg_stats(o);
+        leg_text(o, pats + (size_t)c * patStride, patStride, open, ext, cig + off);
         cig[off + textLen] = 0;
         dpCigar = cigArenaBase + off;
         const int L = (int)t.readLen - st.nI - st.nS;
