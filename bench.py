@@ -800,8 +800,12 @@ def run(args, saved_stdout):
                 sys.stderr.write("".join(l + "\n" for l in cli_err.splitlines() if "[timing]" in l or "Elapsed time on host" in l or "[mp_trace]" in l))
                 out_bytes = os.path.getsize(os.path.join(d, "ourout_cli.stdout.fq"))
                 os.remove(os.path.join(d, "ourout_cli.stdout.fq"))
+                # the same run with stdout discarded: what the driver sustains when the consumer of its stdout is not the limit (a regular
+                # file takes one thread's page-cache copy, about 4 - 5 GB/s on this box)
+                loop0_s, _, cli_err0 = run_our_soap4(args, prefix, cli, os.path.join(d, "ourout_cli"), ncores, sink="/dev/null")
                 out["e2e_cli"] = {"value": args.cli_pairs / loop_s, "unit": "pairs/s", "pairs": args.cli_pairs, "loop_s": loop_s, "process_wall_s": wall_s,
-                                  "stdout_bytes": out_bytes,
+                                  "stdout_bytes": out_bytes, "value_stdout_discarded": args.cli_pairs / loop0_s, "loop_s_stdout_discarded": loop0_s,
+                                  "io": "device" if "formatting on the device" in cli_err else "host",
                                   "what": "megapath_b200/bin/soap4 pair <index> r_1.fq r_2.fq -F -nc -T %d, stdout to a file; its 'Overall alignment time (excl. read "
                                           "loading)' line = wall time of the whole batch loop (parse + pack + upload + align + format + write; index load excluded, "
                                           "as in the reference)" % ncores}

@@ -217,6 +217,55 @@ int  mp_align_pairs(mp_context *ctx, const mp_align_params *params, mp_results *
 void mp_results_release(mp_context *ctx, mp_results *res);
 int  mp_last_stats(mp_context *ctx, mp_stats *stats);
 
+/* ---- FASTQ ingest and annotated-FASTQ egress on the device (the two host loops either side of the hot path) ----
+ * Ingest replaces loadPairReadsKseq + appendToQueryArrays (QueryParser.cpp:160-260, kseq.h) for plain four-line FASTQ text:
+ * the caller hands over the raw bytes of exactly nPairs records of each mate file; record boundaries, name / comment split
+ * (kseq: name up to the first blank), the "/<digit>" name trim, the length clamp to maxReadLength - 1 (QueryParser.cpp:188) and
+ * the 2-bit packing are done by kernels.  The batch is then uploaded exactly as mp_batch_upload leaves it, and the text stays
+ * resident for mp_format_fastq.  Returns MP_ERR_FORMAT (no batch uploaded) when the text is anything but
+ * strict four-line FASTQ ('\r', NUL bytes, multi-line records, quality of another length, a record count other than nPairs):
+ * the caller then parses with its own kseq-style parser and calls mp_batch_upload.
+ * *readLengths (optional): host copy of the clamped lengths, owned by the context until the next upload. */
+#define MP_ERR_FORMAT (-6)
+int  mp_fastq_upload(mp_context *ctx, const char *text1, uint64_t bytes1, const char *text2, uint64_t bytes2,
+                     uint32_t nPairs, uint32_t wordPerQuery, uint32_t maxReadLength, const uint32_t **readLengths);
+
+/* sizes a context's ingest / egress buffers for batches of nPairs pairs and textBytes of FASTQ text (both mates) before the batch loop */
+int  mp_fastq_reserve(mp_context *ctx, uint64_t textBytes, uint32_t nPairs);
+
+/* chromosome translation tables of the index (.ann names, .tra grid + translate table; HSP.c:57-330): what getChrAndPos /
+ * decideTargetChr (BGS-IO.cpp:163-190, 1312-1341) read.  Copied to the device once per context. */
+typedef struct mp_annotation {
+    uint64_t dnaLength;
+    uint32_t numSeq, gridEntries, numTranslate, reserved_;
+    const uint32_t *grid;               /* gridEntries */
+    const uint64_t *trStartPos;         /* numTranslate */
+    const uint32_t *trChrID;            /* numTranslate, 1-based */
+    const char     *names;              /* the .ann name lines, concatenated */
+    const uint64_t *nameOffsets;        /* numSeq + 1 offsets into names */
+} mp_annotation;
+int  mp_annotation_upload(mp_context *ctx, const mp_annotation *ann);
+
+/* Egress replaces pairDeepDPOutputFastqAPI / unproperlypairDPOutputFastqAPI with getMappingFromHeader and decideTargetChr
+ * (BGS-IO.cpp:1312-1446, 1966-2091; OutputDPResult.cpp:65-265) for the batch a context has just aligned (mp_fastq_upload +
+ * mp_align_pairs): the whole stdout text of the batch -- deep-DP pairs, rescued pairs, then every other pair, each read as
+ * "@name\tSCORE:<best>;<score>,<sequence name>;...<kept entries of the previous comment>\n<bases>\n+\n<qualities>\n" -- is
+ * composed on the device.  mp_format_fastq returns its size, mp_format_fetch copies it into caller memory (pinned memory from
+ * mp_host_alloc makes that a single DMA). */
+typedef struct mp_format_params {
+    double  top;                /* -top / 100 */
+    int32_t megapathMode;       /* 1 = -F, 2 = -P */
+    int32_t ignoreComments;     /* -nc */
+} mp_format_params;
+int  mp_format_fastq(mp_context *ctx, const mp_format_params *fmt, uint64_t *bytes);
+/* on != 0: mp_align_pairs leaves the result arrays on the device (for mp_format_fastq) and returns the counters only --
+ * mp_results.pairs / rescued / singles / cigars are empty.  Saves the device-to-host copies when the caller prints nothing else. */
+int  mp_results_on_device(mp_context *ctx, int on);
+int  mp_format_fetch(mp_context *ctx, char *dst, uint64_t bytes);
+/* page-locked host memory for the two calls above */
+void *mp_host_alloc(uint64_t bytes);
+void  mp_host_free(void *p);
+
 /* ---- roofline denominators measured on the spot (bench.py): kind 0 = random 32-byte gathers over an 8 GB table,
  *      1 = random 64-byte gathers (GB/s of requested bytes), 2 = packed 16-bit DPX issue rate (1e9 thread-instr/s) ---- */
 int  mp_microbench(mp_context *ctx, int kind, double *result);

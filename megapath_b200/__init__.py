@@ -72,6 +72,22 @@ class MegapathError(RuntimeError):
     pass
 
 
+class FastqFormatError(MegapathError):
+    """mp_fastq_upload: the text is not strict four-line FASTQ (MP_ERR_FORMAT)"""
+
+
+MP_ERR_FORMAT = -6
+
+
+class Annotation(C.Structure):          # mp_annotation
+    _fields_ = [("dnaLength", C.c_uint64), ("numSeq", C.c_uint32), ("gridEntries", C.c_uint32), ("numTranslate", C.c_uint32), ("reserved_", C.c_uint32),
+                ("grid", C.c_void_p), ("trStartPos", C.c_void_p), ("trChrID", C.c_void_p), ("names", C.c_void_p), ("nameOffsets", C.c_void_p)]
+
+
+class FormatParams(C.Structure):        # mp_format_params
+    _fields_ = [("top", C.c_double), ("megapathMode", C.c_int32), ("ignoreComments", C.c_int32)]
+
+
 def build():
     """Compile the CUDA extension in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "csrc")])
@@ -111,6 +127,15 @@ def lib():
         L.mp_results_release.argtypes = [C.c_void_p, C.c_void_p]
         L.mp_last_stats.argtypes = [C.c_void_p, C.c_void_p]
         L.mp_default_params.argtypes = [C.c_void_p, C.c_int]
+        L.mp_fastq_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.mp_annotation_upload.argtypes = [C.c_void_p, C.c_void_p]
+        L.mp_format_fastq.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mp_format_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.mp_results_on_device.argtypes = [C.c_void_p, C.c_int]
+        L.mp_fastq_reserve.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32]
+        L.mp_host_alloc.argtypes = [C.c_uint64]
+        L.mp_host_alloc.restype = C.c_void_p
+        L.mp_host_free.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -304,6 +329,44 @@ class Context:
         read_lengths = np.ascontiguousarray(read_lengths, dtype=np.uint32)
         self._keep = (read_lengths,)
         self._check(self.L.mp_batch_upload(self.h, C.c_void_p(host_ptr), _ptr(read_lengths), len(read_lengths), wpq))
+
+    def fastq_upload(self, text1, text2, n_pairs, max_read_length):
+        """Device ingest (mp_fastq_upload): the raw four-line FASTQ text of n_pairs records per mate -> clamped read lengths.
+        Raises FastqFormatError when the text is not strict four-line FASTQ (the caller's own parser takes the batch then)."""
+        lens = C.POINTER(C.c_uint32)()
+        self._keep = (text1, text2)
+        rc = self.L.mp_fastq_upload(self.h, C.c_char_p(text1), len(text1), C.c_char_p(text2), len(text2), n_pairs,
+                                    words_per_query(max_read_length), max_read_length, C.byref(lens))
+        if rc == MP_ERR_FORMAT:
+            raise FastqFormatError(self.L.mp_last_error().decode())
+        self._check(rc)
+        return np.ctypeslib.as_array(lens, shape=(2 * n_pairs,)).copy()
+
+    def annotation_upload(self, prefix):
+        """mp_annotation_upload from <prefix>.ann / .tra (the tables getChrAndPos reads, BGS-IO.cpp:163-190)."""
+        ann = open(prefix + ".ann").read().split("\n")
+        n, ns = int(ann[0].split()[0]), int(ann[0].split()[1])
+        names = [ann[1 + 2 * i].split(" ", 1)[1].encode() for i in range(ns)]
+        tra = open(prefix + ".tra").read().split("\n")
+        _, _, removed, grid_entries = (int(x) for x in tra[0].split())
+        grid = np.array([int(x) for x in tra[1:1 + grid_entries]], dtype=np.uint32)
+        rows = [tra[1 + grid_entries + j].split() for j in range(ns + removed)]
+        tr_start = np.array([int(r[0]) for r in rows], dtype=np.uint64)
+        tr_chr = np.array([int(r[1]) for r in rows], dtype=np.uint32)
+        blob = b"".join(names)
+        off = np.zeros(ns + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(x) for x in names])
+        a = Annotation(n, ns, grid_entries, ns + removed, 0, _ptr(grid), _ptr(tr_start), _ptr(tr_chr), C.cast(C.c_char_p(blob), C.c_void_p), _ptr(off))
+        self._check(self.L.mp_annotation_upload(self.h, C.byref(a)))
+
+    def format_fastq(self, top=0.95, mode=1, ignore_comments=True):
+        """Device egress (mp_format_fastq + mp_format_fetch): the annotated FASTQ text of the batch just aligned."""
+        f = FormatParams(top, mode, 1 if ignore_comments else 0)
+        n = C.c_uint64()
+        self._check(self.L.mp_format_fastq(self.h, C.byref(f), C.byref(n)))
+        buf = C.create_string_buffer(max(int(n.value), 1))
+        self._check(self.L.mp_format_fetch(self.h, buf, n.value))
+        return buf.raw[:n.value]
 
     def seed_pairs(self, params):
         self._check(self.L.mp_seed_pairs(self.h, C.byref(params)))

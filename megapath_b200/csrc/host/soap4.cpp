@@ -435,6 +435,60 @@ static long parse_mapped(const SeqReader &r, ReadBatch &b, uint32_t first, uint3
     return (long)nRec;
 }
 
+// Device ingest (mp_fastq_upload): the byte range of the next maxRec four-line records of a memory-mapped file, found by counting
+// newlines in 256 KiB blocks with several threads (the same location step as parse_mapped).  Whether the range really is strict
+// four-line FASTQ is checked by the kernels that index it.
+// -> records in [r.pos, *newPos), 0 at the end of the file, -1: this file needs the sequential parser
+static long locate_records(const SeqReader &r, uint32_t maxRec, unsigned nThr, size_t *newPos)
+{
+    const char *beg = r.base + r.pos, *lim = r.base + r.end;
+    *newPos = r.pos;
+    if (r.last != 0) return -1;
+    if (beg >= lim || maxRec == 0) return 0;
+    if (lim[-1] != '\n') return -1;
+    SeqReader::View v0; const char *next0 = nullptr;
+    if (SeqReader::view_record(beg, lim, v0, &next0) != 1) return -1;
+    const size_t B = (size_t)1 << 18, remaining = (size_t)(lim - beg), rec0 = (size_t)(next0 - beg);
+    nThr = std::max(1u, nThr);
+    size_t window = std::min(remaining, (size_t)((double)maxRec * (double)rec0 * 1.02) + B), fullCounted = 0;
+    std::vector<uint32_t> cnt;
+    uint64_t lines = 0;
+    for (;;) {
+        const size_t nBlocks = (window + B - 1) / B;
+        cnt.resize(nBlocks);
+        const size_t n = nBlocks - fullCounted;
+        const unsigned T = (unsigned)std::min<size_t>(nThr, std::max<size_t>(n, 1));
+        auto run = [&](unsigned t) { for (size_t k = t; k < n; k += T) { const size_t blk = fullCounted + k; cnt[blk] = (uint32_t)count_newlines(beg + blk * B, std::min(B, window - blk * B)); } };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < T; ++t) th.emplace_back(run, t);
+        run(0);
+        for (std::thread &x : th) x.join();
+        lines = 0; for (uint32_t c : cnt) lines += c;
+        if (lines >= 4ull * maxRec || window == remaining) break;
+        fullCounted = window / B;
+        window = std::min(remaining, window + window / 8 + B);
+    }
+    if (lines < 4ull * maxRec && (lines & 3)) return -1;
+    const uint64_t nRec = std::min<uint64_t>(maxRec, lines / 4);
+    if (nRec == 0) return -1;
+    uint64_t need = 4 * nRec, pre = 0; size_t k = 0;
+    while (pre + cnt[k] < need) pre += cnt[k++];
+    const char *q = beg + k * B;
+    for (need -= pre; need; --need) q = (const char *)memchr(q, '\n', (size_t)(lim - q)) + 1;
+    *newPos = (size_t)(q - r.base);
+    return (long)nRec;
+}
+static void parallel_copy(char *dst, const char *src, size_t n, unsigned nThr)
+{
+    const size_t piece = (size_t)4 << 20, nPieces = (n + piece - 1) / piece;
+    const unsigned T = (unsigned)std::min<size_t>(std::max(1u, nThr), std::max<size_t>(nPieces, 1));
+    auto run = [&](unsigned t) { for (size_t k = t; k < nPieces; k += T) memcpy(dst + k * piece, src + k * piece, std::min(piece, n - k * piece)); };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < T; ++t) th.emplace_back(run, t);
+    run(0);
+    for (std::thread &x : th) x.join();
+}
+
 static uint32_t load_batch(SeqReader &r1, SeqReader &r2, ReadBatch &b, uint32_t maxReads, unsigned packThreads = 4)
 {
     const double tSetup0 = now_s();
@@ -1045,6 +1099,54 @@ int main(int argc, char **argv)
     P.maxReadLength = maxLen; P.insert_high = opt.insert_high;
     const double top = opt.top / 100.0;
 
+    fill_char_map();
+    SeqReader r1, r2;
+    if (!r1.open(opt.query1) || !r2.open(opt.query2)) { fprintf(stderr, "Cannot open the read files\n"); return 1; }
+    uint32_t maxNumQueries = 12 * 8192 * 128 / 6;                  // SOAP4.cpp:206
+    if (const char *e = getenv("MP_BATCH_READS")) {                // smaller batches (multi-batch / multi-context tests on small inputs)
+        const long v = atol(e); if (v >= 64 && v <= 12 * 8192 * 128 / 6) maxNumQueries = (uint32_t)v & ~63u;
+    }
+    if (const char *e = getenv("MP_CONTEXTS_PER_GPU")) { int v = atoi(e); if (v >= 1 && v <= 8) opt.contextsPerGpu = v; }
+    const unsigned ioThreads = (unsigned)std::min(8, std::max(1, opt.numCpuThreads));
+    const unsigned stageThreads = (unsigned)std::min(16, std::max(1, opt.numCpuThreads));      // per mate file, while a batch is staged
+    // ---- FASTQ ingest and annotated-FASTQ egress on the device (mp_fastq_upload / mp_format_fastq): plain FASTQ files in, -F / -P text
+    //      out.  Everything else (.gz, pipes, -b, -lsam, anything but strict four-line records) takes the host parser / formatter below.
+    //      MP_HOST_IO=1 forces the host loops (tests compare the two). ----
+    bool deviceIO = opt.megapathMode != 0 && !opt.outputBAM && opt.lsam < 0 && r1.mapped && r2.mapped && !getenv("MP_HOST_IO");
+    struct RawBatch { char *pin = nullptr; size_t pinCap = 0, bytes1 = 0, off2 = 0, bytes2 = 0; uint32_t nReads = 0; };
+    std::mutex pinMu; std::vector<std::pair<char *, size_t>> pinPool;
+    auto pin_take = [&](size_t need) -> std::pair<char *, size_t> {
+        {
+            std::lock_guard<std::mutex> lk(pinMu);
+            for (size_t k = 0; k < pinPool.size(); ++k) if (pinPool[k].second >= need) { auto r = pinPool[k]; pinPool.erase(pinPool.begin() + (long)k); return r; }
+            if (!pinPool.empty()) { mp_host_free(pinPool.back().first); pinPool.pop_back(); }          // too small: replace it
+        }
+        const size_t cap = need + need / 16;
+        return std::make_pair((char *)mp_host_alloc(cap), cap);
+    };
+    auto pin_give = [&](char *p, size_t cap) { if (p) { std::lock_guard<std::mutex> lk(pinMu); pinPool.emplace_back(p, cap); } };
+    // Staging buffers: one per batch in flight (a batch holds its buffer from staging until the ordered writer is through with its
+    // output text).  Page-locking a gigabyte takes half a second and stalls every CUDA call of the process while it runs, so the buffers
+    // are made here, by a thread that runs beside the index load, sized from the first record of either file.
+    double bytesPerRec[2] = { 0, 0 };                              // running estimate per mate file (first record, then the last batch's mean)
+    auto window_cap = [&](int m, const SeqReader &r) -> size_t {  // room for one batch of mate m's text: the estimate + 3 % + two count blocks
+        const size_t est = (size_t)((double)(maxNumQueries / 2) * bytesPerRec[m] * 1.03) + ((size_t)2 << 18);
+        return (std::min<size_t>(est, r.end - r.pos + 64) + 63) & ~(size_t)63;
+    };
+    auto batch_need = [&]() -> size_t { return window_cap(0, r1) + window_cap(1, r2) + (size_t)maxNumQueries * 64 + ((size_t)1 << 20); };
+    std::thread pinThread;
+    if (deviceIO) {
+        SeqReader::View v; const char *nx = nullptr;
+        if (r1.end > r1.pos && r2.end > r2.pos && SeqReader::view_record(r1.base + r1.pos, r1.base + r1.end, v, &nx) == 1) bytesPerRec[0] = (double)(nx - (r1.base + r1.pos));
+        if (bytesPerRec[0] > 0 && SeqReader::view_record(r2.base + r2.pos, r2.base + r2.end, v, &nx) == 1) bytesPerRec[1] = (double)(nx - (r2.base + r2.pos));
+        if (bytesPerRec[0] > 0 && bytesPerRec[1] > 0) {
+            const size_t need = batch_need(), cap = need + need / 16;
+            const size_t batches = (size_t)((double)(r1.end - r1.pos) / (bytesPerRec[0] * (double)(maxNumQueries / 2))) + 1;
+            const size_t count = std::min<size_t>((size_t)opt.numGpus * (size_t)opt.contextsPerGpu + 3, batches);
+            pinThread = std::thread([&, cap, count] { for (size_t k = 0; k < count; ++k) { char *p = (char *)mp_host_alloc(cap); if (p) pin_give(p, cap); } });
+        } else if (r1.end > r1.pos || r2.end > r2.pos) deviceIO = false;           // the first record is not a plain four-line one
+    }
+
     // one index replica per GPU (loaded in parallel), contextsPerGpu contexts sharing it (mp_clone)
     if (const char *e = getenv("MP_CONTEXTS_PER_GPU")) { int v = atoi(e); if (v >= 1 && v <= 8) opt.contextsPerGpu = v; }
     fprintf(stderr, "[Main] loading index into device...\n");
@@ -1076,8 +1178,137 @@ int main(int argc, char **argv)
             for (mp_context *c : contexts) if (mp_reserve(c, &P, batchReads)) { fprintf(stderr, "%s\n", mp_last_error()); return 1; }
         }
     }
+    if (pinThread.joinable()) pinThread.join();
     Annotation ann;
     if (!ann.load(opt.indexName)) return 1;
+    // One mate file's next batch: every 256 KiB block is copied into the staging buffer and its newlines are counted in the copy while
+    // it is still in the cache -- one pass over the page cache.  -> records staged, 0 at the end of the file, -1: not for the device
+    // path, -2: the window estimate did not hold (the caller locates the batch exactly, locate_records, and copies it then)
+    auto stage_file = [&](const SeqReader &r, int m, uint32_t maxRec, char *dst, size_t cap, size_t *bytes) -> long {
+        const char *beg = r.base + r.pos, *lim = r.base + r.end;
+        *bytes = 0;
+        if (r.last != 0) return -1;
+        if (beg >= lim || maxRec == 0) return 0;
+        if (lim[-1] != '\n' || *beg != '@') return -1;
+        const size_t B = (size_t)1 << 18, remaining = (size_t)(lim - beg);
+        size_t window = std::min(remaining, (size_t)((double)maxRec * bytesPerRec[m] * 1.02) + B), done = 0;
+        std::vector<uint32_t> cnt;
+        uint64_t lines = 0;
+        for (;;) {
+            if (window > cap) return -2;
+            const size_t nBlocks = (window + B - 1) / B, n = nBlocks - done;
+            cnt.resize(nBlocks);
+            const unsigned T = (unsigned)std::min<size_t>(stageThreads, std::max<size_t>(n, 1));
+            auto run = [&](unsigned t) {
+                for (size_t k = t; k < n; k += T) {
+                    const size_t blk = done + k, o = blk * B, len = std::min(B, window - o);
+                    memcpy(dst + o, beg + o, len);
+                    cnt[blk] = (uint32_t)count_newlines(dst + o, len);
+                }
+            };
+            std::vector<std::thread> th;
+            for (unsigned t = 1; t < T; ++t) th.emplace_back(run, t);
+            run(0);
+            for (std::thread &x : th) x.join();
+            lines = 0; for (uint32_t c : cnt) lines += c;
+            if (lines >= 4ull * maxRec || window == remaining) break;
+            done = window / B;                                               // the partial last block is copied and counted again
+            window = std::min(remaining, window + window / 8 + B);
+        }
+        if (lines < 4ull * maxRec && (lines & 3)) return -1;
+        const uint64_t nRec = std::min<uint64_t>(maxRec, lines / 4);
+        if (nRec == 0) return -1;
+        uint64_t need = 4 * nRec, pre = 0; size_t k = 0;
+        while (pre + cnt[k] < need) pre += cnt[k++];
+        const char *q = dst + k * B;
+        for (need -= pre; need; --need) q = (const char *)memchr(q, '\n', (size_t)(dst + window - q)) + 1;
+        *bytes = (size_t)(q - dst);
+        return (long)nRec;
+    };
+    // -> 1: the next batch staged in page-locked memory (file positions advanced), 0: end of both files, -1: not for the device path
+    auto stage_raw = [&](RawBatch &rb) -> int {
+        static const bool ltiming = getenv("MP_DRIVER_TIMING") != nullptr;
+        const double ts0 = now_s();
+        const size_t cap1 = window_cap(0, r1), cap2 = window_cap(1, r2);
+        auto pc = pin_take(cap1 + cap2 + (size_t)maxNumQueries * 64 + ((size_t)1 << 20));
+        if (!pc.first) { fprintf(stderr, "%s\n", mp_last_error()); exit(1); }
+        rb.pin = pc.first; rb.pinCap = pc.second; rb.off2 = cap1;
+        const double ts1 = now_s();
+        long n1 = 0, n2 = 0;
+        std::thread t2([&] { n2 = stage_file(r2, 1, maxNumQueries / 2, rb.pin + rb.off2, cap2, &rb.bytes2); });
+        n1 = stage_file(r1, 0, (maxNumQueries + 1) / 2, rb.pin, cap1, &rb.bytes1);
+        t2.join();
+        const double ts2 = now_s();
+        size_t p1 = r1.pos + rb.bytes1, p2 = r2.pos + rb.bytes2;
+        if (n1 == -2 || n2 == -2) {
+            // records much longer than the estimate: locate the batch exactly, then copy it
+            std::thread l2([&] { n2 = locate_records(r2, maxNumQueries / 2, stageThreads, &p2); });
+            n1 = locate_records(r1, (maxNumQueries + 1) / 2, stageThreads, &p1);
+            l2.join();
+            if (n1 > 0 && n2 > 0) {
+                rb.bytes1 = p1 - r1.pos; rb.bytes2 = p2 - r2.pos; rb.off2 = (rb.bytes1 + 63) & ~(size_t)63;
+                const size_t need = rb.off2 + rb.bytes2 + (size_t)maxNumQueries * 64 + ((size_t)1 << 20);
+                if (need > rb.pinCap) {
+                    pin_give(rb.pin, rb.pinCap);
+                    pc = pin_take(need);
+                    if (!pc.first) { fprintf(stderr, "%s\n", mp_last_error()); exit(1); }
+                    rb.pin = pc.first; rb.pinCap = pc.second;
+                }
+                std::thread c2([&] { parallel_copy(rb.pin + rb.off2, r2.base + r2.pos, rb.bytes2, stageThreads); });
+                parallel_copy(rb.pin, r1.base + r1.pos, rb.bytes1, stageThreads);
+                c2.join();
+            }
+        }
+        if (n1 <= 0 || n2 <= 0 || rb.bytes1 >= 0xFFFFFFF0ull || rb.bytes2 >= 0xFFFFFFF0ull) {
+            pin_give(rb.pin, rb.pinCap); rb.pin = nullptr;
+            return n1 == 0 && n2 == 0 ? 0 : -1;
+        }
+        if (n1 != n2) { fprintf(stderr, "Error: number of sequences of pair-end files not matched.\n"); exit(1); }
+        rb.nReads = 2 * (uint32_t)n1;
+        bytesPerRec[0] = (double)rb.bytes1 / (double)n1; bytesPerRec[1] = (double)rb.bytes2 / (double)n2;
+        r1.pos = p1; r2.pos = p2;
+        if (ltiming) fprintf(stderr, "[timing] stage: buffer %.3f copy + count %.3f rest %.3f s (%.0f MB)\n", ts1 - ts0, ts2 - ts1, now_s() - ts2, (rb.bytes1 + rb.bytes2) / 1e6);
+        return 1;
+    };
+    RawBatch firstRaw; bool haveFirstRaw = false;
+    if (deviceIO) {
+        std::vector<uint64_t> nameOff(ann.numSeq + 1, 0); std::string nameBlob;
+        for (uint32_t i = 0; i < ann.numSeq; ++i) { nameOff[i] = nameBlob.size(); nameBlob += ann.names[i]; }
+        nameOff[ann.numSeq] = nameBlob.size();
+        std::vector<uint64_t> trStart(ann.tr.size()); std::vector<uint32_t> trChr(ann.tr.size());
+        for (size_t k = 0; k < ann.tr.size(); ++k) { trStart[k] = ann.tr[k].startPos; trChr[k] = ann.tr[k].chrID; }
+        mp_annotation A; memset(&A, 0, sizeof A);
+        A.dnaLength = ann.dnaLength; A.numSeq = ann.numSeq; A.gridEntries = (uint32_t)ann.grid.size(); A.numTranslate = (uint32_t)ann.tr.size();
+        A.grid = ann.grid.data(); A.trStartPos = trStart.data(); A.trChrID = trChr.data(); A.names = nameBlob.data(); A.nameOffsets = nameOff.data();
+        for (mp_context *c : contexts) if (mp_annotation_upload(c, &A)) { fprintf(stderr, "[Main] %s; formatting on the host\n", mp_last_error()); deviceIO = false; break; }
+    }
+    if (deviceIO) {
+        // The first batch is staged and indexed here, as part of the set-up: its verdict decides between the device and the host loops
+        // for the whole run (CRLF or multi-line files fail it), and its read lengths give the first-batch parameters (SOAP4.cpp:458-474).
+        const size_t save1 = r1.pos, save2 = r2.pos;
+        const int st = stage_raw(firstRaw);
+        if (st == 1) {
+            const uint32_t *lens = nullptr;
+            const int rc = mp_fastq_upload(contexts[0], firstRaw.pin, firstRaw.bytes1, firstRaw.pin + firstRaw.off2, firstRaw.bytes2, firstRaw.nReads / 2,
+                                           ((uint32_t)maxLen + 15) / 16, (uint32_t)maxLen, &lens);
+            if (rc == 0) {
+                std::vector<uint32_t> lv(lens, lens + firstRaw.nReads);
+                const uint32_t d1 = detect_read_length(lv, firstRaw.nReads, 0), d2 = detect_read_length(lv, firstRaw.nReads, 1);
+                if (opt.insert_low < (int)d2) opt.insert_low = (int)d2;
+                if (opt.insert_low < (int)d1) opt.insert_low = (int)d1;
+                P.insert_low = opt.insert_low;
+                haveFirstRaw = true;
+                // every context's ingest / egress buffers sized like the first batch (no cudaMalloc inside the batch loop)
+                if (r1.pos < r1.end)
+                    for (mp_context *c : contexts) if (mp_fastq_reserve(c, firstRaw.bytes1 + firstRaw.bytes2 + (firstRaw.bytes1 + firstRaw.bytes2) / 16, firstRaw.nReads / 2)) { fprintf(stderr, "%s\n", mp_last_error()); return 1; }
+            } else if (rc == MP_ERR_FORMAT) {
+                fprintf(stderr, "[Main] %s: host parser\n", mp_last_error());
+                pin_give(firstRaw.pin, firstRaw.pinCap); r1.pos = save1; r2.pos = save2; deviceIO = false;
+            } else { fprintf(stderr, "%s\n", mp_last_error()); return 1; }
+        } else if (st < 0) { r1.pos = save1; r2.pos = save2; deviceIO = false; }
+        // st == 0: empty input, the reader below ends at once
+    }
+    fprintf(stderr, "[Main] FASTQ parsing and output formatting on the %s\n", deviceIO ? "device" : "host");
     fprintf(stderr, "[Main] Finished loading index into device.\n");
     const double tIndex = now_s();
     fprintf(stderr, "[Main] Loading time : %9.4f seconds\n\n", tIndex - t0);
@@ -1116,35 +1347,46 @@ int main(int argc, char **argv)
         }
     }
 
-    fill_char_map();
-    SeqReader r1, r2;
-    if (!r1.open(opt.query1) || !r2.open(opt.query2)) { fprintf(stderr, "Cannot open the read files\n"); return 1; }
-    uint32_t maxNumQueries = 12 * 8192 * 128 / 6;                  // SOAP4.cpp:206
-    if (const char *e = getenv("MP_BATCH_READS")) {                // smaller batches (multi-batch / multi-context tests on small inputs)
-        const long v = atol(e); if (v >= 64 && v <= 12 * 8192 * 128 / 6) maxNumQueries = (uint32_t)v & ~63u;
-    }
-
     // ---- pipeline: reader thread -> GPU workers (one per context; each formats its own batch) -> ordered writer (this thread).
     //      The reference overlaps read loading with alignment the same way (aio_thread.cpp:804, SOAP4.cpp:424-441, 576-585). ----
     struct Job {
         uint64_t seq = 0; ReadBatch *b = nullptr; uint32_t nReads = 0; std::vector<std::string> fqParts; std::string log; std::vector<uint8_t> bam[3];
         uint64_t pairsAligned = 0; double loadSeconds = 0, alignSeconds = 0; bool failed = false;
+        // device ingest / egress: the batch's FASTQ text staged in page-locked memory; the formatted text comes back into the same buffer
+        bool dev = false, uploaded = false; RawBatch raw; uint64_t outBytes = 0;
     };
     std::mutex mu; std::condition_variable cvIn, cvOut, cvRoom;
     std::vector<ReadBatch *> batchPool;                            // recycled read batches (guarded by mu)
     std::deque<Job *> inq; std::map<uint64_t, Job *> doneq; bool readerDone = false; size_t inflight = 0;
+    Job *firstJob = nullptr;                                       // the batch already uploaded to contexts[0] (device ingest)
     const size_t maxInflight = contexts.size() + 2;
     const int stageUnpaired = P.skipDefaultDP ? 2 : 3;
 
     std::thread reader([&]() {
         uint64_t seq = 0; bool detected = false; double last = now_s();
+        bool devIO = deviceIO;
+        if (haveFirstRaw) {                                         // staged and uploaded to the first context during set-up
+            Job *j = new Job; j->dev = true; j->uploaded = true; j->raw = firstRaw; j->nReads = firstRaw.nReads; j->seq = seq++;
+            detected = true;
+            std::unique_lock<std::mutex> lk(mu);
+            ++inflight; firstJob = j; cvIn.notify_all();
+        }
         for (;;) {
             Job *j = new Job;
+            if (devIO) {
+                const int st = stage_raw(j->raw);
+                if (st == 0) { delete j; break; }
+                if (st == 1) { j->dev = true; j->nReads = j->raw.nReads; }
+                else devIO = false;                                 // the rest of the input goes through the sequential parser
+            }
+            if (!j->dev) {
             { std::lock_guard<std::mutex> lk(mu); if (!batchPool.empty()) { j->b = batchPool.back(); batchPool.pop_back(); } }
             if (!j->b) j->b = new ReadBatch;
             j->b->maxReadLength = (uint32_t)maxLen; j->b->wpq = ((uint32_t)maxLen + 15) / 16;
-            if (load_batch(r1, r2, *j->b, maxNumQueries, (unsigned)std::min(8, std::max(1, opt.numCpuThreads))) == 0) { delete j->b; delete j; break; }
-            j->seq = seq++; j->nReads = j->b->nReads;
+            if (load_batch(r1, r2, *j->b, maxNumQueries, ioThreads) == 0) { delete j->b; delete j; break; }
+            j->nReads = j->b->nReads;
+            }
+            j->seq = seq++;
             double t = now_s(); j->loadSeconds = t - last;
             if (!detected) {                                       // first batch: read-length detection and insert_low clamp (SOAP4.cpp:458-474)
                 uint32_t d1 = detect_read_length(j->b->lens, j->b->nReads, 0), d2 = detect_read_length(j->b->lens, j->b->nReads, 1);
@@ -1169,17 +1411,35 @@ int main(int argc, char **argv)
             Job *j = nullptr;
             {
                 std::unique_lock<std::mutex> lk(mu);
-                cvIn.wait(lk, [&] { return !inq.empty() || readerDone; });
-                if (inq.empty()) return;
-                j = inq.front(); inq.pop_front();
+                const bool mayFirst = gpu == contexts[0];
+                cvIn.wait(lk, [&] { return (mayFirst && firstJob) || !inq.empty() || readerDone; });
+                if (mayFirst && firstJob) { j = firstJob; firstJob = nullptr; }
+                else { if (inq.empty()) return; j = inq.front(); inq.pop_front(); }
             }
             const double ts = now_s();
-            ReadBatch &b = *j->b;
-            const uint32_t numQueries = b.nReads, nPairs = numQueries / 2;
+            const uint32_t numQueries = j->nReads, nPairs = numQueries / 2;
             mp_results R;
             static const bool timing = getenv("MP_DRIVER_TIMING") != nullptr;      // per-batch host breakdown on stderr
             double tUp = 0, tAl = 0, tFmt = 0, libWallMs = 0;
-            int rcUp = mp_batch_upload(gpu, b.queries.data(), b.lens.data(), numQueries, b.wpq);
+            int rcUp = 0;
+            if (j->dev && !j->uploaded) {
+                rcUp = mp_fastq_upload(gpu, j->raw.pin, j->raw.bytes1, j->raw.pin + j->raw.off2, j->raw.bytes2, nPairs, ((uint32_t)maxLen + 15) / 16, (uint32_t)maxLen, nullptr);
+                if (rcUp == MP_ERR_FORMAT) {
+                    // the input stops being strict four-line FASTQ in mid-file: this batch goes through the host parser, from the staged
+                    // bytes.  Its records must be the ones the newline count promised, else the batch boundaries are not the reference's.
+                    SeqReader m1, m2;
+                    m1.base = j->raw.pin; m1.end = j->raw.bytes1; m1.eof = true; m1.mapped = true;
+                    m2.base = j->raw.pin + j->raw.off2; m2.end = j->raw.bytes2; m2.eof = true; m2.mapped = true;
+                    j->b = new ReadBatch; j->b->maxReadLength = (uint32_t)maxLen; j->b->wpq = ((uint32_t)maxLen + 15) / 16;
+                    const uint32_t got = load_batch(m1, m2, *j->b, numQueries, ioThreads);
+                    if (got != numQueries || m1.pos != m1.end || m2.pos != m2.end) {
+                        fprintf(stderr, "Error: the read files are not four-line FASTQ throughout; run with MP_HOST_IO=1\n"); exit(1);
+                    }
+                    j->dev = false; rcUp = 0;
+                }
+            }
+            if (!j->dev && !rcUp) rcUp = mp_batch_upload(gpu, j->b->queries.data(), j->b->lens.data(), numQueries, j->b->wpq);
+            mp_results_on_device(gpu, j->dev ? 1 : 0);               // the host formatter needs the result arrays, the device formatter does not
             tUp = now_s();
             if (rcUp || mp_align_pairs(gpu, &P, &R)) {
                 j->log = std::string(mp_last_error()) + "\n"; j->failed = true;
@@ -1194,7 +1454,23 @@ int main(int argc, char **argv)
                 tAl = now_s();
                 if (timing) { mp_stats st; if (mp_last_stats(gpu, &st) == 0) libWallMs = st.ms_wall; }
                 // ---- output: stage order of the reference (deep DP pairs, rescued pairs, then everything else) ----
-                if (opt.megapathMode || opt.outputBAM) {
+                if (j->dev) {
+                    // the batch's whole stdout text is composed on the device and DMA'd into the staging buffer the input came from
+                    mp_format_params F; F.top = top; F.megapathMode = opt.megapathMode; F.ignoreComments = opt.ignoreComments;
+                    uint64_t ob = 0;
+                    const double tf0 = now_s();
+                    int rc = mp_format_fastq(gpu, &F, &ob);
+                    const double tf1 = now_s();
+                    if (!rc && ob > j->raw.pinCap) {
+                        pin_give(j->raw.pin, j->raw.pinCap); j->raw.pin = nullptr;
+                        auto pc = pin_take(ob + (ob >> 4));
+                        if (!pc.first) rc = -1; else { j->raw.pin = pc.first; j->raw.pinCap = pc.second; }
+                    }
+                    if (!rc) rc = mp_format_fetch(gpu, j->raw.pin, ob);
+                    if (timing) fprintf(stderr, "[timing]  batch %llu: format (device) %.3f fetch %.3f s (%.0f MB)\n", (unsigned long long)j->seq, tf1 - tf0, now_s() - tf1, ob / 1e6);
+                    if (rc) { j->log += std::string(mp_last_error()) + "\n"; j->failed = true; } else j->outBytes = ob;
+                } else if (opt.megapathMode || opt.outputBAM) {
+                    ReadBatch &b = *j->b;
                     oc.b = &b;
                     // Formatting is spread over the -T host threads: every chunk of pairs writes its own text / BAM records, and the
                     // chunks are concatenated in order, so the stream is the one a single thread would have produced.
@@ -1268,11 +1544,11 @@ int main(int argc, char **argv)
                 tFmt = now_s();
                 mp_results_release(gpu, &R);
             }
-            if (timing) fprintf(stderr, "[timing] batch %llu: upload %.3f align %.3f (lib wall %.3f) format %.3f release %.3f s\n", (unsigned long long)j->seq,
-                                tUp - ts, tAl - tUp, libWallMs / 1e3, tFmt - tAl, now_s() - tFmt);
+            if (timing) fprintf(stderr, "[timing] batch %llu: upload %.3f align %.3f (lib wall %.3f) format %.3f release %.3f s; started at %.3f\n", (unsigned long long)j->seq,
+                                tUp - ts, tAl - tUp, libWallMs / 1e3, tFmt - tAl, now_s() - tFmt, ts - t0);
             j->alignSeconds = now_s() - ts;
             std::lock_guard<std::mutex> lk(mu);
-            batchPool.push_back(j->b); j->b = nullptr;              // the text output no longer refers to the batch
+            if (j->b) { batchPool.push_back(j->b); j->b = nullptr; }   // the text output no longer refers to the batch
             doneq[j->seq] = j; cvOut.notify_all();
         }
     };
@@ -1297,23 +1573,28 @@ int main(int argc, char **argv)
         fputs(j->log.c_str(), stderr);
         if (j->failed) failed = true;
         const double tw0 = now_s();
+        if (j->outBytes) { fwrite(j->raw.pin, 1, (size_t)j->outBytes, stdout); writtenBytes += j->outBytes; }
         for (const std::string &part : j->fqParts) if (!part.empty()) { fwrite(part.data(), 1, part.size(), stdout); writtenBytes += part.size(); }
+        pin_give(j->raw.pin, j->raw.pinCap); j->raw.pin = nullptr;
         writeSeconds += now_s() - tw0;
         if (opt.outputBAM) { bamDP.write_blocks(j->bam[0]); bamGout.write_blocks(j->bam[1]); bamUnpair.write_blocks(j->bam[2]); }
         fprintf(stderr, "[Main] Elapsed time : %9.4f seconds\n\n", j->alignSeconds);
+        if (getenv("MP_DRIVER_TIMING")) fprintf(stderr, "[timing] batch %llu written at %.3f\n", (unsigned long long)j->seq, now_s() - t0);
         totalLoad += j->loadSeconds; totalAlign += j->alignSeconds; totalPairsAligned += j->pairsAligned;
         delete j; ++next;
     }
     reader.join();
     for (std::thread &t : workers) t.join();
-    for (ReadBatch *rb : batchPool) delete rb;
     fflush(stdout);
     if (opt.outputBAM) { bamDP.close(); bamGout.close(); bamUnpair.close(); }
+    const double tLoop1 = now_s();                                  // every batch aligned and written: the end of the batch loop
+    for (ReadBatch *rb : batchPool) delete rb;
+    // (the staging buffers are left to the end of the process: unlocking gigabytes page by page here would only delay the exit)
     if (failed) return 1;
-    if (getenv("MP_DRIVER_TIMING")) fprintf(stderr, "[timing] writer: %.3f s in stdout writes, %.1f MB\n", writeSeconds, writtenBytes / 1e6);
+    if (getenv("MP_DRIVER_TIMING")) fprintf(stderr, "[timing] writer: %.3f s in stdout writes, %.1f MB; batch loop from %.3f to %.3f\n", writeSeconds, writtenBytes / 1e6, tLoop0 - t0, tLoop1 - t0);
     fprintf(stderr, "[Main] Overall number of pairs of reads aligned: %llu\n", (unsigned long long)totalPairsAligned);
     fprintf(stderr, "[Main] Overall read load time : %9.4f seconds\n", totalLoad);
-    fprintf(stderr, "[Main] Overall alignment time (excl. read loading) : %9.4f seconds\n", now_s() - tLoop0);
+    fprintf(stderr, "[Main] Overall alignment time (excl. read loading) : %9.4f seconds\n", tLoop1 - tLoop0);
     for (size_t k = contexts.size(); k-- > 0;) mp_destroy(contexts[k]);
     fprintf(stderr, "[Main] Overall running time: %f\n", now_s() - t0);
     return 0;

@@ -302,8 +302,8 @@ static int deep_dp(mp_context *ctx, const mp_align_params *P, mp_results *out, u
     }
     const uint32_t nKept = tot[2], nBytes = tot[1];
     if (H.resize(nKept) || HC.resize(nBytes)) return MP_ERR_CUDA;
-    if (nKept) MP_CUDA(cudaMemcpyAsync(H.data(), ctx->dRes2.p, (size_t)nKept * sizeof(mp_pair_result), cudaMemcpyDeviceToHost, st));
-    if (nBytes) MP_CUDA(cudaMemcpyAsync(HC.data(), dCig.p, nBytes, cudaMemcpyDeviceToHost, st));
+    if (nKept && !ctx->resultsOnDevice) MP_CUDA(cudaMemcpyAsync(H.data(), ctx->dRes2.p, (size_t)nKept * sizeof(mp_pair_result), cudaMemcpyDeviceToHost, st));
+    if (nBytes && !ctx->resultsOnDevice) MP_CUDA(cudaMemcpyAsync(HC.data(), dCig.p, nBytes, cudaMemcpyDeviceToHost, st));
     {   // cells / tasks counted on the device by k_left_tasks / k_right_tasks
         unsigned long long hc2[2];
         MP_CUDA(cudaMemcpyAsync(hc2, dCnt + 11, sizeof hc2, cudaMemcpyDeviceToHost, st));
@@ -371,7 +371,9 @@ extern "C" void mp_destroy(mp_context *ctx)
                        &ctx->dTasks, &ctx->dRefSeq, &ctx->dReadSeq, &ctx->dTable, &ctx->dFill, &ctx->dPattern, &ctx->dDpOut,
                        &ctx->dLT, &ctx->dRT, &ctx->dLO, &ctx->dRO, &ctx->dLP, &ctx->dRP, &ctx->dOk, &ctx->dBytes, &ctx->dIdx, &ctx->dOff,
                        &ctx->dRes, &ctx->dCig, &ctx->dExFlag, &ctx->dExPos, &ctx->dExIdx, &ctx->dAligned, &ctx->dGather, &ctx->dHintTest, &ctx->dRes2, &ctx->dKeep, &ctx->dKeepPos, &ctx->dTotals, &ctx->dS2Counts, &ctx->dS2Start, &ctx->dS2Tasks, &ctx->dS2Res,
-                       &ctx->dRsSlotTasks, &ctx->dRsSlotInfo, &ctx->dRsFlag, &ctx->dRsPos, &ctx->dRsTasks, &ctx->dRsInfo, &ctx->dRsRec, &ctx->dRsOut, &ctx->dRsKeep, &ctx->dRsKeepPos };
+                       &ctx->dRsSlotTasks, &ctx->dRsSlotInfo, &ctx->dRsFlag, &ctx->dRsPos, &ctx->dRsTasks, &ctx->dRsInfo, &ctx->dRsRec, &ctx->dRsOut, &ctx->dRsKeep, &ctx->dRsKeepPos,
+                       &ctx->dFqText, &ctx->dFqCnt, &ctx->dFqCntPos, &ctx->dFqLines, &ctx->dFqRec, &ctx->dFqFlags, &ctx->dAnnGrid, &ctx->dAnnTrStart, &ctx->dAnnTrChr,
+                       &ctx->dAnnNames, &ctx->dAnnNameOff, &ctx->dFmtKeys, &ctx->dFmtGroups, &ctx->dFmtRecLen, &ctx->dFmtTail, &ctx->dFmtLen, &ctx->dFmtOff, &ctx->dFmtOut };
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->stream);
@@ -568,6 +570,7 @@ extern "C" int mp_align_pairs(mp_context *ctx, const mp_align_params *params, mp
     const double wall0 = mp_now_ms();
     MpTrace tr;
     memset(out, 0, sizeof *out);
+    ctx->resValid = false; ctx->fmtReady = false;
     ctx->hPairs.clear(); ctx->hRescued.clear(); ctx->hSingles.clear(); ctx->hCigars.clear();
     ctx->evUsed = 0;
     MP_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
@@ -598,8 +601,19 @@ extern "C" int mp_align_pairs(mp_context *ctx, const mp_align_params *params, mp
     out->singles = ctx->hSingles.data(); out->n_singles = ctx->hSingles.size();
     out->cigars = ctx->hCigars.data(); out->cigar_bytes = ctx->hCigars.size();
     ctx->seeded = false;       // the batch has been consumed
+    ctx->resCount[0] = out->n_pairs; ctx->resCount[1] = out->n_rescued; ctx->resCount[2] = out->n_singles; ctx->resValid = true;
+    if (ctx->resultsOnDevice) {            // nothing was copied: the caller gets the counters only
+        out->pairs = nullptr; out->rescued = nullptr; out->singles = nullptr; out->cigars = nullptr;
+        out->n_pairs = out->n_rescued = out->n_singles = out->cigar_bytes = 0;
+    }
     S.ms_wall = (float)(mp_now_ms() - wall0);
     tr.mark("finish");
+    return 0;
+}
+extern "C" int mp_results_on_device(mp_context *ctx, int on)
+{
+    if (!ctx) { mp_set_error("mp_results_on_device: null argument"); return MP_ERR_ARG; }
+    ctx->resultsOnDevice = on != 0;
     return 0;
 }
 extern "C" int mp_last_stats(mp_context *ctx, mp_stats *stats)

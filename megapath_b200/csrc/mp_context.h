@@ -154,6 +154,17 @@ struct mp_context {
     DevBuf dAligned, dGather;               // per-pair "placed by deep DP" flags; (dGather: unused scratch kept for mp_reserve)
     DevBuf dS2Counts, dS2Start, dS2Tasks, dS2Res;   // stage S2 on the device: kept seeds per read, task offsets, tasks, results
     DevBuf dRsSlotTasks, dRsSlotInfo, dRsFlag, dRsPos, dRsTasks, dRsInfo, dRsRec, dRsOut, dRsKeep, dRsKeepPos;   // stage S3 (mate rescue) on the device
+    // results of the last mp_align_pairs call that are still resident: dRes2[0], dRsOut[1], dS2Res[2] (mp_format_fastq reads them)
+    uint64_t resCount[3] = { 0, 0, 0 }; bool resValid = false;
+    bool resultsOnDevice = false;           // mp_results_on_device: mp_align_pairs skips the device-to-host copies of the result arrays
+    // FASTQ ingest / egress on the device (mp_fastq.cu)
+    bool fqBatch = false;                   // the uploaded batch came through mp_fastq_upload: text + record index are resident
+    uint64_t fqBase[2] = { 0, 0 }, fqBytes[2] = { 0, 0 };
+    DevBuf dFqText, dFqCnt, dFqCntPos, dFqLines, dFqRec, dFqFlags;
+    bool hasAnn = false; uint64_t annDnaLength = 0; uint32_t annGridEntries = 0, annNumTr = 0, annNumSeq = 0;
+    DevBuf dAnnGrid, dAnnTrStart, dAnnTrChr, dAnnNames, dAnnNameOff;
+    DevBuf dFmtKeys, dFmtGroups, dFmtRecLen, dFmtTail, dFmtLen, dFmtOff, dFmtOut;
+    uint64_t fmtBytes = 0; bool fmtReady = false;
 };
 
 // mp_index.cu

@@ -588,6 +588,7 @@ int mps_upload(mp_context *ctx, const uint32_t *queries, const uint32_t *readLen
     MP_CUDA(cudaGetLastError());
     ctx->hLens.assign(readLengths, readLengths + nReads);
     ctx->nReads = nReads; ctx->wpq = wpq; ctx->hasBatch = true; ctx->seeded = false;
+    ctx->fqBatch = false; ctx->resValid = false; ctx->fmtReady = false;
     return 0;
 }
 

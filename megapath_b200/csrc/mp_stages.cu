@@ -410,8 +410,8 @@ int mps_single_and_rescue(mp_context *ctx, const mp_align_params *P, mp_results 
     }
     tr.mark("  s2 dp + assemble (device)");
     if (S.resize(tot[0]) || HC.resize((size_t)cigArenaBase + tot[1])) return MP_ERR_CUDA;
-    if (tot[0]) MP_CUDA(cudaMemcpyAsync(S.data(), ctx->dS2Res.p, (size_t)tot[0] * sizeof(mp_single_result), cudaMemcpyDeviceToHost, st));
-    if (tot[1]) MP_CUDA(cudaMemcpyAsync(HC.data() + cigArenaBase, ctx->dCig.p, tot[1], cudaMemcpyDeviceToHost, st));
+    if (tot[0] && !ctx->resultsOnDevice) MP_CUDA(cudaMemcpyAsync(S.data(), ctx->dS2Res.p, (size_t)tot[0] * sizeof(mp_single_result), cudaMemcpyDeviceToHost, st));
+    if (tot[1] && !ctx->resultsOnDevice) MP_CUDA(cudaMemcpyAsync(HC.data() + cigArenaBase, ctx->dCig.p, tot[1], cudaMemcpyDeviceToHost, st));
     {
         unsigned long long hw[2];
         MP_CUDA(cudaMemcpyAsync(hw, dWork, sizeof hw, cudaMemcpyDeviceToHost, st));
@@ -492,8 +492,8 @@ int mps_single_and_rescue(mp_context *ctx, const mp_align_params *P, mp_results 
     tr.mark("  s3 dp + assemble (device)");
     PinnedBuf<mp_pair_result> &R = ctx->hRescued;
     if (R.resize(t3[2]) || HC.resize((size_t)cigArenaBase3 + t3[1])) return MP_ERR_CUDA;
-    if (t3[2]) MP_CUDA(cudaMemcpyAsync(R.data(), ctx->dRsOut.p, (size_t)t3[2] * sizeof(mp_pair_result), cudaMemcpyDeviceToHost, st));
-    if (t3[1]) MP_CUDA(cudaMemcpyAsync(HC.data() + cigArenaBase3, ctx->dCig.p, t3[1], cudaMemcpyDeviceToHost, st));
+    if (t3[2] && !ctx->resultsOnDevice) MP_CUDA(cudaMemcpyAsync(R.data(), ctx->dRsOut.p, (size_t)t3[2] * sizeof(mp_pair_result), cudaMemcpyDeviceToHost, st));
+    if (t3[1] && !ctx->resultsOnDevice) MP_CUDA(cudaMemcpyAsync(HC.data() + cigArenaBase3, ctx->dCig.p, t3[1], cudaMemcpyDeviceToHost, st));
     {
         unsigned long long hw[2];
         MP_CUDA(cudaMemcpyAsync(hw, dWork, sizeof hw, cudaMemcpyDeviceToHost, st));

@@ -39,18 +39,22 @@ fq1, fq2 = os.path.join(d, "r_1.fq"), os.path.join(d, "r_2.fq")
 exe = os.path.join(ROOT, "megapath_b200", "bin", "soap4")
 ini = os.path.join(ROOT, "megapath_b200", "ini", "soap4.ini")
 total = npairs * rep
-for T, ctxs, sink in ((16, 3, "/dev/null"), (16, 3, os.path.join(d, "our.out")), (8, 2, os.path.join(d, "our.out"))):
+cfgs = ((16, 3, "/dev/null", 0),) if os.environ.get("MP_THR_ALL") else ((16, 3, "/dev/null", 0), (16, 3, os.path.join(d, "our.out"), 0), (16, 3, "/dev/null", 1), (16, 3, os.path.join(d, "our.out"), 1))
+for T, ctxs, sink, host in cfgs:
     t0 = time.time()
     with open(sink, "wb") as fo:
         p = subprocess.run([exe, "pair", prefix, fq1, fq2, "-o", os.path.join(d, "ouro"), "-C", ini, "-L", "151", "-T", str(T), "-u", "750", "-F", "-nc"],
-                           stdout=fo, stderr=subprocess.PIPE, timeout=900, env=dict(os.environ, MP_CONTEXTS_PER_GPU=str(ctxs), MP_DRIVER_TIMING="1", **({"MP_TRACE": "2"} if os.environ.get("MP_THR_TRACE") else {})))
+                           stdout=fo, stderr=subprocess.PIPE, timeout=900, env=dict(os.environ, MP_CONTEXTS_PER_GPU=str(ctxs), MP_DRIVER_TIMING="1", **({"MP_HOST_IO": "1"} if host else {}), **({"MP_TRACE": "2"} if os.environ.get("MP_THR_TRACE") else {})))
     wall = time.time() - t0
     assert p.returncode == 0, p.stderr.decode()[-2000:]
     lines = p.stderr.decode().splitlines()
     loop = [float(l.split(":")[1].split()[0]) for l in lines if "Overall alignment time" in l][0]
     load = [l for l in lines if "Elapsed time on host" in l]
     tim = [l for l in lines if "[timing]" in l]
+    if os.environ.get("MP_THR_ALL"):
+        print("\n".join(l for l in lines if "[timing]" in l or "Elapsed time on host" in l), flush=True)
     if os.environ.get("MP_THR_TRACE"):
         print("\n".join([l for l in lines if "mp_trace" in l or "[timing]" in l][:70]), flush=True)
+    print([l for l in lines if "formatting on the" in l])
     print("-T %d, %d contexts, out=%s: wall %.1f s; batch loop %.2f s = %.2f M pairs/s; reader per batch %s; last batches %s" % (
         T, ctxs, sink, wall, loop, total / loop / 1e6, [l.split(":")[1].split()[0] for l in load[-4:-1]], tim[-4:]), flush=True)
