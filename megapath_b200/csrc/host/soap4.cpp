@@ -48,7 +48,7 @@ struct Options {
     std::string indexName, query1, query2, outputPrefix, iniFile;
     int maxReadLength = 120, insert_low = 1, insert_high = 500, outputBAM = 0, numCpuThreads = 4, device = 0;
     int megapathMode = 0, top = 95, ignoreComments = 0, alignmentType = 2, printMDNM = 0;
-    int numGpus = 1, contextsPerGpu = 2;       // extensions: -G <n> uses GPUs device..device+n-1; MP_CONTEXTS_PER_GPU overrides 2
+    int numGpus = 1, contextsPerGpu = 3;       // extensions: -G <n> uses GPUs device..device+n-1; MP_CONTEXTS_PER_GPU overrides 3
     int lsam = -1;                             // extension: -lsam <0|1> prints what `soap4 -F | fastq2lsam <0|1>` prints (cc/fastq2lsam.cpp)
 };
 
@@ -192,6 +192,7 @@ struct SeqReader {
     // A plain regular file is memory-mapped instead: the whole file is the buffer (nothing left to fill), the record parsers below work
     // on it unchanged, and load_batch can locate a batch's records and parse them with several threads (parse_mapped).
     bool mapped = false;
+    int fd = -1;                   // kept open beside the mapping: batches are staged with pread (no page faults on the source side)
     bool open(const std::string &path) {
         if (!getenv("MP_NO_MMAP")) {
             int fd = ::open(path.c_str(), O_RDONLY);
@@ -202,7 +203,7 @@ struct SeqReader {
                     if (m != MAP_FAILED) {
                         madvise(m, (size_t)sb.st_size, MADV_SEQUENTIAL);
                         base = (char *)m; pos = 0; end = (size_t)sb.st_size; eof = true; mapped = true;
-                        ::close(fd);
+                        this->fd = fd;
                         return true;
                     }
                 }
@@ -1073,6 +1074,7 @@ int main(int argc, char **argv)
     Options opt;
     if (!parse_args(argc, argv, opt)) return 1;
     const double t0 = now_s();
+    setenv("CUDA_MODULE_LOADING", "EAGER", 0);      // every kernel is loaded with the library, not at its first launch inside the batch loop
     Ini ini;
     std::string iniPath = opt.iniFile.empty() ? std::string(argv[0]) + ".ini" : opt.iniFile;
     if (!ini.load(iniPath)) { fprintf(stderr, "Failed to open config file ... %s\n", iniPath.c_str()); return 1; }
@@ -1108,7 +1110,10 @@ int main(int argc, char **argv)
     }
     if (const char *e = getenv("MP_CONTEXTS_PER_GPU")) { int v = atoi(e); if (v >= 1 && v <= 8) opt.contextsPerGpu = v; }
     const unsigned ioThreads = (unsigned)std::min(8, std::max(1, opt.numCpuThreads));
-    const unsigned stageThreads = (unsigned)std::min(16, std::max(1, opt.numCpuThreads));      // per mate file, while a batch is staged
+    // staging threads per mate file: four already move a batch in ~25 ms (measured: 2 -> 23.6, 4 -> 25.5, 8 -> 19, 16 -> 18 M pairs/s on 16
+    // cores; more only take the cores the context threads need to keep their GPU queues full)
+    unsigned stageThreads = (unsigned)std::min(4, std::max(1, opt.numCpuThreads));
+    if (const char *e = getenv("MP_STAGE_THREADS")) { const int v = atoi(e); if (v >= 1 && v <= 64) stageThreads = (unsigned)v; }
     // ---- FASTQ ingest and annotated-FASTQ egress on the device (mp_fastq_upload / mp_format_fastq): plain FASTQ files in, -F / -P text
     //      out.  Everything else (.gz, pipes, -b, -lsam, anything but strict four-line records) takes the host parser / formatter below.
     //      MP_HOST_IO=1 forces the host loops (tests compare the two). ----
@@ -1202,7 +1207,9 @@ int main(int argc, char **argv)
             auto run = [&](unsigned t) {
                 for (size_t k = t; k < n; k += T) {
                     const size_t blk = done + k, o = blk * B, len = std::min(B, window - o);
-                    memcpy(dst + o, beg + o, len);
+                    size_t got = 0;                                           // pread: the kernel copies from the page cache, no faults on a mapping
+                    while (r.fd >= 0 && got < len) { const ssize_t g = pread(r.fd, dst + o + got, len - got, (off_t)(r.pos + o + got)); if (g <= 0) break; got += (size_t)g; }
+                    if (got < len) memcpy(dst + o + got, beg + o + got, len - got);
                     cnt[blk] = (uint32_t)count_newlines(dst + o, len);
                 }
             };

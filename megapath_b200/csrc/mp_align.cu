@@ -582,10 +582,12 @@ extern "C" int mp_align_pairs(mp_context *ctx, const mp_align_params *params, mp
     tr.mark("deep_dp");
     if (int rc = mps_single_and_rescue(ctx, params, out, cells, tasksRun)) return rc;
     MP_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
+    // (on the context's own stream: a cudaMemcpy on the legacy default stream would wait for the work queued by every other context of
+    // the GPU -- their batches' kernels and, with device-side FASTQ I/O, transfers of hundreds of MB)
+    unsigned long long hc[16];
+    MP_CUDA(cudaMemcpyAsync(hc, ctx->dCounters.p, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
     MP_CUDA(cudaStreamSynchronize(ctx->stream));
     tr.mark("single+default dp");
-    unsigned long long hc[16];
-    MP_CUDA(cudaMemcpy(hc, ctx->dCounters.p, sizeof hc, cudaMemcpyDeviceToHost));
     mp_stats &S = ctx->stats;
     memset(&S, 0, sizeof S);
     S.n_occ = hc[2]; S.n_lf = hc[5] + hc[8]; S.n_sa = hc[3]; S.n_lkt = hc[4]; S.n_probe = hc[9]; S.n_text = hc[10];

@@ -39,6 +39,24 @@ fq1, fq2 = os.path.join(d, "r_1.fq"), os.path.join(d, "r_2.fq")
 exe = os.path.join(ROOT, "megapath_b200", "bin", "soap4")
 ini = os.path.join(ROOT, "megapath_b200", "ini", "soap4.ini")
 total = npairs * rep
+if os.environ.get("MP_THR_NCU"):
+    # launch list of the ingest / egress kernels of one run of the driver (per-launch times under ncu are cold-cache and serialised)
+    out = os.path.join(ROOT, "gpurun_out", "launches_cli_io.csv")
+    with open("/dev/null", "wb") as fo:
+        subprocess.run(["ncu", "--metrics", "gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", "regex:k_fq|k_fmt", "-c", "60", "--csv", "--log-file", out,
+                        exe, "pair", prefix, fq1, fq2, "-o", os.path.join(d, "ouro"), "-C", ini, "-L", "151", "-T", "16", "-u", "750", "-F", "-nc"],
+                       stdout=fo, stderr=subprocess.DEVNULL, timeout=900, env=dict(os.environ, MP_CONTEXTS_PER_GPU="1"))
+    print(open(out).read()[-3000:])
+    sys.exit(0)
+if os.environ.get("MP_THR_SWEEP"):
+    for ctxs, st, extra in ((3, 16, {}), (3, 8, {}), (3, 4, {}), (3, 4, {}), (3, 2, {}), (4, 4, {}), (2, 4, {}), (3, 8, {})):
+        with open("/dev/null", "wb") as fo:
+            p = subprocess.run([exe, "pair", prefix, fq1, fq2, "-o", os.path.join(d, "ouro"), "-C", ini, "-L", "151", "-T", "16", "-u", "750", "-F", "-nc"],
+                               stdout=fo, stderr=subprocess.PIPE, timeout=900, env=dict(os.environ, MP_CONTEXTS_PER_GPU=str(ctxs), MP_STAGE_THREADS=str(st), **extra))
+        lines = p.stderr.decode().splitlines()
+        loop = [float(l.split(":")[1].split()[0]) for l in lines if "Overall alignment time" in l][0]
+        print("contexts %d, stage threads %d %s: loop %.3f s = %.2f M pairs/s" % (ctxs, st, extra, loop, total / loop / 1e6), flush=True)
+    sys.exit(0)
 cfgs = ((16, 3, "/dev/null", 0),) if os.environ.get("MP_THR_ALL") else ((16, 3, "/dev/null", 0), (16, 3, os.path.join(d, "our.out"), 0), (16, 3, "/dev/null", 1), (16, 3, os.path.join(d, "our.out"), 1))
 for T, ctxs, sink, host in cfgs:
     t0 = time.time()

@@ -24,3 +24,5 @@ timeout 900 ncu --profile-from-start off --set full --import-source on --clock-c
 tail -2 gpurun_out/ncu_top3.log
 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_step_${tag}.csv python bench.py --profile-step --no-cpu-baseline > gpurun_out/ncu_ps.log 2>&1
 tail -1 gpurun_out/ncu_ps.log
+timeout 600 python tools/driver_throughput.py 16 2>&1 | tail -8 | cut -c1-400 > gpurun_out/driver_throughput_${tag}.txt; cat gpurun_out/driver_throughput_${tag}.txt
+MP_THR_NCU=1 timeout 600 python tools/driver_throughput.py 1 2>&1 | tail -3 | cut -c1-300
