@@ -203,10 +203,10 @@ __device__ int fq_atoi(const char *s, const char *e)
     return (int)sv;
 }
 
-template <bool W> struct Sink {
-    char *p; uint32_t n;
-    __device__ __forceinline__ void put(char c) { if (W) p[n] = c; ++n; }
-    __device__ void str(const char *s, uint32_t l) { if (W) for (uint32_t i = 0; i < l; ++i) p[n + i] = s[i]; n += l; }
+template <bool W> struct Sink {             // counts always; stores the first `cap` bytes when W
+    char *p; uint32_t n, cap;
+    __device__ __forceinline__ void put(char c) { if (W && n < cap) p[n] = c; ++n; }
+    __device__ void str(const char *s, uint32_t l) { if (W) for (uint32_t i = 0; i < l && n + i < cap; ++i) p[n + i] = s[i]; n += l; }
     __device__ void num(long long v) {
         char tmp[24]; int k = 0; const bool neg = v < 0; unsigned long long u = neg ? 0ull - (unsigned long long)v : (unsigned long long)v;
         do { tmp[k++] = (char)('0' + u % 10); u /= 10; } while (u);
@@ -217,10 +217,10 @@ template <bool W> struct Sink {
 
 // everything between the read name and the end of the header line (the driver's header_line: BGS-IO.cpp:1966-2091 with
 // getMappingFromHeader :1348-1371).  keys: the (sequence id, score) entries of this read end; best: their maximal score (>= 0).
-template <bool W> __device__ uint32_t fmt_tail(char *out, const char *comment, uint32_t commentLen, const int2 *__restrict__ keys, uint32_t G, int best,
+template <bool W> __device__ uint32_t fmt_tail(char *out, uint32_t cap, const char *comment, uint32_t commentLen, const int2 *__restrict__ keys, uint32_t G, int best,
                                                double top, const AnnDev &A)
 {
-    Sink<W> o = { out, 0 };
+    Sink<W> o = { out, 0, cap };
     if (commentLen == 6 && comment[0] == 'I' && comment[1] == 'G' && comment[2] == 'N' && comment[3] == 'O' && comment[4] == 'R' && comment[5] == 'E') {
         o.str("\tIGNORE\n", 8);
         return o.n;
@@ -291,8 +291,11 @@ __device__ __forceinline__ int fmt_best(const int2 *keys, uint32_t G)
     return best;
 }
 
-// one thread per read: size of its record; the even thread of a pair stores the pair's size under its stage (0 deep DP, 1 rescued, 2 other)
-__global__ void k_fmt_measure(FmtView V, uint32_t *__restrict__ tailLen, uint32_t *__restrict__ recLen, unsigned long long *__restrict__ lenAll)
+constexpr uint32_t FMT_SLOT = 64;          // header tails up to this size are composed once, by k_fmt_measure, and only copied by k_fmt_write
+// one thread per read: size of its record (and the header tail itself when it fits its slot); the even thread of a pair stores the pair's
+// size under its stage (0 deep DP, 1 rescued, 2 other)
+__global__ void k_fmt_measure(FmtView V, uint32_t *__restrict__ tailLen, uint32_t *__restrict__ recLen, unsigned long long *__restrict__ lenAll,
+                              char *__restrict__ tailText)
 {
     const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = id < V.nReads;
@@ -303,7 +306,7 @@ __global__ void k_fmt_measure(FmtView V, uint32_t *__restrict__ tailLen, uint32_
         const int2 *keys; uint32_t G;
         seg = fmt_group(V, id, keys, G);
         const uint32_t cl = V.ignoreComments ? 0 : R.commentLen;
-        const uint32_t tail = fmt_tail<false>(nullptr, text + R.hdr + R.commentOff, cl, keys, G, fmt_best(keys, G), V.top, V.A);
+        const uint32_t tail = fmt_tail<true>(tailText + (size_t)id * FMT_SLOT, FMT_SLOT, text + R.hdr + R.commentOff, cl, keys, G, fmt_best(keys, G), V.top, V.A);
         tailLen[id] = tail;
         mine = 1 + R.nameLen + tail + R.len + 3 + R.len + 1;
         recLen[id] = mine;
@@ -317,7 +320,7 @@ __global__ void k_fmt_measure(FmtView V, uint32_t *__restrict__ tailLen, uint32_
 
 // one warp per read
 __global__ void k_fmt_write(FmtView V, const uint32_t *__restrict__ tailLen, const uint32_t *__restrict__ recLen, const unsigned long long *__restrict__ off,
-                            char *__restrict__ out)
+                            const char *__restrict__ tailText, char *__restrict__ out)
 {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t nWarps = (gridDim.x * blockDim.x) >> 5;
@@ -329,10 +332,13 @@ __global__ void k_fmt_write(FmtView V, const uint32_t *__restrict__ tailLen, con
         const uint32_t p = id >> 1, nPairs = V.nReads >> 1;
         char *w = out + off[(uint64_t)seg * nPairs + p] + ((id & 1u) ? recLen[id - 1] : 0u);
         const uint32_t tail = tailLen[id];
-        if (lane == 0) {
-            w[0] = '@';
+        if (lane == 0) w[0] = '@';
+        if (tail <= FMT_SLOT) {
+            const char *ts = tailText + (size_t)id * FMT_SLOT;
+            for (uint32_t i = lane; i < tail; i += 32) w[1 + R.nameLen + i] = ts[i];
+        } else if (lane == 0) {                        // a long SCORE: list: composed again, in place
             const uint32_t cl = V.ignoreComments ? 0 : R.commentLen;
-            fmt_tail<true>(w + 1 + R.nameLen, text + R.hdr + R.commentOff, cl, keys, G, fmt_best(keys, G), V.top, V.A);
+            fmt_tail<true>(w + 1 + R.nameLen, 0xFFFFFFFFu, text + R.hdr + R.commentOff, cl, keys, G, fmt_best(keys, G), V.top, V.A);
         }
         for (uint32_t i = lane; i < R.nameLen; i += 32) w[1 + i] = text[R.hdr + 1 + i];
         char *ws = w + 1 + R.nameLen + tail;
@@ -454,7 +460,7 @@ extern "C" int mp_fastq_reserve(mp_context *ctx, uint64_t textBytes, uint32_t nP
         ctx->dFqRec.reserve((size_t)nReads * sizeof(FqRec)) || ctx->dFqFlags.reserve(16) ||
         ctx->dFmtKeys.reserve((size_t)(3 * nReads) * sizeof(int2)) || ctx->dFmtGroups.reserve((size_t)(4 * (uint64_t)nPairs + 2 * nReads) * 4) ||
         ctx->dFmtRecLen.reserve((size_t)nReads * 4) || ctx->dFmtTail.reserve((size_t)nReads * 4) || ctx->dFmtLen.reserve(((size_t)3 * nPairs + 1) * 8) ||
-        ctx->dFmtOff.reserve(((size_t)3 * nPairs + 1) * 8) || ctx->dFmtOut.reserve(outBytes) || ctx->dScanTmp.reserve((size_t)1 << 20)) return MP_ERR_CUDA;
+        ctx->dFmtOff.reserve(((size_t)3 * nPairs + 1) * 8) || ctx->dFmtOut.reserve(outBytes) || ctx->dFmtTailText.reserve((size_t)nReads * FMT_SLOT) || ctx->dScanTmp.reserve((size_t)1 << 20)) return MP_ERR_CUDA;
     return 0;
 }
 
@@ -497,7 +503,8 @@ extern "C" int mp_format_fastq(mp_context *ctx, const mp_format_params *F, uint6
     // keys: P1 | P2 | R1 | R2 | S ; groups: pStart pEnd rStart rEnd (per pair) sStart sEnd (per read)
     const size_t nKeys = 2 * nP + 2 * nR + nS + 1, nGroups = (size_t)4 * nPairs + (size_t)2 * nReads;
     if (ctx->dFmtKeys.reserve(nKeys * sizeof(int2)) || ctx->dFmtGroups.reserve(nGroups * 4) || ctx->dFmtRecLen.reserve((size_t)nReads * 4) ||
-        ctx->dFmtTail.reserve((size_t)nReads * 4) || ctx->dFmtLen.reserve(((size_t)3 * nPairs + 1) * 8) || ctx->dFmtOff.reserve(((size_t)3 * nPairs + 1) * 8)) return MP_ERR_CUDA;
+        ctx->dFmtTail.reserve((size_t)nReads * 4) || ctx->dFmtLen.reserve(((size_t)3 * nPairs + 1) * 8) || ctx->dFmtOff.reserve(((size_t)3 * nPairs + 1) * 8) ||
+        ctx->dFmtTailText.reserve((size_t)nReads * FMT_SLOT)) return MP_ERR_CUDA;
     int2 *kP1 = ctx->dFmtKeys.as<int2>(), *kP2 = kP1 + nP, *kR1 = kP2 + nP, *kR2 = kR1 + nR, *kS = kR2 + nR;
     uint32_t *g = ctx->dFmtGroups.as<uint32_t>();
     uint32_t *pStart = g, *pEnd = g + nPairs, *rStart = g + 2 * (size_t)nPairs, *rEnd = g + 3 * (size_t)nPairs, *sStart = g + 4 * (size_t)nPairs, *sEnd = sStart + nReads;
@@ -515,7 +522,7 @@ extern "C" int mp_format_fastq(mp_context *ctx, const mp_format_params *F, uint6
     unsigned long long *lenAll = ctx->dFmtLen.as<unsigned long long>(), *off = ctx->dFmtOff.as<unsigned long long>();
     const uint64_t nLen = (uint64_t)3 * nPairs;
     MP_CUDA(cudaMemsetAsync(lenAll + nLen, 0, 8, st));
-    (++g_mp_launches), k_fmt_measure<<<(nReads + 127) / 128, 128, 0, st>>>(V, ctx->dFmtTail.as<uint32_t>(), ctx->dFmtRecLen.as<uint32_t>(), lenAll);
+    (++g_mp_launches), k_fmt_measure<<<(nReads + 127) / 128, 128, 0, st>>>(V, ctx->dFmtTail.as<uint32_t>(), ctx->dFmtRecLen.as<uint32_t>(), lenAll, ctx->dFmtTailText.as<char>());
     if (scan_any(ctx, lenAll, off, nLen + 1)) return MP_ERR_CUDA;
     unsigned long long total = 0;
     MP_CUDA(cudaMemcpyAsync(&total, off + nLen, 8, cudaMemcpyDeviceToHost, st));
@@ -523,7 +530,7 @@ extern "C" int mp_format_fastq(mp_context *ctx, const mp_format_params *F, uint6
     MP_CUDA(cudaStreamSynchronize(st));
     if (ctx->dFmtOut.reserve((size_t)total + 16)) return MP_ERR_CUDA;
     int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    (++g_mp_launches), k_fmt_write<<<(unsigned)sms * 8, 256, 0, st>>>(V, ctx->dFmtTail.as<uint32_t>(), ctx->dFmtRecLen.as<uint32_t>(), off, ctx->dFmtOut.as<char>());
+    (++g_mp_launches), k_fmt_write<<<(unsigned)sms * 8, 256, 0, st>>>(V, ctx->dFmtTail.as<uint32_t>(), ctx->dFmtRecLen.as<uint32_t>(), off, ctx->dFmtTailText.as<char>(), ctx->dFmtOut.as<char>());
     MP_CUDA(cudaGetLastError());
     ctx->fmtBytes = total; ctx->fmtReady = true;
     *bytes = total;
