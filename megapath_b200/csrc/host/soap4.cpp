@@ -490,6 +490,54 @@ static void parallel_copy(char *dst, const char *src, size_t n, unsigned nThr)
     for (std::thread &x : th) x.join();
 }
 
+// One mate file's next batch: every 256 KiB block is copied into the staging buffer and its newlines are counted in the copy while
+// it is still in the cache -- one pass over the page cache.  -> records staged, 0 at the end of the file, -1: not for the device
+// path, -2: the window estimate did not hold (the caller locates the batch exactly, locate_records, and copies it then)
+static long stage_file(const SeqReader &r, double bytesPerRec, uint32_t maxRec, unsigned stageThreads, char *dst, size_t cap, size_t *bytes)
+{
+    const char *beg = r.base + r.pos, *lim = r.base + r.end;
+    *bytes = 0;
+    if (r.last != 0) return -1;
+    if (beg >= lim || maxRec == 0) return 0;
+    if (lim[-1] != '\n' || *beg != '@') return -1;
+    const size_t B = (size_t)1 << 18, remaining = (size_t)(lim - beg);
+    size_t window = std::min(remaining, (size_t)((double)maxRec * bytesPerRec * 1.02) + B), done = 0;
+    std::vector<uint32_t> cnt;
+    uint64_t lines = 0;
+    for (;;) {
+        if (window > cap) return -2;
+        const size_t nBlocks = (window + B - 1) / B, n = nBlocks - done;
+        cnt.resize(nBlocks);
+        const unsigned T = (unsigned)std::min<size_t>(stageThreads, std::max<size_t>(n, 1));
+        auto run = [&](unsigned t) {
+            for (size_t k = t; k < n; k += T) {
+                const size_t blk = done + k, o = blk * B, len = std::min(B, window - o);
+                size_t got = 0;                                           // pread: the kernel copies from the page cache, no faults on a mapping
+                while (r.fd >= 0 && got < len) { const ssize_t g = pread(r.fd, dst + o + got, len - got, (off_t)(r.pos + o + got)); if (g <= 0) break; got += (size_t)g; }
+                if (got < len) memcpy(dst + o + got, beg + o + got, len - got);
+                cnt[blk] = (uint32_t)count_newlines(dst + o, len);
+            }
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < T; ++t) th.emplace_back(run, t);
+        run(0);
+        for (std::thread &x : th) x.join();
+        lines = 0; for (uint32_t c : cnt) lines += c;
+        if (lines >= 4ull * maxRec || window == remaining) break;
+        done = window / B;                                               // the partial last block is copied and counted again
+        window = std::min(remaining, window + window / 8 + B);
+    }
+    if (lines < 4ull * maxRec && (lines & 3)) return -1;
+    const uint64_t nRec = std::min<uint64_t>(maxRec, lines / 4);
+    if (nRec == 0) return -1;
+    uint64_t need = 4 * nRec, pre = 0; size_t k = 0;
+    while (pre + cnt[k] < need) pre += cnt[k++];
+    const char *q = dst + k * B;
+    for (need -= pre; need; --need) q = (const char *)memchr(q, '\n', (size_t)(dst + window - q)) + 1;
+    *bytes = (size_t)(q - dst);
+    return (long)nRec;
+}
+
 static uint32_t load_batch(SeqReader &r1, SeqReader &r2, ReadBatch &b, uint32_t maxReads, unsigned packThreads = 4)
 {
     const double tSetup0 = now_s();
@@ -1057,6 +1105,26 @@ int main(int argc, char **argv)
         fwrite(out.data(), 1, out.size(), stdout);
         return 0;
     }
+    if (argc >= 5 && !strcmp(argv[1], "__stage")) {          // hidden: batch boundaries of the device-ingest staging (no GPU): __stage file maxRec threads [bytesPerRec]
+        SeqReader r; if (!r.open(argv[2])) { fprintf(stderr, "cannot open %s\n", argv[2]); return 1; }
+        if (!r.mapped) { printf("unmapped\n"); return 0; }
+        const uint32_t maxRec = (uint32_t)atoi(argv[3]); const unsigned thr = (unsigned)atoi(argv[4]);
+        double bpr = argc >= 6 ? atof(argv[5]) : 0;
+        for (;;) {
+            // exact location, then the fused copy + count with the running estimate: both must name the same byte range
+            size_t np = 0; const long n = locate_records(r, maxRec, thr, &np);
+            if (bpr <= 0) { SeqReader::View v; const char *nx = nullptr; if (r.pos < r.end && SeqReader::view_record(r.base + r.pos, r.base + r.end, v, &nx) == 1) bpr = (double)(nx - (r.base + r.pos)); else bpr = 64; }
+            const size_t cap = std::min<size_t>((size_t)((double)maxRec * bpr * 1.03) + ((size_t)2 << 18), r.end - r.pos + 64);
+            std::vector<char> dst(cap + 64);
+            size_t bytes = 0; const long m = stage_file(r, bpr, maxRec, thr, dst.data(), cap, &bytes);
+            const bool same = m > 0 && bytes == np - r.pos && !memcmp(dst.data(), r.base + r.pos, bytes);
+            printf("%ld %zu %ld %zu %d\n", n, np, m, bytes, same ? 1 : 0);
+            if (n <= 0) break;
+            bpr = (double)(np - r.pos) / (double)n;
+            r.pos = np;
+        }
+        return 0;
+    }
     if (argc >= 3 && !strcmp(argv[1], "__parse")) {
         SeqReader r; if (!r.open(argv[2])) { fprintf(stderr, "cannot open %s\n", argv[2]); return 1; }
         const bool generic = argc >= 4 && !strcmp(argv[3], "generic");
@@ -1186,52 +1254,6 @@ int main(int argc, char **argv)
     if (pinThread.joinable()) pinThread.join();
     Annotation ann;
     if (!ann.load(opt.indexName)) return 1;
-    // One mate file's next batch: every 256 KiB block is copied into the staging buffer and its newlines are counted in the copy while
-    // it is still in the cache -- one pass over the page cache.  -> records staged, 0 at the end of the file, -1: not for the device
-    // path, -2: the window estimate did not hold (the caller locates the batch exactly, locate_records, and copies it then)
-    auto stage_file = [&](const SeqReader &r, int m, uint32_t maxRec, char *dst, size_t cap, size_t *bytes) -> long {
-        const char *beg = r.base + r.pos, *lim = r.base + r.end;
-        *bytes = 0;
-        if (r.last != 0) return -1;
-        if (beg >= lim || maxRec == 0) return 0;
-        if (lim[-1] != '\n' || *beg != '@') return -1;
-        const size_t B = (size_t)1 << 18, remaining = (size_t)(lim - beg);
-        size_t window = std::min(remaining, (size_t)((double)maxRec * bytesPerRec[m] * 1.02) + B), done = 0;
-        std::vector<uint32_t> cnt;
-        uint64_t lines = 0;
-        for (;;) {
-            if (window > cap) return -2;
-            const size_t nBlocks = (window + B - 1) / B, n = nBlocks - done;
-            cnt.resize(nBlocks);
-            const unsigned T = (unsigned)std::min<size_t>(stageThreads, std::max<size_t>(n, 1));
-            auto run = [&](unsigned t) {
-                for (size_t k = t; k < n; k += T) {
-                    const size_t blk = done + k, o = blk * B, len = std::min(B, window - o);
-                    size_t got = 0;                                           // pread: the kernel copies from the page cache, no faults on a mapping
-                    while (r.fd >= 0 && got < len) { const ssize_t g = pread(r.fd, dst + o + got, len - got, (off_t)(r.pos + o + got)); if (g <= 0) break; got += (size_t)g; }
-                    if (got < len) memcpy(dst + o + got, beg + o + got, len - got);
-                    cnt[blk] = (uint32_t)count_newlines(dst + o, len);
-                }
-            };
-            std::vector<std::thread> th;
-            for (unsigned t = 1; t < T; ++t) th.emplace_back(run, t);
-            run(0);
-            for (std::thread &x : th) x.join();
-            lines = 0; for (uint32_t c : cnt) lines += c;
-            if (lines >= 4ull * maxRec || window == remaining) break;
-            done = window / B;                                               // the partial last block is copied and counted again
-            window = std::min(remaining, window + window / 8 + B);
-        }
-        if (lines < 4ull * maxRec && (lines & 3)) return -1;
-        const uint64_t nRec = std::min<uint64_t>(maxRec, lines / 4);
-        if (nRec == 0) return -1;
-        uint64_t need = 4 * nRec, pre = 0; size_t k = 0;
-        while (pre + cnt[k] < need) pre += cnt[k++];
-        const char *q = dst + k * B;
-        for (need -= pre; need; --need) q = (const char *)memchr(q, '\n', (size_t)(dst + window - q)) + 1;
-        *bytes = (size_t)(q - dst);
-        return (long)nRec;
-    };
     // -> 1: the next batch staged in page-locked memory (file positions advanced), 0: end of both files, -1: not for the device path
     auto stage_raw = [&](RawBatch &rb) -> int {
         static const bool ltiming = getenv("MP_DRIVER_TIMING") != nullptr;
@@ -1242,8 +1264,8 @@ int main(int argc, char **argv)
         rb.pin = pc.first; rb.pinCap = pc.second; rb.off2 = cap1;
         const double ts1 = now_s();
         long n1 = 0, n2 = 0;
-        std::thread t2([&] { n2 = stage_file(r2, 1, maxNumQueries / 2, rb.pin + rb.off2, cap2, &rb.bytes2); });
-        n1 = stage_file(r1, 0, (maxNumQueries + 1) / 2, rb.pin, cap1, &rb.bytes1);
+        std::thread t2([&] { n2 = stage_file(r2, bytesPerRec[1], maxNumQueries / 2, stageThreads, rb.pin + rb.off2, cap2, &rb.bytes2); });
+        n1 = stage_file(r1, bytesPerRec[0], (maxNumQueries + 1) / 2, stageThreads, rb.pin, cap1, &rb.bytes1);
         t2.join();
         const double ts2 = now_s();
         size_t p1 = r1.pos + rb.bytes1, p2 = r2.pos + rb.bytes2;

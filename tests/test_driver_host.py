@@ -195,3 +195,50 @@ def test_parallel_mapped_parser_equals_sequential(tmp_path, kind):
     want = _pack(f1, f2, 131, tmp_path / "b.bin", 6, {"MP_NO_MMAP": "1"})
     assert np.frombuffer(want[:4], dtype=np.uint32)[0] == 2 * npairs
     assert got == want
+
+
+# ---- device ingest: the staging step that hands mp_fastq_upload the exact byte range of a batch (locate_records / stage_file) ----
+def _stage(path, max_rec, threads, bpr=None):
+    out = subprocess.run([EXE, "__stage", str(path), str(max_rec), str(threads)] + ([str(bpr)] if bpr else []), capture_output=True, check=True, timeout=120).stdout
+    return [tuple(int(x) for x in l.split()) for l in out.decode().splitlines()]
+
+
+@pytest.mark.parametrize("max_rec,threads", [(1000, 1), (1000, 5), (4096, 3), (100000, 4)])
+def test_staging_names_the_byte_range_of_every_batch(tmp_path, max_rec, threads):
+    """Variable-length records (names that grow, reads of 30 - 250 bases, comments): every batch is exactly max_rec records (the
+    reference's batch size decides the order of stdout), located by block-wise newline counts with any number of threads; the fused
+    copy + count pass finds the same range and copies it faithfully, or asks for the exact path (-2) when its estimate is too small."""
+    rng = np.random.default_rng(max_rec + threads)
+    n = 23456
+    lens = rng.integers(30, 251, size=n)
+    recs = [b"@read%d/1%s\n%s\n+\n%s\n" % (i, b" SCORE:5;5,x;" if i % 7 == 0 else b"", b"ACGT"[i % 4:i % 4 + 1] * int(lens[i]), b"I" * int(lens[i])) for i in range(n)]
+    p = tmp_path / "v.fq"
+    p.write_bytes(b"".join(recs))
+    ends = np.cumsum([len(r) for r in recs])
+    rows = _stage(p, max_rec, threads)
+    pos, k = 0, 0
+    for (nloc, newpos, nst, nbytes, same) in rows[:-1]:
+        want = min(max_rec, n - k)
+        assert nloc == want and newpos == ends[k + want - 1]
+        assert nst == -2 or (nst == want and nbytes == newpos - pos and same == 1)
+        pos, k = newpos, k + want
+    assert k == n and rows[-1][0] == 0 and rows[-1][2] == 0
+    assert sum(1 for r in rows[:-1] if r[2] > 0) >= len(rows) // 2          # the estimate holds for most batches
+
+
+def test_staging_with_a_bad_estimate_asks_for_the_exact_path(tmp_path):
+    recs = [b"@r%d\n%s\n+\n%s\n" % (i, b"A" * 200, b"I" * 200) for i in range(5000)]
+    p = tmp_path / "w.fq"
+    p.write_bytes(b"".join(recs))
+    rows = _stage(p, 4000, 3, bpr=40.0)             # five times too small: the window cannot hold 4000 records within its capacity
+    assert rows[0][0] == 4000 and rows[0][2] == -2
+
+
+@pytest.mark.parametrize("name", ["no_final_newline", "multiline", "garbage_prefix", "fasta", "qual_short_continues"])
+def test_staging_refuses_what_the_kernels_cannot_index(tmp_path, name):
+    """Files that are not plain four-line FASTQ from their first record on never reach the device path (-1); CRLF files pass the
+    newline count and are refused by k_fq_count on the device (tests/test_gpu_fastq_io.py)."""
+    p = tmp_path / (name + ".fq")
+    p.write_bytes(CASES[name])
+    rows = _stage(p, 10, 2)
+    assert rows[0][0] == -1 and rows[0][2] == -1
