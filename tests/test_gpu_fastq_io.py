@@ -201,3 +201,18 @@ def test_format_fastq_through_the_library(workdir, small_ref):
     with pytest.raises(mp.MegapathError):
         c.format_fastq()
     c.close()
+
+
+@needs_ref
+def test_device_io_on_two_gpus(workdir, small_ref):
+    """-G 2: batches dealt to the contexts of two GPUs (staging buffers are page-locked once, for every device) print the stream
+    one GPU prints."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    fq1, fq2 = make_reads(workdir, small_ref, "dio_g2", 4000, 100, seed=17, model="divergent", one_random=0.10, unalignable=0.05)
+    env = {"MP_BATCH_READS": "1024"}
+    one, _ = run_driver(workdir, small_ref["prefix"], fq1, fq2, "dio_g1", 101, "soap4.ini", ["-F", "-nc"], env)
+    two, err = run_driver(workdir, small_ref["prefix"], fq1, fq2, "dio_g2", 101, "soap4.ini", ["-F", "-nc", "-G", "2"], env)
+    assert "formatting on the device" in err
+    assert two == one, first_diff(two, one)
