@@ -796,6 +796,7 @@ def run(args, saved_stdout):
             # e2e_cli: what the reference's own number means (SOAP4.cpp:613): FASTQ files in, annotated FASTQ out, the batch loop's wall time
             try:
                 cli = sample_prefix(args, "cli", args.cli_pairs)
+                os.sync()      # index and read files were written minutes ago at most: their write-back must not run beside the timed process
                 loop_s, wall_s, cli_err = run_our_soap4(args, prefix, cli, os.path.join(d, "ourout_cli"), ncores, sink=os.path.join(d, "ourout_cli.stdout.fq"))
                 sys.stderr.write("".join(l + "\n" for l in cli_err.splitlines() if "[timing]" in l or "Elapsed time on host" in l or "[mp_trace]" in l))
                 out_bytes = os.path.getsize(os.path.join(d, "ourout_cli.stdout.fq"))

@@ -1206,7 +1206,10 @@ int main(int argc, char **argv)
         const size_t est = (size_t)((double)(maxNumQueries / 2) * bytesPerRec[m] * 1.03) + ((size_t)2 << 18);
         return (std::min<size_t>(est, r.end - r.pos + 64) + 63) & ~(size_t)63;
     };
-    auto batch_need = [&]() -> size_t { return window_cap(0, r1) + window_cap(1, r2) + (size_t)maxNumQueries * 64 + ((size_t)1 << 20); };
+    // the formatted text of a batch comes back into the buffer its input came from: room for what the headers grow by (64 bytes per read to
+    // begin with; batches with long SCORE: lists raise it for the buffers taken after them)
+    std::atomic<size_t> growPerRead(64);
+    auto batch_need = [&]() -> size_t { return window_cap(0, r1) + window_cap(1, r2) + (size_t)maxNumQueries * growPerRead.load() + ((size_t)1 << 20); };
     std::thread pinThread;
     if (deviceIO) {
         SeqReader::View v; const char *nx = nullptr;
@@ -1259,7 +1262,7 @@ int main(int argc, char **argv)
         static const bool ltiming = getenv("MP_DRIVER_TIMING") != nullptr;
         const double ts0 = now_s();
         const size_t cap1 = window_cap(0, r1), cap2 = window_cap(1, r2);
-        auto pc = pin_take(cap1 + cap2 + (size_t)maxNumQueries * 64 + ((size_t)1 << 20));
+        auto pc = pin_take(cap1 + cap2 + (size_t)maxNumQueries * growPerRead.load() + ((size_t)1 << 20));
         if (!pc.first) { fprintf(stderr, "%s\n", mp_last_error()); exit(1); }
         rb.pin = pc.first; rb.pinCap = pc.second; rb.off2 = cap1;
         const double ts1 = now_s();
@@ -1276,7 +1279,7 @@ int main(int argc, char **argv)
             l2.join();
             if (n1 > 0 && n2 > 0) {
                 rb.bytes1 = p1 - r1.pos; rb.bytes2 = p2 - r2.pos; rb.off2 = (rb.bytes1 + 63) & ~(size_t)63;
-                const size_t need = rb.off2 + rb.bytes2 + (size_t)maxNumQueries * 64 + ((size_t)1 << 20);
+                const size_t need = rb.off2 + rb.bytes2 + (size_t)maxNumQueries * growPerRead.load() + ((size_t)1 << 20);
                 if (need > rb.pinCap) {
                     pin_give(rb.pin, rb.pinCap);
                     pc = pin_take(need);
@@ -1490,6 +1493,11 @@ int main(int argc, char **argv)
                     const double tf0 = now_s();
                     int rc = mp_format_fastq(gpu, &F, &ob);
                     const double tf1 = now_s();
+                    if (!rc && ob > j->raw.bytes1 + j->raw.bytes2) {       // later buffers are sized for this growth (+ 25 %)
+                        const size_t g = (size_t)((ob - j->raw.bytes1 - j->raw.bytes2) / std::max<uint32_t>(numQueries, 1u)), want = g + g / 4 + 16;
+                        size_t cur = growPerRead.load();
+                        while (want > cur && !growPerRead.compare_exchange_weak(cur, want)) {}
+                    }
                     if (!rc && ob > j->raw.pinCap) {
                         pin_give(j->raw.pin, j->raw.pinCap); j->raw.pin = nullptr;
                         auto pc = pin_take(ob + (ob >> 4));

@@ -163,7 +163,7 @@ struct mp_context {
     DevBuf dFqText, dFqCnt, dFqCntPos, dFqLines, dFqRec, dFqFlags;
     bool hasAnn = false; uint64_t annDnaLength = 0; uint32_t annGridEntries = 0, annNumTr = 0, annNumSeq = 0;
     DevBuf dAnnGrid, dAnnTrStart, dAnnTrChr, dAnnNames, dAnnNameOff;
-    DevBuf dFmtKeys, dFmtGroups, dFmtRecLen, dFmtTail, dFmtTailText, dFmtLen, dFmtOff, dFmtOut;
+    DevBuf dFmtKeys, dFmtGroups, dFmtRecLen, dFmtTail, dFmtTailText, dFmtSeg, dFmtDst, dFmtLen, dFmtOff, dFmtOut;
     uint64_t fmtBytes = 0; bool fmtReady = false;
 };
 

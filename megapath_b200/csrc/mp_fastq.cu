@@ -295,7 +295,7 @@ constexpr uint32_t FMT_SLOT = 64;          // header tails up to this size are c
 // one thread per read: size of its record (and the header tail itself when it fits its slot); the even thread of a pair stores the pair's
 // size under its stage (0 deep DP, 1 rescued, 2 other)
 __global__ void k_fmt_measure(FmtView V, uint32_t *__restrict__ tailLen, uint32_t *__restrict__ recLen, unsigned long long *__restrict__ lenAll,
-                              char *__restrict__ tailText)
+                              char *__restrict__ tailText, uint8_t *__restrict__ segOf)
 {
     const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = id < V.nReads;
@@ -310,6 +310,7 @@ __global__ void k_fmt_measure(FmtView V, uint32_t *__restrict__ tailLen, uint32_
         tailLen[id] = tail;
         mine = 1 + R.nameLen + tail + R.len + 3 + R.len + 1;
         recLen[id] = mine;
+        segOf[id] = (uint8_t)seg;
     }
     const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
     if (live && !(id & 1u)) {
@@ -318,8 +319,49 @@ __global__ void k_fmt_measure(FmtView V, uint32_t *__restrict__ tailLen, uint32_
     }
 }
 
+// the base soap4 prints for four input characters at once ("ACGT"[charMap[c]], IndexHandler.cpp:26-45): clearing bit 5 folds exactly the
+// lower-case letters onto their upper-case ones, then C -> C, G / N -> G, T / U -> T, anything else -> A
+__device__ __forceinline__ uint32_t fq_out4(uint32_t v)
+{
+    const uint32_t x = v & 0xDFDFDFDFu;
+    const uint32_t mC = __vcmpeq4(x, 0x43434343u), mG = __vcmpeq4(x, 0x47474747u) | __vcmpeq4(x, 0x4E4E4E4Eu),
+                   mT = __vcmpeq4(x, 0x54545454u) | __vcmpeq4(x, 0x55555555u);
+    return 0x41414141u ^ (mC & 0x02020202u) ^ (mG & 0x06060606u) ^ (mT & 0x15151515u);
+}
+__device__ __forceinline__ char fq_out1(unsigned char c) { return "ACGT"[fq_code(c)]; }
+// n bytes from src to dst by one warp: the bytes up to dst's next word boundary and the last few one by one, the rest as aligned 32-bit
+// stores whose source word is funnel-shifted out of two aligned loads (src and dst are misaligned independently); MAP: through fq_out4
+template <bool MAP> __device__ __forceinline__ void warp_copy(char *dst, const char *src, uint32_t n, uint32_t lane)
+{
+    uint32_t head = (4u - (uint32_t)((uintptr_t)dst & 3u)) & 3u;
+    if (head > n) head = n;
+    if (lane < head) dst[lane] = MAP ? fq_out1((unsigned char)src[lane]) : src[lane];
+    const uint32_t nw = (n - head) >> 2;
+    const char *s = src + head;
+    const uint32_t mis = (uint32_t)((uintptr_t)s & 3u);
+    const uint32_t *sa = (const uint32_t *)(s - mis);
+    uint32_t *d = (uint32_t *)(dst + head);
+    for (uint32_t w = lane; w < nw; w += 32) {
+        uint32_t v = sa[w];
+        if (mis) v = __funnelshift_r(v, sa[w + 1], mis * 8);
+        d[w] = MAP ? fq_out4(v) : v;
+    }
+    const uint32_t done = head + nw * 4;
+    if (lane < n - done) dst[done + lane] = MAP ? fq_out1((unsigned char)src[done + lane]) : src[done + lane];
+}
+
+// one thread per read: where its record starts in the output (its pair's offset under its stage; mate 2 behind mate 1), so that the
+// writer's warps start copying after one round of independent loads instead of a chain of dependent ones
+__global__ void k_fmt_offsets(uint32_t nReads, const uint8_t *__restrict__ segOf, const uint32_t *__restrict__ recLen, const unsigned long long *__restrict__ off,
+                              unsigned long long *__restrict__ dstOf)
+{
+    const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= nReads) return;
+    dstOf[id] = off[(uint64_t)segOf[id] * (nReads >> 1) + (id >> 1)] + ((id & 1u) ? recLen[id - 1] : 0u);
+}
+
 // one warp per read
-__global__ void k_fmt_write(FmtView V, const uint32_t *__restrict__ tailLen, const uint32_t *__restrict__ recLen, const unsigned long long *__restrict__ off,
+__global__ void k_fmt_write(FmtView V, const uint32_t *__restrict__ tailLen, const unsigned long long *__restrict__ dstOf,
                             const char *__restrict__ tailText, char *__restrict__ out)
 {
     const uint32_t lane = threadIdx.x & 31u;
@@ -327,25 +369,22 @@ __global__ void k_fmt_write(FmtView V, const uint32_t *__restrict__ tailLen, con
     for (uint32_t id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; id < V.nReads; id += nWarps) {
         const FqRec R = V.rec[id];
         const char *text = V.text + ((id & 1u) ? V.base1 : 0);
-        const int2 *keys; uint32_t G;
-        const int seg = fmt_group(V, id, keys, G);
-        const uint32_t p = id >> 1, nPairs = V.nReads >> 1;
-        char *w = out + off[(uint64_t)seg * nPairs + p] + ((id & 1u) ? recLen[id - 1] : 0u);
+        char *w = out + dstOf[id];
         const uint32_t tail = tailLen[id];
         if (lane == 0) w[0] = '@';
-        if (tail <= FMT_SLOT) {
-            const char *ts = tailText + (size_t)id * FMT_SLOT;
-            for (uint32_t i = lane; i < tail; i += 32) w[1 + R.nameLen + i] = ts[i];
-        } else if (lane == 0) {                        // a long SCORE: list: composed again, in place
+        if (tail <= FMT_SLOT) warp_copy<false>(w + 1 + R.nameLen, tailText + (size_t)id * FMT_SLOT, tail, lane);
+        else if (lane == 0) {                        // a long SCORE: list: composed again, in place
+            const int2 *keys; uint32_t G;
+            fmt_group(V, id, keys, G);
             const uint32_t cl = V.ignoreComments ? 0 : R.commentLen;
             fmt_tail<true>(w + 1 + R.nameLen, 0xFFFFFFFFu, text + R.hdr + R.commentOff, cl, keys, G, fmt_best(keys, G), V.top, V.A);
         }
-        for (uint32_t i = lane; i < R.nameLen; i += 32) w[1 + i] = text[R.hdr + 1 + i];
+        warp_copy<false>(w + 1, text + R.hdr + 1, R.nameLen, lane);
         char *ws = w + 1 + R.nameLen + tail;
-        for (uint32_t i = lane; i < R.len; i += 32) ws[i] = "ACGT"[fq_code((unsigned char)text[R.seq + i])];
+        warp_copy<true>(ws, text + R.seq, R.len, lane);
         if (lane < 3) ws[R.len + lane] = lane == 1 ? '+' : '\n';
         char *wq = ws + R.len + 3;
-        for (uint32_t i = lane; i < R.len; i += 32) wq[i] = text[R.qual + i];
+        warp_copy<false>(wq, text + R.qual, R.len, lane);
         if (lane == 0) wq[R.len] = '\n';
     }
 }
@@ -460,7 +499,7 @@ extern "C" int mp_fastq_reserve(mp_context *ctx, uint64_t textBytes, uint32_t nP
         ctx->dFqRec.reserve((size_t)nReads * sizeof(FqRec)) || ctx->dFqFlags.reserve(16) ||
         ctx->dFmtKeys.reserve((size_t)(3 * nReads) * sizeof(int2)) || ctx->dFmtGroups.reserve((size_t)(4 * (uint64_t)nPairs + 2 * nReads) * 4) ||
         ctx->dFmtRecLen.reserve((size_t)nReads * 4) || ctx->dFmtTail.reserve((size_t)nReads * 4) || ctx->dFmtLen.reserve(((size_t)3 * nPairs + 1) * 8) ||
-        ctx->dFmtOff.reserve(((size_t)3 * nPairs + 1) * 8) || ctx->dFmtOut.reserve(outBytes) || ctx->dFmtTailText.reserve((size_t)nReads * FMT_SLOT) || ctx->dScanTmp.reserve((size_t)1 << 20)) return MP_ERR_CUDA;
+        ctx->dFmtOff.reserve(((size_t)3 * nPairs + 1) * 8) || ctx->dFmtOut.reserve(outBytes) || ctx->dFmtTailText.reserve((size_t)nReads * FMT_SLOT) || ctx->dFmtSeg.reserve((size_t)nReads) || ctx->dFmtDst.reserve((size_t)nReads * 8) || ctx->dScanTmp.reserve((size_t)1 << 20)) return MP_ERR_CUDA;
     return 0;
 }
 
@@ -504,7 +543,7 @@ extern "C" int mp_format_fastq(mp_context *ctx, const mp_format_params *F, uint6
     const size_t nKeys = 2 * nP + 2 * nR + nS + 1, nGroups = (size_t)4 * nPairs + (size_t)2 * nReads;
     if (ctx->dFmtKeys.reserve(nKeys * sizeof(int2)) || ctx->dFmtGroups.reserve(nGroups * 4) || ctx->dFmtRecLen.reserve((size_t)nReads * 4) ||
         ctx->dFmtTail.reserve((size_t)nReads * 4) || ctx->dFmtLen.reserve(((size_t)3 * nPairs + 1) * 8) || ctx->dFmtOff.reserve(((size_t)3 * nPairs + 1) * 8) ||
-        ctx->dFmtTailText.reserve((size_t)nReads * FMT_SLOT)) return MP_ERR_CUDA;
+        ctx->dFmtTailText.reserve((size_t)nReads * FMT_SLOT) || ctx->dFmtSeg.reserve((size_t)nReads) || ctx->dFmtDst.reserve((size_t)nReads * 8)) return MP_ERR_CUDA;
     int2 *kP1 = ctx->dFmtKeys.as<int2>(), *kP2 = kP1 + nP, *kR1 = kP2 + nP, *kR2 = kR1 + nR, *kS = kR2 + nR;
     uint32_t *g = ctx->dFmtGroups.as<uint32_t>();
     uint32_t *pStart = g, *pEnd = g + nPairs, *rStart = g + 2 * (size_t)nPairs, *rEnd = g + 3 * (size_t)nPairs, *sStart = g + 4 * (size_t)nPairs, *sEnd = sStart + nReads;
@@ -522,7 +561,7 @@ extern "C" int mp_format_fastq(mp_context *ctx, const mp_format_params *F, uint6
     unsigned long long *lenAll = ctx->dFmtLen.as<unsigned long long>(), *off = ctx->dFmtOff.as<unsigned long long>();
     const uint64_t nLen = (uint64_t)3 * nPairs;
     MP_CUDA(cudaMemsetAsync(lenAll + nLen, 0, 8, st));
-    (++g_mp_launches), k_fmt_measure<<<(nReads + 127) / 128, 128, 0, st>>>(V, ctx->dFmtTail.as<uint32_t>(), ctx->dFmtRecLen.as<uint32_t>(), lenAll, ctx->dFmtTailText.as<char>());
+    (++g_mp_launches), k_fmt_measure<<<(nReads + 127) / 128, 128, 0, st>>>(V, ctx->dFmtTail.as<uint32_t>(), ctx->dFmtRecLen.as<uint32_t>(), lenAll, ctx->dFmtTailText.as<char>(), ctx->dFmtSeg.as<uint8_t>());
     if (scan_any(ctx, lenAll, off, nLen + 1)) return MP_ERR_CUDA;
     unsigned long long total = 0;
     MP_CUDA(cudaMemcpyAsync(&total, off + nLen, 8, cudaMemcpyDeviceToHost, st));
@@ -530,7 +569,8 @@ extern "C" int mp_format_fastq(mp_context *ctx, const mp_format_params *F, uint6
     MP_CUDA(cudaStreamSynchronize(st));
     if (ctx->dFmtOut.reserve((size_t)total + 16)) return MP_ERR_CUDA;
     int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    (++g_mp_launches), k_fmt_write<<<(unsigned)sms * 8, 256, 0, st>>>(V, ctx->dFmtTail.as<uint32_t>(), ctx->dFmtRecLen.as<uint32_t>(), off, ctx->dFmtTailText.as<char>(), ctx->dFmtOut.as<char>());
+    (++g_mp_launches), k_fmt_offsets<<<(nReads + 255) / 256, 256, 0, st>>>(nReads, ctx->dFmtSeg.as<uint8_t>(), ctx->dFmtRecLen.as<uint32_t>(), off, ctx->dFmtDst.as<unsigned long long>());
+    (++g_mp_launches), k_fmt_write<<<(unsigned)sms * 8, 256, 0, st>>>(V, ctx->dFmtTail.as<uint32_t>(), ctx->dFmtDst.as<unsigned long long>(), ctx->dFmtTailText.as<char>(), ctx->dFmtOut.as<char>());
     MP_CUDA(cudaGetLastError());
     ctx->fmtBytes = total; ctx->fmtReady = true;
     *bytes = total;

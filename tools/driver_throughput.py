@@ -36,6 +36,7 @@ for mate in (0, 1):
         for _ in range(rep):
             f.write(blob)
 fq1, fq2 = os.path.join(d, "r_1.fq"), os.path.join(d, "r_2.fq")
+os.sync()          # the read files were written a moment ago: without this their write-back runs beside the first timed run
 exe = os.path.join(ROOT, "megapath_b200", "bin", "soap4")
 ini = os.path.join(ROOT, "megapath_b200", "ini", "soap4.ini")
 total = npairs * rep
