@@ -15,6 +15,12 @@
 //   unpaired bookkeeping     filterOutUnpairedSingleReads, DPSOutputUnpairedAlignment
 //                            SeedPool.cpp:267-322; DV-DPfunctions.cpp:841-920
 //   BAM output (-b)          bam_out.h
+//
+// Two I/O paths.  Plain FASTQ files with -F / -P (no -b, no -lsam): the driver only stages each batch's bytes in page-locked memory
+// (stage_file / locate_records) and writes the finished text; records are indexed and packed, and the output text is composed, by
+// kernels (mp_fastq_upload, mp_format_fastq; csrc/mp_fastq.cu).  Everything else -- .gz, pipes, BAM, -lsam, text that is not strict
+// four-line FASTQ -- goes through the host parser (SeqReader, load_batch) and formatter (header_line, output_pair, output_unpaired)
+// below, which are also what MP_HOST_IO=1 forces and what the device path is tested against.
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -1224,7 +1230,6 @@ int main(int argc, char **argv)
     }
 
     // one index replica per GPU (loaded in parallel), contextsPerGpu contexts sharing it (mp_clone)
-    if (const char *e = getenv("MP_CONTEXTS_PER_GPU")) { int v = atoi(e); if (v >= 1 && v <= 8) opt.contextsPerGpu = v; }
     fprintf(stderr, "[Main] loading index into device...\n");
     std::vector<mp_context *> owners(opt.numGpus, nullptr), contexts;
     {
