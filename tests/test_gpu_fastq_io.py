@@ -216,3 +216,44 @@ def test_device_io_on_two_gpus(workdir, small_ref):
     two, err = run_driver(workdir, small_ref["prefix"], fq1, fq2, "dio_g2", 101, "soap4.ini", ["-F", "-nc", "-G", "2"], env)
     assert "formatting on the device" in err
     assert two == one, first_diff(two, one)
+
+
+@needs_ref
+def test_device_io_long_score_lists(workdir):
+    """Eight near-identical sequences with long names: every read has a SCORE: list of several entries, far longer than the 64-byte
+    slot k_fmt_measure composes header tails in, so k_fmt_write's in-place path (and the staging buffer's growth allowance) is what
+    prints them.  Device == host formatter byte for byte, == reference after the canonical sort."""
+    import shutil
+    from conftest import REF_DIR
+    from tools import synth
+    rng = np.random.default_rng(99)
+    base = synth.ALPHA[rng.integers(0, 4, size=30000)]
+    d = os.path.join(workdir, "copies")
+    os.makedirs(d, exist_ok=True)
+    fa = os.path.join(d, "copies.fa")
+    seqs = []
+    with open(fa, "wb") as f:
+        for i in range(8):
+            s = base.copy()
+            m = rng.random(len(s)) < 0.004
+            s[m] = synth.ALPHA[rng.integers(0, 4, size=int(m.sum()))]
+            seqs.append(s)
+            f.write(b">copy_%d_of_the_same_genome_with_a_long_description_line strain %d\n" % (i + 1, i) + s.tobytes() + b"\n")
+    shutil.copy(os.path.join(REF_DIR, "2bwt-builder.ini"), os.path.join(d, "2bwt-builder.ini"))
+    subprocess.check_call([os.path.join(REF_DIR, "2bwt-builder"), fa], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    seq = np.concatenate(seqs)
+    bounds = np.arange(9, dtype=np.int64) * 30000
+    r1, r2 = synth.make_pairs(seq, bounds, 1500, 100, 5, model="clean")
+    p = os.path.join(d, "cp")
+    synth.write_fastq(p + "_1.fq", r1, 1)
+    synth.write_fastq(p + "_2.fq", r2, 2)
+    flags = ["-F", "-nc", "-top", "95"]
+    dev, err = run_driver(d, fa + ".index", p + "_1.fq", p + "_2.fq", "cp_d", 101, "soap4-nt2.ini", flags)
+    assert "formatting on the device" in err
+    host, _ = run_driver(d, fa + ".index", p + "_1.fq", p + "_2.fq", "cp_h", 101, "soap4-nt2.ini", flags, {"MP_HOST_IO": "1"})
+    tails = [len(l.split(b"\t", 1)[1]) + 2 for l in host.split(b"\n")[0::4] if b"\t" in l]
+    assert sum(t > 64 for t in tails) > 1000 and max(tails) > 300
+    assert dev == host, first_diff(dev, host)
+    want = canon_fastq(run_ref_raw(d, fa + ".index", p + "_1.fq", p + "_2.fq", "cp_r", 101, "soap4-nt2.ini", flags))
+    got = canon_fastq(dev)
+    assert got == want, first_diff(got, want)
