@@ -16,9 +16,9 @@
 //                            SeedPool.cpp:267-322; DV-DPfunctions.cpp:841-920
 //   BAM output (-b)          bam_out.h
 //
-// Two I/O paths.  Plain FASTQ files with -F / -P (no -b, no -lsam): the driver only stages each batch's bytes in page-locked memory
+// Two I/O paths.  Plain FASTQ files with -F / -P (no -b): the driver only stages each batch's bytes in page-locked memory
 // (stage_file / locate_records) and writes the finished text; records are indexed and packed, and the output text is composed, by
-// kernels (mp_fastq_upload, mp_format_fastq; csrc/mp_fastq.cu).  Everything else -- .gz, pipes, BAM, -lsam, text that is not strict
+// kernels (mp_fastq_upload, mp_format_fastq; csrc/mp_fastq.cu; with -lsam host threads rewrite that text).  Everything else -- .gz, pipes, BAM, text that is not strict
 // four-line FASTQ -- goes through the host parser (SeqReader, load_batch) and formatter (header_line, output_pair, output_unpaired)
 // below, which are also what MP_HOST_IO=1 forces and what the device path is tested against.
 #include <stdint.h>
@@ -991,10 +991,10 @@ static void output_unpaired(OutCtx &o, std::string &fq, uint32_t r1, std::vector
 // (:136, 162, 208, 305), which re-parses every record; here a formatted chunk (whole pairs, mate 1 then mate 2) is rewritten into the
 // lines fastq2lsam prints (cc/fastq2lsam.cpp:28-77: name, 64/128/0, score, seq, qual | * *, "score,acc" list | *, [IGNORE]) before it
 // leaves the process.  Records pair up by adjacent equal names after the /<digit> trim, as in fastq2lsam's main loop (:95-108).
-static void fastq_chunk_to_lsam(const std::string &fq, bool outputSeq, std::string &out)
+static void fastq_chunk_to_lsam(const char *fqData, size_t fqSize, bool outputSeq, std::string &out)
 {
     struct Rec { const char *name; size_t nameLen; const char *comm; size_t commLen; const char *seq; size_t seqLen; const char *qual; size_t qualLen; };
-    out.clear(); out.reserve(fq.size());
+    out.clear(); out.reserve(fqSize);
     auto print = [&](const Rec &r, int whichEnd) {
         out.append(r.name, r.nameLen); out += '\t';
         out += whichEnd == 1 ? "64" : whichEnd == 2 ? "128" : "0"; out += '\t';
@@ -1026,7 +1026,7 @@ static void fastq_chunk_to_lsam(const std::string &fq, bool outputSeq, std::stri
         out += '\n';
     };
     Rec last{}; bool hasLast = false;
-    const char *p = fq.data(), *end = p + fq.size();
+    const char *p = fqData, *end = p + fqSize;
     while (p < end) {
         const char *l[4], *e[4];
         bool ok = true;
@@ -1107,7 +1107,7 @@ int main(int argc, char **argv)
         std::string data; char tmp[65536]; size_t n;
         while ((n = fread(tmp, 1, sizeof tmp, in)) > 0) data.append(tmp, n);
         fclose(in);
-        std::string out; fastq_chunk_to_lsam(data, atoi(argv[3]) != 0, out);
+        std::string out; fastq_chunk_to_lsam(data.data(), data.size(), atoi(argv[3]) != 0, out);
         fwrite(out.data(), 1, out.size(), stdout);
         return 0;
     }
@@ -1189,9 +1189,9 @@ int main(int argc, char **argv)
     unsigned stageThreads = (unsigned)std::min(4, std::max(1, opt.numCpuThreads));
     if (const char *e = getenv("MP_STAGE_THREADS")) { const int v = atoi(e); if (v >= 1 && v <= 64) stageThreads = (unsigned)v; }
     // ---- FASTQ ingest and annotated-FASTQ egress on the device (mp_fastq_upload / mp_format_fastq): plain FASTQ files in, -F / -P text
-    //      out.  Everything else (.gz, pipes, -b, -lsam, anything but strict four-line records) takes the host parser / formatter below.
+    //      out.  Everything else (.gz, pipes, -b, anything but strict four-line records) takes the host parser / formatter below.
     //      MP_HOST_IO=1 forces the host loops (tests compare the two). ----
-    bool deviceIO = opt.megapathMode != 0 && !opt.outputBAM && opt.lsam < 0 && r1.mapped && r2.mapped && !getenv("MP_HOST_IO");
+    bool deviceIO = opt.megapathMode != 0 && !opt.outputBAM && r1.mapped && r2.mapped && !getenv("MP_HOST_IO");
     struct RawBatch { char *pin = nullptr; size_t pinCap = 0, bytes1 = 0, off2 = 0, bytes2 = 0; uint32_t nReads = 0; };
     std::mutex pinMu; std::vector<std::pair<char *, size_t>> pinPool;
     auto pin_take = [&](size_t need) -> std::pair<char *, size_t> {
@@ -1510,7 +1510,41 @@ int main(int argc, char **argv)
                     }
                     if (!rc) rc = mp_format_fetch(gpu, j->raw.pin, ob);
                     if (timing) fprintf(stderr, "[timing]  batch %llu: format (device) %.3f fetch %.3f s (%.0f MB)\n", (unsigned long long)j->seq, tf1 - tf0, now_s() - tf1, ob / 1e6);
-                    if (rc) { j->log += std::string(mp_last_error()) + "\n"; j->failed = true; } else j->outBytes = ob;
+                    if (rc) { j->log += std::string(mp_last_error()) + "\n"; j->failed = true; }
+                    else if (opt.lsam < 0) j->outBytes = ob;
+                    else {
+                        // -lsam: the device-made text is cut at pair boundaries (every eighth line, found by counting newlines in blocks) and
+                        // each piece rewritten into fastq2lsam's lines by one of the -T threads
+                        const char *txt = j->raw.pin;
+                        const size_t B = (size_t)1 << 18, nBlocks = ((size_t)ob + B - 1) / B;
+                        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+                        const unsigned nThr = std::min<unsigned>((unsigned)std::max(1, opt.numCpuThreads), std::max<unsigned>(1u, hw / (unsigned)contexts.size()));
+                        std::vector<uint32_t> cnt(nBlocks);
+                        auto par = [&](size_t n, const std::function<void(size_t)> &fn) {
+                            const unsigned T = (unsigned)std::min<size_t>(nThr, std::max<size_t>(n, 1));
+                            std::vector<std::thread> th;
+                            for (unsigned t = 1; t < T; ++t) th.emplace_back([&, t] { for (size_t k = t; k < n; k += T) fn(k); });
+                            for (size_t k = 0; k < n; k += T) fn(k);
+                            for (std::thread &x : th) x.join();
+                        };
+                        par(nBlocks, [&](size_t k) { cnt[k] = (uint32_t)count_newlines(txt + k * B, std::min(B, (size_t)ob - k * B)); });
+                        std::vector<uint64_t> pre(nBlocks + 1, 0);
+                        for (size_t k = 0; k < nBlocks; ++k) pre[k + 1] = pre[k] + cnt[k];
+                        const uint64_t nPairsOut = pre[nBlocks] / 8;
+                        const unsigned nc = (unsigned)std::min<uint64_t>(nThr, std::max<uint64_t>(1, nPairsOut / 4096));
+                        std::vector<size_t> cut(nc + 1, (size_t)ob);
+                        cut[0] = 0;
+                        for (unsigned c = 1; c < nc; ++c) {
+                            const uint64_t L = 8 * (nPairsOut * c / nc);            // the piece starts behind the L-th newline
+                            if (L == 0) { cut[c] = 0; continue; }
+                            const size_t k = (size_t)(std::lower_bound(pre.begin(), pre.end(), L) - pre.begin()) - 1;
+                            const char *q = txt + k * B;
+                            for (uint64_t need = L - pre[k]; need; --need) q = (const char *)memchr(q, '\n', (size_t)(txt + ob - q)) + 1;
+                            cut[c] = (size_t)(q - txt);
+                        }
+                        j->fqParts.assign(nc, std::string());
+                        par(nc, [&](size_t c) { if (cut[c + 1] > cut[c]) fastq_chunk_to_lsam(txt + cut[c], cut[c + 1] - cut[c], opt.lsam != 0, j->fqParts[c]); });
+                    }
                 } else if (opt.megapathMode || opt.outputBAM) {
                     ReadBatch &b = *j->b;
                     oc.b = &b;
@@ -1533,7 +1567,7 @@ int main(int argc, char **argv)
                             occ.bam = opt.outputBAM ? &capw : nullptr;
                             chunks[c].fq.reserve((size_t)(cut[c + 1] - cut[c]) * (size_t)(4 * maxLen + 160));
                             body(occ, chunks[c].fq, cut[c], cut[c + 1]);
-                            if (opt.lsam >= 0 && !chunks[c].fq.empty()) { std::string ls; fastq_chunk_to_lsam(chunks[c].fq, opt.lsam != 0, ls); chunks[c].fq.swap(ls); }
+                            if (opt.lsam >= 0 && !chunks[c].fq.empty()) { std::string ls; fastq_chunk_to_lsam(chunks[c].fq.data(), chunks[c].fq.size(), opt.lsam != 0, ls); chunks[c].fq.swap(ls); }
                             if (!chunks[c].bam.empty()) { BgzfWriter::compress_all(chunks[c].bam.data(), chunks[c].bam.size(), chunks[c].bamz); std::vector<uint8_t>().swap(chunks[c].bam); }
                         };
                         std::vector<std::thread> ths;

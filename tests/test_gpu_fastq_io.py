@@ -257,3 +257,18 @@ def test_device_io_long_score_lists(workdir):
     want = canon_fastq(run_ref_raw(d, fa + ".index", p + "_1.fq", p + "_2.fq", "cp_r", 101, "soap4-nt2.ini", flags))
     got = canon_fastq(dev)
     assert got == want, first_diff(got, want)
+
+
+@needs_ref
+@pytest.mark.parametrize("output_seq", ["0", "1"])
+def test_device_io_lsam_mode(workdir, small_ref, output_seq):
+    """-lsam: the device-made text, cut at pair boundaries and rewritten into fastq2lsam's lines by host threads, is byte-identical to
+    the all-host path, over several batches and with more threads than pieces."""
+    fq1, fq2 = make_reads(workdir, small_ref, "dio_lsam", 9000, 100, seed=8, model="divergent", one_random=0.10, unalignable=0.05)
+    flags = ["-F", "-nc", "-top", "95", "-lsam", output_seq]
+    for env in ({}, {"MP_BATCH_READS": "4096"}):
+        dev, err = run_driver(workdir, small_ref["prefix"], fq1, fq2, "dio_ls_d", 101, "soap4-nt2.ini", flags, env, threads=5)
+        assert "formatting on the device" in err
+        host, _ = run_driver(workdir, small_ref["prefix"], fq1, fq2, "dio_ls_h", 101, "soap4-nt2.ini", flags, dict(env, MP_HOST_IO="1"), threads=5)
+        assert dev.count(b"\n") == 18000 and dev.count(b"\t64\t") == 9000
+        assert dev == host, first_diff(dev, host)
