@@ -1464,6 +1464,8 @@ int main(int argc, char **argv)
                 if (rcUp == MP_ERR_FORMAT) {
                     // the input stops being strict four-line FASTQ in mid-file: this batch goes through the host parser, from the staged
                     // bytes.  Its records must be the ones the newline count promised, else the batch boundaries are not the reference's.
+                    fprintf(stderr, "[Main] batch %llu is not strict four-line FASTQ: host parser and formatter for this batch (if the run stops here, the records do not "
+                                    "lie where the line count put them: rerun with MP_HOST_IO=1)\n", (unsigned long long)j->seq);
                     SeqReader m1, m2;
                     m1.base = j->raw.pin; m1.end = j->raw.bytes1; m1.eof = true; m1.mapped = true;
                     m2.base = j->raw.pin + j->raw.off2; m2.end = j->raw.bytes2; m2.eof = true; m2.mapped = true;

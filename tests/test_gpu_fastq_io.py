@@ -272,3 +272,31 @@ def test_device_io_lsam_mode(workdir, small_ref, output_seq):
         host, _ = run_driver(workdir, small_ref["prefix"], fq1, fq2, "dio_ls_h", 101, "soap4-nt2.ini", flags, dict(env, MP_HOST_IO="1"), threads=5)
         assert dev.count(b"\n") == 18000 and dev.count(b"\t64\t") == 9000
         assert dev == host, first_diff(dev, host)
+
+
+@needs_ref
+def test_device_io_mid_file_fallback(workdir, small_ref):
+    """A file that stops being strict four-line FASTQ after the first batch: a CR inside a later batch sends that batch (only) through
+    the host parser and formatter -- same stream as the all-host run; a folded record, which moves the batch boundaries the newline
+    count promised, stops the run with a message instead of printing batches the reference would not have formed."""
+    fq1, fq2 = make_reads(workdir, small_ref, "dio_mid", 3000, 100, seed=23, model="divergent", one_random=0.10, unalignable=0.05)
+    env = {"MP_BATCH_READS": "1024"}
+    a = open(fq1, "rb").read().split(b"\n")
+    cr = list(a)
+    cr[4 * 2000 + 1] += b"\r"                          # bases line of record 2000 (fourth batch of 512 pairs)
+    cr[4 * 2000 + 3] += b"\r"
+    p_cr = os.path.join(workdir, "dio_mid_cr_1.fq")
+    open(p_cr, "wb").write(b"\n".join(cr))
+    want, _ = run_driver(workdir, small_ref["prefix"], p_cr, fq2, "dio_mid_h", 101, "soap4.ini", ["-F", "-nc"], dict(env, MP_HOST_IO="1"))
+    got, err = run_driver(workdir, small_ref["prefix"], p_cr, fq2, "dio_mid_d", 101, "soap4.ini", ["-F", "-nc"], env)
+    assert "formatting on the device" in err
+    assert got == want, first_diff(got, want)
+    fold = list(a)
+    s = fold[4 * 2000 + 1]
+    fold[4 * 2000 + 1] = s[:50] + b"\n" + s[50:]       # one record of five lines: every later record boundary moves
+    p_fold = os.path.join(workdir, "dio_mid_fold_1.fq")
+    open(p_fold, "wb").write(b"\n".join(fold))
+    exe = os.path.join(ROOT, "megapath_b200", "bin", "soap4")
+    p = subprocess.run([exe, "pair", small_ref["prefix"], p_fold, fq2, "-o", os.path.join(workdir, "dio_mid_f"), "-C", os.path.join(ROOT, "megapath_b200", "ini", "soap4.ini"),
+                        "-L", "101", "-T", "3", "-u", "750", "-F", "-nc"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300, env=dict(os.environ, **env))
+    assert p.returncode != 0 and b"MP_HOST_IO=1" in p.stderr
