@@ -49,6 +49,19 @@ if os.environ.get("MP_THR_NCU"):
                        stdout=fo, stderr=subprocess.DEVNULL, timeout=900, env=dict(os.environ, MP_CONTEXTS_PER_GPU="1"))
     print(open(out).read()[-3000:])
     sys.exit(0)
+if os.environ.get("MP_THR_LSAM"):
+    # -lsam (the fused fastq2lsam consumer) with stdout in a regular file: the text a consumer has to read shrinks, so the page-cache
+    # write of the annotated FASTQ no longer bounds the loop
+    for mode in ("0", "1"):
+        sink = os.path.join(d, "our.lsam")
+        with open(sink, "wb") as fo:
+            p = subprocess.run([exe, "pair", prefix, fq1, fq2, "-o", os.path.join(d, "ouro"), "-C", ini, "-L", "151", "-T", "16", "-u", "750", "-F", "-nc", "-lsam", mode],
+                               stdout=fo, stderr=subprocess.PIPE, timeout=900, env=dict(os.environ, MP_DRIVER_TIMING="1"))
+        lines = p.stderr.decode().splitlines()
+        loop = [float(l.split(":")[1].split()[0]) for l in lines if "Overall alignment time" in l][0]
+        print("-lsam %s to a file (%d MB): loop %.3f s = %.2f M pairs/s; %s" % (mode, os.path.getsize(sink) >> 20, loop, total / loop / 1e6,
+                                                                                 [l for l in lines if "formatting on the" in l]), flush=True)
+    sys.exit(0)
 if os.environ.get("MP_THR_SWEEP"):
     for ctxs, st, extra in ((3, 16, {}), (3, 8, {}), (3, 4, {}), (3, 4, {}), (3, 2, {}), (4, 4, {}), (2, 4, {}), (3, 8, {})):
         with open("/dev/null", "wb") as fo:
