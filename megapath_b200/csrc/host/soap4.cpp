@@ -991,39 +991,69 @@ static void output_unpaired(OutCtx &o, std::string &fq, uint32_t r1, std::vector
 // (:136, 162, 208, 305), which re-parses every record; here a formatted chunk (whole pairs, mate 1 then mate 2) is rewritten into the
 // lines fastq2lsam prints (cc/fastq2lsam.cpp:28-77: name, 64/128/0, score, seq, qual | * *, "score,acc" list | *, [IGNORE]) before it
 // leaves the process.  Records pair up by adjacent equal names after the /<digit> trim, as in fastq2lsam's main loop (:95-108).
+// atoi of the characters [s, e) (glibc: (int) strtol, which saturates at the long limits)
+static int atoi_range(const char *s, const char *e)
+{
+    while (s < e && isspace((unsigned char)*s)) ++s;
+    bool neg = false;
+    if (s < e && (*s == '-' || *s == '+')) { neg = *s == '-'; ++s; }
+    const unsigned long long lim = neg ? 9223372036854775808ull : 9223372036854775807ull;
+    unsigned long long v = 0; bool over = false;
+    for (; s < e && *s >= '0' && *s <= '9'; ++s) {
+        const unsigned d = (unsigned)(*s - '0');
+        if (over || v > (lim - d) / 10) { over = true; continue; }
+        v = v * 10 + d;
+    }
+    if (over) v = lim;
+    return (int)(neg ? (long long)(0ull - v) : (long long)v);
+}
 static void fastq_chunk_to_lsam(const char *fqData, size_t fqSize, bool outputSeq, std::string &out)
 {
     struct Rec { const char *name; size_t nameLen; const char *comm; size_t commLen; const char *seq; size_t seqLen; const char *qual; size_t qualLen; };
-    out.clear(); out.reserve(fqSize);
+    out.clear(); out.reserve(fqSize / (outputSeq ? 1 : 4) + 4096);
+    // one line through a raw pointer into space reserved for it (every "score,acc" item repeats the score: the list of a usual
+    // comment is less than twice the comment, anything longer grows the space item by item)
     auto print = [&](const Rec &r, int whichEnd) {
-        out.append(r.name, r.nameLen); out += '\t';
-        out += whichEnd == 1 ? "64" : whichEnd == 2 ? "128" : "0"; out += '\t';
+        size_t cap = r.nameLen + 48 + (outputSeq ? r.seqLen + r.qualLen + 2 : 4) + 2 * r.commLen;
+        const size_t at = out.size();
+        out.resize(at + cap);
+        char *w0 = &out[at], *w = w0;
+        auto ensure = [&](size_t extra) {
+            const size_t used = (size_t)(w - w0);
+            if (used + extra + 16 > cap) { cap = (used + extra + 16) * 2; out.resize(at + cap); w0 = &out[at]; w = w0 + used; }
+        };
+        memcpy(w, r.name, r.nameLen); w += r.nameLen;
+        *w++ = '\t';
+        if (whichEnd == 1) { *w++ = '6'; *w++ = '4'; } else if (whichEnd == 2) { *w++ = '1'; *w++ = '2'; *w++ = '8'; } else *w++ = '0';
+        *w++ = '\t';
         const bool ignore = r.commLen == 6 && !memcmp(r.comm, "IGNORE", 6);
-        const int score = ignore ? -1 : (r.commLen > 6 ? atoi(std::string(r.comm + 6, r.commLen - 6).c_str()) : 0);
-        out += std::to_string(score); out += '\t';
-        if (outputSeq) { out.append(r.seq, r.seqLen); out += '\t'; out.append(r.qual, r.qualLen); out += '\t'; }
-        else out += "*\t*\t";
-        if (score <= 0) out += '*';
+        const int score = ignore ? -1 : (r.commLen > 6 ? atoi_range(r.comm + 6, r.comm + r.commLen) : 0);
+        w = put_int(w, score); *w++ = '\t';
+        if (outputSeq) { memcpy(w, r.seq, r.seqLen); w += r.seqLen; *w++ = '\t'; memcpy(w, r.qual, r.qualLen); w += r.qualLen; *w++ = '\t'; }
+        else { memcpy(w, "*\t*\t", 4); w += 4; }
+        if (score <= 0) *w++ = '*';
         else {
             // misc.h splitBy: fields between delimiters, a trailing empty field is dropped.  Every field after the first (the
             // "SCORE:n" one) is "score,acc[,acc...]" and prints as "score,acc" per accession, joined by ';'
             bool first = true;
-            int field = 0;
-            for (size_t i = 0, j; i < r.commLen; i = j + 1, ++field) {
-                j = i; while (j < r.commLen && r.comm[j] != ';') ++j;
-                if (field == 0) continue;
-                size_t s0e = i; while (s0e < j && r.comm[s0e] != ',') ++s0e;            // sub[0] = [i, s0e)
-                int sub = 0;
-                for (size_t a = i, e; a < j; a = e + 1, ++sub) {
-                    e = a; while (e < j && r.comm[e] != ',') ++e;
-                    if (sub == 0) continue;
-                    if (!first) out += ';'; else first = false;
-                    out.append(r.comm + i, s0e - i); out += ','; out.append(r.comm + a, e - a);
+            const char *c = r.comm, *ce = r.comm + r.commLen;
+            const char *f = (const char *)memchr(c, ';', r.commLen);                 // end of field 0
+            for (const char *i = f ? f + 1 : ce; i < ce;) {
+                const char *j = (const char *)memchr(i, ';', (size_t)(ce - i)); if (!j) j = ce;
+                const char *s0e = (const char *)memchr(i, ',', (size_t)(j - i)); if (!s0e) s0e = j;      // sub[0] = [i, s0e)
+                for (const char *a = s0e < j ? s0e + 1 : j; a < j;) {
+                    const char *e = (const char *)memchr(a, ',', (size_t)(j - a)); if (!e) e = j;
+                    ensure((size_t)(s0e - i) + (size_t)(e - a) + 2);
+                    if (!first) *w++ = ';'; else first = false;
+                    memcpy(w, i, (size_t)(s0e - i)); w += s0e - i; *w++ = ','; memcpy(w, a, (size_t)(e - a)); w += e - a;
+                    a = e + 1;
                 }
+                i = j + 1;
             }
         }
-        if (score == -1) out += "\tIGNORE";
-        out += '\n';
+        if (score == -1) { memcpy(w, "\tIGNORE", 7); w += 7; }
+        *w++ = '\n';
+        out.resize(at + (size_t)(w - w0));
     };
     Rec last{}; bool hasLast = false;
     const char *p = fqData, *end = p + fqSize;
@@ -1107,7 +1137,9 @@ int main(int argc, char **argv)
         std::string data; char tmp[65536]; size_t n;
         while ((n = fread(tmp, 1, sizeof tmp, in)) > 0) data.append(tmp, n);
         fclose(in);
+        const double tc = now_s();
         std::string out; fastq_chunk_to_lsam(data.data(), data.size(), atoi(argv[3]) != 0, out);
+        fprintf(stderr, "converted %.1f MB in %.3f s\n", data.size() / 1e6, now_s() - tc);
         fwrite(out.data(), 1, out.size(), stdout);
         return 0;
     }

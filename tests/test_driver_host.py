@@ -242,3 +242,47 @@ def test_staging_refuses_what_the_kernels_cannot_index(tmp_path, name):
     p.write_bytes(CASES[name])
     rows = _stage(p, 10, 2)
     assert rows[0][0] == -1 and rows[0][2] == -1
+
+
+@pytest.mark.parametrize("output_seq", ["1", "0"])
+def test_lsam_mode_randomized_against_reference_fastq2lsam(tmp_path, output_seq):
+    """20 000 records with generated comments -- IGNORE, zero / negative / signed scores, lists with several accessions per score, empty
+    fields, long scores with dozens of one-letter accessions (the list outgrows twice the comment), names with and without /1 /2,
+    unpaired names -- through -lsam and through the reference's own cc/fastq2lsam"""
+    ref = os.path.join(ROOT, "oracle", "_ref", "fastq2lsam")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/fastq2lsam not built")
+    rng = np.random.default_rng(int(output_seq) + 5)
+    out = []
+    for i in range(10000):
+        paired = rng.random() < 0.9
+        for m in (1, 2):
+            kind = int(rng.integers(0, 8))
+            sc = int(rng.integers(1, 400))
+            if kind == 0:
+                c = b"IGNORE"
+            elif kind == 1:
+                c = b"SCORE:0;"
+            elif kind == 2:
+                c = b"SCORE:-%d;7,x;" % sc
+            elif kind == 3:
+                c = b"SCORE: +%d;%d,acc%d;" % (sc, sc, i)
+            elif kind == 4:
+                c = b"SCORE:%d;%d,a%d,b%d,,c;;%d,z;" % (sc, sc, i, i, sc - 1)
+            elif kind == 5:
+                c = b"SCORE:%d;1234567890123,%s;" % (sc, b",".join(b"q" for _ in range(int(rng.integers(1, 60)))))
+            elif kind == 6:
+                c = b"SCORE:%d;%d,gi|%d|ref|NC_%d.1| some description, with a comma" % (sc, sc, i, i)
+            else:
+                c = b"SCORE:%d;" % sc
+            name = b"r%d" % i if paired else b"r%d_%d" % (i, m)
+            if rng.random() < 0.5:
+                name += b"/%d" % m
+            L = int(rng.integers(1, 120))
+            out.append(b"@" + name + b"\t" + c + b"\n" + b"ACGT"[m:m + 1] * L + b"\n+\n" + b"I" * L + b"\n")
+    f = tmp_path / "r.fq"
+    f.write_bytes(b"".join(out))
+    want = subprocess.run([ref, output_seq], stdin=open(f, "rb"), capture_output=True, check=True, timeout=120).stdout
+    got = subprocess.run([EXE, "__lsam", str(f), output_seq], capture_output=True, check=True, timeout=120).stdout
+    assert want.count(b"\n") == 20000 and want.count(b"\t64\t") > 8000 and want.count(b"\t0\t") > 1000
+    assert got == want
