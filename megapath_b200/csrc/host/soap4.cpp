@@ -1180,7 +1180,11 @@ int main(int argc, char **argv)
     Options opt;
     if (!parse_args(argc, argv, opt)) return 1;
     const double t0 = now_s();
-    setenv("CUDA_MODULE_LOADING", "EAGER", 0);      // every kernel is loaded with the library, not at its first launch inside the batch loop
+    {   // large inputs: every kernel is loaded with the library, not at its first launch inside the batch loop (must be set before the
+        // first CUDA call); small runs keep lazy loading, which starts the process faster
+        struct stat sb0;
+        if (stat(opt.query1.c_str(), &sb0) == 0 && sb0.st_size > (off_t)(48 << 20)) setenv("CUDA_MODULE_LOADING", "EAGER", 0);
+    }
     Ini ini;
     std::string iniPath = opt.iniFile.empty() ? std::string(argv[0]) + ".ini" : opt.iniFile;
     if (!ini.load(iniPath)) { fprintf(stderr, "Failed to open config file ... %s\n", iniPath.c_str()); return 1; }

@@ -43,10 +43,14 @@ SETS = [
 ]
 
 
+# every set as one batch; the sets with unplaced / rescued pairs and variable lengths also as several batches over the contexts
+CASES = [(s, 0) for s in SETS] + [(s, 1024) for s in SETS if s[0] in ("mixed", "var", "nt2")]
+
+
 @needs_ref
-@pytest.mark.parametrize("name,rlen,lopt,kw,ini,flags", SETS)
-@pytest.mark.parametrize("batch", [0, 1024])
-def test_device_io_is_byte_identical_to_host_io(workdir, small_ref, name, rlen, lopt, kw, ini, flags, batch):
+@pytest.mark.parametrize("case", CASES, ids=["%s-%d" % (s[0], b) for s, b in CASES])
+def test_device_io_is_byte_identical_to_host_io(workdir, small_ref, case):
+    (name, rlen, lopt, kw, ini, flags), batch = case
     """Same process, same batches: stdout of the device loops == stdout of the host loops, byte for byte (single batch and
     several batches over two contexts; the stream order -- deep-DP pairs, rescued pairs, the rest -- included)."""
     fq1, fq2 = make_reads(workdir, small_ref, "dio_" + name, 3000, rlen, seed=91, **kw)
