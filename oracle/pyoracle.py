@@ -458,3 +458,72 @@ def deep_dp(ix, reads, lens, cands, insert_low, insert_high, input_max_read_leng
         res.extend(keep)
         i = j
     return res, cells
+
+
+# ---- stdout contract: the SCORE: header of one read (test infrastructure, restated from the reference) ----
+def c_atoi(b):
+    """glibc atoi on the bytes b (taken as NUL terminated): (int) strtol(b, NULL, 10) -- blanks, one sign, digits; saturates at the
+    long limits before the cast (getMappingFromHeader calls it on whatever follows "SCORE:", BGS-IO.cpp:1353, 1361)"""
+    i, n = 0, len(b)
+    while i < n and b[i] in b" \t\n\v\f\r":
+        i += 1
+    neg = False
+    if i < n and b[i] in b"+-":
+        neg = b[i] == ord("-")
+        i += 1
+    v = 0
+    while i < n and 48 <= b[i] <= 57:
+        v = v * 10 + (b[i] - 48)
+        i += 1
+    v = -v if neg else v
+    v = max(-(1 << 63), min((1 << 63) - 1, v))
+    v &= 0xFFFFFFFF
+    return v - (1 << 32) if v >= (1 << 31) else v
+
+
+def mapping_from_header(comment, top, score_t):
+    """getMappingFromHeader (BGS-IO.cpp:1348-1371) -> (previous best score, [(score, entry bytes)]).  comment: bytes after the first
+    blank of the header, None when there is none (or with -nc).  Comments the reference cannot read (shorter than "SCORE:", an
+    unterminated last entry: it reads past the string / dereferences NULL) are not defined here either."""
+    if comment is None or comment == b"IGNORE":
+        return 0, []
+    score = c_atoi(comment[6:])
+    if score < score_t:
+        return score, []
+    if score_t < score * top:
+        score_t = score * top
+    out = []
+    p = comment.find(b";", 6)
+    while 0 <= p and p + 1 < len(comment):
+        s = p + 1
+        m = c_atoi(comment[s:])
+        p = comment.find(b";", s)
+        if p < 0:
+            break
+        if score >= score_t:
+            out.append((m, comment[s:p]))
+    return score, out
+
+
+def fastq_header(name, comment, own_best, own_hits, top):
+    """The header line pairDeepDPOutputFastqAPI / unproperlypairDPOutputFastqAPI print for one read (BGS-IO.cpp:1384-1446,
+    1966-2091): own_best = best score of this run's alignments of the read, own_hits = [(sequence id, score, sequence name)] of the
+    alignments that lie within one sequence; comment = the previous chunk's comment (None with -nc)."""
+    if comment == b"IGNORE":
+        return b"@" + name + b"\tIGNORE"
+    hits = sorted((cid, -sc, nm) for cid, sc, nm in own_hits)
+    prev, kept = mapping_from_header(comment, top, own_best * top)
+    best = max(own_best, prev)
+    out = b"@" + name + b"\tSCORE:%d;" % best
+    if best > 0:
+        last = None
+        for cid, nsc, nm in hits:
+            if cid == last:
+                continue
+            last = cid
+            if -nsc > 0 and -nsc >= best * top:
+                out += b"%d,%s;" % (-nsc, nm)
+    for m, entry in kept:
+        if m >= best * top:
+            out += entry + b";"
+    return out

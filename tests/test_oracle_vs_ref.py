@@ -234,3 +234,67 @@ def test_exact_occurrence_closed_form_equals_the_dp():
         multi += want[2] > 1
         at_start += want[1] == 0
     assert checked > 2500 and multi > 300 and at_start > 300
+
+
+# ---- the stdout contract's SCORE: header with comment chaining, pinned against the reference binary run here (CPU) ----
+def _headers(stdout_fastq):
+    """annotated FASTQ -> {(name, mate index within its pair): header line}"""
+    lines = stdout_fastq.split(b"\n")
+    recs = [lines[i] for i in range(0, len(lines) - 3, 4)]
+    out = {}
+    for k in range(0, len(recs) - 1, 2):
+        for mate in (0, 1):
+            out[(recs[k + mate][1:].split(b"\t")[0], mate)] = recs[k + mate]
+    return out
+
+
+@needs_ref
+@pytest.mark.parametrize("mode", ["-F", "-P"])
+def test_fastq_header_restatement_matches_reference_chaining(workdir, small_ref, second_ref, mode):
+    """oracle/pyoracle.fastq_header (getMappingFromHeader + the header composition of pairDeepDPOutputFastqAPI /
+    unproperlypairDPOutputFastqAPI, BGS-IO.cpp:1348-1446, 1966-2091) against the reference itself: the reference's chunk-1 header
+    WITHOUT -nc must be what the restatement makes of (its chunk-1 header WITH -nc = this run's own hits, the comment it was fed)."""
+    import os
+    from conftest import make_reads, run_ref_raw, deinterleave
+    from oracle import pyoracle as po
+
+    def edit(k, mate, comm):
+        if k % 19 == 3:
+            return b"IGNORE"
+        if k % 23 == 5 and mate == 1:
+            return b"SCORE:0;"
+        if k % 29 == 7:
+            return b"SCORE:400;400,made_up_hit;"
+        if k % 31 == 11 and mate == 0:
+            return b""
+        if k % 41 == 17:
+            return b"SCORE:  +12;12,x y z;9,low;"
+        if k % 43 == 19:
+            return b"SCORE:99999999999999999999;5,big;"
+        return comm
+    fq1, fq2 = make_reads(workdir, small_ref, "hdr", 2000, 150, seed=79, model="divergent", one_random=0.10, unalignable=0.04)
+    first = run_ref_raw(workdir, small_ref["prefix"], fq1, fq2, "hdr0", 151, "soap4-nt2.ini", ["-F", "-nc", "-top", "95"])
+    in1, in2 = deinterleave(first, os.path.join(workdir, "hdr_in"), edit)
+    own = _headers(run_ref_raw(workdir, second_ref["prefix"], in1, in2, "hdr_own", 151, "soap4-nt2.ini", [mode, "-nc", "-top", "95"]))
+    chained = _headers(run_ref_raw(workdir, second_ref["prefix"], in1, in2, "hdr_ch", 151, "soap4-nt2.ini", [mode, "-top", "95"]))
+    comments = {}
+    for mate, path in ((0, in1), (1, in2)):
+        for line in open(path, "rb").read().split(b"\n")[0::4]:
+            if line:
+                parts = line[1:].split(None, 1)
+                nm = parts[0][:-2] if parts[0][-2:] in (b"/1", b"/2") else parts[0]
+                comments[(nm, mate)] = parts[1] if len(parts) > 1 else None
+    assert len(own) == len(chained) == 4000
+    n_merged = 0
+    for key, hdr in own.items():
+        name, tail = hdr[1:].split(b"\t", 1)
+        assert tail.startswith(b"SCORE:")
+        fields = tail[6:].split(b";")[:-1]
+        own_best = int(fields[0])
+        # this run's hits as the header lists them: one per sequence, ascending sequence order (names stand in for the ids)
+        hits = [(i + 1, int(f.split(b",", 1)[0]), f.split(b",", 1)[1]) for i, f in enumerate(fields[1:])]
+        want = chained[key]
+        got = po.fastq_header(name, comments[key], own_best, hits, 0.95)
+        assert got == want, (key, comments[key], hdr, got, want)
+        n_merged += want != hdr
+    assert n_merged > 500                  # the previous comment changed the header of many reads
